@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py — headline measurement of the BPE hot paths on B200 (contract: task statement ④).
+
+One "step" = one pass of hot path (b), batch encode_as_ids, over BASELINE.json configs[1]:
+1 M synthetic 128-byte sentences, vocab 32 000 (model trained by this framework's own GPU trainer
+on synthetic text of the same distribution, outside the timed region).
+
+  value   Msent/s, whole job, inputs already resident in HBM (yttm_enc_run_device)
+  e2e     same metric through the host-buffer C-ABI call (yttm_enc_run): pinned host input,
+          H2D + kernels + D2H of ids/offsets inside the timed region
+  roofline             dominant kernel of the step (encode_words_kernel), algorithmic bytes
+                       sum(len_i + 4 n_ids_i + 16) / its CUDA-event duration
+  roofline_train_scan  the pair-count scan of hot path (a) on a packed token buffer >> L2
+                       (4T + 12U bytes per launch), the kernel BASELINE.json's 70 % target names
+  train                sizes / stage times of the GPU training run that produced the model
+  cpu_baseline         the unmodified reference (oracle/_ref prod build) encode_as_ids on the host
+
+`--impl reference` times the reference's own CPU implementation (all host threads) on the same
+workload.  N > 1 (torchrun): sentences shard by rank, no collective on the data path (weak scaling).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CACHE = os.environ.get("YTTM_BENCH_CACHE", "/tmp/yttm_b200_bench_cache")
+N_SENT, SENT_LEN, VOCAB = 1_000_000, 128, 32_000
+TRAIN_BYTES = 100_000_000
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def workload(rank, n_sent, train_bytes):
+    """(train text, sentence bytes, uint64 offsets) — cached on local disk between the two arms."""
+    from youtokentome_b200 import synth
+    os.makedirs(CACHE, exist_ok=True)
+    tp = os.path.join(CACHE, "train_%d.bin" % train_bytes)
+    sp = os.path.join(CACHE, "sent_%d_%d_r%d" % (n_sent, SENT_LEN, rank))
+    fz = None
+    if os.path.exists(tp):
+        text = open(tp, "rb").read()
+    else:
+        fz = synth.FastZipf(n_words=200_000, s=1.07, seed=1234)
+        text = fz.text(train_bytes)
+        if rank == 0:
+            with open(tp + ".tmp%d" % os.getpid(), "wb") as f:
+                f.write(text)
+            os.replace(tp + ".tmp%d" % os.getpid(), tp)
+    if os.path.exists(sp + ".bin") and os.path.exists(sp + ".npy"):
+        buf = open(sp + ".bin", "rb").read()
+        offs = np.load(sp + ".npy")
+    else:
+        fz = fz or synth.FastZipf(n_words=200_000, s=1.07, seed=1234)
+        buf, offs = fz.packed_sentences(n_sent, SENT_LEN, seed=4321 + rank)
+        with open(sp + ".bin.tmp", "wb") as f:
+            f.write(buf)
+        os.replace(sp + ".bin.tmp", sp + ".bin")
+        np.save(sp + ".npy", offs)
+    return text, buf, offs
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k] == "Active" for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_encode(model, buf, offs, cores, max_sent):
+    """The unmodified reference (prod build) encode_as_ids with `cores` threads on a bounded sample."""
+    import _bind
+    kind = "reference" if _bind.have_reference("prod") else "port"
+    n = min(len(offs) - 1, max_sent)
+    o = np.ascontiguousarray(offs[:n + 1])
+    if kind == "reference":
+        enc = _bind.Reference("prod").encoder(model, n_threads=cores)
+        ids, _ = enc.encode_packed(buf, o)
+        sec = enc.last_seconds
+    else:
+        enc = _bind.Oracle().encoder(model)
+        ids, _ = enc.encode_packed(buf, o)
+        sec, cores = enc.last_seconds, 1
+    return {"value": n / sec / 1e6, "unit": "Msent/s", "cores": cores, "kind": kind,
+            "sample": "%d of the %d sentences (%.0f MB), encode_as_ids only, %.2f s" %
+                      (n, len(offs) - 1, float(o[-1]) / 1e6, sec)}, ids
+
+
+def reference_arm(args, rank, world):
+    """--impl reference: the reference's CPU encode_as_ids on the same workload, all host threads."""
+    if rank != 0:
+        return
+    import _bind
+    _bind.build_checkers()
+    cores = os.cpu_count() or 1
+    text, buf, offs = workload(0, N_SENT, TRAIN_BYTES)
+    model = os.path.join(CACHE, "model_ref_%d.yttm" % VOCAB)
+    if not os.path.exists(model):
+        # the model must equal the GPU arm's: train it with the reference itself (DETERMINISTIC_QUEUE
+        # build = the tie-break order both implementations are pinned to)
+        kind = "det" if _bind.have_reference("det") else None
+        if kind:
+            _bind.Reference("det").train(text, model, VOCAB, 1.0, n_threads=min(8, cores))
+        else:
+            _bind.Oracle().train(text, model, VOCAB, 1.0)
+    times = []
+    sample = min(N_SENT, max(50_000, 40_000 * cores))
+    base = None
+    for it in range(args.warmup + args.steps):
+        base, _ = cpu_reference_encode(model, buf, offs, cores, sample)
+        if it >= args.warmup:
+            times.append(sample / (base["value"] * 1e6))
+    sec = sum(times) / len(times)
+    val = sample / sec / 1e6
+    base["value"] = val
+    out = {"impl": "reference", "metric": "encode throughput, 1M x 128 B synthetic sentences, vocab 32k",
+           "value": val, "unit": "Msent/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "u8/u32", "data": "synthetic",
+           "config": {"workload": "configs[1]: encode 1M synthetic 128-byte sentences, vocab 32k",
+                      "step": "reference encode_as_ids on %d sentences, %d threads" % (sample, cores)},
+           "cpu_baseline": base,
+           "e2e": {"value": val, "unit": "Msent/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scan-tokens", type=int, default=256 * 1024 * 1024)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from youtokentome_b200 import _lib
+    from _gpu import gpu_train
+    torch.cuda.set_device(local)
+    os.environ["YTTM_DEVICE"] = str(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    L = _lib.lib()
+    hbm_peak, peak_src = peaks()
+
+    text, buf, offs = workload(rank, N_SENT, TRAIN_BYTES)
+    n_sent, n_bytes = len(offs) - 1, int(offs[-1])
+
+    # ---- model: this framework's GPU trainer (hot path a), outside the timed region
+    model = os.path.join(CACHE, "model_gpu_%d_r%d.yttm" % (VOCAB, rank))
+    t0 = time.perf_counter()
+    gpu_train(text, VOCAB, 1.0, model=model)
+    train_wall = time.perf_counter() - t0
+    rep = (C.c_double * 16)()
+    L.yttm_api_train_report(rep, 16)
+    names = ["n_bytes", "data_len", "n_words", "n_unique", "n_tokens", "n_pairs", "n_merges", "read_s", "h2d_ms",
+             "char_hist_ms", "word_count_ms", "tokenise_ms", "pair_hist_ms", "merge_loop_ms", "total_s", "launches"]
+    train = dict(zip(names, [float(x) for x in rep]))
+    train["wall_s"] = train_wall
+    train["GBps_e2e"] = len(text) / train_wall / 1e9
+    train["us_per_merge"] = train["merge_loop_ms"] * 1e3 / max(train["n_merges"], 1)
+
+    # ---- encoder handle + device-resident inputs
+    h = L.yttm_api_open(model.encode(), 1)
+    assert h, L.yttm_api_last_error(None)
+    ctx, enc = L.yttm_api_device_context(h), L.yttm_api_device_encoder(h)
+    host_bytes = torch.frombuffer(bytearray(buf), dtype=torch.uint8).pin_memory()
+    host_offs = torch.from_numpy(offs.astype(np.int64)).pin_memory()
+    d_bytes, d_offs = host_bytes.cuda(), host_offs.cuda()
+    out_cap = n_bytes + 3 * n_sent + 16
+    host_ids = torch.empty(out_cap, dtype=torch.int32).pin_memory()
+    host_oo = torch.empty(n_sent + 1, dtype=torch.int64).pin_memory()
+
+    def step_device():
+        out_n = C.c_uint64(0)
+        p1, p2 = C.c_void_p(), C.c_void_p()
+        rc = L.yttm_enc_run_device(enc, d_bytes.data_ptr(), d_offs.data_ptr(), n_bytes, n_sent, 0, 0, 0, 0.0, 0, 0,
+                                   C.byref(p1), C.byref(p2), C.byref(out_n))
+        assert rc == 0, L.yttm_last_error(ctx)
+        return out_n.value
+
+    def step_host():
+        out_n = C.c_uint64(0)
+        rc = L.yttm_enc_run(enc, host_bytes.data_ptr(), host_offs.data_ptr(), n_sent, 0, 0, 0, 0.0, 0, 0,
+                            host_ids.data_ptr(), out_cap, host_oo.data_ptr(), C.byref(out_n))
+        assert rc == 0, L.yttm_last_error(ctx)
+        return out_n.value
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            n_ids = fn()
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        l0 = L.yttm_launch_count(ctx)
+        kern = {"enc_find": 0.0, "enc_words": 0.0, "enc_gather": 0.0, "enc_scan": 0.0}
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            n_ids = fn()
+            for k in kern:
+                kern[k] += L.yttm_stage_ms(ctx, k.encode())
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - t0
+        clocks = sampler.stop() if sampler else None
+        launches = L.yttm_launch_count(ctx) - l0
+        if world > 1:
+            t = torch.tensor([sec], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        return sec, n_ids, {k: v / steps for k, v in kern.items()}, launches, clocks
+
+    sec_d, n_ids, kern, launches, clocks = timed(step_device, args.steps, args.warmup)
+    sec_h, n_ids_h, _, _, _ = timed(step_host, args.steps, args.warmup)
+    assert n_ids == n_ids_h
+
+    value = world * n_sent * args.steps / sec_d / 1e6
+    e2e = world * n_sent * args.steps / sec_h / 1e6
+    algo = n_bytes + 4 * n_ids + 16 * n_sent
+    dom = max(kern, key=lambda k: kern[k])
+    ach = algo / (kern[dom] * 1e-3) / 1e9 if kern[dom] > 0 else None
+    roofline = {"bound": "hbm", "kernel": {"enc_words": "encode_words_kernel", "enc_find": "find_words_kernel",
+                                           "enc_gather": "gather_ids_kernel", "enc_scan": "scan"}[dom],
+                "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak if ach else None,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
+                "kernel_ms": kern}
+
+    # ---- hot path (a) pair-count scan on a token buffer >> L2 (rank 0 only)
+    scan = None
+    if rank == 0 and args.scan_tokens > 0:
+        c2 = C.c_void_p()
+        assert L.yttm_ctx_create(local, C.byref(c2)) == 0
+        wl = 8
+        rc = L.yttm_train_synth_words(c2, args.scan_tokens // wl, wl, 2000, 7)
+        assert rc == 0, L.yttm_last_error(c2)
+        ms, ab = C.c_double(0), C.c_uint64(0)
+        ts = []
+        for i in range(3 + 5):
+            assert L.yttm_train_scan_once(c2, C.byref(ms), C.byref(ab)) == 0
+            if i >= 3:
+                ts.append(ms.value)
+        t = sum(ts) / len(ts)
+        a = ab.value / (t * 1e-3) / 1e9
+        scan = {"bound": "hbm", "kernel": "pair_hist_kernel", "achieved": a, "peak": hbm_peak, "unit": "GB/s",
+                "frac": a / hbm_peak, "traffic": None, "ms": t, "algorithmic_bytes_per_launch": ab.value,
+                "tokens": args.scan_tokens, "words": args.scan_tokens // wl, "peak_source": peak_src}
+        L.yttm_ctx_destroy(c2)
+
+    cpu = None
+    if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
+        import _bind
+        cores = os.cpu_count() or 1
+        cpu, ref_ids = cpu_reference_encode(model, buf, offs, cores, min(n_sent, max(50_000, 40_000 * cores)))
+        # parity spot check of the timed configuration (not timed): GPU ids == reference ids
+        step_host()
+        k = len(ref_ids)
+        assert np.array_equal(host_ids[:k].numpy(), ref_ids), "bench: GPU ids differ from the reference"
+        cpu["ids_equal_on_sample"] = True
+
+    if rank == 0:
+        out = {"metric": "encode throughput, 1M x 128 B synthetic sentences, vocab 32k", "value": value,
+               "unit": "Msent/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": sec_d / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "u8/u32", "data": "synthetic",
+               "config": {"workload": "configs[1]: encode 1M synthetic 128-byte sentences, vocab 32k, per GPU",
+                          "sentences_per_gpu": n_sent, "bytes_per_gpu": n_bytes, "ids_per_gpu": n_ids,
+                          "l2": "inputs + slot buffers (%.0f MB) exceed the 126 MB L2" % ((5 * n_bytes) / 1e6),
+                          "parallelism": "sentences sharded by rank, no collective"},
+               "e2e": {"value": e2e, "unit": "Msent/s", "h2d_bytes_per_step": n_bytes + 8 * (n_sent + 1),
+                       "d2h_bytes_per_step": 4 * n_ids + 8 * (n_sent + 1), "ms_per_step": sec_h / args.steps * 1e3},
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+               "roofline_train_scan": scan, "train": train, "cpu_baseline": cpu}
+        print(json.dumps(out))
+    L.yttm_api_close(h)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,60 @@
+/* yttm_b200_api.h — flat C entry points over the host C++ surface (bpe_b200.h), bound by the
+ * Python package with ctypes.  They replace the reference's Cython class
+ * (youtokentome/cpp/yttm.pyx:52-181): same operations, same error texts (returned through
+ * yttm_api_last_error instead of a C++ Status).  `handle` is an opened model.
+ */
+#ifndef YTTM_B200_API_H
+#define YTTM_B200_API_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char *yttm_api_last_error(void *handle); /* handle may be NULL: thread-local error */
+
+/* yttm.pyx:64-85 BPE.train -> train_bpe (bpe.h:19) */
+int yttm_api_train(const char *data_path, const char *model_path, int vocab_size, double coverage, int n_threads,
+                   int pad_id, int unk_id, int bos_id, int eos_id);
+/* learn_bpe_from_string (bpe.cpp:859) on an in-memory corpus; model_path may be "" */
+int yttm_api_train_memory(const char *text, uint64_t n, const char *model_path, int vocab_size, double coverage,
+                          int pad_id, int unk_id, int bos_id, int eos_id);
+/* sizes and stage times of the last training on this thread (see TrainReport); returns #values */
+int yttm_api_train_report(double *out, int n);
+
+/* yttm.pyx:58-62 BPE.__init__ -> BaseEncoder(model_path, n_threads, &status) */
+void *yttm_api_open(const char *model_path, int n_threads);
+void yttm_api_close(void *handle);
+int yttm_api_vocab_size(void *handle);
+void yttm_api_set_dropout_seed(void *handle, uint64_t seed);
+
+/* yttm.pyx:87-107 encode(output_type='id'): sentence i = bytes[offsets[i], offsets[i+1]) */
+int yttm_api_encode_ids(void *handle, const char *bytes, const uint64_t *offsets, uint64_t n_sent, int bos, int eos,
+                        int reverse, double dropout, uint64_t *total_ids);
+void yttm_api_result_ids(void *handle, int32_t *ids, uint64_t *offsets /* n_sent + 1 */);
+
+/* yttm.pyx:108-124 encode(output_type='subword'): pieces joined by 0x01, sentences end with '\n' */
+int64_t yttm_api_encode_subwords(void *handle, const char *bytes, const uint64_t *offsets, uint64_t n_sent, int bos,
+                                 int eos, int reverse, double dropout);
+void yttm_api_result_text(void *handle, char *out);
+
+/* yttm.pyx:136-158 decode: one '\n'-terminated line per sentence */
+int64_t yttm_api_decode(void *handle, const int32_t *ids, const uint64_t *offsets, uint64_t n_sent,
+                        const int32_t *ignore, uint64_t n_ignore);
+int64_t yttm_api_id_to_subword(void *handle, int id);
+int yttm_api_subword_to_id(void *handle, const char *subword);
+int64_t yttm_api_vocab(void *handle); /* pieces joined by 0x01 */
+
+int yttm_api_encode_cli(void *handle, const char *output_type, int stream, int bos, int eos, int reverse,
+                        double dropout);
+int yttm_api_decode_cli(void *handle, const int32_t *ignore, uint64_t n_ignore);
+void yttm_api_vocab_cli(void *handle, int verbose);
+
+/* raw yttm_ctx* / yttm_enc* of an opened model, for callers of yttm_b200.h */
+void *yttm_api_device_context(void *handle);
+void *yttm_api_device_encoder(void *handle);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

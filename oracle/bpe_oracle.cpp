@@ -293,27 +293,53 @@ static void encode(const Model &m, const uint8_t *s, uint64_t n, bool bos, bool 
         t.push_back(unk_next++);
       } else { t.push_back(it->second); i++; }
     }
-    uint32_t draw = 0;
-    for (;;) {
-      // candidates = adjacent pairs with a rule, visited in (rule index, position) order
-      int best = -1; uint32_t best_r = 0;
-      int64_t last_r = -1; int last_p = -1;  // dropout: last skipped candidate
-      for (;;) {
-        best = -1;
+    if (thresh == 0) {
+      for (;;) {  // minimum rule index, leftmost first
+        int best = -1; uint32_t best_r = 0;
         for (int p = 0; p + 1 < (int)t.size(); p++) {
           auto it = m.rule2id.find(key(t[p], t[p + 1]));
-          if (it == m.rule2id.end()) continue;
-          uint32_t r = it->second;
-          if ((int64_t)r < last_r || ((int64_t)r == last_r && p <= last_p)) continue;  // already skipped
-          if (best < 0 || r < best_r) { best = p; best_r = r; }
+          if (it != m.rule2id.end() && (best < 0 || it->second < best_r)) { best = p; best_r = it->second; }
         }
-        if (best < 0 || thresh == 0) break;
-        if (!drop_draw(seed, sent_index, word_off, draw++, thresh)) break;  // accepted
-        last_r = best_r; last_p = best;                                      // skipped (bpe.cpp:1440-1442)
+        if (best < 0) break;
+        t[best] = m.rules[best_r].z;
+        t.erase(t.begin() + best + 1);
       }
-      if (best < 0) break;  // nothing (left) to merge: word done (bpe.cpp:1430-1436)
-      t[best] = m.rules[best_r].z;
-      t.erase(t.begin() + best + 1);
+    } else {
+      // DropoutQueue + the caller's loop, restated directly (bpe.cpp:1417-1453, 1549-1589): a set of
+      // events (rule, node) ordered like MergeEvent2; pop() draws once per event in order, returns
+      // the first one not skipped (skipped ones stay queued), or "empty" if all were skipped;
+      // a popped event whose pair no longer matches its rule is stale and simply dropped.
+      const int nn = (int)t.size();
+      std::vector<int> nxt(nn), prv(nn);
+      std::vector<bool> dead(nn, false);
+      for (int i = 0; i < nn; i++) { nxt[i] = i + 1 < nn ? i + 1 : -1; prv[i] = i - 1; }
+      std::set<std::pair<uint32_t, int>> events;
+      auto push_if_rule = [&](int p) {
+        auto it = m.rule2id.find(key(t[p], t[nxt[p]]));
+        if (it != m.rule2id.end()) events.insert({it->second, p});
+      };
+      for (int i = 0; i + 1 < nn; i++) push_if_rule(i);
+      uint32_t draw = 0;
+      for (;;) {
+        auto acc = events.end();
+        for (auto it = events.begin(); it != events.end(); ++it)
+          if (!drop_draw(seed, sent_index, word_off, draw++, thresh)) { acc = it; break; }
+        if (acc == events.end()) break;
+        uint32_t rule = acc->first; int p1 = acc->second;
+        events.erase(acc);
+        int p2 = dead[p1] ? -1 : nxt[p1];
+        if (dead[p1] || p2 == -1 || t[p1] != m.rules[rule].x || t[p2] != m.rules[rule].y) continue;  // stale
+        int pl = prv[p1], p3 = nxt[p2];
+        dead[p2] = true;
+        t[p1] = m.rules[rule].z;
+        nxt[p1] = p3;
+        if (p3 != -1) prv[p3] = p1;
+        if (pl != -1) push_if_rule(pl);
+        if (p3 != -1) push_if_rule(p1);
+      }
+      std::vector<uint32_t> live;
+      for (int i = 0; i != -1; i = nxt[i]) live.push_back(t[i]);
+      t.swap(live);
     }
     for (uint32_t v : t) out->push_back(v >= UNK_BASE ? m.unk : (int32_t)v);
   }

@@ -1,0 +1,333 @@
+// encode.cu — hot path (b): batch encode_as_ids on one B200.
+//
+// Replaces BaseEncoder::encode_parallel / encode_sentence (youtokentome/cpp/bpe.cpp:1697-1738,
+// 1455-1632) behind yttm_enc_run* of include/yttm_b200.h.  The reference gives each CPU thread a
+// contiguous range of sentences and runs a heap-driven merge loop per word.  Here the batch is
+// one flat byte buffer in HBM and the unit of parallel work is the WORD:
+//   find_words_kernel   one warp per sentence: word starts (on raw bytes, see bpe_core.cuh) are
+//                       appended to a global work list; the sentence's output slots are cleared
+//   encode_words_kernel one thread per word: UTF-8 decode -> char ids (unknown runs collapse to
+//                       one pseudo token, bpe.cpp:1513-1533) -> min-rank merge loop, leftmost
+//                       first (MergeEvent2::operator< bpe.cpp:1475-1478), optional BPE-dropout
+//                       (DropoutQueue bpe.cpp:1417-1453 with a counter-based generator)
+//   gather_ids_kernel   one warp per sentence: ordered compaction into the packed id buffer
+// Output positions are a pure function of byte positions (a word of k bytes owns k+1 slots), so
+// no kernel depends on another block's progress.
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+
+using namespace yt;
+
+namespace {
+
+constexpr int32_t EMPTY_SLOT = -1;
+constexpr uint32_t NO_RANK = 0xffffffffu;
+
+struct RuleTab {       // (x,y) -> (rank, z); 16 B per slot, one 128-bit load per probe
+  const uint4 *slots;  // .x = x, .y = y, .z = rank, .w = z ; x == 0xffffffff => empty
+  uint32_t mask;
+};
+
+__device__ __forceinline__ uint32_t rule_rank(const RuleTab &rt, uint32_t a, uint32_t b, uint32_t *z) {
+  if ((a | b) & UNK_FLAG) return NO_RANK;
+  uint32_t h = (uint32_t)mix64(pair_key(a, b)) & rt.mask;
+  while (true) {
+    uint4 s = __ldg(rt.slots + h);
+    if (s.x == a && s.y == b) { *z = s.w; return s.z; }
+    if (s.x == 0xffffffffu) return NO_RANK;
+    h = (h + 1) & rt.mask;
+  }
+}
+
+struct EncArgs {
+  const uint8_t *bytes;      // batch bytes; sentence i = [offs[i]-offs[0], offs[i+1]-offs[0])
+  const uint64_t *offs;      // n_sent + 1
+  uint64_t n_sent;
+  int32_t *slots;            // n_bytes + 3 * n_sent
+  uint32_t *ranks;           // same size: cached pair ranks of the word being merged
+  uint32_t *aux;             // 6x that size, BPE-dropout only: linked list + stale events of the word
+  uint32_t *word_pos;        // work list: byte position of the word start (relative to the batch)
+  uint32_t *word_sent;       //            sentence index inside the batch
+  unsigned long long *n_words;
+  unsigned long long *n_ids;  // per sentence (uint64 so the generic scan applies)
+  const uint32_t *cp2id;
+  RuleTab rt;
+  uint32_t space_id;
+  int32_t unk_id, bos_id, eos_id;
+  int bos, eos, reverse;
+  uint64_t drop_thresh, seed, first_sentence;
+};
+
+// slot of the char token of batch byte p in sentence s (its word's "▁" sits one slot before the
+// word's first byte): base(s) = start(s) + 3 s ; [base] = bos, [base + 1 + rel ..] tokens,
+// [base + len + 2] = eos.
+__device__ __forceinline__ uint64_t sent_base(uint64_t start, uint64_t s) { return start + 3 * s; }
+
+__global__ void __launch_bounds__(256) find_words_kernel(EncArgs a) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint64_t o0 = a.offs[0];
+  for (uint64_t s = warp; s < a.n_sent; s += nwarps) {
+    const uint64_t lo = a.offs[s] - o0, hi = a.offs[s + 1] - o0;
+    const uint64_t base = sent_base(lo, s), len = hi - lo;
+    for (uint64_t i = lane; i < len + 3; i += 32) a.slots[base + i] = EMPTY_SLOT;
+    if (lane == 0) a.n_ids[s] = (a.bos ? 1 : 0) + (a.eos ? 1 : 0);
+    __syncwarp();
+    if (lane == 0) {
+      if (a.bos) a.slots[base] = a.bos_id;
+      if (a.eos) a.slots[base + len + 2] = a.eos_id;
+    }
+    for (uint64_t p0 = lo; p0 < hi; p0 += 32) {
+      uint64_t p = p0 + lane;
+      bool ws = p < hi && word_start_at(a.bytes, p, lo, hi);
+      unsigned m = __ballot_sync(0xffffffffu, ws);
+      if (!m) continue;
+      unsigned long long first = 0;
+      if (lane == 0) first = atomicAdd(a.n_words, (unsigned long long)__popc(m));
+      first = __shfl_sync(0xffffffffu, first, 0);
+      if (ws) {
+        unsigned long long idx = first + __popc(m & ((1u << lane) - 1));
+        a.word_pos[idx] = (uint32_t)p;
+        a.word_sent[idx] = (uint32_t)s;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) encode_words_kernel(EncArgs a, uint64_t n_words) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t o0 = a.offs[0];
+  for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+    const uint64_t p0 = a.word_pos[w], s = a.word_sent[w];
+    const uint64_t lo = a.offs[s] - o0, hi = a.offs[s + 1] - o0;
+    int32_t *t = a.slots + sent_base(lo, s) + 1 + (p0 - lo);  // k+1 private slots
+    uint32_t *r = a.ranks + sent_base(lo, s) + 1 + (p0 - lo);
+    uint32_t *aux = a.aux ? a.aux + 6 * (sent_base(lo, s) + 1 + (p0 - lo)) : nullptr;
+    uint32_t slots_owned;
+    const RuleTab rt = a.rt;
+    uint32_t n = encode_word(
+        a.bytes, p0, lo, hi, a.cp2id, a.space_id,
+        [&](uint32_t x, uint32_t y, uint32_t *z) { return rule_rank(rt, x, y, z); }, a.drop_thresh, a.seed,
+        a.first_sentence + s, t, r, aux, &slots_owned);
+    for (uint32_t i = 0; i < n; i++)
+      if ((uint32_t)t[i] & UNK_FLAG) t[i] = a.unk_id;
+    for (uint32_t i = n; i < slots_owned; i++) t[i] = EMPTY_SLOT;
+    if (n) atomicAdd(a.n_ids + s, (unsigned long long)n);
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_ids_kernel(EncArgs a, const unsigned long long *__restrict__ out_off,
+                                                         int32_t *__restrict__ out) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint64_t o0 = a.offs[0];
+  for (uint64_t s = warp; s < a.n_sent; s += nwarps) {
+    const uint64_t lo = a.offs[s] - o0, len = a.offs[s + 1] - o0 - lo;
+    const uint64_t base = sent_base(lo, s);
+    const unsigned long long ob = out_off[s], cnt = a.n_ids[s];
+    unsigned long long done = 0;
+    for (uint64_t i0 = 0; i0 < len + 3; i0 += 32) {
+      uint64_t i = i0 + lane;
+      int32_t v = i < len + 3 ? a.slots[base + i] : EMPTY_SLOT;
+      unsigned m = __ballot_sync(0xffffffffu, v != EMPTY_SLOT);
+      if (v != EMPTY_SLOT) {
+        unsigned long long k = done + __popc(m & ((1u << lane) - 1));
+        out[ob + (a.reverse ? cnt - 1 - k : k)] = v;
+      }
+      done += __popc(m);
+    }
+  }
+}
+
+}  // namespace
+
+struct yttm_enc {
+  yttm_ctx *ctx = nullptr;
+  ytc::DevBuf cp2id, rules;
+  uint32_t rule_mask = 0, space_id = 0;
+  int unk = -1, pad = -1, bos = -1, eos = -1;
+  // per-call device buffers
+  ytc::DevBuf d_bytes, d_offs, slots, ranks, aux, wpos, wsent, nids, out_off, out_ids, counter;
+};
+
+namespace {
+
+int enc_device(yttm_enc *e, const uint8_t *d_bytes, const uint64_t *d_offs, uint64_t n_bytes, uint64_t n_sent, int bos,
+               int eos, int reverse, double dropout, uint64_t seed, uint64_t first_sentence, uint64_t *out_n) {
+  yttm_ctx *c = e->ctx;
+  if (n_bytes >= 0xfffffff0ull || n_sent >= 0xfffffff0ull)
+    YT_FAIL(c, "encode batch too large: at most 2^32 bytes / sentences per call (split the batch)");
+  const uint64_t n_slots = n_bytes + 3 * n_sent;
+  YT_CUDA(c, e->slots.reserve((n_slots + 8) * 4));
+  YT_CUDA(c, e->ranks.reserve((n_slots + 8) * 4));
+  if (dropout > 0) YT_CUDA(c, e->aux.reserve((n_slots + 8) * 24));
+  const uint64_t max_words = n_bytes / 2 + n_sent + 8;
+  YT_CUDA(c, e->wpos.reserve(max_words * 4));
+  YT_CUDA(c, e->wsent.reserve(max_words * 4));
+  YT_CUDA(c, e->nids.reserve((n_sent + 1) * 8));
+  YT_CUDA(c, e->out_off.reserve((n_sent + 2) * 8));
+  YT_CUDA(c, e->counter.reserve(64));
+  YT_CUDA(c, cudaMemsetAsync(e->counter.p, 0, 64, c->stream));
+  EncArgs a;
+  a.bytes = d_bytes; a.offs = d_offs; a.n_sent = n_sent;
+  a.slots = e->slots.as<int32_t>(); a.ranks = e->ranks.as<uint32_t>();
+  a.aux = dropout > 0 ? e->aux.as<uint32_t>() : nullptr;
+  a.word_pos = e->wpos.as<uint32_t>(); a.word_sent = e->wsent.as<uint32_t>();
+  a.n_words = e->counter.as<unsigned long long>();
+  a.n_ids = e->nids.as<unsigned long long>();
+  a.cp2id = e->cp2id.as<uint32_t>();
+  a.rt.slots = e->rules.as<uint4>(); a.rt.mask = e->rule_mask;
+  a.space_id = e->space_id;
+  a.unk_id = e->unk; a.bos_id = e->bos; a.eos_id = e->eos;
+  a.bos = bos; a.eos = eos; a.reverse = reverse;
+  a.drop_thresh = dropout <= 0 ? 0 : (uint64_t)(dropout * 4294967296.0);
+  a.seed = seed; a.first_sentence = first_sentence;
+  *out_n = 0;
+  auto *d_total = e->counter.as<unsigned long long>() + 1;
+  if (n_sent == 0) return 0;
+  ytc::timer_begin(c, "encode");
+  {
+    uint64_t warps_needed = n_sent;
+    uint64_t blocks = std::min<uint64_t>((warps_needed + 7) / 8, (uint64_t)c->n_sm * 8);
+    ytc::timer_begin(c, "enc_find");
+    find_words_kernel<<<(unsigned)std::max<uint64_t>(blocks, 1), 256, 0, c->stream>>>(a);
+    ytc::timer_end(c, "enc_find");
+    c->launches++;
+  }
+  unsigned long long n_words = 0;
+  YT_CUDA(c, cudaMemcpyAsync(&n_words, a.n_words, 8, cudaMemcpyDeviceToHost, c->stream));
+  YT_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (n_words) {
+    uint64_t blocks = std::min<uint64_t>((n_words + 127) / 128, (uint64_t)c->n_sm * 16);
+    ytc::timer_begin(c, "enc_words");
+    encode_words_kernel<<<(unsigned)blocks, 128, 0, c->stream>>>(a, n_words);
+    ytc::timer_end(c, "enc_words");
+    c->launches++;
+  }
+  // exclusive scan of the per-sentence id counts -> output offsets
+  ytc::timer_begin(c, "enc_scan");
+  if (yttm_device_scan_u64(c, a.n_ids, n_sent, e->out_off.as<unsigned long long>(), d_total)) return 1;
+  ytc::timer_end(c, "enc_scan");
+  unsigned long long total = 0;
+  YT_CUDA(c, cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, c->stream));
+  YT_CUDA(c, cudaMemcpyAsync(e->out_off.as<unsigned long long>() + n_sent, d_total, 8, cudaMemcpyDeviceToDevice,
+                             c->stream));
+  YT_CUDA(c, cudaStreamSynchronize(c->stream));
+  YT_CUDA(c, e->out_ids.reserve((total + 8) * 4));
+  {
+    uint64_t blocks = std::min<uint64_t>((n_sent + 7) / 8, (uint64_t)c->n_sm * 8);
+    ytc::timer_begin(c, "enc_gather");
+    gather_ids_kernel<<<(unsigned)std::max<uint64_t>(blocks, 1), 256, 0, c->stream>>>(
+        a, e->out_off.as<unsigned long long>(), e->out_ids.as<int32_t>());
+    ytc::timer_end(c, "enc_gather");
+    c->launches++;
+  }
+  ytc::timer_end(c, "encode");
+  YT_CUDA(c, cudaGetLastError());
+  *out_n = total;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int yttm_enc_create(yttm_ctx *c, const uint32_t *char_cp, const uint32_t *char_id, uint64_t n_chars,
+                    const uint32_t *rules_xyz, uint64_t n_rules, int unk_id, int pad_id, int bos_id, int eos_id,
+                    yttm_enc **out) {
+  *out = nullptr;
+  YT_CUDA(c, cudaSetDevice(c->device));
+  yttm_enc *e = new yttm_enc();
+  e->ctx = c;
+  e->unk = unk_id; e->pad = pad_id; e->bos = bos_id; e->eos = eos_id;
+  std::vector<uint32_t> tab(CP_LIMIT, NO_ID);
+  bool have_space = false;
+  for (uint64_t i = 0; i < n_chars; i++) {
+    if (char_cp[i] >= CP_LIMIT) { delete e; YT_FAIL(c, "model: code point out of range"); }
+    tab[char_cp[i]] = char_id[i];
+    if (char_cp[i] == SPACE_CP) { e->space_id = char_id[i]; have_space = true; }
+  }
+  if (!have_space) { delete e; YT_FAIL(c, "model: U+2581 missing from char2id"); }
+  uint64_t cap = std::max<uint64_t>(ytc::pow2ceil(n_rules * 2 + 2), 1024);
+  std::vector<uint4> slots(cap, make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0));
+  for (uint64_t i = 0; i < n_rules; i++) {
+    uint32_t x = rules_xyz[3 * i], y = rules_xyz[3 * i + 1], z = rules_xyz[3 * i + 2];
+    uint64_t h = mix64(pair_key(x, y)) & (cap - 1);
+    bool dup = false;
+    while (slots[h].x != 0xffffffffu) {
+      if (slots[h].x == x && slots[h].y == y) { dup = true; break; }  // rule2id keeps the LAST index (bpe.cpp:1672)
+      h = (h + 1) & (cap - 1);
+    }
+    if (dup) { slots[h].z = (uint32_t)i; slots[h].w = z; }
+    else slots[h] = make_uint4(x, y, (uint32_t)i, z);
+  }
+  e->rule_mask = (uint32_t)(cap - 1);
+  if (e->cp2id.reserve(CP_LIMIT * 4) != cudaSuccess || e->rules.reserve(cap * 16) != cudaSuccess) {
+    delete e;
+    YT_FAIL(c, "yttm_enc_create: out of device memory");
+  }
+  YT_CUDA(c, cudaMemcpyAsync(e->cp2id.p, tab.data(), CP_LIMIT * 4, cudaMemcpyHostToDevice, c->stream));
+  YT_CUDA(c, cudaMemcpyAsync(e->rules.p, slots.data(), cap * 16, cudaMemcpyHostToDevice, c->stream));
+  YT_CUDA(c, cudaStreamSynchronize(c->stream));
+  *out = e;
+  return 0;
+}
+
+void yttm_enc_destroy(yttm_enc *e) {
+  if (!e) return;
+  cudaSetDevice(e->ctx->device);
+  ytc::DevBuf *bufs[] = {&e->cp2id, &e->rules, &e->d_bytes, &e->d_offs, &e->slots, &e->ranks, &e->aux, &e->wpos,
+                         &e->wsent, &e->nids, &e->out_off, &e->out_ids, &e->counter};
+  for (auto *b : bufs) b->release();
+  delete e;
+}
+
+int yttm_enc_run_device(yttm_enc *e, const char *d_bytes, const uint64_t *d_offsets, uint64_t n_bytes, uint64_t n_sent,
+                        int bos, int eos, int reverse, double dropout, uint64_t seed, uint64_t first_sentence_index,
+                        const int32_t **d_out_ids, const uint64_t **d_out_offsets, uint64_t *out_n) {
+  yttm_ctx *c = e->ctx;
+  YT_CUDA(c, cudaSetDevice(c->device));
+  if (bos && e->bos == -1) YT_FAIL(c, "Can't add <BOS> token. Model was trained without it.");
+  if (eos && e->eos == -1) YT_FAIL(c, "Can't add <EOS> token. Model was trained without it.");
+  if (enc_device(e, (const uint8_t *)d_bytes, d_offsets, n_bytes, n_sent, bos, eos, reverse, dropout, seed,
+                 first_sentence_index, out_n))
+    return 1;
+  if (d_out_ids) *d_out_ids = e->out_ids.as<int32_t>();
+  if (d_out_offsets) *d_out_offsets = e->out_off.as<uint64_t>();
+  return 0;
+}
+
+int yttm_enc_run(yttm_enc *e, const char *bytes, const uint64_t *offsets, uint64_t n_sent, int bos, int eos, int reverse,
+                 double dropout, uint64_t seed, uint64_t first_sentence_index, int32_t *out_ids, uint64_t out_cap,
+                 uint64_t *out_offsets, uint64_t *out_n) {
+  yttm_ctx *c = e->ctx;
+  YT_CUDA(c, cudaSetDevice(c->device));
+  if (bos && e->bos == -1) YT_FAIL(c, "Can't add <BOS> token. Model was trained without it.");
+  if (eos && e->eos == -1) YT_FAIL(c, "Can't add <EOS> token. Model was trained without it.");
+  *out_n = 0;
+  if (n_sent == 0) { if (out_offsets) out_offsets[0] = 0; return 0; }
+  const uint64_t n_bytes = offsets[n_sent] - offsets[0];
+  ytc::timer_begin(c, "h2d");
+  YT_CUDA(c, e->d_bytes.reserve(n_bytes + 64));
+  YT_CUDA(c, e->d_offs.reserve((n_sent + 1) * 8));
+  if (n_bytes) YT_CUDA(c, cudaMemcpyAsync(e->d_bytes.p, bytes + offsets[0], n_bytes, cudaMemcpyHostToDevice, c->stream));
+  YT_CUDA(c, cudaMemcpyAsync(e->d_offs.p, offsets, (n_sent + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  ytc::timer_end(c, "h2d");
+  uint64_t total = 0;
+  if (enc_device(e, e->d_bytes.as<uint8_t>(), e->d_offs.as<uint64_t>(), n_bytes, n_sent, bos, eos, reverse, dropout,
+                 seed, first_sentence_index, &total))
+    return 1;
+  *out_n = total;
+  if (total > out_cap) { c->err = "yttm_enc_run: output buffer too small"; return 2; }
+  ytc::timer_begin(c, "d2h");
+  if (total) YT_CUDA(c, cudaMemcpyAsync(out_ids, e->out_ids.p, total * 4, cudaMemcpyDeviceToHost, c->stream));
+  YT_CUDA(c, cudaMemcpyAsync(out_offsets, e->out_off.p, (n_sent + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+  ytc::timer_end(c, "d2h");
+  return 0;
+}
+
+}  // extern "C"

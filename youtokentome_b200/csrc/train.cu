@@ -1,0 +1,970 @@
+// train.cu — hot path (a): BPE training on one B200.
+//
+// Replaces, behind the C ABI of include/yttm_b200.h, the data-parallel phases of the
+// reference's learn_bpe_from_string (youtokentome/cpp/bpe.cpp:859-1293):
+//   char_hist_kernel     <- compute_char_count            (bpe.cpp:839-857, utf8.cpp:37-74)
+//   word_insert_kernel   <- compute_word_count / VectorSegment (bpe.cpp:28-54, 388-418)
+//   word_len/tokenise    <- remove_rare_chars + tokenisation   (bpe.cpp:357-380, 405-411)
+//   pair_hist_kernel     <- build_linked_list pair2cnt     (bpe.cpp:436-478)
+//   merge_loop_kernel    <- main loop + worker_doing_merge + PriorityQueue
+//                           (bpe.cpp:1121-1282, 601-811, 149-314; order :110-126)
+// Design (B200-first, not a port): words are deduplicated on the device, their tokens live in
+// one packed uint32 buffer (offsets + uint64 frequencies beside it) that stays resident in
+// HBM/L2; the whole merge loop runs inside ONE persistent cooperative kernel (grid-wide
+// barriers instead of the reference's mutex/condvar ping-pong): each iteration is an exact
+// arg-max over a device open-addressed pair->count table followed by a scan of the packed
+// tokens that rewrites the affected words in place and patches the table with atomics.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+using namespace yt;
+
+namespace {
+
+constexpr unsigned long long PK_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+constexpr uint64_t POS_MASK = (1ull << 40) - 1;
+
+// ------------------------------------------------------------------------------------------
+// pair -> count table: open addressing, linear probing, SoA (keys / counts) so the arg-max
+// sweep streams 8 B per slot and touches keys only for candidates.
+// ------------------------------------------------------------------------------------------
+struct PairTab {
+  unsigned long long *keys;
+  unsigned long long *cnts;
+  uint64_t mask;
+  uint32_t *n_keys;
+  uint32_t *overflow;
+};
+
+__device__ __forceinline__ void pair_add(const PairTab &t, uint64_t key, long long delta) {
+  uint64_t h = mix64(key) & t.mask;
+  for (uint64_t probe = 0; probe <= t.mask; probe++) {
+    unsigned long long k = __ldcg(t.keys + h);
+    if (k == PK_EMPTY) {
+      k = atomicCAS(t.keys + h, PK_EMPTY, (unsigned long long)key);
+      if (k == PK_EMPTY) { atomicAdd(t.n_keys, 1u); k = key; }
+    }
+    if (k == key) { atomicAdd(t.cnts + h, (unsigned long long)delta); return; }
+    h = (h + 1) & t.mask;
+  }
+  atomicExch(t.overflow, 1u);
+}
+
+// ------------------------------------------------------------------------------------------
+// phase 1: decode units + code point histogram
+// ------------------------------------------------------------------------------------------
+constexpr int HIST_SMEM_BINS = 2048;  // every 1- and 2-byte code point
+
+__global__ void __launch_bounds__(512) char_hist_kernel(const uint8_t *__restrict__ s, uint64_t n,
+                                                        unsigned long long *__restrict__ hist) {
+  __shared__ uint32_t sh[HIST_SMEM_BINS];
+  __shared__ unsigned long long s_units;
+  for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x) sh[i] = 0;
+  if (threadIdx.x == 0) s_units = 0;
+  __syncthreads();
+  uint64_t units = 0;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+    if (!is_unit_start(s, p, 0, n)) continue;
+    units++;
+    uint32_t len, cp = decode_unit(s, p, n, &len);
+    if (cp == INVALID_CP || is_space_cp(cp)) continue;
+    if (cp < HIST_SMEM_BINS) atomicAdd(&sh[cp], 1u);
+    else atomicAdd(hist + cp, 1ull);
+  }
+  for (int o = 16; o > 0; o >>= 1) units += __shfl_xor_sync(0xffffffffu, units, o);
+  if ((threadIdx.x & 31) == 0 && units) atomicAdd(&s_units, (unsigned long long)units);
+  __syncthreads();
+  for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x)
+    if (sh[i]) atomicAdd(hist + i, (unsigned long long)sh[i]);
+  if (threadIdx.x == 0 && s_units) atomicAdd(hist + CP_LIMIT, s_units);
+}
+
+__global__ void hist_count_nonzero_kernel(const unsigned long long *__restrict__ hist, unsigned long long *out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool nz = i < CP_LIMIT && hist[i] != 0;
+  unsigned m = __ballot_sync(0xffffffffu, nz);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
+}
+
+// ------------------------------------------------------------------------------------------
+// phase 2: word split + dedup.  Key word = ((tag24 << 40) | (byte position + 1)) of the first
+// occurrence that claimed the slot; duplicates are verified byte by byte against it.
+// ------------------------------------------------------------------------------------------
+struct WordTab {
+  unsigned long long *keys;  // 0 = empty
+  unsigned long long *cnts;
+  uint64_t mask;
+};
+// counters: [0] word occurrences, [1] unique words, [2] overflow flag, [3] compaction cursor
+
+__device__ __forceinline__ bool same_word(const uint8_t *s, uint64_t n, uint64_t a, uint64_t b, uint64_t len) {
+  if (a + len > n) return false;
+  for (uint64_t i = 0; i < len; i++)
+    if (s[a + i] != s[b + i]) return false;
+  uint32_t l;
+  return a + len == n || space_at(s, a + len, n, &l);
+}
+
+__global__ void __launch_bounds__(256) word_insert_kernel(const uint8_t *__restrict__ s, uint64_t n, WordTab wt,
+                                                          unsigned long long *counters, uint64_t max_unique) {
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t occ = 0;
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+    if (!word_start_at(s, p, 0, n)) continue;
+    occ++;
+    uint64_t h = 0xcbf29ce484222325ull, q = p;
+    uint32_t l;
+    while (q < n && !space_at(s, q, n, &l)) { h = (h ^ s[q]) * 0x100000001b3ull; q++; }
+    uint64_t len = q - p;
+    h = mix64(h ^ (len << 1));
+    uint64_t tag = h >> 40;
+    unsigned long long mine = (tag << 40) | (p + 1);
+    uint64_t slot = h & wt.mask;
+    for (uint64_t probe = 0; probe <= wt.mask; probe++) {
+      unsigned long long k = __ldcg(wt.keys + slot);
+      if (k == 0) {
+        if (__ldcg(counters + 1) >= max_unique) { atomicExch(counters + 2, 1ull); break; }
+        k = atomicCAS(wt.keys + slot, 0ull, mine);
+        if (k == 0) { atomicAdd(counters + 1, 1ull); atomicAdd(wt.cnts + slot, 1ull); break; }
+      }
+      if ((k >> 40) == tag && same_word(s, n, (k & POS_MASK) - 1, p, len)) { atomicAdd(wt.cnts + slot, 1ull); break; }
+      slot = (slot + 1) & wt.mask;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) occ += __shfl_xor_sync(0xffffffffu, occ, o);
+  if ((threadIdx.x & 31) == 0 && occ) atomicAdd(counters + 0, (unsigned long long)occ);
+}
+
+__global__ void word_compact_kernel(WordTab wt, unsigned long long *counters, uint64_t *__restrict__ wpos,
+                                    uint64_t *__restrict__ wfreq) {
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= wt.mask; i += stride) {
+    unsigned long long k = wt.keys[i];
+    if (k == 0) continue;
+    unsigned long long idx = atomicAdd(counters + 3, 1ull);
+    wpos[idx] = (k & POS_MASK) - 1;
+    wfreq[idx] = wt.cnts[i];
+  }
+}
+
+// tokens of one unique word: [space_id] + ids of kept chars; removed / invalid units vanish.
+// MODE 0: count only.  MODE 1: write.
+template <int MODE>
+__global__ void word_tokens_kernel(const uint8_t *__restrict__ s, uint64_t n, const uint64_t *__restrict__ wpos,
+                                   uint64_t n_unique, const uint32_t *__restrict__ cp2id, uint32_t space_id,
+                                   unsigned long long *__restrict__ lens, const unsigned long long *__restrict__ scan,
+                                   uint32_t *__restrict__ tok, uint32_t *__restrict__ off) {
+  uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_unique) return;
+  uint64_t q = wpos[w];
+  uint32_t kept = 0, l;
+  uint32_t *t = nullptr;
+  if (MODE == 1) {
+    uint32_t o = (uint32_t)scan[w];
+    off[w] = o;
+    if (w + 1 == n_unique) off[n_unique] = (uint32_t)(scan[w] + lens[w]);
+    if (lens[w] == 0) return;
+    t = tok + o;
+    t[0] = space_id;
+  }
+  while (q < n && !space_at(s, q, n, &l)) {
+    uint32_t cp = decode_unit(s, q, n, &l);
+    q += l;
+    if (cp == INVALID_CP) continue;
+    uint32_t id = cp2id[cp];
+    if (id == NO_ID) continue;
+    kept++;
+    if (MODE == 1) t[kept] = id;
+  }
+  if (MODE == 0) lens[w] = kept ? kept + 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// exclusive scan of uint64 (3 launches; n up to ~2^31)
+// ------------------------------------------------------------------------------------------
+constexpr int SCAN_T = 256, SCAN_I = 8, SCAN_B = SCAN_T * SCAN_I;
+
+__device__ __forceinline__ unsigned long long block_excl_scan(unsigned long long v, unsigned long long *total) {
+  __shared__ unsigned long long wsum[SCAN_T / 32];
+  __shared__ unsigned long long wtot;
+  unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned long long x = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= (unsigned)o) x += y;
+  }
+  if (lane == 31) wsum[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    unsigned long long s = lane < SCAN_T / 32 ? wsum[lane] : 0, xs = s;
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned long long y = __shfl_up_sync(0xffffffffu, xs, o);
+      if (lane >= (unsigned)o) xs += y;
+    }
+    if (lane < SCAN_T / 32) wsum[lane] = xs - s;
+    if (lane == 31) wtot = xs;
+  }
+  __syncthreads();
+  unsigned long long r = x - v + wsum[wid];
+  *total = wtot;
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(SCAN_T) scan_block_sums_kernel(const unsigned long long *__restrict__ in, uint64_t n,
+                                                                 unsigned long long *__restrict__ bsum) {
+  uint64_t base = (uint64_t)blockIdx.x * SCAN_B + (uint64_t)threadIdx.x * SCAN_I;
+  unsigned long long v = 0;
+  for (int i = 0; i < SCAN_I; i++)
+    if (base + i < n) v += in[base + i];
+  unsigned long long tot;
+  block_excl_scan(v, &tot);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(SCAN_T) scan_sums_kernel(unsigned long long *bsum, uint64_t nb,
+                                                           unsigned long long *total) {
+  unsigned long long carry = 0;
+  for (uint64_t base = 0; base < nb; base += SCAN_T) {
+    uint64_t i = base + threadIdx.x;
+    unsigned long long v = i < nb ? bsum[i] : 0, tot;
+    unsigned long long e = block_excl_scan(v, &tot);
+    if (i < nb) bsum[i] = carry + e;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(SCAN_T) scan_final_kernel(const unsigned long long *__restrict__ in, uint64_t n,
+                                                            const unsigned long long *__restrict__ bsum,
+                                                            unsigned long long *__restrict__ out) {
+  uint64_t base = (uint64_t)blockIdx.x * SCAN_B + (uint64_t)threadIdx.x * SCAN_I;
+  unsigned long long a[SCAN_I], v = 0;
+  for (int i = 0; i < SCAN_I; i++) { a[i] = base + i < n ? in[base + i] : 0; v += a[i]; }
+  unsigned long long tot;
+  unsigned long long e = block_excl_scan(v, &tot) + bsum[blockIdx.x];
+  for (int i = 0; i < SCAN_I; i++) {
+    if (base + i < n) out[base + i] = e;
+    e += a[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// phase 3: the pair-count scan (headline kernel): packed tokens -> pair table.
+// Algorithmic bytes per launch: 4 T (tokens) + 4 U (offsets) + 8 U (frequencies).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pair_hist_kernel(const uint32_t *__restrict__ tok,
+                                                        const uint32_t *__restrict__ off,
+                                                        const uint64_t *__restrict__ freq, uint64_t n_words,
+                                                        PairTab tab) {
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+    uint32_t o = off[w], cap = off[w + 1] - o;
+    if (cap < 2) continue;
+    long long f = (long long)freq[w];
+    for_each_pair(tok + o, cap, [&](uint64_t key, uint64_t mult) { pair_add(tab, key, (long long)mult * f); });
+  }
+}
+
+__global__ void pair_count_live_kernel(const unsigned long long *__restrict__ cnts, uint64_t cap,
+                                       unsigned long long *out) {
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  unsigned long long c = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride) c += cnts[i] != 0;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+__global__ void pair_dump_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ cnts,
+                                 uint64_t cap, unsigned long long *cursor, uint64_t out_cap,
+                                 unsigned long long *okeys, unsigned long long *ocnts) {
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride) {
+    if (keys[i] == PK_EMPTY || cnts[i] == 0) continue;
+    unsigned long long idx = atomicAdd(cursor, 1ull);
+    if (idx < out_cap) { okeys[idx] = keys[i]; ocnts[idx] = cnts[i]; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// phase 4: the persistent merge loop
+// ------------------------------------------------------------------------------------------
+struct LoopArgs {
+  uint32_t *tok;
+  const uint32_t *off;
+  const uint64_t *freq;
+  uint64_t n_words;
+  PairTab tab;
+  YtLoopCtl *ctl;
+  unsigned long long *blockbest;  // 3 per block: count, prio, slot
+  uint32_t *rules;                // 3 per merge
+  unsigned long long *rfreq;
+  uint32_t first_new_id;          // id of merge number 0
+  uint32_t max_total;             // stop when ctl->n_done reaches this
+  uint32_t max_iters;             // iterations allowed in this launch
+  uint32_t key_limit;             // leave for a rebuild above this table occupancy
+};
+
+struct Best { unsigned long long c, prio, slot; };
+__device__ __forceinline__ bool better(const Best &a, const Best &b) {  // a beats b
+  return a.c > b.c || (a.c == b.c && a.prio > b.prio);
+}
+__device__ __forceinline__ Best warp_best(Best v) {
+  for (int o = 16; o > 0; o >>= 1) {
+    Best w;
+    w.c = __shfl_xor_sync(0xffffffffu, v.c, o);
+    w.prio = __shfl_xor_sync(0xffffffffu, v.prio, o);
+    w.slot = __shfl_xor_sync(0xffffffffu, v.slot, o);
+    if (better(w, v)) v = w;
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(512) merge_loop_kernel(LoopArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ Best s_warp[16];
+  __shared__ Best s_best;
+  __shared__ unsigned long long s_dead;
+  const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t gstride = (uint64_t)gridDim.x * blockDim.x;
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const uint64_t cap = a.tab.mask + 1;
+  const uint32_t n_done0 = a.ctl->n_done;
+
+  for (uint32_t it = 0; it < a.max_iters; ++it) {
+    const uint32_t n_done = n_done0 + it;
+    if (n_done >= a.max_total) break;
+    // ---------------- arg-max over the table under MergeCandidate::operator< (bpe.cpp:110-126)
+    Best b{0, 0, 0};
+    for (uint64_t i = gtid; i < cap; i += gstride) {
+      unsigned long long c = __ldcg(a.tab.cnts + i);
+      if (c != 0 && c >= b.c) {
+        unsigned long long k = __ldcg(a.tab.keys + i);
+        Best cand{c, pair_prio((uint32_t)(k >> 32), (uint32_t)k), i};
+        if (better(cand, b)) b = cand;
+      }
+    }
+    b = warp_best(b);
+    if (lane == 0) s_warp[wid] = b;
+    __syncthreads();
+    if (wid == 0) {
+      Best v = lane < nwarp ? s_warp[lane] : Best{0, 0, 0};
+      v = warp_best(v);
+      if (lane == 0) {
+        a.blockbest[3 * blockIdx.x + 0] = v.c;
+        a.blockbest[3 * blockIdx.x + 1] = v.prio;
+        a.blockbest[3 * blockIdx.x + 2] = v.slot;
+      }
+    }
+    grid.sync();
+    if (wid == 0) {
+      Best v{0, 0, 0};
+      for (unsigned j = lane; j < gridDim.x; j += 32) {
+        Best w{__ldcg(a.blockbest + 3 * j), __ldcg(a.blockbest + 3 * j + 1), __ldcg(a.blockbest + 3 * j + 2)};
+        if (better(w, v)) v = w;
+      }
+      v = warp_best(v);
+      if (lane == 0) { s_best = v; s_dead = 0; }
+    }
+    __syncthreads();
+    const Best win = s_best;
+    if (win.c == 0) {  // no pair left: "merged only" (bpe.cpp:1137-1145)
+      if (gtid == 0) a.ctl->stop = 1;
+      break;
+    }
+    const unsigned long long wkey = __ldcg(a.tab.keys + win.slot);
+    const uint32_t x = (uint32_t)(wkey >> 32), y = (uint32_t)wkey, z = a.first_new_id + n_done;
+    if (gtid == 0) {
+      a.rules[3 * n_done + 0] = x; a.rules[3 * n_done + 1] = y; a.rules[3 * n_done + 2] = z;
+      a.rfreq[n_done] = win.c;
+      a.tab.cnts[win.slot] = 0;  // every occurrence of (x,y) is merged below; no deltas are sent for it
+      a.ctl->n_done = n_done + 1;
+    }
+    // ---------------- apply x y -> z to every word that holds it; patch the table
+    unsigned long long dead = 0;
+    for (uint64_t w = gtid; w < a.n_words; w += gstride) {
+      uint32_t o = a.off[w], wcap = a.off[w + 1] - o;
+      uint32_t *t = a.tok + o;
+      if (!has_pair(t, wcap, x, y)) continue;
+      long long f = (long long)a.freq[w];
+      for_each_pair(t, wcap, [&](uint64_t key, uint64_t mult) {
+        if (key != wkey) pair_add(a.tab, key, -(long long)mult * f);
+      });
+      dead += rewrite_word(t, wcap, x, y, z);
+      for_each_pair(t, wcap, [&](uint64_t key, uint64_t mult) { pair_add(a.tab, key, (long long)mult * f); });
+    }
+    for (int o = 16; o > 0; o >>= 1) dead += __shfl_xor_sync(0xffffffffu, dead, o);
+    if (lane == 0 && dead) atomicAdd(&s_dead, dead);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_dead) atomicAdd(&a.ctl->dead, s_dead);
+    grid.sync();
+    // ---------------- uniform exit checks (every block reads the same values)
+    uint32_t nk = __ldcg(&a.ctl->n_keys), ov = __ldcg(&a.ctl->overflow);
+    unsigned long long dd = __ldcg(&a.ctl->dead), sl = __ldcg(&a.ctl->slots);
+    if (ov || nk > a.key_limit) { if (gtid == 0) a.ctl->stop = 2; break; }
+    if (dd * 4 > sl && sl > 65536) { if (gtid == 0) a.ctl->stop = 3; break; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// compaction of the packed words: drop tombstones and words with fewer than 2 live tokens
+// ------------------------------------------------------------------------------------------
+__global__ void compact_len_kernel(const uint32_t *__restrict__ tok, const uint32_t *__restrict__ off,
+                                   uint64_t n_words, unsigned long long *__restrict__ packed) {
+  uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  uint32_t o = off[w];
+  uint32_t live = live_len(tok + o, off[w + 1] - o);
+  packed[w] = live >= 2 ? ((1ull << 32) | live) : 0ull;  // hi: keeps a word, lo: its tokens
+}
+__global__ void compact_copy_kernel(const uint32_t *__restrict__ tok, const uint32_t *__restrict__ off,
+                                    const uint64_t *__restrict__ freq, uint64_t n_words,
+                                    const unsigned long long *__restrict__ packed,
+                                    const unsigned long long *__restrict__ scan, uint32_t *__restrict__ ntok,
+                                    uint32_t *__restrict__ noff, uint64_t *__restrict__ nfreq) {
+  uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  unsigned long long p = packed[w];
+  if (p == 0) return;
+  uint32_t live = (uint32_t)p, nw = (uint32_t)(scan[w] >> 32), no = (uint32_t)scan[w];
+  const uint32_t *t = tok + off[w];
+  for (uint32_t i = 0; i < live; i++) ntok[no + i] = t[i];
+  noff[nw] = no;
+  nfreq[nw] = freq[w];
+}
+__global__ void set_u32_kernel(uint32_t *p, uint32_t v) { *p = v; }
+
+// synthetic packed words for roofline runs of the scan kernel
+__global__ void synth_words_kernel(uint32_t *tok, uint32_t *off, uint64_t *freq, uint64_t n_words, uint32_t len,
+                                   uint32_t alphabet, uint64_t seed) {
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w <= n_words; w += stride) {
+    off[w] = (uint32_t)(w * len);
+    if (w == n_words) break;
+    freq[w] = 1 + (mix64(w ^ seed) & 7);
+    uint64_t r = mix64(w * 0x9E3779B97F4A7C15ull + seed);
+    for (uint32_t i = 0; i < len; i++) {
+      r = r * 6364136223846793005ull + 1442695040888963407ull;
+      tok[w * len + i] = 4 + (uint32_t)((r >> 33) % alphabet);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side helpers
+// ------------------------------------------------------------------------------------------
+int grid_for(yttm_ctx *c, uint64_t n, int threads, int per_sm) {
+  uint64_t need = (n + threads - 1) / threads;
+  uint64_t cap = (uint64_t)c->n_sm * per_sm;
+  return (int)std::max<uint64_t>(1, std::min(need, cap));
+}
+
+int device_scan(yttm_ctx *c, const unsigned long long *in, uint64_t n, unsigned long long *out,
+                unsigned long long *d_total) {
+  uint64_t nb = (n + SCAN_B - 1) / SCAN_B;
+  YT_CUDA(c, c->scan_tmp.reserve((nb + 1) * 8));
+  auto *bs = c->scan_tmp.as<unsigned long long>();
+  scan_block_sums_kernel<<<(unsigned)nb, SCAN_T, 0, c->stream>>>(in, n, bs);
+  scan_sums_kernel<<<1, SCAN_T, 0, c->stream>>>(bs, nb, d_total);
+  scan_final_kernel<<<(unsigned)nb, SCAN_T, 0, c->stream>>>(in, n, bs, out);
+  c->launches += 3;
+  YT_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+PairTab tab_of(yttm_ctx *c) {
+  PairTab t;
+  t.keys = c->pkey.as<unsigned long long>();
+  t.cnts = c->pcnt.as<unsigned long long>();
+  t.mask = c->pcap - 1;
+  YtLoopCtl *ctl = c->ctl.as<YtLoopCtl>();
+  t.n_keys = &ctl->n_keys;
+  t.overflow = &ctl->overflow;
+  return t;
+}
+
+// (Re)build the pair table from the current packed words.  Grows the table until the load
+// factor after the build is <= 1/4.
+int rebuild_pair_table(yttm_ctx *c, uint64_t min_cap) {
+  uint64_t cap = std::max<uint64_t>(ytc::pow2ceil(min_cap), 1u << 16);
+  YT_CUDA(c, c->ctl.reserve(sizeof(YtLoopCtl)));
+  for (int attempt = 0; attempt < 12; attempt++) {
+    YT_CUDA(c, c->pkey.reserve(cap * 8));
+    YT_CUDA(c, c->pcnt.reserve(cap * 8));
+    c->pcap = cap;
+    YT_CUDA(c, cudaMemsetAsync(c->pkey.p, 0xff, cap * 8, c->stream));
+    YT_CUDA(c, cudaMemsetAsync(c->pcnt.p, 0, cap * 8, c->stream));
+    YtLoopCtl *ctl = c->ctl.as<YtLoopCtl>();
+    YT_CUDA(c, cudaMemsetAsync(&ctl->n_keys, 0, 8, c->stream));  // n_keys + overflow
+    if (c->n_words) {
+      pair_hist_kernel<<<grid_for(c, c->n_words, 256, 8), 256, 0, c->stream>>>(
+          c->tok[c->cur].as<uint32_t>(), c->off[c->cur].as<uint32_t>(), c->freq[c->cur].as<uint64_t>(), c->n_words,
+          tab_of(c));
+      c->launches++;
+    }
+    YT_CUDA(c, cudaGetLastError());
+    uint32_t h[2];
+    YT_CUDA(c, cudaMemcpyAsync(h, &ctl->n_keys, 8, cudaMemcpyDeviceToHost, c->stream));
+    YT_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!h[1] && (uint64_t)h[0] * 4 <= cap) { c->stats.n_pairs = h[0]; c->stats.table_capacity = cap; return 0; }
+    cap *= 4;
+  }
+  YT_FAIL(c, "pair table: could not reach load factor 1/4");
+}
+
+// Compact the packed words into the other buffer set.
+int compact_words(yttm_ctx *c) {
+  if (c->n_words == 0) return 0;
+  uint64_t nw = c->n_words;
+  int src = c->cur, dst = 1 - c->cur;
+  YT_CUDA(c, c->wlen.reserve((nw + 1) * 8));
+  YT_CUDA(c, c->wpos.reserve((nw + 1) * 8));
+  auto *packed = c->wlen.as<unsigned long long>();
+  auto *scan = c->wpos.as<unsigned long long>();
+  YT_CUDA(c, c->counters.reserve(64));
+  auto *d_total = c->counters.as<unsigned long long>() + 4;
+  unsigned nb = (unsigned)((nw + 255) / 256);
+  compact_len_kernel<<<nb, 256, 0, c->stream>>>(c->tok[src].as<uint32_t>(), c->off[src].as<uint32_t>(), nw, packed);
+  c->launches++;
+  if (device_scan(c, packed, nw, scan, d_total)) return 1;
+  unsigned long long tot;
+  YT_CUDA(c, cudaMemcpyAsync(&tot, d_total, 8, cudaMemcpyDeviceToHost, c->stream));
+  YT_CUDA(c, cudaStreamSynchronize(c->stream));
+  uint64_t new_words = tot >> 32, new_slots = tot & 0xffffffffull;
+  YT_CUDA(c, c->tok[dst].reserve((new_slots + 4) * 4));
+  YT_CUDA(c, c->off[dst].reserve((new_words + 2) * 4));
+  YT_CUDA(c, c->freq[dst].reserve((new_words + 1) * 8));
+  compact_copy_kernel<<<nb, 256, 0, c->stream>>>(c->tok[src].as<uint32_t>(), c->off[src].as<uint32_t>(),
+                                                  c->freq[src].as<uint64_t>(), nw, packed, scan,
+                                                  c->tok[dst].as<uint32_t>(), c->off[dst].as<uint32_t>(),
+                                                  c->freq[dst].as<uint64_t>());
+  set_u32_kernel<<<1, 1, 0, c->stream>>>(c->off[dst].as<uint32_t>() + new_words, (uint32_t)new_slots);
+  c->launches += 2;
+  YT_CUDA(c, cudaGetLastError());
+  c->cur = dst;
+  c->n_words = new_words;
+  c->n_slots = new_slots;
+  return 0;
+}
+
+}  // namespace
+
+thread_local std::string g_yttm_create_error;
+
+int yttm_device_scan_u64(yttm_ctx *c, const unsigned long long *in, uint64_t n, unsigned long long *out,
+                         unsigned long long *d_total) {
+  return device_scan(c, in, n, out, d_total);
+}
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int yttm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int yttm_ctx_create(int device, yttm_ctx **out) {
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    g_yttm_create_error = std::string("yttm_b200: no CUDA device available (") +
+                          (e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e)) +
+                          "); this library has no CPU fallback";
+    return 1;
+  }
+  if (device < 0 || device >= n) { g_yttm_create_error = "yttm_b200: bad device index"; return 1; }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { g_yttm_create_error = cudaGetErrorString(e); return 1; }
+  yttm_ctx *c = new yttm_ctx();
+  c->device = device;
+  cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device);
+  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    g_yttm_create_error = cudaGetErrorString(e);
+    delete c;
+    return 1;
+  }
+  *out = c;
+  return 0;
+}
+
+void yttm_ctx_destroy(yttm_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  ytc::DevBuf *bufs[] = {&c->text_buf, &c->hist, &c->cp2id, &c->wkey, &c->wcnt, &c->wpos, &c->wfreq, &c->wlen,
+                         &c->scan_tmp, &c->counters, &c->tok[0], &c->tok[1], &c->off[0], &c->off[1], &c->freq[0],
+                         &c->freq[1], &c->pkey, &c->pcnt, &c->scratch_key, &c->scratch_cnt, &c->ctl, &c->blockbest,
+                         &c->d_rules, &c->d_rfreq};
+  for (auto *b : bufs) b->release();
+  for (auto &kv : c->timers) { if (kv.second.a) cudaEventDestroy(kv.second.a); if (kv.second.b) cudaEventDestroy(kv.second.b); }
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char *yttm_last_error(const yttm_ctx *c) { return c ? c->err.c_str() : g_yttm_create_error.c_str(); }
+
+double yttm_stage_ms(const yttm_ctx *c, const char *stage) { return ytc::timer_ms(const_cast<yttm_ctx *>(c), stage); }
+uint64_t yttm_launch_count(const yttm_ctx *c) { return c->launches; }
+
+int yttm_train_load_corpus(yttm_ctx *c, const char *bytes, uint64_t n, int on_device) {
+  YT_CUDA(c, cudaSetDevice(c->device));
+  if (n >= POS_MASK) YT_FAIL(c, "corpus shard too large (>= 2^40 bytes)");
+  c->n_text = n;
+  c->have_alphabet = false;
+  if (on_device) {
+    c->d_text = reinterpret_cast<const uint8_t *>(bytes);
+    c->text_external = true;
+    return 0;
+  }
+  ytc::timer_begin(c, "h2d");
+  YT_CUDA(c, c->text_buf.reserve(n + 64));
+  uint8_t *base = c->text_buf.as<uint8_t>();
+  YT_CUDA(c, cudaMemsetAsync(base, ' ', 16, c->stream));
+  YT_CUDA(c, cudaMemsetAsync(base + 16 + n, ' ', 32, c->stream));
+  if (n) YT_CUDA(c, cudaMemcpyAsync(base + 16, bytes, n, cudaMemcpyHostToDevice, c->stream));
+  ytc::timer_end(c, "h2d");
+  c->d_text = base + 16;
+  c->text_external = false;
+  return 0;
+}
+
+static int hist_summarise(yttm_ctx *c, uint64_t *data_len, uint64_t *n_distinct) {
+  std::vector<unsigned long long> h(CP_LIMIT + 1);
+  YT_CUDA(c, cudaMemcpyAsync(h.data(), c->hist.p, (CP_LIMIT + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+  YT_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->h_hist_cp.clear(); c->h_hist_cnt.clear();
+  for (uint32_t cp = 0; cp < CP_LIMIT; cp++)
+    if (h[cp]) { c->h_hist_cp.push_back(cp); c->h_hist_cnt.push_back(h[cp]); }
+  c->data_len = h[CP_LIMIT];
+  if (data_len) *data_len = c->data_len;
+  if (n_distinct) *n_distinct = c->h_hist_cp.size();
+  return 0;
+}
+
+int yttm_train_char_hist(yttm_ctx *c, uint64_t *data_len, uint64_t *n_distinct) {
+  YT_CUDA(c, cudaSetDevice(c->device));
+  YT_CUDA(c, c->hist.reserve((CP_LIMIT + 1) * 8));
+  YT_CUDA(c, cudaMemsetAsync(c->hist.p, 0, (CP_LIMIT + 1) * 8, c->stream));
+  ytc::timer_begin(c, "char_hist");
+  if (c->n_text) {
+    char_hist_kernel<<<grid_for(c, c->n_text, 512, 4), 512, 0, c->stream>>>(c->d_text, c->n_text,
+                                                                            c->hist.as<unsigned long long>());
+    c->launches++;
+  }
+  ytc::timer_end(c, "char_hist");
+  YT_CUDA(c, cudaGetLastError());
+  return hist_summarise(c, data_len, n_distinct);
+}
+
+int yttm_train_char_hist_devptr(yttm_ctx *c, void **dptr, uint64_t *n_u64) {
+  if (!c->hist.p) YT_FAIL(c, "char_hist not computed");
+  *dptr = c->hist.p;
+  *n_u64 = CP_LIMIT + 1;
+  return 0;
+}
+int yttm_train_char_hist_refresh(yttm_ctx *c, uint64_t *data_len, uint64_t *n_distinct) {
+  if (!c->hist.p) YT_FAIL(c, "char_hist not computed");
+  return hist_summarise(c, data_len, n_distinct);
+}
+
+int yttm_train_get_char_hist(yttm_ctx *c, uint32_t *cps, uint64_t *counts) {
+  std::memcpy(cps, c->h_hist_cp.data(), c->h_hist_cp.size() * 4);
+  std::memcpy(counts, c->h_hist_cnt.data(), c->h_hist_cnt.size() * 8);
+  return 0;
+}
+
+int yttm_train_set_alphabet(yttm_ctx *c, const uint32_t *cps, const uint32_t *ids, uint64_t n_kept, uint32_t space_id) {
+  YT_CUDA(c, cudaSetDevice(c->device));
+  std::vector<uint32_t> tab(CP_LIMIT, NO_ID);
+  for (uint64_t i = 0; i < n_kept; i++) {
+    if (cps[i] >= CP_LIMIT) YT_FAIL(c, "alphabet code point out of range");
+    tab[cps[i]] = ids[i];
+  }
+  YT_CUDA(c, c->cp2id.reserve(CP_LIMIT * 4));
+  YT_CUDA(c, cudaMemcpyAsync(c->cp2id.p, tab.data(), CP_LIMIT * 4, cudaMemcpyHostToDevice, c->stream));
+  YT_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->space_id = space_id;
+  c->have_alphabet = true;
+  return 0;
+}
+
+static int finish_build(yttm_ctx *c, yttm_train_stats *stats) {
+  ytc::timer_begin(c, "pair_hist");
+  int rc = rebuild_pair_table(c, std::max<uint64_t>(c->n_slots / 2, 1u << 16));
+  ytc::timer_end(c, "pair_hist");
+  if (rc) return rc;
+  YtLoopCtl *ctl = c->ctl.as<YtLoopCtl>();
+  YtLoopCtl h{};
+  YT_CUDA(c, cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  YT_CUDA(c, cudaStreamSynchronize(c->stream));
+  h.n_done = 0; h.stop = 0; h.dead = 0; h.slots = c->n_slots;
+  YT_CUDA(c, cudaMemcpyAsync(ctl, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+  YT_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->stats.n_bytes = c->n_text;
+  c->stats.n_words = c->n_word_occ;
+  c->stats.n_unique = c->n_words;
+  c->stats.n_tokens = c->n_slots;
+  if (stats) *stats = c->stats;
+  return 0;
+}
+
+int yttm_train_build(yttm_ctx *c, yttm_train_stats *stats) {
+  YT_CUDA(c, cudaSetDevice(c->device));
+  if (!c->have_alphabet) YT_FAIL(c, "yttm_train_build: alphabet not set");
+  const uint64_t n = c->n_text;
+  YT_CUDA(c, c->counters.reserve(64));
+  auto *counters = c->counters.as<unsigned long long>();
+  // ---- word split + dedup (retry with a larger table on overflow)
+  ytc::timer_begin(c, "word_count");
+  uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(ytc::pow2ceil(n / 16 + 1), 1u << 16), 1ull << 26);
+  unsigned long long h_cnt[4] = {0, 0, 0, 0};
+  for (int attempt = 0;; attempt++) {
+    if (attempt > 10) YT_FAIL(c, "word table: too many retries");
+    YT_CUDA(c, c->wkey.reserve(cap * 8));
+    YT_CUDA(c, c->wcnt.reserve(cap * 8));
+    YT_CUDA(c, cudaMemsetAsync(c->wkey.p, 0, cap * 8, c->stream));
+    YT_CUDA(c, cudaMemsetAsync(c->wcnt.p, 0, cap * 8, c->stream));
+    YT_CUDA(c, cudaMemsetAsync(counters, 0, 64, c->stream));
+    WordTab wt{c->wkey.as<unsigned long long>(), c->wcnt.as<unsigned long long>(), cap - 1};
+    if (n) {
+      word_insert_kernel<<<grid_for(c, n, 256, 8), 256, 0, c->stream>>>(c->d_text, n, wt, counters, cap / 2);
+      c->launches++;
+    }
+    YT_CUDA(c, cudaGetLastError());
+    YT_CUDA(c, cudaMemcpyAsync(h_cnt, counters, 32, cudaMemcpyDeviceToHost, c->stream));
+    YT_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!h_cnt[2]) break;
+    cap *= 4;
+  }
+  c->n_word_occ = h_cnt[0];
+  uint64_t U = h_cnt[1];
+  YT_CUDA(c, c->wpos.reserve((U + 1) * 8));
+  YT_CUDA(c, c->wfreq.reserve((U + 1) * 8));
+  if (U) {
+    WordTab wt{c->wkey.as<unsigned long long>(), c->wcnt.as<unsigned long long>(), cap - 1};
+    word_compact_kernel<<<grid_for(c, cap, 256, 8), 256, 0, c->stream>>>(wt, counters, c->wpos.as<uint64_t>(),
+                                                                         c->wfreq.as<uint64_t>());
+    c->launches++;
+  }
+  ytc::timer_end(c, "word_count");
+  YT_CUDA(c, cudaGetLastError());
+  // ---- tokenise the unique words into the packed buffer
+  ytc::timer_begin(c, "tokenise");
+  YT_CUDA(c, c->wlen.reserve((U + 1) * 8));
+  ytc::DevBuf &scanb = c->scratch_key;
+  YT_CUDA(c, scanb.reserve((U + 1) * 8));
+  auto *lens = c->wlen.as<unsigned long long>();
+  auto *scan = scanb.as<unsigned long long>();
+  unsigned long long T = 0;
+  c->cur = 0;
+  YT_CUDA(c, c->off[0].reserve((U + 2) * 4));
+  if (U) {
+    unsigned nb = (unsigned)((U + 255) / 256);
+    word_tokens_kernel<0><<<nb, 256, 0, c->stream>>>(c->d_text, n, c->wpos.as<uint64_t>(), U, c->cp2id.as<uint32_t>(),
+                                                     c->space_id, lens, nullptr, nullptr, nullptr);
+    c->launches++;
+    if (device_scan(c, lens, U, scan, counters + 4)) return 1;
+    YT_CUDA(c, cudaMemcpyAsync(&T, counters + 4, 8, cudaMemcpyDeviceToHost, c->stream));
+    YT_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (T >= 0xfffffff0ull) YT_FAIL(c, "more than 2^32 tokens in the unique words of one shard");
+    YT_CUDA(c, c->tok[0].reserve((T + 4) * 4));
+    word_tokens_kernel<1><<<nb, 256, 0, c->stream>>>(c->d_text, n, c->wpos.as<uint64_t>(), U, c->cp2id.as<uint32_t>(),
+                                                     c->space_id, lens, scan, c->tok[0].as<uint32_t>(),
+                                                     c->off[0].as<uint32_t>());
+    c->launches++;
+  } else {
+    YT_CUDA(c, cudaMemsetAsync(c->off[0].p, 0, 8, c->stream));
+  }
+  YT_CUDA(c, cudaGetLastError());
+  // frequencies travel with the words: freq[0] aliases wfreq (swap the buffers)
+  std::swap(c->freq[0], c->wfreq);
+  c->n_words = U;
+  c->n_slots = T;
+  // drop words that vanished (only removed chars) or cannot pair; gives the canonical layout
+  if (compact_words(c)) return 1;
+  ytc::timer_end(c, "tokenise");
+  return finish_build(c, stats);
+}
+
+int yttm_train_export_words(yttm_ctx *c, uint32_t *tokens, uint64_t tokens_cap, uint32_t *offsets, uint64_t *freq,
+                            uint64_t words_cap, uint64_t *n_words, uint64_t *n_tokens) {
+  YT_CUDA(c, cudaSetDevice(c->device));
+  *n_words = c->n_words;
+  *n_tokens = c->n_slots;
+  if (!tokens) return 0;  // size query
+  if (tokens_cap < c->n_slots || words_cap < c->n_words) YT_FAIL(c, "export_words: buffers too small");
+  YT_CUDA(c, cudaMemcpyAsync(tokens, c->tok[c->cur].p, c->n_slots * 4, cudaMemcpyDeviceToHost, c->stream));
+  YT_CUDA(c, cudaMemcpyAsync(offsets, c->off[c->cur].p, (c->n_words + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+  YT_CUDA(c, cudaMemcpyAsync(freq, c->freq[c->cur].p, c->n_words * 8, cudaMemcpyDeviceToHost, c->stream));
+  YT_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int yttm_train_import_words(yttm_ctx *c, const uint32_t *tokens, uint64_t n_tokens, const uint32_t *offsets,
+                            const uint64_t *freq, uint64_t n_words, yttm_train_stats *stats) {
+  YT_CUDA(c, cudaSetDevice(c->device));
+  if (n_tokens >= 0xfffffff0ull) YT_FAIL(c, "import_words: too many tokens");
+  c->cur = 0;
+  YT_CUDA(c, c->tok[0].reserve((n_tokens + 4) * 4));
+  YT_CUDA(c, c->off[0].reserve((n_words + 2) * 4));
+  YT_CUDA(c, c->freq[0].reserve((n_words + 1) * 8));
+  YT_CUDA(c, cudaMemcpyAsync(c->tok[0].p, tokens, n_tokens * 4, cudaMemcpyHostToDevice, c->stream));
+  YT_CUDA(c, cudaMemcpyAsync(c->off[0].p, offsets, (n_words + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+  YT_CUDA(c, cudaMemcpyAsync(c->freq[0].p, freq, n_words * 8, cudaMemcpyHostToDevice, c->stream));
+  YT_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->n_words = n_words;
+  c->n_slots = n_tokens;
+  return finish_build(c, stats);
+}
+
+int yttm_train_synth_words(yttm_ctx *c, uint64_t n_words, uint32_t len, uint32_t alphabet, uint64_t seed) {
+  YT_CUDA(c, cudaSetDevice(c->device));
+  uint64_t T = n_words * len;
+  if (T >= 0xfffffff0ull) YT_FAIL(c, "synth_words: too many tokens");
+  c->cur = 0;
+  YT_CUDA(c, c->tok[0].reserve((T + 4) * 4));
+  YT_CUDA(c, c->off[0].reserve((n_words + 2) * 4));
+  YT_CUDA(c, c->freq[0].reserve((n_words + 1) * 8));
+  synth_words_kernel<<<grid_for(c, n_words + 1, 256, 8), 256, 0, c->stream>>>(
+      c->tok[0].as<uint32_t>(), c->off[0].as<uint32_t>(), c->freq[0].as<uint64_t>(), n_words, len, alphabet, seed);
+  c->launches++;
+  YT_CUDA(c, cudaGetLastError());
+  YT_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->n_words = n_words;
+  c->n_slots = T;
+  c->n_word_occ = n_words;
+  return finish_build(c, nullptr);
+}
+
+int yttm_train_scan_once(yttm_ctx *c, double *ms, uint64_t *algo_bytes) {
+  YT_CUDA(c, cudaSetDevice(c->device));
+  if (!c->pcap) YT_FAIL(c, "scan_once: nothing built");
+  uint64_t cap = c->pcap;
+  YT_CUDA(c, c->scratch_key.reserve(cap * 8));
+  YT_CUDA(c, c->scratch_cnt.reserve(cap * 8));
+  YT_CUDA(c, c->counters.reserve(64));
+  YT_CUDA(c, cudaMemsetAsync(c->scratch_key.p, 0xff, cap * 8, c->stream));
+  YT_CUDA(c, cudaMemsetAsync(c->scratch_cnt.p, 0, cap * 8, c->stream));
+  YT_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 64, c->stream));
+  PairTab t;
+  t.keys = c->scratch_key.as<unsigned long long>();
+  t.cnts = c->scratch_cnt.as<unsigned long long>();
+  t.mask = cap - 1;
+  t.n_keys = reinterpret_cast<uint32_t *>(c->counters.as<unsigned long long>() + 6);
+  t.overflow = t.n_keys + 1;
+  ytc::timer_begin(c, "scan");
+  pair_hist_kernel<<<grid_for(c, c->n_words, 256, 8), 256, 0, c->stream>>>(
+      c->tok[c->cur].as<uint32_t>(), c->off[c->cur].as<uint32_t>(), c->freq[c->cur].as<uint64_t>(), c->n_words, t);
+  c->launches++;
+  ytc::timer_end(c, "scan");
+  YT_CUDA(c, cudaGetLastError());
+  if (ms) *ms = ytc::timer_ms(c, "scan");
+  if (algo_bytes) *algo_bytes = 4 * c->n_slots + 12 * c->n_words;
+  return 0;
+}
+
+int yttm_train_dump_pairs(yttm_ctx *c, uint64_t *keys, uint64_t *counts, uint64_t cap, uint64_t *n) {
+  YT_CUDA(c, cudaSetDevice(c->device));
+  if (!c->pcap) { *n = 0; return 0; }
+  ytc::DevBuf dk, dc;
+  YT_CUDA(c, dk.reserve((cap + 1) * 8));
+  YT_CUDA(c, dc.reserve((cap + 1) * 8));
+  YT_CUDA(c, c->counters.reserve(64));
+  auto *cursor = c->counters.as<unsigned long long>() + 5;
+  YT_CUDA(c, cudaMemsetAsync(cursor, 0, 8, c->stream));
+  pair_dump_kernel<<<grid_for(c, c->pcap, 256, 8), 256, 0, c->stream>>>(
+      c->pkey.as<unsigned long long>(), c->pcnt.as<unsigned long long>(), c->pcap, cursor, cap,
+      dk.as<unsigned long long>(), dc.as<unsigned long long>());
+  c->launches++;
+  unsigned long long cnt = 0;
+  YT_CUDA(c, cudaMemcpyAsync(&cnt, cursor, 8, cudaMemcpyDeviceToHost, c->stream));
+  YT_CUDA(c, cudaStreamSynchronize(c->stream));
+  *n = cnt;
+  uint64_t m = std::min<uint64_t>(cnt, cap);
+  if (m) {
+    YT_CUDA(c, cudaMemcpy(keys, dk.p, m * 8, cudaMemcpyDeviceToHost));
+    YT_CUDA(c, cudaMemcpy(counts, dc.p, m * 8, cudaMemcpyDeviceToHost));
+  }
+  dk.release(); dc.release();
+  return 0;
+}
+
+int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint32_t *rules_xyz, uint64_t *freqs,
+                   uint32_t *n_done_out) {
+  YT_CUDA(c, cudaSetDevice(c->device));
+  if (!c->pcap) YT_FAIL(c, "yttm_train_run: yttm_train_build has not run");
+  *n_done_out = 0;
+  if (max_merges == 0) return 0;
+  // launch geometry of the cooperative kernel: co-resident blocks only
+  if (!c->loop_blocks) {
+    int threads = 512, per_sm = 0;
+    YT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_loop_kernel, threads, 0));
+    if (per_sm < 1) YT_FAIL(c, "merge_loop_kernel does not fit on an SM");
+    c->loop_threads = threads;
+    c->loop_blocks = c->n_sm * std::min(per_sm, 2);
+  }
+  YT_CUDA(c, c->blockbest.reserve((size_t)c->loop_blocks * 3 * 8));
+  YT_CUDA(c, c->d_rules.reserve((size_t)max_merges * 12 + 16));
+  YT_CUDA(c, c->d_rfreq.reserve((size_t)max_merges * 8 + 16));
+  YtLoopCtl *ctl = c->ctl.as<YtLoopCtl>();
+  YtLoopCtl h{};
+  YT_CUDA(c, cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  YT_CUDA(c, cudaStreamSynchronize(c->stream));
+  h.n_done = 0; h.stop = 0;
+  YT_CUDA(c, cudaMemcpyAsync(ctl, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+  ytc::timer_begin(c, "merge_loop");
+  while (h.n_done < max_merges && h.stop != 1) {
+    LoopArgs a;
+    a.tok = c->tok[c->cur].as<uint32_t>();
+    a.off = c->off[c->cur].as<uint32_t>();
+    a.freq = c->freq[c->cur].as<uint64_t>();
+    a.n_words = c->n_words;
+    a.tab = tab_of(c);
+    a.ctl = ctl;
+    a.blockbest = c->blockbest.as<unsigned long long>();
+    a.rules = c->d_rules.as<uint32_t>();
+    a.rfreq = c->d_rfreq.as<unsigned long long>();
+    a.first_new_id = first_new_id;
+    a.max_total = max_merges;
+    a.max_iters = max_merges;
+    a.key_limit = (uint32_t)std::min<uint64_t>(c->pcap / 2, 0xfffffff0ull);
+    void *args[] = {&a};
+    YT_CUDA(c, cudaLaunchCooperativeKernel((void *)merge_loop_kernel, dim3(c->loop_blocks), dim3(c->loop_threads), args,
+                                           0, c->stream));
+    c->launches++;
+    YT_CUDA(c, cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    YT_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (h.overflow) YT_FAIL(c, "pair table overflow inside the merge loop");
+    if (h.stop == 1 || h.n_done >= max_merges) break;
+    // stop == 3: compaction wanted; stop == 2: table wants a rebuild
+    uint32_t why = h.stop;
+    if (compact_words(c)) return 1;
+    if (why == 2) {
+      uint32_t keep_done = h.n_done;
+      if (rebuild_pair_table(c, std::max<uint64_t>(c->pcap, 1u << 16))) return 1;
+      h.n_done = keep_done;
+      YT_CUDA(c, cudaMemcpyAsync(&h.n_keys, &ctl->n_keys, 8, cudaMemcpyDeviceToHost, c->stream));
+      YT_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    h.stop = 0; h.dead = 0; h.slots = c->n_slots;
+    YT_CUDA(c, cudaMemcpyAsync(ctl, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+  }
+  ytc::timer_end(c, "merge_loop");
+  *n_done_out = h.n_done;
+  if (h.n_done) {
+    YT_CUDA(c, cudaMemcpyAsync(rules_xyz, c->d_rules.p, (size_t)h.n_done * 12, cudaMemcpyDeviceToHost, c->stream));
+    if (freqs) YT_CUDA(c, cudaMemcpyAsync(freqs, c->d_rfreq.p, (size_t)h.n_done * 8, cudaMemcpyDeviceToHost, c->stream));
+    YT_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
+}  // extern "C"
