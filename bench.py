@@ -283,25 +283,42 @@ def main():
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
                 "kernel_ms": kern}
 
-    # ---- hot path (a) pair-count scan on a token buffer >> L2 (rank 0 only)
+    # ---- hot path (a): the per-merge-iteration scan of the packed token buffer, on a buffer >> L2
+    # (rank 0 only).  Each iteration of merge_loop_kernel streams every token slot and word offset
+    # once (TMA-staged tiles): algorithmic bytes 4T + 4U per iteration (frequencies are only read
+    # for rewritten words).  Time = device-side timers of the apply phase incl. its tail barrier.
     scan = None
     if rank == 0 and args.scan_tokens > 0:
         c2 = C.c_void_p()
         assert L.yttm_ctx_create(local, C.byref(c2)) == 0
-        wl = 8
-        rc = L.yttm_train_synth_words(c2, args.scan_tokens // wl, wl, 2000, 7)
+        wl, alpha, iters = 8, 2000, 12
+        n_w = args.scan_tokens // wl
+        rc = L.yttm_train_synth_words(c2, n_w, wl, alpha, 7)
         assert rc == 0, L.yttm_last_error(c2)
-        ms, ab = C.c_double(0), C.c_uint64(0)
-        ts = []
-        for i in range(3 + 5):
-            assert L.yttm_train_scan_once(c2, C.byref(ms), C.byref(ab)) == 0
-            if i >= 3:
-                ts.append(ms.value)
-        t = sum(ts) / len(ts)
-        a = ab.value / (t * 1e-3) / 1e9
-        scan = {"bound": "hbm", "kernel": "pair_hist_kernel", "achieved": a, "peak": hbm_peak, "unit": "GB/s",
-                "frac": a / hbm_peak, "traffic": None, "ms": t, "algorithmic_bytes_per_launch": ab.value,
-                "tokens": args.scan_tokens, "words": args.scan_tokens // wl, "peak_source": peak_src}
+        rules = np.zeros(3 * iters, dtype=np.uint32)
+        fr = np.zeros(iters, dtype=np.uint64)
+        nd = C.c_uint32(0)
+        assert L.yttm_train_run(c2, 4 + alpha, iters, rules.ctypes.data, fr.ctypes.data, C.byref(nd)) == 0, \
+            L.yttm_last_error(c2)
+        g = lambda k: L.yttm_stage_ms(c2, k.encode())
+        it = max(g("loop_iters"), 1.0)
+        t_scan = (g("loop_apply") + g("loop_barrier2")) / it          # ms per iteration
+        t_iter = g("merge_loop") / max(nd.value, 1)
+        ab = 4 * args.scan_tokens + 4 * n_w
+        ach = ab / (t_scan * 1e-3) / 1e9
+        # the one-off histogram kernel (atomics-bound, not the per-iteration scan) for reference
+        ms, ab2 = C.c_double(0), C.c_uint64(0)
+        L.yttm_train_scan_once(c2, C.byref(ms), C.byref(ab2))
+        scan = {"bound": "hbm", "kernel": "merge_loop_kernel (apply phase, STREAMING tiles via TMA)",
+                "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                "ms_per_iteration_scan": t_scan, "ms_per_iteration_total": t_iter, "iterations": int(nd.value),
+                "resident": int(g("loop_resident")), "algorithmic_bytes_per_launch": ab,
+                "tokens": args.scan_tokens, "words": n_w, "peak_source": peak_src,
+                "phase_ms_per_iter": {k: g(k) / it for k in ["loop_argmax", "loop_barrier1", "loop_apply",
+                                                              "loop_barrier2"]},
+                "table_slots": g("table_capacity"),
+                "initial_histogram": {"kernel": "pair_hist_kernel", "ms": ms.value,
+                                      "GBps": ab2.value / (ms.value * 1e-3) / 1e9}}
         L.yttm_ctx_destroy(c2)
 
     cpu = None

@@ -148,3 +148,33 @@ def test_initial_pair_table(product, oracle):
         assert st.n_unique == len(set(w for w in text.decode().split()))
     finally:
         L.yttm_ctx_destroy(ctx)
+
+
+@pytest.mark.parametrize("q", ["64", "1000"])
+def test_streaming_tiles(product, oracle, monkeypatch, q):
+    """The STREAMING mode of the merge loop (token buffer larger than shared memory) forced on
+    small inputs: many tiny tiles, words straddling tile windows, write-through to HBM."""
+    monkeypatch.setenv("YTTM_FORCE_STREAM", "1")
+    monkeypatch.setenv("YTTM_STREAM_Q", q)
+    for seed in range(8):
+        text, vocab, cov, _ = _cases.stress_case(seed)
+        _same(oracle, text, vocab, cov)
+    _same(oracle, _cases.dirty_zipf_text(), 1500, 0.98)
+    _same(oracle, b"a" * 500 + b" " + b"ab" * 300 + b" aaa aaaa aaaaa " + b"b" * 1001, 40)
+    _same(oracle, synth.readme_corpus(n_lines=1500), 1200)
+
+
+def test_oversized_word_direct_path(product, oracle):
+    """One word longer than the shared-memory tile buffer (60k tokens): the loop leaves resident
+    mode and handles that tile straight on global memory."""
+    rng = np.random.default_rng(5)
+    long_word = bytes(rng.choice(list(b"abc"), size=60_000).tolist())
+    text = synth.readme_corpus(n_lines=300) + long_word + b" " + synth.readme_corpus(n_lines=50, seed=3)
+    _same(oracle, text, 400)
+
+
+def test_words_of_33_plus_tokens(product, oracle):
+    """Words longer than a warp (scalar lane-0 path inside a tile) next to short ones."""
+    rng = np.random.default_rng(9)
+    words = [bytes(rng.choice(list(b"abcd"), size=int(n)).tolist()) for n in rng.integers(1, 90, size=3000)]
+    _same(oracle, b" ".join(words), 600)

@@ -40,8 +40,8 @@ struct YtLoopCtl {
   uint32_t overflow;          // a probe sequence wrapped (fatal)
   unsigned long long dead;    // token slots tombstoned since the last compaction
   unsigned long long slots;   // token slots at the last compaction
-  unsigned long long sync_a;  // (reserved)
-  unsigned long long sync_b;
+  unsigned long long t_phase[4];  // ns spent by block 0 in: arg-max sweep, barrier 1, apply scan, barrier 2
+  unsigned long long iters;       // iterations those times cover
 };
 
 struct yttm_ctx {
@@ -82,8 +82,12 @@ struct yttm_ctx {
   uint64_t pcap = 0;
 
   // ---- merge loop
-  ytc::DevBuf ctl, blockbest, d_rules, d_rfreq;
+  ytc::DevBuf ctl, blockbest, d_rules, d_rfreq, tiles;
+  int loop_smem = 0, loop_resident = 0;
+  uint32_t loop_tok_cap = 0, loop_word_cap = 0, loop_stream_q = 0, loop_stream_tok_cap = 0, loop_stream_word_cap = 0;
   int loop_blocks = 0, loop_threads = 0;
+  double loop_phase_ms[4] = {0, 0, 0, 0};
+  uint64_t loop_iters = 0, loop_relaunches = 0;
 
   yttm_train_stats stats{};
 };

@@ -65,56 +65,93 @@ struct EncArgs {
 // [base + len + 2] = eos.
 __device__ __forceinline__ uint64_t sent_base(uint64_t start, uint64_t s) { return start + 3 * s; }
 
+// One warp per sentence, 8 sentences per block and round.  Pass 1 counts the word starts of each
+// sentence, one atomicAdd per BLOCK reserves a contiguous range of the work list (a single
+// counter hammered once per warp was the bottleneck of the first version), pass 2 writes the
+// entries.  The slot buffer was cleared by a memset before the launch.
 __global__ void __launch_bounds__(256) find_words_kernel(EncArgs a) {
-  const unsigned lane = threadIdx.x & 31;
-  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  __shared__ unsigned long long s_cnt[8], s_base;
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint64_t o0 = a.offs[0];
-  for (uint64_t s = warp; s < a.n_sent; s += nwarps) {
-    const uint64_t lo = a.offs[s] - o0, hi = a.offs[s + 1] - o0;
-    const uint64_t base = sent_base(lo, s), len = hi - lo;
-    for (uint64_t i = lane; i < len + 3; i += 32) a.slots[base + i] = EMPTY_SLOT;
-    if (lane == 0) a.n_ids[s] = (a.bos ? 1 : 0) + (a.eos ? 1 : 0);
-    __syncwarp();
-    if (lane == 0) {
-      if (a.bos) a.slots[base] = a.bos_id;
-      if (a.eos) a.slots[base + len + 2] = a.eos_id;
-    }
-    for (uint64_t p0 = lo; p0 < hi; p0 += 32) {
-      uint64_t p = p0 + lane;
-      bool ws = p < hi && word_start_at(a.bytes, p, lo, hi);
-      unsigned m = __ballot_sync(0xffffffffu, ws);
-      if (!m) continue;
-      unsigned long long first = 0;
-      if (lane == 0) first = atomicAdd(a.n_words, (unsigned long long)__popc(m));
-      first = __shfl_sync(0xffffffffu, first, 0);
-      if (ws) {
-        unsigned long long idx = first + __popc(m & ((1u << lane) - 1));
-        a.word_pos[idx] = (uint32_t)p;
-        a.word_sent[idx] = (uint32_t)s;
+  for (uint64_t g = (uint64_t)blockIdx.x * 8; g < a.n_sent; g += (uint64_t)gridDim.x * 8) {  // block-uniform
+    const uint64_t s = g + wid;
+    const bool live = s < a.n_sent;
+    uint64_t lo = 0, hi = 0;
+    unsigned long long cnt = 0;
+    if (live) {
+      lo = a.offs[s] - o0;
+      hi = a.offs[s + 1] - o0;
+      for (uint64_t p0 = lo; p0 < hi; p0 += 32) {
+        const uint64_t p = p0 + lane;
+        const bool ws = p < hi && word_start_at(a.bytes, p, lo, hi);
+        cnt += __popc(__ballot_sync(0xffffffffu, ws));
+      }
+      if (lane == 0) {
+        const uint64_t base = sent_base(lo, s), len = hi - lo;
+        a.n_ids[s] = (a.bos ? 1 : 0) + (a.eos ? 1 : 0);
+        if (a.bos) a.slots[base] = a.bos_id;
+        if (a.eos) a.slots[base + len + 2] = a.eos_id;
       }
     }
+    if (lane == 0) s_cnt[wid] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long tot = 0;
+      for (int i = 0; i < 8; i++) { unsigned long long c = s_cnt[i]; s_cnt[i] = tot; tot += c; }
+      s_base = tot ? atomicAdd(a.n_words, tot) : 0ull;
+    }
+    __syncthreads();
+    if (live && cnt) {
+      unsigned long long idx = s_base + s_cnt[wid];
+      for (uint64_t p0 = lo; p0 < hi; p0 += 32) {
+        const uint64_t p = p0 + lane;
+        const bool ws = p < hi && word_start_at(a.bytes, p, lo, hi);
+        const unsigned m = __ballot_sync(0xffffffffu, ws);
+        if (ws) {
+          const unsigned long long i = idx + __popc(m & ((1u << lane) - 1));
+          a.word_pos[i] = (uint32_t)p;
+          a.word_sent[i] = (uint32_t)s;
+        }
+        idx += __popc(m);
+      }
+    }
+    __syncthreads();  // s_cnt / s_base are reused by the next round
   }
 }
 
+// One thread per word.  Words of at most LOCAL_W - 1 bytes (nearly all) are merged in thread-private
+// local arrays (L1-resident) and only the final tokens go to the slot buffer; longer words work in
+// place in their private slots in global memory.
+template <bool DROPOUT>
 __global__ void __launch_bounds__(128) encode_words_kernel(EncArgs a, uint64_t n_words) {
+  constexpr uint32_t LOCAL_W = 40;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t o0 = a.offs[0];
+  const RuleTab rt = a.rt;
+  auto rank = [&](uint32_t x, uint32_t y, uint32_t *z) { return rule_rank(rt, x, y, z); };
   for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
     const uint64_t p0 = a.word_pos[w], s = a.word_sent[w];
     const uint64_t lo = a.offs[s] - o0, hi = a.offs[s + 1] - o0;
-    int32_t *t = a.slots + sent_base(lo, s) + 1 + (p0 - lo);  // k+1 private slots
-    uint32_t *r = a.ranks + sent_base(lo, s) + 1 + (p0 - lo);
-    uint32_t *aux = a.aux ? a.aux + 6 * (sent_base(lo, s) + 1 + (p0 - lo)) : nullptr;
-    uint32_t slots_owned;
-    const RuleTab rt = a.rt;
-    uint32_t n = encode_word(
-        a.bytes, p0, lo, hi, a.cp2id, a.space_id,
-        [&](uint32_t x, uint32_t y, uint32_t *z) { return rule_rank(rt, x, y, z); }, a.drop_thresh, a.seed,
-        a.first_sentence + s, t, r, aux, &slots_owned);
-    for (uint32_t i = 0; i < n; i++)
-      if ((uint32_t)t[i] & UNK_FLAG) t[i] = a.unk_id;
-    for (uint32_t i = n; i < slots_owned; i++) t[i] = EMPTY_SLOT;
+    const uint64_t slot0 = sent_base(lo, s) + 1 + (p0 - lo);
+    int32_t *t = a.slots + slot0;  // k+1 private slots
+    uint64_t q = p0;
+    uint32_t l;
+    while (q < hi && !space_at(a.bytes, q, hi, &l)) q++;
+    uint32_t owned = (uint32_t)(q - p0) + 1, n;
+    if (owned <= LOCAL_W) {
+      int32_t lt[LOCAL_W];
+      uint32_t lr[LOCAL_W];
+      uint32_t laux[DROPOUT ? 6 * LOCAL_W : 1];
+      n = encode_word(a.bytes, p0, lo, hi, a.cp2id, a.space_id, rank, DROPOUT ? a.drop_thresh : 0, a.seed,
+                      a.first_sentence + s, lt, lr, laux, &owned);
+      for (uint32_t i = 0; i < n; i++) t[i] = ((uint32_t)lt[i] & UNK_FLAG) ? a.unk_id : lt[i];
+    } else {
+      n = encode_word(a.bytes, p0, lo, hi, a.cp2id, a.space_id, rank, DROPOUT ? a.drop_thresh : 0, a.seed,
+                      a.first_sentence + s, t, a.ranks + slot0, DROPOUT ? a.aux + 6 * slot0 : nullptr, &owned);
+      for (uint32_t i = 0; i < n; i++)
+        if ((uint32_t)t[i] & UNK_FLAG) t[i] = a.unk_id;
+      for (uint32_t i = n; i < owned; i++) t[i] = EMPTY_SLOT;
+    }
     if (n) atomicAdd(a.n_ids + s, (unsigned long long)n);
   }
 }
@@ -194,6 +231,7 @@ int enc_device(yttm_enc *e, const uint8_t *d_bytes, const uint64_t *d_offs, uint
     uint64_t warps_needed = n_sent;
     uint64_t blocks = std::min<uint64_t>((warps_needed + 7) / 8, (uint64_t)c->n_sm * 8);
     ytc::timer_begin(c, "enc_find");
+    YT_CUDA(c, cudaMemsetAsync(a.slots, 0xff, n_slots * 4, c->stream));  // EMPTY_SLOT == -1
     find_words_kernel<<<(unsigned)std::max<uint64_t>(blocks, 1), 256, 0, c->stream>>>(a);
     ytc::timer_end(c, "enc_find");
     c->launches++;
@@ -204,7 +242,8 @@ int enc_device(yttm_enc *e, const uint8_t *d_bytes, const uint64_t *d_offs, uint
   if (n_words) {
     uint64_t blocks = std::min<uint64_t>((n_words + 127) / 128, (uint64_t)c->n_sm * 16);
     ytc::timer_begin(c, "enc_words");
-    encode_words_kernel<<<(unsigned)blocks, 128, 0, c->stream>>>(a, n_words);
+    if (a.drop_thresh) encode_words_kernel<true><<<(unsigned)blocks, 128, 0, c->stream>>>(a, n_words);
+    else encode_words_kernel<false><<<(unsigned)blocks, 128, 0, c->stream>>>(a, n_words);
     ytc::timer_end(c, "enc_words");
     c->launches++;
   }

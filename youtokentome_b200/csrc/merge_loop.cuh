@@ -1,0 +1,456 @@
+// merge_loop.cuh — phase 4 of training: the persistent merge loop (included by train.cu).
+//
+// Replaces the reference's main loop + worker_doing_merge + PriorityQueue
+// (bpe.cpp:1121-1282, 601-811, 149-314).  One cooperative kernel runs every merge iteration on
+// the device; per iteration:
+//   1. exact arg-max over the pair table under MergeCandidate::operator< (bpe.cpp:110-126)
+//   2. grid barrier; every block reduces the per-block winners redundantly (no second barrier)
+//   3. apply x y -> z: the packed words are organised in TILES (windows of `tile_tok` token
+//      slots, cut at word boundaries).  RESIDENT mode: block b keeps tile b in shared memory for
+//      the whole launch (the working set of deduplicated words fits the 148 x 227 KB of SMEM:
+//      no HBM/L2 token traffic inside the loop at all).  STREAMING mode (token buffer larger than
+//      the SMEM of the chip): tiles are staged into shared memory each iteration, coalesced,
+//      and modified words are written through to HBM.
+//      Inside a tile a lane tests one word (has_pair); words that hold the pair are rewritten by
+//      the whole warp in parallel (ballot/popc compaction, run-parity rule for x == y) and their
+//      pair multiset is re-counted (-old, +new) with one table update per lane.
+//   4. grid barrier.
+#pragma once
+
+struct LoopArgs {
+  uint32_t *tok;
+  const uint32_t *off;
+  const uint64_t *freq;
+  uint64_t n_words;
+  const uint2 *tile_desc;      // n_tiles + 1 entries (first word, its token offset); last = (n_words, n_slots)
+  uint32_t stream_tok_cap;     // STREAMING: token / word capacity of ONE of the two pipeline stages
+  uint32_t stream_word_cap;
+  uint32_t n_tiles;
+  uint32_t resident;           // 1: block b owns tile b and keeps it in shared memory
+  uint32_t smem_tok_cap;       // token capacity of the shared tile buffer
+  uint32_t smem_word_cap;      // word capacity of the shared tile buffer
+  PairTab tab;
+  YtLoopCtl *ctl;
+  unsigned long long *blockbest;  // 4 per block: count, prio, slot, (pad)
+  uint32_t *rules;                // 3 per merge
+  unsigned long long *rfreq;
+  uint32_t first_new_id;          // id of merge number 0
+  uint32_t max_total;             // stop when ctl->n_done reaches this
+  uint32_t max_iters;             // iterations allowed in this launch
+  uint32_t key_limit;             // leave for a rebuild above this table occupancy
+};
+
+struct Best { unsigned long long c, prio, slot; };
+__device__ __forceinline__ bool better(const Best &a, const Best &b) {  // a beats b
+  return a.c > b.c || (a.c == b.c && a.prio > b.prio);
+}
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ Best warp_best(Best v) {
+  for (int o = 16; o > 0; o >>= 1) {
+    Best w;
+    w.c = __shfl_xor_sync(0xffffffffu, v.c, o);
+    w.prio = __shfl_xor_sync(0xffffffffu, v.prio, o);
+    w.slot = __shfl_xor_sync(0xffffffffu, v.slot, o);
+    if (better(w, v)) v = w;
+  }
+  return v;
+}
+
+struct MergeOp { uint32_t x, y, z; unsigned long long key; };
+
+// Per-warp queue of pending table updates in shared memory: the updates of several rewritten
+// words are issued together, one per lane, so their L2 round trips overlap.
+constexpr int UQ_CAP = 64;
+struct WarpQueue {
+  unsigned long long *key;  // UQ_CAP entries of this warp
+  long long *delta;
+  uint32_t n;               // warp-uniform
+};
+__device__ __forceinline__ void uq_drain(WarpQueue &q, unsigned lane, const PairTab &tab) {
+  __syncwarp();
+  for (uint32_t i = lane; i < q.n; i += 32) pair_add(tab, q.key[i], q.delta[i]);
+  __syncwarp();
+  q.n = 0;
+}
+// every lane may contribute one update (has == true); direct == true bypasses the queue
+__device__ __forceinline__ void uq_push(WarpQueue &q, bool direct, bool has, unsigned long long key, long long delta,
+                                        unsigned lane, const PairTab &tab) {
+  if (direct) { if (has) pair_add(tab, key, delta); return; }
+  const unsigned m = __ballot_sync(0xffffffffu, has);
+  if (has) {
+    const uint32_t i = q.n + __popc(m & ((1u << lane) - 1u));
+    q.key[i] = key;
+    q.delta[i] = delta;
+  }
+  q.n += __popc(m);
+}
+
+// Run structure of <= 32 live tokens held one per lane (t == DEAD beyond the n live ones): every
+// run start owns floor(L/2) self pairs and one cross pair to the next run (for_each_pair()).
+struct RunInfo { bool start; uint32_t nxt, L, b; unsigned starts; };
+__device__ __forceinline__ RunInfo warp_runs(uint32_t t, uint32_t n, unsigned lane) {
+  RunInfo r;
+  const bool valid = lane < n;
+  uint32_t prev = __shfl_up_sync(0xffffffffu, t, 1);
+  r.start = valid && (lane == 0 || prev != t);
+  r.starts = __ballot_sync(0xffffffffu, r.start);
+  const unsigned above = lane == 31 ? 0u : r.starts & ~((2u << lane) - 1u);
+  r.nxt = above ? (uint32_t)__ffs(above) - 1u : n;
+  r.b = __shfl_sync(0xffffffffu, t, r.nxt & 31);
+  r.L = r.nxt - lane;
+  return r;
+}
+
+// One warp rewrites one word that holds (x,y): st = its `cap` token slots (shared or global
+// memory), gt = optional write-through copy in global memory.  Table updates: only the pairs
+// whose run is touched by a merge are sent (-old, +new); untouched runs cancel exactly.
+// Returns the number of merges.
+__device__ __forceinline__ uint32_t warp_apply_word(uint32_t *st, uint32_t cap, uint32_t *gt, long long f,
+                                                    const MergeOp &op, unsigned lane, const PairTab &tab,
+                                                    WarpQueue &q) {
+  if (cap > 32) {  // long word: scalar path on lane 0 (exact, slow)
+    uint32_t merges = 0;
+    if (lane == 0) {
+      for_each_pair(st, cap, [&](uint64_t key, uint64_t mult) {
+        if (key != op.key) pair_add(tab, key, -(long long)mult * f);
+      });
+      merges = rewrite_word(st, cap, op.x, op.y, op.z);
+      for_each_pair(st, cap, [&](uint64_t key, uint64_t mult) { pair_add(tab, key, (long long)mult * f); });
+    }
+    __syncwarp();
+    if (gt)
+      for (uint32_t i = lane; i < cap; i += 32) gt[i] = st[i];
+    return __shfl_sync(0xffffffffu, merges, 0);
+  }
+  const uint32_t t = lane < cap ? st[lane] : DEAD;
+  const bool valid = t != DEAD;
+  const uint32_t n = __popc(__ballot_sync(0xffffffffu, valid));  // live tokens form a prefix
+  const RunInfo ro = warp_runs(t, n, lane);
+  // greedy left-to-right matches
+  const uint32_t nx = __shfl_down_sync(0xffffffffu, t, 1);
+  bool m = valid && lane + 1 < n && t == op.x && nx == op.y;
+  if (op.x == op.y) {  // inside a run x^L only every second position starts a pair (bpe.cpp:654-690)
+    const unsigned upto = ro.starts & (lane == 31 ? 0xffffffffu : ((2u << lane) - 1u));
+    const uint32_t run_start = upto ? 31u - (uint32_t)__clz(upto) : 0u;
+    m = m && (((lane - run_start) & 1u) == 0u);
+  }
+  const unsigned mm = __ballot_sync(0xffffffffu, m);
+  const unsigned touched = mm | (mm << 1);                       // first and second token of every merged pair
+  const bool keep = valid && !((mm << 1) >> lane & 1u);
+  const unsigned km = __ballot_sync(0xffffffffu, keep);
+  const uint32_t newpos = __popc(km & ((1u << lane) - 1u));
+  const uint32_t n2 = __popc(km);
+  const uint32_t nv = m ? op.z : t;
+  // an old run [lane, nxt) (plus the first token of the next run) without a touched token is unchanged
+  const unsigned span_mask = (ro.nxt >= 31 ? 0xffffffffu : ((2u << ro.nxt) - 1u)) & ~((1u << lane) - 1u);
+  const bool old_changed = ro.start && (touched & span_mask) != 0u;
+  const unsigned unchanged_starts = __ballot_sync(0xffffffffu, ro.start && !old_changed);
+  __syncwarp();
+  if (keep) { st[newpos] = nv; if (gt) gt[newpos] = nv; }
+  if (valid && lane >= n2) { st[lane] = DEAD; if (gt) gt[lane] = DEAD; }
+  __syncwarp();
+  const uint32_t t2 = lane < n2 ? st[lane] : DEAD;
+  const RunInfo rn = warp_runs(t2, n2, lane);
+  // new lane p came from old lane src = (p+1)-th kept lane; its run is unchanged iff that old run was
+  const uint32_t src = lane < n2 ? __fns(km, 0, lane + 1) : 0u;
+  const bool new_changed = rn.start && !((unchanged_starts >> (src & 31)) & 1u);
+  // the four possible updates of this lane
+  const bool h0 = old_changed && ro.L >= 2 && pair_key(t, t) != op.key;
+  const bool h1 = old_changed && ro.nxt < n && pair_key(t, ro.b) != op.key;
+  const bool h2 = new_changed && rn.L >= 2;
+  const bool h3 = new_changed && rn.nxt < n2;
+  const uint32_t total = __popc(__ballot_sync(0xffffffffu, h0)) + __popc(__ballot_sync(0xffffffffu, h1)) +
+                         __popc(__ballot_sync(0xffffffffu, h2)) + __popc(__ballot_sync(0xffffffffu, h3));
+  const bool direct = total > UQ_CAP;
+  if (!direct && q.n + total > UQ_CAP) uq_drain(q, lane, tab);
+  uq_push(q, direct, h0, pair_key(t, t), -f * (long long)(ro.L >> 1), lane, tab);
+  uq_push(q, direct, h1, pair_key(t, ro.b), -f, lane, tab);
+  uq_push(q, direct, h2, pair_key(t2, t2), f * (long long)(rn.L >> 1), lane, tab);
+  uq_push(q, direct, h3, pair_key(t2, rn.b), f, lane, tab);
+  return n - n2;
+}
+
+// All words of one tile whose tokens sit in `stok` (offsets relative to the tile in `soff`).
+__device__ __forceinline__ unsigned long long process_tile(uint32_t *stok, const uint32_t *soff, uint32_t obase,
+                                                           uint32_t nw, uint32_t *gtok, const uint64_t *gfreq,
+                                                           const MergeOp &op, const PairTab &tab, WarpQueue &q) {
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  unsigned long long dead = 0;
+  for (uint32_t base = wid * 32; base < nw; base += nwarp * 32) {
+    const uint32_t w = base + lane;
+    uint32_t o = 0, cap = 0;
+    bool flag = false;
+    if (w < nw) {
+      o = soff[w] - obase;
+      cap = soff[w + 1] - obase - o;
+      flag = has_pair(stok + o, cap, op.x, op.y);
+    }
+    const long long fw = flag ? (long long)gfreq[w] : 0;  // all flagged lanes fetch their frequency at once
+    unsigned mask = __ballot_sync(0xffffffffu, flag);
+    while (mask) {
+      const int j = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const uint32_t oj = __shfl_sync(0xffffffffu, o, j), cj = __shfl_sync(0xffffffffu, cap, j);
+      const long long f = __shfl_sync(0xffffffffu, fw, j);
+      dead += warp_apply_word(stok + oj, cj, gtok ? gtok + oj : nullptr, f, op, lane, tab, q);
+    }
+  }
+  if (q.n) uq_drain(q, lane, tab);
+  return lane == 0 ? dead : 0ull;
+}
+
+// Oversized tile (a word longer than the shared buffer): thread per word straight on global memory.
+__device__ __forceinline__ unsigned long long process_tile_direct(uint32_t *tok, const uint32_t *off,
+                                                                  const uint64_t *freq, uint32_t w0, uint32_t w1,
+                                                                  const MergeOp &op, const PairTab &tab) {
+  unsigned long long dead = 0;
+  for (uint32_t w = w0 + threadIdx.x; w < w1; w += blockDim.x) {
+    uint32_t o = off[w], wcap = off[w + 1] - o;
+    uint32_t *t = tok + o;
+    if (!has_pair(t, wcap, op.x, op.y)) continue;
+    long long f = (long long)freq[w];
+    for_each_pair(t, wcap, [&](uint64_t key, uint64_t mult) {
+      if (key != op.key) pair_add(tab, key, -(long long)mult * f);
+    });
+    dead += rewrite_word(t, wcap, op.x, op.y, op.z);
+    for_each_pair(t, wcap, [&](uint64_t key, uint64_t mult) { pair_add(tab, key, (long long)mult * f); });
+  }
+  return dead;
+}
+
+// ---- TMA (bulk async copy) staging of a tile: global -> shared, completion on an mbarrier ----------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; !ok; spin++) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (spin > (1u << 28)) asm volatile("trap;");  // a lost transaction must not hang the box
+  }
+}
+// bytes of a 16-byte aligned window [lo & ~3, roundup(hi, 4)) over uint32 elements
+__device__ __forceinline__ uint32_t win_lo(uint32_t lo) { return lo & ~3u; }
+__device__ __forceinline__ uint32_t win_bytes(uint32_t lo, uint32_t hi) { return (((hi + 3u) & ~3u) - (lo & ~3u)) * 4u; }
+
+__device__ __forceinline__ void load_tile(const LoopArgs &a, uint32_t w0, uint32_t w1, uint32_t *stok, uint32_t *soff) {
+  const uint32_t o0 = a.off[w0], span = a.off[w1] - o0, nw = w1 - w0;  // resident mode: plain coalesced copy, once
+  for (uint32_t i = threadIdx.x; i <= nw; i += blockDim.x) soff[i] = a.off[w0 + i] - o0;
+  const uint32_t *src = a.tok + o0;
+  for (uint32_t i = threadIdx.x; i < span; i += blockDim.x) stok[i] = __ldcg(src + i);
+}
+
+extern __shared__ __align__(16) uint32_t yt_dyn_smem[];
+
+__global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ Best s_warp[32];
+  __shared__ Best s_best;
+  __shared__ unsigned long long s_dead;
+  // dynamic shared memory: [update queues: 32 warps x UQ_CAP x 16 B][tile tokens][tile offsets]
+  unsigned long long *uq_keys = reinterpret_cast<unsigned long long *>(yt_dyn_smem);
+  long long *uq_deltas = reinterpret_cast<long long *>(uq_keys + 32 * UQ_CAP);
+  uint32_t *stok = reinterpret_cast<uint32_t *>(uq_deltas + 32 * UQ_CAP);
+  uint32_t *soff = stok + a.smem_tok_cap;
+  // STREAMING carve of the same region: two stages of (tokens, offsets), each 16-byte aligned
+  __shared__ __align__(8) unsigned long long s_bar[2];
+  uint32_t *s_stage_tok[2], *s_stage_off[2];
+  s_stage_tok[0] = stok;
+  s_stage_off[0] = s_stage_tok[0] + a.stream_tok_cap;
+  s_stage_tok[1] = s_stage_off[0] + a.stream_word_cap;
+  s_stage_off[1] = s_stage_tok[1] + a.stream_tok_cap;
+  uint32_t stream_phase = 0;  // bit s = parity the next wait on stage s expects
+  if (!a.resident && threadIdx.x == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  WarpQueue uq;
+  uq.key = uq_keys + (threadIdx.x >> 5) * UQ_CAP;
+  uq.delta = uq_deltas + (threadIdx.x >> 5) * UQ_CAP;
+  uq.n = 0;
+  const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t gstride = (uint64_t)gridDim.x * blockDim.x;
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const uint64_t cap = a.tab.mask + 1;
+  const uint32_t n_done0 = a.ctl->n_done;
+
+  // resident mode: this block's tile moves into shared memory once
+  uint32_t rw0 = 0, rw1 = 0;
+  if (a.resident && blockIdx.x < a.n_tiles) {
+    rw0 = a.tile_desc[blockIdx.x].x;
+    rw1 = a.tile_desc[blockIdx.x + 1].x;
+    if (rw1 > rw0) load_tile(a, rw0, rw1, stok, soff);
+  }
+  __syncthreads();
+
+  for (uint32_t it = 0; it < a.max_iters; ++it) {
+    const uint32_t n_done = n_done0 + it;
+    if (n_done >= a.max_total) break;
+    // ---------------- arg-max over the table under MergeCandidate::operator< (bpe.cpp:110-126)
+    unsigned long long tq0 = gtid == 0 ? gtimer() : 0, tq1 = 0, tq2 = 0, tq3 = 0;
+    Best b{0, 0, 0};
+    for (uint64_t i = gtid; i < cap; i += gstride) {
+      unsigned long long c = __ldcg(a.tab.cnts + i);
+      if (c != 0 && c >= b.c) {
+        unsigned long long k = __ldcg(a.tab.keys + i);
+        Best cand{c, pair_prio((uint32_t)(k >> 32), (uint32_t)k), i};
+        if (better(cand, b)) b = cand;
+      }
+    }
+    b = warp_best(b);
+    if (lane == 0) s_warp[wid] = b;
+    __syncthreads();
+    if (wid == 0) {
+      Best v = lane < nwarp ? s_warp[lane] : Best{0, 0, 0};
+      v = warp_best(v);
+      if (lane == 0) {
+        a.blockbest[4 * blockIdx.x + 0] = v.c;
+        a.blockbest[4 * blockIdx.x + 1] = v.prio;
+        a.blockbest[4 * blockIdx.x + 2] = v.slot;
+      }
+    }
+    if (gtid == 0) tq1 = gtimer();
+    grid.sync();
+    if (gtid == 0) tq2 = gtimer();
+    if (wid == 0) {
+      Best v{0, 0, 0};
+      for (unsigned j = lane; j < gridDim.x; j += 32) {
+        Best w{__ldcg(a.blockbest + 4 * j), __ldcg(a.blockbest + 4 * j + 1), __ldcg(a.blockbest + 4 * j + 2)};
+        if (better(w, v)) v = w;
+      }
+      v = warp_best(v);
+      if (lane == 0) { s_best = v; s_dead = 0; }
+    }
+    __syncthreads();
+    const Best win = s_best;
+    if (win.c == 0) {  // no pair left: "merged only" (bpe.cpp:1137-1145)
+      if (gtid == 0) a.ctl->stop = 1;
+      break;
+    }
+    MergeOp op;
+    {  // (x, y) is recoverable from the priority word (pair_prio), no dependent table load needed
+      const uint32_t mx = 0xffffffffu - (uint32_t)(win.prio >> 32);
+      const uint32_t mn = 0x7fffffffu - (uint32_t)((win.prio & 0xffffffffull) >> 1);
+      op.x = (win.prio & 1ull) ? mx : mn;
+      op.y = (win.prio & 1ull) ? mn : mx;
+      op.key = pair_key(op.x, op.y);
+    }
+    op.z = a.first_new_id + n_done;
+    if (gtid == 0) {
+      a.rules[3 * n_done + 0] = op.x; a.rules[3 * n_done + 1] = op.y; a.rules[3 * n_done + 2] = op.z;
+      a.rfreq[n_done] = win.c;
+      a.tab.cnts[win.slot] = 0;  // every occurrence of (x,y) is merged below; no deltas are sent for it
+      a.ctl->n_done = n_done + 1;
+    }
+    // ---------------- apply x y -> z
+    unsigned long long dead = 0;
+    if (a.resident) {
+      if (rw1 > rw0) dead = process_tile(stok, soff, 0, rw1 - rw0, nullptr, a.freq + rw0, op, a.tab, uq);
+    } else {
+      // STREAMING: this block's tiles k = blockIdx.x, +gridDim.x, ... flow through a 2-stage
+      // TMA pipeline: thread 0 issues the bulk copies of tile i+1 (tokens + offsets, 16-byte
+      // aligned windows) while all warps process tile i out of shared memory.
+      const uint32_t my_tiles = a.n_tiles > blockIdx.x ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      auto staged = [&](uint2 d0, uint2 d1) {  // does this tile go through shared memory?
+        return d1.x > d0.x && win_bytes(d0.y, d1.y) <= a.stream_tok_cap * 4u &&
+               win_bytes(d0.x, d1.x + 1) <= a.stream_word_cap * 4u;
+      };
+      auto issue = [&](uint32_t i) {  // thread 0 only
+        const uint32_t k = blockIdx.x + i * gridDim.x;
+        const uint2 d0 = a.tile_desc[k], d1 = a.tile_desc[k + 1];
+        if (!staged(d0, d1)) return;
+        const uint32_t st = i & 1u;
+        const uint32_t bt = win_bytes(d0.y, d1.y), bo = win_bytes(d0.x, d1.x + 1);
+        mbar_expect_tx(&s_bar[st], bt + bo);
+        tma_bulk_g2s(s_stage_tok[st], a.tok + win_lo(d0.y), bt, &s_bar[st]);
+        tma_bulk_g2s(s_stage_off[st], a.off + win_lo(d0.x), bo, &s_bar[st]);
+      };
+      if (threadIdx.x == 0 && my_tiles) issue(0);
+      for (uint32_t i = 0; i < my_tiles; i++) {
+        const uint32_t k = blockIdx.x + i * gridDim.x;
+        const uint2 d0 = a.tile_desc[k], d1 = a.tile_desc[k + 1];
+        if (threadIdx.x == 0 && i + 1 < my_tiles) issue(i + 1);  // stage (i+1)&1 was released by the barrier below
+        if (d1.x > d0.x) {
+          if (staged(d0, d1)) {
+            const uint32_t st = i & 1u;
+            mbar_wait(&s_bar[st], (stream_phase >> st) & 1u);
+            stream_phase ^= 1u << st;
+            dead += process_tile(s_stage_tok[st] + (d0.y - win_lo(d0.y)), s_stage_off[st] + (d0.x - win_lo(d0.x)), d0.y,
+                                 d1.x - d0.x, a.tok + d0.y, a.freq + d0.x, op, a.tab, uq);
+          } else {
+            dead += process_tile_direct(a.tok, a.off, a.freq, d0.x, d1.x, op, a.tab);
+          }
+        }
+        __syncthreads();  // every warp is done with this stage before it is refilled
+      }
+      // write-through stores (generic proxy) must be ordered before the next iteration's bulk loads
+      asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    for (int o = 16; o > 0; o >>= 1) dead += __shfl_xor_sync(0xffffffffu, dead, o);
+    if (lane == 0 && dead) atomicAdd(&s_dead, dead);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_dead) atomicAdd(&a.ctl->dead, s_dead);
+    if (gtid == 0) tq3 = gtimer();
+    grid.sync();
+    if (gtid == 0) {
+      unsigned long long tq4 = gtimer();
+      a.ctl->t_phase[0] += tq1 - tq0; a.ctl->t_phase[1] += tq2 - tq1;
+      a.ctl->t_phase[2] += tq3 - tq2; a.ctl->t_phase[3] += tq4 - tq3;
+      a.ctl->iters += 1;
+    }
+    // ---------------- uniform exit checks (every block reads the same values)
+    uint32_t nk = __ldcg(&a.ctl->n_keys), ov = __ldcg(&a.ctl->overflow);
+    unsigned long long dd = __ldcg(&a.ctl->dead), sl = __ldcg(&a.ctl->slots);
+    if (ov || nk > a.key_limit) { if (gtid == 0) a.ctl->stop = 2; break; }
+    if (dd * 4 > sl && sl > 65536) { if (gtid == 0) a.ctl->stop = 3; break; }
+  }
+  // resident tiles go back to HBM on every exit path
+  __syncthreads();
+  if (a.resident && rw1 > rw0) {
+    const uint32_t o0 = a.off[rw0], span = a.off[rw1] - o0;
+    for (uint32_t i = threadIdx.x; i < span; i += blockDim.x) a.tok[o0 + i] = stok[i];
+  }
+}
+
+// ---- tile planning -----------------------------------------------------------------------------
+// tile k = words whose first token slot lies in [k*q, (k+1)*q); tile_desc[k] = (its first word,
+// that word's token offset); tile_desc[n_tiles] = (n_words, n_slots).
+__global__ void tile_desc_kernel(const uint32_t *__restrict__ off, uint64_t n_words, uint32_t q, uint32_t n_tiles,
+                                 uint2 *__restrict__ desc) {
+  uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  const uint32_t ow = off[w];
+  const uint32_t k1 = ow / q;
+  const int64_t k0 = w == 0 ? -1 : (int64_t)(off[w - 1] / q);
+  for (int64_t k = k0 + 1; k <= (int64_t)k1; k++) desc[k] = make_uint2((uint32_t)w, ow);
+  if (w + 1 == n_words)
+    for (uint32_t k = k1 + 1; k <= n_tiles; k++) desc[k] = make_uint2((uint32_t)n_words, off[n_words]);
+}
+__global__ void tile_stats_kernel(const uint2 *__restrict__ desc, uint32_t n_tiles,
+                                  uint32_t *out /* [0] max span, [1] max words */) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_tiles) return;
+  uint2 d0 = desc[k], d1 = desc[k + 1];
+  if (d1.x <= d0.x) return;
+  atomicMax(out, d1.y - d0.y);
+  atomicMax(out + 1, d1.x - d0.x);
+}

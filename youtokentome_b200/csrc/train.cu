@@ -17,6 +17,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -41,9 +42,13 @@ struct PairTab {
   uint32_t *overflow;
 };
 
+// A probe sequence longer than PROBE_LIMIT means the table is over-full: the update is dropped
+// and the overflow flag makes the host rebuild a larger table from the (always consistent) tokens.
+constexpr uint64_t PROBE_LIMIT = 512;
 __device__ __forceinline__ void pair_add(const PairTab &t, uint64_t key, long long delta) {
   uint64_t h = mix64(key) & t.mask;
-  for (uint64_t probe = 0; probe <= t.mask; probe++) {
+  const uint64_t limit = t.mask < PROBE_LIMIT ? t.mask : PROBE_LIMIT;
+  for (uint64_t probe = 0; probe <= limit; probe++) {
     unsigned long long k = __ldcg(t.keys + h);
     if (k == PK_EMPTY) {
       k = atomicCAS(t.keys + h, PK_EMPTY, (unsigned long long)key);
@@ -262,7 +267,10 @@ __global__ void __launch_bounds__(256) pair_hist_kernel(const uint32_t *__restri
                                                         const uint64_t *__restrict__ freq, uint64_t n_words,
                                                         PairTab tab) {
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint32_t key_limit = (uint32_t)((tab.mask + 1) / 2 < 0xffffffffull ? (tab.mask + 1) / 2 : 0xffffffffull);
   for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+    // a table that is already half full will be rejected by the host anyway: stop early
+    if (__ldcg(tab.overflow) || __ldcg(tab.n_keys) > key_limit) { atomicExch(tab.overflow, 1u); return; }
     uint32_t o = off[w], cap = off[w + 1] - o;
     if (cap < 2) continue;
     long long f = (long long)freq[w];
@@ -290,125 +298,7 @@ __global__ void pair_dump_kernel(const unsigned long long *__restrict__ keys, co
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// phase 4: the persistent merge loop
-// ------------------------------------------------------------------------------------------
-struct LoopArgs {
-  uint32_t *tok;
-  const uint32_t *off;
-  const uint64_t *freq;
-  uint64_t n_words;
-  PairTab tab;
-  YtLoopCtl *ctl;
-  unsigned long long *blockbest;  // 3 per block: count, prio, slot
-  uint32_t *rules;                // 3 per merge
-  unsigned long long *rfreq;
-  uint32_t first_new_id;          // id of merge number 0
-  uint32_t max_total;             // stop when ctl->n_done reaches this
-  uint32_t max_iters;             // iterations allowed in this launch
-  uint32_t key_limit;             // leave for a rebuild above this table occupancy
-};
-
-struct Best { unsigned long long c, prio, slot; };
-__device__ __forceinline__ bool better(const Best &a, const Best &b) {  // a beats b
-  return a.c > b.c || (a.c == b.c && a.prio > b.prio);
-}
-__device__ __forceinline__ Best warp_best(Best v) {
-  for (int o = 16; o > 0; o >>= 1) {
-    Best w;
-    w.c = __shfl_xor_sync(0xffffffffu, v.c, o);
-    w.prio = __shfl_xor_sync(0xffffffffu, v.prio, o);
-    w.slot = __shfl_xor_sync(0xffffffffu, v.slot, o);
-    if (better(w, v)) v = w;
-  }
-  return v;
-}
-
-__global__ void __launch_bounds__(512) merge_loop_kernel(LoopArgs a) {
-  cg::grid_group grid = cg::this_grid();
-  __shared__ Best s_warp[16];
-  __shared__ Best s_best;
-  __shared__ unsigned long long s_dead;
-  const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t gstride = (uint64_t)gridDim.x * blockDim.x;
-  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  const uint64_t cap = a.tab.mask + 1;
-  const uint32_t n_done0 = a.ctl->n_done;
-
-  for (uint32_t it = 0; it < a.max_iters; ++it) {
-    const uint32_t n_done = n_done0 + it;
-    if (n_done >= a.max_total) break;
-    // ---------------- arg-max over the table under MergeCandidate::operator< (bpe.cpp:110-126)
-    Best b{0, 0, 0};
-    for (uint64_t i = gtid; i < cap; i += gstride) {
-      unsigned long long c = __ldcg(a.tab.cnts + i);
-      if (c != 0 && c >= b.c) {
-        unsigned long long k = __ldcg(a.tab.keys + i);
-        Best cand{c, pair_prio((uint32_t)(k >> 32), (uint32_t)k), i};
-        if (better(cand, b)) b = cand;
-      }
-    }
-    b = warp_best(b);
-    if (lane == 0) s_warp[wid] = b;
-    __syncthreads();
-    if (wid == 0) {
-      Best v = lane < nwarp ? s_warp[lane] : Best{0, 0, 0};
-      v = warp_best(v);
-      if (lane == 0) {
-        a.blockbest[3 * blockIdx.x + 0] = v.c;
-        a.blockbest[3 * blockIdx.x + 1] = v.prio;
-        a.blockbest[3 * blockIdx.x + 2] = v.slot;
-      }
-    }
-    grid.sync();
-    if (wid == 0) {
-      Best v{0, 0, 0};
-      for (unsigned j = lane; j < gridDim.x; j += 32) {
-        Best w{__ldcg(a.blockbest + 3 * j), __ldcg(a.blockbest + 3 * j + 1), __ldcg(a.blockbest + 3 * j + 2)};
-        if (better(w, v)) v = w;
-      }
-      v = warp_best(v);
-      if (lane == 0) { s_best = v; s_dead = 0; }
-    }
-    __syncthreads();
-    const Best win = s_best;
-    if (win.c == 0) {  // no pair left: "merged only" (bpe.cpp:1137-1145)
-      if (gtid == 0) a.ctl->stop = 1;
-      break;
-    }
-    const unsigned long long wkey = __ldcg(a.tab.keys + win.slot);
-    const uint32_t x = (uint32_t)(wkey >> 32), y = (uint32_t)wkey, z = a.first_new_id + n_done;
-    if (gtid == 0) {
-      a.rules[3 * n_done + 0] = x; a.rules[3 * n_done + 1] = y; a.rules[3 * n_done + 2] = z;
-      a.rfreq[n_done] = win.c;
-      a.tab.cnts[win.slot] = 0;  // every occurrence of (x,y) is merged below; no deltas are sent for it
-      a.ctl->n_done = n_done + 1;
-    }
-    // ---------------- apply x y -> z to every word that holds it; patch the table
-    unsigned long long dead = 0;
-    for (uint64_t w = gtid; w < a.n_words; w += gstride) {
-      uint32_t o = a.off[w], wcap = a.off[w + 1] - o;
-      uint32_t *t = a.tok + o;
-      if (!has_pair(t, wcap, x, y)) continue;
-      long long f = (long long)a.freq[w];
-      for_each_pair(t, wcap, [&](uint64_t key, uint64_t mult) {
-        if (key != wkey) pair_add(a.tab, key, -(long long)mult * f);
-      });
-      dead += rewrite_word(t, wcap, x, y, z);
-      for_each_pair(t, wcap, [&](uint64_t key, uint64_t mult) { pair_add(a.tab, key, (long long)mult * f); });
-    }
-    for (int o = 16; o > 0; o >>= 1) dead += __shfl_xor_sync(0xffffffffu, dead, o);
-    if (lane == 0 && dead) atomicAdd(&s_dead, dead);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_dead) atomicAdd(&a.ctl->dead, s_dead);
-    grid.sync();
-    // ---------------- uniform exit checks (every block reads the same values)
-    uint32_t nk = __ldcg(&a.ctl->n_keys), ov = __ldcg(&a.ctl->overflow);
-    unsigned long long dd = __ldcg(&a.ctl->dead), sl = __ldcg(&a.ctl->slots);
-    if (ov || nk > a.key_limit) { if (gtid == 0) a.ctl->stop = 2; break; }
-    if (dd * 4 > sl && sl > 65536) { if (gtid == 0) a.ctl->stop = 3; break; }
-  }
-}
+#include "merge_loop.cuh"
 
 // ------------------------------------------------------------------------------------------
 // compaction of the packed words: drop tombstones and words with fewer than 2 live tokens
@@ -551,6 +441,49 @@ int compact_words(yttm_ctx *c) {
   return 0;
 }
 
+// Decide how the merge loop sees the packed words: RESIDENT (one tile per block, kept in shared
+// memory for the whole launch) when every tile fits, else STREAMING tiles of `q` token slots.
+int plan_tiles(yttm_ctx *c, LoopArgs *a) {
+  const uint32_t *off = c->off[c->cur].as<uint32_t>();
+  a->smem_tok_cap = c->loop_tok_cap;
+  a->smem_word_cap = c->loop_word_cap;
+  a->resident = 0;
+  a->n_tiles = 0;
+  a->tile_desc = nullptr;
+  a->stream_tok_cap = c->loop_stream_tok_cap;
+  a->stream_word_cap = c->loop_stream_word_cap;
+  c->loop_resident = 0;
+  if (c->n_words == 0 || c->n_slots == 0) return 0;
+  YT_CUDA(c, c->counters.reserve(64));
+  uint32_t *d_stats = reinterpret_cast<uint32_t *>(c->counters.as<unsigned long long>() + 7);
+  const bool force_stream = std::getenv("YTTM_FORCE_STREAM") != nullptr;
+  uint32_t stream_q = c->loop_stream_q;
+  if (const char *e = std::getenv("YTTM_STREAM_Q")) stream_q = (uint32_t)std::max(1, std::atoi(e));
+  for (int pass = force_stream ? 1 : 0; pass < 2; pass++) {
+    uint64_t q = pass == 0 ? (c->n_slots + c->loop_blocks - 1) / c->loop_blocks : stream_q;
+    if (q == 0) q = 1;
+    uint64_t n_tiles = (c->n_slots + q - 1) / q;
+    YT_CUDA(c, c->tiles.reserve((n_tiles + 2) * 8));
+    unsigned nb = (unsigned)((c->n_words + 255) / 256);
+    tile_desc_kernel<<<nb, 256, 0, c->stream>>>(off, c->n_words, (uint32_t)q, (uint32_t)n_tiles,
+                                                 c->tiles.as<uint2>());
+    c->launches++;
+    a->tile_desc = c->tiles.as<uint2>();
+    a->n_tiles = (uint32_t)n_tiles;
+    if (pass == 1) break;
+    YT_CUDA(c, cudaMemsetAsync(d_stats, 0, 8, c->stream));
+    tile_stats_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, c->stream>>>(c->tiles.as<uint2>(),
+                                                                                  (uint32_t)n_tiles, d_stats);
+    c->launches++;
+    uint32_t h[2];
+    YT_CUDA(c, cudaMemcpyAsync(h, d_stats, 8, cudaMemcpyDeviceToHost, c->stream));
+    YT_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (h[0] <= c->loop_tok_cap && h[1] <= c->loop_word_cap) { a->resident = 1; c->loop_resident = 1; break; }
+  }
+  YT_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
 }  // namespace
 
 thread_local std::string g_yttm_create_error;
@@ -601,7 +534,7 @@ void yttm_ctx_destroy(yttm_ctx *c) {
   cudaStreamSynchronize(c->stream);
   ytc::DevBuf *bufs[] = {&c->text_buf, &c->hist, &c->cp2id, &c->wkey, &c->wcnt, &c->wpos, &c->wfreq, &c->wlen,
                          &c->scan_tmp, &c->counters, &c->tok[0], &c->tok[1], &c->off[0], &c->off[1], &c->freq[0],
-                         &c->freq[1], &c->pkey, &c->pcnt, &c->scratch_key, &c->scratch_cnt, &c->ctl, &c->blockbest,
+                         &c->freq[1], &c->pkey, &c->pcnt, &c->scratch_key, &c->scratch_cnt, &c->ctl, &c->blockbest, &c->tiles,
                          &c->d_rules, &c->d_rfreq};
   for (auto *b : bufs) b->release();
   for (auto &kv : c->timers) { if (kv.second.a) cudaEventDestroy(kv.second.a); if (kv.second.b) cudaEventDestroy(kv.second.b); }
@@ -611,7 +544,16 @@ void yttm_ctx_destroy(yttm_ctx *c) {
 
 const char *yttm_last_error(const yttm_ctx *c) { return c ? c->err.c_str() : g_yttm_create_error.c_str(); }
 
-double yttm_stage_ms(const yttm_ctx *c, const char *stage) { return ytc::timer_ms(const_cast<yttm_ctx *>(c), stage); }
+double yttm_stage_ms(const yttm_ctx *c, const char *stage) {
+  static const char *ph[] = {"loop_argmax", "loop_barrier1", "loop_apply", "loop_barrier2"};
+  for (int i = 0; i < 4; i++)
+    if (!std::strcmp(stage, ph[i])) return c->loop_phase_ms[i];
+  if (!std::strcmp(stage, "loop_iters")) return (double)c->loop_iters;
+  if (!std::strcmp(stage, "loop_launches")) return (double)c->loop_relaunches;
+  if (!std::strcmp(stage, "table_capacity")) return (double)c->pcap;
+  if (!std::strcmp(stage, "loop_resident")) return (double)c->loop_resident;
+  return ytc::timer_ms(const_cast<yttm_ctx *>(c), stage);
+}
 uint64_t yttm_launch_count(const yttm_ctx *c) { return c->launches; }
 
 int yttm_train_load_corpus(yttm_ctx *c, const char *bytes, uint64_t n, int on_device) {
@@ -698,7 +640,9 @@ int yttm_train_set_alphabet(yttm_ctx *c, const uint32_t *cps, const uint32_t *id
 
 static int finish_build(yttm_ctx *c, yttm_train_stats *stats) {
   ytc::timer_begin(c, "pair_hist");
-  int rc = rebuild_pair_table(c, std::max<uint64_t>(c->n_slots / 2, 1u << 16));
+  // start small and let rebuild_pair_table grow to load <= 1/4: the arg-max sweeps the whole table
+  // every merge, so a tight table is worth a few extra histogram launches here
+  int rc = rebuild_pair_table(c, 1u << 16);
   ytc::timer_end(c, "pair_hist");
   if (rc) return rc;
   YtLoopCtl *ctl = c->ctl.as<YtLoopCtl>();
@@ -903,26 +847,51 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
   if (!c->pcap) YT_FAIL(c, "yttm_train_run: yttm_train_build has not run");
   *n_done_out = 0;
   if (max_merges == 0) return 0;
-  // launch geometry of the cooperative kernel: co-resident blocks only
+  // launch geometry of the cooperative kernel: one 1024-thread block per SM, all co-resident,
+  // with (almost) all of the SM's shared memory as the tile buffer
   if (!c->loop_blocks) {
-    int threads = 512, per_sm = 0;
-    YT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_loop_kernel, threads, 0));
+    int optin = 0;
+    YT_CUDA(c, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    int dyn = optin - 2048;  // static shared memory of the kernel + margin
+    if (dyn < 64 * 1024) YT_FAIL(c, "merge_loop_kernel: not enough shared memory per block");
+    c->loop_smem = dyn;
+    const int tile_bytes = dyn - 32 * UQ_CAP * 16;                           // minus the per-warp update queues
+    c->loop_word_cap = (uint32_t)(tile_bytes / 4 / 4 - 1);                  // 1/4 of the words for offsets
+    c->loop_tok_cap = (uint32_t)(tile_bytes / 4 - (c->loop_word_cap + 1)); // the rest for token slots
+    // STREAMING: two stages; a stage holds a window of q slots plus the overhang of its last word
+    // (words of up to q/4 slots stay on the shared-memory path) and at most q/2 + 1 offsets
+    {
+      const uint32_t per_stage = (uint32_t)(tile_bytes / 2 / 4) & ~3u;  // uint32 per stage
+      // tokens: q + q/4 + 8, offsets: q/2 + 16  ->  q * 1.75 + 24 <= per_stage
+      uint32_t q = (uint32_t)((per_stage - 24) / 1.75);
+      q &= ~15u;
+      c->loop_stream_q = q;
+      c->loop_stream_word_cap = (q / 2 + 16) & ~3u;
+      c->loop_stream_tok_cap = (per_stage - c->loop_stream_word_cap) & ~3u;
+    }
+    YT_CUDA(c, cudaFuncSetAttribute(merge_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    int threads = 1024, per_sm = 0;
+    if (const char *e = std::getenv("YTTM_LOOP_THREADS")) threads = std::atoi(e);
+    YT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_loop_kernel, threads, dyn));
     if (per_sm < 1) YT_FAIL(c, "merge_loop_kernel does not fit on an SM");
     c->loop_threads = threads;
-    c->loop_blocks = c->n_sm * std::min(per_sm, 2);
+    c->loop_blocks = c->n_sm;
   }
-  YT_CUDA(c, c->blockbest.reserve((size_t)c->loop_blocks * 3 * 8));
+  YT_CUDA(c, c->blockbest.reserve((size_t)c->loop_blocks * 4 * 8));
   YT_CUDA(c, c->d_rules.reserve((size_t)max_merges * 12 + 16));
   YT_CUDA(c, c->d_rfreq.reserve((size_t)max_merges * 8 + 16));
   YtLoopCtl *ctl = c->ctl.as<YtLoopCtl>();
   YtLoopCtl h{};
   YT_CUDA(c, cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   YT_CUDA(c, cudaStreamSynchronize(c->stream));
-  h.n_done = 0; h.stop = 0;
+  h.n_done = 0; h.stop = 0; h.iters = 0;
+  for (int i = 0; i < 4; i++) h.t_phase[i] = 0;
   YT_CUDA(c, cudaMemcpyAsync(ctl, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+  c->loop_relaunches = 0;
   ytc::timer_begin(c, "merge_loop");
   while (h.n_done < max_merges && h.stop != 1) {
     LoopArgs a;
+    if (plan_tiles(c, &a)) return 1;
     a.tok = c->tok[c->cur].as<uint32_t>();
     a.off = c->off[c->cur].as<uint32_t>();
     a.freq = c->freq[c->cur].as<uint64_t>();
@@ -938,18 +907,18 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
     a.key_limit = (uint32_t)std::min<uint64_t>(c->pcap / 2, 0xfffffff0ull);
     void *args[] = {&a};
     YT_CUDA(c, cudaLaunchCooperativeKernel((void *)merge_loop_kernel, dim3(c->loop_blocks), dim3(c->loop_threads), args,
-                                           0, c->stream));
+                                           (size_t)c->loop_smem, c->stream));
     c->launches++;
     YT_CUDA(c, cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     YT_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (h.overflow) YT_FAIL(c, "pair table overflow inside the merge loop");
+    c->loop_relaunches++;
     if (h.stop == 1 || h.n_done >= max_merges) break;
     // stop == 3: compaction wanted; stop == 2: table wants a rebuild
-    uint32_t why = h.stop;
+    uint32_t why = h.overflow ? 2u : h.stop;  // an overflowed table lost updates: rebuild it from the tokens
     if (compact_words(c)) return 1;
     if (why == 2) {
       uint32_t keep_done = h.n_done;
-      if (rebuild_pair_table(c, std::max<uint64_t>(c->pcap, 1u << 16))) return 1;
+      if (rebuild_pair_table(c, std::max<uint64_t>(h.overflow ? c->pcap * 4 : c->pcap, 1u << 16))) return 1;
       h.n_done = keep_done;
       YT_CUDA(c, cudaMemcpyAsync(&h.n_keys, &ctl->n_keys, 8, cudaMemcpyDeviceToHost, c->stream));
       YT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -958,6 +927,8 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
     YT_CUDA(c, cudaMemcpyAsync(ctl, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
   }
   ytc::timer_end(c, "merge_loop");
+  for (int i = 0; i < 4; i++) c->loop_phase_ms[i] = (double)h.t_phase[i] * 1e-6;
+  c->loop_iters = h.iters;
   *n_done_out = h.n_done;
   if (h.n_done) {
     YT_CUDA(c, cudaMemcpyAsync(rules_xyz, c->d_rules.p, (size_t)h.n_done * 12, cudaMemcpyDeviceToHost, c->stream));
