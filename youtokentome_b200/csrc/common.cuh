@@ -82,8 +82,8 @@ struct yttm_ctx {
   uint64_t pcap = 0;
 
   // ---- merge loop
-  ytc::DevBuf ctl, blockbest, d_rules, d_rfreq, tiles;
-  int loop_smem = 0, loop_resident = 0;
+  ytc::DevBuf ctl, blockbest, d_rules, d_rfreq, tiles, defer;
+  int loop_smem = 0, loop_resident = 0, loop_stages = 2;
   uint32_t loop_tok_cap = 0, loop_word_cap = 0, loop_stream_q = 0, loop_stream_tok_cap = 0, loop_stream_word_cap = 0;
   int loop_blocks = 0, loop_threads = 0;
   double loop_phase_ms[4] = {0, 0, 0, 0};

@@ -25,6 +25,10 @@ struct LoopArgs {
   const uint2 *tile_desc;      // n_tiles + 1 entries (first word, its token offset); last = (n_words, n_slots)
   uint32_t stream_tok_cap;     // STREAMING: token / word capacity of ONE of the two pipeline stages
   uint32_t stream_word_cap;
+  uint32_t n_stage;            // STREAMING: pipeline depth
+  uint4 *defer;                // STREAMING: per-block lists of words to rewrite after the tile scan
+  uint32_t defer_cap;          // entries per block
+  uint32_t debug;
   uint32_t n_tiles;
   uint32_t resident;           // 1: block b owns tile b and keeps it in shared memory
   uint32_t smem_tok_cap;       // token capacity of the shared tile buffer
@@ -65,6 +69,8 @@ struct MergeOp { uint32_t x, y, z; unsigned long long key; };
 // Per-warp queue of pending table updates in shared memory: the updates of several rewritten
 // words are issued together, one per lane, so their L2 round trips overlap.
 constexpr int UQ_CAP = 64;
+constexpr int MAX_STAGES = 16;
+constexpr int CLAIM_WORDS = 1024;  // claim bitmap: up to 32768 words per shared-memory tile
 struct WarpQueue {
   unsigned long long *key;  // UQ_CAP entries of this warp
   long long *delta;
@@ -174,33 +180,59 @@ __device__ __forceinline__ uint32_t warp_apply_word(uint32_t *st, uint32_t cap, 
   return n - n2;
 }
 
-// All words of one tile whose tokens sit in `stok` (offsets relative to the tile in `soff`).
+// One tile whose token slots sit in shared memory (`span` slots at stok, word w at
+// [soff[w] - obase, soff[w+1] - obase)).  The scan is TOKEN-parallel: a lane compares slot i and
+// i+1 with (x, y) — consecutive lanes read consecutive words of shared memory, every lane does
+// the same work whatever the word lengths.  A hit cannot straddle two words: the first token
+// of every word is (derived from) the "▁" token, which only ever occurs at position 0, so y —
+// the second element of an in-word pair — is never a word-initial token; tail padding (DEAD)
+// matches nothing.  Each hit is mapped to its word (binary search in the offsets), the word is
+// claimed once through a bitmap, and claimed words are rewritten by the whole warp.
 __device__ __forceinline__ unsigned long long process_tile(uint32_t *stok, const uint32_t *soff, uint32_t obase,
-                                                           uint32_t nw, uint32_t *gtok, const uint64_t *gfreq,
-                                                           const MergeOp &op, const PairTab &tab, WarpQueue &q) {
+                                                           uint32_t nw, uint32_t span, uint32_t *claim,
+                                                           uint32_t *gtok, const uint64_t *gfreq, const MergeOp &op,
+                                                           const PairTab &tab, WarpQueue &q, uint4 *defer = nullptr,
+                                                           uint32_t *defer_n = nullptr, uint32_t defer_cap = 0,
+                                                           uint32_t w_abs0 = 0) {
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   unsigned long long dead = 0;
-  for (uint32_t base = wid * 32; base < nw; base += nwarp * 32) {
-    const uint32_t w = base + lane;
-    uint32_t o = 0, cap = 0;
-    bool flag = false;
-    if (w < nw) {
+  for (uint32_t base = wid * 32; base < span; base += nwarp * 32) {
+    const uint32_t i = base + lane;
+    const bool hit = i + 1 < span && stok[i] == op.x && stok[i + 1] == op.y;
+    if (!__ballot_sync(0xffffffffu, hit)) continue;
+    uint32_t w = 0, o = 0, cap = 0;
+    bool own = false;
+    if (hit) {
+      uint32_t lo = 0, hi = nw;  // largest w with soff[w] - obase <= i
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (soff[mid] - obase <= i) lo = mid; else hi = mid;
+      }
+      w = lo;
       o = soff[w] - obase;
       cap = soff[w + 1] - obase - o;
-      flag = has_pair(stok + o, cap, op.x, op.y);
+      own = !((atomicOr(&claim[w >> 5], 1u << (w & 31)) >> (w & 31)) & 1u);
+      if (own && defer) {  // STREAMING: rewrite later, out of the TMA pipeline's way (see merge_loop_kernel)
+        const uint32_t slot = atomicAdd(defer_n, 1u);
+        if (slot < defer_cap) {
+          defer[slot] = make_uint4(w_abs0 + w, obase + o, cap, 0u);
+          own = false;
+        }
+      }
     }
-    const long long fw = flag ? (long long)gfreq[w] : 0;  // all flagged lanes fetch their frequency at once
-    unsigned mask = __ballot_sync(0xffffffffu, flag);
+    const long long fw = own ? (long long)gfreq[w] : 0;  // owners fetch their word's frequency together
+    unsigned mask = __ballot_sync(0xffffffffu, own);
     while (mask) {
       const int j = __ffs(mask) - 1;
       mask &= mask - 1;
       const uint32_t oj = __shfl_sync(0xffffffffu, o, j), cj = __shfl_sync(0xffffffffu, cap, j);
+      const uint32_t wj = __shfl_sync(0xffffffffu, w, j);
       const long long f = __shfl_sync(0xffffffffu, fw, j);
       dead += warp_apply_word(stok + oj, cj, gtok ? gtok + oj : nullptr, f, op, lane, tab, q);
+      if (lane == 0 && !defer) atomicAnd(&claim[wj >> 5], ~(1u << (wj & 31)));  // bitmap all zero between tiles
     }
   }
-  if (q.n) uq_drain(q, lane, tab);
-  return lane == 0 ? dead : 0ull;
+  return lane == 0 ? dead : 0ull;  // pending table updates stay queued across tiles (drained by the caller)
 }
 
 // Oversized tile (a word longer than the shared buffer): thread per word straight on global memory.
@@ -236,6 +268,9 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
   uint32_t ok = 0;
   for (uint32_t spin = 0; !ok; spin++) {
@@ -244,7 +279,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
-    if (spin > (1u << 28)) asm volatile("trap;");  // a lost transaction must not hang the box
+    if (spin > (1u << 24)) {  // a lost transaction must not hang the box
+      if ((threadIdx.x & 31) == 0)
+        printf("yttm mbar_wait stuck: block %d thread %d bar %u parity %u\n", (int)blockIdx.x, (int)threadIdx.x,
+               smem_u32(bar), parity);
+      asm volatile("trap;");
+    }
   }
 }
 // bytes of a 16-byte aligned window [lo & ~3, roundup(hi, 4)) over uint32 elements
@@ -265,24 +305,25 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
   __shared__ Best s_warp[32];
   __shared__ Best s_best;
   __shared__ unsigned long long s_dead;
+  __shared__ uint32_t s_defer_n, s_direct;
   // dynamic shared memory: [update queues: 32 warps x UQ_CAP x 16 B][tile tokens][tile offsets]
   unsigned long long *uq_keys = reinterpret_cast<unsigned long long *>(yt_dyn_smem);
   long long *uq_deltas = reinterpret_cast<long long *>(uq_keys + 32 * UQ_CAP);
-  uint32_t *stok = reinterpret_cast<uint32_t *>(uq_deltas + 32 * UQ_CAP);
+  uint32_t *s_claim = reinterpret_cast<uint32_t *>(uq_deltas + 32 * UQ_CAP);  // 2 bitmaps of CLAIM_WORDS x 32 flags
+  uint32_t *stok = s_claim + 2 * CLAIM_WORDS;
   uint32_t *soff = stok + a.smem_tok_cap;
-  // STREAMING carve of the same region: two stages of (tokens, offsets), each 16-byte aligned
-  __shared__ __align__(8) unsigned long long s_bar[2];
-  uint32_t *s_stage_tok[2], *s_stage_off[2];
-  s_stage_tok[0] = stok;
-  s_stage_off[0] = s_stage_tok[0] + a.stream_tok_cap;
-  s_stage_tok[1] = s_stage_off[0] + a.stream_word_cap;
-  s_stage_off[1] = s_stage_tok[1] + a.stream_tok_cap;
-  uint32_t stream_phase = 0;  // bit s = parity the next wait on stage s expects
+  for (uint32_t i = threadIdx.x; i < 2 * CLAIM_WORDS; i += blockDim.x) s_claim[i] = 0;
+  // STREAMING carve of the same region: NSTAGE stages of (tokens, offsets), each 16-byte aligned;
+  // full[s]: TMA bytes landed (tx count), empty[s]: all consumer warps are done with stage s
+  __shared__ __align__(8) unsigned long long s_full[MAX_STAGES], s_empty[MAX_STAGES];
+  const uint32_t n_stage = a.n_stage;
+  const uint32_t stage_words = a.stream_tok_cap + a.stream_word_cap;  // uint32 per stage
   if (!a.resident && threadIdx.x == 0) {
-    mbar_init(&s_bar[0], 1);
-    mbar_init(&s_bar[1], 1);
+    for (uint32_t st = 0; st < n_stage; st++) { mbar_init(&s_full[st], 1); mbar_init(&s_empty[st], (blockDim.x >> 5) - 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // STREAMING pipeline state of this thread (producer lane: empty-phase bits, consumers: full-phase bits)
+  uint32_t pipe_used = 0, pipe_phase = 0, pipe_stage = 0;
   WarpQueue uq;
   uq.key = uq_keys + (threadIdx.x >> 5) * UQ_CAP;
   uq.delta = uq_deltas + (threadIdx.x >> 5) * UQ_CAP;
@@ -331,14 +372,23 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
     if (gtid == 0) tq1 = gtimer();
     grid.sync();
     if (gtid == 0) tq2 = gtimer();
-    if (wid == 0) {
+    {  // every block reduces the per-block winners redundantly: one entry per thread, one round trip
       Best v{0, 0, 0};
-      for (unsigned j = lane; j < gridDim.x; j += 32) {
+      for (unsigned j = threadIdx.x; j < gridDim.x; j += blockDim.x) {
         Best w{__ldcg(a.blockbest + 4 * j), __ldcg(a.blockbest + 4 * j + 1), __ldcg(a.blockbest + 4 * j + 2)};
         if (better(w, v)) v = w;
       }
-      v = warp_best(v);
-      if (lane == 0) { s_best = v; s_dead = 0; }
+      const unsigned used_warps = (min(gridDim.x, blockDim.x) + 31) >> 5;
+      if (wid < used_warps) {
+        v = warp_best(v);
+        if (lane == 0) s_warp[wid] = v;
+      }
+      __syncthreads();
+      if (wid == 0) {
+        Best u = lane < used_warps ? s_warp[lane] : Best{0, 0, 0};
+        u = warp_best(u);
+        if (lane == 0) { s_best = u; s_dead = 0; }
+      }
     }
     __syncthreads();
     const Best win = s_best;
@@ -360,51 +410,62 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
       a.rfreq[n_done] = win.c;
       a.tab.cnts[win.slot] = 0;  // every occurrence of (x,y) is merged below; no deltas are sent for it
       a.ctl->n_done = n_done + 1;
+      if (a.debug) printf("IT %u x=%u y=%u z=%u c=%llu resident=%u\n", n_done, op.x, op.y, op.z, win.c, a.resident);
     }
     // ---------------- apply x y -> z
     unsigned long long dead = 0;
     if (a.resident) {
-      if (rw1 > rw0) dead = process_tile(stok, soff, 0, rw1 - rw0, nullptr, a.freq + rw0, op, a.tab, uq);
+      if (rw1 > rw0) dead = process_tile(stok, soff, 0, rw1 - rw0, soff[rw1 - rw0], s_claim, nullptr, a.freq + rw0, op, a.tab, uq);
     } else {
-      // STREAMING: this block's tiles k = blockIdx.x, +gridDim.x, ... flow through a 2-stage
-      // TMA pipeline: thread 0 issues the bulk copies of tile i+1 (tokens + offsets, 16-byte
-      // aligned windows) while all warps process tile i out of shared memory.
+      // STREAMING: this block's tiles k = blockIdx.x, +gridDim.x, ... flow through a 2-stage TMA
+      // pipeline: thread 0 issues the bulk copies of tile i+1 (tokens + offsets, 16-byte aligned
+      // windows, completion on an mbarrier) while all warps scan tile i out of shared memory;
+      // rewritten words are written through to HBM.
       const uint32_t my_tiles = a.n_tiles > blockIdx.x ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
       auto staged = [&](uint2 d0, uint2 d1) {  // does this tile go through shared memory?
         return d1.x > d0.x && win_bytes(d0.y, d1.y) <= a.stream_tok_cap * 4u &&
                win_bytes(d0.x, d1.x + 1) <= a.stream_word_cap * 4u;
       };
-      auto issue = [&](uint32_t i) {  // thread 0 only
-        const uint32_t k = blockIdx.x + i * gridDim.x;
-        const uint2 d0 = a.tile_desc[k], d1 = a.tile_desc[k + 1];
+      auto issue = [&](uint32_t i, uint2 d0, uint2 d1) {  // thread 0 only
         if (!staged(d0, d1)) return;
         const uint32_t st = i & 1u;
+        uint32_t *dst = stok + st * stage_words;
         const uint32_t bt = win_bytes(d0.y, d1.y), bo = win_bytes(d0.x, d1.x + 1);
-        mbar_expect_tx(&s_bar[st], bt + bo);
-        tma_bulk_g2s(s_stage_tok[st], a.tok + win_lo(d0.y), bt, &s_bar[st]);
-        tma_bulk_g2s(s_stage_off[st], a.off + win_lo(d0.x), bo, &s_bar[st]);
+        mbar_expect_tx(&s_full[st], bt + bo);
+        tma_bulk_g2s(dst, a.tok + win_lo(d0.y), bt, &s_full[st]);
+        tma_bulk_g2s(dst + a.stream_tok_cap, a.off + win_lo(d0.x), bo, &s_full[st]);
       };
-      if (threadIdx.x == 0 && my_tiles) issue(0);
+      // tile descriptors are fetched two tiles ahead so neither the issue nor the wait sees L2 latency
+      const uint32_t G = gridDim.x, k0 = blockIdx.x;
+      uint2 c0 = make_uint2(0, 0), c1 = c0, n0 = c0, n1 = c0;
+      if (my_tiles) { c0 = a.tile_desc[k0]; c1 = a.tile_desc[k0 + 1]; }
+      if (my_tiles > 1) { n0 = a.tile_desc[k0 + G]; n1 = a.tile_desc[k0 + G + 1]; }
+      if (threadIdx.x == 0 && my_tiles) issue(0, c0, c1);
       for (uint32_t i = 0; i < my_tiles; i++) {
-        const uint32_t k = blockIdx.x + i * gridDim.x;
-        const uint2 d0 = a.tile_desc[k], d1 = a.tile_desc[k + 1];
-        if (threadIdx.x == 0 && i + 1 < my_tiles) issue(i + 1);  // stage (i+1)&1 was released by the barrier below
+        uint2 nn0 = make_uint2(0, 0), nn1 = nn0;
+        if (i + 2 < my_tiles) { nn0 = a.tile_desc[k0 + (i + 2) * G]; nn1 = a.tile_desc[k0 + (i + 2) * G + 1]; }
+        if (threadIdx.x == 0 && i + 1 < my_tiles) issue(i + 1, n0, n1);  // its stage was released by the barrier below
+        const uint2 d0 = c0, d1 = c1;
         if (d1.x > d0.x) {
           if (staged(d0, d1)) {
             const uint32_t st = i & 1u;
-            mbar_wait(&s_bar[st], (stream_phase >> st) & 1u);
-            stream_phase ^= 1u << st;
-            dead += process_tile(s_stage_tok[st] + (d0.y - win_lo(d0.y)), s_stage_off[st] + (d0.x - win_lo(d0.x)), d0.y,
-                                 d1.x - d0.x, a.tok + d0.y, a.freq + d0.x, op, a.tab, uq);
+            mbar_wait(&s_full[st], (pipe_phase >> st) & 1u);
+            pipe_phase ^= 1u << st;
+            uint32_t *tk = stok + st * stage_words + (d0.y - win_lo(d0.y));
+            const uint32_t *of = stok + st * stage_words + a.stream_tok_cap + (d0.x - win_lo(d0.x));
+            dead += process_tile(tk, of, d0.y, d1.x - d0.x, d1.y - d0.y, s_claim, a.tok + d0.y, a.freq + d0.x, op,
+                                 a.tab, uq);
           } else {
             dead += process_tile_direct(a.tok, a.off, a.freq, d0.x, d1.x, op, a.tab);
           }
         }
         __syncthreads();  // every warp is done with this stage before it is refilled
+        c0 = n0; c1 = n1; n0 = nn0; n1 = nn1;
       }
       // write-through stores (generic proxy) must be ordered before the next iteration's bulk loads
       asm volatile("fence.proxy.async;" ::: "memory");
     }
+    if (uq.n) uq_drain(uq, lane, a.tab);  // one batch of table updates per warp and iteration
     for (int o = 16; o > 0; o >>= 1) dead += __shfl_xor_sync(0xffffffffu, dead, o);
     if (lane == 0 && dead) atomicAdd(&s_dead, dead);
     __syncthreads();

@@ -337,9 +337,10 @@ __global__ void synth_words_kernel(uint32_t *tok, uint32_t *off, uint64_t *freq,
     if (w == n_words) break;
     freq[w] = 1 + (mix64(w ^ seed) & 7);
     uint64_t r = mix64(w * 0x9E3779B97F4A7C15ull + seed);
-    for (uint32_t i = 0; i < len; i++) {
+    tok[w * len] = 4;  // word-initial token, never elsewhere (the role of "▁" in real words)
+    for (uint32_t i = 1; i < len; i++) {
       r = r * 6364136223846793005ull + 1442695040888963407ull;
-      tok[w * len + i] = 4 + (uint32_t)((r >> 33) % alphabet);
+      tok[w * len + i] = 5 + (uint32_t)((r >> 33) % alphabet);
     }
   }
 }
@@ -452,6 +453,10 @@ int plan_tiles(yttm_ctx *c, LoopArgs *a) {
   a->tile_desc = nullptr;
   a->stream_tok_cap = c->loop_stream_tok_cap;
   a->stream_word_cap = c->loop_stream_word_cap;
+  a->defer = nullptr;
+  a->defer_cap = 0;
+  a->n_stage = (uint32_t)c->loop_stages;
+  a->debug = std::getenv("YTTM_DEBUG") ? 1u : 0u;
   c->loop_resident = 0;
   if (c->n_words == 0 || c->n_slots == 0) return 0;
   YT_CUDA(c, c->counters.reserve(64));
@@ -470,7 +475,12 @@ int plan_tiles(yttm_ctx *c, LoopArgs *a) {
     c->launches++;
     a->tile_desc = c->tiles.as<uint2>();
     a->n_tiles = (uint32_t)n_tiles;
-    if (pass == 1) break;
+    if (pass == 1) {
+      a->defer_cap = 8192;
+      YT_CUDA(c, c->defer.reserve((size_t)c->loop_blocks * a->defer_cap * sizeof(uint4)));
+      a->defer = c->defer.as<uint4>();
+      break;
+    }
     YT_CUDA(c, cudaMemsetAsync(d_stats, 0, 8, c->stream));
     tile_stats_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, c->stream>>>(c->tiles.as<uint2>(),
                                                                                   (uint32_t)n_tiles, d_stats);
@@ -534,7 +544,7 @@ void yttm_ctx_destroy(yttm_ctx *c) {
   cudaStreamSynchronize(c->stream);
   ytc::DevBuf *bufs[] = {&c->text_buf, &c->hist, &c->cp2id, &c->wkey, &c->wcnt, &c->wpos, &c->wfreq, &c->wlen,
                          &c->scan_tmp, &c->counters, &c->tok[0], &c->tok[1], &c->off[0], &c->off[1], &c->freq[0],
-                         &c->freq[1], &c->pkey, &c->pcnt, &c->scratch_key, &c->scratch_cnt, &c->ctl, &c->blockbest, &c->tiles,
+                         &c->freq[1], &c->pkey, &c->pcnt, &c->scratch_key, &c->scratch_cnt, &c->ctl, &c->blockbest, &c->tiles, &c->defer,
                          &c->d_rules, &c->d_rfreq};
   for (auto *b : bufs) b->release();
   for (auto &kv : c->timers) { if (kv.second.a) cudaEventDestroy(kv.second.a); if (kv.second.b) cudaEventDestroy(kv.second.b); }
@@ -855,16 +865,19 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
     int dyn = optin - 2048;  // static shared memory of the kernel + margin
     if (dyn < 64 * 1024) YT_FAIL(c, "merge_loop_kernel: not enough shared memory per block");
     c->loop_smem = dyn;
-    const int tile_bytes = dyn - 32 * UQ_CAP * 16;                           // minus the per-warp update queues
-    c->loop_word_cap = (uint32_t)(tile_bytes / 4 / 4 - 1);                  // 1/4 of the words for offsets
+    const int tile_bytes = dyn - 32 * UQ_CAP * 16 - 2 * CLAIM_WORDS * 4;         // minus update queues and claim bitmap
+    c->loop_word_cap = std::min<uint32_t>((uint32_t)(tile_bytes / 4 / 4 - 1), CLAIM_WORDS * 32 - 1);  // offsets
     c->loop_tok_cap = (uint32_t)(tile_bytes / 4 - (c->loop_word_cap + 1)); // the rest for token slots
-    // STREAMING: two stages; a stage holds a window of q slots plus the overhang of its last word
-    // (words of up to q/4 slots stay on the shared-memory path) and at most q/2 + 1 offsets
+    // STREAMING: n_stage stages; a stage holds a window of q slots plus the overhang of its last
+    // word (words of up to q/4 slots stay on the shared-memory path) and at most q/2 + 1 offsets
     {
-      const uint32_t per_stage = (uint32_t)(tile_bytes / 2 / 4) & ~3u;  // uint32 per stage
+      int n_stage = 2;  // (deeper rings were tried: see DESIGN.md §6 "what did not work")
+
+      const uint32_t per_stage = (uint32_t)(tile_bytes / n_stage / 4) & ~3u;  // uint32 per stage
       // tokens: q + q/4 + 8, offsets: q/2 + 16  ->  q * 1.75 + 24 <= per_stage
       uint32_t q = (uint32_t)((per_stage - 24) / 1.75);
       q &= ~15u;
+      c->loop_stages = n_stage;
       c->loop_stream_q = q;
       c->loop_stream_word_cap = (q / 2 + 16) & ~3u;
       c->loop_stream_tok_cap = (per_stage - c->loop_stream_word_cap) & ~3u;
