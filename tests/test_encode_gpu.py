@@ -146,3 +146,20 @@ def test_config2_shape_vs_reference(product, checkers):
     sents = zc.sentences(50_000, 128, seed=77)
     want = ref.encoder(m, n_threads=8).encode(sents)
     assert GpuEncoder(m).encode(sents) == want
+
+
+def test_chunked_h2d_pipeline(product, oracle, monkeypatch):
+    """yttm_enc_run pipelines the batch in chunks (H2D / kernels / D2H overlapped, two buffer
+    sets): force 1 MB chunks so that several chunks and both buffer sets are exercised; the
+    result must not depend on the chunking (incl. the dropout stream, keyed by sentence index)."""
+    m = _model(oracle, _cases.dirty_zipf_text(), 1500)
+    zc = _cases.zipf()
+    sents = zc.sentences(30_000, 120, seed=21) + _cases.EDGE_SENTENCES + [b" ".join(zc.sentences(2000, 100, seed=5))]
+    o = oracle.encoder(m)
+    want = o.encode(sents, bos=True, eos=True)
+    want_drop = o.encode(sents, dropout=0.2, seed=77)
+    for mb in ("1", "64"):
+        monkeypatch.setenv("YTTM_ENC_CHUNK_MB", mb)
+        g = GpuEncoder(m)
+        assert g.encode(sents, bos=True, eos=True) == want
+        assert g.encode(sents, dropout=0.2, seed=77) == want_drop

@@ -14,6 +14,7 @@
 // Output positions are a pure function of byte positions (a word of k bytes owns k+1 slots), so
 // no kernel depends on another block's progress.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -187,15 +188,25 @@ struct yttm_enc {
   ytc::DevBuf cp2id, rules;
   uint32_t rule_mask = 0, space_id = 0;
   int unk = -1, pad = -1, bos = -1, eos = -1;
-  // per-call device buffers
-  ytc::DevBuf d_bytes, d_offs, slots, ranks, aux, wpos, wsent, nids, out_off, out_ids, counter;
+  // per-call device buffers: two sets, so that the host-buffer entry point can pipeline chunks
+  // (H2D of chunk i+1 and D2H of chunk i-1 overlap the kernels of chunk i)
+  struct Slot {
+    ytc::DevBuf d_bytes, d_offs, slots, ranks, aux, wpos, wsent, nids, out_off, out_ids, counter;
+    void release() {
+      ytc::DevBuf *b[] = {&d_bytes, &d_offs, &slots, &ranks, &aux, &wpos, &wsent, &nids, &out_off, &out_ids, &counter};
+      for (auto *x : b) x->release();
+    }
+  } slot[2];
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
 };
 
 namespace {
 
-int enc_device(yttm_enc *e, const uint8_t *d_bytes, const uint64_t *d_offs, uint64_t n_bytes, uint64_t n_sent, int bos,
-               int eos, int reverse, double dropout, uint64_t seed, uint64_t first_sentence, uint64_t *out_n) {
-  yttm_ctx *c = e->ctx;
+int enc_device(yttm_enc *enc, yttm_enc::Slot *e, const uint8_t *d_bytes, const uint64_t *d_offs, uint64_t n_bytes,
+               uint64_t n_sent, int bos, int eos, int reverse, double dropout, uint64_t seed, uint64_t first_sentence,
+               uint64_t *out_n) {
+  yttm_ctx *c = enc->ctx;
   if (n_bytes >= 0xfffffff0ull || n_sent >= 0xfffffff0ull)
     YT_FAIL(c, "encode batch too large: at most 2^32 bytes / sentences per call (split the batch)");
   const uint64_t n_slots = n_bytes + 3 * n_sent;
@@ -216,10 +227,10 @@ int enc_device(yttm_enc *e, const uint8_t *d_bytes, const uint64_t *d_offs, uint
   a.word_pos = e->wpos.as<uint32_t>(); a.word_sent = e->wsent.as<uint32_t>();
   a.n_words = e->counter.as<unsigned long long>();
   a.n_ids = e->nids.as<unsigned long long>();
-  a.cp2id = e->cp2id.as<uint32_t>();
-  a.rt.slots = e->rules.as<uint4>(); a.rt.mask = e->rule_mask;
-  a.space_id = e->space_id;
-  a.unk_id = e->unk; a.bos_id = e->bos; a.eos_id = e->eos;
+  a.cp2id = enc->cp2id.as<uint32_t>();
+  a.rt.slots = enc->rules.as<uint4>(); a.rt.mask = enc->rule_mask;
+  a.space_id = enc->space_id;
+  a.unk_id = enc->unk; a.bos_id = enc->bos; a.eos_id = enc->eos;
   a.bos = bos; a.eos = eos; a.reverse = reverse;
   a.drop_thresh = dropout <= 0 ? 0 : (uint64_t)(dropout * 4294967296.0);
   a.seed = seed; a.first_sentence = first_sentence;
@@ -319,9 +330,16 @@ int yttm_enc_create(yttm_ctx *c, const uint32_t *char_cp, const uint32_t *char_i
 void yttm_enc_destroy(yttm_enc *e) {
   if (!e) return;
   cudaSetDevice(e->ctx->device);
-  ytc::DevBuf *bufs[] = {&e->cp2id, &e->rules, &e->d_bytes, &e->d_offs, &e->slots, &e->ranks, &e->aux, &e->wpos,
-                         &e->wsent, &e->nids, &e->out_off, &e->out_ids, &e->counter};
-  for (auto *b : bufs) b->release();
+  e->cp2id.release();
+  e->rules.release();
+  for (int i = 0; i < 2; i++) {
+    e->slot[i].release();
+    if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
+    if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
+    if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
+  }
+  if (e->s_in) cudaStreamDestroy(e->s_in);
+  if (e->s_out) cudaStreamDestroy(e->s_out);
   delete e;
 }
 
@@ -332,11 +350,11 @@ int yttm_enc_run_device(yttm_enc *e, const char *d_bytes, const uint64_t *d_offs
   YT_CUDA(c, cudaSetDevice(c->device));
   if (bos && e->bos == -1) YT_FAIL(c, "Can't add <BOS> token. Model was trained without it.");
   if (eos && e->eos == -1) YT_FAIL(c, "Can't add <EOS> token. Model was trained without it.");
-  if (enc_device(e, (const uint8_t *)d_bytes, d_offsets, n_bytes, n_sent, bos, eos, reverse, dropout, seed,
-                 first_sentence_index, out_n))
+  if (enc_device(e, &e->slot[0], (const uint8_t *)d_bytes, d_offsets, n_bytes, n_sent, bos, eos, reverse, dropout,
+                 seed, first_sentence_index, out_n))
     return 1;
-  if (d_out_ids) *d_out_ids = e->out_ids.as<int32_t>();
-  if (d_out_offsets) *d_out_offsets = e->out_off.as<uint64_t>();
+  if (d_out_ids) *d_out_ids = e->slot[0].out_ids.as<int32_t>();
+  if (d_out_offsets) *d_out_offsets = e->slot[0].out_off.as<uint64_t>();
   return 0;
 }
 
@@ -349,23 +367,76 @@ int yttm_enc_run(yttm_enc *e, const char *bytes, const uint64_t *offsets, uint64
   if (eos && e->eos == -1) YT_FAIL(c, "Can't add <EOS> token. Model was trained without it.");
   *out_n = 0;
   if (n_sent == 0) { if (out_offsets) out_offsets[0] = 0; return 0; }
-  const uint64_t n_bytes = offsets[n_sent] - offsets[0];
-  ytc::timer_begin(c, "h2d");
-  YT_CUDA(c, e->d_bytes.reserve(n_bytes + 64));
-  YT_CUDA(c, e->d_offs.reserve((n_sent + 1) * 8));
-  if (n_bytes) YT_CUDA(c, cudaMemcpyAsync(e->d_bytes.p, bytes + offsets[0], n_bytes, cudaMemcpyHostToDevice, c->stream));
-  YT_CUDA(c, cudaMemcpyAsync(e->d_offs.p, offsets, (n_sent + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-  ytc::timer_end(c, "h2d");
-  uint64_t total = 0;
-  if (enc_device(e, e->d_bytes.as<uint8_t>(), e->d_offs.as<uint64_t>(), n_bytes, n_sent, bos, eos, reverse, dropout,
-                 seed, first_sentence_index, &total))
-    return 1;
-  *out_n = total;
-  if (total > out_cap) { c->err = "yttm_enc_run: output buffer too small"; return 2; }
-  ytc::timer_begin(c, "d2h");
-  if (total) YT_CUDA(c, cudaMemcpyAsync(out_ids, e->out_ids.p, total * 4, cudaMemcpyDeviceToHost, c->stream));
-  YT_CUDA(c, cudaMemcpyAsync(out_offsets, e->out_off.p, (n_sent + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
-  ytc::timer_end(c, "d2h");
+  if (!e->s_in) {
+    YT_CUDA(c, cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+    YT_CUDA(c, cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      YT_CUDA(c, cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming));
+      YT_CUDA(c, cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming));
+      YT_CUDA(c, cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming));
+    }
+  }
+  // chunks of about CHUNK bytes, cut at sentence boundaries; chunk i lives in slot i & 1
+  const uint64_t total_bytes = offsets[n_sent] - offsets[0];
+  uint64_t chunk_bytes = 32ull << 20;
+  if (const char *env = std::getenv("YTTM_ENC_CHUNK_MB")) chunk_bytes = (uint64_t)std::max(1, std::atoi(env)) << 20;
+  std::vector<uint64_t> cut(1, 0);  // sentence indices
+  while (cut.back() < n_sent) {
+    const uint64_t lo = cut.back();
+    const uint64_t want = offsets[lo] + chunk_bytes;
+    uint64_t hi = (uint64_t)(std::upper_bound(offsets + lo + 1, offsets + n_sent + 1, want) - offsets) - 1;
+    if (hi <= lo) hi = lo + 1;  // a single sentence longer than the chunk size
+    if (offsets[n_sent] - offsets[hi] < chunk_bytes / 4) hi = n_sent;  // no tiny tail chunk
+    cut.push_back(std::min<uint64_t>(hi, n_sent));
+  }
+  const size_t K = cut.size() - 1;
+  auto h2d = [&](size_t i) -> int {  // enqueue the input copies of chunk i on the copy-in stream
+    yttm_enc::Slot &sl = e->slot[i & 1];
+    const uint64_t lo = cut[i], hi = cut[i + 1], nb = offsets[hi] - offsets[lo];
+    YT_CUDA(c, sl.d_bytes.reserve(nb + 64));
+    YT_CUDA(c, sl.d_offs.reserve((hi - lo + 1) * 8));
+    if (i >= 2) YT_CUDA(c, cudaStreamWaitEvent(e->s_in, e->ev_done[i & 1], 0));  // kernels of chunk i-2 are done with it
+    if (nb) YT_CUDA(c, cudaMemcpyAsync(sl.d_bytes.p, bytes + offsets[lo], nb, cudaMemcpyHostToDevice, e->s_in));
+    YT_CUDA(c, cudaMemcpyAsync(sl.d_offs.p, offsets + lo, (hi - lo + 1) * 8, cudaMemcpyHostToDevice, e->s_in));
+    YT_CUDA(c, cudaEventRecord(e->ev_in[i & 1], e->s_in));
+    return 0;
+  };
+  ytc::timer_begin(c, "e2e");
+  if (h2d(0)) return 1;
+  uint64_t base = 0;
+  std::vector<uint64_t> bases(K + 1, 0);
+  int rc_small = 0;
+  for (size_t i = 0; i < K; i++) {
+    yttm_enc::Slot &sl = e->slot[i & 1];
+    const uint64_t lo = cut[i], hi = cut[i + 1], nb = offsets[hi] - offsets[lo];
+    if (i + 1 < K && h2d(i + 1)) return 1;
+    YT_CUDA(c, cudaStreamWaitEvent(c->stream, e->ev_in[i & 1], 0));
+    if (i >= 2) YT_CUDA(c, cudaStreamWaitEvent(c->stream, e->ev_out[i & 1], 0));  // results of chunk i-2 have left
+    uint64_t total = 0;
+    if (enc_device(e, &sl, sl.d_bytes.as<uint8_t>(), sl.d_offs.as<uint64_t>(), nb, hi - lo, bos, eos, reverse, dropout,
+                   seed, first_sentence_index + lo, &total))
+      return 1;
+    YT_CUDA(c, cudaEventRecord(e->ev_done[i & 1], c->stream));
+    bases[i] = base;
+    if (base + total > out_cap) rc_small = 2;
+    if (!rc_small) {
+      YT_CUDA(c, cudaStreamWaitEvent(e->s_out, e->ev_done[i & 1], 0));
+      if (total)
+        YT_CUDA(c, cudaMemcpyAsync(out_ids + base, sl.out_ids.p, total * 4, cudaMemcpyDeviceToHost, e->s_out));
+      YT_CUDA(c, cudaMemcpyAsync(out_offsets + lo, sl.out_off.p, (hi - lo) * 8, cudaMemcpyDeviceToHost, e->s_out));
+      YT_CUDA(c, cudaEventRecord(e->ev_out[i & 1], e->s_out));
+    }
+    base += total;
+  }
+  YT_CUDA(c, cudaStreamSynchronize(e->s_out));
+  YT_CUDA(c, cudaStreamSynchronize(c->stream));
+  ytc::timer_end(c, "e2e");
+  *out_n = base;
+  if (rc_small) { c->err = "yttm_enc_run: output buffer too small"; return 2; }
+  for (size_t i = 1; i < K; i++)  // chunk-local offsets -> batch offsets
+    for (uint64_t s2 = cut[i]; s2 < cut[i + 1]; s2++) out_offsets[s2] += bases[i];
+  out_offsets[n_sent] = base;
+  (void)total_bytes;
   return 0;
 }
 

@@ -28,7 +28,6 @@ struct LoopArgs {
   uint32_t n_stage;            // STREAMING: pipeline depth
   uint4 *defer;                // STREAMING: per-block lists of words to rewrite after the tile scan
   uint32_t defer_cap;          // entries per block
-  uint32_t debug;
   uint32_t n_tiles;
   uint32_t resident;           // 1: block b owns tile b and keeps it in shared memory
   uint32_t smem_tok_cap;       // token capacity of the shared tile buffer
@@ -279,12 +278,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
-    if (spin > (1u << 24)) {  // a lost transaction must not hang the box
-      if ((threadIdx.x & 31) == 0)
-        printf("yttm mbar_wait stuck: block %d thread %d bar %u parity %u\n", (int)blockIdx.x, (int)threadIdx.x,
-               smem_u32(bar), parity);
-      asm volatile("trap;");
-    }
+    if (spin > (1u << 28)) asm volatile("trap;");  // a lost transaction must not hang the box
   }
 }
 // bytes of a 16-byte aligned window [lo & ~3, roundup(hi, 4)) over uint32 elements
@@ -312,6 +306,8 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
   uint32_t *s_claim = reinterpret_cast<uint32_t *>(uq_deltas + 32 * UQ_CAP);  // 2 bitmaps of CLAIM_WORDS x 32 flags
   uint32_t *stok = s_claim + 2 * CLAIM_WORDS;
   uint32_t *soff = stok + a.smem_tok_cap;
+  // RESIDENT only: word frequencies behind the offsets (8-byte aligned: both caps are even)
+  unsigned long long *sfreq = reinterpret_cast<unsigned long long *>(soff + a.smem_word_cap + 2);
   for (uint32_t i = threadIdx.x; i < 2 * CLAIM_WORDS; i += blockDim.x) s_claim[i] = 0;
   // STREAMING carve of the same region: NSTAGE stages of (tokens, offsets), each 16-byte aligned;
   // full[s]: TMA bytes landed (tx count), empty[s]: all consumer warps are done with stage s
@@ -339,7 +335,10 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
   if (a.resident && blockIdx.x < a.n_tiles) {
     rw0 = a.tile_desc[blockIdx.x].x;
     rw1 = a.tile_desc[blockIdx.x + 1].x;
-    if (rw1 > rw0) load_tile(a, rw0, rw1, stok, soff);
+    if (rw1 > rw0) {
+      load_tile(a, rw0, rw1, stok, soff);
+      for (uint32_t i = threadIdx.x; i < rw1 - rw0; i += blockDim.x) sfreq[i] = a.freq[rw0 + i];
+    }
   }
   __syncthreads();
 
@@ -410,12 +409,12 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
       a.rfreq[n_done] = win.c;
       a.tab.cnts[win.slot] = 0;  // every occurrence of (x,y) is merged below; no deltas are sent for it
       a.ctl->n_done = n_done + 1;
-      if (a.debug) printf("IT %u x=%u y=%u z=%u c=%llu resident=%u\n", n_done, op.x, op.y, op.z, win.c, a.resident);
     }
     // ---------------- apply x y -> z
     unsigned long long dead = 0;
     if (a.resident) {
-      if (rw1 > rw0) dead = process_tile(stok, soff, 0, rw1 - rw0, soff[rw1 - rw0], s_claim, nullptr, a.freq + rw0, op, a.tab, uq);
+      if (rw1 > rw0) dead = process_tile(stok, soff, 0, rw1 - rw0, soff[rw1 - rw0], s_claim, nullptr,
+                                           reinterpret_cast<const uint64_t *>(sfreq), op, a.tab, uq);
     } else {
       // STREAMING: this block's tiles k = blockIdx.x, +gridDim.x, ... flow through a 2-stage TMA
       // pipeline: thread 0 issues the bulk copies of tile i+1 (tokens + offsets, 16-byte aligned

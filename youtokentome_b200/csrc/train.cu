@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(256) pair_hist_kernel(const uint32_t *__restri
                                                         const uint64_t *__restrict__ freq, uint64_t n_words,
                                                         PairTab tab) {
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  const uint32_t key_limit = (uint32_t)((tab.mask + 1) / 2 < 0xffffffffull ? (tab.mask + 1) / 2 : 0xffffffffull);
+  const uint32_t key_limit = (uint32_t)((tab.mask + 1) / 2 < 0xffffffffull ? (tab.mask + 1) / 2 : 0xffffffffull);  // > 3/8
   for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
     // a table that is already half full will be rejected by the host anyway: stop early
     if (__ldcg(tab.overflow) || __ldcg(tab.n_keys) > key_limit) { atomicExch(tab.overflow, 1u); return; }
@@ -383,7 +383,7 @@ PairTab tab_of(yttm_ctx *c) {
 int rebuild_pair_table(yttm_ctx *c, uint64_t min_cap) {
   uint64_t cap = std::max<uint64_t>(ytc::pow2ceil(min_cap), 1u << 16);
   YT_CUDA(c, c->ctl.reserve(sizeof(YtLoopCtl)));
-  for (int attempt = 0; attempt < 12; attempt++) {
+  for (int attempt = 0; attempt < 24; attempt++) {
     YT_CUDA(c, c->pkey.reserve(cap * 8));
     YT_CUDA(c, c->pcnt.reserve(cap * 8));
     c->pcap = cap;
@@ -401,10 +401,11 @@ int rebuild_pair_table(yttm_ctx *c, uint64_t min_cap) {
     uint32_t h[2];
     YT_CUDA(c, cudaMemcpyAsync(h, &ctl->n_keys, 8, cudaMemcpyDeviceToHost, c->stream));
     YT_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (!h[1] && (uint64_t)h[0] * 4 <= cap) { c->stats.n_pairs = h[0]; c->stats.table_capacity = cap; return 0; }
-    cap *= 4;
+    // accept at load <= 3/8: the arg-max sweeps every slot every merge, so the table is kept tight
+    if (!h[1] && (uint64_t)h[0] * 8 <= cap * 3) { c->stats.n_pairs = h[0]; c->stats.table_capacity = cap; return 0; }
+    cap *= 2;
   }
-  YT_FAIL(c, "pair table: could not reach load factor 1/4");
+  YT_FAIL(c, "pair table: could not reach load factor 3/8");
 }
 
 // Compact the packed words into the other buffer set.
@@ -456,7 +457,6 @@ int plan_tiles(yttm_ctx *c, LoopArgs *a) {
   a->defer = nullptr;
   a->defer_cap = 0;
   a->n_stage = (uint32_t)c->loop_stages;
-  a->debug = std::getenv("YTTM_DEBUG") ? 1u : 0u;
   c->loop_resident = 0;
   if (c->n_words == 0 || c->n_slots == 0) return 0;
   YT_CUDA(c, c->counters.reserve(64));
@@ -866,8 +866,10 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
     if (dyn < 64 * 1024) YT_FAIL(c, "merge_loop_kernel: not enough shared memory per block");
     c->loop_smem = dyn;
     const int tile_bytes = dyn - 32 * UQ_CAP * 16 - 2 * CLAIM_WORDS * 4;         // minus update queues and claim bitmap
-    c->loop_word_cap = std::min<uint32_t>((uint32_t)(tile_bytes / 4 / 4 - 1), CLAIM_WORDS * 32 - 1);  // offsets
-    c->loop_tok_cap = (uint32_t)(tile_bytes / 4 - (c->loop_word_cap + 1)); // the rest for token slots
+    // RESIDENT tile: per word 4 B offset + 8 B frequency (kept in shared memory too, so a rewritten
+    // word costs no L2 round trip for its frequency), the rest token slots
+    c->loop_word_cap = std::min<uint32_t>((uint32_t)(tile_bytes / 24 - 2), CLAIM_WORDS * 32 - 1) & ~1u;
+    c->loop_tok_cap = (uint32_t)((tile_bytes - 12 * (c->loop_word_cap + 2)) / 4) & ~3u;
     // STREAMING: n_stage stages; a stage holds a window of q slots plus the overhang of its last
     // word (words of up to q/4 slots stay on the shared-memory path) and at most q/2 + 1 offsets
     {
@@ -917,7 +919,7 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
     a.first_new_id = first_new_id;
     a.max_total = max_merges;
     a.max_iters = max_merges;
-    a.key_limit = (uint32_t)std::min<uint64_t>(c->pcap / 2, 0xfffffff0ull);
+    a.key_limit = (uint32_t)std::min<uint64_t>(c->pcap / 4 * 3, 0xfffffff0ull);  // rebuild above load 3/4
     void *args[] = {&a};
     YT_CUDA(c, cudaLaunchCooperativeKernel((void *)merge_loop_kernel, dim3(c->loop_blocks), dim3(c->loop_threads), args,
                                            (size_t)c->loop_smem, c->stream));
@@ -931,7 +933,8 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
     if (compact_words(c)) return 1;
     if (why == 2) {
       uint32_t keep_done = h.n_done;
-      if (rebuild_pair_table(c, std::max<uint64_t>(h.overflow ? c->pcap * 4 : c->pcap, 1u << 16))) return 1;
+      // dead keys vanish in the rebuild, so the table usually keeps its size (it grows only if still above 3/8)
+      if (rebuild_pair_table(c, std::max<uint64_t>(h.overflow ? c->pcap * 2 : c->pcap / 2, 1u << 16))) return 1;
       h.n_done = keep_done;
       YT_CUDA(c, cudaMemcpyAsync(&h.n_keys, &ctl->n_keys, 8, cudaMemcpyDeviceToHost, c->stream));
       YT_CUDA(c, cudaStreamSynchronize(c->stream));
