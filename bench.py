@@ -303,7 +303,7 @@ def main():
         rules = np.zeros(3 * iters, dtype=np.uint32)
         fr = np.zeros(iters, dtype=np.uint64)
         nd = C.c_uint32(0)
-        assert L.yttm_train_run(c2, 5 + alpha, iters, rules.ctypes.data, fr.ctypes.data, C.byref(nd)) == 0, \
+        assert L.yttm_train_run(c2, 4 + 1 + alpha, iters, rules.ctypes.data, fr.ctypes.data, C.byref(nd)) == 0, \
             L.yttm_last_error(c2)
         g = lambda k: L.yttm_stage_ms(c2, k.encode())
         it = max(g("loop_iters"), 1.0)

@@ -98,7 +98,9 @@ int yttm_train_dump_pairs(yttm_ctx *ctx, uint64_t *keys, uint64_t *counts, uint6
 int yttm_train_scan_once(yttm_ctx *ctx, double *ms, uint64_t *algo_bytes);
 
 /* Synthetic packed words generated ON DEVICE for roofline measurement of the scan kernel:
- * n_words words of `len` tokens over `alphabet` ids (LCG, fixed seed). */
+ * n_words words of `len` tokens: the first token of word w is 4 + w % n_first (word-initial ids,
+ * never used elsewhere - the role of U+2581), the others 4 + n_first + (LCG % (alphabet & 0xffffff));
+ * n_first = 1 << (alphabet >> 24).  New ids must start at 4 + n_first + (alphabet & 0xffffff). */
 int yttm_train_synth_words(yttm_ctx *ctx, uint64_t n_words, uint32_t len, uint32_t alphabet, uint64_t seed);
 
 /* ---- encoding: replaces encode_parallel / encode_sentence (bpe.cpp:1455-1632, 1697-1738) -- */

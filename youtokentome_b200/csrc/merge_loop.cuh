@@ -416,38 +416,49 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
       if (rw1 > rw0) dead = process_tile(stok, soff, 0, rw1 - rw0, soff[rw1 - rw0], s_claim, nullptr,
                                            reinterpret_cast<const uint64_t *>(sfreq), op, a.tab, uq);
     } else {
-      // STREAMING: this block's tiles k = blockIdx.x, +gridDim.x, ... flow through a 2-stage TMA
-      // pipeline: thread 0 issues the bulk copies of tile i+1 (tokens + offsets, 16-byte aligned
-      // windows, completion on an mbarrier) while all warps scan tile i out of shared memory;
-      // rewritten words are written through to HBM.
-      const uint32_t my_tiles = a.n_tiles > blockIdx.x ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      // STREAMING: this block owns a contiguous chunk of tiles that flows through an n_stage ring of
+      // shared-memory stages.  Thread 0 is the producer: it keeps n_stage - 1 tiles in flight ahead
+      // of the one being scanned (TMA bulk copies of tokens + offsets, 16-byte aligned windows,
+      // completion on full[s]).  All warps scan the current tile token-parallel and rewrite the
+      // words that hold (x,y) right there (shared memory + write-through to HBM); the block barrier
+      // at the end of a tile releases its stage.
+      const uint32_t per_block = (a.n_tiles + gridDim.x - 1) / gridDim.x;
+      const uint32_t k_first = min(a.n_tiles, blockIdx.x * per_block);
+      const uint32_t my_tiles = min(a.n_tiles, k_first + per_block) - k_first;
       auto staged = [&](uint2 d0, uint2 d1) {  // does this tile go through shared memory?
         return d1.x > d0.x && win_bytes(d0.y, d1.y) <= a.stream_tok_cap * 4u &&
                win_bytes(d0.x, d1.x + 1) <= a.stream_word_cap * 4u;
       };
-      auto issue = [&](uint32_t i, uint2 d0, uint2 d1) {  // thread 0 only
-        if (!staged(d0, d1)) return;
-        const uint32_t st = i & 1u;
-        uint32_t *dst = stok + st * stage_words;
-        const uint32_t bt = win_bytes(d0.y, d1.y), bo = win_bytes(d0.x, d1.x + 1);
-        mbar_expect_tx(&s_full[st], bt + bo);
-        tma_bulk_g2s(dst, a.tok + win_lo(d0.y), bt, &s_full[st]);
-        tma_bulk_g2s(dst + a.stream_tok_cap, a.off + win_lo(d0.x), bo, &s_full[st]);
+      uint32_t issued = 0;                       // thread 0: tiles handed to the TMA so far
+      uint2 pd0 = make_uint2(0, 0), pd1 = pd0;   // thread 0: descriptor of the next tile to issue
+      auto issue_next = [&]() {                  // thread 0 only
+        const uint2 d0 = pd0, d1 = pd1;
+        if (issued + 1 < my_tiles) { pd0 = d1; pd1 = a.tile_desc[k_first + issued + 2]; }  // prefetch
+        if (staged(d0, d1)) {
+          const uint32_t st = issued % n_stage;
+          uint32_t *dst = stok + st * stage_words;
+          const uint32_t bt = win_bytes(d0.y, d1.y), bo = win_bytes(d0.x, d1.x + 1);
+          mbar_expect_tx(&s_full[st], bt + bo);
+          tma_bulk_g2s(dst, a.tok + win_lo(d0.y), bt, &s_full[st]);
+          tma_bulk_g2s(dst + a.stream_tok_cap, a.off + win_lo(d0.x), bo, &s_full[st]);
+        }
+        issued++;
       };
-      // tile descriptors are fetched two tiles ahead so neither the issue nor the wait sees L2 latency
-      const uint32_t G = gridDim.x, k0 = blockIdx.x;
-      uint2 c0 = make_uint2(0, 0), c1 = c0, n0 = c0, n1 = c0;
-      if (my_tiles) { c0 = a.tile_desc[k0]; c1 = a.tile_desc[k0 + 1]; }
-      if (my_tiles > 1) { n0 = a.tile_desc[k0 + G]; n1 = a.tile_desc[k0 + G + 1]; }
-      if (threadIdx.x == 0 && my_tiles) issue(0, c0, c1);
-      for (uint32_t i = 0; i < my_tiles; i++) {
-        uint2 nn0 = make_uint2(0, 0), nn1 = nn0;
-        if (i + 2 < my_tiles) { nn0 = a.tile_desc[k0 + (i + 2) * G]; nn1 = a.tile_desc[k0 + (i + 2) * G + 1]; }
-        if (threadIdx.x == 0 && i + 1 < my_tiles) issue(i + 1, n0, n1);  // its stage was released by the barrier below
-        const uint2 d0 = c0, d1 = c1;
+      if (threadIdx.x == 0 && my_tiles) {
+        pd0 = a.tile_desc[k_first];
+        pd1 = a.tile_desc[k_first + 1];
+        for (uint32_t j = 0; j + 1 < n_stage && issued < my_tiles; j++) issue_next();
+      }
+      uint2 dn0 = make_uint2(0, 0), dn1 = dn0;
+      if (my_tiles) { dn0 = a.tile_desc[k_first]; dn1 = a.tile_desc[k_first + 1]; }
+      for (uint32_t t = 0; t < my_tiles; t++) {
+        const uint2 d0 = dn0, d1 = dn1;
+        if (t + 1 < my_tiles) { dn0 = d1; dn1 = a.tile_desc[k_first + t + 2]; }
+        // tile t + n_stage - 1 goes into the stage tile t - 1 used, released by the barrier below
+        if (threadIdx.x == 0 && issued < my_tiles) issue_next();
         if (d1.x > d0.x) {
           if (staged(d0, d1)) {
-            const uint32_t st = i & 1u;
+            const uint32_t st = t % n_stage;
             mbar_wait(&s_full[st], (pipe_phase >> st) & 1u);
             pipe_phase ^= 1u << st;
             uint32_t *tk = stok + st * stage_words + (d0.y - win_lo(d0.y));
@@ -459,7 +470,6 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
           }
         }
         __syncthreads();  // every warp is done with this stage before it is refilled
-        c0 = n0; c1 = n1; n0 = nn0; n1 = nn1;
       }
       // write-through stores (generic proxy) must be ordered before the next iteration's bulk loads
       asm volatile("fence.proxy.async;" ::: "memory");

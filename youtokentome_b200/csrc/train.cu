@@ -330,17 +330,17 @@ __global__ void set_u32_kernel(uint32_t *p, uint32_t v) { *p = v; }
 
 // synthetic packed words for roofline runs of the scan kernel
 __global__ void synth_words_kernel(uint32_t *tok, uint32_t *off, uint64_t *freq, uint64_t n_words, uint32_t len,
-                                   uint32_t alphabet, uint64_t seed) {
+                                   uint32_t alphabet, uint64_t seed, uint32_t n_first) {
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w <= n_words; w += stride) {
     off[w] = (uint32_t)(w * len);
     if (w == n_words) break;
     freq[w] = 1 + (mix64(w ^ seed) & 7);
     uint64_t r = mix64(w * 0x9E3779B97F4A7C15ull + seed);
-    tok[w * len] = 4;  // word-initial token, never elsewhere (the role of "▁" in real words)
+    tok[w * len] = 4 + (uint32_t)(w % n_first);  // word-initial tokens, never elsewhere (the role of "▁")
     for (uint32_t i = 1; i < len; i++) {
       r = r * 6364136223846793005ull + 1442695040888963407ull;
-      tok[w * len + i] = 5 + (uint32_t)((r >> 33) % alphabet);
+      tok[w * len + i] = 4 + n_first + (uint32_t)((r >> 33) % alphabet);
     }
   }
 }
@@ -788,7 +788,8 @@ int yttm_train_synth_words(yttm_ctx *c, uint64_t n_words, uint32_t len, uint32_t
   YT_CUDA(c, c->off[0].reserve((n_words + 2) * 4));
   YT_CUDA(c, c->freq[0].reserve((n_words + 1) * 8));
   synth_words_kernel<<<grid_for(c, n_words + 1, 256, 8), 256, 0, c->stream>>>(
-      c->tok[0].as<uint32_t>(), c->off[0].as<uint32_t>(), c->freq[0].as<uint64_t>(), n_words, len, alphabet, seed);
+      c->tok[0].as<uint32_t>(), c->off[0].as<uint32_t>(), c->freq[0].as<uint64_t>(), n_words, len, alphabet & 0xffffffu,
+      seed, std::max<uint32_t>(1u, alphabet >> 24 ? 1u << (alphabet >> 24) : 1u));
   c->launches++;
   YT_CUDA(c, cudaGetLastError());
   YT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -873,7 +874,8 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
     // STREAMING: n_stage stages; a stage holds a window of q slots plus the overhang of its last
     // word (words of up to q/4 slots stay on the shared-memory path) and at most q/2 + 1 offsets
     {
-      int n_stage = 2;  // (deeper rings were tried: see DESIGN.md §6 "what did not work")
+      int n_stage = 2;  // measured best: deeper rings shrink the tiles and the per-tile cost wins
+      if (const char *e = std::getenv("YTTM_STAGES")) n_stage = std::max(2, std::min(MAX_STAGES, std::atoi(e)));
 
       const uint32_t per_stage = (uint32_t)(tile_bytes / n_stage / 4) & ~3u;  // uint32 per stage
       // tokens: q + q/4 + 8, offsets: q/2 + 16  ->  q * 1.75 + 24 <= per_stage
