@@ -863,7 +863,7 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
   if (!c->loop_blocks) {
     int optin = 0;
     YT_CUDA(c, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-    int dyn = optin - 2048;  // static shared memory of the kernel + margin
+    int dyn = optin - 4096;  // static shared memory of the kernel (3.4 KB) + margin
     if (dyn < 64 * 1024) YT_FAIL(c, "merge_loop_kernel: not enough shared memory per block");
     c->loop_smem = dyn;
     const int tile_bytes = dyn - 32 * UQ_CAP * 16 - 2 * CLAIM_WORDS * 4;         // minus update queues and claim bitmap
