@@ -154,14 +154,15 @@ __device__ __forceinline__ uint32_t warp_apply_word(uint32_t *st, uint32_t cap, 
   const unsigned span_mask = (ro.nxt >= 31 ? 0xffffffffu : ((2u << ro.nxt) - 1u)) & ~((1u << lane) - 1u);
   const bool old_changed = ro.start && (touched & span_mask) != 0u;
   const unsigned unchanged_starts = __ballot_sync(0xffffffffu, ro.start && !old_changed);
-  __syncwarp();
+  __syncwarp();  // every lane holds its old token in a register before any slot is overwritten
   if (keep) { st[newpos] = nv; if (gt) gt[newpos] = nv; }
   if (valid && lane >= n2) { st[lane] = DEAD; if (gt) gt[lane] = DEAD; }
-  __syncwarp();
-  const uint32_t t2 = lane < n2 ? st[lane] : DEAD;
-  const RunInfo rn = warp_runs(t2, n2, lane);
-  // new lane p came from old lane src = (p+1)-th kept lane; its run is unchanged iff that old run was
+  // new lane p came from old lane src = (p+1)-th kept lane: fetch its token with a shuffle (st may be
+  // global memory in the deferred path: no re-read through L1); its run is unchanged iff that old run was
   const uint32_t src = lane < n2 ? __fns(km, 0, lane + 1) : 0u;
+  const uint32_t moved = __shfl_sync(0xffffffffu, nv, src & 31);
+  const uint32_t t2 = lane < n2 ? moved : DEAD;
+  const RunInfo rn = warp_runs(t2, n2, lane);
   const bool new_changed = rn.start && !((unchanged_starts >> (src & 31)) & 1u);
   // the four possible updates of this lane
   const bool h0 = old_changed && ro.L >= 2 && pair_key(t, t) != op.key;
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
   const uint32_t n_stage = a.n_stage;
   const uint32_t stage_words = a.stream_tok_cap + a.stream_word_cap;  // uint32 per stage
   if (!a.resident && threadIdx.x == 0) {
-    for (uint32_t st = 0; st < n_stage; st++) { mbar_init(&s_full[st], 1); mbar_init(&s_empty[st], (blockDim.x >> 5) - 1); }
+    for (uint32_t st = 0; st < n_stage; st++) { mbar_init(&s_full[st], 1); mbar_init(&s_empty[st], (blockDim.x >> 5) - 1);  /* consumer warps */ }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // STREAMING pipeline state of this thread (producer lane: empty-phase bits, consumers: full-phase bits)
@@ -417,59 +418,112 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
                                            reinterpret_cast<const uint64_t *>(sfreq), op, a.tab, uq);
     } else {
       // STREAMING: this block owns a contiguous chunk of tiles that flows through an n_stage ring of
-      // shared-memory stages.  Thread 0 is the producer: it keeps n_stage - 1 tiles in flight ahead
-      // of the one being scanned (TMA bulk copies of tokens + offsets, 16-byte aligned windows,
-      // completion on full[s]).  All warps scan the current tile token-parallel and rewrite the
-      // words that hold (x,y) right there (shared memory + write-through to HBM); the block barrier
-      // at the end of a tile releases its stage.
+      // shared-memory stages.  Lane 0 of warp 0 is the PRODUCER: it keeps up to n_stage tiles in
+      // flight with TMA bulk copies (tokens + offsets, 16-byte aligned windows, completion on
+      // full[s]) and refills a stage as soon as all consumer warps have released it (empty[s]).
+      // Warps 1.. are CONSUMERS: they scan a tile out of shared memory token-parallel and append
+      // the words that hold (x,y) to the block's deferred list; no block barrier in the tile loop.
+      // The deferred words are rewritten afterwards straight in HBM, one warp per word, so their
+      // latencies overlap each other instead of stalling the copy pipeline.
       const uint32_t per_block = (a.n_tiles + gridDim.x - 1) / gridDim.x;
       const uint32_t k_first = min(a.n_tiles, blockIdx.x * per_block);
       const uint32_t my_tiles = min(a.n_tiles, k_first + per_block) - k_first;
+      uint4 *defer = a.defer + (size_t)blockIdx.x * a.defer_cap;
+      if (threadIdx.x == 0) { s_defer_n = 0; s_direct = 0; }
+      __syncthreads();
       auto staged = [&](uint2 d0, uint2 d1) {  // does this tile go through shared memory?
         return d1.x > d0.x && win_bytes(d0.y, d1.y) <= a.stream_tok_cap * 4u &&
                win_bytes(d0.x, d1.x + 1) <= a.stream_word_cap * 4u;
       };
-      uint32_t issued = 0;                       // thread 0: tiles handed to the TMA so far
-      uint2 pd0 = make_uint2(0, 0), pd1 = pd0;   // thread 0: descriptor of the next tile to issue
-      auto issue_next = [&]() {                  // thread 0 only
-        const uint2 d0 = pd0, d1 = pd1;
-        if (issued + 1 < my_tiles) { pd0 = d1; pd1 = a.tile_desc[k_first + issued + 2]; }  // prefetch
-        if (staged(d0, d1)) {
-          const uint32_t st = issued % n_stage;
-          uint32_t *dst = stok + st * stage_words;
-          const uint32_t bt = win_bytes(d0.y, d1.y), bo = win_bytes(d0.x, d1.x + 1);
-          mbar_expect_tx(&s_full[st], bt + bo);
-          tma_bulk_g2s(dst, a.tok + win_lo(d0.y), bt, &s_full[st]);
-          tma_bulk_g2s(dst + a.stream_tok_cap, a.off + win_lo(d0.x), bo, &s_full[st]);
-        }
-        issued++;
+      // tile descriptors travel in lane-distributed batches: lane j of a warp holds tile_desc[base + j],
+      // tiles base .. base+30 take (d0, d1) from lanes (j, j+1) by shuffle, so the L2 latency of the
+      // descriptor loads is paid once per 31 tiles instead of once per tile
+      auto load_batch = [&](uint32_t base) {
+        const uint32_t idx = min(k_first + base + lane, k_first + my_tiles);
+        return a.tile_desc[idx];
       };
-      if (threadIdx.x == 0 && my_tiles) {
-        pd0 = a.tile_desc[k_first];
-        pd1 = a.tile_desc[k_first + 1];
-        for (uint32_t j = 0; j + 1 < n_stage && issued < my_tiles; j++) issue_next();
-      }
-      uint2 dn0 = make_uint2(0, 0), dn1 = dn0;
-      if (my_tiles) { dn0 = a.tile_desc[k_first]; dn1 = a.tile_desc[k_first + 1]; }
-      for (uint32_t t = 0; t < my_tiles; t++) {
-        const uint2 d0 = dn0, d1 = dn1;
-        if (t + 1 < my_tiles) { dn0 = d1; dn1 = a.tile_desc[k_first + t + 2]; }
-        // tile t + n_stage - 1 goes into the stage tile t - 1 used, released by the barrier below
-        if (threadIdx.x == 0 && issued < my_tiles) issue_next();
-        if (d1.x > d0.x) {
-          if (staged(d0, d1)) {
-            const uint32_t st = t % n_stage;
-            mbar_wait(&s_full[st], (pipe_phase >> st) & 1u);
-            pipe_phase ^= 1u << st;
-            uint32_t *tk = stok + st * stage_words + (d0.y - win_lo(d0.y));
-            const uint32_t *of = stok + st * stage_words + a.stream_tok_cap + (d0.x - win_lo(d0.x));
-            dead += process_tile(tk, of, d0.y, d1.x - d0.x, d1.y - d0.y, s_claim, a.tok + d0.y, a.freq + d0.x, op,
-                                 a.tab, uq);
-          } else {
-            dead += process_tile_direct(a.tok, a.off, a.freq, d0.x, d1.x, op, a.tab);
+      if (wid == 0) {
+        uint32_t used = pipe_used, ephase = pipe_phase, st = pipe_stage;  // barrier phases persist across merges
+        uint2 batch = make_uint2(0, 0);
+        for (uint32_t t = 0; t < my_tiles; t++) {
+          const uint32_t j = t % 31;
+          if (j == 0) batch = load_batch(t);
+          uint2 d0, d1;
+          d0.x = __shfl_sync(0xffffffffu, batch.x, j);     d0.y = __shfl_sync(0xffffffffu, batch.y, j);
+          d1.x = __shfl_sync(0xffffffffu, batch.x, j + 1); d1.y = __shfl_sync(0xffffffffu, batch.y, j + 1);
+          if (!staged(d0, d1)) continue;
+          if (lane == 0) {
+            if ((used >> st) & 1u) mbar_wait(&s_empty[st], (ephase >> st) & 1u);
+            uint32_t *dst = stok + st * stage_words;
+            const uint32_t bt = win_bytes(d0.y, d1.y), bo = win_bytes(d0.x, d1.x + 1);
+            mbar_expect_tx(&s_full[st], bt + bo);
+            tma_bulk_g2s(dst, a.tok + win_lo(d0.y), bt, &s_full[st]);
+            tma_bulk_g2s(dst + a.stream_tok_cap, a.off + win_lo(d0.x), bo, &s_full[st]);
           }
+          if ((used >> st) & 1u) ephase ^= 1u << st;
+          used |= 1u << st;
+          st = st + 1 == n_stage ? 0 : st + 1;
+          __syncwarp();
         }
-        __syncthreads();  // every warp is done with this stage before it is refilled
+        pipe_used = used; pipe_phase = ephase; pipe_stage = st;
+      } else {
+        uint32_t fphase = pipe_phase, st = pipe_stage;
+        const unsigned cw = wid - 1, ncw = nwarp - 1;  // consumer warp index / count
+        uint2 batch = make_uint2(0, 0);
+        for (uint32_t t = 0; t < my_tiles; t++) {
+          const uint32_t j = t % 31;
+          if (j == 0) batch = load_batch(t);
+          uint2 d0, d1;
+          d0.x = __shfl_sync(0xffffffffu, batch.x, j);     d0.y = __shfl_sync(0xffffffffu, batch.y, j);
+          d1.x = __shfl_sync(0xffffffffu, batch.x, j + 1); d1.y = __shfl_sync(0xffffffffu, batch.y, j + 1);
+          if (d1.x <= d0.x) continue;
+          if (!staged(d0, d1)) { if (cw == 0 && lane == 0) s_direct = 1; continue; }  // oversized: direct pass below
+          mbar_wait(&s_full[st], (fphase >> st) & 1u);
+          fphase ^= 1u << st;
+          const uint32_t *tk = stok + st * stage_words + (d0.y - win_lo(d0.y));
+          const uint32_t *of = stok + st * stage_words + a.stream_tok_cap + (d0.x - win_lo(d0.x));
+          const uint32_t span = d1.y - d0.y, nw = d1.x - d0.x, obase = d0.y;
+          for (uint32_t base = cw * 32; base < span; base += ncw * 32) {
+            const uint32_t i = base + lane;
+            const bool hit = i + 1 < span && tk[i] == op.x && tk[i + 1] == op.y;
+            if (!__ballot_sync(0xffffffffu, hit)) continue;
+            if (hit) {
+              uint32_t lo = 0, hi = nw;  // largest w with of[w] - obase <= i
+              while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (of[mid] - obase <= i) lo = mid; else hi = mid;
+              }
+              const uint32_t o = of[lo] - obase, wcap = of[lo + 1] - obase - o;
+              bool first = true;  // only the first hit of a word reports it
+              for (uint32_t q2 = o; q2 < i; q2++)
+                if (tk[q2] == op.x && tk[q2 + 1] == op.y) { first = false; break; }
+              if (first) {
+                const uint32_t slot = atomicAdd(&s_defer_n, 1u);
+                if (slot < a.defer_cap) defer[slot] = make_uint4(d0.x + lo, obase + o, wcap, 0u);
+                else s_direct = 1;  // list full: the direct pass below picks the rest up
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[st]);
+          st = st + 1 == n_stage ? 0 : st + 1;
+        }
+        pipe_phase = fphase; pipe_stage = st;
+      }
+      __syncthreads();
+      {
+        const uint32_t n_def = min(s_defer_n, a.defer_cap);
+        for (uint32_t j = wid; j < n_def; j += nwarp) {
+          const uint4 e = defer[j];
+          const long long f = (long long)a.freq[e.x];
+          const uint32_t merges = warp_apply_word(a.tok + e.y, e.z, nullptr, f, op, lane, a.tab, uq);
+          if (lane == 0) dead += merges;
+        }
+        if (s_direct && my_tiles) {  // oversized tiles / overflowed list: exact thread-per-word pass on global memory
+          __syncthreads();
+          const uint32_t w_lo = a.tile_desc[k_first].x, w_hi = a.tile_desc[k_first + my_tiles].x;
+          dead += process_tile_direct(a.tok, a.off, a.freq, w_lo, w_hi, op, a.tab);
+        }
       }
       // write-through stores (generic proxy) must be ordered before the next iteration's bulk loads
       asm volatile("fence.proxy.async;" ::: "memory");
