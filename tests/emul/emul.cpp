@@ -143,7 +143,8 @@ int emul_encode(const char *model_path, const char *bytes_c, const uint64_t *off
   uint32_t space_id = 0;
   for (int i = 0; i < nc; i++) { uint32_t a, b; f >> a >> b; cp2id[a] = b; if (a == SPACE_CP) space_id = b; }
   std::unordered_map<uint64_t, std::pair<uint32_t, uint32_t>> rt;
-  for (int i = 0; i < nr; i++) { uint32_t x, y, z; f >> x >> y >> z; rt[pair_key(x, y)] = {(uint32_t)i, z}; }
+  std::vector<uint32_t> zs(nr + 1, 0);
+  for (int i = 0; i < nr; i++) { uint32_t x, y, z; f >> x >> y >> z; rt[pair_key(x, y)] = {(uint32_t)i, z}; zs[i] = z; }
   int unk_id, pad_id, bos_id, eos_id;
   f >> unk_id >> pad_id >> bos_id >> eos_id;
   auto rank = [&](uint32_t a, uint32_t b, uint32_t *z) -> uint32_t {
@@ -169,7 +170,7 @@ int emul_encode(const char *model_path, const char *bytes_c, const uint64_t *off
       uint32_t *r = ranks.data() + 1 + (p - lo);
       uint32_t *aux = auxv.data() + 6 * (1 + (p - lo));
       uint32_t owned;
-      uint32_t n = encode_word(s, p, lo, hi, cp2id.data(), space_id, rank, thresh, seed, first_index + si, t, r, aux, &owned);
+      uint32_t n = encode_word(s, p, lo, hi, cp2id.data(), space_id, rank, zs.data(), thresh, seed, first_index + si, t, r, aux, &owned);
       for (uint32_t i = 0; i < n; i++) if ((uint32_t)t[i] & UNK_FLAG) t[i] = unk_id;
       for (uint32_t i = n; i < owned; i++) t[i] = -1;
     }

@@ -29,11 +29,12 @@ constexpr uint32_t NO_RANK = 0xffffffffu;
 struct RuleTab {       // (x,y) -> (rank, z); 16 B per slot, one 128-bit load per probe
   const uint4 *slots;  // .x = x, .y = y, .z = rank, .w = z ; x == 0xffffffff => empty
   uint32_t mask;
+  const uint32_t *zs;  // z by rule index
 };
 
 __device__ __forceinline__ uint32_t rule_rank(const RuleTab &rt, uint32_t a, uint32_t b, uint32_t *z) {
   if ((a | b) & UNK_FLAG) return NO_RANK;
-  uint32_t h = (uint32_t)mix64(pair_key(a, b)) & rt.mask;
+  uint32_t h = rule_hash(a, b) & rt.mask;
   while (true) {
     uint4 s = __ldg(rt.slots + h);
     if (s.x == a && s.y == b) { *z = s.w; return s.z; }
@@ -143,11 +144,11 @@ __global__ void __launch_bounds__(128) encode_words_kernel(EncArgs a, uint64_t n
       int32_t lt[LOCAL_W];
       uint32_t lr[LOCAL_W];
       uint32_t laux[DROPOUT ? 6 * LOCAL_W : 1];
-      n = encode_word(a.bytes, p0, lo, hi, a.cp2id, a.space_id, rank, DROPOUT ? a.drop_thresh : 0, a.seed,
+      n = encode_word(a.bytes, p0, lo, hi, a.cp2id, a.space_id, rank, rt.zs, DROPOUT ? a.drop_thresh : 0, a.seed,
                       a.first_sentence + s, lt, lr, laux, &owned);
       for (uint32_t i = 0; i < n; i++) t[i] = ((uint32_t)lt[i] & UNK_FLAG) ? a.unk_id : lt[i];
     } else {
-      n = encode_word(a.bytes, p0, lo, hi, a.cp2id, a.space_id, rank, DROPOUT ? a.drop_thresh : 0, a.seed,
+      n = encode_word(a.bytes, p0, lo, hi, a.cp2id, a.space_id, rank, rt.zs, DROPOUT ? a.drop_thresh : 0, a.seed,
                       a.first_sentence + s, t, a.ranks + slot0, DROPOUT ? a.aux + 6 * slot0 : nullptr, &owned);
       for (uint32_t i = 0; i < n; i++)
         if ((uint32_t)t[i] & UNK_FLAG) t[i] = a.unk_id;
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(256) gather_ids_kernel(EncArgs a, const unsign
 
 struct yttm_enc {
   yttm_ctx *ctx = nullptr;
-  ytc::DevBuf cp2id, rules;
+  ytc::DevBuf cp2id, rules, rule_z;
   uint32_t rule_mask = 0, space_id = 0;
   int unk = -1, pad = -1, bos = -1, eos = -1;
   // per-call device buffers: two sets, so that the host-buffer entry point can pipeline chunks
@@ -228,7 +229,7 @@ int enc_device(yttm_enc *enc, yttm_enc::Slot *e, const uint8_t *d_bytes, const u
   a.n_words = e->counter.as<unsigned long long>();
   a.n_ids = e->nids.as<unsigned long long>();
   a.cp2id = enc->cp2id.as<uint32_t>();
-  a.rt.slots = enc->rules.as<uint4>(); a.rt.mask = enc->rule_mask;
+  a.rt.slots = enc->rules.as<uint4>(); a.rt.mask = enc->rule_mask; a.rt.zs = enc->rule_z.as<uint32_t>();
   a.space_id = enc->space_id;
   a.unk_id = enc->unk; a.bos_id = enc->bos; a.eos_id = enc->eos;
   a.bos = bos; a.eos = eos; a.reverse = reverse;
@@ -306,7 +307,7 @@ int yttm_enc_create(yttm_ctx *c, const uint32_t *char_cp, const uint32_t *char_i
   std::vector<uint4> slots(cap, make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0));
   for (uint64_t i = 0; i < n_rules; i++) {
     uint32_t x = rules_xyz[3 * i], y = rules_xyz[3 * i + 1], z = rules_xyz[3 * i + 2];
-    uint64_t h = mix64(pair_key(x, y)) & (cap - 1);
+    uint64_t h = rule_hash(x, y) & (cap - 1);
     bool dup = false;
     while (slots[h].x != 0xffffffffu) {
       if (slots[h].x == x && slots[h].y == y) { dup = true; break; }  // rule2id keeps the LAST index (bpe.cpp:1672)
@@ -316,12 +317,16 @@ int yttm_enc_create(yttm_ctx *c, const uint32_t *char_cp, const uint32_t *char_i
     else slots[h] = make_uint4(x, y, (uint32_t)i, z);
   }
   e->rule_mask = (uint32_t)(cap - 1);
-  if (e->cp2id.reserve(CP_LIMIT * 4) != cudaSuccess || e->rules.reserve(cap * 16) != cudaSuccess) {
+  std::vector<uint32_t> zs(n_rules + 1, 0);
+  for (uint64_t i = 0; i < n_rules; i++) zs[i] = rules_xyz[3 * i + 2];
+  if (e->cp2id.reserve(CP_LIMIT * 4) != cudaSuccess || e->rules.reserve(cap * 16) != cudaSuccess ||
+      e->rule_z.reserve((n_rules + 1) * 4) != cudaSuccess) {
     delete e;
     YT_FAIL(c, "yttm_enc_create: out of device memory");
   }
   YT_CUDA(c, cudaMemcpyAsync(e->cp2id.p, tab.data(), CP_LIMIT * 4, cudaMemcpyHostToDevice, c->stream));
   YT_CUDA(c, cudaMemcpyAsync(e->rules.p, slots.data(), cap * 16, cudaMemcpyHostToDevice, c->stream));
+  YT_CUDA(c, cudaMemcpyAsync(e->rule_z.p, zs.data(), (n_rules + 1) * 4, cudaMemcpyHostToDevice, c->stream));
   YT_CUDA(c, cudaStreamSynchronize(c->stream));
   *out = e;
   return 0;
@@ -332,6 +337,7 @@ void yttm_enc_destroy(yttm_enc *e) {
   cudaSetDevice(e->ctx->device);
   e->cp2id.release();
   e->rules.release();
+  e->rule_z.release();
   for (int i = 0; i < 2; i++) {
     e->slot[i].release();
     if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
