@@ -77,7 +77,11 @@ struct WarpQueue {
 };
 __device__ __forceinline__ void uq_drain(WarpQueue &q, unsigned lane, const PairTab &tab) {
   __syncwarp();
-  for (uint32_t i = lane; i < q.n; i += 32) pair_add(tab, q.key[i], q.delta[i]);
+  for (uint32_t i = lane; i < q.n; i += 32) {
+    const long long d = q.delta[i];
+    if (d > 0) pair_add<true>(tab, q.key[i], d);  // additions are mostly pairs with the new token: CAS first
+    else pair_add<false>(tab, q.key[i], d);
+  }
   __syncwarp();
   q.n = 0;
 }

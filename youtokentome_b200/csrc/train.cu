@@ -45,14 +45,21 @@ struct PairTab {
 // A probe sequence longer than PROBE_LIMIT means the table is over-full: the update is dropped
 // and the overflow flag makes the host rebuild a larger table from the (always consistent) tokens.
 constexpr uint64_t PROBE_LIMIT = 512;
+template <bool CAS_FIRST = false>
 __device__ __forceinline__ void pair_add(const PairTab &t, uint64_t key, long long delta) {
   uint64_t h = mix64(key) & t.mask;
   const uint64_t limit = t.mask < PROBE_LIMIT ? t.mask : PROBE_LIMIT;
   for (uint64_t probe = 0; probe <= limit; probe++) {
-    unsigned long long k = __ldcg(t.keys + h);
-    if (k == PK_EMPTY) {
+    unsigned long long k;
+    if (CAS_FIRST) {  // a pair that most likely is new (it holds the token just created): claim without looking
       k = atomicCAS(t.keys + h, PK_EMPTY, (unsigned long long)key);
       if (k == PK_EMPTY) { atomicAdd(t.n_keys, 1u); k = key; }
+    } else {
+      k = __ldcg(t.keys + h);
+      if (k == PK_EMPTY) {
+        k = atomicCAS(t.keys + h, PK_EMPTY, (unsigned long long)key);
+        if (k == PK_EMPTY) { atomicAdd(t.n_keys, 1u); k = key; }
+      }
     }
     if (k == key) { atomicAdd(t.cnts + h, (unsigned long long)delta); return; }
     h = (h + 1) & t.mask;
