@@ -99,3 +99,27 @@ def test_train_argument_errors_match_reference(product, reference):
         assert str(e_new.value) == str(e_ref.value)
     with pytest.raises(ValueError, match="Failed to open file"):
         yttm.BPE.train("/nonexistent/file", path + ".m", 20)
+
+
+def test_cli_host_commands_match_reference_format(product, oracle, reference):
+    """`yttm vocab [--verbose]` and `yttm decode [--ignore_ids]` (host-only paths, no GPU needed):
+    stdout framing of the reference (bpe.cpp:1896-1940, 2016-2028)."""
+    import subprocess
+    import sys
+    m = tmp_model_path()
+    train, test, vocab = synth.GOLDEN_TEXTS["english"]
+    oracle.train(train.encode(), m, vocab)
+    base = [sys.executable, "-m", "youtokentome_b200.yttm_cli"]
+    out = subprocess.run(base + ["vocab", "--model", m], capture_output=True, text=True, cwd=ROOT, check=True).stdout
+    lines = out.rstrip("\n").split("\n")
+    import youtokentome_b200 as yttm
+    assert len(lines) == yttm.BPE(m).vocab_size() and lines[0] == "0\t<PAD>" and lines[4] == "4\t▁"
+    verbose = subprocess.run(base + ["vocab", "--model", m, "--verbose"], capture_output=True, text=True, cwd=ROOT,
+                             check=True).stdout
+    assert "=" in verbose and "+" in verbose
+    ref = reference.encoder(m)
+    ids = ref.encode([test.encode(), b"chrono"], bos=True, eos=True)
+    stdin = "\n".join(" ".join(map(str, s)) for s in ids) + "\n"
+    dec = subprocess.run(base + ["decode", "--model", m, "--ignore_ids", "2,3"], input=stdin, capture_output=True,
+                         text=True, cwd=ROOT, check=True).stdout
+    assert dec.split("\n")[:-1] == [ref.decode([i for i in s if i not in (2, 3)]) for s in ids]

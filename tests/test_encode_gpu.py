@@ -163,3 +163,29 @@ def test_chunked_h2d_pipeline(product, oracle, monkeypatch):
         g = GpuEncoder(m)
         assert g.encode(sents, bos=True, eos=True) == want
         assert g.encode(sents, dropout=0.2, seed=77) == want_drop
+
+
+def test_cli_bpe_encode_roundtrip(product, tmp_path):
+    """test_cli.py of the reference in miniature: `yttm bpe`, `yttm encode --output_type id --bos --eos`
+    (ids separated by a blank, trailing blank before the newline, utils.h:92-103), `yttm decode`."""
+    import random
+    import subprocess
+    import sys
+    from _bind import ROOT
+    rnd = random.Random(19)
+    lines = ["".join(rnd.choice("abcd ") for _ in range(100)) for _ in range(1500)]
+    data = tmp_path / "train.txt"
+    data.write_text("\n".join(lines) + "\n")
+    model = str(tmp_path / "cli.yttm")
+    base = [sys.executable, "-m", "youtokentome_b200.yttm_cli"]
+    subprocess.run(base + ["bpe", "--data", str(data), "--model", model, "--vocab_size", "900", "--coverage", "0.999"],
+                   cwd=ROOT, check=True, capture_output=True)
+    test_lines = ["".join(rnd.choice("abcd ") for _ in range(60)).strip() for _ in range(50)]
+    enc = subprocess.run(base + ["encode", "--model", model, "--output_type", "id", "--bos", "--eos"],
+                         input="\n".join(test_lines) + "\n", capture_output=True, text=True, cwd=ROOT, check=True).stdout
+    rows = enc.split("\n")[:-1]
+    assert len(rows) == len(test_lines) and all(r.endswith(" ") for r in rows)
+    assert all(r.split()[0] == "2" and r.split()[-1] == "3" for r in rows)
+    dec = subprocess.run(base + ["decode", "--model", model, "--ignore_ids", "2,3"], input=enc, capture_output=True,
+                         text=True, cwd=ROOT, check=True).stdout
+    assert dec.split("\n")[:-1] == [" ".join(l.split()) for l in test_lines]
