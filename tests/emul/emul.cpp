@@ -161,7 +161,7 @@ int emul_encode(const char *model_path, const char *bytes_c, const uint64_t *off
     out_offs[si] = pos;
     uint64_t lo = offs[si] - offs[0], hi = offs[si + 1] - offs[0], len = hi - lo;
     std::vector<int32_t> slots(len + 3, -1);
-    std::vector<uint32_t> ranks(len + 3, 0), auxv(6 * (len + 3), 0);
+    std::vector<uint32_t> ranks(len + 3, 0), zcache(len + 3, 0), auxv(6 * (len + 3), 0);
     if (bos) slots[0] = bos_id;
     if (eos) slots[len + 2] = eos_id;
     for (uint64_t p = lo; p < hi; p++) {
@@ -170,7 +170,7 @@ int emul_encode(const char *model_path, const char *bytes_c, const uint64_t *off
       uint32_t *r = ranks.data() + 1 + (p - lo);
       uint32_t *aux = auxv.data() + 6 * (1 + (p - lo));
       uint32_t owned;
-      uint32_t n = encode_word(s, p, lo, hi, cp2id.data(), space_id, rank, zs.data(), thresh, seed, first_index + si, t, r, aux, &owned);
+      uint32_t n = encode_word(s, p, lo, hi, cp2id.data(), space_id, rank, thresh ? nullptr : zcache.data() + 1 + (p - lo), thresh, seed, first_index + si, t, r, aux, &owned);
       for (uint32_t i = 0; i < n; i++) if ((uint32_t)t[i] & UNK_FLAG) t[i] = unk_id;
       for (uint32_t i = n; i < owned; i++) t[i] = -1;
     }

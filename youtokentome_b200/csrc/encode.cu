@@ -29,7 +29,6 @@ constexpr uint32_t NO_RANK = 0xffffffffu;
 struct RuleTab {       // (x,y) -> (rank, z); 16 B per slot, one 128-bit load per probe
   const uint4 *slots;  // .x = x, .y = y, .z = rank, .w = z ; x == 0xffffffff => empty
   uint32_t mask;
-  const uint32_t *zs;  // z by rule index
 };
 
 __device__ __forceinline__ uint32_t rule_rank(const RuleTab &rt, uint32_t a, uint32_t b, uint32_t *z) {
@@ -144,11 +143,13 @@ __global__ void __launch_bounds__(128) encode_words_kernel(EncArgs a, uint64_t n
       int32_t lt[LOCAL_W];
       uint32_t lr[LOCAL_W];
       uint32_t laux[DROPOUT ? 6 * LOCAL_W : 1];
-      n = encode_word(a.bytes, p0, lo, hi, a.cp2id, a.space_id, rank, rt.zs, DROPOUT ? a.drop_thresh : 0, a.seed,
+      // (caching z beside the ranks, or a z-by-rank table, both measured slower than re-probing the
+      // L1-hot slot at merge time: 3.8 ms vs 5.8 / 4.8 ms)
+      n = encode_word(a.bytes, p0, lo, hi, a.cp2id, a.space_id, rank, nullptr, DROPOUT ? a.drop_thresh : 0, a.seed,
                       a.first_sentence + s, lt, lr, laux, &owned);
       for (uint32_t i = 0; i < n; i++) t[i] = ((uint32_t)lt[i] & UNK_FLAG) ? a.unk_id : lt[i];
     } else {
-      n = encode_word(a.bytes, p0, lo, hi, a.cp2id, a.space_id, rank, rt.zs, DROPOUT ? a.drop_thresh : 0, a.seed,
+      n = encode_word(a.bytes, p0, lo, hi, a.cp2id, a.space_id, rank, nullptr, DROPOUT ? a.drop_thresh : 0, a.seed,
                       a.first_sentence + s, t, a.ranks + slot0, DROPOUT ? a.aux + 6 * slot0 : nullptr, &owned);
       for (uint32_t i = 0; i < n; i++)
         if ((uint32_t)t[i] & UNK_FLAG) t[i] = a.unk_id;
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(256) gather_ids_kernel(EncArgs a, const unsign
 
 struct yttm_enc {
   yttm_ctx *ctx = nullptr;
-  ytc::DevBuf cp2id, rules, rule_z;
+  ytc::DevBuf cp2id, rules;
   uint32_t rule_mask = 0, space_id = 0;
   int unk = -1, pad = -1, bos = -1, eos = -1;
   // per-call device buffers: two sets, so that the host-buffer entry point can pipeline chunks
@@ -229,7 +230,7 @@ int enc_device(yttm_enc *enc, yttm_enc::Slot *e, const uint8_t *d_bytes, const u
   a.n_words = e->counter.as<unsigned long long>();
   a.n_ids = e->nids.as<unsigned long long>();
   a.cp2id = enc->cp2id.as<uint32_t>();
-  a.rt.slots = enc->rules.as<uint4>(); a.rt.mask = enc->rule_mask; a.rt.zs = enc->rule_z.as<uint32_t>();
+  a.rt.slots = enc->rules.as<uint4>(); a.rt.mask = enc->rule_mask;
   a.space_id = enc->space_id;
   a.unk_id = enc->unk; a.bos_id = enc->bos; a.eos_id = enc->eos;
   a.bos = bos; a.eos = eos; a.reverse = reverse;
@@ -317,16 +318,12 @@ int yttm_enc_create(yttm_ctx *c, const uint32_t *char_cp, const uint32_t *char_i
     else slots[h] = make_uint4(x, y, (uint32_t)i, z);
   }
   e->rule_mask = (uint32_t)(cap - 1);
-  std::vector<uint32_t> zs(n_rules + 1, 0);
-  for (uint64_t i = 0; i < n_rules; i++) zs[i] = rules_xyz[3 * i + 2];
-  if (e->cp2id.reserve(CP_LIMIT * 4) != cudaSuccess || e->rules.reserve(cap * 16) != cudaSuccess ||
-      e->rule_z.reserve((n_rules + 1) * 4) != cudaSuccess) {
+  if (e->cp2id.reserve(CP_LIMIT * 4) != cudaSuccess || e->rules.reserve(cap * 16) != cudaSuccess) {
     delete e;
     YT_FAIL(c, "yttm_enc_create: out of device memory");
   }
   YT_CUDA(c, cudaMemcpyAsync(e->cp2id.p, tab.data(), CP_LIMIT * 4, cudaMemcpyHostToDevice, c->stream));
   YT_CUDA(c, cudaMemcpyAsync(e->rules.p, slots.data(), cap * 16, cudaMemcpyHostToDevice, c->stream));
-  YT_CUDA(c, cudaMemcpyAsync(e->rule_z.p, zs.data(), (n_rules + 1) * 4, cudaMemcpyHostToDevice, c->stream));
   YT_CUDA(c, cudaStreamSynchronize(c->stream));
   *out = e;
   return 0;
@@ -337,7 +334,6 @@ void yttm_enc_destroy(yttm_enc *e) {
   cudaSetDevice(e->ctx->device);
   e->cp2id.release();
   e->rules.release();
-  e->rule_z.release();
   for (int i = 0; i < 2; i++) {
     e->slot[i].release();
     if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
