@@ -299,37 +299,44 @@ def main():
     # for rewritten words).  Time = device-side timers of the apply phase incl. its tail barrier.
     scan = None
     if rank == 0 and args.scan_tokens > 0:
-        c2 = C.c_void_p()
-        assert L.yttm_ctx_create(local, C.byref(c2)) == 0
-        wl, alpha, iters = 8, 2000, 12
-        n_w = args.scan_tokens // wl
-        rc = L.yttm_train_synth_words(c2, n_w, wl, alpha, 7)
-        assert rc == 0, L.yttm_last_error(c2)
-        rules = np.zeros(3 * iters, dtype=np.uint32)
-        fr = np.zeros(iters, dtype=np.uint64)
-        nd = C.c_uint32(0)
-        assert L.yttm_train_run(c2, 4 + 1 + alpha, iters, rules.ctypes.data, fr.ctypes.data, C.byref(nd)) == 0, \
-            L.yttm_last_error(c2)
-        g = lambda k: L.yttm_stage_ms(c2, k.encode())
-        it = max(g("loop_iters"), 1.0)
-        t_scan = (g("loop_apply") + g("loop_barrier2")) / it          # ms per iteration
-        t_iter = g("merge_loop") / max(nd.value, 1)
-        ab = 4 * args.scan_tokens + 4 * n_w
-        ach = ab / (t_scan * 1e-3) / 1e9
-        # the one-off histogram kernel (atomics-bound, not the per-iteration scan) for reference
-        ms, ab2 = C.c_double(0), C.c_uint64(0)
-        L.yttm_train_scan_once(c2, C.byref(ms), C.byref(ab2))
-        scan = {"bound": "hbm", "kernel": "merge_loop_kernel (apply phase, STREAMING tiles via TMA)",
-                "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
-                "ms_per_iteration_scan": t_scan, "ms_per_iteration_total": t_iter, "iterations": int(nd.value),
-                "resident": int(g("loop_resident")), "algorithmic_bytes_per_launch": ab,
-                "tokens": args.scan_tokens, "words": n_w, "peak_source": peak_src,
-                "phase_ms_per_iter": {k: g(k) / it for k in ["loop_argmax", "loop_barrier1", "loop_apply",
-                                                              "loop_barrier2"]},
-                "table_slots": g("table_capacity"),
-                "initial_histogram": {"kernel": "pair_hist_kernel", "ms": ms.value,
-                                      "GBps": ab2.value / (ms.value * 1e-3) / 1e9}}
-        L.yttm_ctx_destroy(c2)
+        def scan_probe(log2_first):
+            """12 merges over synthetic words of 8 tokens; log2_first = 0: all words start with the same
+            token, every merge rewrites ~16 700 words (mid-training regime); 10: 1024 different initial
+            tokens, a merge rewrites a few dozen words (the bulk of a long training run)."""
+            c2 = C.c_void_p()
+            assert L.yttm_ctx_create(local, C.byref(c2)) == 0
+            wl, alpha, iters = 8, 2000, 12
+            n_w = args.scan_tokens // wl
+            rc = L.yttm_train_synth_words(c2, n_w, wl, alpha | (log2_first << 24), 7)
+            assert rc == 0, L.yttm_last_error(c2)
+            rules = np.zeros(3 * iters, dtype=np.uint32)
+            fr = np.zeros(iters, dtype=np.uint64)
+            nd = C.c_uint32(0)
+            assert L.yttm_train_run(c2, 4 + (1 << log2_first) + alpha, iters, rules.ctypes.data, fr.ctypes.data,
+                                    C.byref(nd)) == 0, L.yttm_last_error(c2)
+            g = lambda k: L.yttm_stage_ms(c2, k.encode())
+            it = max(g("loop_iters"), 1.0)
+            t_scan = (g("loop_apply") + g("loop_barrier2")) / it          # ms per merge
+            ab = 4 * args.scan_tokens + 4 * n_w
+            ach = ab / (t_scan * 1e-3) / 1e9
+            out = {"achieved": ach, "frac": ach / hbm_peak, "ms_per_iteration_scan": t_scan,
+                   "iterations": int(nd.value), "resident": int(g("loop_resident")),
+                   "words_rewritten_per_merge": float(fr[:nd.value].mean() / 4.5) if nd.value else None,
+                   "phase_ms_per_iter": {k: g(k) / it for k in ["loop_argmax", "loop_barrier1", "loop_apply",
+                                                                 "loop_barrier2"]},
+                   "table_slots": g("table_capacity")}
+            ms, ab2 = C.c_double(0), C.c_uint64(0)
+            L.yttm_train_scan_once(c2, C.byref(ms), C.byref(ab2))
+            out["initial_histogram"] = {"kernel": "pair_hist_kernel", "ms": ms.value,
+                                        "GBps": ab2.value / (ms.value * 1e-3) / 1e9}
+            L.yttm_ctx_destroy(c2)
+            return out, ab, n_w
+        heavy, ab, n_w = scan_probe(0)
+        light, _, _ = scan_probe(10)
+        scan = {"bound": "hbm", "kernel": "merge_loop_kernel (apply phase, STREAMING tiles through the TMA ring)",
+                "achieved": heavy["achieved"], "peak": hbm_peak, "unit": "GB/s", "frac": heavy["frac"],
+                "traffic": None, "algorithmic_bytes_per_launch": ab, "tokens": args.scan_tokens, "words": n_w,
+                "peak_source": peak_src, "heavy_merges": heavy, "light_merges": light}
 
     cpu = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:

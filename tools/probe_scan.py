@@ -1,7 +1,7 @@
 """Probe: per-iteration scan of a synthetic packed token buffer >> L2 (STREAMING tiles via TMA)."""
 import ctypes as C, sys, os, json
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from youtokentome_b200 import _lib
 L = _lib.lib()
 T = int(float(sys.argv[1])) if len(sys.argv) > 1 else 256 * 1024 * 1024

@@ -1,7 +1,7 @@
 """Probe: train on a synthetic corpus through the device ABI and print the merge-loop phase split."""
 import ctypes as C, sys, os, time, json
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests"))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from youtokentome_b200 import _lib, synth
 L = _lib.lib()
 which = sys.argv[1] if len(sys.argv) > 1 else "zipf"

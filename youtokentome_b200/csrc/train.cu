@@ -97,13 +97,6 @@ __global__ void __launch_bounds__(512) char_hist_kernel(const uint8_t *__restric
   if (threadIdx.x == 0 && s_units) atomicAdd(hist + CP_LIMIT, s_units);
 }
 
-__global__ void hist_count_nonzero_kernel(const unsigned long long *__restrict__ hist, unsigned long long *out) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool nz = i < CP_LIMIT && hist[i] != 0;
-  unsigned m = __ballot_sync(0xffffffffu, nz);
-  if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
-}
-
 // ------------------------------------------------------------------------------------------
 // phase 2: word split + dedup.  Key word = ((tag24 << 40) | (byte position + 1)) of the first
 // occurrence that claimed the slot; duplicates are verified byte by byte against it.
@@ -283,15 +276,6 @@ __global__ void __launch_bounds__(256) pair_hist_kernel(const uint32_t *__restri
     long long f = (long long)freq[w];
     for_each_pair(tok + o, cap, [&](uint64_t key, uint64_t mult) { pair_add(tab, key, (long long)mult * f); });
   }
-}
-
-__global__ void pair_count_live_kernel(const unsigned long long *__restrict__ cnts, uint64_t cap,
-                                       unsigned long long *out) {
-  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  unsigned long long c = 0;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride) c += cnts[i] != 0;
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
 __global__ void pair_dump_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ cnts,
