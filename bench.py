@@ -203,19 +203,27 @@ def main():
 
     # ---- model: this framework's GPU trainer (hot path a), outside the timed region
     model = os.path.join(CACHE, "model_gpu_%d_r%d.yttm" % (VOCAB, rank))
+    def read_report():
+        rep = (C.c_double * 16)()
+        L.yttm_api_train_report(rep, 16)
+        names = ["n_bytes", "data_len", "n_words", "n_unique", "n_tokens", "n_pairs", "n_merges", "read_s", "h2d_ms",
+                 "char_hist_ms", "word_count_ms", "tokenise_ms", "pair_hist_ms", "merge_loop_ms", "total_s", "launches"]
+        return dict(zip(names, [float(x) for x in rep]))
+
     t0 = time.perf_counter()
     gpu_train(text, VOCAB, 1.0, model=model)           # cold: first CUDA work of the process, clocks still ramping
     cold_wall = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    gpu_train(text, VOCAB, 1.0, model=model)           # warm: what a long-running service sees
-    train_wall = time.perf_counter() - t0
-    rep = (C.c_double * 16)()
-    L.yttm_api_train_report(rep, 16)
-    names = ["n_bytes", "data_len", "n_words", "n_unique", "n_tokens", "n_pairs", "n_merges", "read_s", "h2d_ms",
-             "char_hist_ms", "word_count_ms", "tokenise_ms", "pair_hist_ms", "merge_loop_ms", "total_s", "launches"]
-    train = dict(zip(names, [float(x) for x in rep]))
+    runs = []
+    for _ in range(3):                                 # warm runs; the median is reported (the box is shared: noisy)
+        t0 = time.perf_counter()
+        gpu_train(text, VOCAB, 1.0, model=model)
+        runs.append((time.perf_counter() - t0, read_report()))
+    runs.sort(key=lambda r: r[0])
+    train_wall, train = runs[1]
     train["wall_s"] = train_wall
     train["cold_wall_s"] = cold_wall
+    train["warm_walls_s"] = [r[0] for r in runs]
+    train["merge_loop_ms_runs"] = [r[1]["merge_loop_ms"] for r in runs]
     train["GBps_e2e"] = len(text) / train_wall / 1e9
     train["us_per_merge"] = train["merge_loop_ms"] * 1e3 / max(train["n_merges"], 1)
 
