@@ -215,9 +215,21 @@ static void rename_tokens(flat_hash_map<uint32_t, uint32_t> &char2id, std::vecto
 static Status train_on_buffer(const char *text, uint64_t n, int n_tokens, const std::string &output_file,
                               BpeConfig cfg, BPEState *out_state) {
   double t_start = now_s();
-  yttm_ctx *ctx = nullptr;
-  if (yttm_ctx_create(default_device(), &ctx)) return Status(1, yttm_last_error(nullptr));
-  struct Guard { yttm_ctx *c; ~Guard() { yttm_ctx_destroy(c); } } guard{ctx};
+  // one training context per host thread and device, kept between calls: its device buffers
+  // (corpus, word table, packed words, pair table) are reused instead of cudaMalloc'ed / freed
+  // on every train_bpe (release_training_cache() gives the memory back)
+  struct Cache {  // deliberately not destroyed at thread / process exit (no CUDA calls during teardown)
+    yttm_ctx *ctx = nullptr;
+    int device = -1;
+  };
+  static thread_local Cache cache;
+  if (cache.ctx && cache.device != default_device()) { yttm_ctx_destroy(cache.ctx); cache.ctx = nullptr; }
+  if (!cache.ctx) {
+    if (yttm_ctx_create(default_device(), &cache.ctx)) { cache.ctx = nullptr; return Status(1, yttm_last_error(nullptr)); }
+    cache.device = default_device();
+  }
+  yttm_ctx *ctx = cache.ctx;
+  const uint64_t launches0 = yttm_launch_count(ctx);
 
   if (yttm_train_load_corpus(ctx, text, n, 0)) return Status(1, ctx_err(ctx));
   uint64_t data_len = 0, n_distinct = 0;
@@ -274,7 +286,7 @@ static Status train_on_buffer(const char *text, uint64_t n, int n_tokens, const 
   r.h2d_ms = yttm_stage_ms(ctx, "h2d"); r.char_hist_ms = yttm_stage_ms(ctx, "char_hist");
   r.word_count_ms = yttm_stage_ms(ctx, "word_count"); r.tokenise_ms = yttm_stage_ms(ctx, "tokenise");
   r.pair_hist_ms = yttm_stage_ms(ctx, "pair_hist"); r.merge_loop_ms = yttm_stage_ms(ctx, "merge_loop");
-  r.launches = yttm_launch_count(ctx);
+  r.launches = yttm_launch_count(ctx) - launches0;
   r.total_s = now_s() - t_start;
   return Status();
 }
