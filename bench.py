@@ -191,7 +191,8 @@ def main():
     torch.cuda.set_device(local)
     os.environ["YTTM_DEVICE"] = str(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (no "NCCL version" banner)
+        # keep stdout to the one JSON line: NCCL's banner / debug output goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if not os.path.exists(_lib.LIB_PATH):
         _lib.build()
