@@ -26,6 +26,7 @@ struct LoopArgs {
   uint32_t stream_tok_cap;     // STREAMING: token / word capacity of ONE of the two pipeline stages
   uint32_t stream_word_cap;
   uint32_t n_stage;            // STREAMING: pipeline depth
+  uint32_t dbg;                // experiments only (env YTTM_DBG): 1 = consumers skip the scan, 2 = scalar scan
   uint4 *defer;                // STREAMING: per-block lists of words to rewrite after the tile scan
   uint32_t defer_cap;          // entries per block
   uint32_t n_tiles;
@@ -484,27 +485,50 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
           if (!staged(d0, d1)) { if (cw == 0 && lane == 0) s_direct = 1; continue; }  // oversized: direct pass below
           mbar_wait(&s_full[st], (fphase >> st) & 1u);
           fphase ^= 1u << st;
-          const uint32_t *tk = stok + st * stage_words + (d0.y - win_lo(d0.y));
-          const uint32_t *of = stok + st * stage_words + a.stream_tok_cap + (d0.x - win_lo(d0.x));
+          const uint32_t *stg = stok + st * stage_words;     // 16-byte aligned window of the stage
+          const uint32_t head = d0.y - win_lo(d0.y);         // 0..3 tokens of the previous tile in front
+          const uint32_t *tk = stg + head;
+          const uint32_t *of = stg + a.stream_tok_cap + (d0.x - win_lo(d0.x));
           const uint32_t span = d1.y - d0.y, nw = d1.x - d0.x, obase = d0.y;
-          for (uint32_t base = cw * 32; base < span; base += ncw * 32) {
-            const uint32_t i = base + lane;
-            const bool hit = i + 1 < span && tk[i] == op.x && tk[i + 1] == op.y;
-            if (!__ballot_sync(0xffffffffu, hit)) continue;
-            if (hit) {
-              uint32_t lo = 0, hi = nw;  // largest w with of[w] - obase <= i
-              while (hi - lo > 1) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (of[mid] - obase <= i) lo = mid; else hi = mid;
-              }
-              const uint32_t o = of[lo] - obase, wcap = of[lo + 1] - obase - o;
-              bool first = true;  // only the first hit of a word reports it
-              for (uint32_t q2 = o; q2 < i; q2++)
-                if (tk[q2] == op.x && tk[q2 + 1] == op.y) { first = false; break; }
-              if (first) {
-                const uint32_t slot = atomicAdd(&s_defer_n, 1u);
-                if (slot < a.defer_cap) defer[slot] = make_uint4(d0.x + lo, obase + o, wcap, 0u);
-                else s_direct = 1;  // list full: the direct pass below picks the rest up
+          auto report = [&](uint32_t i) {  // token i of the tile starts an (x,y) occurrence
+            uint32_t lo = 0, hi = nw;      // largest w with of[w] - obase <= i
+            while (hi - lo > 1) {
+              const uint32_t mid = (lo + hi) >> 1;
+              if (of[mid] - obase <= i) lo = mid; else hi = mid;
+            }
+            const uint32_t o = of[lo] - obase, wcap = of[lo + 1] - obase - o;
+            for (uint32_t q2 = o; q2 < i; q2++)  // only the first hit of a word reports it
+              if (tk[q2] == op.x && tk[q2 + 1] == op.y) return;
+            const uint32_t slot = atomicAdd(&s_defer_n, 1u);
+            if (slot < a.defer_cap) defer[slot] = make_uint4(d0.x + lo, obase + o, wcap, 0u);
+            else s_direct = 1;  // list full: the direct pass below picks the rest up
+          };
+          if (a.dbg & 1u) {
+          } else if (a.dbg & 2u) {
+            for (uint32_t base = cw * 32; base < span; base += ncw * 32) {
+              const uint32_t i = base + lane;
+              const bool hit = i + 1 < span && tk[i] == op.x && tk[i + 1] == op.y;
+              if (!__ballot_sync(0xffffffffu, hit)) continue;
+              if (hit) report(i);
+            }
+          } else {
+            // four tokens per lane from one 16-byte shared load; the token after them comes from the
+            // next lane.  p = position in the aligned window; occurrence p is inside the tile iff
+            // head <= p and p + 1 < total (a word-initial token is never y, so none straddles tiles)
+            const uint32_t total = head + span;
+            for (uint32_t base = cw * 128; base < total; base += ncw * 128) {
+              const uint32_t p = base + lane * 4;
+              uint4 v = make_uint4(~0u, ~0u, ~0u, ~0u);
+              if (p < total) v = *reinterpret_cast<const uint4 *>(stg + p);
+              uint32_t nxt = __shfl_down_sync(0xffffffffu, v.x, 1);
+              if (lane == 31) nxt = p + 4 < total ? stg[p + 4] : ~0u;
+              uint32_t m = (v.x == op.x && v.y == op.y ? 1u : 0u) | (v.y == op.x && v.z == op.y ? 2u : 0u) |
+                           (v.z == op.x && v.w == op.y ? 4u : 0u) | (v.w == op.x && nxt == op.y ? 8u : 0u);
+              if (!__ballot_sync(0xffffffffu, m)) continue;
+              while (m) {
+                const uint32_t pk = p + (uint32_t)__ffs(m) - 1u;
+                m &= m - 1u;
+                if (pk >= head && pk + 1 < total) report(pk - head);
               }
             }
           }

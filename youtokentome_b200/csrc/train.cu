@@ -448,6 +448,8 @@ int plan_tiles(yttm_ctx *c, LoopArgs *a) {
   a->defer = nullptr;
   a->defer_cap = 0;
   a->n_stage = (uint32_t)c->loop_stages;
+  a->dbg = 0;
+  if (const char *e = std::getenv("YTTM_DBG")) a->dbg = (uint32_t)std::atoi(e);
   c->loop_resident = 0;
   if (c->n_words == 0 || c->n_slots == 0) return 0;
   YT_CUDA(c, c->counters.reserve(64));
@@ -866,7 +868,6 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
     // word (words of up to q/4 slots stay on the shared-memory path) and at most q/2 + 1 offsets
     {
       int n_stage = 2;  // measured best on B200 (2: 46 %, 3: 44 %, 4: 41 %, 6: 34 %, 8: 30 % of HBM peak)
-      if (const char *e = std::getenv("YTTM_STAGES")) n_stage = std::max(2, std::min(MAX_STAGES, std::atoi(e)));
       if (const char *e = std::getenv("YTTM_STAGES")) n_stage = std::max(2, std::min(MAX_STAGES, std::atoi(e)));
 
       const uint32_t per_stage = (uint32_t)(tile_bytes / n_stage / 4) & ~3u;  // uint32 per stage
