@@ -164,10 +164,34 @@ def reference_arm(args, rank, world):
                       "step": "reference encode_as_ids on %d sentences, %d threads" % (sample, cores)},
            "cpu_baseline": base,
            "e2e": {"value": val, "unit": "Msent/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout must carry the ONE JSON line and nothing else, but libraries write to fd 1 behind
+    Python's back (NCCL prints its version banner there): point fd 1 at stderr for the whole run
+    and keep a private duplicate of the real stdout for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(out):
+    line = (json.dumps(out) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, line)
+    else:
+        os.write(_REAL_STDOUT, line)
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -191,8 +215,6 @@ def main():
     torch.cuda.set_device(local)
     os.environ["YTTM_DEVICE"] = str(local)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL's banner / debug output goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if not os.path.exists(_lib.LIB_PATH):
         _lib.build()
@@ -299,8 +321,11 @@ def main():
     roofline = {"bound": "hbm", "kernel": {"enc_words": "encode_words_kernel", "enc_find": "find_words_kernel",
                                            "enc_gather": "gather_ids_kernel", "enc_scan": "scan"}[dom],
                 "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak if ach else None,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
-                "kernel_ms": kern}
+                # dram__bytes_read.sum + dram__bytes_write.sum of ONE ncu --set full capture of this kernel on
+                # this workload (profiles/r01_prof_encode_words.raw.csv: 591.2 MB + 468.0 MB); not re-measured here
+                "traffic": 1059194624 if dom == "enc_words" and n_sent == N_SENT else None,
+                "traffic_source": "profiles/r01_prof_encode_words.raw.csv (ncu --set full, same workload)",
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": algo, "kernel_ms": kern}
 
     # ---- hot path (a): the per-merge-iteration scan of the packed token buffer, on a buffer >> L2
     # (rank 0 only).  Each iteration of merge_loop_kernel streams every token slot and word offset
@@ -344,7 +369,13 @@ def main():
         light, _, _ = scan_probe(10)
         scan = {"bound": "hbm", "kernel": "merge_loop_kernel (apply phase, STREAMING tiles through the TMA ring)",
                 "achieved": heavy["achieved"], "peak": hbm_peak, "unit": "GB/s", "frac": heavy["frac"],
-                "traffic": None, "algorithmic_bytes_per_launch": ab, "tokens": args.scan_tokens, "words": n_w,
+                "traffic": None,
+                # the ncu capture is of a smaller probe (one launch = 6 merges over 64 Mi tokens, arg-max sweeps
+                # of the 16 Mi-slot table included), so it is reported beside, not as, this launch's traffic
+                "traffic_ncu": {"capture": "profiles/r01_prof_merge_loop_stream_v4.raw.csv", "tokens": 67108864,
+                                "merges": 6, "dram_bytes": 2914580920, "algorithmic_bytes_scan": 6 * 301989888,
+                                "algorithmic_bytes_argmax_sweep": 6 * 134217728},
+                "algorithmic_bytes_per_launch": ab, "tokens": args.scan_tokens, "words": n_w,
                 "peak_source": peak_src, "heavy_merges": heavy, "light_merges": light}
 
     cpu = None
@@ -379,7 +410,7 @@ def main():
                        "d2h_bytes_per_step": 4 * n_ids + 8 * (n_sent + 1), "ms_per_step": sec_h / args.steps * 1e3},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                "roofline_train_scan": scan, "train": train, "cpu_baseline": cpu}
-        print(json.dumps(out))
+        emit(out)
     L.yttm_api_close(h)
     if world > 1:
         dist.destroy_process_group()

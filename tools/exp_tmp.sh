@@ -1,7 +1,2 @@
 mkdir -p gpurun_out
-{
-timeout 300 python -m pytest tests/test_train_gpu.py -x -q -m gpu -k "stream or oversized or zipf or stress" 2>&1 | tail -3
-for d in 0 2 1; do for lf in 0 6; do
-echo "DBG=$d lf=$lf"; YTTM_DBG=$d timeout 120 python tools/probe_scan.py 268435456 8 12 $lf
-done; done
-} > gpurun_out/exp_vec.log 2>&1
+timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 5 --warmup 3 --scan-tokens 0 > gpurun_out/bench_n2_v2.json 2> gpurun_out/bench_n2_v2.err; echo rc=$? > gpurun_out/bench_n2_v2.rc

@@ -40,7 +40,9 @@ struct YtLoopCtl {
   uint32_t overflow;          // a probe sequence wrapped (fatal)
   unsigned long long dead;    // token slots tombstoned since the last compaction
   unsigned long long slots;   // token slots at the last compaction
-  unsigned long long t_phase[4];  // ns spent by block 0 in: arg-max sweep, barrier 1, apply scan, barrier 2
+  unsigned long long t_phase[8];  // ns spent by block 0 in: arg-max sweep, barrier 1, apply scan, barrier 2;
+                                  // with YTTM_DBG&8 also, over ALL blocks: [4] max apply, [5] mean apply, [6] max apply before the table drain
+  unsigned long long blk[2][3];   // per-iteration scratch of [4..6] (double-buffered by iteration parity)
   unsigned long long iters;       // iterations those times cover
 };
 
@@ -86,7 +88,7 @@ struct yttm_ctx {
   int loop_smem = 0, loop_resident = 0, loop_stages = 2;
   uint32_t loop_tok_cap = 0, loop_word_cap = 0, loop_stream_q = 0, loop_stream_tok_cap = 0, loop_stream_word_cap = 0;
   int loop_blocks = 0, loop_threads = 0;
-  double loop_phase_ms[4] = {0, 0, 0, 0};
+  double loop_phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   uint64_t loop_iters = 0, loop_relaunches = 0;
 
   yttm_train_stats stats{};

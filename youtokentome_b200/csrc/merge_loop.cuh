@@ -17,6 +17,8 @@
 //   4. grid barrier.
 #pragma once
 
+constexpr int SWEEP_UNROLL = 8;  // arg-max sweep: table counts in flight per thread
+
 struct LoopArgs {
   uint32_t *tok;
   const uint32_t *off;
@@ -26,7 +28,7 @@ struct LoopArgs {
   uint32_t stream_tok_cap;     // STREAMING: token / word capacity of ONE of the two pipeline stages
   uint32_t stream_word_cap;
   uint32_t n_stage;            // STREAMING: pipeline depth
-  uint32_t dbg;                // experiments only (env YTTM_DBG): 1 = consumers skip the scan, 2 = scalar scan
+  uint32_t dbg;                // diagnostics (env YTTM_DBG): 1 = consumers skip the scan, 2 = scalar scan, 8 = per-block apply timers
   uint4 *defer;                // STREAMING: per-block lists of words to rewrite after the tile scan
   uint32_t defer_cap;          // entries per block
   uint32_t n_tiles;
@@ -193,51 +195,55 @@ __device__ __forceinline__ uint32_t warp_apply_word(uint32_t *st, uint32_t cap, 
 // the second element of an in-word pair — is never a word-initial token; tail padding (DEAD)
 // matches nothing.  Each hit is mapped to its word (binary search in the offsets), the word is
 // claimed once through a bitmap, and claimed words are rewritten by the whole warp.
-__device__ __forceinline__ unsigned long long process_tile(uint32_t *stok, const uint32_t *soff, uint32_t obase,
-                                                           uint32_t nw, uint32_t span, uint32_t *claim,
-                                                           uint32_t *gtok, const uint64_t *gfreq, const MergeOp &op,
-                                                           const PairTab &tab, WarpQueue &q, uint4 *defer = nullptr,
-                                                           uint32_t *defer_n = nullptr, uint32_t defer_cap = 0,
-                                                           uint32_t w_abs0 = 0) {
+__device__ __forceinline__ unsigned long long process_tile(uint32_t *stok, const uint32_t *soff, uint32_t nw,
+                                                           uint32_t span, uint32_t *claim, const uint64_t *gfreq,
+                                                           const MergeOp &op, const PairTab &tab, WarpQueue &q) {
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   unsigned long long dead = 0;
-  for (uint32_t base = wid * 32; base < span; base += nwarp * 32) {
-    const uint32_t i = base + lane;
-    const bool hit = i + 1 < span && stok[i] == op.x && stok[i + 1] == op.y;
-    if (!__ballot_sync(0xffffffffu, hit)) continue;
-    uint32_t w = 0, o = 0, cap = 0;
-    bool own = false;
-    if (hit) {
-      uint32_t lo = 0, hi = nw;  // largest w with soff[w] - obase <= i
-      while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (soff[mid] - obase <= i) lo = mid; else hi = mid;
-      }
-      w = lo;
-      o = soff[w] - obase;
-      cap = soff[w + 1] - obase - o;
-      own = !((atomicOr(&claim[w >> 5], 1u << (w & 31)) >> (w & 31)) & 1u);
-      if (own && defer) {  // STREAMING: rewrite later, out of the TMA pipeline's way (see merge_loop_kernel)
-        const uint32_t slot = atomicAdd(defer_n, 1u);
-        if (slot < defer_cap) {
-          defer[slot] = make_uint4(w_abs0 + w, obase + o, cap, 0u);
-          own = false;
+  // a lane compares four tokens from one 16-byte shared load (stok is 16-byte aligned, its capacity a
+  // multiple of 4); the token after them comes from the next lane
+  for (uint32_t base = wid * 128; base < span; base += nwarp * 128) {
+    const uint32_t p = base + lane * 4;
+    uint4 v = make_uint4(DEAD, DEAD, DEAD, DEAD);
+    if (p < span) v = *reinterpret_cast<const uint4 *>(stok + p);
+    uint32_t nxt = __shfl_down_sync(0xffffffffu, v.x, 1);
+    if (lane == 31) nxt = p + 4 < span ? stok[p + 4] : DEAD;
+    uint32_t m = (v.x == op.x && v.y == op.y ? 1u : 0u) | (v.y == op.x && v.z == op.y ? 2u : 0u) |
+                 (v.z == op.x && v.w == op.y ? 4u : 0u) | (v.w == op.x && nxt == op.y ? 8u : 0u);
+    if (p + 4 >= span) m &= span > p + 1 ? (1u << (span - p - 1)) - 1u : 0u;  // occurrence i needs i + 1 < span
+    while (__ballot_sync(0xffffffffu, m != 0)) {  // one round per hit of the busiest lane (almost always one)
+      uint32_t w = 0, o = 0, cap = 0;
+      bool own = false;
+      if (m) {
+        const uint32_t i = p + (uint32_t)__ffs(m) - 1u;
+        m &= m - 1u;
+        // re-read: an earlier round (or another warp) may already have rewritten this word
+        if (stok[i] == op.x && stok[i + 1] == op.y) {
+          uint32_t lo = 0, hi = nw;  // largest w with soff[w] <= i
+          while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (soff[mid] <= i) lo = mid; else hi = mid;
+          }
+          w = lo;
+          o = soff[w];
+          cap = soff[w + 1] - o;
+          own = !((atomicOr(&claim[w >> 5], 1u << (w & 31)) >> (w & 31)) & 1u);
         }
       }
-    }
-    const long long fw = own ? (long long)gfreq[w] : 0;  // owners fetch their word's frequency together
-    unsigned mask = __ballot_sync(0xffffffffu, own);
-    while (mask) {
-      const int j = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const uint32_t oj = __shfl_sync(0xffffffffu, o, j), cj = __shfl_sync(0xffffffffu, cap, j);
-      const uint32_t wj = __shfl_sync(0xffffffffu, w, j);
-      const long long f = __shfl_sync(0xffffffffu, fw, j);
-      dead += warp_apply_word(stok + oj, cj, gtok ? gtok + oj : nullptr, f, op, lane, tab, q);
-      if (lane == 0 && !defer) atomicAnd(&claim[wj >> 5], ~(1u << (wj & 31)));  // bitmap all zero between tiles
+      const long long fw = own ? (long long)gfreq[w] : 0;  // owners fetch their word's frequency together
+      unsigned mask = __ballot_sync(0xffffffffu, own);
+      while (mask) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const uint32_t oj = __shfl_sync(0xffffffffu, o, j), cj = __shfl_sync(0xffffffffu, cap, j);
+        const uint32_t wj = __shfl_sync(0xffffffffu, w, j);
+        const long long f = __shfl_sync(0xffffffffu, fw, j);
+        dead += warp_apply_word(stok + oj, cj, nullptr, f, op, lane, tab, q);
+        if (lane == 0) atomicAnd(&claim[wj >> 5], ~(1u << (wj & 31)));  // bitmap all zero between tiles
+      }
     }
   }
-  return lane == 0 ? dead : 0ull;  // pending table updates stay queued across tiles (drained by the caller)
+  return lane == 0 ? dead : 0ull;  // pending table updates stay queued (drained by the caller)
 }
 
 // Oversized tile (a word longer than the shared buffer): thread per word straight on global memory.
@@ -306,6 +312,8 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
   __shared__ Best s_best;
   __shared__ unsigned long long s_dead;
   __shared__ uint32_t s_defer_n, s_direct;
+  __shared__ unsigned long long s_tpre;
+  const bool dbgt = (a.dbg & 8u) != 0;  // per-block apply-phase timing (diagnostic)
   // dynamic shared memory: [update queues: 32 warps x UQ_CAP x 16 B][tile tokens][tile offsets]
   unsigned long long *uq_keys = reinterpret_cast<unsigned long long *>(yt_dyn_smem);
   long long *uq_deltas = reinterpret_cast<long long *>(uq_keys + 32 * UQ_CAP);
@@ -354,12 +362,23 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
     // ---------------- arg-max over the table under MergeCandidate::operator< (bpe.cpp:110-126)
     unsigned long long tq0 = gtid == 0 ? gtimer() : 0, tq1 = 0, tq2 = 0, tq3 = 0;
     Best b{0, 0, 0};
-    for (uint64_t i = gtid; i < cap; i += gstride) {
-      unsigned long long c = __ldcg(a.tab.cnts + i);
-      if (c != 0 && c >= b.c) {
-        unsigned long long k = __ldcg(a.tab.keys + i);
-        Best cand{c, pair_prio((uint32_t)(k >> 32), (uint32_t)k), i};
-        if (better(cand, b)) b = cand;
+    // the counts of SWEEP_UNROLL slots are requested together: one L2 round trip per batch instead of
+    // one per slot (a thread owns cap / (148 * 1024) slots, 7 at the 1 M-slot table of the 100 MB corpus)
+    for (uint64_t i0 = gtid; i0 < cap; i0 += gstride * SWEEP_UNROLL) {
+      unsigned long long c[SWEEP_UNROLL];
+#pragma unroll
+      for (int u = 0; u < SWEEP_UNROLL; u++) {
+        const uint64_t i = i0 + (uint64_t)u * gstride;
+        c[u] = i < cap ? __ldcg(a.tab.cnts + i) : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < SWEEP_UNROLL; u++) {
+        if (c[u] != 0 && c[u] >= b.c) {
+          const uint64_t i = i0 + (uint64_t)u * gstride;
+          const unsigned long long k = __ldcg(a.tab.keys + i);
+          Best cand{c[u], pair_prio((uint32_t)(k >> 32), (uint32_t)k), i};
+          if (better(cand, b)) b = cand;
+        }
       }
     }
     b = warp_best(b);
@@ -377,6 +396,7 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
     if (gtid == 0) tq1 = gtimer();
     grid.sync();
     if (gtid == 0) tq2 = gtimer();
+    const unsigned long long tw0 = dbgt && lane == 0 ? gtimer() : 0;
     {  // every block reduces the per-block winners redundantly: one entry per thread, one round trip
       Best v{0, 0, 0};
       for (unsigned j = threadIdx.x; j < gridDim.x; j += blockDim.x) {
@@ -392,7 +412,7 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
       if (wid == 0) {
         Best u = lane < used_warps ? s_warp[lane] : Best{0, 0, 0};
         u = warp_best(u);
-        if (lane == 0) { s_best = u; s_dead = 0; }
+        if (lane == 0) { s_best = u; s_dead = 0; s_tpre = 0; }
       }
     }
     __syncthreads();
@@ -419,7 +439,7 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
     // ---------------- apply x y -> z
     unsigned long long dead = 0;
     if (a.resident) {
-      if (rw1 > rw0) dead = process_tile(stok, soff, 0, rw1 - rw0, soff[rw1 - rw0], s_claim, nullptr,
+      if (rw1 > rw0) dead = process_tile(stok, soff, rw1 - rw0, soff[rw1 - rw0], s_claim,
                                            reinterpret_cast<const uint64_t *>(sfreq), op, a.tab, uq);
     } else {
       // STREAMING: this block owns a contiguous chunk of tiles that flows through an n_stage ring of
@@ -512,18 +532,22 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
               if (hit) report(i);
             }
           } else {
-            // four tokens per lane from one 16-byte shared load; the token after them comes from the
+            // eight tokens per lane from two 16-byte shared loads; the token after them comes from the
             // next lane.  p = position in the aligned window; occurrence p is inside the tile iff
-            // head <= p and p + 1 < total (a word-initial token is never y, so none straddles tiles)
+            // head <= p and p + 1 < total (a word-initial token is never y, so none straddles tiles).
+            // Measured on B200, 2 stages: scalar 45 %, 4 per lane 74-87 %, 8 per lane 75-92 % of HBM peak.
             const uint32_t total = head + span;
-            for (uint32_t base = cw * 128; base < total; base += ncw * 128) {
-              const uint32_t p = base + lane * 4;
-              uint4 v = make_uint4(~0u, ~0u, ~0u, ~0u);
+            for (uint32_t base = cw * 256; base < total; base += ncw * 256) {
+              const uint32_t p = base + lane * 8;
+              uint4 v = make_uint4(~0u, ~0u, ~0u, ~0u), u = v;
               if (p < total) v = *reinterpret_cast<const uint4 *>(stg + p);
+              if (p + 4 < total) u = *reinterpret_cast<const uint4 *>(stg + p + 4);
               uint32_t nxt = __shfl_down_sync(0xffffffffu, v.x, 1);
-              if (lane == 31) nxt = p + 4 < total ? stg[p + 4] : ~0u;
+              if (lane == 31) nxt = p + 8 < total ? stg[p + 8] : ~0u;
               uint32_t m = (v.x == op.x && v.y == op.y ? 1u : 0u) | (v.y == op.x && v.z == op.y ? 2u : 0u) |
-                           (v.z == op.x && v.w == op.y ? 4u : 0u) | (v.w == op.x && nxt == op.y ? 8u : 0u);
+                           (v.z == op.x && v.w == op.y ? 4u : 0u) | (v.w == op.x && u.x == op.y ? 8u : 0u) |
+                           (u.x == op.x && u.y == op.y ? 16u : 0u) | (u.y == op.x && u.z == op.y ? 32u : 0u) |
+                           (u.z == op.x && u.w == op.y ? 64u : 0u) | (u.w == op.x && nxt == op.y ? 128u : 0u);
               if (!__ballot_sync(0xffffffffu, m)) continue;
               while (m) {
                 const uint32_t pk = p + (uint32_t)__ffs(m) - 1u;
@@ -556,15 +580,28 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
       // write-through stores (generic proxy) must be ordered before the next iteration's bulk loads
       asm volatile("fence.proxy.async;" ::: "memory");
     }
+    if (dbgt && lane == 0) atomicMax(&s_tpre, gtimer() - tw0);
     if (uq.n) uq_drain(uq, lane, a.tab);  // one batch of table updates per warp and iteration
     for (int o = 16; o > 0; o >>= 1) dead += __shfl_xor_sync(0xffffffffu, dead, o);
     if (lane == 0 && dead) atomicAdd(&s_dead, dead);
     __syncthreads();
     if (threadIdx.x == 0 && s_dead) atomicAdd(&a.ctl->dead, s_dead);
+    if (dbgt && threadIdx.x == 0) {
+      const unsigned long long t = gtimer() - tw0;
+      atomicMax(&a.ctl->blk[it & 1][0], t);
+      atomicAdd(&a.ctl->blk[it & 1][1], t);
+      atomicMax(&a.ctl->blk[it & 1][2], s_tpre);
+    }
     if (gtid == 0) tq3 = gtimer();
     grid.sync();
     if (gtid == 0) {
       unsigned long long tq4 = gtimer();
+      if (dbgt) {
+        a.ctl->t_phase[4] += __ldcg(&a.ctl->blk[it & 1][0]);
+        a.ctl->t_phase[5] += __ldcg(&a.ctl->blk[it & 1][1]) / gridDim.x;
+        a.ctl->t_phase[6] += __ldcg(&a.ctl->blk[it & 1][2]);
+        a.ctl->blk[it & 1][0] = 0; a.ctl->blk[it & 1][1] = 0; a.ctl->blk[it & 1][2] = 0;
+      }
       a.ctl->t_phase[0] += tq1 - tq0; a.ctl->t_phase[1] += tq2 - tq1;
       a.ctl->t_phase[2] += tq3 - tq2; a.ctl->t_phase[3] += tq4 - tq3;
       a.ctl->iters += 1;

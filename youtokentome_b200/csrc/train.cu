@@ -548,8 +548,9 @@ void yttm_ctx_destroy(yttm_ctx *c) {
 const char *yttm_last_error(const yttm_ctx *c) { return c ? c->err.c_str() : g_yttm_create_error.c_str(); }
 
 double yttm_stage_ms(const yttm_ctx *c, const char *stage) {
-  static const char *ph[] = {"loop_argmax", "loop_barrier1", "loop_apply", "loop_barrier2"};
-  for (int i = 0; i < 4; i++)
+  static const char *ph[] = {"loop_argmax", "loop_barrier1", "loop_apply", "loop_barrier2",
+                             "loop_apply_blkmax", "loop_apply_blkmean", "loop_predrain_blkmax"};
+  for (int i = 0; i < 7; i++)
     if (!std::strcmp(stage, ph[i])) return c->loop_phase_ms[i];
   if (!std::strcmp(stage, "loop_iters")) return (double)c->loop_iters;
   if (!std::strcmp(stage, "loop_launches")) return (double)c->loop_relaunches;
@@ -895,7 +896,8 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
   YT_CUDA(c, cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   YT_CUDA(c, cudaStreamSynchronize(c->stream));
   h.n_done = 0; h.stop = 0; h.iters = 0;
-  for (int i = 0; i < 4; i++) h.t_phase[i] = 0;
+  for (int i = 0; i < 8; i++) h.t_phase[i] = 0;
+  for (int i = 0; i < 6; i++) (&h.blk[0][0])[i] = 0;
   YT_CUDA(c, cudaMemcpyAsync(ctl, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
   c->loop_relaunches = 0;
   ytc::timer_begin(c, "merge_loop");
@@ -938,7 +940,7 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
     YT_CUDA(c, cudaMemcpyAsync(ctl, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
   }
   ytc::timer_end(c, "merge_loop");
-  for (int i = 0; i < 4; i++) c->loop_phase_ms[i] = (double)h.t_phase[i] * 1e-6;
+  for (int i = 0; i < 8; i++) c->loop_phase_ms[i] = (double)h.t_phase[i] * 1e-6;
   c->loop_iters = h.iters;
   *n_done_out = h.n_done;
   if (h.n_done) {
