@@ -396,6 +396,17 @@ def main():
                                       "kind": "reference", "sample": "learn_bpe_from_string on the same %d MB"
                                                                      % (len(text) // 1_000_000)}
             train["speedup_vs_cpu_reference_wall"] = sec / train["wall_s"]
+        # SURVEY.md §8d also asks for the single-thread figures (bounded: 50 k sentences / one training run)
+        try:
+            one, _ = cpu_reference_encode(model, buf, offs, 1, min(n_sent, 50_000))
+            cpu["one_thread"] = {"value": one["value"], "unit": "Msent/s", "sample": one["sample"]}
+            if _bind.have_reference("prod"):
+                sec1 = _bind.Reference("prod").train(text, os.path.join(CACHE, "model_refprod1.yttm"), VOCAB, 1.0,
+                                                     n_threads=1)
+                train["cpu_reference_1thread"] = {"seconds": sec1, "GBps": len(text) / sec1 / 1e9, "threads": 1,
+                                                  "kind": "reference"}
+        except Exception as e:  # the extra legs must never cost the JSON line
+            cpu["one_thread"] = {"error": repr(e)}
 
     if rank == 0:
         out = {"metric": "encode throughput, 1M x 128 B synthetic sentences, vocab 32k", "value": value,
