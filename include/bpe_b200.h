@@ -113,6 +113,11 @@ flat_hash_map<uint32_t, uint32_t> compute_alphabet_helper(const flat_hash_map<ui
                                                           std::unordered_set<uint32_t> &removed_chars,
                                                           const BpeConfig &bpe_config);
 
+// Order of the char2id lines in the reference's model file (BPEState::dump, utils.cpp:57-59, iterates a
+// ska::flat_hash_map): `filled` = code points in the order the reference inserted them (U+2581, then by
+// ascending id) -> the same code points in the order the reference's dump lists them.  Host only.
+std::vector<uint32_t> reference_dump_order(const std::vector<uint32_t> &filled);
+
 // Device selection for this process: YTTM_DEVICE env var, else LOCAL_RANK, else 0.
 int default_device();
 

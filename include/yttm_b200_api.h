@@ -50,6 +50,13 @@ int yttm_api_encode_cli(void *handle, const char *output_type, int stream, int b
 int yttm_api_decode_cli(void *handle, const int32_t *ignore, uint64_t n_ignore);
 void yttm_api_vocab_cli(void *handle, int verbose);
 
+/* order of the char2id lines of a model file written by the reference (BPEState::dump, utils.cpp:57-59):
+ * filled[n] = code points by ascending id -> out[n].  Host only, needs no GPU. */
+int yttm_api_dump_order(const uint32_t *filled, uint64_t n, uint32_t *out);
+/* BPEState::load (utils.cpp:68-91) then BPEState::dump (utils.cpp:50-66) of a model file: rewrites any valid
+ * model file in the reference's canonical line order.  Host only.  0 = ok, 1 = cannot read in_path. */
+int yttm_api_redump(const char *in_path, const char *out_path);
+
 /* raw yttm_ctx* / yttm_enc* of an opened model, for callers of yttm_b200.h */
 void *yttm_api_device_context(void *handle);
 void *yttm_api_device_encoder(void *handle);

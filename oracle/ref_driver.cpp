@@ -159,6 +159,19 @@ int64_t ref_decode_ids(void *hv, const int32_t *ids, uint64_t n, char *out, int6
   return need;
 }
 
+// The reference's own container: fill a flat_hash_map<uint32_t,uint32_t> the way compute_alphabet_helper
+// does (operator[] per key, bpe.cpp:340-353), copy it the way `*bpe_state = {char2id, ...}` does
+// (bpe.cpp:1289) and list the copy's iteration order, i.e. the order BPEState::dump writes (utils.cpp:57).
+// Pins the product's slot-order replay (yttm_api_dump_order) on arbitrary key sets.
+int ref_char2id_order(const uint32_t *keys, uint64_t n, uint32_t *out) {
+  vkcom::flat_hash_map<uint32_t, uint32_t> filled;
+  for (uint64_t i = 0; i < n; i++) filled[keys[i]] = (uint32_t)i;
+  vkcom::BPEState state = {filled, {}, vkcom::SpecialTokens()};
+  uint64_t j = 0;
+  for (auto kv : state.char2id) out[j++] = kv.first;
+  return j == n ? 0 : 1;
+}
+
 int ref_is_deterministic_queue() {
 #ifdef DETERMINISTIC_QUEUE
   return 1;

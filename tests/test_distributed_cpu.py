@@ -111,3 +111,27 @@ def test_host_alphabet_and_model_writer_match_oracle(oracle, cov):
     D.write_model(out, char2id, np.zeros((0, 3), np.uint32), (0, 1, 2, 3), 1200)
     got_c2i, _, got_special = read_model(out)
     assert got_c2i == want_c2i and got_special == want_special
+
+
+@pytest.mark.parametrize("special", [(0, 1, 2, 3), (-1, 0, -1, 5)])
+def test_model_writer_is_byte_identical_to_the_reference(special):
+    """write_model (rank 0 of train_distributed) writes the very bytes the reference's BPEState::dump does,
+    char2id lines in flat_hash_map order included: feed it the reference's own result un-renamed."""
+    import _bind
+    if not _bind.have_reference("det"):
+        pytest.skip("oracle/_ref not built")
+    pad, unk, bos, eos = special
+    text = _cases.zipf().text(60_000)
+    m = tmp_model_path("refw")
+    _bind.Reference("det").train(text, m, 900, 1.0, n_threads=1, pad=pad, unk=unk, bos=bos, eos=eos)
+    c2i, rules, _ = read_model(m)
+    # undo rename_tokens: final ids -> internal ids (specials first, then the rest ascending)
+    taken = {s for s in special if s != -1}
+    free = [i for i in range(900) if i not in taken]
+    back = {final: len(taken) + k for k, final in enumerate(free)}
+    char2id = {cp: back[i] for cp, i in c2i.items()}
+    internal = np.asarray([[back[x], back[y], back[z]] for x, y, z in rules], dtype=np.uint32).reshape(-1, 3)
+    out = tmp_model_path("oursw")
+    D.write_model(out, char2id, internal, special, 900)
+    with open(m, "rb") as a, open(out, "rb") as b:
+        assert a.read() == b.read()

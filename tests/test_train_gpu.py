@@ -178,3 +178,20 @@ def test_words_of_33_plus_tokens(product, oracle):
     rng = np.random.default_rng(9)
     words = [bytes(rng.choice(list(b"abcd"), size=int(n)).tolist()) for n in rng.integers(1, 90, size=3000)]
     _same(oracle, b" ".join(words), 600)
+
+
+def test_zz_model_file_bytes_equal_the_reference(product, checkers):
+    """the model FILE (not only its parsed content) equals the one the unmodified reference
+    (DETERMINISTIC_QUEUE build) writes — char2id lines in flat_hash_map slot order (tests/test_dump_order.py
+    pins that order on the CPU).  Kept last: everything above compares parsed models."""
+    if not checkers.have_reference("det"):
+        pytest.skip("oracle/_ref absent")
+    ref = checkers.Reference("det")
+    for text, vocab, cov in [(synth.readme_corpus(n_lines=800), 600, 1.0), (_cases.zipf().text(300_000), 3000, 1.0),
+                             (_cases.dirty_zipf_text(), 2500, 0.995)]:
+        m_r = tmp_model_path("refbytes")
+        ref.train(text, m_r, vocab, cov, n_threads=2)
+        m_g = gpu_train(text, vocab, cov)
+        assert read_model(m_r) == read_model(m_g)
+        with open(m_r, "rb") as a, open(m_g, "rb") as b:
+            assert a.read() == b.read(), "model file differs in bytes although its content is equal"

@@ -51,6 +51,8 @@ def lib():
         "yttm_api_encode_cli": (i32, [vp, cp, i32, i32, i32, i32, dbl]),
         "yttm_api_decode_cli": (i32, [vp, vp, u64]),
         "yttm_api_vocab_cli": (None, [vp, i32]),
+        "yttm_api_dump_order": (i32, [vp, u64, vp]),
+        "yttm_api_redump": (i32, [cp, cp]),
         "yttm_api_device_context": (vp, [vp]),
         "yttm_api_device_encoder": (vp, [vp]),
         # ---- device ABI (include/yttm_b200.h)

@@ -92,16 +92,116 @@ std::vector<uint32_t> decode_utf8(const char *begin, const char *end) {
 std::vector<uint32_t> decode_utf8(const std::string &s) { return decode_utf8(s.data(), s.data() + s.size()); }
 
 // ---------------------------------------------------------------------------------------------
-// model file (utils.cpp:50-91).  char2id lines are written in ascending code point order: the
-// reference writes them in flat_hash_map iteration order and its loader is order-agnostic.
+// model file (utils.cpp:50-91).  The reference writes the char2id lines in the iteration order of
+// its ska::flat_hash_map (third_party/flat_hash_map.h), i.e. in the slot order of an
+// open-addressing robin-hood table.  To make the dump byte-identical we replay, keys only, what
+// happens to that table: compute_alphabet_helper inserts U+2581 and then the kept characters by
+// descending (count, code point) (bpe.cpp:340-353) = ascending id, and `*bpe_state = {char2id,...}`
+// (bpe.cpp:1289) copy-constructs it (flat_hash_map.h:361-375: size the new table for the other
+// one, then re-insert in the other one's slot order).  Behaviour restated from the header:
+//   * home slot of key k = (11400714819323198485 * k) >> shift, shift = 64 - log2(buckets)
+//     (fibonacci_hash_policy :1274-1301; std::hash<uint32_t> is the identity);
+//   * a table of b buckets has b + max_lookups slots, max_lookups = max(4, log2 b) (:803-807);
+//   * emplace walks from the home slot while the resident is at least as far from its own home
+//     (:578-593), then takes an empty slot or swaps with the "richer" resident and carries that
+//     one on (:830-873); the table doubles (min 4 buckets) when it has none, when a walk reaches
+//     max_lookups or when size + 1 > buckets / 2, re-inserting the old slots in ascending slot
+//     order (:630-662, :875-878).
 // ---------------------------------------------------------------------------------------------
+namespace {
+class SlotOrderReplay {
+ public:
+  void insert(uint32_t k) {
+    for (;;) {
+      if (buckets_ == 0) { rehash(4); continue; }
+      uint64_t p = (11400714819323198485ull * (uint64_t)k) >> shift_;
+      int d = 0;
+      bool found = false;
+      for (; dist_[p] >= d; ++p, ++d)
+        if (key_[p] == k && p + 1 < dist_.size()) { found = true; break; }
+      if (found) return;
+      if (d == max_lookups_ || (double)(size_ + 1) > (double)buckets_ * 0.5) { rehash(2 * buckets_); continue; }
+      if (dist_[p] < 0) { put(p, d, k); return; }
+      // robin hood: the new key takes this slot, the displaced resident is carried forward
+      const uint64_t taken = p;
+      uint32_t carry = k;
+      swap_in(p, d, carry);
+      bool regrow = false;
+      for (++d, ++p;; ++p) {
+        if (dist_[p] < 0) { put(p, d, carry); return; }
+        if (dist_[p] < d) { swap_in(p, d, carry); ++d; continue; }
+        if (++d == max_lookups_) { regrow = true; break; }
+      }
+      if (regrow) {  // the carried resident goes back into the taken slot, the new key is retried after growing
+        std::swap(carry, key_[taken]);
+        rehash(2 * buckets_);
+        k = carry;
+      }
+    }
+  }
+  // copy construction: rehash_for_other_container (:813-816) + insert(other.begin(), other.end())
+  SlotOrderReplay copy() const {
+    SlotOrderReplay c;
+    c.rehash(std::min<uint64_t>(2 * size_, buckets_));
+    for (uint32_t k : order()) c.insert(k);
+    return c;
+  }
+  std::vector<uint32_t> order() const {
+    std::vector<uint32_t> out;
+    for (size_t i = 0; i + 1 < dist_.size(); i++)
+      if (dist_[i] >= 0) out.push_back(key_[i]);
+    return out;
+  }
+
+ private:
+  void put(uint64_t p, int d, uint32_t k) { dist_[p] = (int8_t)d; key_[p] = k; ++size_; }
+  void swap_in(uint64_t p, int &d, uint32_t &k) {
+    const int od = dist_[p];
+    dist_[p] = (int8_t)d;
+    d = od;
+    std::swap(k, key_[p]);
+  }
+  static int log2u(uint64_t v) { int r = 0; while (v >>= 1) ++r; return r; }
+  void rehash(uint64_t want) {
+    want = std::max<uint64_t>(want, (uint64_t)std::ceil((double)size_ / 0.5));
+    if (want == 0) return;  // nothing allocated yet and nothing to hold
+    uint64_t b = 2;
+    while (b < want) b <<= 1;
+    if (b == buckets_) return;
+    const std::vector<uint32_t> old = order();
+    buckets_ = b;
+    shift_ = 64 - log2u(b);
+    max_lookups_ = std::max(4, log2u(b));
+    dist_.assign(b + max_lookups_, (int8_t)-1);
+    key_.assign(b + max_lookups_, 0u);
+    dist_.back() = 0;  // the end marker is "occupied at distance 0" for the walks
+    size_ = 0;
+    for (uint32_t k : old) insert(k);
+  }
+  std::vector<int8_t> dist_;
+  std::vector<uint32_t> key_;
+  uint64_t buckets_ = 0, size_ = 0;
+  int shift_ = 63, max_lookups_ = 3;
+};
+}  // namespace
+
+// keys in the order the reference's char2id was filled -> keys in the order its dump lists them
+std::vector<uint32_t> reference_dump_order(const std::vector<uint32_t> &insertion_order) {
+  SlotOrderReplay t;
+  for (uint32_t k : insertion_order) t.insert(k);
+  return t.copy().order();
+}
+
 void BPEState::dump(const std::string &file_name) {
   std::ofstream fout(file_name, std::ios::out);
   if (fout.fail()) { std::cerr << "Can't open file: " << file_name << std::endl; assert(false); }
   fout << char2id.size() << " " << rules.size() << std::endl;
-  std::vector<std::pair<uint32_t, uint32_t>> sorted(char2id.begin(), char2id.end());
-  std::sort(sorted.begin(), sorted.end());
-  for (auto &s : sorted) fout << s.first << " " << s.second << std::endl;
+  std::vector<std::pair<uint32_t, uint32_t>> by_id;  // (id, code point): ids ascend in insertion order
+  for (auto &kv : char2id) by_id.emplace_back(kv.second, kv.first);
+  std::sort(by_id.begin(), by_id.end());
+  std::vector<uint32_t> filled;
+  for (auto &s : by_id) filled.push_back(s.second);
+  for (uint32_t cp : reference_dump_order(filled)) fout << cp << " " << char2id.at(cp) << std::endl;
   for (auto &r : rules) fout << r.x << " " << r.y << " " << r.z << std::endl;
   fout << special_tokens.unk_id << " " << special_tokens.pad_id << " " << special_tokens.bos_id << " "
        << special_tokens.eos_id << std::endl;

@@ -175,6 +175,20 @@ int yttm_api_decode_cli(void *hv, const int32_t *ignore, uint64_t n_ignore) {
 }
 void yttm_api_vocab_cli(void *hv, int verbose) { static_cast<Handle *>(hv)->enc->vocab_cli(verbose != 0); }
 
+int yttm_api_dump_order(const uint32_t *filled, uint64_t n, uint32_t *out) {
+  const std::vector<uint32_t> o = reference_dump_order(std::vector<uint32_t>(filled, filled + n));
+  if (o.size() != n) return 1;  // duplicate keys in `filled`
+  std::copy(o.begin(), o.end(), out);
+  return 0;
+}
+
+int yttm_api_redump(const char *in_path, const char *out_path) {
+  BPEState st;
+  if (!st.load(in_path).ok()) return 1;
+  st.dump(out_path);
+  return 0;
+}
+
 // raw handles for bench.py / tests that drive the device ABI of yttm_b200.h directly
 void *yttm_api_device_context(void *hv) { return static_cast<Handle *>(hv)->enc->device_context(); }
 void *yttm_api_device_encoder(void *hv) { return static_cast<Handle *>(hv)->enc->device_encoder(); }

@@ -198,7 +198,9 @@ def choose_alphabet(cps, counts, data_len, coverage, special):
 
 
 def write_model(path, char2id, rules, special, vocab_size):
-    """rename_tokens (bpe.cpp:814-837) + BPEState::dump (utils.cpp:50-66)."""
+    """rename_tokens (bpe.cpp:814-837) + BPEState::dump (utils.cpp:50-66); the char2id lines come in the
+    reference's flat_hash_map iteration order (yttm_api_dump_order), so the file is byte-identical."""
+    from . import _lib
     pad, unk, bos, eos = special
     taken = {s for s in special if s != -1}
     n_special = len(taken)
@@ -208,9 +210,14 @@ def write_model(path, char2id, rules, special, vocab_size):
         if i not in taken:
             ren[cur] = i
             cur += 1
+    filled = np.array(sorted(char2id, key=lambda cp: char2id[cp]), dtype=np.uint32)
+    order = np.zeros(len(filled), dtype=np.uint32)
+    L = _lib.lib()
+    if L.yttm_api_dump_order(filled.ctypes.data, len(filled), order.ctypes.data) != 0:
+        raise ValueError("duplicate code points in char2id")
     with open(path, "w") as f:
         f.write("%d %d\n" % (len(char2id), len(rules)))
-        for cp in sorted(char2id):
+        for cp in order.tolist():
             f.write("%d %d\n" % (cp, ren[char2id[cp]]))
         for x, y, z in rules:
             f.write("%d %d %d\n" % (ren[int(x)], ren[int(y)], ren[int(z)]))
