@@ -159,6 +159,97 @@ __global__ void __launch_bounds__(128) encode_words_kernel(EncArgs a, uint64_t n
   }
 }
 
+// EXPERIMENTAL variant (env YTTM_ENC_BUCKETED=1, off by default until measured on a B200): the same
+// per-word work, but a block first takes a window of BUCKET_WINDOW consecutive work items, measures
+// every word (end position, number of UTF-8 lead bytes = tokens before merging) and hands the items
+// out in order of that token count (counting sort in shared memory).  A warp then holds 32 words of
+// nearly the same length: the merge loop of encode_word is data-dependent (decode + ~2.5 probes per
+// token), and with thread-per-word every warp used to run as long as its longest word.
+constexpr uint32_t BUCKET_WINDOW = 512, BUCKET_KEYS = 64;
+template <bool DROPOUT>
+__global__ void __launch_bounds__(128) encode_words_bucketed_kernel(EncArgs a, uint64_t n_words) {
+  constexpr uint32_t LOCAL_W = 40;
+  __shared__ uint32_t s_pos[BUCKET_WINDOW], s_sent[BUCKET_WINDOW], s_end[BUCKET_WINDOW];
+  __shared__ uint16_t s_perm[BUCKET_WINDOW];
+  __shared__ uint32_t s_hist[BUCKET_KEYS];
+  const uint64_t o0 = a.offs[0];
+  const RuleTab rt = a.rt;
+  auto rank = [&](uint32_t x, uint32_t y, uint32_t *z) { return rule_rank(rt, x, y, z); };
+  const uint64_t n_win = (n_words + BUCKET_WINDOW - 1) / BUCKET_WINDOW;
+  for (uint64_t win = blockIdx.x; win < n_win; win += gridDim.x) {  // block-uniform
+    const uint64_t w0 = win * BUCKET_WINDOW;
+    const uint32_t cnt = (uint32_t)min((uint64_t)BUCKET_WINDOW, n_words - w0);
+    if (threadIdx.x < BUCKET_KEYS) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t key[BUCKET_WINDOW / 128], rk[BUCKET_WINDOW / 128];
+#pragma unroll
+    for (uint32_t j = 0; j < BUCKET_WINDOW / 128; j++) {
+      const uint32_t i = j * 128 + threadIdx.x;
+      key[j] = 0;
+      rk[j] = 0;
+      if (i < cnt) {
+        const uint64_t p0 = a.word_pos[w0 + i], s = a.word_sent[w0 + i];
+        const uint64_t hi = a.offs[s + 1] - o0;
+        uint64_t q = p0;
+        uint32_t l, units = 0;
+        while (q < hi && !space_at(a.bytes, q, hi, &l)) {
+          units += (a.bytes[q] & 0xC0u) != 0x80u;
+          q++;
+        }
+        s_pos[i] = (uint32_t)p0;
+        s_sent[i] = (uint32_t)s;
+        s_end[i] = (uint32_t)q;
+        key[j] = min(units, BUCKET_KEYS - 1);
+        rk[j] = atomicAdd(&s_hist[key[j]], 1u);  // arrival order inside the bucket (any order is valid)
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {  // exclusive scan of the 64 bucket sizes by one warp, longest words first
+      const uint32_t k0 = BUCKET_KEYS - 1 - threadIdx.x, k1 = BUCKET_KEYS - 1 - (threadIdx.x + 32);
+      const uint32_t c0 = s_hist[k0], c1 = s_hist[k1];
+      uint32_t x0 = c0, x1 = c1;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y0 = __shfl_up_sync(0xffffffffu, x0, o), y1 = __shfl_up_sync(0xffffffffu, x1, o);
+        if ((int)threadIdx.x >= o) { x0 += y0; x1 += y1; }
+      }
+      const uint32_t tot0 = __shfl_sync(0xffffffffu, x0, 31);
+      s_hist[k0] = x0 - c0;
+      s_hist[k1] = tot0 + x1 - c1;
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t j = 0; j < BUCKET_WINDOW / 128; j++) {
+      const uint32_t i = j * 128 + threadIdx.x;
+      if (i < cnt) s_perm[s_hist[key[j]] + rk[j]] = (uint16_t)i;
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < cnt; j += 128) {
+      const uint32_t i = s_perm[j];
+      const uint64_t p0 = s_pos[i], s = s_sent[i], q = s_end[i];
+      const uint64_t lo = a.offs[s] - o0, hi = a.offs[s + 1] - o0;
+      const uint64_t slot0 = sent_base(lo, s) + 1 + (p0 - lo);
+      int32_t *t = a.slots + slot0;  // k+1 private slots
+      uint32_t owned = (uint32_t)(q - p0) + 1, n;
+      if (owned <= LOCAL_W) {
+        int32_t lt[LOCAL_W];
+        uint32_t lr[LOCAL_W];
+        uint32_t laux[DROPOUT ? 6 * LOCAL_W : 1];
+        n = encode_word(a.bytes, p0, lo, hi, a.cp2id, a.space_id, rank, nullptr, DROPOUT ? a.drop_thresh : 0, a.seed,
+                        a.first_sentence + s, lt, lr, laux, &owned);
+        for (uint32_t k = 0; k < n; k++) t[k] = ((uint32_t)lt[k] & UNK_FLAG) ? a.unk_id : lt[k];
+      } else {
+        n = encode_word(a.bytes, p0, lo, hi, a.cp2id, a.space_id, rank, nullptr, DROPOUT ? a.drop_thresh : 0, a.seed,
+                        a.first_sentence + s, t, a.ranks + slot0, DROPOUT ? a.aux + 6 * slot0 : nullptr, &owned);
+        for (uint32_t k = 0; k < n; k++)
+          if ((uint32_t)t[k] & UNK_FLAG) t[k] = a.unk_id;
+        for (uint32_t k = n; k < owned; k++) t[k] = EMPTY_SLOT;
+      }
+      if (n) atomicAdd(a.n_ids + s, (unsigned long long)n);
+    }
+    __syncthreads();  // the window's shared arrays are reused by the next one
+  }
+}
+
 __global__ void __launch_bounds__(256) gather_ids_kernel(EncArgs a, const unsigned long long *__restrict__ out_off,
                                                          int32_t *__restrict__ out) {
   const unsigned lane = threadIdx.x & 31;
@@ -255,7 +346,12 @@ int enc_device(yttm_enc *enc, yttm_enc::Slot *e, const uint8_t *d_bytes, const u
   if (n_words) {
     uint64_t blocks = std::min<uint64_t>((n_words + 127) / 128, (uint64_t)c->n_sm * 16);
     ytc::timer_begin(c, "enc_words");
-    if (a.drop_thresh) encode_words_kernel<true><<<(unsigned)blocks, 128, 0, c->stream>>>(a, n_words);
+    static const bool bucketed = std::getenv("YTTM_ENC_BUCKETED") != nullptr;  // experimental, see the kernel
+    if (bucketed) {
+      const unsigned wb = (unsigned)std::min<uint64_t>((n_words + BUCKET_WINDOW - 1) / BUCKET_WINDOW, (uint64_t)c->n_sm * 16);
+      if (a.drop_thresh) encode_words_bucketed_kernel<true><<<wb, 128, 0, c->stream>>>(a, n_words);
+      else encode_words_bucketed_kernel<false><<<wb, 128, 0, c->stream>>>(a, n_words);
+    } else if (a.drop_thresh) encode_words_kernel<true><<<(unsigned)blocks, 128, 0, c->stream>>>(a, n_words);
     else encode_words_kernel<false><<<(unsigned)blocks, 128, 0, c->stream>>>(a, n_words);
     ytc::timer_end(c, "enc_words");
     c->launches++;
