@@ -1,0 +1,143 @@
+"""The product's CUDA kernels — the very sources of youtokentome_b200/csrc, compiled by g++ against the stand-in
+cuda_runtime.h of tests/emul/simt — run on the CPU under a fiber SIMT emulator and go through the SAME parity
+checks as the GPU tests (the bodies of tests/test_train_gpu.py / tests/test_encode_gpu.py are reused as they are).
+
+TEST HARNESS ONLY.  The emulated library is reachable from tests/ alone (tests/_emu.py); the package loads
+libyttm_b200.so and nothing else, and the GPU tests stay the parity tests proper.  What this buys in a container
+without a GPU: every kernel's control flow (tile rings and mbarrier phases of the STREAMING merge loop, claim
+bitmaps, vectorised hit scans, update queues, cooperative grid barriers, the slot scheme of the encoder) is executed
+and compared bit for bit with the oracle by `pytest -m "not gpu"`; it cannot see memory-ordering races or speed."""
+import numpy as np
+import pytest
+
+import _cases
+import test_encode_gpu as EG
+import test_train_gpu as TG
+from _bind import tmp_model_path
+from youtokentome_b200 import _lib, synth
+
+
+@pytest.fixture
+def emu(monkeypatch):
+    from _emu import emu_lib
+    L = emu_lib()
+    monkeypatch.setattr(_lib, "_lib", L)  # what _lib.lib() hands to tests/_gpu.py and to the Python BPE class
+    monkeypatch.setenv("YT_EMU_SMS", "2")
+    return L
+
+
+# ---- hot path (a): training ---------------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(16))
+def test_train_stress(emu, oracle, seed):
+    TG.test_stress(emu, oracle, seed)
+
+
+@pytest.mark.parametrize("sms", ["1", "3", "5"])
+def test_train_other_grid_sizes(emu, oracle, monkeypatch, sms):
+    """1, 3 and 5 blocks: tile ownership, the per-block winners of the arg-max and the grid barrier count change."""
+    monkeypatch.setenv("YT_EMU_SMS", sms)
+    for seed in (1, 4, 9):
+        text, vocab, cov, _ = _cases.stress_case(seed)
+        TG._same(oracle, text, vocab, cov)
+    TG._same(oracle, _cases.dirty_zipf_text(60_000), 700, 0.98)
+
+
+def test_train_unicode_and_runs(emu, oracle):
+    TG._same(oracle, _cases.dirty_zipf_text(120_000), 900, 0.98)
+    TG._same(oracle, b"a" * 500 + b" " + b"ab" * 300 + b" aaa aaaa aaaaa " + b"b" * 1001, 40)
+    TG._same(oracle, synth.readme_corpus(n_lines=300), 300)
+
+
+@pytest.mark.parametrize("q", ["64", "1000"])
+def test_train_streaming_tiles(emu, oracle, monkeypatch, q):
+    """STREAMING mode forced: TMA ring model (mbarrier phases persisting across merges), eight-tokens-per-lane
+    scan over 16-byte aligned windows, deferred rewrites, tiles cut inside words' neighbourhoods."""
+    monkeypatch.setenv("YTTM_FORCE_STREAM", "1")
+    monkeypatch.setenv("YTTM_STREAM_Q", q)
+    for seed in range(6):
+        text, vocab, cov, _ = _cases.stress_case(seed)
+        TG._same(oracle, text, vocab, cov)
+    TG._same(oracle, _cases.dirty_zipf_text(60_000), 600, 0.98)
+    TG._same(oracle, b"a" * 500 + b" " + b"ab" * 300 + b" aaa aaaa aaaaa " + b"b" * 1001, 40)
+
+
+@pytest.mark.parametrize("stages", ["3", "4"])
+def test_train_streaming_deeper_rings(emu, oracle, monkeypatch, stages):
+    monkeypatch.setenv("YTTM_FORCE_STREAM", "1")
+    monkeypatch.setenv("YTTM_STREAM_Q", "128")
+    monkeypatch.setenv("YTTM_STAGES", stages)
+    for seed in (2, 5):
+        text, vocab, cov, _ = _cases.stress_case(seed)
+        TG._same(oracle, text, vocab, cov)
+
+
+@pytest.mark.parametrize("dbg", ["2", "8"])
+def test_train_diagnostic_modes(emu, oracle, monkeypatch, dbg):
+    """YTTM_DBG=2 (scalar streaming scan) and =8 (per-block apply timers) must not change the result."""
+    monkeypatch.setenv("YTTM_DBG", dbg)
+    monkeypatch.setenv("YTTM_FORCE_STREAM", "1")
+    monkeypatch.setenv("YTTM_STREAM_Q", "256")
+    text, vocab, cov, _ = _cases.stress_case(7)
+    TG._same(oracle, text, vocab, cov)
+
+
+def test_train_words_of_33_plus_tokens(emu, oracle):
+    rng = np.random.default_rng(9)
+    words = [bytes(rng.choice(list(b"abcd"), size=int(n)).tolist()) for n in rng.integers(1, 90, size=400)]
+    TG._same(oracle, b" ".join(words), 200)
+
+
+def test_train_errors_and_special_ids(emu, oracle):
+    TG._same(oracle, b"abc abd", 5)                      # vocab too small: same Status text
+    TG._same(oracle, _cases.dirty_zipf_text(40_000), 500, 1.0, pad=-1, bos=-1, eos=5, unk=0)
+
+
+# ---- hot path (b): encoding ---------------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(10))
+def test_encode_stress(emu, oracle, seed):
+    EG.test_stress(emu, oracle, seed)
+
+
+@pytest.mark.parametrize("name", sorted(synth.GOLDEN_TEXTS))
+def test_encode_manual_corpora(emu, oracle, name):
+    EG.test_manual_corpora(emu, oracle, name)
+
+
+def test_encode_unicode_long_words_dropout(emu, oracle):
+    m = EG._model(oracle, _cases.dirty_zipf_text(), 1500, 0.95)
+    zc = _cases.zipf()
+    long_word = b"".join(zc.sentences(20, 60, seed=6)).replace(b" ", b"")  # > LOCAL_W: works in its global slots
+    sents = _cases.zipf_sentences(300) + _cases.EDGE_SENTENCES + [long_word, b"a" * 700, long_word + b" x " + long_word]
+    g, o = EG.GpuEncoder(m), oracle.encoder(m)
+    for kw in EG.KW:
+        assert g.encode(sents, **kw) == o.encode(sents, **kw)
+    for p, seed in ((0.1, 3), (0.6, 4), (1.0, 5)):
+        assert g.encode(sents, dropout=p, seed=seed) == o.encode(sents, dropout=p, seed=seed)
+
+
+def test_encode_bucketed_variant(emu, oracle, monkeypatch):
+    """The experimental length-bucketed word kernel (YTTM_ENC_BUCKETED, off by default, not yet run on hardware):
+    same ids as the oracle, with and without dropout, across window boundaries (BUCKET_WINDOW = 512 words)."""
+    monkeypatch.setenv("YTTM_ENC_BUCKETED", "1")
+    m = EG._model(oracle, _cases.dirty_zipf_text(), 1500)
+    zc = _cases.zipf()
+    long_word = b"".join(zc.sentences(20, 60, seed=6)).replace(b" ", b"")
+    sents = _cases.zipf_sentences(400) + _cases.EDGE_SENTENCES + [long_word, b"\x80\x80\x80 \xbf\xbf"]
+    g, o = EG.GpuEncoder(m), oracle.encoder(m)
+    assert sum(len(s.split()) for s in sents) > 3 * 512
+    for kw in EG.KW[:2]:
+        assert g.encode(sents, **kw) == o.encode(sents, **kw)
+    assert g.encode(sents, dropout=0.3, seed=9) == o.encode(sents, dropout=0.3, seed=9)
+
+
+def test_encode_chunked_pipeline(emu, oracle, monkeypatch):
+    m = EG._model(oracle, _cases.dirty_zipf_text(), 1500)
+    zc = _cases.zipf()
+    sents = zc.sentences(3000, 400, seed=21) + _cases.EDGE_SENTENCES
+    want = oracle.encoder(m).encode(sents, bos=True, eos=True)
+    monkeypatch.setenv("YTTM_ENC_CHUNK_MB", "1")   # 1.2 MB of sentences: two chunks, both buffer sets
+    assert EG.GpuEncoder(m).encode(sents, bos=True, eos=True) == want
+
+
+def test_python_api_on_the_emulated_library(emu, tmp_path):
+    EG.test_python_api_roundtrip(emu, tmp_path)

@@ -28,7 +28,12 @@ def lib():
         raise ImportError(
             "youtokentome_b200: %s is missing - run `python -c 'import __graft_entry__ as g; g.build()'` "
             "(there is no CPU fallback)" % LIB_PATH)
-    L = C.CDLL(LIB_PATH)
+    _lib = bind(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def bind(L):
+    """Declare the C signatures of include/yttm_b200.h and include/yttm_b200_api.h on a loaded library."""
     vp, cp, u64, i32, dbl, i64 = C.c_void_p, C.c_char_p, C.c_uint64, C.c_int, C.c_double, C.c_int64
     sig = {
         # ---- host-level API (include/yttm_b200_api.h)
@@ -85,7 +90,6 @@ def lib():
         f = getattr(L, name)
         f.restype = res
         f.argtypes = args
-    _lib = L
     return L
 
 

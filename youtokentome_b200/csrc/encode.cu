@@ -346,7 +346,7 @@ int enc_device(yttm_enc *enc, yttm_enc::Slot *e, const uint8_t *d_bytes, const u
   if (n_words) {
     uint64_t blocks = std::min<uint64_t>((n_words + 127) / 128, (uint64_t)c->n_sm * 16);
     ytc::timer_begin(c, "enc_words");
-    static const bool bucketed = std::getenv("YTTM_ENC_BUCKETED") != nullptr;  // experimental, see the kernel
+    const bool bucketed = std::getenv("YTTM_ENC_BUCKETED") != nullptr;  // experimental, see the kernel
     if (bucketed) {
       const unsigned wb = (unsigned)std::min<uint64_t>((n_words + BUCKET_WINDOW - 1) / BUCKET_WINDOW, (uint64_t)c->n_sm * 16);
       if (a.drop_thresh) encode_words_bucketed_kernel<true><<<wb, 128, 0, c->stream>>>(a, n_words);

@@ -50,11 +50,19 @@ struct Best { unsigned long long c, prio, slot; };
 __device__ __forceinline__ bool better(const Best &a, const Best &b) {  // a beats b
   return a.c > b.c || (a.c == b.c && a.prio > b.prio);
 }
+#ifndef YT_SIMT_EMU
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+#else   // tests/emul/simt: the CPU clock
+inline unsigned long long gtimer() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
+}
+#endif
 __device__ __forceinline__ Best warp_best(Best v) {
   for (int o = 16; o > 0; o >>= 1) {
     Best w;
@@ -266,6 +274,7 @@ __device__ __forceinline__ unsigned long long process_tile_direct(uint32_t *tok,
 }
 
 // ---- TMA (bulk async copy) staging of a tile: global -> shared, completion on an mbarrier ----------
+#ifndef YT_SIMT_EMU
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -293,6 +302,44 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
     if (spin > (1u << 28)) asm volatile("trap;");  // a lost transaction must not hang the box
   }
 }
+#else
+// tests/emul/simt (CPU emulation of the kernels, test harness only): the mbarrier word is modelled as
+// { pending arrivals : 16, arrival count : 16, outstanding transaction bytes : 31, phase : 1 }; a bulk copy is an
+// immediate memcpy that completes its bytes on the barrier; a waiter yields to the other fibers of the block.
+struct EmuMbar { uint64_t pending : 16, count : 16, tx : 31, phase : 1; };
+inline EmuMbar *emu_bar(unsigned long long *bar) { return reinterpret_cast<EmuMbar *>(bar); }
+inline void emu_bar_check(EmuMbar *m) {
+  if (m->pending == 0 && m->tx == 0) { m->phase ^= 1u; m->pending = m->count; }
+}
+inline void mbar_init(unsigned long long *bar, uint32_t count) {
+  EmuMbar *m = emu_bar(bar);
+  m->pending = count; m->count = count; m->tx = 0; m->phase = 0;
+}
+inline void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {  // one arrival + expected bytes
+  EmuMbar *m = emu_bar(bar);
+  m->tx += bytes;
+  m->pending -= 1;
+  emu_bar_check(m);
+}
+inline void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+  if (((uintptr_t)dst | (uintptr_t)src | bytes) & 15u) { fprintf(stderr, "emu: misaligned bulk copy\n"); abort(); }
+  memcpy(dst, src, bytes);
+  EmuMbar *m = emu_bar(bar);
+  m->tx -= bytes;
+  emu_bar_check(m);
+}
+inline void mbar_arrive(unsigned long long *bar) {
+  EmuMbar *m = emu_bar(bar);
+  m->pending -= 1;
+  emu_bar_check(m);
+}
+inline void mbar_wait(unsigned long long *bar, uint32_t parity) {  // returns once the phase of that parity is over
+  for (uint64_t spin = 0; emu_bar(bar)->phase == (parity & 1u); spin++) {
+    if (spin > (1u << 24)) { fprintf(stderr, "emu: mbarrier wait never completes\n"); abort(); }
+    emu::yield();
+  }
+}
+#endif
 // bytes of a 16-byte aligned window [lo & ~3, roundup(hi, 4)) over uint32 elements
 __device__ __forceinline__ uint32_t win_lo(uint32_t lo) { return lo & ~3u; }
 __device__ __forceinline__ uint32_t win_bytes(uint32_t lo, uint32_t hi) { return (((hi + 3u) & ~3u) - (lo & ~3u)) * 4u; }
@@ -304,7 +351,11 @@ __device__ __forceinline__ void load_tile(const LoopArgs &a, uint32_t w0, uint32
   for (uint32_t i = threadIdx.x; i < span; i += blockDim.x) stok[i] = __ldcg(src + i);
 }
 
+#ifndef YT_SIMT_EMU
 extern __shared__ __align__(16) uint32_t yt_dyn_smem[];
+#else
+#define yt_dyn_smem (reinterpret_cast<uint32_t *>(emu::dyn_smem()))
+#endif
 
 __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
   cg::grid_group grid = cg::this_grid();
@@ -330,7 +381,9 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
   const uint32_t stage_words = a.stream_tok_cap + a.stream_word_cap;  // uint32 per stage
   if (!a.resident && threadIdx.x == 0) {
     for (uint32_t st = 0; st < n_stage; st++) { mbar_init(&s_full[st], 1); mbar_init(&s_empty[st], (blockDim.x >> 5) - 1);  /* consumer warps */ }
+#ifndef YT_SIMT_EMU
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
   }
   // STREAMING pipeline state of this thread (producer lane: empty-phase bits, consumers: full-phase bits)
   uint32_t pipe_used = 0, pipe_phase = 0, pipe_stage = 0;
@@ -578,7 +631,9 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
         }
       }
       // write-through stores (generic proxy) must be ordered before the next iteration's bulk loads
+#ifndef YT_SIMT_EMU
       asm volatile("fence.proxy.async;" ::: "memory");
+#endif
     }
     if (dbgt && lane == 0) atomicMax(&s_tpre, gtimer() - tw0);
     if (uq.n) uq_drain(uq, lane, a.tab);  // one batch of table updates per warp and iteration

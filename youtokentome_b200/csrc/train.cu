@@ -917,9 +917,14 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
     a.max_total = max_merges;
     a.max_iters = max_merges;
     a.key_limit = (uint32_t)std::min<uint64_t>(c->pcap / 4 * 3, 0xfffffff0ull);  // rebuild above load 3/4
+#ifndef YT_SIMT_EMU
     void *args[] = {&a};
     YT_CUDA(c, cudaLaunchCooperativeKernel((void *)merge_loop_kernel, dim3(c->loop_blocks), dim3(c->loop_threads), args,
                                            (size_t)c->loop_smem, c->stream));
+#else  // tests/emul/simt: every block on its own OS thread, grid.sync() = pthread barrier
+    emu::launch_cooperative((unsigned)c->loop_blocks, (unsigned)c->loop_threads, (size_t)c->loop_smem,
+                            [=]() { merge_loop_kernel(a); });
+#endif
     c->launches++;
     YT_CUDA(c, cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     YT_CUDA(c, cudaStreamSynchronize(c->stream));
