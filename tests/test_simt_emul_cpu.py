@@ -130,6 +130,21 @@ def test_encode_bucketed_variant(emu, oracle, monkeypatch):
     assert g.encode(sents, dropout=0.3, seed=9) == o.encode(sents, dropout=0.3, seed=9)
 
 
+def test_encode_find_cached_variant(emu, oracle, monkeypatch):
+    """The experimental find_words kernel that keeps the ballots of the first 256 bytes in registers
+    (YTTM_ENC_FIND_CACHED, off by default): sentences shorter, equal and longer than the cached window."""
+    monkeypatch.setenv("YTTM_ENC_FIND_CACHED", "1")
+    m = EG._model(oracle, _cases.dirty_zipf_text(), 1500)
+    zc = _cases.zipf()
+    sents = (_cases.zipf_sentences(200) + _cases.EDGE_SENTENCES + zc.sentences(40, 255, seed=2) + zc.sentences(40, 257, seed=3) +
+             [b" ".join(zc.sentences(30, 100, seed=5)), b"x" * 256, b"x " * 128, b" " * 300 + b"y", b"z" * 31 + b" " + b"w" * 300])
+    g, o = EG.GpuEncoder(m), oracle.encoder(m)
+    for kw in EG.KW:
+        assert g.encode(sents, **kw) == o.encode(sents, **kw)
+    monkeypatch.setenv("YTTM_ENC_BUCKETED", "1")   # both experimental kernels together
+    assert g.encode(sents, bos=True) == o.encode(sents, bos=True)
+
+
 def test_encode_chunked_pipeline(emu, oracle, monkeypatch):
     m = EG._model(oracle, _cases.dirty_zipf_text(), 1500)
     zc = _cases.zipf()

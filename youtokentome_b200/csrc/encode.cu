@@ -120,6 +120,80 @@ __global__ void __launch_bounds__(256) find_words_kernel(EncArgs a) {
   }
 }
 
+// EXPERIMENTAL variant (env YTTM_ENC_FIND_CACHED=1, off by default until measured on a B200): the same two
+// passes, but the word-start ballots of the first FIND_CACHE chunks (256 bytes) of a sentence stay in registers, so
+// pass 2 re-runs word_start_at only for the tail of longer sentences (128-byte sentences: never).
+constexpr int FIND_CACHE = 8;
+__global__ void __launch_bounds__(256) find_words_cached_kernel(EncArgs a) {
+  __shared__ unsigned long long s_cnt[8], s_base;
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint64_t o0 = a.offs[0];
+  for (uint64_t g = (uint64_t)blockIdx.x * 8; g < a.n_sent; g += (uint64_t)gridDim.x * 8) {  // block-uniform
+    const uint64_t s = g + wid;
+    const bool live = s < a.n_sent;
+    uint64_t lo = 0, hi = 0;
+    unsigned long long cnt = 0;
+    unsigned masks[FIND_CACHE];
+#pragma unroll
+    for (int j = 0; j < FIND_CACHE; j++) masks[j] = 0;
+    if (live) {
+      lo = a.offs[s] - o0;
+      hi = a.offs[s + 1] - o0;
+#pragma unroll
+      for (int j = 0; j < FIND_CACHE; j++) {
+        const uint64_t p = lo + 32ull * j + lane;
+        if (lo + 32ull * j < hi) {  // warp-uniform
+          masks[j] = __ballot_sync(0xffffffffu, p < hi && word_start_at(a.bytes, p, lo, hi));
+          cnt += __popc(masks[j]);
+        }
+      }
+      for (uint64_t p0 = lo + 32ull * FIND_CACHE; p0 < hi; p0 += 32) {
+        const uint64_t p = p0 + lane;
+        cnt += __popc(__ballot_sync(0xffffffffu, p < hi && word_start_at(a.bytes, p, lo, hi)));
+      }
+      if (lane == 0) {
+        const uint64_t base = sent_base(lo, s), len = hi - lo;
+        a.n_ids[s] = (a.bos ? 1 : 0) + (a.eos ? 1 : 0);
+        if (a.bos) a.slots[base] = a.bos_id;
+        if (a.eos) a.slots[base + len + 2] = a.eos_id;
+      }
+    }
+    if (lane == 0) s_cnt[wid] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long tot = 0;
+      for (int i = 0; i < 8; i++) { unsigned long long c = s_cnt[i]; s_cnt[i] = tot; tot += c; }
+      s_base = tot ? atomicAdd(a.n_words, tot) : 0ull;
+    }
+    __syncthreads();
+    if (live && cnt) {
+      unsigned long long idx = s_base + s_cnt[wid];
+#pragma unroll
+      for (int j = 0; j < FIND_CACHE; j++) {
+        const unsigned m = masks[j];
+        if ((m >> lane) & 1u) {
+          const unsigned long long i = idx + __popc(m & ((1u << lane) - 1));
+          a.word_pos[i] = (uint32_t)(lo + 32ull * j + lane);
+          a.word_sent[i] = (uint32_t)s;
+        }
+        idx += __popc(m);
+      }
+      for (uint64_t p0 = lo + 32ull * FIND_CACHE; p0 < hi; p0 += 32) {
+        const uint64_t p = p0 + lane;
+        const bool ws = p < hi && word_start_at(a.bytes, p, lo, hi);
+        const unsigned m = __ballot_sync(0xffffffffu, ws);
+        if (ws) {
+          const unsigned long long i = idx + __popc(m & ((1u << lane) - 1));
+          a.word_pos[i] = (uint32_t)p;
+          a.word_sent[i] = (uint32_t)s;
+        }
+        idx += __popc(m);
+      }
+    }
+    __syncthreads();  // s_cnt / s_base are reused by the next round
+  }
+}
+
 // One thread per word.  Words of at most LOCAL_W - 1 bytes (nearly all) are merged in thread-private
 // local arrays (L1-resident) and only the final tokens go to the slot buffer; longer words work in
 // place in their private slots in global memory.
@@ -336,7 +410,10 @@ int enc_device(yttm_enc *enc, yttm_enc::Slot *e, const uint8_t *d_bytes, const u
     uint64_t blocks = std::min<uint64_t>((warps_needed + 7) / 8, (uint64_t)c->n_sm * 8);
     ytc::timer_begin(c, "enc_find");
     YT_CUDA(c, cudaMemsetAsync(a.slots, 0xff, n_slots * 4, c->stream));  // EMPTY_SLOT == -1
-    find_words_kernel<<<(unsigned)std::max<uint64_t>(blocks, 1), 256, 0, c->stream>>>(a);
+    if (std::getenv("YTTM_ENC_FIND_CACHED"))  // experimental, see the kernel
+      find_words_cached_kernel<<<(unsigned)std::max<uint64_t>(blocks, 1), 256, 0, c->stream>>>(a);
+    else
+      find_words_kernel<<<(unsigned)std::max<uint64_t>(blocks, 1), 256, 0, c->stream>>>(a);
     ytc::timer_end(c, "enc_find");
     c->launches++;
   }
