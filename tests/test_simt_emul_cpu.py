@@ -156,3 +156,71 @@ def test_encode_chunked_pipeline(emu, oracle, monkeypatch):
 
 def test_python_api_on_the_emulated_library(emu, tmp_path):
     EG.test_python_api_roundtrip(emu, tmp_path)
+
+
+# ---- rare paths of the merge loop, reached through host-only test knobs ---------------------------
+def _abi_train(L, text, vocab):
+    """Drive the device ABI of include/yttm_b200.h phase by phase (as tools/probe_train.py does); returns
+    (rules as a list of tuples, number of merge-loop launches)."""
+    import ctypes as C
+    ctx = C.c_void_p()
+    assert L.yttm_ctx_create(0, C.byref(ctx)) == 0
+    try:
+        dl, nd = C.c_uint64(0), C.c_uint64(0)
+        assert L.yttm_train_load_corpus(ctx, C.cast(C.c_char_p(text), C.c_void_p), len(text), 0) == 0
+        assert L.yttm_train_char_hist(ctx, C.byref(dl), C.byref(nd)) == 0
+        cps = np.zeros(nd.value, dtype=np.uint32)
+        cnt = np.zeros(nd.value, dtype=np.uint64)
+        L.yttm_train_get_char_hist(ctx, cps.ctypes.data, cnt.ctypes.data)
+        order = np.lexsort((cps, cnt))[::-1]
+        kc = np.concatenate([[9601], cps[order]]).astype(np.uint32)
+        ki = np.arange(4, 4 + len(kc), dtype=np.uint32)
+        assert L.yttm_train_set_alphabet(ctx, kc.ctypes.data, ki.ctypes.data, len(kc), 4) == 0
+        st = _lib.TrainStats()
+        assert L.yttm_train_build(ctx, C.byref(st)) == 0, L.yttm_last_error(ctx)
+        nm = vocab - 4 - len(kc)
+        rules = np.zeros(3 * nm, dtype=np.uint32)
+        fr = np.zeros(nm, dtype=np.uint64)
+        done = C.c_uint32(0)
+        assert L.yttm_train_run(ctx, 4 + len(kc), nm, rules.ctypes.data, fr.ctypes.data, C.byref(done)) == 0, \
+            L.yttm_last_error(ctx)
+        launches = int(L.yttm_stage_ms(ctx, b"loop_launches"))
+        return [tuple(r) for r in rules[:3 * done.value].reshape(-1, 3).tolist()], launches, st
+    finally:
+        L.yttm_ctx_destroy(ctx)
+
+
+def _oracle_rules(oracle, text, vocab):
+    from _bind import read_model
+    m = tmp_model_path("orc")
+    oracle.train(text, m, vocab, 1.0)
+    return read_model(m)[1]
+
+
+def test_train_table_rebuilds_on_a_tiny_pair_table(emu, oracle, monkeypatch):
+    """YTTM_PAIR_CAP_FLOOR=16: the table starts at load 3/8 of a few dozen slots, so the loop stops again and
+    again for a rebuild (stop = 2 / probe overflow) — the relaunch path, with the tokens as the only truth."""
+    monkeypatch.setenv("YTTM_PAIR_CAP_FLOOR", "16")
+    text = _cases.zipf().text(20_000)
+    rules, launches, _ = _abi_train(emu, text, 700)
+    assert launches >= 2
+    assert rules == _oracle_rules(oracle, text, 700)
+
+
+def test_train_compaction_of_dead_slots(emu, oracle):
+    """> 65 536 token slots and enough merges to tombstone a quarter of them: the loop stops with stop = 3, the host
+    compacts the packed words (compact_len / scan / compact_copy) and relaunches on the other buffer."""
+    text = synth.readme_corpus(n_lines=1300, n_chars=100, seed=5)
+    rules, launches, st = _abi_train(emu, text, 260)
+    assert st.n_tokens > 65536 and launches >= 2
+    assert rules == _oracle_rules(oracle, text, 260)
+
+
+def test_train_deferred_list_overflow_falls_back_to_the_direct_pass(emu, oracle, monkeypatch):
+    monkeypatch.setenv("YTTM_FORCE_STREAM", "1")
+    monkeypatch.setenv("YTTM_STREAM_Q", "128")
+    monkeypatch.setenv("YTTM_DEFER_CAP", "1")
+    for seed in (0, 3):
+        text, vocab, cov, _ = _cases.stress_case(seed)
+        TG._same(oracle, text, vocab, cov)
+    TG._same(oracle, synth.readme_corpus(n_lines=120), 150)

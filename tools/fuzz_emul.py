@@ -1,0 +1,82 @@
+"""Fuzz the kernels under the SIMT emulator (tests/emul/simt; TEST HARNESS ONLY): random corpora x random
+geometry (blocks, STREAMING window, ring depth, pair-table floor, deferred-list capacity) against the oracle.
+usage: python tools/fuzz_emul.py [n_cases] [first_seed]"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+
+import _bind  # noqa: E402
+import _cases  # noqa: E402
+from _bind import read_model, tmp_model_path  # noqa: E402
+from _emu import emu_lib  # noqa: E402
+from youtokentome_b200 import synth  # noqa: E402
+
+KNOBS = ["YT_EMU_SMS", "YTTM_FORCE_STREAM", "YTTM_STREAM_Q", "YTTM_STAGES", "YTTM_PAIR_CAP_FLOOR", "YTTM_DEFER_CAP"]
+
+
+def corpus(rng):
+    kind = int(rng.integers(0, 5))
+    if kind == 0:
+        return synth.stress_text(int(rng.integers(0, 10 ** 6)))
+    if kind == 1:
+        return synth.readme_corpus(n_lines=int(rng.integers(5, 120)), n_chars=int(rng.integers(5, 120)),
+                                   alphabet="abcd "[:int(rng.integers(2, 5))] + " ", seed=int(rng.integers(0, 999)))
+    if kind == 2:
+        return _cases.zipf().text(int(rng.integers(2000, 40000)), seed=int(rng.integers(0, 999)))
+    if kind == 3:  # long runs and long words
+        parts = [bytes([int(rng.choice(list(b"ab")))]) * int(rng.integers(1, 400)) for _ in range(int(rng.integers(2, 60)))]
+        return b" ".join(parts) + b" " + b"ab" * int(rng.integers(1, 300))
+    t = _cases.dirty_zipf_text(int(rng.integers(3000, 30000)))
+    return t
+
+
+def main():
+    n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 50
+    first = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    _bind.build_checkers()
+    L, orc = emu_lib(), _bind.Oracle()
+    t0 = time.time()
+    for seed in range(first, first + n_cases):
+        rng = np.random.default_rng(seed)
+        text = corpus(rng)
+        n_chars = len(set(text.decode("utf-8", "ignore")))
+        vocab = n_chars + 4 + int(rng.integers(0, 120))
+        cov = 1.0 if rng.integers(0, 2) else 1 - float(rng.random()) * 0.2
+        env = {"YT_EMU_SMS": str(int(rng.integers(1, 5)))}
+        if rng.integers(0, 3):
+            env["YTTM_FORCE_STREAM"] = "1"
+            env["YTTM_STREAM_Q"] = str(int(rng.choice([16, 32, 64, 100, 256, 1000, 4096])))
+            env["YTTM_STAGES"] = str(int(rng.integers(2, 6)))
+            if rng.integers(0, 2):
+                env["YTTM_DEFER_CAP"] = str(int(rng.choice([1, 2, 5, 50])))
+        if rng.integers(0, 2):
+            env["YTTM_PAIR_CAP_FLOOR"] = str(int(rng.choice([16, 64, 256, 2048])))
+        for k in KNOBS:
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        m_o, m_e = tmp_model_path("fo"), tmp_model_path("fe")
+        try:
+            orc.train(text, m_o, vocab, cov)
+            want = read_model(m_o)
+        except ValueError as e:
+            want = str(e)
+        rc = L.yttm_api_train_memory(text, len(text), m_e.encode(), vocab, cov, 0, 1, 2, 3)
+        got = read_model(m_e) if rc == 0 else L.yttm_api_last_error(None).decode()
+        ok = got == want
+        print("seed %d  %6d B  vocab %4d  cov %.3f  %s  %s" % (seed, len(text), vocab, cov, env, "ok" if ok else "MISMATCH"),
+              flush=True)
+        if not ok:
+            sys.exit(1)
+        for p in (m_o, m_e):
+            if os.path.exists(p):
+                os.remove(p)
+    print("all %d cases ok in %.0f s" % (n_cases, time.time() - t0))
+
+
+if __name__ == "__main__":
+    main()

@@ -371,8 +371,14 @@ PairTab tab_of(yttm_ctx *c) {
 
 // (Re)build the pair table from the current packed words.  Grows the table until the load
 // factor after the build is <= 1/4.
+// smallest pair table; YTTM_PAIR_CAP_FLOOR lowers it so that tests reach the rebuild / overflow paths on tiny inputs
+static uint64_t pair_cap_floor() {
+  if (const char *e = std::getenv("YTTM_PAIR_CAP_FLOOR")) return ytc::pow2ceil((uint64_t)std::max(16, std::atoi(e)));
+  return 1u << 16;
+}
+
 int rebuild_pair_table(yttm_ctx *c, uint64_t min_cap) {
-  uint64_t cap = std::max<uint64_t>(ytc::pow2ceil(min_cap), 1u << 16);
+  uint64_t cap = std::max<uint64_t>(ytc::pow2ceil(min_cap), pair_cap_floor());
   YT_CUDA(c, c->ctl.reserve(sizeof(YtLoopCtl)));
   for (int attempt = 0; attempt < 24; attempt++) {
     YT_CUDA(c, c->pkey.reserve(cap * 8));
@@ -469,7 +475,8 @@ int plan_tiles(yttm_ctx *c, LoopArgs *a) {
     a->tile_desc = c->tiles.as<uint2>();
     a->n_tiles = (uint32_t)n_tiles;
     if (pass == 1) {
-      a->defer_cap = 8192;
+      a->defer_cap = 8192;  // words per block and merge on the deferred path; beyond it the direct pass takes over
+      if (const char *e = std::getenv("YTTM_DEFER_CAP")) a->defer_cap = (uint32_t)std::max(1, std::atoi(e));
       YT_CUDA(c, c->defer.reserve((size_t)c->loop_blocks * a->defer_cap * sizeof(uint4)));
       a->defer = c->defer.as<uint4>();
       break;
@@ -646,7 +653,7 @@ static int finish_build(yttm_ctx *c, yttm_train_stats *stats) {
   ytc::timer_begin(c, "pair_hist");
   // start small and let rebuild_pair_table grow to load <= 1/4: the arg-max sweeps the whole table
   // every merge, so a tight table is worth a few extra histogram launches here
-  int rc = rebuild_pair_table(c, 1u << 16);
+  int rc = rebuild_pair_table(c, pair_cap_floor());
   ytc::timer_end(c, "pair_hist");
   if (rc) return rc;
   YtLoopCtl *ctl = c->ctl.as<YtLoopCtl>();
@@ -936,7 +943,7 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
     if (why == 2) {
       uint32_t keep_done = h.n_done;
       // dead keys vanish in the rebuild, so the table usually keeps its size (it grows only if still above 3/8)
-      if (rebuild_pair_table(c, std::max<uint64_t>(h.overflow ? c->pcap * 2 : c->pcap / 2, 1u << 16))) return 1;
+      if (rebuild_pair_table(c, std::max<uint64_t>(h.overflow ? c->pcap * 2 : c->pcap / 2, pair_cap_floor()))) return 1;
       h.n_done = keep_done;
       YT_CUDA(c, cudaMemcpyAsync(&h.n_keys, &ctl->n_keys, 8, cudaMemcpyDeviceToHost, c->stream));
       YT_CUDA(c, cudaStreamSynchronize(c->stream));
