@@ -16,7 +16,61 @@ from _bind import read_model, tmp_model_path  # noqa: E402
 from _emu import emu_lib  # noqa: E402
 from youtokentome_b200 import synth  # noqa: E402
 
-KNOBS = ["YT_EMU_SMS", "YTTM_FORCE_STREAM", "YTTM_STREAM_Q", "YTTM_STAGES", "YTTM_PAIR_CAP_FLOOR", "YTTM_DEFER_CAP"]
+KNOBS = ["YT_EMU_SMS", "YTTM_FORCE_STREAM", "YTTM_STREAM_Q", "YTTM_STAGES", "YTTM_PAIR_CAP_FLOOR", "YTTM_DEFER_CAP",
+         "YTTM_ENC_BUCKETED", "YTTM_ENC_FIND_CACHED", "YTTM_ENC_CHUNK_MB"]
+
+
+def sentences(rng, text):
+    words = text.split() or [b"a"]
+    out = []
+    for _ in range(int(rng.integers(1, 120))):
+        k = int(rng.integers(0, 40))
+        s = b" ".join(words[int(i)] for i in rng.integers(0, len(words), k))
+        r = int(rng.integers(0, 8))
+        if r == 0:
+            s = s + b" \xff\xfe\xe2\x96 "
+        elif r == 1:
+            s = b"  " + s.replace(b" ", b"\xe2\x96\x81", 2) + b"\t"
+        elif r == 2:
+            s = s + b" unseen-\xd1\x8f\xf0\x9f\x98\x80 zzz"
+        elif r == 3 and words:
+            s = b"".join(words[int(i)] for i in rng.integers(0, len(words), int(rng.integers(1, 30))))  # one long word
+        out.append(s)
+    return out + list(_cases.EDGE_SENTENCES)
+
+
+def encode_case(rng, L, orc, model, text):
+    import ctypes as C
+    sents = sentences(rng, text)
+    buf, offs = _bind._pack(sents)
+    o = orc.encoder(model)
+    h = L.yttm_api_open(model.encode(), 1)
+    assert h
+    try:
+        for _ in range(3):
+            kw = dict(bos=bool(rng.integers(0, 2)), eos=bool(rng.integers(0, 2)), reverse=bool(rng.integers(0, 2)))
+            p = float(rng.choice([0.0, 0.0, 0.1, 0.5, 1.0]))
+            seed = int(rng.integers(0, 2 ** 31))
+            for k in ("YTTM_ENC_BUCKETED", "YTTM_ENC_FIND_CACHED"):
+                os.environ.pop(k, None)
+                if rng.integers(0, 2):
+                    os.environ[k] = "1"
+            want = o.encode(sents, dropout=p, seed=seed, **kw)
+            L.yttm_api_set_dropout_seed(h, seed)
+            total = C.c_uint64(0)
+            rc = L.yttm_api_encode_ids(h, buf, offs.ctypes.data, len(sents), int(kw["bos"]), int(kw["eos"]),
+                                       int(kw["reverse"]), p, C.byref(total))
+            assert rc == 0, L.yttm_api_last_error(h)
+            ids = np.zeros(max(total.value, 1), dtype=np.int32)
+            oo = np.zeros(len(sents) + 1, dtype=np.uint64)
+            L.yttm_api_result_ids(h, ids.ctypes.data, oo.ctypes.data)
+            got = _bind._unpack(ids[:total.value], oo)
+            if got != want:
+                print("ENCODE MISMATCH", kw, p, seed, {k: os.environ.get(k) for k in KNOBS})
+                return False
+    finally:
+        L.yttm_api_close(h)
+    return True
 
 
 def corpus(rng):
@@ -68,6 +122,8 @@ def main():
         rc = L.yttm_api_train_memory(text, len(text), m_e.encode(), vocab, cov, 0, 1, 2, 3)
         got = read_model(m_e) if rc == 0 else L.yttm_api_last_error(None).decode()
         ok = got == want
+        if ok and rc == 0:
+            ok = encode_case(rng, L, orc, m_o, text)
         print("seed %d  %6d B  vocab %4d  cov %.3f  %s  %s" % (seed, len(text), vocab, cov, env, "ok" if ok else "MISMATCH"),
               flush=True)
         if not ok:
