@@ -268,11 +268,18 @@ static void encode(const Model &m, const uint8_t *s, uint64_t n, bool bos, bool 
                    uint64_t seed, uint64_t sent_index, std::vector<int32_t> *out) {
   size_t out0 = out->size();
   if (bos) out->push_back(m.bos);
-  // decode_utf8 (utf8.cpp:111-128) drops invalid bytes; keep each unit's byte offset for the RNG key
+  // decode_utf8 (utf8.cpp:111-128) drops invalid bytes.  For the RNG key every kept unit remembers the byte offset
+  // at which its WORD starts on the raw bytes: the first unit - valid or not - of the maximal run of non-space
+  // units it belongs to (an invalid byte is a non-space unit: "\xc0\xafabc" is one word starting at offset 0).
   std::vector<uint32_t> cps; std::vector<uint32_t> offs;
+  bool in_word = false;
+  uint32_t word_start = 0;
   for (uint64_t p = 0; p < n;) {
     uint32_t len, cp = decode_one(s + p, n - p, &len);
-    if (cp != INVALID_CP) { cps.push_back(cp); offs.push_back((uint32_t)p); }
+    const bool space = cp != INVALID_CP && is_space(cp);
+    if (space) in_word = false;
+    else if (!in_word) { in_word = true; word_start = (uint32_t)p; }
+    if (cp != INVALID_CP) { cps.push_back(cp); offs.push_back(space ? (uint32_t)p : word_start); }
     p += len;
   }
   while (!cps.empty() && is_space(cps.back())) { cps.pop_back(); offs.pop_back(); }  // bpe.cpp:1500

@@ -7,6 +7,8 @@ EDGE_SENTENCES = [
     b"", b" ", b"   \t\n ", b"a", b" a ", b"a\xff\xfeb \xe2\x96\x81 c\xe2\x96", b"\x80\x80 \xbf", "яы a".encode(),
     b"aaaaaaaaaaaaaaaaaaaa aaaaaaa", b"abcabcabc" * 40, ("▁".join(["ab", "cd", "e"])).encode(),
     b"\xf0\x9f\x98\x80 \xf0\x9f\x98 \xed\xa0\x80 \xc0\xaf z", b"d d", b"a  b   c    d", "日本語 テキスト abc".encode(),
+    # words that START with invalid bytes (the BPE-dropout key uses the word's raw start) - found by tools/fuzz_emul.py
+    b"\xc0\xafabcabc ab \xff\xfeabab\xff ba \x80b\xe2\x96ab",
 ]
 
 
