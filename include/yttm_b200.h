@@ -115,7 +115,9 @@ void yttm_enc_destroy(yttm_enc *enc);
 /* encode_as_ids (bpe.cpp:1740): sentence i = bytes[offsets[i], offsets[i+1]).  HOST buffers;
  * H2D / D2H inside.  out_offsets has n_sent+1 entries; *out_n = total ids.  If out_cap is too
  * small returns 2 with *out_n = required size (nothing written).  dropout > 0 draws from
- * Philox4x32-10 keyed (seed, first_sentence_index + i, word byte offset, draw#). */
+ * Philox4x32-10 keyed (seed, first_sentence_index + i, word byte offset, draw#); the word byte offset is the
+ * offset inside the sentence of the first byte of the word's maximal run of non-space units, invalid bytes
+ * included ("\xc0\xafabc" is one word at offset 0). */
 int yttm_enc_run(yttm_enc *enc, const char *bytes, const uint64_t *offsets, uint64_t n_sent, int bos, int eos,
                  int reverse, double dropout, uint64_t seed, uint64_t first_sentence_index, int32_t *out_ids,
                  uint64_t out_cap, uint64_t *out_offsets, uint64_t *out_n);
