@@ -195,10 +195,10 @@ __device__ __forceinline__ uint32_t warp_apply_word(uint32_t *st, uint32_t cap, 
   return n - n2;
 }
 
-// One tile whose token slots sit in shared memory (`span` slots at stok, word w at
-// [soff[w] - obase, soff[w+1] - obase)).  The scan is TOKEN-parallel: a lane compares slot i and
-// i+1 with (x, y) — consecutive lanes read consecutive words of shared memory, every lane does
-// the same work whatever the word lengths.  A hit cannot straddle two words: the first token
+// One RESIDENT tile: its token slots sit in shared memory (`span` slots at stok, word w at
+// [soff[w], soff[w+1])).  The scan is TOKEN-parallel: a lane compares four consecutive slots and
+// the one after them with (x, y) — consecutive lanes read consecutive 16-byte pieces of shared
+// memory, every lane does the same work whatever the word lengths.  A hit cannot straddle two words: the first token
 // of every word is (derived from) the "▁" token, which only ever occurs at position 0, so y —
 // the second element of an in-word pair — is never a word-initial token; tail padding (DEAD)
 // matches nothing.  Each hit is mapped to its word (binary search in the offsets), the word is
