@@ -244,7 +244,7 @@ template <bool DROPOUT>
 __global__ void __launch_bounds__(128) encode_words_bucketed_kernel(EncArgs a, uint64_t n_words) {
   constexpr uint32_t LOCAL_W = 40;
   __shared__ uint32_t s_pos[BUCKET_WINDOW], s_sent[BUCKET_WINDOW], s_end[BUCKET_WINDOW];
-  __shared__ uint16_t s_perm[BUCKET_WINDOW];
+  __shared__ uint16_t s_perm[BUCKET_WINDOW], s_key[BUCKET_WINDOW], s_rk[BUCKET_WINDOW];
   __shared__ uint32_t s_hist[BUCKET_KEYS];
   const uint64_t o0 = a.offs[0];
   const RuleTab rt = a.rt;
@@ -255,27 +255,22 @@ __global__ void __launch_bounds__(128) encode_words_bucketed_kernel(EncArgs a, u
     const uint32_t cnt = (uint32_t)min((uint64_t)BUCKET_WINDOW, n_words - w0);
     if (threadIdx.x < BUCKET_KEYS) s_hist[threadIdx.x] = 0;
     __syncthreads();
-    uint32_t key[BUCKET_WINDOW / 128], rk[BUCKET_WINDOW / 128];
-#pragma unroll
-    for (uint32_t j = 0; j < BUCKET_WINDOW / 128; j++) {
-      const uint32_t i = j * 128 + threadIdx.x;
-      key[j] = 0;
-      rk[j] = 0;
-      if (i < cnt) {
-        const uint64_t p0 = a.word_pos[w0 + i], s = a.word_sent[w0 + i];
-        const uint64_t hi = a.offs[s + 1] - o0;
-        uint64_t q = p0;
-        uint32_t l, units = 0;
-        while (q < hi && !space_at(a.bytes, q, hi, &l)) {
-          units += (a.bytes[q] & 0xC0u) != 0x80u;
-          q++;
-        }
-        s_pos[i] = (uint32_t)p0;
-        s_sent[i] = (uint32_t)s;
-        s_end[i] = (uint32_t)q;
-        key[j] = min(units, BUCKET_KEYS - 1);
-        rk[j] = atomicAdd(&s_hist[key[j]], 1u);  // arrival order inside the bucket (any order is valid)
+#pragma unroll 1
+    for (uint32_t i = threadIdx.x; i < cnt; i += 128) {  // measure: word end, token count before merging
+      const uint64_t p0 = a.word_pos[w0 + i], s = a.word_sent[w0 + i];
+      const uint64_t hi = a.offs[s + 1] - o0;
+      uint64_t q = p0;
+      uint32_t l, units = 0;
+      while (q < hi && !space_at(a.bytes, q, hi, &l)) {
+        units += (a.bytes[q] & 0xC0u) != 0x80u;
+        q++;
       }
+      s_pos[i] = (uint32_t)p0;
+      s_sent[i] = (uint32_t)s;
+      s_end[i] = (uint32_t)q;
+      const uint32_t key = min(units, BUCKET_KEYS - 1);
+      s_key[i] = (uint16_t)key;
+      s_rk[i] = (uint16_t)atomicAdd(&s_hist[key], 1u);  // arrival order inside the bucket (any order is valid)
     }
     __syncthreads();
     if (threadIdx.x < 32) {  // exclusive scan of the 64 bucket sizes by one warp, longest words first
@@ -291,12 +286,10 @@ __global__ void __launch_bounds__(128) encode_words_bucketed_kernel(EncArgs a, u
       s_hist[k1] = tot0 + x1 - c1;
     }
     __syncthreads();
-#pragma unroll
-    for (uint32_t j = 0; j < BUCKET_WINDOW / 128; j++) {
-      const uint32_t i = j * 128 + threadIdx.x;
-      if (i < cnt) s_perm[s_hist[key[j]] + rk[j]] = (uint16_t)i;
-    }
+#pragma unroll 1
+    for (uint32_t i = threadIdx.x; i < cnt; i += 128) s_perm[s_hist[s_key[i]] + s_rk[i]] = (uint16_t)i;
     __syncthreads();
+#pragma unroll 1
     for (uint32_t j = threadIdx.x; j < cnt; j += 128) {
       const uint32_t i = s_perm[j];
       const uint64_t p0 = s_pos[i], s = s_sent[i], q = s_end[i];
