@@ -145,6 +145,47 @@ def test_encode_find_cached_variant(emu, oracle, monkeypatch):
     assert g.encode(sents, bos=True) == o.encode(sents, bos=True)
 
 
+@pytest.mark.parametrize("special", [dict(), dict(pad=-1, bos=-1, eos=7, unk=0), dict(pad=3, unk=40, bos=41, eos=1000)])
+def test_encode_linear_product_id_variant(emu, oracle, monkeypatch, special):
+    """YTTM_ENC_ZLIN (experimental, off by default): the id a rule produces is computed from its rank (special ids
+    skipped) instead of probing the table again; enabled by the host only if it reproduces every rule of the model."""
+    monkeypatch.setenv("YTTM_ENC_ZLIN", "1")
+    m = tmp_model_path("orc")
+    oracle.train(_cases.dirty_zipf_text(), m, 1200, 1.0, **special)
+    sents = _cases.zipf_sentences(300) + _cases.EDGE_SENTENCES
+    g, o = EG.GpuEncoder(m), oracle.encoder(m)
+    kws = [dict(), dict(reverse=True)] + ([dict(eos=True)] if special.get("eos", 3) != -1 else [])
+    for kw in kws:
+        assert g.encode(sents, **kw) == o.encode(sents, **kw)
+    assert g.encode(sents, dropout=0.4, seed=11) == o.encode(sents, dropout=0.4, seed=11)
+    assert emu.yttm_stage_ms(emu.yttm_api_device_context(g.h), b"enc_variant") == 3.0  # the shortcut really ran
+
+
+def test_encode_linear_product_id_is_refused_for_a_foreign_model(emu, oracle, monkeypatch, tmp_path):
+    """A model whose rule products are NOT the k-th free id (two product ids swapped by hand): the shortcut must be
+    switched off by the check at load time, the result stays exact."""
+    from _bind import read_model
+    monkeypatch.setenv("YTTM_ENC_ZLIN", "1")
+    m = tmp_model_path("orc")
+    oracle.train(synth.readme_corpus(n_lines=200), m, 60, 1.0)
+    c2i, rules, special = read_model(m)
+    a, b = rules[5][2], rules[9][2]
+    swap = {a: b, b: a}
+    rules2 = [tuple(swap.get(v, v) for v in r) for r in rules]
+    m2 = str(tmp_path / "swapped.yttm")
+    with open(m2, "w") as f:
+        f.write("%d %d\n" % (len(c2i), len(rules2)))
+        for cp, i in c2i.items():
+            f.write("%d %d\n" % (cp, i))
+        for r in rules2:
+            f.write("%d %d %d\n" % r)
+        f.write("%d %d %d %d\n" % special)
+    sents = [synth.readme_corpus(n_lines=3, seed=4), b"abab cdcd abcd", b"dddd aaaa"]
+    g = EG.GpuEncoder(m2)
+    assert g.encode(sents) == oracle.encoder(m2).encode(sents)
+    assert emu.yttm_stage_ms(emu.yttm_api_device_context(g.h), b"enc_variant") == 0.0  # refused: default kernel
+
+
 def test_encode_chunked_pipeline(emu, oracle, monkeypatch):
     m = EG._model(oracle, _cases.dirty_zipf_text(), 1500)
     zc = _cases.zipf()

@@ -35,8 +35,9 @@ def main(L=None, n_sent=None, reps=None, train_bytes=20_000_000, vocab=8000):
     base = None
     out = {}
     for name, env in [("default", []), ("find_cached", ["YTTM_ENC_FIND_CACHED"]), ("bucketed", ["YTTM_ENC_BUCKETED"]),
-                      ("both", ["YTTM_ENC_FIND_CACHED", "YTTM_ENC_BUCKETED"])]:
-        for k in ("YTTM_ENC_FIND_CACHED", "YTTM_ENC_BUCKETED"):
+                      ("both", ["YTTM_ENC_FIND_CACHED", "YTTM_ENC_BUCKETED"]),
+                      ("both+zlin", ["YTTM_ENC_FIND_CACHED", "YTTM_ENC_BUCKETED", "YTTM_ENC_ZLIN"])]:
+        for k in ("YTTM_ENC_FIND_CACHED", "YTTM_ENC_BUCKETED", "YTTM_ENC_ZLIN"):
             os.environ.pop(k, None)
         for k in env:
             os.environ[k] = "1"

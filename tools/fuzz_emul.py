@@ -17,7 +17,7 @@ from _emu import emu_lib  # noqa: E402
 from youtokentome_b200 import synth  # noqa: E402
 
 KNOBS = ["YT_EMU_SMS", "YTTM_FORCE_STREAM", "YTTM_STREAM_Q", "YTTM_STAGES", "YTTM_PAIR_CAP_FLOOR", "YTTM_DEFER_CAP",
-         "YTTM_ENC_BUCKETED", "YTTM_ENC_FIND_CACHED", "YTTM_ENC_CHUNK_MB"]
+         "YTTM_ENC_BUCKETED", "YTTM_ENC_FIND_CACHED", "YTTM_ENC_ZLIN", "YTTM_ENC_CHUNK_MB"]
 
 
 def sentences(rng, text):
@@ -51,7 +51,7 @@ def encode_case(rng, L, orc, model, text):
             kw = dict(bos=bool(rng.integers(0, 2)), eos=bool(rng.integers(0, 2)), reverse=bool(rng.integers(0, 2)))
             p = float(rng.choice([0.0, 0.0, 0.1, 0.5, 1.0]))
             seed = int(rng.integers(0, 2 ** 31))
-            for k in ("YTTM_ENC_BUCKETED", "YTTM_ENC_FIND_CACHED"):
+            for k in ("YTTM_ENC_BUCKETED", "YTTM_ENC_FIND_CACHED", "YTTM_ENC_ZLIN"):
                 os.environ.pop(k, None)
                 if rng.integers(0, 2):
                     os.environ[k] = "1"

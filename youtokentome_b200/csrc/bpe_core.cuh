@@ -218,10 +218,28 @@ YT_HD bool dropout_skip(uint64_t seed, uint64_t sent, uint32_t word_off, uint32_
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t NO_RANK_V = 0xffffffffu;
 
-template <class RankFn>
+// Optional shortcut for the id a rule produces.  In a model written by this trainer or by the reference, rule
+// number k makes the k-th id after the characters, special ids skipped (rename_tokens bpe.cpp:814-837), so z is a
+// function of the rank and the merge step need not probe the table again for it.  The host enables a ZFn only after
+// checking it against every rule of the loaded model (yttm_enc_create); NoZFn = always re-probe.
+struct NoZFn {
+  static constexpr bool enabled = false;
+  YT_HD uint32_t operator()(uint32_t) const { return 0; }
+};
+struct LinearZFn {
+  static constexpr bool enabled = true;
+  uint32_t base, skip[4];  // z = base + rank, then +1 for every special id (ascending, 0xffffffff = unused) <= z
+  YT_HD uint32_t operator()(uint32_t rank) const {
+    uint32_t z = base + rank;
+    for (int k = 0; k < 4; k++) z += skip[k] <= z ? 1u : 0u;
+    return z;
+  }
+};
+
+template <class RankFn, class ZFn = NoZFn>
 YT_HD uint32_t encode_word(const uint8_t *s, uint64_t p0, uint64_t lo, uint64_t hi, const uint32_t *cp2id,
                            uint32_t space_id, RankFn rank, uint32_t *zr, uint64_t drop_thresh, uint64_t seed, uint64_t sent_index,
-                           int32_t *t, uint32_t *r, uint32_t *aux, uint32_t *slots_owned) {
+                           int32_t *t, uint32_t *r, uint32_t *aux, uint32_t *slots_owned, ZFn zfn = ZFn()) {
   uint32_t n = 1, l;
   bool last_unk = false;
   uint64_t q = p0;
@@ -247,7 +265,7 @@ YT_HD uint32_t encode_word(const uint8_t *s, uint64_t p0, uint64_t lo, uint64_t 
       for (uint32_t i = 0; i + 1 < n; i++)
         if (r[i] < best) { best = r[i]; bi = i; }
       if (best == NO_RANK_V) break;
-      if (zr) z = zr[bi]; else rank((uint32_t)t[bi], (uint32_t)t[bi + 1], &z);
+      if (zr) z = zr[bi]; else if (ZFn::enabled) z = zfn(best); else rank((uint32_t)t[bi], (uint32_t)t[bi + 1], &z);
       t[bi] = (int32_t)z;
       for (uint32_t i = bi + 1; i + 1 < n; i++) { t[i] = t[i + 1]; if (i + 2 < n) { r[i] = r[i + 1]; if (zr) zr[i] = zr[i + 1]; } }
       n--;
@@ -293,7 +311,7 @@ YT_HD uint32_t encode_word(const uint8_t *s, uint64_t p0, uint64_t lo, uint64_t 
     const uint32_t p1 = bp, p2 = nx[p1], pl = pv[p1], p3 = nx[p2];
     if (pl != NIL && r[pl] != NO_RANK_V) { st_rule[n_stale] = r[pl]; st_pos[n_stale++] = pl; }
     if (r[p2] != NO_RANK_V) { st_rule[n_stale] = r[p2]; st_pos[n_stale++] = p2; }
-    rank((uint32_t)t[p1], (uint32_t)t[p2], &z);
+    if (ZFn::enabled) z = zfn(br); else rank((uint32_t)t[p1], (uint32_t)t[p2], &z);
     t[p1] = (int32_t)z;
     nx[p1] = p3;
     if (p3 != NIL) pv[p3] = p1;

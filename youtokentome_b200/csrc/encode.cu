@@ -240,8 +240,8 @@ __global__ void __launch_bounds__(128) encode_words_kernel(EncArgs a, uint64_t n
 // nearly the same length: the merge loop of encode_word is data-dependent (decode + ~2.5 probes per
 // token), and with thread-per-word every warp used to run as long as its longest word.
 constexpr uint32_t BUCKET_WINDOW = 512, BUCKET_KEYS = 64;
-template <bool DROPOUT>
-__global__ void __launch_bounds__(128) encode_words_bucketed_kernel(EncArgs a, uint64_t n_words) {
+template <bool DROPOUT, bool ZLIN>
+__global__ void __launch_bounds__(128) encode_words_bucketed_kernel(EncArgs a, uint64_t n_words, LinearZFn zlin) {
   constexpr uint32_t LOCAL_W = 40;
   __shared__ uint32_t s_pos[BUCKET_WINDOW], s_sent[BUCKET_WINDOW], s_end[BUCKET_WINDOW];
   __shared__ uint16_t s_perm[BUCKET_WINDOW], s_key[BUCKET_WINDOW], s_rk[BUCKET_WINDOW];
@@ -301,12 +301,20 @@ __global__ void __launch_bounds__(128) encode_words_bucketed_kernel(EncArgs a, u
         int32_t lt[LOCAL_W];
         uint32_t lr[LOCAL_W];
         uint32_t laux[DROPOUT ? 6 * LOCAL_W : 1];
-        n = encode_word(a.bytes, p0, lo, hi, a.cp2id, a.space_id, rank, nullptr, DROPOUT ? a.drop_thresh : 0, a.seed,
-                        a.first_sentence + s, lt, lr, laux, &owned);
+        if (ZLIN)
+          n = encode_word(a.bytes, p0, lo, hi, a.cp2id, a.space_id, rank, nullptr, DROPOUT ? a.drop_thresh : 0, a.seed,
+                          a.first_sentence + s, lt, lr, laux, &owned, zlin);
+        else
+          n = encode_word(a.bytes, p0, lo, hi, a.cp2id, a.space_id, rank, nullptr, DROPOUT ? a.drop_thresh : 0, a.seed,
+                          a.first_sentence + s, lt, lr, laux, &owned);
         for (uint32_t k = 0; k < n; k++) t[k] = ((uint32_t)lt[k] & UNK_FLAG) ? a.unk_id : lt[k];
       } else {
-        n = encode_word(a.bytes, p0, lo, hi, a.cp2id, a.space_id, rank, nullptr, DROPOUT ? a.drop_thresh : 0, a.seed,
-                        a.first_sentence + s, t, a.ranks + slot0, DROPOUT ? a.aux + 6 * slot0 : nullptr, &owned);
+        if (ZLIN)
+          n = encode_word(a.bytes, p0, lo, hi, a.cp2id, a.space_id, rank, nullptr, DROPOUT ? a.drop_thresh : 0, a.seed,
+                          a.first_sentence + s, t, a.ranks + slot0, DROPOUT ? a.aux + 6 * slot0 : nullptr, &owned, zlin);
+        else
+          n = encode_word(a.bytes, p0, lo, hi, a.cp2id, a.space_id, rank, nullptr, DROPOUT ? a.drop_thresh : 0, a.seed,
+                          a.first_sentence + s, t, a.ranks + slot0, DROPOUT ? a.aux + 6 * slot0 : nullptr, &owned);
         for (uint32_t k = 0; k < n; k++)
           if ((uint32_t)t[k] & UNK_FLAG) t[k] = a.unk_id;
         for (uint32_t k = n; k < owned; k++) t[k] = EMPTY_SLOT;
@@ -347,6 +355,8 @@ struct yttm_enc {
   yttm_ctx *ctx = nullptr;
   ytc::DevBuf cp2id, rules;
   uint32_t rule_mask = 0, space_id = 0;
+  bool zlin_ok = false;  // every rule's product id equals LinearZFn(rank): checked at create time
+  LinearZFn zlin{0, {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}};
   int unk = -1, pad = -1, bos = -1, eos = -1;
   // per-call device buffers: two sets, so that the host-buffer entry point can pipeline chunks
   // (H2D of chunk i+1 and D2H of chunk i-1 overlap the kernels of chunk i)
@@ -416,11 +426,17 @@ int enc_device(yttm_enc *enc, yttm_enc::Slot *e, const uint8_t *d_bytes, const u
   if (n_words) {
     uint64_t blocks = std::min<uint64_t>((n_words + 127) / 128, (uint64_t)c->n_sm * 16);
     ytc::timer_begin(c, "enc_words");
-    const bool bucketed = std::getenv("YTTM_ENC_BUCKETED") != nullptr;  // experimental, see the kernel
+    // experimental kernels, see there; the linear product-id shortcut exists in the bucketed kernel only
+    const bool zlin = enc->zlin_ok && std::getenv("YTTM_ENC_ZLIN") != nullptr;
+    const bool bucketed = zlin || std::getenv("YTTM_ENC_BUCKETED") != nullptr;
+    c->timers["enc_variant"].ms = (float)((zlin ? 2 : 0) + (bucketed ? 1 : 0));  // yttm_stage_ms(ctx, "enc_variant")
     if (bucketed) {
       const unsigned wb = (unsigned)std::min<uint64_t>((n_words + BUCKET_WINDOW - 1) / BUCKET_WINDOW, (uint64_t)c->n_sm * 16);
-      if (a.drop_thresh) encode_words_bucketed_kernel<true><<<wb, 128, 0, c->stream>>>(a, n_words);
-      else encode_words_bucketed_kernel<false><<<wb, 128, 0, c->stream>>>(a, n_words);
+      if (zlin) {
+        if (a.drop_thresh) encode_words_bucketed_kernel<true, true><<<wb, 128, 0, c->stream>>>(a, n_words, enc->zlin);
+        else encode_words_bucketed_kernel<false, true><<<wb, 128, 0, c->stream>>>(a, n_words, enc->zlin);
+      } else if (a.drop_thresh) encode_words_bucketed_kernel<true, false><<<wb, 128, 0, c->stream>>>(a, n_words, enc->zlin);
+      else encode_words_bucketed_kernel<false, false><<<wb, 128, 0, c->stream>>>(a, n_words, enc->zlin);
     } else if (a.drop_thresh) encode_words_kernel<true><<<(unsigned)blocks, 128, 0, c->stream>>>(a, n_words);
     else encode_words_kernel<false><<<(unsigned)blocks, 128, 0, c->stream>>>(a, n_words);
     ytc::timer_end(c, "enc_words");
@@ -484,6 +500,17 @@ int yttm_enc_create(yttm_ctx *c, const uint32_t *char_cp, const uint32_t *char_i
     else slots[h] = make_uint4(x, y, (uint32_t)i, z);
   }
   e->rule_mask = (uint32_t)(cap - 1);
+  {  // can the id a rule produces be computed from its rank?  (true for models of this trainer / the reference)
+    int sp[4] = {unk_id, pad_id, bos_id, eos_id};
+    std::sort(sp, sp + 4);
+    int k = 0;
+    for (int v : sp)
+      if (v >= 0 && (k == 0 || e->zlin.skip[k - 1] != (uint32_t)v)) e->zlin.skip[k++] = (uint32_t)v;
+    e->zlin.base = (uint32_t)n_chars;
+    e->zlin_ok = n_rules > 0;
+    for (uint64_t h = 0; h < cap && e->zlin_ok; h++)
+      if (slots[h].x != 0xffffffffu && e->zlin(slots[h].z) != slots[h].w) e->zlin_ok = false;
+  }
   if (e->cp2id.reserve(CP_LIMIT * 4) != cudaSuccess || e->rules.reserve(cap * 16) != cudaSuccess) {
     delete e;
     YT_FAIL(c, "yttm_enc_create: out of device memory");
