@@ -4,7 +4,8 @@
 // run queue.  A fiber leaves the CPU only at a rendezvous (warp collective, __syncthreads, grid.sync) or in an
 // explicit emu::yield() of a spin loop, so the interleaving is deterministic for a given launch.  A normal launch
 // runs its blocks one after the other on the calling thread; a cooperative launch gives every block its own OS
-// thread and grid.sync() is a pthread barrier entered by the last fiber of each block.
+// thread and grid.sync() is a pthread barrier entered by the last fiber of each block.  With YT_EMU_SCHED_SEED=n the
+// next fiber is drawn at random from the run queue instead of in FIFO order.
 #include <pthread.h>
 #include <stdio.h>
 #include <sys/mman.h>
@@ -167,6 +168,10 @@ void run_block(unsigned bid, unsigned grid, unsigned threads, size_t smem, const
     f.sp = sp;
     blk.runq.push_back(&f);
   }
+  const char *ss = getenv("YT_EMU_SCHED_SEED");
+  const uint64_t sched_seed = ss ? strtoull(ss, nullptr, 10) : 0;
+  uint64_t rng = (sched_seed * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)bid + 1) * 0xD1B54A32D192ED03ull;
+  if (!rng) rng = 1;
   Block *outer_blk = t_blk;
   Coords *outer_co = t_coords;
   t_blk = &blk;
@@ -176,6 +181,10 @@ void run_block(unsigned bid, unsigned grid, unsigned threads, size_t smem, const
       fprintf(stderr, "simt_emu: DEADLOCK in block %u: %u of %u threads finished, %u at a block/grid barrier\n", bid, done,
               threads, blk.sync_arrived);
       abort();
+    }
+    if (sched_seed) {  // YT_EMU_SCHED_SEED: any runnable fiber may go next (order-dependence / missing-barrier hunt)
+      rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+      std::swap(blk.runq.front(), blk.runq[rng % blk.runq.size()]);
     }
     Fiber *f = blk.runq.front();
     blk.runq.pop_front();

@@ -16,7 +16,7 @@ from _bind import read_model, tmp_model_path  # noqa: E402
 from _emu import emu_lib  # noqa: E402
 from youtokentome_b200 import synth  # noqa: E402
 
-KNOBS = ["YT_EMU_SMS", "YTTM_FORCE_STREAM", "YTTM_STREAM_Q", "YTTM_STAGES", "YTTM_PAIR_CAP_FLOOR", "YTTM_DEFER_CAP",
+KNOBS = ["YT_EMU_SMS", "YT_EMU_SCHED_SEED", "YTTM_FORCE_STREAM", "YTTM_STREAM_Q", "YTTM_STAGES", "YTTM_PAIR_CAP_FLOOR", "YTTM_DEFER_CAP",
          "YTTM_ENC_BUCKETED", "YTTM_ENC_FIND_CACHED", "YTTM_ENC_ZLIN", "YTTM_ENC_CHUNK_MB"]
 
 
@@ -102,6 +102,8 @@ def main():
         vocab = n_chars + 4 + int(rng.integers(0, 120))
         cov = 1.0 if rng.integers(0, 2) else 1 - float(rng.random()) * 0.2
         env = {"YT_EMU_SMS": str(int(rng.integers(1, 5)))}
+        if rng.integers(0, 2):
+            env["YT_EMU_SCHED_SEED"] = str(int(rng.integers(1, 10 ** 6)))  # random fiber order inside every block
         if rng.integers(0, 3):
             env["YTTM_FORCE_STREAM"] = "1"
             env["YTTM_STREAM_Q"] = str(int(rng.choice([16, 32, 64, 100, 256, 1000, 4096])))
