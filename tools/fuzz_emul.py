@@ -74,7 +74,7 @@ def encode_case(rng, L, orc, model, text):
 
 
 def corpus(rng):
-    kind = int(rng.integers(0, 5))
+    kind = int(rng.integers(0, 7))
     if kind == 0:
         return synth.stress_text(int(rng.integers(0, 10 ** 6)))
     if kind == 1:
@@ -85,8 +85,14 @@ def corpus(rng):
     if kind == 3:  # long runs and long words
         parts = [bytes([int(rng.choice(list(b"ab")))]) * int(rng.integers(1, 400)) for _ in range(int(rng.integers(2, 60)))]
         return b" ".join(parts) + b" " + b"ab" * int(rng.integers(1, 300))
-    t = _cases.dirty_zipf_text(int(rng.integers(3000, 30000)))
-    return t
+    if kind == 4:
+        return _cases.dirty_zipf_text(int(rng.integers(3000, 30000)))
+    if kind == 5:  # every kind of separator, NUL, stray continuation / truncated bytes between short words
+        alphabet = [b"a", b"b", b"ab", b"\x00", b"\t", b"\n", b"\r", b"\x0b", b"\x0c", b" ", b"\xe2\x96\x81", b"\xe2\x96", b"\x81",
+                    b"\xff", b"\xc3\xa9", b"\xf0\x9f\x98\x80", b"\xf0\x9f", b"\xed\xa0\x80", b"\xc0\xaf", "я".encode(), "日".encode()]
+        return b"".join(alphabet[int(i)] for i in rng.integers(0, len(alphabet), int(rng.integers(1, 3000))))
+    # degenerate corpora
+    return [b"", b" ", b"a", b"\xff", b"   \n\t ", b"aaaa", b"a a a a", b"\xe2\x96\x81", b"ab", "я".encode() * 3][int(rng.integers(0, 10))]
 
 
 def main():
