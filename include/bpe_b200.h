@@ -23,6 +23,8 @@ namespace vkcom {
 // a hash map is part of the API, so the standard container is used here
 template <class K, class V>
 using flat_hash_map = std::unordered_map<K, V>;
+template <class K>
+using flat_hash_set = std::unordered_set<K>;
 
 const uint32_t SPACE_TOKEN = 9601;  // U+2581, utils.h:9
 
