@@ -1,0 +1,11 @@
+#!/bin/bash
+# A/B of merge-loop launch geometry on a B200: µs per merge and phase split (tools/probe_train.py) for each setting.
+#   usage: tools/ab_train.sh [corpus: zipf|readme] [vocab] [bytes]
+cd "$(dirname "$0")/.."
+C=${1:-zipf}; V=${2:-32000}; B=${3:-100e6}
+for t in 1024 512 256; do
+  echo "== YTTM_LOOP_THREADS=$t"
+  YTTM_LOOP_THREADS=$t python tools/probe_train.py "$C" "$V" "$B" 2>/dev/null | tail -1 | cut -c1-600
+done
+echo "== YTTM_DBG=8 (per-block apply timers; perturbs the loop by ~1.5 us / merge)"
+YTTM_DBG=8 python tools/probe_train.py "$C" "$V" "$B" 2>/dev/null | tail -1 | cut -c1-900
