@@ -1,0 +1,22 @@
+#!/bin/bash
+# First GPU session of the next round, one gpurun call (≈ 8–10 GPU-minutes):
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_session_round2.sh'
+# 1. the GPU tests (incl. the reference's own stress test binary and the byte-identical model file test),
+# 2. A/B of the experimental encode kernels and of the merge-loop geometry,
+# 3. ncu: launch list of bench.py and one --set full capture of encode_words (default and bucketed).
+# Everything lands in gpurun_out/ ; copy what is to be judged into profiles/ (r02_*).
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+{
+echo "### pytest -m gpu"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+echo "### ab_encode"; timeout 300 python tools/ab_encode.py 1000000 7 2>/dev/null | tail -45
+echo "### ab_train"; timeout 400 bash tools/ab_train.sh zipf 32000 100e6
+echo "### bench"; timeout 600 python bench.py > gpurun_out/r02_bench_first.json 2> gpurun_out/r02_bench_first.err; echo "bench rc=$?"
+echo "### ncu launch list"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+    --log-file gpurun_out/r02_launches.csv python bench.py --steps 2 --warmup 3 --scan-tokens 67108864 > /dev/null 2>&1; echo "rc=$?"
+echo "### ncu encode_words (default)"; timeout 400 ncu --set full --clock-control none --import-source on -k regex:encode_words -s 2 -c 1 -f \
+    -o gpurun_out/r02_prof_encode_words python tools/ab_encode.py 1000000 1 > /dev/null 2>&1; echo "rc=$?"
+echo "### ncu encode_words (bucketed)"; YTTM_ENC_BUCKETED=1 timeout 400 ncu --set full --clock-control none --import-source on \
+    -k regex:bucketed -s 2 -c 1 -f -o gpurun_out/r02_prof_encode_words_bucketed python tools/ab_encode.py 1000000 1 > /dev/null 2>&1; echo "rc=$?"
+} > gpurun_out/r02_session1.log 2>&1
+tail -5 gpurun_out/r02_session1.log
