@@ -41,10 +41,11 @@ TRAIN_BYTES = 100_000_000
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
+    try:
         with open(p) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    except (OSError, KeyError, ValueError, TypeError):  # absent or of another shape: the recipe's stated fallback
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
 def workload(rank, n_sent, train_bytes):
