@@ -265,3 +265,33 @@ def test_train_deferred_list_overflow_falls_back_to_the_direct_pass(emu, oracle,
         text, vocab, cov, _ = _cases.stress_case(seed)
         TG._same(oracle, text, vocab, cov)
     TG._same(oracle, synth.readme_corpus(n_lines=120), 150)
+
+
+def test_encode_long_words_block_kernel(emu, oracle, monkeypatch):
+    """YTTM_ENC_LONG (experimental, off by default): words of more than 512 slots get a whole block and are merged
+    pass by pass (all occurrences of the minimum rule per pass) instead of one merge at a time by one thread."""
+    monkeypatch.setenv("YTTM_ENC_LONG", "1")
+    rng = np.random.default_rng(3)
+    train = synth.readme_corpus(n_lines=400) + b" " + _cases.dirty_zipf_text(60_000)
+    m = EG._model(oracle, train, 700)
+    rnd = lambda n, alpha=b"abcd": bytes(rng.choice(list(alpha), size=n).tolist())
+    zc = _cases.zipf()
+    glued = b"".join(zc.sentences(60, 80, seed=6)).replace(b" ", b"")       # ~4 KB multi-script word
+    sents = [rnd(600), rnd(5000), b"a" * 513, b"a" * 4001, b"ab" * 700, b"aab" * 400, rnd(3000, b"ab"),
+             glued, glued[:700] + b"\xff\xfe" + glued[700:1500] + "☃☃☃".encode() * 30 + rnd(900),
+             b"x " + rnd(2000) + b" y " + rnd(513) + b" " + rnd(512) + b" " + rnd(511) + b" z",
+             b"\xff" * 600, b"\xf0\x9f\x98\x80" * 200 + b"abab" * 200] + _cases.zipf_sentences(50) + _cases.EDGE_SENTENCES
+    g, o = EG.GpuEncoder(m), oracle.encoder(m)
+    for kw in EG.KW:
+        assert g.encode(sents, **kw) == o.encode(sents, **kw)
+    assert emu.yttm_stage_ms(emu.yttm_api_device_context(g.h), b"enc_variant") == 5.0   # long-word path + bucketed
+    # with dropout the words stay on the sequential path (the per-event draws are order dependent)
+    assert g.encode(sents[:4], dropout=0.3, seed=5) == o.encode(sents[:4], dropout=0.3, seed=5)
+    # a model made of x x rules ((a,a), (aa,aa), ...): runs take every second occurrence from the run's start
+    runs = b" ".join(b"a" * int(k) + b" " + b"b" * int(j) + b"ab" * int(k % 5) for k, j in rng.integers(1, 40, (300, 2)))
+    m2 = EG._model(oracle, runs, 40)
+    sents2 = [b"a" * k for k in (513, 514, 515, 1023, 1024, 1025, 2047, 4096, 7001)] + [b"b" * 999 + b"a" * 1000, b"ab" * 600 + b"a" * 777,
+              b"a" * 300 + b"b" + b"a" * 300, b"a" * 512 + b" " + b"a" * 600]
+    g2, o2 = EG.GpuEncoder(m2), oracle.encoder(m2)
+    assert g2.encode(sents2) == o2.encode(sents2)
+    assert g2.encode(sents2, bos=True, eos=True, reverse=True) == o2.encode(sents2, bos=True, eos=True, reverse=True)

@@ -17,7 +17,7 @@ from _emu import emu_lib  # noqa: E402
 from youtokentome_b200 import synth  # noqa: E402
 
 KNOBS = ["YT_EMU_SMS", "YT_EMU_SCHED_SEED", "YTTM_FORCE_STREAM", "YTTM_STREAM_Q", "YTTM_STAGES", "YTTM_PAIR_CAP_FLOOR", "YTTM_DEFER_CAP",
-         "YTTM_ENC_BUCKETED", "YTTM_ENC_FIND_CACHED", "YTTM_ENC_ZLIN", "YTTM_ENC_CHUNK_MB"]
+         "YTTM_ENC_BUCKETED", "YTTM_ENC_FIND_CACHED", "YTTM_ENC_ZLIN", "YTTM_ENC_LONG", "YTTM_ENC_CHUNK_MB"]
 
 
 def sentences(rng, text):
@@ -34,7 +34,8 @@ def sentences(rng, text):
         elif r == 2:
             s = s + b" unseen-\xd1\x8f\xf0\x9f\x98\x80 zzz"
         elif r == 3 and words:
-            s = b"".join(words[int(i)] for i in rng.integers(0, len(words), int(rng.integers(1, 30))))  # one long word
+            s = b"".join(words[int(i)] for i in rng.integers(0, len(words), int(rng.integers(1, 400))))[:6000]  # one long word, often > 512
+            # slots (capped: the ORACLE merges a word in O(n^2))
         out.append(s)
     return out + list(_cases.EDGE_SENTENCES)
 
@@ -51,7 +52,7 @@ def encode_case(rng, L, orc, model, text):
             kw = dict(bos=bool(rng.integers(0, 2)), eos=bool(rng.integers(0, 2)), reverse=bool(rng.integers(0, 2)))
             p = float(rng.choice([0.0, 0.0, 0.1, 0.5, 1.0]))
             seed = int(rng.integers(0, 2 ** 31))
-            for k in ("YTTM_ENC_BUCKETED", "YTTM_ENC_FIND_CACHED", "YTTM_ENC_ZLIN"):
+            for k in ("YTTM_ENC_BUCKETED", "YTTM_ENC_FIND_CACHED", "YTTM_ENC_ZLIN", "YTTM_ENC_LONG"):
                 os.environ.pop(k, None)
                 if rng.integers(0, 2):
                     os.environ[k] = "1"

@@ -233,6 +233,18 @@ __global__ void __launch_bounds__(128) encode_words_kernel(EncArgs a, uint64_t n
   }
 }
 
+// Words of more than LONG_W slots.  One thread merges a word in O(n^2) (min scan + shift per merge): fine for words,
+// hopeless for a 100 KB "word" (a base64 blob, a URL list without blanks) - the reference's heap is O(n log n) there.
+// EXPERIMENTAL (YTTM_ENC_LONG=1, implies the bucketed kernel; dropout = 0 only): such words are set aside in a list
+// and encode_long_words_kernel gives each of them a whole block.
+constexpr uint32_t LONG_W = 512;
+constexpr uint32_t DEAD_T = 0xfffffffeu;  // token merged away in the current pass (has UNK_FLAG set: never a rule operand)
+struct LongList {
+  uint32_t *pos, *sent, *end;  // word start, sentence, word end (batch byte positions)
+  unsigned long long *n;
+  uint32_t cap;                // 0 = feature off
+};
+
 // EXPERIMENTAL variant (env YTTM_ENC_BUCKETED=1, off by default until measured on a B200): the same
 // per-word work, but a block first takes a window of BUCKET_WINDOW consecutive work items, measures
 // every word (end position, number of UTF-8 lead bytes = tokens before merging) and hands the items
@@ -241,7 +253,7 @@ __global__ void __launch_bounds__(128) encode_words_kernel(EncArgs a, uint64_t n
 // token), and with thread-per-word every warp used to run as long as its longest word.
 constexpr uint32_t BUCKET_WINDOW = 512, BUCKET_KEYS = 64;
 template <bool DROPOUT, bool ZLIN>
-__global__ void __launch_bounds__(128) encode_words_bucketed_kernel(EncArgs a, uint64_t n_words, LinearZFn zlin) {
+__global__ void __launch_bounds__(128) encode_words_bucketed_kernel(EncArgs a, uint64_t n_words, LinearZFn zlin, LongList ll) {
   constexpr uint32_t LOCAL_W = 40;
   __shared__ uint32_t s_pos[BUCKET_WINDOW], s_sent[BUCKET_WINDOW], s_end[BUCKET_WINDOW];
   __shared__ uint16_t s_perm[BUCKET_WINDOW], s_key[BUCKET_WINDOW], s_rk[BUCKET_WINDOW];
@@ -297,6 +309,10 @@ __global__ void __launch_bounds__(128) encode_words_bucketed_kernel(EncArgs a, u
       const uint64_t slot0 = sent_base(lo, s) + 1 + (p0 - lo);
       int32_t *t = a.slots + slot0;  // k+1 private slots
       uint32_t owned = (uint32_t)(q - p0) + 1, n;
+      if (!DROPOUT && ll.cap && owned > LONG_W) {  // a whole block will take it (encode_long_words_kernel)
+        const unsigned long long k = atomicAdd(ll.n, 1ull);
+        if (k < ll.cap) { ll.pos[k] = (uint32_t)p0; ll.sent[k] = (uint32_t)s; ll.end[k] = (uint32_t)q; continue; }
+      }
       if (owned <= LOCAL_W) {
         int32_t lt[LOCAL_W];
         uint32_t lr[LOCAL_W];
@@ -322,6 +338,157 @@ __global__ void __launch_bounds__(128) encode_words_bucketed_kernel(EncArgs a, u
       if (n) atomicAdd(a.n_ids + s, (unsigned long long)n);
     }
     __syncthreads();  // the window's shared arrays are reused by the next one
+  }
+}
+
+// One block per long word, dropout = 0.  The merge order of encode_sentence (minimum rule index, leftmost first,
+// bpe.cpp:1475-1478) is reproduced pass by pass: find the minimum rank r* over the word; every occurrence of that rule
+// is applied in this pass, left to right without overlap - the sequential order would pick exactly these, because the
+// tokens a merge creates only form pairs of HIGHER rule index (the product of rule k appears in rules > k only) and
+// occurrences of the pair itself can only disappear (runs x x x ... take every second one from the run's start).
+// Then the word is compacted and the ranks next to the new tokens are looked up again.  Work per pass is O(n / threads).
+constexpr int LONG_T = 512;
+__device__ __forceinline__ uint32_t long_block_min(uint32_t v, uint32_t *s_red) {
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  uint32_t r = s_red[0];
+  for (unsigned i = 1; i < (blockDim.x >> 5); i++) r = min(r, s_red[i]);
+  return r;
+}
+// exclusive sum and inclusive max of one value per thread over the block; *tot = block sum / block max
+__device__ __forceinline__ uint32_t long_block_scan_sum(uint32_t v, uint32_t *s_red, uint32_t *tot) {
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  uint32_t x = v;
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if ((int)lane >= o) x += y; }
+  __syncthreads();
+  if (lane == 31) s_red[wid] = x;
+  __syncthreads();
+  uint32_t base = 0, all = 0;
+  for (unsigned i = 0; i < nw; i++) { const uint32_t w = s_red[i]; if (i < wid) base += w; all += w; }
+  *tot = all;
+  return base + x - v;
+}
+__device__ __forceinline__ uint32_t long_block_scan_max(uint32_t v, uint32_t *s_red) {
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t x = v;
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if ((int)lane >= o) x = max(x, y); }
+  __syncthreads();
+  if (lane == 31) s_red[wid] = x;
+  __syncthreads();
+  for (unsigned i = 0; i < wid; i++) x = max(x, s_red[i]);
+  return x;
+}
+
+__global__ void __launch_bounds__(LONG_T) encode_long_words_kernel(EncArgs a, LongList ll) {
+  __shared__ uint32_t s_red[LONG_T / 32];
+  __shared__ uint32_t s_n, s_hit, s_z, s_xeqy;
+  const uint64_t o0 = a.offs[0];
+  const RuleTab rt = a.rt;
+  const unsigned long long n_long = min(*ll.n, (unsigned long long)ll.cap);
+  for (unsigned long long w = blockIdx.x; w < n_long; w += gridDim.x) {  // block-uniform
+    const uint64_t p0 = ll.pos[w], s = ll.sent[w], q_end = ll.end[w];
+    const uint64_t lo = a.offs[s] - o0, hi = a.offs[s + 1] - o0;
+    const uint64_t slot0 = sent_base(lo, s) + 1 + (p0 - lo);
+    uint32_t *t = reinterpret_cast<uint32_t *>(a.slots + slot0);
+    uint32_t *r = a.ranks + slot0;
+    const uint32_t owned = (uint32_t)(q_end - p0) + 1;
+    if (threadIdx.x == 0) {  // decode: O(bytes), the cheap part (same rules as encode_word)
+      uint32_t n = 1, l;
+      bool last_unk = false;
+      uint64_t q = p0;
+      while (q < q_end) {
+        const uint32_t cp = decode_unit(a.bytes, q, hi, &l);
+        q += l;
+        if (cp == INVALID_CP) continue;
+        const uint32_t id = a.cp2id[cp];
+        if (id == NO_ID) {
+          if (!last_unk) t[n++] = UNK_FLAG | 1u;
+          last_unk = true;
+        } else { t[n++] = id; last_unk = false; }
+      }
+      t[0] = a.space_id;
+      s_n = n;
+    }
+    __syncthreads();
+    uint32_t n = s_n;
+    const bool no_unit = n == 1;  // a word without a valid unit does not exist for the reference
+    if (n > 1) {
+      for (uint32_t i = threadIdx.x; i < n; i += LONG_T) {
+        uint32_t z;
+        r[i] = i + 1 < n ? rule_rank(rt, t[i], t[i + 1], &z) : NO_RANK;
+      }
+      __syncthreads();
+      while (n > 1) {
+        // ---- minimum rank of the word and one of its positions
+        uint32_t best = NO_RANK, where = 0;
+        for (uint32_t i = threadIdx.x; i + 1 < n; i += LONG_T)
+          if (r[i] < best) { best = r[i]; where = i; }
+        const uint32_t rmin = long_block_min(best, s_red);
+        if (rmin == NO_RANK) break;
+        if (best == rmin) s_hit = where;  // any of them
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          const uint32_t x = t[s_hit], y = t[s_hit + 1];
+          uint32_t z = 0;
+          rule_rank(rt, x, y, &z);
+          s_z = z;
+          s_xeqy = x == y;
+        }
+        __syncthreads();
+        const uint32_t z = s_z;
+        const bool xeqy = s_xeqy != 0;
+        // ---- apply every occurrence, left to right without overlap (only r is read here, only t written)
+        uint32_t carry = 0;  // run start + 1 of a run of hits that reaches the end of the previous chunk
+        for (uint32_t b = 0; b + 1 < n; b += LONG_T) {
+          const uint32_t i = b + threadIdx.x;
+          const bool hit = i + 1 < n && r[i] == rmin;
+          bool take = hit;
+          if (xeqy) {  // x x x x ...: every second occurrence, counted from the start of the run of hits
+            const bool starts = hit && !(i > 0 && r[i - 1] == rmin);
+            uint32_t m = long_block_scan_max(starts ? i + 1 : 0u, s_red);
+            if (m == 0) m = carry;  // the run began in an earlier chunk
+            take = hit && (((i + 1 - m) & 1u) == 0);
+            // hand the run start over if the last position of this chunk is still inside a run
+            __syncthreads();
+            if (threadIdx.x == LONG_T - 1) s_red[0] = hit ? m : 0u;
+            __syncthreads();
+            carry = s_red[0];
+          }
+          if (take) { t[i] = z; t[i + 1] = DEAD_T; }
+        }
+        __syncthreads();
+        // ---- compact tokens and ranks (writes trail reads: destination <= source, chunk by chunk)
+        uint32_t off = 0;
+        for (uint32_t b = 0; b < n; b += LONG_T) {
+          const uint32_t i = b + threadIdx.x;
+          const uint32_t ti = i < n ? t[i] : DEAD_T, ri = i < n ? r[i] : NO_RANK;
+          const uint32_t alive = ti != DEAD_T ? 1u : 0u;
+          uint32_t tot;
+          const uint32_t pos = long_block_scan_sum(alive, s_red, &tot);  // has the barriers between reads and writes
+          if (alive) { t[off + pos] = ti; r[off + pos] = ri; }
+          off += tot;
+          __syncthreads();
+        }
+        n = off;
+        // ---- ranks next to the new tokens
+        for (uint32_t j = threadIdx.x; j < n; j += LONG_T) {
+          if (j + 1 >= n) { r[j] = NO_RANK; continue; }
+          const uint32_t u = t[j], v = t[j + 1];
+          if (u == z || v == z) { uint32_t zz; r[j] = rule_rank(rt, u, v, &zz); }
+        }
+        __syncthreads();
+      }
+    }
+    // ---- final ids; the unused slots of the word go back to EMPTY
+    const uint32_t n_out = no_unit ? 0 : n;
+    for (uint32_t i = threadIdx.x; i < owned; i += LONG_T) {
+      const uint32_t v = t[i];
+      t[i] = i < n_out ? ((v & UNK_FLAG) ? (uint32_t)a.unk_id : v) : (uint32_t)EMPTY_SLOT;
+    }
+    if (threadIdx.x == 0 && n_out) atomicAdd(a.n_ids + s, (unsigned long long)n_out);
+    __syncthreads();
   }
 }
 
@@ -361,9 +528,9 @@ struct yttm_enc {
   // per-call device buffers: two sets, so that the host-buffer entry point can pipeline chunks
   // (H2D of chunk i+1 and D2H of chunk i-1 overlap the kernels of chunk i)
   struct Slot {
-    ytc::DevBuf d_bytes, d_offs, slots, ranks, aux, wpos, wsent, nids, out_off, out_ids, counter;
+    ytc::DevBuf d_bytes, d_offs, slots, ranks, aux, wpos, wsent, nids, out_off, out_ids, counter, longw;
     void release() {
-      ytc::DevBuf *b[] = {&d_bytes, &d_offs, &slots, &ranks, &aux, &wpos, &wsent, &nids, &out_off, &out_ids, &counter};
+      ytc::DevBuf *b[] = {&d_bytes, &d_offs, &slots, &ranks, &aux, &wpos, &wsent, &nids, &out_off, &out_ids, &counter, &longw};
       for (auto *x : b) x->release();
     }
   } slot[2];
@@ -428,15 +595,31 @@ int enc_device(yttm_enc *enc, yttm_enc::Slot *e, const uint8_t *d_bytes, const u
     ytc::timer_begin(c, "enc_words");
     // experimental kernels, see there; the linear product-id shortcut exists in the bucketed kernel only
     const bool zlin = enc->zlin_ok && std::getenv("YTTM_ENC_ZLIN") != nullptr;
-    const bool bucketed = zlin || std::getenv("YTTM_ENC_BUCKETED") != nullptr;
-    c->timers["enc_variant"].ms = (float)((zlin ? 2 : 0) + (bucketed ? 1 : 0));  // yttm_stage_ms(ctx, "enc_variant")
+    const bool longw = a.drop_thresh == 0 && std::getenv("YTTM_ENC_LONG") != nullptr;
+    const bool bucketed = zlin || longw || std::getenv("YTTM_ENC_BUCKETED") != nullptr;
+    LongList ll{nullptr, nullptr, nullptr, nullptr, 0};
+    if (longw) {
+      const uint32_t cap = (uint32_t)(n_bytes / LONG_W + 16);
+      YT_CUDA(c, e->longw.reserve((size_t)cap * 12 + 16));
+      ll.n = e->longw.as<unsigned long long>();
+      ll.pos = reinterpret_cast<uint32_t *>(ll.n + 2);
+      ll.sent = ll.pos + cap;
+      ll.end = ll.sent + cap;
+      ll.cap = cap;
+      YT_CUDA(c, cudaMemsetAsync(ll.n, 0, 8, c->stream));
+    }
+    c->timers["enc_variant"].ms = (float)((longw ? 4 : 0) + (zlin ? 2 : 0) + (bucketed ? 1 : 0));  // yttm_stage_ms(ctx, "enc_variant")
     if (bucketed) {
       const unsigned wb = (unsigned)std::min<uint64_t>((n_words + BUCKET_WINDOW - 1) / BUCKET_WINDOW, (uint64_t)c->n_sm * 16);
       if (zlin) {
-        if (a.drop_thresh) encode_words_bucketed_kernel<true, true><<<wb, 128, 0, c->stream>>>(a, n_words, enc->zlin);
-        else encode_words_bucketed_kernel<false, true><<<wb, 128, 0, c->stream>>>(a, n_words, enc->zlin);
-      } else if (a.drop_thresh) encode_words_bucketed_kernel<true, false><<<wb, 128, 0, c->stream>>>(a, n_words, enc->zlin);
-      else encode_words_bucketed_kernel<false, false><<<wb, 128, 0, c->stream>>>(a, n_words, enc->zlin);
+        if (a.drop_thresh) encode_words_bucketed_kernel<true, true><<<wb, 128, 0, c->stream>>>(a, n_words, enc->zlin, ll);
+        else encode_words_bucketed_kernel<false, true><<<wb, 128, 0, c->stream>>>(a, n_words, enc->zlin, ll);
+      } else if (a.drop_thresh) encode_words_bucketed_kernel<true, false><<<wb, 128, 0, c->stream>>>(a, n_words, enc->zlin, ll);
+      else encode_words_bucketed_kernel<false, false><<<wb, 128, 0, c->stream>>>(a, n_words, enc->zlin, ll);
+      if (longw) {  // no host round trip: the blocks read the list length themselves
+        encode_long_words_kernel<<<(unsigned)c->n_sm, LONG_T, 0, c->stream>>>(a, ll);
+        c->launches++;
+      }
     } else if (a.drop_thresh) encode_words_kernel<true><<<(unsigned)blocks, 128, 0, c->stream>>>(a, n_words);
     else encode_words_kernel<false><<<(unsigned)blocks, 128, 0, c->stream>>>(a, n_words);
     ytc::timer_end(c, "enc_words");
