@@ -10,6 +10,7 @@ mkdir -p gpurun_out
 {
 echo "### pytest -m gpu"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
 echo "### ab_encode"; timeout 300 python tools/ab_encode.py 1000000 7 2>/dev/null | tail -45
+echo "### ab_long_words"; timeout 180 python tools/ab_long_words.py 16384 8 2>/dev/null | tail -20
 echo "### ab_train"; timeout 400 bash tools/ab_train.sh zipf 32000 100e6
 echo "### bench"; timeout 600 python bench.py > gpurun_out/r02_bench_first.json 2> gpurun_out/r02_bench_first.err; echo "bench rc=$?"
 echo "### ncu launch list"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
