@@ -295,3 +295,37 @@ def test_encode_long_words_block_kernel(emu, oracle, monkeypatch):
     g2, o2 = EG.GpuEncoder(m2), oracle.encoder(m2)
     assert g2.encode(sents2) == o2.encode(sents2)
     assert g2.encode(sents2, bos=True, eos=True, reverse=True) == o2.encode(sents2, bos=True, eos=True, reverse=True)
+
+
+@pytest.mark.parametrize("knobs", [dict(), dict(YTTM_ENC_DEDUP_SLOTS="4"), dict(YTTM_ENC_DEDUP_WEAKTAG="1"),
+                                   dict(YTTM_ENC_DEDUP_SLOTS="64", YTTM_ENC_DEDUP_WEAKTAG="1")])
+def test_encode_dedup_variant(emu, oracle, monkeypatch, knobs):
+    """YTTM_ENC_DEDUP (experimental, off by default): every distinct word of the batch is encoded once, the other
+    occurrences copy the ids of their representative.  Same ids as the oracle, including words that differ only in
+    what follows them (end of sentence / space / U+2581), prefixes of each other, truncated UTF-8, repeated long words
+    (> LOCAL_W, merged in global slots); a 4-slot table (nearly every word represents itself), equal tags (every
+    probe ends in the byte compare) and both."""
+    monkeypatch.setenv("YTTM_ENC_DEDUP", "1")
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    m = EG._model(oracle, _cases.dirty_zipf_text(), 1500, 0.95)
+    zc = _cases.zipf()
+    long_word = b"".join(zc.sentences(20, 60, seed=6)).replace(b" ", b"")
+    edge = [b"ab\xe2\x96", b"ab\xe2\x96 x", b"ab\xe2\x96\x81x ab", b"ab\xe2", b"ab\xe2 ab\xe2\x96 ab", b"x ab\xf0\x9f\x98",
+            b"ab\xf0\x9f\x98 ab\xf0\x9f\x98\x80 ab\xf0\x9f\x98", b"abc abcd ab a abcd abc ab a", b"\xe2\x96\x81ab\xe2\x96\x81ab\xe2\x96",
+            b"\xe2\x96 \xe2\x96", b"\x96 \x96\x81 \x96", b"", b" ", b"\xff\xff \xff \xff\xff", b"\x80 \x80 \xbf",
+            long_word + b" " + long_word + b"x " + long_word, long_word[:41] + b" " + long_word[:40] + b" " + long_word[:41],
+            "☃ ☃☃ ☃ zz☃ zz☃".encode(), b"a" * 700 + b" " + b"a" * 700 + b" " + b"a" * 699]
+    sents = _cases.zipf_sentences(400) + _cases.EDGE_SENTENCES + edge + _cases.zipf_sentences(100) + edge[::-1]
+    g, o = EG.GpuEncoder(m), oracle.encoder(m)
+    for kw in EG.KW:
+        assert g.encode(sents, **kw) == o.encode(sents, **kw)
+    ctx = emu.yttm_api_device_context(g.h)
+    assert emu.yttm_stage_ms(ctx, b"enc_variant") == 8.0
+    # with dropout every occurrence draws for itself: the default kernel runs
+    assert g.encode(sents[:200], dropout=0.3, seed=5) == o.encode(sents[:200], dropout=0.3, seed=5)
+    assert emu.yttm_stage_ms(ctx, b"enc_variant") == 0.0
+    monkeypatch.setenv("YTTM_ENC_CHUNK_MB", "1")  # representatives never cross a chunk of the host-buffer pipeline
+    big = sents * 40
+    assert sum(map(len, big)) > 2 << 20
+    assert g.encode(big, eos=True) == o.encode(big, eos=True)

@@ -1,6 +1,6 @@
 """A/B of the encode kernels' experimental variants on the bench workload (run on a B200):
     python tools/ab_encode.py [n_sentences] [reps]
-For each of {default, YTTM_ENC_FIND_CACHED, YTTM_ENC_BUCKETED, both}: median CUDA-event ms of find / words / gather
+For each of {default, YTTM_ENC_FIND_CACHED, YTTM_ENC_BUCKETED, both, both + YTTM_ENC_ZLIN, YTTM_ENC_DEDUP (+ find)}: median CUDA-event ms of find / words / gather
 over `reps` runs of yttm_enc_run_device on inputs resident in HBM, and a check that the ids are identical."""
 import ctypes as C
 import json
@@ -36,12 +36,15 @@ def main(L=None, n_sent=None, reps=None, train_bytes=20_000_000, vocab=8000):
     out = {}
     for name, env in [("default", []), ("find_cached", ["YTTM_ENC_FIND_CACHED"]), ("bucketed", ["YTTM_ENC_BUCKETED"]),
                       ("both", ["YTTM_ENC_FIND_CACHED", "YTTM_ENC_BUCKETED"]),
-                      ("both+zlin", ["YTTM_ENC_FIND_CACHED", "YTTM_ENC_BUCKETED", "YTTM_ENC_ZLIN"])]:
-        for k in ("YTTM_ENC_FIND_CACHED", "YTTM_ENC_BUCKETED", "YTTM_ENC_ZLIN"):
+                      ("both+zlin", ["YTTM_ENC_FIND_CACHED", "YTTM_ENC_BUCKETED", "YTTM_ENC_ZLIN"]),
+                      ("dedup", ["YTTM_ENC_DEDUP"]), ("dedup+find_cached", ["YTTM_ENC_DEDUP", "YTTM_ENC_FIND_CACHED"])]:
+        for k in ("YTTM_ENC_FIND_CACHED", "YTTM_ENC_BUCKETED", "YTTM_ENC_ZLIN", "YTTM_ENC_DEDUP"):
             os.environ.pop(k, None)
         for k in env:
             os.environ[k] = "1"
-        ms = {"enc_find": [], "enc_words": [], "enc_gather": []}
+        ms = {"enc_find": [], "enc_words": [], "enc_gather": [], "encode": []}
+        if "YTTM_ENC_DEDUP" in env:  # the three launches inside enc_words
+            ms.update({"enc_dedup": [], "enc_rep": [], "enc_copy": []})
         for _ in range(reps + 2):
             p_ids, p_off, n = C.c_void_p(), C.c_void_p(), C.c_uint64(0)
             rc = L.yttm_enc_run_device(enc, d_bytes.data_ptr(), d_offs.data_ptr(), len(buf), n_sent, 0, 0, 0, 0.0, 0, 0,

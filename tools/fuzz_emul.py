@@ -17,7 +17,8 @@ from _emu import emu_lib  # noqa: E402
 from youtokentome_b200 import synth  # noqa: E402
 
 KNOBS = ["YT_EMU_SMS", "YT_EMU_SCHED_SEED", "YTTM_FORCE_STREAM", "YTTM_STREAM_Q", "YTTM_STAGES", "YTTM_PAIR_CAP_FLOOR", "YTTM_DEFER_CAP",
-         "YTTM_ENC_BUCKETED", "YTTM_ENC_FIND_CACHED", "YTTM_ENC_ZLIN", "YTTM_ENC_LONG", "YTTM_ENC_CHUNK_MB"]
+         "YTTM_ENC_BUCKETED", "YTTM_ENC_FIND_CACHED", "YTTM_ENC_ZLIN", "YTTM_ENC_LONG", "YTTM_ENC_CHUNK_MB",
+         "YTTM_ENC_DEDUP", "YTTM_ENC_DEDUP_SLOTS", "YTTM_ENC_DEDUP_WEAKTAG"]
 
 
 def sentences(rng, text):
@@ -52,10 +53,14 @@ def encode_case(rng, L, orc, model, text):
             kw = dict(bos=bool(rng.integers(0, 2)), eos=bool(rng.integers(0, 2)), reverse=bool(rng.integers(0, 2)))
             p = float(rng.choice([0.0, 0.0, 0.1, 0.5, 1.0]))
             seed = int(rng.integers(0, 2 ** 31))
-            for k in ("YTTM_ENC_BUCKETED", "YTTM_ENC_FIND_CACHED", "YTTM_ENC_ZLIN", "YTTM_ENC_LONG"):
+            for k in ("YTTM_ENC_BUCKETED", "YTTM_ENC_FIND_CACHED", "YTTM_ENC_ZLIN", "YTTM_ENC_LONG", "YTTM_ENC_DEDUP",
+                      "YTTM_ENC_DEDUP_WEAKTAG"):
                 os.environ.pop(k, None)
                 if rng.integers(0, 2):
                     os.environ[k] = "1"
+            os.environ.pop("YTTM_ENC_DEDUP_SLOTS", None)
+            if rng.integers(0, 2):
+                os.environ["YTTM_ENC_DEDUP_SLOTS"] = str(int(rng.choice([1, 8, 64, 1024])))  # tiny tables: probe overflow
             want = o.encode(sents, dropout=p, seed=seed, **kw)
             L.yttm_api_set_dropout_seed(h, seed)
             total = C.c_uint64(0)

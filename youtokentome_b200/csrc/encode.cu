@@ -492,6 +492,132 @@ __global__ void __launch_bounds__(LONG_T) encode_long_words_kernel(EncArgs a, Lo
   }
 }
 
+// EXPERIMENTAL variant (env YTTM_ENC_DEDUP=1, dropout = 0 only, off by default until measured on a B200): every
+// distinct word of the batch is encoded ONCE.  Without dropout the ids of a word are a pure function of its bytes
+// [p0, q): a lead byte whose announced length reaches past q sees either the end of the sentence or the first byte of
+// a space unit (never a continuation byte), INVALID_CP with length 1 in both cases (decode_unit), so nothing outside
+// the word enters.  Natural text repeats its words (the bench batch: 20 M occurrences of < 200 k words), and the
+// merge loop of encode_word is the expensive part of the default kernel.  Three launches:
+//   dedup_words_kernel       one thread per occurrence: end of the word + 64-bit FNV-1a/mix64 hash of its bytes; an
+//                            open-addressed table of (32-bit tag, work item) words, small enough to stay in L2, elects
+//                            the first occurrence that claims a slot as the word's representative; later occurrences
+//                            with the same tag compare BYTES with it (exactness never rests on the hash).  A word that
+//                            finds neither itself nor a free slot within DEDUP_PROBES probes represents itself, so the
+//                            table is a bounded cache, not a limit.
+//   encode_rep_words_kernel  the default per-word body, over the representatives only (list length read on the device)
+//   copy_word_ids_kernel     every other occurrence copies its representative's ids into its own slots
+// The slot of the first token of work item w is word_pos[w] + 3 word_sent[w] + 1 (sent_base(): the sentence start
+// cancels), so a copy needs no sentence offsets.
+constexpr unsigned long long DEDUP_EMPTY = ~0ull;
+constexpr uint32_t DEDUP_PROBES = 8;
+struct DedupArgs {
+  unsigned long long *tab;     // (tag << 32) | representative work item ; DEDUP_EMPTY = free
+  uint32_t mask;
+  uint32_t *rep;               // per work item: its representative (itself if it is one)
+  uint32_t *n_tok;             // per representative: number of ids of its encoding
+  uint32_t *list;              // the representatives, in arrival order
+  unsigned long long *n_list;
+  uint32_t weak_tag;           // tests only: all tags equal, so every probe ends in the byte compare
+};
+
+__global__ void __launch_bounds__(128) dedup_words_kernel(EncArgs a, uint64_t n_words, DedupArgs d) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t o0 = a.offs[0];
+  for (uint64_t w0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); w0 < n_words; w0 += stride) {  // warp-uniform
+    const uint64_t w = w0 + lane;
+    bool is_rep = false;
+    if (w < n_words) {
+      const uint64_t p0 = a.word_pos[w], hi = a.offs[(uint64_t)a.word_sent[w] + 1] - o0;
+      uint64_t q = p0, h = 0xcbf29ce484222325ull;
+      uint32_t l;
+      while (q < hi && !space_at(a.bytes, q, hi, &l)) { h = (h ^ a.bytes[q]) * 0x100000001b3ull; q++; }
+      const uint64_t len = q - p0;
+      h = mix64(h);
+      const uint32_t tag = d.weak_tag ? 7u : (uint32_t)(h >> 32);
+      const unsigned long long mine = ((unsigned long long)tag << 32) | (uint32_t)w;
+      uint32_t idx = (uint32_t)h & d.mask, r = (uint32_t)w;
+      is_rep = true;  // also the outcome of running out of probes
+      for (uint32_t k = 0; k < DEDUP_PROBES; k++, idx = (idx + 1) & d.mask) {
+        unsigned long long cur = *(volatile unsigned long long *)(d.tab + idx);
+        if (cur == DEDUP_EMPTY) {
+          cur = atomicCAS(d.tab + idx, DEDUP_EMPTY, mine);
+          if (cur == DEDUP_EMPTY) break;  // slot claimed: this occurrence represents the word
+        }
+        if ((uint32_t)(cur >> 32) != tag) continue;
+        const uint32_t w2 = (uint32_t)cur;  // written by find_words (the previous launch), like everything read below
+        const uint64_t p2 = a.word_pos[w2], hi2 = a.offs[(uint64_t)a.word_sent[w2] + 1] - o0;
+        // Equal iff the len bytes match AND the word at p2 ends right after them.  No space unit can start inside the
+        // matching bytes: an ASCII space or a whole E2 96 81 there would be one in this word too, and an E2 96 81 that
+        // starts inside and ends beyond leaves a continuation byte at p2 + len, which the end check rejects.
+        bool same = true;
+        for (uint64_t i = 0; i < len; i++)
+          if (p2 + i >= hi2 || a.bytes[p2 + i] != a.bytes[p0 + i]) { same = false; break; }
+        if (same && p2 + len < hi2 && !space_at(a.bytes, p2 + len, hi2, &l)) same = false;  // the other word is longer
+        if (same) { r = w2; is_rep = false; break; }
+      }
+      d.rep[w] = r;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, is_rep);
+    if (m) {  // one atomicAdd per warp reserves the list entries of its new representatives
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(d.n_list, (unsigned long long)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (is_rep) d.list[base + __popc(m & ((1u << lane) - 1))] = (uint32_t)w;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) encode_rep_words_kernel(EncArgs a, DedupArgs d) {
+  constexpr uint32_t LOCAL_W = 40;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t o0 = a.offs[0];
+  const RuleTab rt = a.rt;
+  auto rank = [&](uint32_t x, uint32_t y, uint32_t *z) { return rule_rank(rt, x, y, z); };
+  const unsigned long long n_list = *d.n_list;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_list; i += stride) {
+    const uint32_t w = d.list[i];
+    const uint64_t p0 = a.word_pos[w], s = a.word_sent[w];
+    const uint64_t lo = a.offs[s] - o0, hi = a.offs[s + 1] - o0;
+    const uint64_t slot0 = p0 + 3 * s + 1;
+    int32_t *t = a.slots + slot0;  // k+1 private slots
+    uint64_t q = p0;
+    uint32_t l;
+    while (q < hi && !space_at(a.bytes, q, hi, &l)) q++;
+    uint32_t owned = (uint32_t)(q - p0) + 1, n;
+    if (owned <= LOCAL_W) {
+      int32_t lt[LOCAL_W];
+      uint32_t lr[LOCAL_W];
+      n = encode_word(a.bytes, p0, lo, hi, a.cp2id, a.space_id, rank, nullptr, 0, a.seed, a.first_sentence + s, lt, lr,
+                      nullptr, &owned);
+      for (uint32_t k = 0; k < n; k++) t[k] = ((uint32_t)lt[k] & UNK_FLAG) ? a.unk_id : lt[k];
+    } else {
+      n = encode_word(a.bytes, p0, lo, hi, a.cp2id, a.space_id, rank, nullptr, 0, a.seed, a.first_sentence + s, t,
+                      a.ranks + slot0, nullptr, &owned);
+      for (uint32_t k = 0; k < n; k++)
+        if ((uint32_t)t[k] & UNK_FLAG) t[k] = a.unk_id;
+      for (uint32_t k = n; k < owned; k++) t[k] = EMPTY_SLOT;
+    }
+    d.n_tok[w] = n;
+    if (n) atomicAdd(a.n_ids + s, (unsigned long long)n);
+  }
+}
+
+__global__ void __launch_bounds__(256) copy_word_ids_kernel(EncArgs a, uint64_t n_words, DedupArgs d) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+    const uint32_t r = d.rep[w];
+    if (r == (uint32_t)w) continue;
+    const uint32_t n = d.n_tok[r];
+    if (!n) continue;
+    const uint64_t s = a.word_sent[w];
+    const int32_t *src = a.slots + ((uint64_t)a.word_pos[r] + 3ull * a.word_sent[r] + 1);
+    int32_t *dst = a.slots + ((uint64_t)a.word_pos[w] + 3ull * s + 1);  // the same number of slots as the representative's
+    for (uint32_t k = 0; k < n; k++) dst[k] = src[k];
+    atomicAdd(a.n_ids + s, (unsigned long long)n);
+  }
+}
+
 __global__ void __launch_bounds__(256) gather_ids_kernel(EncArgs a, const unsigned long long *__restrict__ out_off,
                                                          int32_t *__restrict__ out) {
   const unsigned lane = threadIdx.x & 31;
@@ -529,8 +655,10 @@ struct yttm_enc {
   // (H2D of chunk i+1 and D2H of chunk i-1 overlap the kernels of chunk i)
   struct Slot {
     ytc::DevBuf d_bytes, d_offs, slots, ranks, aux, wpos, wsent, nids, out_off, out_ids, counter, longw;
+    ytc::DevBuf dd_tab, dd_rep, dd_ntok, dd_list;  // YTTM_ENC_DEDUP only
     void release() {
-      ytc::DevBuf *b[] = {&d_bytes, &d_offs, &slots, &ranks, &aux, &wpos, &wsent, &nids, &out_off, &out_ids, &counter, &longw};
+      ytc::DevBuf *b[] = {&d_bytes, &d_offs, &slots, &ranks, &aux, &wpos, &wsent, &nids, &out_off, &out_ids, &counter, &longw,
+                          &dd_tab, &dd_rep, &dd_ntok, &dd_list};
       for (auto *x : b) x->release();
     }
   } slot[2];
@@ -608,8 +736,33 @@ int enc_device(yttm_enc *enc, yttm_enc::Slot *e, const uint8_t *d_bytes, const u
       ll.cap = cap;
       YT_CUDA(c, cudaMemsetAsync(ll.n, 0, 8, c->stream));
     }
-    c->timers["enc_variant"].ms = (float)((longw ? 4 : 0) + (zlin ? 2 : 0) + (bucketed ? 1 : 0));  // yttm_stage_ms(ctx, "enc_variant")
-    if (bucketed) {
+    const bool dedup = a.drop_thresh == 0 && std::getenv("YTTM_ENC_DEDUP") != nullptr;  // takes precedence over the others
+    c->timers["enc_variant"].ms = dedup ? 8.f : (float)((longw ? 4 : 0) + (zlin ? 2 : 0) + (bucketed ? 1 : 0));  // yttm_stage_ms(ctx, "enc_variant")
+    if (dedup) {
+      // table: 2 slots per occurrence up to 2^21 slots (16 MB, L2-resident); beyond that it works as a cache
+      uint64_t tslots = std::max<uint64_t>(ytc::pow2ceil(std::min<uint64_t>(n_words, 1ull << 20) * 2), 1024);
+      if (const char *env = std::getenv("YTTM_ENC_DEDUP_SLOTS")) tslots = ytc::pow2ceil((uint64_t)std::max(1, std::atoi(env)));  // tests: tiny tables
+      YT_CUDA(c, e->dd_tab.reserve(tslots * 8));
+      YT_CUDA(c, e->dd_rep.reserve(n_words * 4 + 16));
+      YT_CUDA(c, e->dd_ntok.reserve(n_words * 4 + 16));
+      YT_CUDA(c, e->dd_list.reserve(n_words * 4 + 16));
+      DedupArgs d;
+      d.tab = e->dd_tab.as<unsigned long long>(); d.mask = (uint32_t)(tslots - 1);
+      d.rep = e->dd_rep.as<uint32_t>(); d.n_tok = e->dd_ntok.as<uint32_t>(); d.list = e->dd_list.as<uint32_t>();
+      d.n_list = e->counter.as<unsigned long long>() + 2;  // zeroed with the other counters above
+      d.weak_tag = std::getenv("YTTM_ENC_DEDUP_WEAKTAG") != nullptr;  // tests: tag collisions everywhere
+      YT_CUDA(c, cudaMemsetAsync(d.tab, 0xff, tslots * 8, c->stream));
+      ytc::timer_begin(c, "enc_dedup");
+      dedup_words_kernel<<<(unsigned)blocks, 128, 0, c->stream>>>(a, n_words, d);
+      ytc::timer_end(c, "enc_dedup");
+      ytc::timer_begin(c, "enc_rep");
+      encode_rep_words_kernel<<<(unsigned)blocks, 128, 0, c->stream>>>(a, d);
+      ytc::timer_end(c, "enc_rep");
+      ytc::timer_begin(c, "enc_copy");
+      copy_word_ids_kernel<<<(unsigned)std::min<uint64_t>((n_words + 255) / 256, (uint64_t)c->n_sm * 8), 256, 0, c->stream>>>(a, n_words, d);
+      ytc::timer_end(c, "enc_copy");
+      c->launches += 2;
+    } else if (bucketed) {
       const unsigned wb = (unsigned)std::min<uint64_t>((n_words + BUCKET_WINDOW - 1) / BUCKET_WINDOW, (uint64_t)c->n_sm * 16);
       if (zlin) {
         if (a.drop_thresh) encode_words_bucketed_kernel<true, true><<<wb, 128, 0, c->stream>>>(a, n_words, enc->zlin, ll);
