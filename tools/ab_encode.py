@@ -1,5 +1,5 @@
 """A/B of the encode kernels' experimental variants on the bench workload (run on a B200):
-    python tools/ab_encode.py [n_sentences] [reps]
+    python tools/ab_encode.py [n_sentences] [reps] [result.json]
 For each of {default, YTTM_ENC_FIND_CACHED, YTTM_ENC_BUCKETED, both, both + YTTM_ENC_ZLIN, YTTM_ENC_DEDUP (+ find)}: median CUDA-event ms of find / words / gather
 over `reps` runs of yttm_enc_run_device on inputs resident in HBM, and a check that the ids are identical."""
 import ctypes as C
@@ -66,6 +66,9 @@ def main(L=None, n_sent=None, reps=None, train_bytes=20_000_000, vocab=8000):
         out[name]["n_ids"] = int(n.value)
     L.yttm_api_close(h)
     print(json.dumps(out, indent=1))
+    if len(sys.argv) > 3:  # optional: also write the result to a file
+        with open(sys.argv[3], "w") as fh:
+            json.dump(out, fh, indent=1)
     return out
 
 
