@@ -329,3 +329,45 @@ def test_encode_dedup_variant(emu, oracle, monkeypatch, knobs):
     big = sents * 40
     assert sum(map(len, big)) > 2 << 20
     assert g.encode(big, eos=True) == o.encode(big, eos=True)
+
+
+def test_encode_find_vec_variant(emu, oracle, monkeypatch):
+    """YTTM_ENC_FIND_VEC (experimental, off by default): the word-start kernel that gives a lane four bytes (one aligned
+    32-bit load) and decides on a register window.  Sentence starts at every alignment, sentences shorter / equal /
+    longer than the 1024-byte flag cache, U+2581 and stray bytes at the sentence bounds, a batch whose base address is
+    not 4-byte aligned (yttm_enc_run_device on an offset pointer), and the variant combined with the dedup kernels."""
+    import ctypes as C
+    monkeypatch.setenv("YTTM_ENC_FIND_VEC", "1")
+    m = EG._model(oracle, _cases.dirty_zipf_text(), 1500)
+    zc = _cases.zipf()
+    sp = b"\xe2\x96\x81"
+    edge = [sp, sp + sp, sp + b"a", b"a" + sp, b"a" + sp + b"b", sp[:2], sp[:1], sp[1:], sp[2:] + b"a", b"a" + sp[:2], b"ab " + sp[:2] + b" " + sp[1:],
+            b"\x81a \x81", b"\x96\x81 a", b"a\xe2", b"\xe2 \x96 \x81", b"a" * 127 + b" b", b"a" * 128 + b" b", b"a " * 64, b" a" * 64 + b" ",
+            b"x" * 125 + sp + b"y", b"x" * 126 + sp + b"y", b"x" * 127 + sp + b"y", b"x" * 128 + sp + b"y", b"", b" ", b"\t\n", b"a",
+            # U+2581 split over a sentence boundary must not be seen as one: neither side's neighbour bytes count
+            b"a\xe2\x96", b"\x81b c", b"a\xe2", b"\x96\x81b c", b"ab\xe2\x96", b"\x81", b"q", b"\x96\x81", b"zz " + sp[:2], sp[2:] + sp + b"k"]
+    sents = (_cases.zipf_sentences(200) + _cases.EDGE_SENTENCES + edge + zc.sentences(12, 1023, seed=2) + zc.sentences(12, 1025, seed=3) +
+             [b" ".join(zc.sentences(40, 100, seed=5)), b"x" * 1024, b"x " * 700, b" " * 1100 + b"y", b"z" * 31 + b" " + b"w" * 1300] + edge[::-1])
+    g, o = EG.GpuEncoder(m), oracle.encoder(m)
+    for kw in EG.KW:
+        assert g.encode(sents, **kw) == o.encode(sents, **kw)
+    assert g.encode(sents, dropout=0.4, seed=11) == o.encode(sents, dropout=0.4, seed=11)
+    monkeypatch.setenv("YTTM_ENC_DEDUP", "1")
+    assert g.encode(sents, eos=True) == o.encode(sents, eos=True)
+    monkeypatch.delenv("YTTM_ENC_DEDUP")
+    # misaligned batch base: the same bytes at offsets 1, 2, 3 of an aligned buffer
+    import _bind
+    buf, offs = _bind._pack(sents)
+    want = o.encode(sents)
+    ctx, enc = emu.yttm_api_device_context(g.h), emu.yttm_api_device_encoder(g.h)
+    for shift in (1, 2, 3):
+        raw = np.zeros(len(buf) + 16, dtype=np.uint8)
+        base = raw.ctypes.data + (-raw.ctypes.data) % 4 + shift
+        C.memmove(base, bytes(buf), len(buf))
+        p_ids, p_off, n = C.c_void_p(), C.c_void_p(), C.c_uint64(0)
+        rc = emu.yttm_enc_run_device(enc, base, offs.ctypes.data, len(buf), len(sents), 0, 0, 0, 0.0, 0, 0,
+                                     C.byref(p_ids), C.byref(p_off), C.byref(n))
+        assert rc == 0, emu.yttm_last_error(ctx)
+        ids = np.ctypeslib.as_array(C.cast(p_ids, C.POINTER(C.c_int32)), shape=(n.value,)).copy()
+        oo = np.ctypeslib.as_array(C.cast(p_off, C.POINTER(C.c_uint64)), shape=(len(sents) + 1,)).copy()
+        assert _bind._unpack(ids, oo) == want, shift

@@ -1,4 +1,4 @@
-"""The env-gated EXPERIMENTAL encode kernels (YTTM_ENC_FIND_CACHED / _BUCKETED / _ZLIN / _DEDUP; off by default, parity
+"""The env-gated EXPERIMENTAL encode kernels (YTTM_ENC_FIND_CACHED / _FIND_VEC / _BUCKETED / _ZLIN / _DEDUP; off by default, parity
 proven only under the CPU SIMT emulator: tests/test_simt_emul_cpu.py, tools/fuzz_emul.py) on real hardware: tools/ab_encode.py
 in a SUBPROCESS with a hard timeout, on a 200 k-sentence cut of the bench workload.  The default kernels are what the
 other GPU tests pin against the oracle; this file only asks whether every variant returns the default kernels' ids.
@@ -37,4 +37,4 @@ def test_experimental_encode_variants_return_the_default_ids(product, tmp_path):
     bad = [k for k, v in res.items() if not v["ids_equal_default"]]
     if bad:
         pytest.xfail("experimental encode variants differ from the default ids on hardware: %s" % bad)
-    assert set(res) >= {"default", "find_cached", "bucketed", "both", "both+zlin", "dedup", "dedup+find_cached"}
+    assert set(res) >= {"default", "find_cached", "bucketed", "both", "both+zlin", "dedup", "dedup+find_cached", "find_vec", "dedup+find_vec"}

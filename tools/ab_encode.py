@@ -1,6 +1,6 @@
 """A/B of the encode kernels' experimental variants on the bench workload (run on a B200):
     python tools/ab_encode.py [n_sentences] [reps] [result.json]
-For each of {default, YTTM_ENC_FIND_CACHED, YTTM_ENC_BUCKETED, both, both + YTTM_ENC_ZLIN, YTTM_ENC_DEDUP (+ find)}: median CUDA-event ms of find / words / gather
+For each of {default, YTTM_ENC_FIND_CACHED, YTTM_ENC_BUCKETED, both, both + YTTM_ENC_ZLIN, YTTM_ENC_DEDUP, YTTM_ENC_FIND_VEC, both}: median CUDA-event ms of find / words / gather
 over `reps` runs of yttm_enc_run_device on inputs resident in HBM, and a check that the ids are identical."""
 import ctypes as C
 import json
@@ -37,8 +37,9 @@ def main(L=None, n_sent=None, reps=None, train_bytes=20_000_000, vocab=8000):
     for name, env in [("default", []), ("find_cached", ["YTTM_ENC_FIND_CACHED"]), ("bucketed", ["YTTM_ENC_BUCKETED"]),
                       ("both", ["YTTM_ENC_FIND_CACHED", "YTTM_ENC_BUCKETED"]),
                       ("both+zlin", ["YTTM_ENC_FIND_CACHED", "YTTM_ENC_BUCKETED", "YTTM_ENC_ZLIN"]),
-                      ("dedup", ["YTTM_ENC_DEDUP"]), ("dedup+find_cached", ["YTTM_ENC_DEDUP", "YTTM_ENC_FIND_CACHED"])]:
-        for k in ("YTTM_ENC_FIND_CACHED", "YTTM_ENC_BUCKETED", "YTTM_ENC_ZLIN", "YTTM_ENC_DEDUP"):
+                      ("dedup", ["YTTM_ENC_DEDUP"]), ("dedup+find_cached", ["YTTM_ENC_DEDUP", "YTTM_ENC_FIND_CACHED"]),
+                      ("find_vec", ["YTTM_ENC_FIND_VEC"]), ("dedup+find_vec", ["YTTM_ENC_DEDUP", "YTTM_ENC_FIND_VEC"])]:
+        for k in ("YTTM_ENC_FIND_CACHED", "YTTM_ENC_BUCKETED", "YTTM_ENC_ZLIN", "YTTM_ENC_DEDUP", "YTTM_ENC_FIND_VEC"):
             os.environ.pop(k, None)
         for k in env:
             os.environ[k] = "1"

@@ -9,7 +9,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 {
 echo "### pytest -m gpu"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
-echo "### ab_encode"; timeout 300 python tools/ab_encode.py 1000000 7 2>/dev/null | tail -75
+echo "### ab_encode"; timeout 300 python tools/ab_encode.py 1000000 7 2>/dev/null | tail -110
 echo "### ab_long_words"; timeout 180 python tools/ab_long_words.py 16384 8 2>/dev/null | tail -20
 echo "### ab_train"; timeout 400 bash tools/ab_train.sh zipf 32000 100e6
 echo "### bench"; timeout 600 python bench.py > gpurun_out/r02_bench_first.json 2> gpurun_out/r02_bench_first.err; echo "bench rc=$?"
@@ -19,7 +19,7 @@ echo "### ncu encode_words (default)"; timeout 400 ncu --set full --clock-contro
     -o gpurun_out/r02_prof_encode_words python tools/ab_encode.py 1000000 1 > /dev/null 2>&1; echo "rc=$?"
 echo "### ncu encode_words (bucketed)"; YTTM_ENC_BUCKETED=1 timeout 400 ncu --set full --clock-control none --import-source on \
     -k regex:bucketed -s 2 -c 1 -f -o gpurun_out/r02_prof_encode_words_bucketed python tools/ab_encode.py 1000000 1 > /dev/null 2>&1; echo "rc=$?"
-echo "### ncu dedup kernels"; YTTM_ENC_DEDUP=1 timeout 400 ncu --set full --clock-control none --import-source on \
-    -k regex:'dedup_words|encode_rep_words|copy_word_ids' -s 6 -c 3 -f -o gpurun_out/r02_prof_encode_dedup python tools/ab_encode.py 1000000 1 > /dev/null 2>&1; echo "rc=$?"
+echo "### ncu find_vec + dedup kernels (ab_encode sets the variants itself: 21 matching launches precede the dedup+find_vec variant)"; timeout 400 ncu --set full --clock-control none --import-source on \
+    -k regex:'find_words_vec|dedup_words|encode_rep_words|copy_word_ids' -s 21 -c 4 -f -o gpurun_out/r02_prof_encode_dedup python tools/ab_encode.py 1000000 1 > /dev/null 2>&1; echo "rc=$?"
 } > gpurun_out/r02_session1.log 2>&1
 tail -5 gpurun_out/r02_session1.log

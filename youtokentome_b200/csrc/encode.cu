@@ -194,6 +194,112 @@ __global__ void __launch_bounds__(256) find_words_cached_kernel(EncArgs a) {
   }
 }
 
+// EXPERIMENTAL variant (env YTTM_ENC_FIND_VEC=1, off by default until measured on a B200): the same two passes and the
+// same work-list order, but a lane owns FOUR consecutive bytes - one aligned 32-bit load - instead of one, and decides
+// the word starts on a 12-byte register window (previous / own / next word, the neighbours' by shuffle) instead of
+// 3 - 6 byte loads per position; the 4-bit flags of the first FIND_VEC_CACHE x 128 bytes of a sentence stay in one
+// register for the write pass.  word_start_at(p) == space_before(p) && !space_at(p) on raw bytes (a continuation
+// byte is never a space), and the text bounds become sentinel bytes: 0x20 before the sentence (space_before(lo) is
+// true; E2 96 81 cannot match across lo), 0x00 at and after its end (E2 96 81 cannot match across hi).
+constexpr int FIND_VEC_CACHE = 8;
+// the four bytes at batch positions p .. p+3 (p may be negative or reach past the batch), sentinels applied
+__device__ __forceinline__ uint32_t find_vec_word(const uint8_t *s, int64_t p, int64_t lo, int64_t hi, int64_t n_total) {
+  if (p + 4 <= lo) return 0x20202020u;
+  if (p >= hi) return 0u;
+  uint32_t w = 0;
+  if (p >= 0 && p + 4 <= n_total) w = *reinterpret_cast<const uint32_t *>(s + p);  // p is address-aligned by construction
+  else
+    for (int k = 0; k < 4; k++)
+      if (p + k >= 0 && p + k < n_total) w |= (uint32_t)s[p + k] << (8 * k);
+  if (p < lo || p + 4 > hi)
+    for (int k = 0; k < 4; k++) {
+      if (p + k < lo) w = (w & ~(0xffu << (8 * k))) | (0x20u << (8 * k));
+      else if (p + k >= hi) w &= ~(0xffu << (8 * k));
+    }
+  return w;
+}
+// word-start flags (bit k = byte p + k) of the lane's four bytes
+__device__ __forceinline__ uint32_t find_vec_flags(const uint8_t *s, int64_t p, int64_t lo, int64_t hi, int64_t n_total,
+                                                   unsigned lane) {
+  const uint32_t c = find_vec_word(s, p, lo, hi, n_total);
+  uint32_t pv = __shfl_up_sync(0xffffffffu, c, 1), nx = __shfl_down_sync(0xffffffffu, c, 1);
+  if (lane == 0) pv = find_vec_word(s, p - 4, lo, hi, n_total);
+  if (lane == 31) nx = find_vec_word(s, p + 4, lo, hi, n_total);
+  const uint64_t X = (uint64_t)pv | ((uint64_t)c << 32), Y = (uint64_t)c | ((uint64_t)nx << 32);  // bytes p-4 .. p+3, p .. p+7
+  uint32_t f = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const uint32_t t = (uint32_t)(X >> (8 * (1 + k))), u = (uint32_t)(Y >> (8 * k));  // t: bytes p+k-3 .., u: bytes p+k ..
+    const bool before = is_space_byte((uint8_t)(t >> 16)) || (t & 0xffffffu) == 0x8196e2u;
+    const bool at = is_space_byte((uint8_t)u) || (u & 0xffffffu) == 0x8196e2u;
+    if (p + k >= lo && p + k < hi && before && !at) f |= 1u << k;
+  }
+  return f;
+}
+__global__ void __launch_bounds__(256) find_words_vec_kernel(EncArgs a) {
+  __shared__ unsigned long long s_cnt[8], s_base;
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint64_t o0 = a.offs[0];
+  const int64_t n_total = (int64_t)(a.offs[a.n_sent] - o0);
+  const int64_t mis = (int64_t)(reinterpret_cast<uintptr_t>(a.bytes) & 3u);
+  for (uint64_t g = (uint64_t)blockIdx.x * 8; g < a.n_sent; g += (uint64_t)gridDim.x * 8) {  // block-uniform
+    const uint64_t s = g + wid;
+    const bool live = s < a.n_sent;
+    int64_t lo = 0, hi = 0, start = 0;
+    unsigned long long cnt = 0;
+    uint32_t cache = 0;
+    if (live) {
+      lo = (int64_t)(a.offs[s] - o0);
+      hi = (int64_t)(a.offs[s + 1] - o0);
+      start = lo - ((lo + mis) & 3);  // the address of batch byte `start` is 4-byte aligned
+      uint32_t mine = 0;
+      int j = 0;
+      for (int64_t pw = start; pw < hi; pw += 128, j++) {  // warp-uniform
+        const uint32_t f = find_vec_flags(a.bytes, pw + 4 * lane, lo, hi, n_total, lane);
+        if (j < FIND_VEC_CACHE) cache |= f << (4 * j);
+        mine += __popc(f);
+      }
+      for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+      cnt = mine;
+      if (lane == 0) {
+        const uint64_t base = sent_base((uint64_t)lo, s), len = (uint64_t)(hi - lo);
+        a.n_ids[s] = (a.bos ? 1 : 0) + (a.eos ? 1 : 0);
+        if (a.bos) a.slots[base] = a.bos_id;
+        if (a.eos) a.slots[base + len + 2] = a.eos_id;
+      }
+    }
+    if (lane == 0) s_cnt[wid] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long tot = 0;
+      for (int i = 0; i < 8; i++) { unsigned long long c = s_cnt[i]; s_cnt[i] = tot; tot += c; }
+      s_base = tot ? atomicAdd(a.n_words, tot) : 0ull;
+    }
+    __syncthreads();
+    if (live && cnt) {
+      unsigned long long idx = s_base + s_cnt[wid];
+      const unsigned below = (1u << lane) - 1u;
+      int j = 0;
+      for (int64_t pw = start; pw < hi; pw += 128, j++) {
+        const int64_t p = pw + 4 * lane;
+        const uint32_t f = j < FIND_VEC_CACHE ? (cache >> (4 * j)) & 15u : find_vec_flags(a.bytes, p, lo, hi, n_total, lane);
+        const unsigned b0 = __ballot_sync(0xffffffffu, f & 1u), b1 = __ballot_sync(0xffffffffu, f & 2u),
+                       b2 = __ballot_sync(0xffffffffu, f & 4u), b3 = __ballot_sync(0xffffffffu, f & 8u);
+        unsigned long long i = idx + __popc(b0 & below) + __popc(b1 & below) + __popc(b2 & below) + __popc(b3 & below);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if ((f >> k) & 1u) {  // byte order: lanes first, then the lane's four bytes
+            a.word_pos[i] = (uint32_t)(p + k);
+            a.word_sent[i] = (uint32_t)s;
+            i++;
+          }
+        idx += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+      }
+    }
+    __syncthreads();  // s_cnt / s_base are reused by the next round
+  }
+}
+
 // One thread per word.  Words of at most LOCAL_W - 1 bytes (nearly all) are merged in thread-private
 // local arrays (L1-resident) and only the final tokens go to the slot buffer; longer words work in
 // place in their private slots in global memory.
@@ -708,7 +814,9 @@ int enc_device(yttm_enc *enc, yttm_enc::Slot *e, const uint8_t *d_bytes, const u
     uint64_t blocks = std::min<uint64_t>((warps_needed + 7) / 8, (uint64_t)c->n_sm * 8);
     ytc::timer_begin(c, "enc_find");
     YT_CUDA(c, cudaMemsetAsync(a.slots, 0xff, n_slots * 4, c->stream));  // EMPTY_SLOT == -1
-    if (std::getenv("YTTM_ENC_FIND_CACHED"))  // experimental, see the kernel
+    if (std::getenv("YTTM_ENC_FIND_VEC"))  // experimental, see the kernels
+      find_words_vec_kernel<<<(unsigned)std::max<uint64_t>(blocks, 1), 256, 0, c->stream>>>(a);
+    else if (std::getenv("YTTM_ENC_FIND_CACHED"))
       find_words_cached_kernel<<<(unsigned)std::max<uint64_t>(blocks, 1), 256, 0, c->stream>>>(a);
     else
       find_words_kernel<<<(unsigned)std::max<uint64_t>(blocks, 1), 256, 0, c->stream>>>(a);
