@@ -171,6 +171,50 @@ def reference_arm(args, rank, world):
 _REAL_STDOUT = None
 
 
+def experimental_ab(model):
+    """INFORMATIONAL, rank 0 at N = 1 only, after every measurement of the line has been taken: the env-gated
+    experimental kernels (off by default, parity-checked under the CPU emulator) against the default ones
+    on this box, each in its own subprocess with a hard timeout so that neither a wrong nor a hanging experimental
+    kernel can cost the JSON line.  Nothing here enters `value`, `e2e` or `roofline`."""
+    import tempfile
+    env = {k: v for k, v in os.environ.items()
+           if not k.startswith(("YTTM_ENC_", "YTTM_LOOP_", "YTTM_DBG")) and k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    out = {"note": "informational A/B of env-gated experimental kernels vs the defaults (median CUDA-event ms per stage, "
+                   "same workload and model as the line); not part of value / e2e"}
+    try:
+        with tempfile.TemporaryDirectory() as d:
+            js = os.path.join(d, "ab.json")
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ab_encode.py"), str(N_SENT), "5", js, model],
+                               env=env, cwd=ROOT, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=300)
+            if r.returncode == 0 and os.path.exists(js):
+                with open(js) as fh:
+                    out["encode_stage_ms"] = json.load(fh)
+            else:
+                out["encode_stage_ms"] = {"error": r.stderr.decode(errors="replace")[-300:]}
+    except subprocess.TimeoutExpired:
+        out["encode_stage_ms"] = {"error": "timeout (300 s)"}
+    except Exception as e:
+        out["encode_stage_ms"] = {"error": repr(e)}
+    loop = {}
+    for name, extra in (("threads_1024", {"YTTM_LOOP_THREADS": "1024"}), ("threads_512", {"YTTM_LOOP_THREADS": "512"}),
+                        ("threads_256", {"YTTM_LOOP_THREADS": "256"}), ("per_block_timers", {"YTTM_DBG": "8"})):
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "probe_train.py"), "zipf", str(VOCAB), str(TRAIN_BYTES)],
+                               env=dict(env, **extra), cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=180)
+            last = [ln for ln in r.stdout.decode(errors="replace").splitlines() if ln.startswith("{")]
+            if r.returncode == 0 and last:
+                j = json.loads(last[-1])
+                loop[name] = {"us_per_merge": j["us_per_merge"], "merges": j["merges"], "phase_us_per_iter": j["phase_us_per_iter"]}
+            else:
+                loop[name] = {"error": "rc %d" % r.returncode}
+        except subprocess.TimeoutExpired:
+            loop[name] = {"error": "timeout (180 s)"}
+        except Exception as e:
+            loop[name] = {"error": repr(e)}
+    out["merge_loop"] = loop
+    return out
+
+
 def quiet_stdout():
     """stdout must carry the ONE JSON line and nothing else, but libraries write to fd 1 behind
     Python's back (NCCL prints its version banner there): point fd 1 at stderr for the whole run
@@ -199,6 +243,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-experimental-ab", action="store_true")
     ap.add_argument("--scan-tokens", type=int, default=256 * 1024 * 1024)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -409,6 +454,10 @@ def main():
         except Exception as e:  # the extra legs must never cost the JSON line
             cpu["one_thread"] = {"error": repr(e)}
 
+    ab = None
+    if rank == 0 and args.gpus == 1 and world == 1 and not args.no_cpu_baseline and not args.no_experimental_ab:
+        ab = experimental_ab(model)
+
     if rank == 0:
         out = {"metric": "encode throughput, 1M x 128 B synthetic sentences, vocab 32k", "value": value,
                "unit": "Msent/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -422,6 +471,8 @@ def main():
                        "d2h_bytes_per_step": 4 * n_ids + 8 * (n_sent + 1), "ms_per_step": sec_h / args.steps * 1e3},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                "roofline_train_scan": scan, "train": train, "cpu_baseline": cpu}
+        if ab is not None:
+            out["experimental_ab"] = ab
         emit(out)
     L.yttm_api_close(h)
     if world > 1:

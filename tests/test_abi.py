@@ -55,6 +55,16 @@ def test_fails_loudly_without_gpu(product, oracle):
         yttm.BPE.train(m, m + ".out", 12)
 
 
+def test_null_encoder_handle_is_an_error_not_a_crash(product):
+    """yttm_enc_run / yttm_enc_run_device on a null handle (what yttm_api_device_encoder returns when no device context
+    could be created): error code + message, on any box."""
+    n, p1, p2 = C.c_uint64(7), C.c_void_p(), C.c_void_p()
+    assert product.yttm_enc_run_device(None, None, None, 0, 0, 0, 0, 0, 0.0, 0, 0, C.byref(p1), C.byref(p2), C.byref(n)) == 1
+    assert b"null encoder handle" in product.yttm_last_error(None)
+    assert product.yttm_enc_run(None, None, None, 0, 0, 0, 0, 0.0, 0, 0, None, 0, None, C.byref(n)) == 1
+    assert b"null encoder handle" in product.yttm_last_error(None)
+
+
 def test_host_surface_matches_reference(product, oracle, reference):
     """decode / vocab / id_to_subword / subword_to_id / error texts vs the unmodified reference."""
     import youtokentome_b200 as yttm

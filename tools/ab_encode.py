@@ -1,5 +1,5 @@
 """A/B of the encode kernels' experimental variants on the bench workload (run on a B200):
-    python tools/ab_encode.py [n_sentences] [reps] [result.json]
+    python tools/ab_encode.py [n_sentences] [reps] [result.json] [model file]
 For each of {default, YTTM_ENC_FIND_CACHED, YTTM_ENC_BUCKETED, both, both + YTTM_ENC_ZLIN, YTTM_ENC_DEDUP, YTTM_ENC_FIND_VEC, both}: median CUDA-event ms of find / words / gather
 over `reps` runs of yttm_enc_run_device on inputs resident in HBM, and a check that the ids are identical."""
 import ctypes as C
@@ -22,11 +22,15 @@ def main(L=None, n_sent=None, reps=None, train_bytes=20_000_000, vocab=8000):
     n_sent = n_sent or (int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000)
     reps = reps or (int(sys.argv[2]) if len(sys.argv) > 2 else 7)
     fz = synth.FastZipf(n_words=200_000, s=1.07, seed=1234)
-    model = gpu_train(fz.text(train_bytes), vocab, 1.0)
+    if len(sys.argv) > 4:  # an existing model file (bench.py passes its 32 k model: the bench configuration exactly)
+        model = sys.argv[4]
+    else:
+        model = gpu_train(fz.text(train_bytes), vocab, 1.0)
     buf, offs = fz.packed_sentences(n_sent, 128, seed=4321)
     h = L.yttm_api_open(model.encode(), 1)
     assert h, L.yttm_api_last_error(None)
     ctx, enc = L.yttm_api_device_context(h), L.yttm_api_device_encoder(h)
+    assert ctx and enc, "no device encoder: " + (L.yttm_last_error(None) or b"").decode()
     on_gpu = torch.cuda.is_available()
     d_bytes = torch.frombuffer(bytearray(buf), dtype=torch.uint8)
     d_offs = torch.from_numpy(offs.astype(np.int64))

@@ -985,6 +985,7 @@ void yttm_enc_destroy(yttm_enc *e) {
 int yttm_enc_run_device(yttm_enc *e, const char *d_bytes, const uint64_t *d_offsets, uint64_t n_bytes, uint64_t n_sent,
                         int bos, int eos, int reverse, double dropout, uint64_t seed, uint64_t first_sentence_index,
                         const int32_t **d_out_ids, const uint64_t **d_out_offsets, uint64_t *out_n) {
+  if (!e) { g_yttm_create_error = "yttm_enc_run_device: null encoder handle (no CUDA device, or yttm_enc_create failed)"; return 1; }
   yttm_ctx *c = e->ctx;
   YT_CUDA(c, cudaSetDevice(c->device));
   if (bos && e->bos == -1) YT_FAIL(c, "Can't add <BOS> token. Model was trained without it.");
@@ -1000,6 +1001,7 @@ int yttm_enc_run_device(yttm_enc *e, const char *d_bytes, const uint64_t *d_offs
 int yttm_enc_run(yttm_enc *e, const char *bytes, const uint64_t *offsets, uint64_t n_sent, int bos, int eos, int reverse,
                  double dropout, uint64_t seed, uint64_t first_sentence_index, int32_t *out_ids, uint64_t out_cap,
                  uint64_t *out_offsets, uint64_t *out_n) {
+  if (!e) { g_yttm_create_error = "yttm_enc_run: null encoder handle (no CUDA device, or yttm_enc_create failed)"; return 1; }
   yttm_ctx *c = e->ctx;
   YT_CUDA(c, cudaSetDevice(c->device));
   if (bos && e->bos == -1) YT_FAIL(c, "Can't add <BOS> token. Model was trained without it.");
