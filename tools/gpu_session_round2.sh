@@ -1,9 +1,10 @@
 #!/bin/bash
-# First GPU session of the next round, one gpurun call (≈ 8–10 GPU-minutes):
+# First GPU session of the next round, one gpurun call (≈ 12–15 GPU-minutes):
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_session_round2.sh'
 # 1. the GPU tests (incl. the reference's own stress test binary and the byte-identical model file test),
 # 2. A/B of the experimental encode kernels and of the merge-loop geometry,
-# 3. ncu: launch list of bench.py and one --set full capture of encode_words (default and bucketed).
+# 3. compute-sanitizer memcheck / racecheck / synccheck on a tiny workload,
+# 4. ncu: launch list of bench.py and --set full captures of encode_words (default, bucketed) and of the dedup / vector-find kernels.
 # Everything lands in gpurun_out/ ; copy what is to be judged into profiles/ (r02_*).
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
@@ -12,6 +13,11 @@ echo "### pytest -m gpu"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 |
 echo "### ab_encode"; timeout 300 python tools/ab_encode.py 1000000 7 2>/dev/null | tail -110
 echo "### ab_long_words"; timeout 180 python tools/ab_long_words.py 16384 8 2>/dev/null | tail -20
 echo "### ab_train"; timeout 400 bash tools/ab_train.sh zipf 32000 100e6
+echo "### compute-sanitizer (tools/sanitize_small.py: tiny train + encode incl. the experimental variants, checked against the oracle)"
+for t in memcheck racecheck synccheck; do
+  timeout 420 compute-sanitizer --tool $t --error-exitcode 9 python tools/sanitize_small.py > gpurun_out/r02_sanitizer_$t.log 2>&1; echo "$t rc=$?"
+  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitize_small:" gpurun_out/r02_sanitizer_$t.log | tail -3
+done
 echo "### bench"; timeout 600 python bench.py > gpurun_out/r02_bench_first.json 2> gpurun_out/r02_bench_first.err; echo "bench rc=$?"
 echo "### ncu launch list"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file gpurun_out/r02_launches.csv python bench.py --steps 2 --warmup 3 --scan-tokens 67108864 > /dev/null 2>&1; echo "rc=$?"
