@@ -69,6 +69,19 @@ def main(L=None, n_sent=None, reps=None, train_bytes=20_000_000, vocab=8000):
         out[name] = {k: statistics.median(v[2:]) for k, v in ms.items()}
         out[name]["ids_equal_default"] = same
         out[name]["n_ids"] = int(n.value)
+    # BASELINE config 4 encodes with dropout_prob = 0.1: the default kernels' stage times there (ids are random by design)
+    for k in ("YTTM_ENC_FIND_CACHED", "YTTM_ENC_BUCKETED", "YTTM_ENC_ZLIN", "YTTM_ENC_DEDUP", "YTTM_ENC_FIND_VEC"):
+        os.environ.pop(k, None)
+    ms = {"enc_find": [], "enc_words": [], "enc_gather": [], "encode": []}
+    for r in range(reps + 2):
+        p_ids, p_off, n = C.c_void_p(), C.c_void_p(), C.c_uint64(0)
+        rc = L.yttm_enc_run_device(enc, d_bytes.data_ptr(), d_offs.data_ptr(), len(buf), n_sent, 0, 0, 0, 0.1, 1234 + r, 0,
+                                   C.byref(p_ids), C.byref(p_off), C.byref(n))
+        assert rc == 0, L.yttm_last_error(ctx)
+        for k in ms:
+            ms[k].append(L.yttm_stage_ms(ctx, k.encode()))
+    out["default_dropout_0.1"] = {k: statistics.median(v[2:]) for k, v in ms.items()}
+    out["default_dropout_0.1"]["n_ids"] = int(n.value)
     L.yttm_api_close(h)
     print(json.dumps(out, indent=1))
     if len(sys.argv) > 3:  # optional: also write the result to a file
