@@ -171,12 +171,14 @@ def reference_arm(args, rank, world):
 _REAL_STDOUT = None
 
 
-def experimental_ab(model):
+def experimental_ab(model, budget_s=240.0):
     """INFORMATIONAL, rank 0 at N = 1 only, after every measurement of the line has been taken: the env-gated
     experimental kernels (off by default, parity-checked under the CPU emulator) against the default ones
     on this box, each in its own subprocess with a hard timeout so that neither a wrong nor a hanging experimental
     kernel can cost the JSON line.  Nothing here enters `value`, `e2e` or `roofline`."""
     import tempfile
+    deadline = time.time() + budget_s   # the whole leg, however many of its subprocesses hang
+    left = lambda cap: max(1.0, min(cap, deadline - time.time()))
     env = {k: v for k, v in os.environ.items()
            if not k.startswith(("YTTM_ENC_", "YTTM_LOOP_", "YTTM_DBG")) and k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
     out = {"note": "informational A/B of env-gated experimental kernels vs the defaults (median CUDA-event ms per stage, "
@@ -185,22 +187,25 @@ def experimental_ab(model):
         with tempfile.TemporaryDirectory() as d:
             js = os.path.join(d, "ab.json")
             r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ab_encode.py"), str(N_SENT), "5", js, model],
-                               env=env, cwd=ROOT, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=300)
+                               env=env, cwd=ROOT, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=left(150))
             if r.returncode == 0 and os.path.exists(js):
                 with open(js) as fh:
                     out["encode_stage_ms"] = json.load(fh)
             else:
                 out["encode_stage_ms"] = {"error": r.stderr.decode(errors="replace")[-300:]}
     except subprocess.TimeoutExpired:
-        out["encode_stage_ms"] = {"error": "timeout (300 s)"}
+        out["encode_stage_ms"] = {"error": "timeout"}
     except Exception as e:
         out["encode_stage_ms"] = {"error": repr(e)}
     loop = {}
     for name, extra in (("threads_1024", {"YTTM_LOOP_THREADS": "1024"}), ("threads_512", {"YTTM_LOOP_THREADS": "512"}),
                         ("threads_256", {"YTTM_LOOP_THREADS": "256"}), ("per_block_timers", {"YTTM_DBG": "8"})):
+        if deadline - time.time() < 15:
+            loop[name] = {"error": "skipped: the leg's %d s budget is spent" % budget_s}
+            continue
         try:
             r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "probe_train.py"), "zipf", str(VOCAB), str(TRAIN_BYTES)],
-                               env=dict(env, **extra), cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=180)
+                               env=dict(env, **extra), cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=left(60))
             last = [ln for ln in r.stdout.decode(errors="replace").splitlines() if ln.startswith("{")]
             if r.returncode == 0 and last:
                 j = json.loads(last[-1])
@@ -208,7 +213,7 @@ def experimental_ab(model):
             else:
                 loop[name] = {"error": "rc %d" % r.returncode}
         except subprocess.TimeoutExpired:
-            loop[name] = {"error": "timeout (180 s)"}
+            loop[name] = {"error": "timeout"}
         except Exception as e:
             loop[name] = {"error": repr(e)}
     out["merge_loop"] = loop
@@ -233,6 +238,9 @@ def emit(out):
         os.write(1, line)
     else:
         os.write(_REAL_STDOUT, line)
+
+
+T_START = time.time()
 
 
 def main():
@@ -456,7 +464,10 @@ def main():
 
     ab = None
     if rank == 0 and args.gpus == 1 and world == 1 and not args.no_cpu_baseline and not args.no_experimental_ab:
-        ab = experimental_ab(model)
+        if time.time() - T_START < 420:   # a slow box: the line matters more than the extras
+            ab = experimental_ab(model)
+        else:
+            ab = {"note": "skipped: the run had already taken %.0f s" % (time.time() - T_START)}
 
     if rank == 0:
         out = {"metric": "encode throughput, 1M x 128 B synthetic sentences, vocab 32k", "value": value,
