@@ -171,7 +171,7 @@ def reference_arm(args, rank, world):
 _REAL_STDOUT = None
 
 
-def experimental_ab(model, budget_s=240.0):
+def experimental_ab(model, budget_s=270.0):
     """INFORMATIONAL, rank 0 at N = 1 only, after every measurement of the line has been taken: the env-gated
     experimental kernels (off by default, parity-checked under the CPU emulator) against the default ones
     on this box, each in its own subprocess with a hard timeout so that neither a wrong nor a hanging experimental
@@ -198,8 +198,11 @@ def experimental_ab(model, budget_s=240.0):
     except Exception as e:
         out["encode_stage_ms"] = {"error": repr(e)}
     loop = {}
-    for name, extra in (("threads_1024", {"YTTM_LOOP_THREADS": "1024"}), ("threads_512", {"YTTM_LOOP_THREADS": "512"}),
-                        ("threads_256", {"YTTM_LOOP_THREADS": "256"}), ("per_block_timers", {"YTTM_DBG": "8"})):
+    for name, extra in (("default", {}), ("wide_probe", {"YTTM_LOOP_WIDEPROBE": "1"}),
+                        ("max_load_50", {"YTTM_PAIR_MAX_LOAD_PCT": "50"}),
+                        ("wide_probe+max_load_50", {"YTTM_LOOP_WIDEPROBE": "1", "YTTM_PAIR_MAX_LOAD_PCT": "50"}),
+                        ("per_block_timers", {"YTTM_DBG": "8"}), ("wide_probe+per_block_timers", {"YTTM_LOOP_WIDEPROBE": "1", "YTTM_DBG": "8"}),
+                        ("threads_512", {"YTTM_LOOP_THREADS": "512"}), ("threads_256", {"YTTM_LOOP_THREADS": "256"})):
         if deadline - time.time() < 15:
             loop[name] = {"error": "skipped: the leg's %d s budget is spent" % budget_s}
             continue
@@ -209,7 +212,8 @@ def experimental_ab(model, budget_s=240.0):
             last = [ln for ln in r.stdout.decode(errors="replace").splitlines() if ln.startswith("{")]
             if r.returncode == 0 and last:
                 j = json.loads(last[-1])
-                loop[name] = {"us_per_merge": j["us_per_merge"], "merges": j["merges"], "phase_us_per_iter": j["phase_us_per_iter"]}
+                loop[name] = {"us_per_merge": j["us_per_merge"], "merges": j["merges"], "table_slots": j["cap"], "launches": j["launches"],
+                              "phase_us_per_iter": j["phase_us_per_iter"]}
             else:
                 loop[name] = {"error": "rc %d" % r.returncode}
         except subprocess.TimeoutExpired:

@@ -226,9 +226,13 @@ def _abi_train(L, text, vocab):
         assert L.yttm_train_run(ctx, 4 + len(kc), nm, rules.ctypes.data, fr.ctypes.data, C.byref(done)) == 0, \
             L.yttm_last_error(ctx)
         launches = int(L.yttm_stage_ms(ctx, b"loop_launches"))
+        _LAST["loop_variant"] = L.yttm_stage_ms(ctx, b"loop_variant")
         return [tuple(r) for r in rules[:3 * done.value].reshape(-1, 3).tolist()], launches, st
     finally:
         L.yttm_ctx_destroy(ctx)
+
+
+_LAST = {}
 
 
 def _oracle_rules(oracle, text, vocab):
@@ -371,3 +375,47 @@ def test_encode_find_vec_variant(emu, oracle, monkeypatch):
         ids = np.ctypeslib.as_array(C.cast(p_ids, C.POINTER(C.c_int32)), shape=(n.value,)).copy()
         oo = np.ctypeslib.as_array(C.cast(p_off, C.POINTER(C.c_uint64)), shape=(len(sents) + 1,)).copy()
         assert _bind._unpack(ids, oo) == want, shift
+
+
+@pytest.mark.parametrize("floor", [None, "16", "64"])
+def test_train_wide_probe_variant(emu, oracle, monkeypatch, floor):
+    """YTTM_LOOP_WIDEPROBE (experimental, off by default): the merge loop whose table updates fetch four slots (one
+    32-byte sector of the key array) per round trip.  Same rules as the oracle on stress seeds, dirty Unicode, runs,
+    RESIDENT and STREAMING tiles; with pair-table floors of 16 / 64 slots the table lives at high load, probe chains run
+    across many groups of four, wrap around the end of the table, overflow (probe limit) and are rebuilt again and again."""
+    monkeypatch.setenv("YTTM_LOOP_WIDEPROBE", "1")
+    if floor:
+        monkeypatch.setenv("YTTM_PAIR_CAP_FLOOR", floor)
+    for seed in range(8):
+        text, vocab, cov, _ = _cases.stress_case(seed)
+        TG._same(oracle, text, vocab, cov)
+    TG._same(oracle, _cases.dirty_zipf_text(60_000), 700, 0.98)
+    TG._same(oracle, b"a" * 500 + b" " + b"ab" * 300 + b" aaa aaaa aaaaa " + b"b" * 1001, 40)
+    text = _cases.zipf().text(20_000)
+    rules, launches, _ = _abi_train(emu, text, 700)
+    assert _LAST["loop_variant"] == 1.0 and (launches >= 2 or not floor)
+    assert rules == _oracle_rules(oracle, text, 700)
+    monkeypatch.setenv("YTTM_FORCE_STREAM", "1")
+    monkeypatch.setenv("YTTM_STREAM_Q", "128")
+    for seed in (1, 5):
+        text, vocab, cov, _ = _cases.stress_case(seed)
+        TG._same(oracle, text, vocab, cov)
+    monkeypatch.setenv("YT_EMU_SMS", "5")
+    TG._same(oracle, _cases.dirty_zipf_text(40_000), 500, 0.98)
+
+
+@pytest.mark.parametrize("pct", ["30", "50", "90"])
+def test_train_pair_table_load_knob(emu, oracle, monkeypatch, pct):
+    """YTTM_PAIR_MAX_LOAD_PCT (A/B knob, default 75): the load factor at which the loop leaves for a rebuild (a rebuilt
+    table is accepted at half of it) changes table sizes and rebuild points, never the rules."""
+    monkeypatch.setenv("YTTM_PAIR_MAX_LOAD_PCT", pct)
+    monkeypatch.setenv("YTTM_PAIR_CAP_FLOOR", "32")
+    for seed in (0, 2, 6):
+        text, vocab, cov, _ = _cases.stress_case(seed)
+        TG._same(oracle, text, vocab, cov)
+    text = _cases.zipf().text(20_000)
+    rules, launches, _ = _abi_train(emu, text, 700)
+    assert rules == _oracle_rules(oracle, text, 700)   # (at 30 % the first table is large enough for the whole run)
+    monkeypatch.setenv("YTTM_LOOP_WIDEPROBE", "1")
+    rules, _, _ = _abi_train(emu, text, 700)
+    assert _LAST["loop_variant"] == 1.0 and rules == _oracle_rules(oracle, text, 700)

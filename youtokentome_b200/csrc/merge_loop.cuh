@@ -86,7 +86,8 @@ struct WarpQueue {
   long long *delta;
   uint32_t n;               // warp-uniform
 };
-__device__ __forceinline__ void uq_drain(WarpQueue &q, unsigned lane, const PairTab &tab) {
+template <class Tab>
+__device__ __forceinline__ void uq_drain(WarpQueue &q, unsigned lane, const Tab &tab) {
   __syncwarp();
   for (uint32_t i = lane; i < q.n; i += 32) {
     const long long d = q.delta[i];
@@ -97,8 +98,9 @@ __device__ __forceinline__ void uq_drain(WarpQueue &q, unsigned lane, const Pair
   q.n = 0;
 }
 // every lane may contribute one update (has == true); direct == true bypasses the queue
+template <class Tab>
 __device__ __forceinline__ void uq_push(WarpQueue &q, bool direct, bool has, unsigned long long key, long long delta,
-                                        unsigned lane, const PairTab &tab) {
+                                        unsigned lane, const Tab &tab) {
   if (direct) { if (has) pair_add(tab, key, delta); return; }
   const unsigned m = __ballot_sync(0xffffffffu, has);
   if (has) {
@@ -129,8 +131,9 @@ __device__ __forceinline__ RunInfo warp_runs(uint32_t t, uint32_t n, unsigned la
 // memory), gt = optional write-through copy in global memory.  Table updates: only the pairs
 // whose run is touched by a merge are sent (-old, +new); untouched runs cancel exactly.
 // Returns the number of merges.
+template <class Tab>
 __device__ __forceinline__ uint32_t warp_apply_word(uint32_t *st, uint32_t cap, uint32_t *gt, long long f,
-                                                    const MergeOp &op, unsigned lane, const PairTab &tab,
+                                                    const MergeOp &op, unsigned lane, const Tab &tab,
                                                     WarpQueue &q) {
   if (cap > 32) {  // long word: scalar path on lane 0 (exact, slow)
     uint32_t merges = 0;
@@ -203,9 +206,10 @@ __device__ __forceinline__ uint32_t warp_apply_word(uint32_t *st, uint32_t cap, 
 // the second element of an in-word pair — is never a word-initial token; tail padding (DEAD)
 // matches nothing.  Each hit is mapped to its word (binary search in the offsets), the word is
 // claimed once through a bitmap, and claimed words are rewritten by the whole warp.
+template <class Tab>
 __device__ __forceinline__ unsigned long long process_tile(uint32_t *stok, const uint32_t *soff, uint32_t nw,
                                                            uint32_t span, uint32_t *claim, const uint64_t *gfreq,
-                                                           const MergeOp &op, const PairTab &tab, WarpQueue &q) {
+                                                           const MergeOp &op, const Tab &tab, WarpQueue &q) {
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   unsigned long long dead = 0;
   // a lane compares four tokens from one 16-byte shared load (stok is 16-byte aligned, its capacity a
@@ -255,9 +259,10 @@ __device__ __forceinline__ unsigned long long process_tile(uint32_t *stok, const
 }
 
 // Oversized tile (a word longer than the shared buffer): thread per word straight on global memory.
+template <class Tab>
 __device__ __forceinline__ unsigned long long process_tile_direct(uint32_t *tok, const uint32_t *off,
                                                                   const uint64_t *freq, uint32_t w0, uint32_t w1,
-                                                                  const MergeOp &op, const PairTab &tab) {
+                                                                  const MergeOp &op, const Tab &tab) {
   unsigned long long dead = 0;
   for (uint32_t w = w0 + threadIdx.x; w < w1; w += blockDim.x) {
     uint32_t o = off[w], wcap = off[w + 1] - o;
@@ -357,7 +362,9 @@ extern __shared__ __align__(16) uint32_t yt_dyn_smem[];
 #define yt_dyn_smem (reinterpret_cast<uint32_t *>(emu::dyn_smem()))
 #endif
 
-__global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
+template <bool WIDE>
+__device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
+  const auto &tab = TabView<WIDE>::of(a.tab);  // WIDE: the table probed four slots per round trip (experimental)
   cg::grid_group grid = cg::this_grid();
   __shared__ Best s_warp[32];
   __shared__ Best s_best;
@@ -493,7 +500,7 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
     unsigned long long dead = 0;
     if (a.resident) {
       if (rw1 > rw0) dead = process_tile(stok, soff, rw1 - rw0, soff[rw1 - rw0], s_claim,
-                                           reinterpret_cast<const uint64_t *>(sfreq), op, a.tab, uq);
+                                           reinterpret_cast<const uint64_t *>(sfreq), op, tab, uq);
     } else {
       // STREAMING: this block owns a contiguous chunk of tiles that flows through an n_stage ring of
       // shared-memory stages.  Lane 0 of warp 0 is the PRODUCER: it keeps up to n_stage tiles in
@@ -621,13 +628,13 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
         for (uint32_t j = wid; j < n_def; j += nwarp) {
           const uint4 e = defer[j];
           const long long f = (long long)a.freq[e.x];
-          const uint32_t merges = warp_apply_word(a.tok + e.y, e.z, nullptr, f, op, lane, a.tab, uq);
+          const uint32_t merges = warp_apply_word(a.tok + e.y, e.z, nullptr, f, op, lane, tab, uq);
           if (lane == 0) dead += merges;
         }
         if (s_direct && my_tiles) {  // oversized tiles / overflowed list: exact thread-per-word pass on global memory
           __syncthreads();
           const uint32_t w_lo = a.tile_desc[k_first].x, w_hi = a.tile_desc[k_first + my_tiles].x;
-          dead += process_tile_direct(a.tok, a.off, a.freq, w_lo, w_hi, op, a.tab);
+          dead += process_tile_direct(a.tok, a.off, a.freq, w_lo, w_hi, op, tab);
         }
       }
       // write-through stores (generic proxy) must be ordered before the next iteration's bulk loads
@@ -636,7 +643,7 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
 #endif
     }
     if (dbgt && lane == 0) atomicMax(&s_tpre, gtimer() - tw0);
-    if (uq.n) uq_drain(uq, lane, a.tab);  // one batch of table updates per warp and iteration
+    if (uq.n) uq_drain(uq, lane, tab);  // one batch of table updates per warp and iteration
     for (int o = 16; o > 0; o >>= 1) dead += __shfl_xor_sync(0xffffffffu, dead, o);
     if (lane == 0 && dead) atomicAdd(&s_dead, dead);
     __syncthreads();
@@ -674,6 +681,8 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) {
     for (uint32_t i = threadIdx.x; i < span; i += blockDim.x) a.tok[o0 + i] = stok[i];
   }
 }
+__global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) { merge_loop_body<false>(a); }
+__global__ void __launch_bounds__(1024, 1) merge_loop_wide_kernel(LoopArgs a) { merge_loop_body<true>(a); }  // YTTM_LOOP_WIDEPROBE
 
 // ---- tile planning -----------------------------------------------------------------------------
 // tile k = words whose first token slot lies in [k*q, (k+1)*q); tile_desc[k] = (its first word,

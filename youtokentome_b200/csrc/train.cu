@@ -56,6 +56,9 @@ __device__ __forceinline__ void pair_add(const PairTab &t, uint64_t key, long lo
       if (k == PK_EMPTY) { atomicAdd(t.n_keys, 1u); k = key; }
     } else {
       k = __ldcg(t.keys + h);
+#ifdef YT_SIMT_EMU
+      emu::yield();  // test harness: see pair_add(PairTabWide)
+#endif
       if (k == PK_EMPTY) {
         k = atomicCAS(t.keys + h, PK_EMPTY, (unsigned long long)key);
         if (k == PK_EMPTY) { atomicAdd(t.n_keys, 1u); k = key; }
@@ -66,6 +69,51 @@ __device__ __forceinline__ void pair_add(const PairTab &t, uint64_t key, long lo
   }
   atomicExch(t.overflow, 1u);
 }
+
+// EXPERIMENTAL (env YTTM_LOOP_WIDEPROBE=1, merge loop only; off by default until measured on a B200): the same table
+// and the same placement rule (the first empty or matching slot along h, h+1, ...), but FOUR slots - one aligned
+// 32-byte sector of the key array - are fetched per L2 round trip by independent loads, instead of one dependent
+// round trip per slot.  Why: keys are never deleted, the table runs between load 3/8 and 3/4, and a linear-probe
+// insert at load 0.7 walks ~6 slots on average and several times that in the worst of the ~100 inserts of a merge -
+// each a dependent __ldcg / CAS of ~1 us - which is the suspected "one unlucky block" tail of the apply phase
+// (DESIGN.md 6).  A slot that was occupied by another key when loaded stays so (keys never change), a slot that was
+// empty is claimed by CAS, whose return value is the truth; two inserters of one key meet at the same slot.
+struct PairTabWide : PairTab {};
+template <bool CAS_FIRST = false>
+__device__ __forceinline__ void pair_add(const PairTabWide &t, uint64_t key, long long delta) {
+  uint64_t h = mix64(key) & t.mask;
+  const uint64_t limit = t.mask < PROBE_LIMIT ? t.mask : PROBE_LIMIT;
+  uint64_t probe = 0;
+  while (probe <= limit) {
+    const uint64_t g = h & ~3ull;  // the capacity is a power of two >= 16: a group of four never wraps
+    unsigned long long k4[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) k4[j] = __ldcg(t.keys + g + j);
+#ifdef YT_SIMT_EMU
+    emu::yield();  // test harness: other fibers run between the loads and the CAS, so the lost-race path is exercised
+#endif
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if ((uint64_t)j < (h & 3ull) || probe > limit) continue;
+      probe++;
+      unsigned long long k = k4[j];
+      if (k == PK_EMPTY) {
+        k = atomicCAS(t.keys + g + j, PK_EMPTY, (unsigned long long)key);
+        if (k == PK_EMPTY) { atomicAdd(t.n_keys, 1u); k = key; }
+      }
+      if (k == key) { atomicAdd(t.cnts + g + j, (unsigned long long)delta); return; }
+    }
+    h = (g + 4) & t.mask;
+  }
+  atomicExch(t.overflow, 1u);
+}
+template <bool W> struct TabView;
+template <> struct TabView<false> {
+  static __device__ __forceinline__ const PairTab &of(const PairTab &t) { return t; }
+};
+template <> struct TabView<true> {
+  static __device__ __forceinline__ PairTabWide of(const PairTab &t) { PairTabWide w; static_cast<PairTab &>(w) = t; return w; }
+};
 
 // ------------------------------------------------------------------------------------------
 // phase 1: decode units + code point histogram
@@ -372,6 +420,13 @@ PairTab tab_of(yttm_ctx *c) {
 // (Re)build the pair table from the current packed words.  Grows the table until the load
 // factor after the build is <= 1/4.
 // smallest pair table; YTTM_PAIR_CAP_FLOOR lowers it so that tests reach the rebuild / overflow paths on tiny inputs
+// Load factor (percent) above which the merge loop leaves for a rebuild; a rebuilt table is accepted at half of it.
+// Default 75 / 37.5 (the measured configuration); YTTM_PAIR_MAX_LOAD_PCT = 30..90 is an A/B knob: a lower load means
+// shorter probe chains for the table updates and a larger table for the arg-max sweep.
+static uint64_t pair_max_load_pct() {
+  if (const char *e = std::getenv("YTTM_PAIR_MAX_LOAD_PCT")) return (uint64_t)std::min(90, std::max(30, std::atoi(e)));
+  return 75;
+}
 static uint64_t pair_cap_floor() {
   if (const char *e = std::getenv("YTTM_PAIR_CAP_FLOOR")) return ytc::pow2ceil((uint64_t)std::max(16, std::atoi(e)));
   return 1u << 16;
@@ -399,7 +454,7 @@ int rebuild_pair_table(yttm_ctx *c, uint64_t min_cap) {
     YT_CUDA(c, cudaMemcpyAsync(h, &ctl->n_keys, 8, cudaMemcpyDeviceToHost, c->stream));
     YT_CUDA(c, cudaStreamSynchronize(c->stream));
     // accept at load <= 3/8: the arg-max sweeps every slot every merge, so the table is kept tight
-    if (!h[1] && (uint64_t)h[0] * 8 <= cap * 3) { c->stats.n_pairs = h[0]; c->stats.table_capacity = cap; return 0; }
+    if (!h[1] && (uint64_t)h[0] * 200 <= cap * pair_max_load_pct()) { c->stats.n_pairs = h[0]; c->stats.table_capacity = cap; return 0; }
     cap *= 2;
   }
   YT_FAIL(c, "pair table: could not reach load factor 3/8");
@@ -888,6 +943,7 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
       c->loop_stream_tok_cap = (per_stage - c->loop_stream_word_cap) & ~3u;
     }
     YT_CUDA(c, cudaFuncSetAttribute(merge_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    YT_CUDA(c, cudaFuncSetAttribute(merge_loop_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
     int threads = 1024, per_sm = 0;
     if (const char *e = std::getenv("YTTM_LOOP_THREADS")) threads = std::atoi(e);
     YT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_loop_kernel, threads, dyn));
@@ -923,14 +979,17 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
     a.first_new_id = first_new_id;
     a.max_total = max_merges;
     a.max_iters = max_merges;
-    a.key_limit = (uint32_t)std::min<uint64_t>(c->pcap / 4 * 3, 0xfffffff0ull);  // rebuild above load 3/4
+    a.key_limit = (uint32_t)std::min<uint64_t>(c->pcap / 100 * pair_max_load_pct() + c->pcap % 100 * pair_max_load_pct() / 100,
+                                               0xfffffff0ull);  // rebuild above load 3/4 (default)
+    const bool wide = std::getenv("YTTM_LOOP_WIDEPROBE") != nullptr;  // experimental, see pair_add(PairTabWide)
+    c->timers["loop_variant"].ms = wide ? 1.f : 0.f;                   // yttm_stage_ms(ctx, "loop_variant")
 #ifndef YT_SIMT_EMU
     void *args[] = {&a};
-    YT_CUDA(c, cudaLaunchCooperativeKernel((void *)merge_loop_kernel, dim3(c->loop_blocks), dim3(c->loop_threads), args,
-                                           (size_t)c->loop_smem, c->stream));
+    YT_CUDA(c, cudaLaunchCooperativeKernel(wide ? (void *)merge_loop_wide_kernel : (void *)merge_loop_kernel,
+                                           dim3(c->loop_blocks), dim3(c->loop_threads), args, (size_t)c->loop_smem, c->stream));
 #else  // tests/emul/simt: every block on its own OS thread, grid.sync() = pthread barrier
     emu::launch_cooperative((unsigned)c->loop_blocks, (unsigned)c->loop_threads, (size_t)c->loop_smem,
-                            [=]() { merge_loop_kernel(a); });
+                            [=]() { if (wide) merge_loop_wide_kernel(a); else merge_loop_kernel(a); });
 #endif
     c->launches++;
     YT_CUDA(c, cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
