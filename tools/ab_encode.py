@@ -32,6 +32,8 @@ def main(L=None, n_sent=None, reps=None, train_bytes=20_000_000, vocab=8000):
     ctx, enc = L.yttm_api_device_context(h), L.yttm_api_device_encoder(h)
     assert ctx and enc, "no device encoder: " + (L.yttm_last_error(None) or b"").decode()
     on_gpu = torch.cuda.is_available()
+    if on_gpu:
+        from youtokentome_b200.distributed import _DevView
     d_bytes = torch.frombuffer(bytearray(buf), dtype=torch.uint8)
     d_offs = torch.from_numpy(offs.astype(np.int64))
     if on_gpu:
@@ -83,6 +85,30 @@ def main(L=None, n_sent=None, reps=None, train_bytes=20_000_000, vocab=8000):
     out["default_dropout_0.1"] = {k: statistics.median(v[2:]) for k, v in ms.items()}
     out["default_dropout_0.1"]["n_ids"] = int(n.value)
     L.yttm_api_close(h)
+    # host-only knob: slots per rule of the encoder's rule table (default 2), read when the encoder is created
+    for slots in (4, 8, 16):
+        os.environ["YTTM_ENC_RULE_SLOTS"] = str(slots)
+        h2 = L.yttm_api_open(model.encode(), 1)
+        assert h2, L.yttm_api_last_error(None)
+        ctx2, enc2 = L.yttm_api_device_context(h2), L.yttm_api_device_encoder(h2)
+        ms = {"enc_find": [], "enc_words": [], "enc_gather": [], "encode": []}
+        for _ in range(reps + 2):
+            p_ids, p_off, n = C.c_void_p(), C.c_void_p(), C.c_uint64(0)
+            rc = L.yttm_enc_run_device(enc2, d_bytes.data_ptr(), d_offs.data_ptr(), len(buf), n_sent, 0, 0, 0, 0.0, 0, 0,
+                                       C.byref(p_ids), C.byref(p_off), C.byref(n))
+            assert rc == 0, L.yttm_last_error(ctx2)
+            for k in ms:
+                ms[k].append(L.yttm_stage_ms(ctx2, k.encode()))
+        if on_gpu:
+            torch.cuda.synchronize()
+            ids = torch.as_tensor(_DevView(p_ids.value, n.value, "<i4"), device="cuda").cpu().numpy()
+        else:
+            ids = np.ctypeslib.as_array(C.cast(p_ids, C.POINTER(C.c_int32)), shape=(n.value,)).copy()
+        out["rule_slots_%d" % slots] = {k: statistics.median(v[2:]) for k, v in ms.items()}
+        out["rule_slots_%d" % slots]["ids_equal_default"] = bool(np.array_equal(base, ids))
+        out["rule_slots_%d" % slots]["n_ids"] = int(n.value)
+        L.yttm_api_close(h2)
+    os.environ.pop("YTTM_ENC_RULE_SLOTS", None)
     print(json.dumps(out, indent=1))
     if len(sys.argv) > 3:  # optional: also write the result to a file
         with open(sys.argv[3], "w") as fh:

@@ -930,7 +930,13 @@ int yttm_enc_create(yttm_ctx *c, const uint32_t *char_cp, const uint32_t *char_i
     if (char_cp[i] == SPACE_CP) { e->space_id = char_id[i]; have_space = true; }
   }
   if (!have_space) { delete e; YT_FAIL(c, "model: U+2581 missing from char2id"); }
-  uint64_t cap = std::max<uint64_t>(ytc::pow2ceil(n_rules * 2 + 2), 1024);
+  // slots per rule of the open-addressed rule table.  Default 2 (load <= 1/2, the measured configuration); most
+  // adjacent token pairs have NO rule, and an unsuccessful linear-probe search costs ~2.5 probes at load 1/2 but
+  // ~1.15 at 1/8, each probe a dependent 16-byte load: YTTM_ENC_RULE_SLOTS = 2..64 is an A/B knob (tools/ab_encode.py);
+  // 32 000 rules at 8 slots per rule are 4 MB, still L2-resident.
+  uint64_t per_rule = 2;
+  if (const char *env = std::getenv("YTTM_ENC_RULE_SLOTS")) per_rule = (uint64_t)std::min(64, std::max(2, std::atoi(env)));
+  uint64_t cap = std::max<uint64_t>(ytc::pow2ceil(n_rules * per_rule + 2), 1024);
   std::vector<uint4> slots(cap, make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0));
   for (uint64_t i = 0; i < n_rules; i++) {
     uint32_t x = rules_xyz[3 * i], y = rules_xyz[3 * i + 1], z = rules_xyz[3 * i + 2];
