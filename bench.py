@@ -171,7 +171,7 @@ def reference_arm(args, rank, world):
 _REAL_STDOUT = None
 
 
-def experimental_ab(model, budget_s=270.0):
+def experimental_ab(model, budget_s=300.0):
     """INFORMATIONAL, rank 0 at N = 1 only, after every measurement of the line has been taken: the env-gated
     experimental kernels (off by default, parity-checked under the CPU emulator) against the default ones
     on this box, each in its own subprocess with a hard timeout so that neither a wrong nor a hanging experimental
@@ -202,6 +202,7 @@ def experimental_ab(model, budget_s=270.0):
                         ("max_load_50", {"YTTM_PAIR_MAX_LOAD_PCT": "50"}),
                         ("wide_probe+max_load_50", {"YTTM_LOOP_WIDEPROBE": "1", "YTTM_PAIR_MAX_LOAD_PCT": "50"}),
                         ("per_block_timers", {"YTTM_DBG": "8"}), ("wide_probe+per_block_timers", {"YTTM_LOOP_WIDEPROBE": "1", "YTTM_DBG": "8"}),
+                        ("blocks_74", {"YTTM_LOOP_BLOCKS": "74"}), ("blocks_111", {"YTTM_LOOP_BLOCKS": "111"}),
                         ("threads_512", {"YTTM_LOOP_THREADS": "512"}), ("threads_256", {"YTTM_LOOP_THREADS": "256"})):
         if deadline - time.time() < 15:
             loop[name] = {"error": "skipped: the leg's %d s budget is spent" % budget_s}

@@ -419,3 +419,19 @@ def test_train_pair_table_load_knob(emu, oracle, monkeypatch, pct):
     monkeypatch.setenv("YTTM_LOOP_WIDEPROBE", "1")
     rules, _, _ = _abi_train(emu, text, 700)
     assert _LAST["loop_variant"] == 1.0 and rules == _oracle_rules(oracle, text, 700)
+
+
+@pytest.mark.parametrize("blocks", ["1", "2", "3"])
+def test_train_loop_blocks_knob(emu, oracle, monkeypatch, blocks):
+    """YTTM_LOOP_BLOCKS (A/B knob): fewer blocks than SMs in the cooperative launch - tile ownership, the per-block
+    winners and the barrier count change, the rules do not."""
+    monkeypatch.setenv("YT_EMU_SMS", "4")
+    monkeypatch.setenv("YTTM_LOOP_BLOCKS", blocks)
+    for seed in (1, 3):
+        text, vocab, cov, _ = _cases.stress_case(seed)
+        TG._same(oracle, text, vocab, cov)
+    TG._same(oracle, _cases.dirty_zipf_text(40_000), 500, 0.98)
+    monkeypatch.setenv("YTTM_FORCE_STREAM", "1")
+    monkeypatch.setenv("YTTM_STREAM_Q", "128")
+    text, vocab, cov, _ = _cases.stress_case(5)
+    TG._same(oracle, text, vocab, cov)

@@ -7,6 +7,10 @@ for t in 1024 512 256; do
   echo "== YTTM_LOOP_THREADS=$t"
   YTTM_LOOP_THREADS=$t python tools/probe_train.py "$C" "$V" "$B" 2>/dev/null | tail -1 | cut -c1-600
 done
+for b in 74 111; do
+  echo "== YTTM_LOOP_BLOCKS=$b"
+  YTTM_LOOP_BLOCKS=$b python tools/probe_train.py "$C" "$V" "$B" 2>/dev/null | tail -1 | cut -c1-600
+done
 echo "== YTTM_LOOP_WIDEPROBE=1 (table updates fetch four slots per round trip)"
 YTTM_LOOP_WIDEPROBE=1 python tools/probe_train.py "$C" "$V" "$B" 2>/dev/null | tail -1 | cut -c1-600
 echo "== YTTM_PAIR_MAX_LOAD_PCT=50 (rebuild above load 1/2 instead of 3/4), default kernel / wide probe"

@@ -321,12 +321,25 @@ static Status train_on_buffer(const char *text, uint64_t n, int n_tokens, const 
   struct Cache {  // deliberately not destroyed at thread / process exit (no CUDA calls during teardown)
     yttm_ctx *ctx = nullptr;
     int device = -1;
+    std::string geometry;
   };
   static thread_local Cache cache;
-  if (cache.ctx && cache.device != default_device()) { yttm_ctx_destroy(cache.ctx); cache.ctx = nullptr; }
+  // a context fixes its launch geometry when it first trains: the knobs that shape it are part of the cache key, so a
+  // changed setting takes effect in a running process (the A/B tools and the tests vary them between calls)
+  std::string geometry;
+  for (const char *k : {"YTTM_STAGES", "YTTM_LOOP_THREADS", "YTTM_LOOP_BLOCKS", "YT_EMU_SMS"}) {
+    const char *v = std::getenv(k);
+    geometry += v ? v : "";
+    geometry += '|';
+  }
+  if (cache.ctx && (cache.device != default_device() || cache.geometry != geometry)) {
+    yttm_ctx_destroy(cache.ctx);
+    cache.ctx = nullptr;
+  }
   if (!cache.ctx) {
     if (yttm_ctx_create(default_device(), &cache.ctx)) { cache.ctx = nullptr; return Status(1, yttm_last_error(nullptr)); }
     cache.device = default_device();
+    cache.geometry = geometry;
   }
   yttm_ctx *ctx = cache.ctx;
   const uint64_t launches0 = yttm_launch_count(ctx);

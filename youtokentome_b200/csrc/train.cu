@@ -950,6 +950,9 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
     if (per_sm < 1) YT_FAIL(c, "merge_loop_kernel does not fit on an SM");
     c->loop_threads = threads;
     c->loop_blocks = c->n_sm;
+    // A/B knob: fewer blocks make the two grid barriers and the winner reduce cheaper and the per-block sweep /
+    // tile longer (the tile planner falls back to STREAMING by itself if the words no longer fit)
+    if (const char *e = std::getenv("YTTM_LOOP_BLOCKS")) c->loop_blocks = std::max(1, std::min(c->n_sm, std::atoi(e)));
   }
   YT_CUDA(c, c->blockbest.reserve((size_t)c->loop_blocks * 4 * 8));
   YT_CUDA(c, c->d_rules.reserve((size_t)max_merges * 12 + 16));
