@@ -101,6 +101,9 @@ struct TrainReport {
   uint64_t launches = 0;
 };
 const TrainReport &last_train_report();
+// train_bpe keeps one training context (device buffers of the corpus, word table, packed words, pair table) per host
+// thread between calls; this frees the calling thread's.
+void release_training_cache();
 
 // bpe.h:19 — reads input_path, trains on the GPU, writes the model file.
 Status train_bpe(const std::string &input_path, const std::string &model_path, int vocab_size, BpeConfig config);

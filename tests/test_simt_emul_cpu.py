@@ -435,3 +435,13 @@ def test_train_loop_blocks_knob(emu, oracle, monkeypatch, blocks):
     monkeypatch.setenv("YTTM_STREAM_Q", "128")
     text, vocab, cov, _ = _cases.stress_case(5)
     TG._same(oracle, text, vocab, cov)
+
+
+def test_release_training_cache(emu, oracle):
+    """release_training_cache(): a no-op before any training, and a training after it builds a fresh context."""
+    emu.yttm_api_release_training_cache()
+    text, vocab, cov, _ = _cases.stress_case(2)
+    TG._same(oracle, text, vocab, cov)
+    emu.yttm_api_release_training_cache()
+    emu.yttm_api_release_training_cache()
+    TG._same(oracle, text, vocab, cov)

@@ -312,18 +312,27 @@ static void rename_tokens(flat_hash_map<uint32_t, uint32_t> &char2id, std::vecto
   for (auto &r : rules) { r.x = ren[r.x]; r.y = ren[r.y]; r.z = ren[r.z]; }
 }
 
+struct TrainCache {  // deliberately not destroyed at thread / process exit (no CUDA calls during teardown)
+  yttm_ctx *ctx = nullptr;
+  int device = -1;
+  std::string geometry;
+};
+static thread_local TrainCache g_train_cache;
+
+// Gives the device memory of this thread's cached training context back (the next train_bpe builds a new one).
+void release_training_cache() {
+  if (g_train_cache.ctx) yttm_ctx_destroy(g_train_cache.ctx);
+  g_train_cache.ctx = nullptr;
+  g_train_cache.device = -1;
+}
+
 static Status train_on_buffer(const char *text, uint64_t n, int n_tokens, const std::string &output_file,
                               BpeConfig cfg, BPEState *out_state) {
   double t_start = now_s();
   // one training context per host thread and device, kept between calls: its device buffers
   // (corpus, word table, packed words, pair table) are reused instead of cudaMalloc'ed / freed
   // on every train_bpe (release_training_cache() gives the memory back)
-  struct Cache {  // deliberately not destroyed at thread / process exit (no CUDA calls during teardown)
-    yttm_ctx *ctx = nullptr;
-    int device = -1;
-    std::string geometry;
-  };
-  static thread_local Cache cache;
+  TrainCache &cache = g_train_cache;
   // a context fixes its launch geometry when it first trains: the knobs that shape it are part of the cache key, so a
   // changed setting takes effect in a running process (the A/B tools and the tests vary them between calls)
   std::string geometry;

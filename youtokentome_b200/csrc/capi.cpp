@@ -46,6 +46,8 @@ int yttm_api_train_memory(const char *text, uint64_t n, const char *model_path, 
   return 0;
 }
 
+void yttm_api_release_training_cache(void) { release_training_cache(); }
+
 int yttm_api_train_report(double *out, int n) {
   const TrainReport &r = last_train_report();
   double v[] = {(double)r.n_bytes, (double)r.data_len, (double)r.n_words, (double)r.n_unique, (double)r.n_tokens,

@@ -183,6 +183,12 @@ class BPE:
         self._open()
 
 
+def release_training_cache():
+    """BPE.train keeps its device buffers (corpus, word table, packed words, pair table) cached per host thread so
+    that repeated trainings do not reallocate; this gives the calling thread's back to the device."""
+    _lib.lib().yttm_api_release_training_cache()
+
+
 def train_report():
     """Sizes / stage timings of the last BPE.train on this thread (dict)."""
     out = (C.c_double * 16)()
