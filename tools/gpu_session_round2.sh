@@ -27,5 +27,10 @@ echo "### ncu encode_words (bucketed)"; YTTM_ENC_BUCKETED=1 timeout 400 ncu --se
     -k regex:bucketed -s 2 -c 1 -f -o gpurun_out/r02_prof_encode_words_bucketed python tools/ab_encode.py 1000000 1 > /dev/null 2>&1; echo "rc=$?"
 echo "### ncu find_vec + dedup kernels (ab_encode sets the variants itself: 21 matching launches precede the dedup+find_vec variant)"; timeout 400 ncu --set full --clock-control none --import-source on \
     -k regex:'find_words_vec|dedup_words|encode_rep_words|copy_word_ids' -s 21 -c 4 -f -o gpurun_out/r02_prof_encode_dedup python tools/ab_encode.py 1000000 1 > /dev/null 2>&1; echo "rc=$?"
+echo "### ncu merge loop on the 100 MB training (RESIDENT): default and wide-probe"
+timeout 500 ncu --set full --clock-control none --import-source on -k regex:'^merge_loop_kernel' -s 1 -c 1 -f \
+    -o gpurun_out/r02_prof_merge_loop_resident python tools/probe_train.py zipf 32000 100e6 > /dev/null 2>&1; echo "rc=$?"
+YTTM_LOOP_WIDEPROBE=1 timeout 500 ncu --set full --clock-control none --import-source on -k regex:merge_loop_wide -s 1 -c 1 -f \
+    -o gpurun_out/r02_prof_merge_loop_resident_wide python tools/probe_train.py zipf 32000 100e6 > /dev/null 2>&1; echo "rc=$?"
 } > gpurun_out/r02_session1.log 2>&1
 tail -5 gpurun_out/r02_session1.log
