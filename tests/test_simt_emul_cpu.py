@@ -189,10 +189,14 @@ def test_encode_linear_product_id_is_refused_for_a_foreign_model(emu, oracle, mo
 def test_encode_chunked_pipeline(emu, oracle, monkeypatch):
     m = EG._model(oracle, _cases.dirty_zipf_text(), 1500)
     zc = _cases.zipf()
-    sents = zc.sentences(3000, 400, seed=21) + _cases.EDGE_SENTENCES
+    sents = zc.sentences(3000, 400, seed=21) + _cases.EDGE_SENTENCES + zc.sentences(3000, 400, seed=22) + zc.sentences(3000, 400, seed=23)
     want = oracle.encoder(m).encode(sents, bos=True, eos=True)
-    monkeypatch.setenv("YTTM_ENC_CHUNK_MB", "1")   # 1.2 MB of sentences: two chunks, both buffer sets
-    assert EG.GpuEncoder(m).encode(sents, bos=True, eos=True) == want
+    monkeypatch.setenv("YTTM_ENC_CHUNK_MB", "1")   # 3.6 MB of sentences: at least three chunks, both buffer sets reused
+    g = EG.GpuEncoder(m)
+    assert g.encode(sents, bos=True, eos=True) == want
+    # (the previous version used 1.2 MB: the "no tiny tail chunk" rule folded it into ONE chunk)
+    assert emu.yttm_stage_ms(emu.yttm_api_device_context(g.h), b"enc_chunks") >= 3
+    assert g.encode(sents, dropout=0.2, seed=77) == oracle.encoder(m).encode(sents, dropout=0.2, seed=77)
 
 
 def test_python_api_on_the_emulated_library(emu, tmp_path):

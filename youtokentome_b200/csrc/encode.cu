@@ -748,6 +748,13 @@ __global__ void __launch_bounds__(256) gather_ids_kernel(EncArgs a, const unsign
   }
 }
 
+// yttm_enc_run: a chunk's id offsets are chunk-local; the ids in front of the chunk are added on the device before the
+// offsets leave, so the host does no per-sentence work after the copies.
+__global__ void __launch_bounds__(256) add_base_kernel(unsigned long long *__restrict__ off, uint64_t n, unsigned long long base) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) off[i] += base;
+}
+
 }  // namespace
 
 struct yttm_enc {
@@ -1037,6 +1044,7 @@ int yttm_enc_run(yttm_enc *e, const char *bytes, const uint64_t *offsets, uint64
     cut.push_back(std::min<uint64_t>(hi, n_sent));
   }
   const size_t K = cut.size() - 1;
+  c->timers["enc_chunks"].ms = (float)K;  // yttm_stage_ms(ctx, "enc_chunks"): how many chunks the last call used
   auto h2d = [&](size_t i) -> int {  // enqueue the input copies of chunk i on the copy-in stream
     yttm_enc::Slot &sl = e->slot[i & 1];
     const uint64_t lo = cut[i], hi = cut[i + 1], nb = offsets[hi] - offsets[lo];
@@ -1051,7 +1059,6 @@ int yttm_enc_run(yttm_enc *e, const char *bytes, const uint64_t *offsets, uint64
   ytc::timer_begin(c, "e2e");
   if (h2d(0)) return 1;
   uint64_t base = 0;
-  std::vector<uint64_t> bases(K + 1, 0);
   int rc_small = 0;
   for (size_t i = 0; i < K; i++) {
     yttm_enc::Slot &sl = e->slot[i & 1];
@@ -1063,8 +1070,12 @@ int yttm_enc_run(yttm_enc *e, const char *bytes, const uint64_t *offsets, uint64
     if (enc_device(e, &sl, sl.d_bytes.as<uint8_t>(), sl.d_offs.as<uint64_t>(), nb, hi - lo, bos, eos, reverse, dropout,
                    seed, first_sentence_index + lo, &total))
       return 1;
+    if (base && hi > lo) {  // chunk-local offsets -> batch offsets
+      add_base_kernel<<<(unsigned)std::min<uint64_t>((hi - lo + 255) / 256, (uint64_t)c->n_sm * 4), 256, 0, c->stream>>>(
+          sl.out_off.as<unsigned long long>(), hi - lo, (unsigned long long)base);
+      c->launches++;
+    }
     YT_CUDA(c, cudaEventRecord(e->ev_done[i & 1], c->stream));
-    bases[i] = base;
     if (base + total > out_cap) rc_small = 2;
     if (!rc_small) {
       YT_CUDA(c, cudaStreamWaitEvent(e->s_out, e->ev_done[i & 1], 0));
@@ -1080,8 +1091,6 @@ int yttm_enc_run(yttm_enc *e, const char *bytes, const uint64_t *offsets, uint64
   ytc::timer_end(c, "e2e");
   *out_n = base;
   if (rc_small) { c->err = "yttm_enc_run: output buffer too small"; return 2; }
-  for (size_t i = 1; i < K; i++)  // chunk-local offsets -> batch offsets
-    for (uint64_t s2 = cut[i]; s2 < cut[i + 1]; s2++) out_offsets[s2] += bases[i];
   out_offsets[n_sent] = base;
   (void)total_bytes;
   return 0;
