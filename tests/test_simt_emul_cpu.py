@@ -197,6 +197,10 @@ def test_encode_chunked_pipeline(emu, oracle, monkeypatch):
     # (the previous version used 1.2 MB: the "no tiny tail chunk" rule folded it into ONE chunk)
     assert emu.yttm_stage_ms(emu.yttm_api_device_context(g.h), b"enc_chunks") >= 3
     assert g.encode(sents, dropout=0.2, seed=77) == oracle.encoder(m).encode(sents, dropout=0.2, seed=77)
+    monkeypatch.setenv("YTTM_ENC_CHUNK_MB", "2")
+    monkeypatch.setenv("YTTM_ENC_FIRST_CHUNK_MB", "1")   # A/B knob: a smaller first chunk (1 + 2 + rest)
+    assert g.encode(sents, bos=True, eos=True) == want
+    assert emu.yttm_stage_ms(emu.yttm_api_device_context(g.h), b"enc_chunks") == 2
 
 
 def test_python_api_on_the_emulated_library(emu, tmp_path):
