@@ -474,6 +474,24 @@ def main():
         else:
             ab = {"note": "skipped: the run had already taken %.0f s" % (time.time() - T_START)}
 
+    if ab is not None and "encode_stage_ms" in ab:
+        # e2e with a smaller FIRST chunk (host-only knob of yttm_enc_run, default kernels; DESIGN.md knob table): the
+        # copy-in of the first chunk overlaps nothing.  Same timed() as the line's e2e, after it, informational.
+        try:
+            e2e_ab = {}
+            for mb in ("8", "16", None):
+                if mb:
+                    os.environ["YTTM_ENC_FIRST_CHUNK_MB"] = mb
+                else:
+                    os.environ.pop("YTTM_ENC_FIRST_CHUNK_MB", None)
+                sec_x, _, _, _ = timed(step_host, args.steps, 2)
+                e2e_ab["first_chunk_%s_mb" % mb if mb else "default_again"] = n_sent * args.steps / sec_x / 1e6
+            ab["e2e_msent_per_s"] = e2e_ab
+        except Exception as e:
+            ab["e2e_msent_per_s"] = {"error": repr(e)}
+        finally:
+            os.environ.pop("YTTM_ENC_FIRST_CHUNK_MB", None)
+
     if rank == 0:
         out = {"metric": "encode throughput, 1M x 128 B synthetic sentences, vocab 32k", "value": value,
                "unit": "Msent/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
