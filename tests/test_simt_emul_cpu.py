@@ -453,3 +453,10 @@ def test_release_training_cache(emu, oracle):
     emu.yttm_api_release_training_cache()
     emu.yttm_api_release_training_cache()
     TG._same(oracle, text, vocab, cov)
+
+
+def test_graft_entry_smoke_on_the_emulator(emu, capsys):
+    """__graft_entry__.smoke() as the driver calls it on the GPU box, here with the emulated library in place."""
+    import __graft_entry__ as ge
+    ge.smoke()
+    assert "smoke ok" in capsys.readouterr().out
