@@ -202,6 +202,7 @@ def experimental_ab(model, budget_s=300.0):
                         ("max_load_50", {"YTTM_PAIR_MAX_LOAD_PCT": "50"}),
                         ("wide_probe+max_load_50", {"YTTM_LOOP_WIDEPROBE": "1", "YTTM_PAIR_MAX_LOAD_PCT": "50"}),
                         ("per_block_timers", {"YTTM_DBG": "8"}), ("wide_probe+per_block_timers", {"YTTM_LOOP_WIDEPROBE": "1", "YTTM_DBG": "8"}),
+                        ("pinned_h2d_8_threads", {"YTTM_TRAIN_PINNED_H2D": "8"}),
                         ("blocks_74", {"YTTM_LOOP_BLOCKS": "74"}), ("blocks_111", {"YTTM_LOOP_BLOCKS": "111"}),
                         ("threads_512", {"YTTM_LOOP_THREADS": "512"}), ("threads_256", {"YTTM_LOOP_THREADS": "256"})):
         if deadline - time.time() < 15:
@@ -214,7 +215,7 @@ def experimental_ab(model, budget_s=300.0):
             if r.returncode == 0 and last:
                 j = json.loads(last[-1])
                 loop[name] = {"us_per_merge": j["us_per_merge"], "merges": j["merges"], "table_slots": j["cap"], "launches": j["launches"],
-                              "phase_us_per_iter": j["phase_us_per_iter"]}
+                              "h2d_ms": j["front_ms"]["h2d"], "phase_us_per_iter": j["phase_us_per_iter"]}
             else:
                 loop[name] = {"error": "rc %d" % r.returncode}
         except subprocess.TimeoutExpired:

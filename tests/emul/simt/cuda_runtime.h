@@ -166,6 +166,9 @@ inline cudaError_t cudaMalloc(void **p, size_t n) {
 }
 template <class T> inline cudaError_t cudaMalloc(T **p, size_t n) { return cudaMalloc((void **)p, n); }
 inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+constexpr unsigned cudaHostAllocDefault = 0;   // "pinned" host memory is plain host memory here
+inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) {
   memmove(d, s, n);

@@ -460,3 +460,19 @@ def test_graft_entry_smoke_on_the_emulator(emu, capsys):
     import __graft_entry__ as ge
     ge.smoke()
     assert "smoke ok" in capsys.readouterr().out
+
+
+@pytest.mark.parametrize("threads,chunk_kb", [("1", "16"), ("3", "16"), ("8", "1"), ("4", "4096")])
+def test_train_staged_pinned_h2d(emu, oracle, monkeypatch, threads, chunk_kb):
+    """YTTM_TRAIN_PINNED_H2D (experimental, off by default): the corpus goes to the device through two pinned staging
+    buffers filled by `threads` host threads.  Chunk sizes of 1 / 16 KB make these small corpora span many chunks and
+    both buffers (slices per thread, the ragged last chunk, a chunk smaller than the thread count's slices)."""
+    monkeypatch.setenv("YTTM_TRAIN_PINNED_H2D", threads)
+    monkeypatch.setenv("YTTM_TRAIN_PINNED_CHUNK_KB", chunk_kb)
+    for seed in (0, 4):
+        text, vocab, cov, _ = _cases.stress_case(seed)
+        TG._same(oracle, text, vocab, cov)
+    TG._same(oracle, _cases.dirty_zipf_text(70_001), 600, 0.98)
+    text = _cases.zipf().text(33_333)
+    rules, _, _ = _abi_train(emu, text, 500)
+    assert rules == _oracle_rules(oracle, text, 500)

@@ -7,6 +7,8 @@ for t in 1024 512 256; do
   echo "== YTTM_LOOP_THREADS=$t"
   YTTM_LOOP_THREADS=$t python tools/probe_train.py "$C" "$V" "$B" 2>/dev/null | tail -1 | cut -c1-600
 done
+echo "== YTTM_TRAIN_PINNED_H2D=8 (corpus through two pinned staging buffers filled by 8 host threads; compare front_ms.h2d)"
+YTTM_TRAIN_PINNED_H2D=8 python tools/probe_train.py "$C" "$V" "$B" 2>/dev/null | tail -1 | cut -c1-600
 for b in 74 111; do
   echo "== YTTM_LOOP_BLOCKS=$b"
   YTTM_LOOP_BLOCKS=$b python tools/probe_train.py "$C" "$V" "$B" 2>/dev/null | tail -1 | cut -c1-600

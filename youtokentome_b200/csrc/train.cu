@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "common.cuh"
 
@@ -622,6 +623,45 @@ double yttm_stage_ms(const yttm_ctx *c, const char *stage) {
 }
 uint64_t yttm_launch_count(const yttm_ctx *c) { return c->launches; }
 
+// EXPERIMENTAL (env YTTM_TRAIN_PINNED_H2D=<host threads>, off by default until measured on a B200): the
+// corpus comes from PAGEABLE host memory, which cudaMemcpyAsync stages through the driver's own bounce buffer at
+// ~10 GB/s (9.4 ms for 100 MB measured, ~1 s for 10 GB).  Here `threads` host threads copy 32 MB slices into one of two
+// pinned staging buffers while the DMA engine drains the other one; an event per buffer guards its reuse.
+static int staged_h2d(yttm_ctx *c, uint8_t *dst, const char *src, uint64_t n, int threads) {
+  constexpr uint64_t CH_MAX = 32ull << 20;
+  uint64_t CH = CH_MAX;  // tests: YTTM_TRAIN_PINNED_CHUNK_KB makes small corpora span several chunks
+  if (const char *e = std::getenv("YTTM_TRAIN_PINNED_CHUNK_KB")) CH = std::min<uint64_t>(CH_MAX, (uint64_t)std::max(1, std::atoi(e)) << 10);
+  struct Stage { void *pin[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr}; };
+  static thread_local Stage st;  // kept for the life of the host thread, like the training context itself
+  for (int k = 0; k < 2; k++)
+    if (!st.pin[k]) {
+      YT_CUDA(c, cudaHostAlloc(&st.pin[k], CH_MAX, cudaHostAllocDefault));
+      YT_CUDA(c, cudaEventCreateWithFlags(&st.ev[k], cudaEventDisableTiming));
+    }
+  bool used[2] = {false, false};
+  int k = 0;
+  for (uint64_t off = 0; off < n; off += CH, k ^= 1) {
+    const uint64_t len = std::min<uint64_t>(CH, n - off);
+    if (used[k]) YT_CUDA(c, cudaEventSynchronize(st.ev[k]));  // the copy out of this buffer has finished
+    const uint64_t per = (len + (uint64_t)threads - 1) / (uint64_t)threads;
+    char *buf = static_cast<char *>(st.pin[k]);  // a local copy: `st` is thread_local, a worker would see its own (empty) one
+    const char *from = src + off;
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++) {
+      const uint64_t lo = std::min<uint64_t>(len, (uint64_t)t * per), hi = std::min<uint64_t>(len, lo + per);
+      if (hi > lo) pool.emplace_back([=]() { std::memcpy(buf + lo, from + lo, hi - lo); });
+    }
+    std::memcpy(buf, from, std::min<uint64_t>(len, per));
+    for (auto &th : pool) th.join();
+    YT_CUDA(c, cudaMemcpyAsync(dst + off, st.pin[k], len, cudaMemcpyHostToDevice, c->stream));
+    YT_CUDA(c, cudaEventRecord(st.ev[k], c->stream));
+    used[k] = true;
+  }
+  for (int j = 0; j < 2; j++)
+    if (used[j]) YT_CUDA(c, cudaEventSynchronize(st.ev[j]));  // the staging buffers are free again when we return
+  return 0;
+}
+
 int yttm_train_load_corpus(yttm_ctx *c, const char *bytes, uint64_t n, int on_device) {
   YT_CUDA(c, cudaSetDevice(c->device));
   if (n >= POS_MASK) YT_FAIL(c, "corpus shard too large (>= 2^40 bytes)");
@@ -637,7 +677,11 @@ int yttm_train_load_corpus(yttm_ctx *c, const char *bytes, uint64_t n, int on_de
   uint8_t *base = c->text_buf.as<uint8_t>();
   YT_CUDA(c, cudaMemsetAsync(base, ' ', 16, c->stream));
   YT_CUDA(c, cudaMemsetAsync(base + 16 + n, ' ', 32, c->stream));
-  if (n) YT_CUDA(c, cudaMemcpyAsync(base + 16, bytes, n, cudaMemcpyHostToDevice, c->stream));
+  int staged = 0;
+  if (const char *e = std::getenv("YTTM_TRAIN_PINNED_H2D")) staged = std::max(0, std::min(64, std::atoi(e)));
+  c->timers["h2d_variant"].ms = (float)staged;  // yttm_stage_ms(ctx, "h2d_variant")
+  if (n && staged) { if (staged_h2d(c, base + 16, bytes, n, staged)) return 1; }
+  else if (n) YT_CUDA(c, cudaMemcpyAsync(base + 16, bytes, n, cudaMemcpyHostToDevice, c->stream));
   ytc::timer_end(c, "h2d");
   c->d_text = base + 16;
   c->text_external = false;
