@@ -1,6 +1,7 @@
 #!/bin/bash
-# First GPU session of the next round, one gpurun call (≈ 12–15 GPU-minutes):
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_session_round2.sh'
+# First GPU session of the next round, one gpurun call (≈ 20–30 GPU-minutes with the sanitizer passes and the six ncu captures;
+# drop sections to fit the budget - every section is independent):
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/gpu_session_round2.sh'
 # 1. the GPU tests (incl. the reference's own stress test binary and the byte-identical model file test),
 # 2. A/B of the experimental encode kernels and of the merge-loop geometry,
 # 3. compute-sanitizer memcheck / racecheck / synccheck on a tiny workload,
