@@ -19,7 +19,7 @@ from youtokentome_b200 import synth  # noqa: E402
 KNOBS = ["YT_EMU_SMS", "YT_EMU_SCHED_SEED", "YTTM_FORCE_STREAM", "YTTM_STREAM_Q", "YTTM_STAGES", "YTTM_PAIR_CAP_FLOOR", "YTTM_DEFER_CAP",
          "YTTM_ENC_BUCKETED", "YTTM_ENC_FIND_CACHED", "YTTM_ENC_ZLIN", "YTTM_ENC_LONG", "YTTM_ENC_CHUNK_MB",
          "YTTM_ENC_DEDUP", "YTTM_ENC_DEDUP_SLOTS", "YTTM_ENC_DEDUP_WEAKTAG", "YTTM_ENC_FIND_VEC", "YTTM_LOOP_WIDEPROBE",
-         "YTTM_PAIR_MAX_LOAD_PCT"]
+         "YTTM_PAIR_MAX_LOAD_PCT", "YTTM_TRAIN_PINNED_H2D", "YTTM_TRAIN_PINNED_CHUNK_KB", "YTTM_LOOP_BLOCKS"]
 
 
 def sentences(rng, text):
@@ -129,6 +129,11 @@ def main():
             env["YTTM_LOOP_WIDEPROBE"] = "1"   # experimental merge loop: four table slots per round trip
         if rng.integers(0, 3) == 0:
             env["YTTM_PAIR_MAX_LOAD_PCT"] = str(int(rng.choice([30, 50, 90])))
+        if rng.integers(0, 3) == 0:   # corpus through the pinned staging buffers, tiny chunks
+            env["YTTM_TRAIN_PINNED_H2D"] = str(int(rng.integers(1, 6)))
+            env["YTTM_TRAIN_PINNED_CHUNK_KB"] = str(int(rng.choice([1, 2, 16])))
+        if rng.integers(0, 4) == 0:
+            env["YTTM_LOOP_BLOCKS"] = str(int(rng.integers(1, 4)))
         for k in KNOBS:
             os.environ.pop(k, None)
         os.environ.update(env)
