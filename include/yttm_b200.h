@@ -73,13 +73,44 @@ typedef struct yttm_train_stats {
  * + offsets + uint64 frequencies, initial pair->count table. */
 int yttm_train_build(yttm_ctx *ctx, yttm_train_stats *stats);
 
-/* Multi-GPU word exchange: export this rank's unique words (tokens, offsets[n_unique+1],
- * freq) to host buffers, or import a concatenation of all ranks' exports and rebuild the
- * pair table from it (duplicates across ranks are harmless: statistics are additive). */
+/* Multi-GPU word exchange (round 1, kept for callers that gather through the host): export this rank's unique
+ * words (tokens, offsets[n_unique+1], freq) to host buffers, or import a concatenation of all ranks' exports and
+ * rebuild the pair table from it (duplicates across ranks are harmless: statistics are additive). */
 int yttm_train_export_words(yttm_ctx *ctx, uint32_t *tokens, uint64_t tokens_cap, uint32_t *offsets,
                             uint64_t *freq, uint64_t words_cap, uint64_t *n_words, uint64_t *n_tokens);
 int yttm_train_import_words(yttm_ctx *ctx, const uint32_t *tokens, uint64_t n_tokens, const uint32_t *offsets,
                             const uint64_t *freq, uint64_t n_words, yttm_train_stats *stats);
+
+/* ---- multi-GPU training: one process (or host thread) per GPU, world <= 8 ------------------------------------
+ * Replaces the cooperation of the reference's training threads: the thread partition of the unique words
+ * (bpe.cpp:1066-1069), the merge of the per-thread word maps (:1029-1039) and the per-merge exchange of pair counts
+ * between workers and main (:789-804, :1099-1108, :1239-1266).  Protocol, every rank in lockstep:
+ *   yttm_train_dist_init(ctx, rank, world, handle)   allocate this rank's exchange buffer, get its 128-byte handle
+ *   <all-gather the handles, any transport>           (torch.distributed in youtokentome_b200/distributed.py)
+ *   yttm_train_dist_connect(ctx, handles)             map every peer's buffer (CUDA IPC; same process: peer access)
+ *   load_corpus(shard) / char_hist / <allreduce of the histogram> / set_alphabet      as on one GPU
+ *   yttm_train_dist_word_table                        word split + dedup of the shard
+ *   yttm_train_dist_export_words                      unique words grouped by owner rank = hash(bytes) % world
+ *   <all-to-all of the three device buffers>
+ *   yttm_train_dist_import_words                      dedup across ranks (equal words met on one rank), tokenise,
+ *                                                     pair table = sum over ranks (exchange rounds through the peers'
+ *                                                     buffers, no collective library involved)
+ *   yttm_train_run                                    the merge loop: every rank rewrites its own words and stores the
+ *                                                     count changes of a merge straight into every peer's exchange
+ *                                                     buffer over NVLink; every rank keeps the full table and elects
+ *                                                     the same pair.  All ranks return the same rules.
+ * A rank whose peer stays silent for YTTM_XQ_TIMEOUT_MS (default 30 000) aborts its kernel instead of hanging. */
+int yttm_train_dist_init(yttm_ctx *ctx, uint32_t rank, uint32_t world, void *handle_out /* 128 bytes */);
+int yttm_train_dist_connect(yttm_ctx *ctx, const void *handles /* world x 128 bytes, by rank */);
+int yttm_train_dist_word_table(yttm_ctx *ctx, uint64_t *n_unique);
+/* bytes_per_dst / words_per_dst: world entries each.  *d_bytes: the words of destination 0, 1, ... back to back, each
+ * followed by one space; *d_pos (uint64 per word): its first byte relative to its destination's first byte;
+ * *d_freq (uint64 per word): its count.  Device memory owned by the context, valid until the next call on it. */
+int yttm_train_dist_export_words(yttm_ctx *ctx, uint64_t *bytes_per_dst, uint64_t *words_per_dst, void **d_bytes,
+                                 void **d_pos, void **d_freq);
+/* the same three buffers after the all-to-all (DEVICE pointers, sources back to back) + the per-source sizes */
+int yttm_train_dist_import_words(yttm_ctx *ctx, const void *d_bytes, const uint64_t *bytes_per_src, const void *d_pos,
+                                 const void *d_freq, const uint64_t *words_per_src, yttm_train_stats *stats);
 
 /* Phase 4 — the merge loop (main bpe.cpp:1121-1282 + worker_doing_merge :601-811): up to
  * max_merges iterations of { argmax under MergeCandidate::operator< (bpe.cpp:110-126); apply

@@ -99,6 +99,17 @@ inline unsigned __ballot_sync(unsigned, int pred) {
 }
 inline void __syncwarp(unsigned = 0xffffffffu) { uint32_t live; emu::warp_gather(0, &live); }
 inline void __syncthreads() { emu::block_sync(); }
+inline int __syncthreads_or(int pred) {  // three rendezvous: previous readers are gone, the flag is cleared, all have voted
+  static thread_local int acc;
+  emu::block_sync();
+  acc = 0;
+  emu::block_sync();
+  if (pred) acc = 1;
+  emu::block_sync();
+  return acc;
+}
+inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
@@ -112,6 +123,10 @@ inline unsigned __fns(unsigned mask, unsigned base, int offset) {  // offset-th 
 }
 template <class T> inline T __ldg(const T *p) { return *p; }
 template <class T> inline T __ldcg(const T *p) { return *(const volatile T *)p; }
+inline uint4 __ldcg(const uint4 *p) {
+  const volatile uint32_t *q = reinterpret_cast<const volatile uint32_t *>(p);
+  return uint4{q[0], q[1], q[2], q[3]};
+}
 
 template <class T, class U> inline T atomicAdd(T *p, U v) { return __atomic_fetch_add(p, (T)v, __ATOMIC_SEQ_CST); }
 template <class T, class U> inline T atomicOr(T *p, U v) { return __atomic_fetch_or(p, (T)v, __ATOMIC_SEQ_CST); }
@@ -140,7 +155,13 @@ template <class A, class B> inline typename std::common_type<A, B>::type max(A a
 
 // ---- runtime API: one synchronous "device" whose memory is host memory ------------------------------
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2 };
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorPeerAccessAlreadyEnabled = 704 };
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { memset(h, 0, sizeof(*h)); memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof(*p)); return cudaSuccess; }
+inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice,
                       cudaMemcpyDefault };
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };

@@ -254,6 +254,7 @@ def test_train_table_rebuilds_on_a_tiny_pair_table(emu, oracle, monkeypatch):
     """YTTM_PAIR_CAP_FLOOR=16: the table starts at load 3/8 of a few dozen slots, so the loop stops again and
     again for a rebuild (stop = 2 / probe overflow) — the relaunch path, with the tokens as the only truth."""
     monkeypatch.setenv("YTTM_PAIR_CAP_FLOOR", "16")
+    monkeypatch.setenv("YTTM_PAIR_MAX_LOAD_PCT", "70")   # accept at 35 %, leave at 70 %: the 4096-slot table is rebuilt on the way
     text = _cases.zipf().text(20_000)
     rules, launches, _ = _abi_train(emu, text, 700)
     assert launches >= 2
@@ -385,13 +386,16 @@ def test_encode_find_vec_variant(emu, oracle, monkeypatch):
         assert _bind._unpack(ids, oo) == want, shift
 
 
-@pytest.mark.parametrize("floor", [None, "16", "64"])
-def test_train_wide_probe_variant(emu, oracle, monkeypatch, floor):
-    """YTTM_LOOP_WIDEPROBE (experimental, off by default): the merge loop whose table updates fetch four slots (one
-    32-byte sector of the key array) per round trip.  Same rules as the oracle on stress seeds, dirty Unicode, runs,
-    RESIDENT and STREAMING tiles; with pair-table floors of 16 / 64 slots the table lives at high load, probe chains run
-    across many groups of four, wrap around the end of the table, overflow (probe limit) and are rebuilt again and again."""
-    monkeypatch.setenv("YTTM_LOOP_WIDEPROBE", "1")
+@pytest.mark.parametrize("floor,seg", [(None, None), ("16", "4"), (None, "16"), ("64", None)])
+def test_train_exchange_segments(emu, oracle, monkeypatch, floor, seg):
+    """The owner-computes merge loop (round 2): count changes travel through per-block exchange segments and are applied
+    by the block that owns the key's table partition.  YTTM_XQ_SEG_CAP = 4 / 16 entries makes segments overflow on almost
+    every early merge (the merge is still applied to the words and the table is rebuilt from them); pair-table floors of
+    16 / 64 slots keep the partitions tiny (16 slots each), so that they fill up, the loop leaves for a larger table and
+    probe chains wrap around the end of a partition.  Same rules as the oracle on stress seeds, dirty Unicode, runs,
+    RESIDENT and STREAMING tiles."""
+    if seg:
+        monkeypatch.setenv("YTTM_XQ_SEG_CAP", seg)
     if floor:
         monkeypatch.setenv("YTTM_PAIR_CAP_FLOOR", floor)
     for seed in range(8):
@@ -401,7 +405,7 @@ def test_train_wide_probe_variant(emu, oracle, monkeypatch, floor):
     TG._same(oracle, b"a" * 500 + b" " + b"ab" * 300 + b" aaa aaaa aaaaa " + b"b" * 1001, 40)
     text = _cases.zipf().text(20_000)
     rules, launches, _ = _abi_train(emu, text, 700)
-    assert _LAST["loop_variant"] == 1.0 and (launches >= 2 or not floor)
+    assert launches >= 2 or not seg
     assert rules == _oracle_rules(oracle, text, 700)
     monkeypatch.setenv("YTTM_FORCE_STREAM", "1")
     monkeypatch.setenv("YTTM_STREAM_Q", "128")
@@ -414,7 +418,7 @@ def test_train_wide_probe_variant(emu, oracle, monkeypatch, floor):
 
 @pytest.mark.parametrize("pct", ["30", "50", "90"])
 def test_train_pair_table_load_knob(emu, oracle, monkeypatch, pct):
-    """YTTM_PAIR_MAX_LOAD_PCT (A/B knob, default 75): the load factor at which the loop leaves for a rebuild (a rebuilt
+    """YTTM_PAIR_MAX_LOAD_PCT (A/B knob, default 50): the load factor at which the loop leaves for a rebuild (a rebuilt
     table is accepted at half of it) changes table sizes and rebuild points, never the rules."""
     monkeypatch.setenv("YTTM_PAIR_MAX_LOAD_PCT", pct)
     monkeypatch.setenv("YTTM_PAIR_CAP_FLOOR", "32")
@@ -424,9 +428,6 @@ def test_train_pair_table_load_knob(emu, oracle, monkeypatch, pct):
     text = _cases.zipf().text(20_000)
     rules, launches, _ = _abi_train(emu, text, 700)
     assert rules == _oracle_rules(oracle, text, 700)   # (at 30 % the first table is large enough for the whole run)
-    monkeypatch.setenv("YTTM_LOOP_WIDEPROBE", "1")
-    rules, _, _ = _abi_train(emu, text, 700)
-    assert _LAST["loop_variant"] == 1.0 and rules == _oracle_rules(oracle, text, 700)
 
 
 @pytest.mark.parametrize("blocks", ["1", "2", "3"])

@@ -40,10 +40,14 @@ struct YtLoopCtl {
   uint32_t overflow;          // a probe sequence wrapped (fatal)
   unsigned long long dead;    // token slots tombstoned since the last compaction
   unsigned long long slots;   // token slots at the last compaction
-  unsigned long long t_phase[8];  // ns spent by block 0 in: arg-max sweep, barrier 1, apply scan, barrier 2;
-                                  // with YTTM_DBG&8 also, over ALL blocks: [4] max apply, [5] mean apply, [6] max apply before the table drain
-  unsigned long long blk[2][3];   // per-iteration scratch of [4..6] (double-buffered by iteration parity)
+  unsigned long long t_phase[8];  // ns spent by block 0 in: [0] drain, [1] arg-max of its partition, [2] barrier 1, [3] apply, [4] barrier 2;
+                                  // with YTTM_DBG&8 also, over ALL blocks: [5] max apply, [6] mean apply, [7] max drain
+  unsigned long long blk[2][3];   // per-iteration scratch of [5..7] (double-buffered by iteration parity)
   unsigned long long iters;       // iterations those times cover
+  uint32_t xq_round;              // exchange rounds completed (same on every rank of the job)
+  uint32_t stop_why;              // stop == 2: 1 partition nearly full, 2 exchange segment overflowed, 4 partition full, 8 load factor
+  uint32_t xq_flags;              // flags of the peers' last out-of-loop round (xq_absorb_kernel)
+  uint32_t max_part_occ;          // part_occ_kernel: fullest partition of the table
 };
 
 struct yttm_ctx {
@@ -79,9 +83,18 @@ struct yttm_ctx {
   uint64_t n_words = 0;  // entries of off minus one
   uint64_t n_slots = 0;  // token slots
 
-  // ---- pair table
+  // ---- pair table: p_nparts partitions of p_rmask + 1 slots (pcap = their product)
   ytc::DevBuf pkey, pcnt, scratch_key, scratch_cnt;
   uint64_t pcap = 0;
+  uint32_t p_rmask = 0, p_nparts = 0;
+
+  // ---- exchange buffer of the merge loop (merge_loop.cuh); world > 1: peers[] are the other ranks' regions
+  ytc::DevBuf xq_buf, xq_arrive;
+  uint32_t xq_world = 1, xq_me = 0, xq_seg_cap = 0, xq_nblocks = 0;
+  uint64_t xq_per_sender = 0, xq_bytes = 0;
+  void *xq_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool xq_peer_ipc[8] = {false, false, false, false, false, false, false, false};
+  bool xq_connected = false;
 
   // ---- merge loop
   ytc::DevBuf ctl, blockbest, d_rules, d_rfreq, tiles, defer;

@@ -1,23 +1,98 @@
 // merge_loop.cuh — phase 4 of training: the persistent merge loop (included by train.cu).
 //
 // Replaces the reference's main loop + worker_doing_merge + PriorityQueue
-// (bpe.cpp:1121-1282, 601-811, 149-314).  One cooperative kernel runs every merge iteration on
-// the device; per iteration:
-//   1. exact arg-max over the pair table under MergeCandidate::operator< (bpe.cpp:110-126)
-//   2. grid barrier; every block reduces the per-block winners redundantly (no second barrier)
-//   3. apply x y -> z: the packed words are organised in TILES (windows of `tile_tok` token
-//      slots, cut at word boundaries).  RESIDENT mode: block b keeps tile b in shared memory for
-//      the whole launch (the working set of deduplicated words fits the 148 x 227 KB of SMEM:
-//      no HBM/L2 token traffic inside the loop at all).  STREAMING mode (token buffer larger than
-//      the SMEM of the chip): tiles are staged into shared memory each iteration, coalesced,
-//      and modified words are written through to HBM.
-//      Inside a tile a lane tests one word (has_pair); words that hold the pair are rewritten by
-//      the whole warp in parallel (ballot/popc compaction, run-parity rule for x == y) and their
-//      pair multiset is re-counted (-old, +new) with one table update per lane.
-//   4. grid barrier.
+// (bpe.cpp:1121-1282, 601-811, 149-314) and, across GPUs, the per-merge count exchange between
+// its worker threads (check_cnt :1099-1108, workers reporting the pairs of the new token :789-804,
+// main gathering them :1239-1266).  One cooperative kernel per GPU runs every merge iteration on
+// the device.  Design (round 2, "owner computes"):
+//   * the pair table is cut into one PARTITION per block (PairTab::nparts == gridDim.x); block b
+//     is the only one that ever reads or writes partition b inside the loop;
+//   * a block never touches the table while it rewrites words: the count changes of a merge
+//     (key, +-delta) are appended to the block's own SEGMENT of an exchange buffer (plain
+//     stores, no atomics, no dependent L2 round trips in the apply phase);
+//   * the same segment is written, with the same stores, into the exchange buffer of every
+//     other GPU of the job over NVLink (peer pointers, Xq::base[]) — the exchange step of the
+//     multi-GPU merge loop is fused into the kernel, there is no NCCL call per merge;
+//   * after the grid barrier that ends the apply phase every block drains ALL segments of ALL
+//     GPUs, keeps the entries whose key it owns, applies them to its partition and then finds
+//     the best pair of its partition (exact arg-max under MergeCandidate::operator<,
+//     bpe.cpp:110-126); every GPU holds the full table, so every GPU elects the same pair
+//     without a second exchange;
+//   * a second grid barrier publishes the per-block winners; every block reduces them
+//     redundantly.
+// Per merge: two grid barriers (as before), but the table updates of merge k are applied by
+// their owners in parallel instead of by the block that happens to rewrite the word, and the
+// arg-max of a block covers cap/gridDim slots that only it has modified.
+// Words live in TILES: RESIDENT mode keeps tile b in the shared memory of block b for the whole
+// launch; STREAMING mode (token buffer larger than the chip's shared memory) stages tiles through
+// a TMA ring every merge (see below).
 #pragma once
 
 constexpr int SWEEP_UNROLL = 8;  // arg-max sweep: table counts in flight per thread
+
+// ---- exchange buffer ("xq") --------------------------------------------------------------------
+// Every rank owns one region: [parity 0/1][sender 0..world-1]{ XqHdr, entries[nblocks][seg_cap] }.
+// Round r (r = 1, 2, ...) uses parity r & 1.  A sender writes its entries and per-block counts
+// into slot [r & 1][me] of EVERY rank's region (its own included), then — after a grid barrier
+// and a system-scope fence — the word seq_flags = (r << 8) | flags of the remote copies.
+// Double buffering suffices: a sender can start round r + 2 only after it has drained round
+// r + 1 of every peer, which those peers publish after they have finished draining round r.
+constexpr int XQ_MAX_WORLD = 8;
+constexpr int XQ_MAX_BLOCKS = 256;
+constexpr uint32_t XQF_COMPACT = 1u;    // sender wants a compaction of its packed words (rank-local state)
+constexpr uint32_t XQF_OVERFLOW = 2u;   // a segment of the sender overflowed: counts are stale, rebuild the table
+constexpr uint32_t XQF_MORE = 4u;       // out-of-loop table rounds: the sender has more chunks to publish
+constexpr uint32_t XQ_CNT_OVF = 0x80000000u;   // count word: the segment overflowed
+constexpr uint32_t XQ_CNT_MORE = 0x40000000u;  // count word (table rounds): further entries follow in the next round
+constexpr uint32_t XQ_CNT_MASK = 0x3fffffffu;
+struct XqHdr {
+  unsigned long long seq_flags;       // written LAST by the sender (remote copies only)
+  unsigned long long pad;
+  uint32_t counts[XQ_MAX_BLOCKS];     // entries of the sender's segment b (bit 31: it overflowed)
+};
+struct Xq {
+  unsigned char *base[XQ_MAX_WORLD];  // region of every rank; base[me] is local memory
+  uint32_t world, me, nblocks, seg_cap;
+  unsigned long long per_sender;      // bytes of one {header, entries} slot
+};
+__device__ __forceinline__ unsigned char *xq_base(const Xq &x, uint32_t rank) {
+  unsigned char *p = x.base[0];
+#pragma unroll
+  for (int d = 1; d < XQ_MAX_WORLD; d++)
+    if ((uint32_t)d == rank) p = x.base[d];
+  return p;
+}
+__device__ __forceinline__ XqHdr *xq_hdr(const Xq &x, uint32_t rank, uint32_t parity, uint32_t sender) {
+  return reinterpret_cast<XqHdr *>(xq_base(x, rank) + (size_t)(parity * x.world + sender) * x.per_sender);
+}
+// byte offset (inside any rank's region) of segment `block` of (parity, sender)
+__device__ __forceinline__ size_t xq_seg_off(const Xq &x, uint32_t parity, uint32_t sender, uint32_t block) {
+  return (size_t)(parity * x.world + sender) * x.per_sender + sizeof(XqHdr) + (size_t)block * x.seg_cap * sizeof(uint4);
+}
+// system-scope release store / acquire load of a flag word in (possibly peer) global memory
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+#ifndef YT_SIMT_EMU
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#else
+  __atomic_store_n(p, v, __ATOMIC_RELEASE);
+#endif
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+#ifndef YT_SIMT_EMU
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+#else
+  return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+#endif
+}
+__device__ __forceinline__ void fence_sys() {
+#ifndef YT_SIMT_EMU
+  __threadfence_system();
+#else
+  __atomic_thread_fence(__ATOMIC_SEQ_CST);
+#endif
+}
 
 struct LoopArgs {
   uint32_t *tok;
@@ -25,25 +100,27 @@ struct LoopArgs {
   const uint64_t *freq;
   uint64_t n_words;
   const uint2 *tile_desc;      // n_tiles + 1 entries (first word, its token offset); last = (n_words, n_slots)
-  uint32_t stream_tok_cap;     // STREAMING: token / word capacity of ONE of the two pipeline stages
+  uint32_t stream_tok_cap;     // STREAMING: token / word capacity of ONE pipeline stage
   uint32_t stream_word_cap;
   uint32_t n_stage;            // STREAMING: pipeline depth
-  uint32_t dbg;                // diagnostics (env YTTM_DBG): 1 = consumers skip the scan, 2 = scalar scan, 8 = per-block apply timers
+  uint32_t dbg;                // diagnostics (env YTTM_DBG): 1 = consumers skip the scan, 2 = scalar scan, 8 = per-block timers
   uint4 *defer;                // STREAMING: per-block lists of words to rewrite after the tile scan
   uint32_t defer_cap;          // entries per block
   uint32_t n_tiles;
   uint32_t resident;           // 1: block b owns tile b and keeps it in shared memory
   uint32_t smem_tok_cap;       // token capacity of the shared tile buffer
   uint32_t smem_word_cap;      // word capacity of the shared tile buffer
-  PairTab tab;
+  PairTab tab;                 // tab.nparts == gridDim.x
+  Xq xq;
   YtLoopCtl *ctl;
-  unsigned long long *blockbest;  // 4 per block: count, prio, slot, (pad)
+  unsigned long long *blockbest;  // 4 per block: count, prio, slot, flags
   uint32_t *rules;                // 3 per merge
   unsigned long long *rfreq;
   uint32_t first_new_id;          // id of merge number 0
   uint32_t max_total;             // stop when ctl->n_done reaches this
   uint32_t max_iters;             // iterations allowed in this launch
   uint32_t key_limit;             // leave for a rebuild above this table occupancy
+  unsigned long long spin_limit_ns;  // a peer that stays silent this long traps the kernel (never hang the box)
 };
 
 struct Best { unsigned long long c, prio, slot; };
@@ -56,12 +133,14 @@ __device__ __forceinline__ unsigned long long gtimer() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+__device__ __forceinline__ void loop_trap() { asm volatile("trap;"); }
 #else   // tests/emul/simt: the CPU clock
 inline unsigned long long gtimer() {
   timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);
   return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
 }
+inline void loop_trap() { fprintf(stderr, "emu: merge loop gave up waiting for a peer\n"); abort(); }
 #endif
 __device__ __forceinline__ Best warp_best(Best v) {
   for (int o = 16; o > 0; o >>= 1) {
@@ -76,39 +155,35 @@ __device__ __forceinline__ Best warp_best(Best v) {
 
 struct MergeOp { uint32_t x, y, z; unsigned long long key; };
 
-// Per-warp queue of pending table updates in shared memory: the updates of several rewritten
-// words are issued together, one per lane, so their L2 round trips overlap.
-constexpr int UQ_CAP = 64;
 constexpr int MAX_STAGES = 16;
 constexpr int CLAIM_WORDS = 1024;  // claim bitmap: up to 32768 words per shared-memory tile
-struct WarpQueue {
-  unsigned long long *key;  // UQ_CAP entries of this warp
-  long long *delta;
-  uint32_t n;               // warp-uniform
+
+// This block's outgoing segment of the current round: the same offset in every rank's region.
+struct XqOut {
+  size_t off;        // byte offset of the segment inside a region
+  uint32_t *s_n;     // shared-memory entry counter of the block (may run past cap: overflow)
 };
-template <class Tab>
-__device__ __forceinline__ void uq_drain(WarpQueue &q, unsigned lane, const Tab &tab) {
-  __syncwarp();
-  for (uint32_t i = lane; i < q.n; i += 32) {
-    const long long d = q.delta[i];
-    if (d > 0) pair_add<true>(tab, q.key[i], d);  // additions are mostly pairs with the new token: CAS first
-    else pair_add<false>(tab, q.key[i], d);
-  }
-  __syncwarp();
-  q.n = 0;
+__device__ __forceinline__ void xq_store(const LoopArgs &a, const XqOut &o, uint32_t i, unsigned long long key,
+                                         long long delta) {
+  if (i >= a.xq.seg_cap) return;  // overflow: the count word carries the flag, the host rebuilds the table
+  const uint4 e = make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)delta, (uint32_t)((unsigned long long)delta >> 32));
+#pragma unroll
+  for (int d = 0; d < XQ_MAX_WORLD; d++)
+    if ((uint32_t)d < a.xq.world) reinterpret_cast<uint4 *>(a.xq.base[d] + o.off)[i] = e;
 }
-// every lane may contribute one update (has == true); direct == true bypasses the queue
-template <class Tab>
-__device__ __forceinline__ void uq_push(WarpQueue &q, bool direct, bool has, unsigned long long key, long long delta,
-                                        unsigned lane, const Tab &tab) {
-  if (direct) { if (has) pair_add(tab, key, delta); return; }
+// every lane of a warp may contribute one update (has == true)
+__device__ __forceinline__ void xq_push(const LoopArgs &a, const XqOut &o, bool has, unsigned long long key,
+                                        long long delta, unsigned lane) {
   const unsigned m = __ballot_sync(0xffffffffu, has);
-  if (has) {
-    const uint32_t i = q.n + __popc(m & ((1u << lane) - 1u));
-    q.key[i] = key;
-    q.delta[i] = delta;
-  }
-  q.n += __popc(m);
+  if (!m) return;
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(o.s_n, (uint32_t)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (has) xq_store(a, o, base + __popc(m & ((1u << lane) - 1u)), key, delta);
+}
+// one thread on its own (scalar paths)
+__device__ __forceinline__ void xq_push1(const LoopArgs &a, const XqOut &o, unsigned long long key, long long delta) {
+  xq_store(a, o, atomicAdd(o.s_n, 1u), key, delta);
 }
 
 // Run structure of <= 32 live tokens held one per lane (t == DEAD beyond the n live ones): every
@@ -128,21 +203,20 @@ __device__ __forceinline__ RunInfo warp_runs(uint32_t t, uint32_t n, unsigned la
 }
 
 // One warp rewrites one word that holds (x,y): st = its `cap` token slots (shared or global
-// memory), gt = optional write-through copy in global memory.  Table updates: only the pairs
-// whose run is touched by a merge are sent (-old, +new); untouched runs cancel exactly.
+// memory), gt = optional write-through copy in global memory.  Count changes: only the pairs
+// whose run is touched by a merge are emitted (-old, +new); untouched runs cancel exactly.
 // Returns the number of merges.
-template <class Tab>
 __device__ __forceinline__ uint32_t warp_apply_word(uint32_t *st, uint32_t cap, uint32_t *gt, long long f,
-                                                    const MergeOp &op, unsigned lane, const Tab &tab,
-                                                    WarpQueue &q) {
+                                                    const MergeOp &op, unsigned lane, const LoopArgs &a,
+                                                    const XqOut &xo) {
   if (cap > 32) {  // long word: scalar path on lane 0 (exact, slow)
     uint32_t merges = 0;
     if (lane == 0) {
       for_each_pair(st, cap, [&](uint64_t key, uint64_t mult) {
-        if (key != op.key) pair_add(tab, key, -(long long)mult * f);
+        if (key != op.key) xq_push1(a, xo, key, -(long long)mult * f);
       });
       merges = rewrite_word(st, cap, op.x, op.y, op.z);
-      for_each_pair(st, cap, [&](uint64_t key, uint64_t mult) { pair_add(tab, key, (long long)mult * f); });
+      for_each_pair(st, cap, [&](uint64_t key, uint64_t mult) { xq_push1(a, xo, key, (long long)mult * f); });
     }
     __syncwarp();
     if (gt)
@@ -187,14 +261,10 @@ __device__ __forceinline__ uint32_t warp_apply_word(uint32_t *st, uint32_t cap, 
   const bool h1 = old_changed && ro.nxt < n && pair_key(t, ro.b) != op.key;
   const bool h2 = new_changed && rn.L >= 2;
   const bool h3 = new_changed && rn.nxt < n2;
-  const uint32_t total = __popc(__ballot_sync(0xffffffffu, h0)) + __popc(__ballot_sync(0xffffffffu, h1)) +
-                         __popc(__ballot_sync(0xffffffffu, h2)) + __popc(__ballot_sync(0xffffffffu, h3));
-  const bool direct = total > UQ_CAP;
-  if (!direct && q.n + total > UQ_CAP) uq_drain(q, lane, tab);
-  uq_push(q, direct, h0, pair_key(t, t), -f * (long long)(ro.L >> 1), lane, tab);
-  uq_push(q, direct, h1, pair_key(t, ro.b), -f, lane, tab);
-  uq_push(q, direct, h2, pair_key(t2, t2), f * (long long)(rn.L >> 1), lane, tab);
-  uq_push(q, direct, h3, pair_key(t2, rn.b), f, lane, tab);
+  xq_push(a, xo, h0, pair_key(t, t), -f * (long long)(ro.L >> 1), lane);
+  xq_push(a, xo, h1, pair_key(t, ro.b), -f, lane);
+  xq_push(a, xo, h2, pair_key(t2, t2), f * (long long)(rn.L >> 1), lane);
+  xq_push(a, xo, h3, pair_key(t2, rn.b), f, lane);
   return n - n2;
 }
 
@@ -206,10 +276,9 @@ __device__ __forceinline__ uint32_t warp_apply_word(uint32_t *st, uint32_t cap, 
 // the second element of an in-word pair — is never a word-initial token; tail padding (DEAD)
 // matches nothing.  Each hit is mapped to its word (binary search in the offsets), the word is
 // claimed once through a bitmap, and claimed words are rewritten by the whole warp.
-template <class Tab>
 __device__ __forceinline__ unsigned long long process_tile(uint32_t *stok, const uint32_t *soff, uint32_t nw,
                                                            uint32_t span, uint32_t *claim, const uint64_t *gfreq,
-                                                           const MergeOp &op, const Tab &tab, WarpQueue &q) {
+                                                           const MergeOp &op, const LoopArgs &a, const XqOut &xo) {
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   unsigned long long dead = 0;
   // a lane compares four tokens from one 16-byte shared load (stok is 16-byte aligned, its capacity a
@@ -250,19 +319,18 @@ __device__ __forceinline__ unsigned long long process_tile(uint32_t *stok, const
         const uint32_t oj = __shfl_sync(0xffffffffu, o, j), cj = __shfl_sync(0xffffffffu, cap, j);
         const uint32_t wj = __shfl_sync(0xffffffffu, w, j);
         const long long f = __shfl_sync(0xffffffffu, fw, j);
-        dead += warp_apply_word(stok + oj, cj, nullptr, f, op, lane, tab, q);
+        dead += warp_apply_word(stok + oj, cj, nullptr, f, op, lane, a, xo);
         if (lane == 0) atomicAnd(&claim[wj >> 5], ~(1u << (wj & 31)));  // bitmap all zero between tiles
       }
     }
   }
-  return lane == 0 ? dead : 0ull;  // pending table updates stay queued (drained by the caller)
+  return lane == 0 ? dead : 0ull;
 }
 
 // Oversized tile (a word longer than the shared buffer): thread per word straight on global memory.
-template <class Tab>
 __device__ __forceinline__ unsigned long long process_tile_direct(uint32_t *tok, const uint32_t *off,
                                                                   const uint64_t *freq, uint32_t w0, uint32_t w1,
-                                                                  const MergeOp &op, const Tab &tab) {
+                                                                  const MergeOp &op, const LoopArgs &a, const XqOut &xo) {
   unsigned long long dead = 0;
   for (uint32_t w = w0 + threadIdx.x; w < w1; w += blockDim.x) {
     uint32_t o = off[w], wcap = off[w + 1] - o;
@@ -270,10 +338,10 @@ __device__ __forceinline__ unsigned long long process_tile_direct(uint32_t *tok,
     if (!has_pair(t, wcap, op.x, op.y)) continue;
     long long f = (long long)freq[w];
     for_each_pair(t, wcap, [&](uint64_t key, uint64_t mult) {
-      if (key != op.key) pair_add(tab, key, -(long long)mult * f);
+      if (key != op.key) xq_push1(a, xo, key, -(long long)mult * f);
     });
     dead += rewrite_word(t, wcap, op.x, op.y, op.z);
-    for_each_pair(t, wcap, [&](uint64_t key, uint64_t mult) { pair_add(tab, key, (long long)mult * f); });
+    for_each_pair(t, wcap, [&](uint64_t key, uint64_t mult) { xq_push1(a, xo, key, (long long)mult * f); });
   }
   return dead;
 }
@@ -362,20 +430,114 @@ extern __shared__ __align__(16) uint32_t yt_dyn_smem[];
 #define yt_dyn_smem (reinterpret_cast<uint32_t *>(emu::dyn_smem()))
 #endif
 
-template <bool WIDE>
+// Wait until every OTHER rank has published round `round` into this rank's region; returns the
+// OR of their flags.  One thread per peer polls local memory (the peers wrote it over NVLink).
+__device__ __forceinline__ uint32_t xq_wait_peers(const LoopArgs &a, uint32_t round) {
+  uint32_t flags = 0;
+  if (threadIdx.x < a.xq.world && threadIdx.x != a.xq.me) {
+    const XqHdr *h = xq_hdr(a.xq, a.xq.me, round & 1u, threadIdx.x);
+    const unsigned long long t0 = gtimer();
+    for (uint32_t spin = 0;; spin++) {
+      const unsigned long long v = ld_acquire_sys(&h->seq_flags);
+      if ((uint32_t)(v >> 8) == round) { flags = (uint32_t)v & 0xffu; break; }
+#ifdef YT_SIMT_EMU
+      emu::yield();
+#endif
+      if ((spin & 1023u) == 1023u && gtimer() - t0 > a.spin_limit_ns) loop_trap();
+    }
+  }
+  return flags;
+}
+
+// Drain round `round`: every entry of every sender's segments whose key belongs to partition
+// blockIdx.x is applied to that partition.  s_pref: world * nblocks + 1 words of shared memory.
+// Returns (block-uniform) bit 0: a segment overflowed, bit 1: a sender announced more chunks; *s_occ_add is increased by the keys this call inserted.
+__device__ __forceinline__ uint32_t xq_drain(const LoopArgs &a, uint32_t round, bool skip_self, uint32_t *s_pref,
+                                             uint32_t *s_scan /* 33 words */, uint32_t *s_occ_add) {
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const uint32_t nseg = a.xq.world * a.xq.nblocks, parity = round & 1u;
+  // ---- segment sizes -> exclusive prefix in shared memory (items per thread: ceil(nseg / blockDim))
+  const uint32_t ipt = (nseg + blockDim.x - 1) / blockDim.x;
+  uint32_t mine = 0, ovf = 0;
+  for (uint32_t k = 0; k < ipt; k++) {
+    const uint32_t j = threadIdx.x * ipt + k;
+    if (j < nseg) {
+      const uint32_t s = j / a.xq.nblocks, b = j - s * a.xq.nblocks;
+      uint32_t c = __ldcg(&xq_hdr(a.xq, a.xq.me, parity, s)->counts[b]);
+      if (c & XQ_CNT_OVF) ovf |= 1u;
+      if (c & XQ_CNT_MORE) ovf |= 2u;
+      c &= XQ_CNT_MASK;
+      if (skip_self && s == a.xq.me) c = 0;
+      mine += c < a.xq.seg_cap ? c : a.xq.seg_cap;
+    }
+  }
+  uint32_t x = mine;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= (unsigned)o) x += y;
+  }
+  if (lane == 31) s_scan[wid] = x;
+  ovf = (__syncthreads_or((int)(ovf & 1u)) ? 1u : 0u) | (__syncthreads_or((int)(ovf & 2u)) ? 2u : 0u);
+  if (wid == 0) {
+    const uint32_t v = lane < nwarp ? s_scan[lane] : 0u;
+    uint32_t xs = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, xs, o);
+      if (lane >= (unsigned)o) xs += y;
+    }
+    s_scan[lane] = xs - v;
+    if (lane == 31) s_scan[32] = xs;
+  }
+  __syncthreads();
+  {
+    uint32_t run = s_scan[wid] + x - mine;  // exclusive prefix of this thread's first item
+    for (uint32_t k = 0; k < ipt; k++) {
+      const uint32_t j = threadIdx.x * ipt + k;
+      if (j < nseg) {
+        const uint32_t s = j / a.xq.nblocks, b = j - s * a.xq.nblocks;
+        uint32_t c = (skip_self && s == a.xq.me) ? 0u : __ldcg(&xq_hdr(a.xq, a.xq.me, parity, s)->counts[b]) & XQ_CNT_MASK;
+        if (c > a.xq.seg_cap) c = a.xq.seg_cap;
+        s_pref[j] = run;
+        run += c;
+      }
+    }
+  }
+  const uint32_t total = s_scan[32];
+  __syncthreads();
+  if (threadIdx.x == 0) s_pref[nseg] = total;
+  __syncthreads();
+  // ---- entries
+  const uint32_t R = a.tab.rmask + 1;
+  uint32_t added = 0;
+  for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+    uint32_t lo = 0, hi = nseg;  // largest j with s_pref[j] <= i (empty segments share a prefix value: take the last)
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (s_pref[mid] <= i) lo = mid; else hi = mid;
+    }
+    const uint32_t s = lo / a.xq.nblocks, b = lo - s * a.xq.nblocks;
+    const uint4 e = __ldcg(reinterpret_cast<const uint4 *>(xq_base(a.xq, a.xq.me) + xq_seg_off(a.xq, parity, s, b)) + (i - s_pref[lo]));
+    const unsigned long long key = ((unsigned long long)e.y << 32) | e.x;
+    const long long delta = (long long)(((unsigned long long)e.w << 32) | e.z);
+    const uint64_t hh = mix64(key);
+    if (pair_part(a.tab, hh) != blockIdx.x) continue;
+    added += pair_add_at(a.tab, (uint64_t)blockIdx.x * R, (uint32_t)hh & a.tab.rmask, key, delta) ? 1u : 0u;
+  }
+  if (added) atomicAdd(s_occ_add, added);
+  return ovf;
+}
+
 __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
-  const auto &tab = TabView<WIDE>::of(a.tab);  // WIDE: the table probed four slots per round trip (experimental)
   cg::grid_group grid = cg::this_grid();
   __shared__ Best s_warp[32];
   __shared__ Best s_best;
   __shared__ unsigned long long s_dead;
-  __shared__ uint32_t s_defer_n, s_direct;
+  __shared__ uint32_t s_defer_n, s_direct, s_out_n, s_occ, s_xf, s_bflags, s_scan[33];
   __shared__ unsigned long long s_tpre;
-  const bool dbgt = (a.dbg & 8u) != 0;  // per-block apply-phase timing (diagnostic)
-  // dynamic shared memory: [update queues: 32 warps x UQ_CAP x 16 B][tile tokens][tile offsets]
-  unsigned long long *uq_keys = reinterpret_cast<unsigned long long *>(yt_dyn_smem);
-  long long *uq_deltas = reinterpret_cast<long long *>(uq_keys + 32 * UQ_CAP);
-  uint32_t *s_claim = reinterpret_cast<uint32_t *>(uq_deltas + 32 * UQ_CAP);  // 2 bitmaps of CLAIM_WORDS x 32 flags
+  const bool dbgt = (a.dbg & 8u) != 0;  // per-block phase timing (diagnostic)
+  // dynamic shared memory: [segment prefix: XQ_MAX_WORLD * XQ_MAX_BLOCKS + 1 words][claim bitmaps][tile tokens][tile offsets]
+  uint32_t *s_pref = yt_dyn_smem;
+  uint32_t *s_claim = s_pref + (XQ_MAX_WORLD * XQ_MAX_BLOCKS + 4);  // 2 bitmaps of CLAIM_WORDS x 32 flags
   uint32_t *stok = s_claim + 2 * CLAIM_WORDS;
   uint32_t *soff = stok + a.smem_tok_cap;
   // RESIDENT only: word frequencies behind the offsets (8-byte aligned: both caps are even)
@@ -394,15 +556,23 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   }
   // STREAMING pipeline state of this thread (producer lane: empty-phase bits, consumers: full-phase bits)
   uint32_t pipe_used = 0, pipe_phase = 0, pipe_stage = 0;
-  WarpQueue uq;
-  uq.key = uq_keys + (threadIdx.x >> 5) * UQ_CAP;
-  uq.delta = uq_deltas + (threadIdx.x >> 5) * UQ_CAP;
-  uq.n = 0;
   const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t gstride = (uint64_t)gridDim.x * blockDim.x;
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  const uint64_t cap = a.tab.mask + 1;
+  const uint32_t R = a.tab.rmask + 1;
+  const uint64_t pbase = (uint64_t)blockIdx.x * R;  // this block's partition of the pair table
   const uint32_t n_done0 = a.ctl->n_done;
+  uint32_t round = a.ctl->xq_round;                   // last exchange round completed by every rank
+  bool pending = false;                               // a published round waits to be drained
+
+  // occupancy of this block's partition (keys never leave the table between rebuilds)
+  {
+    uint32_t occ = 0;
+    for (uint32_t i = threadIdx.x; i < R; i += blockDim.x) occ += __ldcg(a.tab.keys + pbase + i) != PK_EMPTY ? 1u : 0u;
+    for (int o = 16; o > 0; o >>= 1) occ += __shfl_xor_sync(0xffffffffu, occ, o);
+    if (threadIdx.x == 0) { s_occ = 0; s_xf = 0; s_bflags = 0; s_tpre = 0; }
+    __syncthreads();
+    if (lane == 0 && occ) atomicAdd(&s_occ, occ);
+  }
 
   // resident mode: this block's tile moves into shared memory once
   uint32_t rw0 = 0, rw1 = 0;
@@ -416,25 +586,41 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   }
   __syncthreads();
 
-  for (uint32_t it = 0; it < a.max_iters; ++it) {
+  for (uint32_t it = 0; it <= a.max_iters; ++it) {
     const uint32_t n_done = n_done0 + it;
-    if (n_done >= a.max_total) break;
-    // ---------------- arg-max over the table under MergeCandidate::operator< (bpe.cpp:110-126)
-    unsigned long long tq0 = gtid == 0 ? gtimer() : 0, tq1 = 0, tq2 = 0, tq3 = 0;
+    unsigned long long tq0 = gtid == 0 ? gtimer() : 0, tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0;
+    const unsigned long long tw0 = dbgt && lane == 0 ? gtimer() : 0;
+    // ---------------- drain: the count changes of the previous merge, from every GPU
+    if (pending) {  // block-uniform
+      if (a.xq.world > 1) {
+        const uint32_t f = xq_wait_peers(a, round);
+        if (f) atomicOr(&s_xf, f);
+        __syncthreads();  // the peers' data is ordered behind the acquire loads of the polling threads
+      }
+      if ((xq_drain(a, round, false, s_pref, s_scan, &s_occ) & 1u) && threadIdx.x == 0) atomicOr(&s_xf, XQF_OVERFLOW);
+      // this rank's own compaction wish is a function of ctl, which is quiescent since the barrier
+      if (threadIdx.x == 0) {
+        const unsigned long long dd = __ldcg(&a.ctl->dead), sl = __ldcg(&a.ctl->slots);
+        if (dd * 4 > sl && sl > 65536) atomicOr(&s_xf, XQF_COMPACT);
+      }
+      pending = false;
+    }
+    __syncthreads();  // the partition is up to date (drain's atomics are block-local traffic to L2: ordered by the barrier)
+    if (gtid == 0) tq1 = gtimer();
+    if (dbgt && lane == 0) atomicMax(&s_tpre, gtimer() - tw0);
+    // ---------------- arg-max over this block's partition under MergeCandidate::operator< (bpe.cpp:110-126)
     Best b{0, 0, 0};
-    // the counts of SWEEP_UNROLL slots are requested together: one L2 round trip per batch instead of
-    // one per slot (a thread owns cap / (148 * 1024) slots, 7 at the 1 M-slot table of the 100 MB corpus)
-    for (uint64_t i0 = gtid; i0 < cap; i0 += gstride * SWEEP_UNROLL) {
+    for (uint32_t i0 = threadIdx.x; i0 < R; i0 += blockDim.x * SWEEP_UNROLL) {
       unsigned long long c[SWEEP_UNROLL];
 #pragma unroll
       for (int u = 0; u < SWEEP_UNROLL; u++) {
-        const uint64_t i = i0 + (uint64_t)u * gstride;
-        c[u] = i < cap ? __ldcg(a.tab.cnts + i) : 0ull;
+        const uint32_t i = i0 + (uint32_t)u * blockDim.x;
+        c[u] = i < R ? __ldcg(a.tab.cnts + pbase + i) : 0ull;
       }
 #pragma unroll
       for (int u = 0; u < SWEEP_UNROLL; u++) {
         if (c[u] != 0 && c[u] >= b.c) {
-          const uint64_t i = i0 + (uint64_t)u * gstride;
+          const uint64_t i = pbase + i0 + (uint64_t)u * blockDim.x;
           const unsigned long long k = __ldcg(a.tab.keys + i);
           Best cand{c[u], pair_prio((uint32_t)(k >> 32), (uint32_t)k), i};
           if (better(cand, b)) b = cand;
@@ -451,16 +637,21 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
         a.blockbest[4 * blockIdx.x + 0] = v.c;
         a.blockbest[4 * blockIdx.x + 1] = v.prio;
         a.blockbest[4 * blockIdx.x + 2] = v.slot;
+        // bit 0: this partition is nearly full (deterministic in the key set, hence the same on every rank);
+        // bits 8..: exchange flags seen by this block (identical in all blocks of all ranks)
+        a.blockbest[4 * blockIdx.x + 3] = ((unsigned long long)s_occ * 8ull > (unsigned long long)R * 7ull ? 1ull : 0ull) |
+                                          ((unsigned long long)s_xf << 8);
       }
     }
-    if (gtid == 0) tq1 = gtimer();
-    grid.sync();
     if (gtid == 0) tq2 = gtimer();
-    const unsigned long long tw0 = dbgt && lane == 0 ? gtimer() : 0;
+    grid.sync();
+    if (gtid == 0) tq3 = gtimer();
+    uint32_t bflags = 0;
     {  // every block reduces the per-block winners redundantly: one entry per thread, one round trip
       Best v{0, 0, 0};
       for (unsigned j = threadIdx.x; j < gridDim.x; j += blockDim.x) {
         Best w{__ldcg(a.blockbest + 4 * j), __ldcg(a.blockbest + 4 * j + 1), __ldcg(a.blockbest + 4 * j + 2)};
+        bflags |= (uint32_t)__ldcg(a.blockbest + 4 * j + 3);
         if (better(w, v)) v = w;
       }
       const unsigned used_warps = (min(gridDim.x, blockDim.x) + 31) >> 5;
@@ -468,19 +659,35 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
         v = warp_best(v);
         if (lane == 0) s_warp[wid] = v;
       }
+      if (bflags) atomicOr(&s_bflags, bflags);
       __syncthreads();
       if (wid == 0) {
         Best u = lane < used_warps ? s_warp[lane] : Best{0, 0, 0};
         u = warp_best(u);
-        if (lane == 0) { s_best = u; s_dead = 0; s_tpre = 0; }
+        if (lane == 0) { s_best = u; s_dead = 0; s_out_n = 0; }
       }
     }
     __syncthreads();
     const Best win = s_best;
-    if (win.c == 0) {  // no pair left: "merged only" (bpe.cpp:1137-1145)
-      if (gtid == 0) a.ctl->stop = 1;
-      break;
+    bflags = s_bflags;
+    // ---------------- uniform exit checks (every block of every rank evaluates the same values)
+    {
+      uint32_t stop = 0, why = 0;
+      const uint32_t xf = bflags >> 8;
+      if (bflags & 1u) why |= 1u;                                   // a partition is nearly full: grow the table
+      if (xf & XQF_OVERFLOW) why |= 2u;                             // lost count changes: rebuild from the tokens
+      if (__ldcg(a.tab.overflow)) why |= 4u;                        // a partition ran full: grow
+      if (__ldcg(a.tab.n_keys) > a.key_limit) why |= 8u;            // load factor: rebuild (dead keys vanish)
+      if (n_done >= a.max_total || it == a.max_iters) stop = 4;     // done (or launch budget spent)
+      else if (why) stop = 2;
+      else if (xf & XQF_COMPACT) stop = 3;                          // some rank wants a compaction
+      else if (win.c == 0) stop = 1;                                // no pair left (bpe.cpp:1137-1145)
+      if (stop) {
+        if (gtid == 0) { a.ctl->stop = stop == 4 ? 0u : stop; a.ctl->stop_why = why; }
+        break;
+      }
     }
+    const unsigned long long tw1 = dbgt && lane == 0 ? gtimer() : 0;
     MergeOp op;
     {  // (x, y) is recoverable from the priority word (pair_prio), no dependent table load needed
       const uint32_t mx = 0xffffffffu - (uint32_t)(win.prio >> 32);
@@ -493,14 +700,19 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     if (gtid == 0) {
       a.rules[3 * n_done + 0] = op.x; a.rules[3 * n_done + 1] = op.y; a.rules[3 * n_done + 2] = op.z;
       a.rfreq[n_done] = win.c;
-      a.tab.cnts[win.slot] = 0;  // every occurrence of (x,y) is merged below; no deltas are sent for it
       a.ctl->n_done = n_done + 1;
     }
-    // ---------------- apply x y -> z
+    // every occurrence of (x,y) is merged below and no deltas are emitted for it: its owner clears the count
+    if (threadIdx.x == 0 && win.slot >= pbase && win.slot < pbase + R) a.tab.cnts[win.slot] = 0;
+    // ---------------- apply x y -> z: count changes go to this block's segment of round + 1 (on every rank)
+    const uint32_t nround = round + 1;
+    XqOut xo;
+    xo.off = xq_seg_off(a.xq, nround & 1u, a.xq.me, blockIdx.x);
+    xo.s_n = &s_out_n;
     unsigned long long dead = 0;
     if (a.resident) {
       if (rw1 > rw0) dead = process_tile(stok, soff, rw1 - rw0, soff[rw1 - rw0], s_claim,
-                                           reinterpret_cast<const uint64_t *>(sfreq), op, tab, uq);
+                                           reinterpret_cast<const uint64_t *>(sfreq), op, a, xo);
     } else {
       // STREAMING: this block owns a contiguous chunk of tiles that flows through an n_stage ring of
       // shared-memory stages.  Lane 0 of warp 0 is the PRODUCER: it keeps up to n_stage tiles in
@@ -628,13 +840,13 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
         for (uint32_t j = wid; j < n_def; j += nwarp) {
           const uint4 e = defer[j];
           const long long f = (long long)a.freq[e.x];
-          const uint32_t merges = warp_apply_word(a.tok + e.y, e.z, nullptr, f, op, lane, tab, uq);
+          const uint32_t merges = warp_apply_word(a.tok + e.y, e.z, nullptr, f, op, lane, a, xo);
           if (lane == 0) dead += merges;
         }
         if (s_direct && my_tiles) {  // oversized tiles / overflowed list: exact thread-per-word pass on global memory
           __syncthreads();
           const uint32_t w_lo = a.tile_desc[k_first].x, w_hi = a.tile_desc[k_first + my_tiles].x;
-          dead += process_tile_direct(a.tok, a.off, a.freq, w_lo, w_hi, op, tab);
+          dead += process_tile_direct(a.tok, a.off, a.freq, w_lo, w_hi, op, a, xo);
         }
       }
       // write-through stores (generic proxy) must be ordered before the next iteration's bulk loads
@@ -642,38 +854,53 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       asm volatile("fence.proxy.async;" ::: "memory");
 #endif
     }
-    if (dbgt && lane == 0) atomicMax(&s_tpre, gtimer() - tw0);
-    if (uq.n) uq_drain(uq, lane, tab);  // one batch of table updates per warp and iteration
     for (int o = 16; o > 0; o >>= 1) dead += __shfl_xor_sync(0xffffffffu, dead, o);
     if (lane == 0 && dead) atomicAdd(&s_dead, dead);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_dead) atomicAdd(&a.ctl->dead, s_dead);
-    if (dbgt && threadIdx.x == 0) {
-      const unsigned long long t = gtimer() - tw0;
-      atomicMax(&a.ctl->blk[it & 1][0], t);
-      atomicAdd(&a.ctl->blk[it & 1][1], t);
-      atomicMax(&a.ctl->blk[it & 1][2], s_tpre);
-    }
-    if (gtid == 0) tq3 = gtimer();
-    grid.sync();
-    if (gtid == 0) {
-      unsigned long long tq4 = gtimer();
+    __syncthreads();  // all entries of this block are on their way
+    if (threadIdx.x == 0) {
+      if (s_dead) atomicAdd(&a.ctl->dead, s_dead);
+      const uint32_t n = s_out_n;
+      const uint32_t word = n > a.xq.seg_cap ? (a.xq.seg_cap | XQ_CNT_OVF) : n;
+#pragma unroll
+      for (int d = 0; d < XQ_MAX_WORLD; d++)
+        if ((uint32_t)d < a.xq.world) xq_hdr(a.xq, (uint32_t)d, nround & 1u, a.xq.me)->counts[blockIdx.x] = word;
+      if (a.xq.world > 1) fence_sys();  // this block's entries and count, as observed through the barrier above
+      s_xf = 0; s_bflags = 0;  // next iteration's accumulators (read again only after the grid barrier below)
       if (dbgt) {
-        a.ctl->t_phase[4] += __ldcg(&a.ctl->blk[it & 1][0]);
-        a.ctl->t_phase[5] += __ldcg(&a.ctl->blk[it & 1][1]) / gridDim.x;
-        a.ctl->t_phase[6] += __ldcg(&a.ctl->blk[it & 1][2]);
+        const unsigned long long t = gtimer() - tw1;
+        atomicMax(&a.ctl->blk[it & 1][0], t);
+        atomicAdd(&a.ctl->blk[it & 1][1], t);
+        atomicMax(&a.ctl->blk[it & 1][2], s_tpre);
+        s_tpre = 0;
+      }
+    }
+    if (gtid == 0) tq4 = gtimer();
+    grid.sync();
+    round = nround;
+    pending = true;
+    if (gtid == 0) {
+      unsigned long long tq5 = gtimer();
+      if (a.xq.world > 1) {  // publish: every peer may now read this rank's segments of `round`
+        const unsigned long long dd = __ldcg(&a.ctl->dead), sl = __ldcg(&a.ctl->slots);
+        const unsigned long long word = ((unsigned long long)round << 8) | ((dd * 4 > sl && sl > 65536) ? XQF_COMPACT : 0u);
+        fence_sys();
+#pragma unroll
+        for (int d = 0; d < XQ_MAX_WORLD; d++)
+          if ((uint32_t)d < a.xq.world && (uint32_t)d != a.xq.me)
+            st_release_sys(&xq_hdr(a.xq, (uint32_t)d, round & 1u, a.xq.me)->seq_flags, word);
+      }
+      if (dbgt) {
+        a.ctl->t_phase[5] += __ldcg(&a.ctl->blk[it & 1][0]);
+        a.ctl->t_phase[6] += __ldcg(&a.ctl->blk[it & 1][1]) / gridDim.x;
+        a.ctl->t_phase[7] += __ldcg(&a.ctl->blk[it & 1][2]);
         a.ctl->blk[it & 1][0] = 0; a.ctl->blk[it & 1][1] = 0; a.ctl->blk[it & 1][2] = 0;
       }
-      a.ctl->t_phase[0] += tq1 - tq0; a.ctl->t_phase[1] += tq2 - tq1;
-      a.ctl->t_phase[2] += tq3 - tq2; a.ctl->t_phase[3] += tq4 - tq3;
+      a.ctl->t_phase[0] += tq1 - tq0; a.ctl->t_phase[1] += tq2 - tq1; a.ctl->t_phase[2] += tq3 - tq2;
+      a.ctl->t_phase[3] += tq4 - tq3; a.ctl->t_phase[4] += tq5 - tq4;
       a.ctl->iters += 1;
     }
-    // ---------------- uniform exit checks (every block reads the same values)
-    uint32_t nk = __ldcg(&a.ctl->n_keys), ov = __ldcg(&a.ctl->overflow);
-    unsigned long long dd = __ldcg(&a.ctl->dead), sl = __ldcg(&a.ctl->slots);
-    if (ov || nk > a.key_limit) { if (gtid == 0) a.ctl->stop = 2; break; }
-    if (dd * 4 > sl && sl > 65536) { if (gtid == 0) a.ctl->stop = 3; break; }
   }
+  if (gtid == 0) a.ctl->xq_round = round;
   // resident tiles go back to HBM on every exit path
   __syncthreads();
   if (a.resident && rw1 > rw0) {
@@ -681,8 +908,77 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     for (uint32_t i = threadIdx.x; i < span; i += blockDim.x) a.tok[o0 + i] = stok[i];
   }
 }
-__global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) { merge_loop_body<false>(a); }
-__global__ void __launch_bounds__(1024, 1) merge_loop_wide_kernel(LoopArgs a) { merge_loop_body<true>(a); }  // YTTM_LOOP_WIDEPROBE
+__global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) { merge_loop_body(a); }
+
+// ---- exchange rounds outside the loop (multi-GPU table build): one block per partition -----------
+// xq_publish_table_kernel: block b enumerates the live (key, count) pairs of partition b of the LOCAL table in slot
+// order and copies those numbered [chunk * seg_cap, (chunk + 1) * seg_cap) into segment b of round `round` on every
+// OTHER rank; the count word says whether more follow.  The last block to finish publishes the round.
+__global__ void __launch_bounds__(256) xq_publish_table_kernel(LoopArgs a, uint32_t round, uint32_t chunk, unsigned int *arrive) {
+  const uint32_t R = a.tab.rmask + 1;
+  const uint64_t pbase = (uint64_t)blockIdx.x * R;
+  const size_t off = xq_seg_off(a.xq, round & 1u, a.xq.me, blockIdx.x);
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const uint64_t lo = (uint64_t)chunk * a.xq.seg_cap, hi = lo + a.xq.seg_cap;
+  __shared__ uint32_t s_w[32];
+  uint32_t done = 0;  // live pairs before this pass (block-uniform)
+  for (uint32_t i0 = 0; i0 < R; i0 += blockDim.x) {  // block-uniform trip count, slot order
+    const uint32_t i = i0 + threadIdx.x;
+    unsigned long long k = PK_EMPTY, c = 0;
+    if (i < R) { k = a.tab.keys[pbase + i]; c = a.tab.cnts[pbase + i]; }
+    const bool has = k != PK_EMPTY && c != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, has);
+    if (lane == 0) s_w[wid] = (uint32_t)__popc(m);
+    __syncthreads();
+    uint32_t before = 0, all = 0;
+    for (unsigned w = 0; w < nwarp; w++) { const uint32_t v = s_w[w]; if (w < wid) before += v; all += v; }
+    if (has) {
+      const uint64_t idx = (uint64_t)done + before + __popc(m & ((1u << lane) - 1u));
+      if (idx >= lo && idx < hi) {
+        const uint4 e = make_uint4((uint32_t)k, (uint32_t)(k >> 32), (uint32_t)c, (uint32_t)(c >> 32));
+#pragma unroll
+        for (int d = 0; d < XQ_MAX_WORLD; d++)
+          if ((uint32_t)d < a.xq.world && (uint32_t)d != a.xq.me) reinterpret_cast<uint4 *>(a.xq.base[d] + off)[idx - lo] = e;
+      }
+    }
+    done += all;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const uint64_t total = done;
+    uint32_t word = total > lo ? (uint32_t)(total - lo < (uint64_t)a.xq.seg_cap ? total - lo : (uint64_t)a.xq.seg_cap) : 0u;
+    if (total > hi) word |= XQ_CNT_MORE;
+#pragma unroll
+    for (int d = 0; d < XQ_MAX_WORLD; d++)
+      if ((uint32_t)d < a.xq.world) xq_hdr(a.xq, (uint32_t)d, round & 1u, a.xq.me)->counts[blockIdx.x] = word;
+    fence_sys();
+    // the last block to arrive publishes the round (every block's stores precede its fence and its arrival)
+    if (atomicAdd(arrive, 1u) + 1u == gridDim.x) {
+      fence_sys();
+      const unsigned long long hw = ((unsigned long long)round << 8) | (__ldcg(a.tab.overflow) ? XQF_OVERFLOW : 0u);
+#pragma unroll
+      for (int d = 0; d < XQ_MAX_WORLD; d++)
+        if ((uint32_t)d < a.xq.world && (uint32_t)d != a.xq.me)
+          st_release_sys(&xq_hdr(a.xq, (uint32_t)d, round & 1u, a.xq.me)->seq_flags, hw);
+      *arrive = 0;
+    }
+  }
+}
+// xq_absorb_kernel: block b waits for round `round` of every peer and adds the peers' pairs it owns to partition b.
+__global__ void __launch_bounds__(256) xq_absorb_kernel(LoopArgs a, uint32_t round) {
+  __shared__ uint32_t s_scan[33], s_occ;
+  uint32_t *s_pref = yt_dyn_smem;
+  if (threadIdx.x == 0) s_occ = 0;
+  const uint32_t f = xq_wait_peers(a, round);
+  if (f) atomicOr(&a.ctl->xq_flags, f);
+  __syncthreads();
+  const uint32_t r = xq_drain(a, round, true, s_pref, s_scan, &s_occ);
+  if (threadIdx.x == 0) {
+    if (r & 1u) atomicExch(a.tab.overflow, 1u);
+    if (r & 2u) atomicOr(&a.ctl->xq_flags, XQF_MORE);
+    if (blockIdx.x == 0) a.ctl->xq_round = round;
+  }
+}
 
 // ---- tile planning -----------------------------------------------------------------------------
 // tile k = words whose first token slot lies in [k*q, (k+1)*q); tile_desc[k] = (its first word,

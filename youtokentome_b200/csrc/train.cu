@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <thread>
+#include <unistd.h>
 
 #include "common.cuh"
 
@@ -33,88 +34,57 @@ constexpr uint64_t POS_MASK = (1ull << 40) - 1;
 
 // ------------------------------------------------------------------------------------------
 // pair -> count table: open addressing, linear probing, SoA (keys / counts) so the arg-max
-// sweep streams 8 B per slot and touches keys only for candidates.
+// sweep streams 8 B per slot and touches keys only for candidates.  The table is cut into
+// `nparts` PARTITIONS of R = rmask + 1 slots (R a power of two): a key lives in partition
+// mulhi(hash_hi, nparts) and probes inside it (wrapping at the partition's end).  Inside the merge
+// loop partition b belongs to block b alone (merge_loop.cuh); the one-off histogram kernels below
+// write it from everywhere with atomics.
 // ------------------------------------------------------------------------------------------
 struct PairTab {
   unsigned long long *keys;
   unsigned long long *cnts;
-  uint64_t mask;
-  uint32_t *n_keys;
-  uint32_t *overflow;
+  uint32_t rmask;      // slots per partition - 1
+  uint32_t nparts;
+  uint32_t *n_keys;    // occupied slots (keys never leave between rebuilds)
+  uint32_t *overflow;  // a partition ran full: the update was dropped, the host rebuilds a larger table
 };
+__device__ __forceinline__ uint64_t tab_slots(const PairTab &t) { return (uint64_t)t.nparts * ((uint64_t)t.rmask + 1); }
+__device__ __forceinline__ uint32_t pair_part(const PairTab &t, uint64_t h) { return mulhi32((uint32_t)(h >> 32), t.nparts); }
 
-// A probe sequence longer than PROBE_LIMIT means the table is over-full: the update is dropped
-// and the overflow flag makes the host rebuild a larger table from the (always consistent) tokens.
-constexpr uint64_t PROBE_LIMIT = 512;
+// Add delta to `key` inside the partition that starts at slot `base`, first probe at base + i0.
+// Returns true when the key was inserted.  A full partition drops the update and raises the flag.
 template <bool CAS_FIRST = false>
-__device__ __forceinline__ void pair_add(const PairTab &t, uint64_t key, long long delta) {
-  uint64_t h = mix64(key) & t.mask;
-  const uint64_t limit = t.mask < PROBE_LIMIT ? t.mask : PROBE_LIMIT;
-  for (uint64_t probe = 0; probe <= limit; probe++) {
+__device__ __forceinline__ bool pair_add_at(const PairTab &t, uint64_t base, uint32_t i0, uint64_t key, long long delta) {
+  for (uint32_t probe = 0; probe <= t.rmask; probe++) {
+    const uint64_t h = base + ((i0 + probe) & t.rmask);
     unsigned long long k;
-    if (CAS_FIRST) {  // a pair that most likely is new (it holds the token just created): claim without looking
+    bool fresh = false;
+    if (CAS_FIRST) {  // a pair that most likely is new: claim without looking
       k = atomicCAS(t.keys + h, PK_EMPTY, (unsigned long long)key);
-      if (k == PK_EMPTY) { atomicAdd(t.n_keys, 1u); k = key; }
+      if (k == PK_EMPTY) { fresh = true; k = key; }
     } else {
       k = __ldcg(t.keys + h);
 #ifdef YT_SIMT_EMU
-      emu::yield();  // test harness: see pair_add(PairTabWide)
+      emu::yield();  // test harness: other fibers run between the load and the CAS, so the lost-race path is exercised
 #endif
       if (k == PK_EMPTY) {
         k = atomicCAS(t.keys + h, PK_EMPTY, (unsigned long long)key);
-        if (k == PK_EMPTY) { atomicAdd(t.n_keys, 1u); k = key; }
+        if (k == PK_EMPTY) { fresh = true; k = key; }
       }
     }
-    if (k == key) { atomicAdd(t.cnts + h, (unsigned long long)delta); return; }
-    h = (h + 1) & t.mask;
-  }
-  atomicExch(t.overflow, 1u);
-}
-
-// EXPERIMENTAL (env YTTM_LOOP_WIDEPROBE=1, merge loop only; off by default until measured on a B200): the same table
-// and the same placement rule (the first empty or matching slot along h, h+1, ...), but FOUR slots - one aligned
-// 32-byte sector of the key array - are fetched per L2 round trip by independent loads, instead of one dependent
-// round trip per slot.  Why: keys are never deleted, the table runs between load 3/8 and 3/4, and a linear-probe
-// insert at load 0.7 walks ~6 slots on average and several times that in the worst of the ~100 inserts of a merge -
-// each a dependent __ldcg / CAS of ~1 us - which is the suspected "one unlucky block" tail of the apply phase
-// (DESIGN.md 6).  A slot that was occupied by another key when loaded stays so (keys never change), a slot that was
-// empty is claimed by CAS, whose return value is the truth; two inserters of one key meet at the same slot.
-struct PairTabWide : PairTab {};
-template <bool CAS_FIRST = false>
-__device__ __forceinline__ void pair_add(const PairTabWide &t, uint64_t key, long long delta) {
-  uint64_t h = mix64(key) & t.mask;
-  const uint64_t limit = t.mask < PROBE_LIMIT ? t.mask : PROBE_LIMIT;
-  uint64_t probe = 0;
-  while (probe <= limit) {
-    const uint64_t g = h & ~3ull;  // the capacity is a power of two >= 16: a group of four never wraps
-    unsigned long long k4[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) k4[j] = __ldcg(t.keys + g + j);
-#ifdef YT_SIMT_EMU
-    emu::yield();  // test harness: other fibers run between the loads and the CAS, so the lost-race path is exercised
-#endif
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      if ((uint64_t)j < (h & 3ull) || probe > limit) continue;
-      probe++;
-      unsigned long long k = k4[j];
-      if (k == PK_EMPTY) {
-        k = atomicCAS(t.keys + g + j, PK_EMPTY, (unsigned long long)key);
-        if (k == PK_EMPTY) { atomicAdd(t.n_keys, 1u); k = key; }
-      }
-      if (k == key) { atomicAdd(t.cnts + g + j, (unsigned long long)delta); return; }
+    if (k == key) {
+      atomicAdd(t.cnts + h, (unsigned long long)delta);
+      if (fresh) atomicAdd(t.n_keys, 1u);
+      return fresh;
     }
-    h = (g + 4) & t.mask;
   }
   atomicExch(t.overflow, 1u);
+  return false;
 }
-template <bool W> struct TabView;
-template <> struct TabView<false> {
-  static __device__ __forceinline__ const PairTab &of(const PairTab &t) { return t; }
-};
-template <> struct TabView<true> {
-  static __device__ __forceinline__ PairTabWide of(const PairTab &t) { PairTabWide w; static_cast<PairTab &>(w) = t; return w; }
-};
+__device__ __forceinline__ void pair_add(const PairTab &t, uint64_t key, long long delta) {
+  const uint64_t h = mix64(key);
+  pair_add_at(t, (uint64_t)pair_part(t, h) * ((uint64_t)t.rmask + 1), (uint32_t)h & t.rmask, key, delta);
+}
 
 // ------------------------------------------------------------------------------------------
 // phase 1: decode units + code point histogram
@@ -165,6 +135,31 @@ __device__ __forceinline__ bool same_word(const uint8_t *s, uint64_t n, uint64_t
   return a + len == n || space_at(s, a + len, n, &l);
 }
 
+// insert the word that starts at byte p (weight = its number of occurrences) ; returns false when the table is full
+__device__ __forceinline__ bool word_table_insert(const uint8_t *__restrict__ s, uint64_t n, uint64_t p, const WordTab &wt,
+                                                  unsigned long long *counters, uint64_t max_unique,
+                                                  unsigned long long weight) {
+  uint64_t h = 0xcbf29ce484222325ull, q = p;
+  uint32_t l;
+  while (q < n && !space_at(s, q, n, &l)) { h = (h ^ s[q]) * 0x100000001b3ull; q++; }
+  uint64_t len = q - p;
+  h = mix64(h ^ (len << 1));
+  uint64_t tag = h >> 40;
+  unsigned long long mine = (tag << 40) | (p + 1);
+  uint64_t slot = h & wt.mask;
+  for (uint64_t probe = 0; probe <= wt.mask; probe++) {
+    unsigned long long k = __ldcg(wt.keys + slot);
+    if (k == 0) {
+      if (__ldcg(counters + 1) >= max_unique) { atomicExch(counters + 2, 1ull); return false; }
+      k = atomicCAS(wt.keys + slot, 0ull, mine);
+      if (k == 0) { atomicAdd(counters + 1, 1ull); atomicAdd(wt.cnts + slot, weight); return true; }
+    }
+    if ((k >> 40) == tag && same_word(s, n, (k & POS_MASK) - 1, p, len)) { atomicAdd(wt.cnts + slot, weight); return true; }
+    slot = (slot + 1) & wt.mask;
+  }
+  return false;
+}
+
 __global__ void __launch_bounds__(256) word_insert_kernel(const uint8_t *__restrict__ s, uint64_t n, WordTab wt,
                                                           unsigned long long *counters, uint64_t max_unique) {
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -172,27 +167,57 @@ __global__ void __launch_bounds__(256) word_insert_kernel(const uint8_t *__restr
   for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
     if (!word_start_at(s, p, 0, n)) continue;
     occ++;
-    uint64_t h = 0xcbf29ce484222325ull, q = p;
-    uint32_t l;
-    while (q < n && !space_at(s, q, n, &l)) { h = (h ^ s[q]) * 0x100000001b3ull; q++; }
-    uint64_t len = q - p;
-    h = mix64(h ^ (len << 1));
-    uint64_t tag = h >> 40;
-    unsigned long long mine = (tag << 40) | (p + 1);
-    uint64_t slot = h & wt.mask;
-    for (uint64_t probe = 0; probe <= wt.mask; probe++) {
-      unsigned long long k = __ldcg(wt.keys + slot);
-      if (k == 0) {
-        if (__ldcg(counters + 1) >= max_unique) { atomicExch(counters + 2, 1ull); break; }
-        k = atomicCAS(wt.keys + slot, 0ull, mine);
-        if (k == 0) { atomicAdd(counters + 1, 1ull); atomicAdd(wt.cnts + slot, 1ull); break; }
-      }
-      if ((k >> 40) == tag && same_word(s, n, (k & POS_MASK) - 1, p, len)) { atomicAdd(wt.cnts + slot, 1ull); break; }
-      slot = (slot + 1) & wt.mask;
-    }
+    word_table_insert(s, n, p, wt, counters, max_unique, 1ull);
   }
   for (int o = 16; o > 0; o >>= 1) occ += __shfl_xor_sync(0xffffffffu, occ, o);
   if ((threadIdx.x & 31) == 0 && occ) atomicAdd(counters + 0, (unsigned long long)occ);
+}
+
+// Multi-GPU import: the "text" is a list of words (word i starts at byte base + pos[i], a space follows it) that other
+// ranks found freq[i] times each (yttm_train_dist_export_words); same table, same exact byte compare.
+__global__ void __launch_bounds__(256) word_insert_list_kernel(const uint8_t *__restrict__ s, uint64_t n, uint64_t base,
+                                                               const uint64_t *__restrict__ pos,
+                                                               const uint64_t *__restrict__ freq, uint64_t n_list,
+                                                               WordTab wt, unsigned long long *counters, uint64_t max_unique) {
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  unsigned long long occ = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_list; i += stride) {
+    occ += freq[i];
+    word_table_insert(s, n, base + pos[i], wt, counters, max_unique, (unsigned long long)freq[i]);
+  }
+  for (int o = 16; o > 0; o >>= 1) occ += __shfl_xor_sync(0xffffffffu, occ, o);
+  if ((threadIdx.x & 31) == 0 && occ) atomicAdd(counters + 0, occ);
+}
+
+// Multi-GPU export: unique word w of this rank goes to rank owner(w) = hash(bytes) % world (every rank uses the same
+// function, so equal words meet on one rank).  PASS 0 counts bytes (word + one space) and words per destination;
+// PASS 1 writes them behind the per-destination cursors (any order inside a destination).
+template <int PASS>
+__global__ void __launch_bounds__(256) word_export_kernel(const uint8_t *__restrict__ s, uint64_t n,
+                                                          const uint64_t *__restrict__ wpos,
+                                                          const uint64_t *__restrict__ wfreq, uint64_t n_unique,
+                                                          uint32_t world, unsigned long long *cur_bytes /* [world] */,
+                                                          unsigned long long *cur_words /* [world] */,
+                                                          const unsigned long long *byte_base /* [world], PASS 1 */,
+                                                          uint8_t *__restrict__ out_bytes, uint64_t *__restrict__ out_pos,
+                                                          uint64_t *__restrict__ out_freq) {
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_unique; w += stride) {
+    const uint64_t p = wpos[w];
+    uint64_t h = 0xcbf29ce484222325ull, q = p;
+    uint32_t l;
+    while (q < n && !space_at(s, q, n, &l)) { h = (h ^ s[q]) * 0x100000001b3ull; q++; }
+    const uint64_t len = q - p;
+    const uint32_t dst = mulhi32((uint32_t)(mix64(h + len) >> 32), world);
+    const unsigned long long at = atomicAdd(cur_bytes + dst, (unsigned long long)(len + 1));
+    const unsigned long long idx = atomicAdd(cur_words + dst, 1ull);
+    if (PASS == 1) {
+      for (uint64_t i = 0; i < len; i++) out_bytes[at + i] = s[p + i];
+      out_bytes[at + len] = ' ';
+      out_pos[idx] = at - byte_base[dst];  // relative to the destination's first byte
+      out_freq[idx] = wfreq[w];
+    }
+  }
 }
 
 __global__ void word_compact_kernel(WordTab wt, unsigned long long *counters, uint64_t *__restrict__ wpos,
@@ -316,7 +341,8 @@ __global__ void __launch_bounds__(256) pair_hist_kernel(const uint32_t *__restri
                                                         const uint64_t *__restrict__ freq, uint64_t n_words,
                                                         PairTab tab) {
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  const uint32_t key_limit = (uint32_t)((tab.mask + 1) / 2 < 0xffffffffull ? (tab.mask + 1) / 2 : 0xffffffffull);  // > 3/8
+  const uint64_t half = tab_slots(tab) / 2;
+  const uint32_t key_limit = (uint32_t)(half < 0xffffffffull ? half : 0xffffffffull);
   for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
     // a table that is already half full will be rejected by the host anyway: stop early
     if (__ldcg(tab.overflow) || __ldcg(tab.n_keys) > key_limit) { atomicExch(tab.overflow, 1u); return; }
@@ -325,6 +351,20 @@ __global__ void __launch_bounds__(256) pair_hist_kernel(const uint32_t *__restri
     long long f = (long long)freq[w];
     for_each_pair(tok + o, cap, [&](uint64_t key, uint64_t mult) { pair_add(tab, key, (long long)mult * f); });
   }
+}
+
+// fullest partition of the table (one block per partition)
+__global__ void __launch_bounds__(256) part_occ_kernel(PairTab tab, uint32_t *max_occ) {
+  __shared__ uint32_t s_n;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  const uint64_t base = (uint64_t)blockIdx.x * ((uint64_t)tab.rmask + 1);
+  uint32_t n = 0;
+  for (uint32_t i = threadIdx.x; i <= tab.rmask; i += blockDim.x) n += tab.keys[base + i] != PK_EMPTY ? 1u : 0u;
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(&s_n, n);
+  __syncthreads();
+  if (threadIdx.x == 0) atomicMax(max_occ, s_n);
 }
 
 __global__ void pair_dump_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ cnts,
@@ -411,54 +451,194 @@ PairTab tab_of(yttm_ctx *c) {
   PairTab t;
   t.keys = c->pkey.as<unsigned long long>();
   t.cnts = c->pcnt.as<unsigned long long>();
-  t.mask = c->pcap - 1;
+  t.rmask = c->p_rmask;
+  t.nparts = c->p_nparts;
   YtLoopCtl *ctl = c->ctl.as<YtLoopCtl>();
   t.n_keys = &ctl->n_keys;
   t.overflow = &ctl->overflow;
   return t;
 }
 
-// (Re)build the pair table from the current packed words.  Grows the table until the load
-// factor after the build is <= 1/4.
-// smallest pair table; YTTM_PAIR_CAP_FLOOR lowers it so that tests reach the rebuild / overflow paths on tiny inputs
 // Load factor (percent) above which the merge loop leaves for a rebuild; a rebuilt table is accepted at half of it.
-// Default 75 / 37.5 (the measured configuration); YTTM_PAIR_MAX_LOAD_PCT = 30..90 is an A/B knob: a lower load means
-// shorter probe chains for the table updates and a larger table for the arg-max sweep.
+// Default 50 / 25: since round 2 a block sweeps only its own partition, so a roomier table costs little and keeps the
+// probe chains of the owners' updates short.  YTTM_PAIR_MAX_LOAD_PCT = 30..90 is an A/B knob.
 static uint64_t pair_max_load_pct() {
   if (const char *e = std::getenv("YTTM_PAIR_MAX_LOAD_PCT")) return (uint64_t)std::min(90, std::max(30, std::atoi(e)));
-  return 75;
+  return 50;
 }
+// smallest pair table; YTTM_PAIR_CAP_FLOOR lowers it so that tests reach the rebuild / overflow paths on tiny inputs
 static uint64_t pair_cap_floor() {
   if (const char *e = std::getenv("YTTM_PAIR_CAP_FLOOR")) return ytc::pow2ceil((uint64_t)std::max(16, std::atoi(e)));
   return 1u << 16;
 }
 
-int rebuild_pair_table(yttm_ctx *c, uint64_t min_cap) {
-  uint64_t cap = std::max<uint64_t>(ytc::pow2ceil(min_cap), pair_cap_floor());
-  YT_CUDA(c, c->ctl.reserve(sizeof(YtLoopCtl)));
-  for (int attempt = 0; attempt < 24; attempt++) {
-    YT_CUDA(c, c->pkey.reserve(cap * 8));
-    YT_CUDA(c, c->pcnt.reserve(cap * 8));
-    c->pcap = cap;
-    YT_CUDA(c, cudaMemsetAsync(c->pkey.p, 0xff, cap * 8, c->stream));
-    YT_CUDA(c, cudaMemsetAsync(c->pcnt.p, 0, cap * 8, c->stream));
-    YtLoopCtl *ctl = c->ctl.as<YtLoopCtl>();
-    YT_CUDA(c, cudaMemsetAsync(&ctl->n_keys, 0, 8, c->stream));  // n_keys + overflow
-    if (c->n_words) {
-      pair_hist_kernel<<<grid_for(c, c->n_words, 256, 8), 256, 0, c->stream>>>(
-          c->tok[c->cur].as<uint32_t>(), c->off[c->cur].as<uint32_t>(), c->freq[c->cur].as<uint64_t>(), c->n_words,
-          tab_of(c));
-      c->launches++;
-    }
-    YT_CUDA(c, cudaGetLastError());
-    uint32_t h[2];
-    YT_CUDA(c, cudaMemcpyAsync(h, &ctl->n_keys, 8, cudaMemcpyDeviceToHost, c->stream));
+// Launch geometry of the cooperative merge loop: one block per SM, all co-resident, with (almost) all of the SM's
+// shared memory as the tile buffer.  Fixed per context before the first table is built, because the pair table has one
+// partition per block.
+constexpr int LOOP_SMEM_HEAD = (XQ_MAX_WORLD * XQ_MAX_BLOCKS + 4) * 4 + 2 * CLAIM_WORDS * 4;  // segment prefix + claim bitmaps
+int ensure_loop_geometry(yttm_ctx *c) {
+  if (c->loop_blocks) return 0;
+  int optin = 0;
+  YT_CUDA(c, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+  int dyn = optin - 4096;  // static shared memory of the kernel (~1.5 KB) + margin
+  if (dyn < 64 * 1024) YT_FAIL(c, "merge_loop_kernel: not enough shared memory per block");
+  c->loop_smem = dyn;
+  const int tile_bytes = dyn - LOOP_SMEM_HEAD;
+  // RESIDENT tile: per word 4 B offset + 8 B frequency (kept in shared memory too, so a rewritten
+  // word costs no L2 round trip for its frequency), the rest token slots
+  c->loop_word_cap = std::min<uint32_t>((uint32_t)(tile_bytes / 24 - 2), CLAIM_WORDS * 32 - 1) & ~1u;
+  c->loop_tok_cap = (uint32_t)((tile_bytes - 12 * (c->loop_word_cap + 2)) / 4) & ~3u;
+  // STREAMING: n_stage stages; a stage holds a window of q slots plus the overhang of its last
+  // word (words of up to q/4 slots stay on the shared-memory path) and at most q/2 + 1 offsets
+  {
+    int n_stage = 2;  // measured best on B200 (2: 46 %, 3: 44 %, 4: 41 %, 6: 34 %, 8: 30 % of HBM peak)
+    if (const char *e = std::getenv("YTTM_STAGES")) n_stage = std::max(2, std::min(MAX_STAGES, std::atoi(e)));
+    const uint32_t per_stage = (uint32_t)(tile_bytes / n_stage / 4) & ~3u;  // uint32 per stage
+    // tokens: q + q/4 + 8, offsets: q/2 + 16  ->  q * 1.75 + 24 <= per_stage
+    uint32_t q = (uint32_t)((per_stage - 24) / 1.75);
+    q &= ~15u;
+    c->loop_stages = n_stage;
+    c->loop_stream_q = q;
+    c->loop_stream_word_cap = (q / 2 + 16) & ~3u;
+    c->loop_stream_tok_cap = (per_stage - c->loop_stream_word_cap) & ~3u;
+  }
+  YT_CUDA(c, cudaFuncSetAttribute(merge_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+  int threads = 1024, per_sm = 0;
+  if (const char *e = std::getenv("YTTM_LOOP_THREADS")) threads = std::atoi(e);
+  YT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_loop_kernel, threads, dyn));
+  if (per_sm < 1) YT_FAIL(c, "merge_loop_kernel does not fit on an SM");
+  c->loop_threads = threads;
+  int blocks = std::min(c->n_sm, XQ_MAX_BLOCKS);
+  // A/B knob: fewer blocks make the two grid barriers and the winner reduce cheaper and the per-block partition /
+  // tile larger (the tile planner falls back to STREAMING by itself if the words no longer fit)
+  if (const char *e = std::getenv("YTTM_LOOP_BLOCKS")) blocks = std::max(1, std::min(blocks, std::atoi(e)));
+  if (c->xq_nblocks && (int)c->xq_nblocks != blocks) YT_FAIL(c, "merge loop geometry differs from the exchange buffer's");
+  c->loop_blocks = blocks;
+  return 0;
+}
+
+// Exchange buffer of the merge loop.  Entries per (sender, block) segment: YTTM_XQ_SEG_CAP (tests use tiny values
+// to reach the overflow -> rebuild path); a merge whose count changes do not fit is still applied to the words and
+// the table is rebuilt from them, so the capacity is a performance knob, not a limit.
+int xq_alloc(yttm_ctx *c, uint32_t me, uint32_t world) {
+  if (ensure_loop_geometry(c)) return 1;
+  uint32_t seg_cap = 8192;
+  if (const char *e = std::getenv("YTTM_XQ_SEG_CAP")) seg_cap = (uint32_t)std::max(4, std::atoi(e));
+  c->xq_world = world; c->xq_me = me; c->xq_seg_cap = seg_cap; c->xq_nblocks = (uint32_t)c->loop_blocks;
+  c->xq_per_sender = (sizeof(XqHdr) + (uint64_t)c->xq_nblocks * seg_cap * sizeof(uint4) + 255) / 256 * 256;
+  c->xq_bytes = 2ull * world * c->xq_per_sender;
+  YT_CUDA(c, c->xq_buf.reserve(c->xq_bytes));
+  YT_CUDA(c, c->xq_arrive.reserve(64));
+  // only the headers need clearing (sequence numbers start at 0, counts are rewritten every round)
+  for (uint32_t k = 0; k < 2 * world; k++)
+    YT_CUDA(c, cudaMemsetAsync(c->xq_buf.as<unsigned char>() + k * c->xq_per_sender, 0, sizeof(XqHdr), c->stream));
+  YT_CUDA(c, cudaMemsetAsync(c->xq_arrive.p, 0, 64, c->stream));
+  YT_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int d = 0; d < XQ_MAX_WORLD; d++) c->xq_peer[d] = nullptr;
+  c->xq_peer[me] = c->xq_buf.p;
+  c->xq_connected = world == 1;
+  return 0;
+}
+static unsigned long long xq_spin_limit_ns() {
+  if (const char *e = std::getenv("YTTM_XQ_TIMEOUT_MS")) return (unsigned long long)std::max(1, std::atoi(e)) * 1000000ull;
+  return 30ull * 1000000000ull;
+}
+int xq_args(yttm_ctx *c, LoopArgs *a) {
+  if (!c->xq_buf.p && xq_alloc(c, 0, 1)) return 1;
+  if (!c->xq_connected) YT_FAIL(c, "distributed training: yttm_train_dist_connect has not run");
+  for (int d = 0; d < XQ_MAX_WORLD; d++) a->xq.base[d] = static_cast<unsigned char *>(c->xq_peer[d < (int)c->xq_world ? d : (int)c->xq_me]);
+  a->xq.world = c->xq_world; a->xq.me = c->xq_me; a->xq.nblocks = c->xq_nblocks; a->xq.seg_cap = c->xq_seg_cap;
+  a->xq.per_sender = c->xq_per_sender;
+  a->spin_limit_ns = xq_spin_limit_ns();
+  return 0;
+}
+
+// capacity -> (partitions, slots per partition): one partition per loop block, R a power of two >= 16
+static void set_table_shape(yttm_ctx *c, uint64_t want_slots) {
+  const uint64_t parts = (uint64_t)c->loop_blocks;
+  const uint64_t R = std::max<uint64_t>(ytc::pow2ceil((want_slots + parts - 1) / parts), 16);
+  c->p_nparts = (uint32_t)parts;
+  c->p_rmask = (uint32_t)(R - 1);
+  c->pcap = parts * R;
+}
+
+// One attempt: clear a table of >= want_slots slots and histogram the local packed words into it; then, in a
+// multi-GPU job, one exchange round adds every other rank's pairs (all ranks run this in lockstep with the same
+// want_slots).  *ok: the table is usable (nothing dropped, load factor and fullest partition within bounds) — a
+// function of the key set and the shape only, hence the same verdict on every rank.
+static int build_table_once(yttm_ctx *c, uint64_t want_slots, bool *ok) {
+  set_table_shape(c, want_slots);
+  const uint64_t cap = c->pcap;
+  YT_CUDA(c, c->pkey.reserve(cap * 8));
+  YT_CUDA(c, c->pcnt.reserve(cap * 8));
+  YT_CUDA(c, cudaMemsetAsync(c->pkey.p, 0xff, cap * 8, c->stream));
+  YT_CUDA(c, cudaMemsetAsync(c->pcnt.p, 0, cap * 8, c->stream));
+  YtLoopCtl *ctl = c->ctl.as<YtLoopCtl>();
+  YT_CUDA(c, cudaMemsetAsync(&ctl->n_keys, 0, 8, c->stream));  // n_keys + overflow
+  YT_CUDA(c, cudaMemsetAsync(&ctl->xq_flags, 0, 8, c->stream));  // xq_flags + max_part_occ
+  if (c->n_words) {
+    pair_hist_kernel<<<grid_for(c, c->n_words, 256, 8), 256, 0, c->stream>>>(
+        c->tok[c->cur].as<uint32_t>(), c->off[c->cur].as<uint32_t>(), c->freq[c->cur].as<uint64_t>(), c->n_words,
+        tab_of(c));
+    c->launches++;
+  }
+  uint32_t peer_flags = 0;
+  if (c->xq_world > 1) {
+    LoopArgs a{};
+    if (xq_args(c, &a)) return 1;
+    a.tab = tab_of(c);
+    a.ctl = ctl;
+    uint32_t round = 0;
+    YT_CUDA(c, cudaMemcpyAsync(&round, &ctl->xq_round, 4, cudaMemcpyDeviceToHost, c->stream));
     YT_CUDA(c, cudaStreamSynchronize(c->stream));
-    // accept at load <= 3/8: the arg-max sweeps every slot every merge, so the table is kept tight
-    if (!h[1] && (uint64_t)h[0] * 200 <= cap * pair_max_load_pct()) { c->stats.n_pairs = h[0]; c->stats.table_capacity = cap; return 0; }
+    for (uint32_t chunk = 0;; chunk++) {  // every rank runs the same number of rounds: "more" is OR-ed over all senders
+      round += 1;
+      xq_publish_table_kernel<<<c->p_nparts, 256, 0, c->stream>>>(a, round, chunk, c->xq_arrive.as<unsigned int>());
+      xq_absorb_kernel<<<c->p_nparts, 256, (XQ_MAX_WORLD * XQ_MAX_BLOCKS + 4) * 4, c->stream>>>(a, round);
+      c->launches += 2;
+      uint32_t f = 0;
+      YT_CUDA(c, cudaMemcpyAsync(&f, &ctl->xq_flags, 4, cudaMemcpyDeviceToHost, c->stream));
+      YT_CUDA(c, cudaStreamSynchronize(c->stream));
+      peer_flags |= f;
+      if (!(f & XQF_MORE)) break;
+      if (chunk > 100000) YT_FAIL(c, "distributed table build: too many exchange rounds");
+      YT_CUDA(c, cudaMemsetAsync(&ctl->xq_flags, 0, 4, c->stream));
+    }
+  }
+  part_occ_kernel<<<c->p_nparts, 256, 0, c->stream>>>(tab_of(c), &ctl->max_part_occ);
+  c->launches++;
+  YT_CUDA(c, cudaGetLastError());
+  uint32_t h[2], g[2];
+  YT_CUDA(c, cudaMemcpyAsync(h, &ctl->n_keys, 8, cudaMemcpyDeviceToHost, c->stream));
+  YT_CUDA(c, cudaMemcpyAsync(g, &ctl->xq_flags, 8, cudaMemcpyDeviceToHost, c->stream));
+  YT_CUDA(c, cudaStreamSynchronize(c->stream));
+  peer_flags |= g[0];
+  const uint64_t R = (uint64_t)c->p_rmask + 1;
+  // local overflow is rank-specific, but it reaches every rank as XQF_OVERFLOW of this rank's round
+  *ok = !h[1] && !(peer_flags & XQF_OVERFLOW) && (uint64_t)h[0] * 200 <= cap * pair_max_load_pct() &&
+        (uint64_t)g[1] * 4 <= R * 3;
+  if (*ok) { c->stats.n_pairs = h[0]; c->stats.table_capacity = cap; }
+  return 0;
+}
+
+// (Re)build the pair table from the current packed words: grows it until build_table_once accepts.
+int ensure_ctl(yttm_ctx *c) {
+  if (c->ctl.p) return 0;
+  YT_CUDA(c, c->ctl.reserve(sizeof(YtLoopCtl)));
+  YT_CUDA(c, cudaMemsetAsync(c->ctl.p, 0, sizeof(YtLoopCtl), c->stream));
+  return 0;
+}
+int rebuild_pair_table(yttm_ctx *c, uint64_t min_cap) {
+  if (ensure_loop_geometry(c)) return 1;
+  if (ensure_ctl(c)) return 1;
+  uint64_t cap = std::max<uint64_t>(ytc::pow2ceil(min_cap), pair_cap_floor());
+  for (int attempt = 0; attempt < 28; attempt++) {
+    bool ok = false;
+    if (build_table_once(c, cap, &ok)) return 1;
+    if (ok) return 0;
     cap *= 2;
   }
-  YT_FAIL(c, "pair table: could not reach load factor 3/8");
+  YT_FAIL(c, "pair table: could not reach the target load factor");
 }
 
 // Compact the packed words into the other buffer set.
@@ -601,7 +781,9 @@ void yttm_ctx_destroy(yttm_ctx *c) {
   ytc::DevBuf *bufs[] = {&c->text_buf, &c->hist, &c->cp2id, &c->wkey, &c->wcnt, &c->wpos, &c->wfreq, &c->wlen,
                          &c->scan_tmp, &c->counters, &c->tok[0], &c->tok[1], &c->off[0], &c->off[1], &c->freq[0],
                          &c->freq[1], &c->pkey, &c->pcnt, &c->scratch_key, &c->scratch_cnt, &c->ctl, &c->blockbest, &c->tiles, &c->defer,
-                         &c->d_rules, &c->d_rfreq};
+                         &c->d_rules, &c->d_rfreq, &c->xq_arrive, &c->xq_buf};
+  for (int d = 0; d < 8; d++)
+    if (c->xq_peer_ipc[d] && c->xq_peer[d]) { cudaIpcCloseMemHandle(c->xq_peer[d]); c->xq_peer[d] = nullptr; }
   for (auto *b : bufs) b->release();
   for (auto &kv : c->timers) { if (kv.second.a) cudaEventDestroy(kv.second.a); if (kv.second.b) cudaEventDestroy(kv.second.b); }
   cudaStreamDestroy(c->stream);
@@ -611,9 +793,9 @@ void yttm_ctx_destroy(yttm_ctx *c) {
 const char *yttm_last_error(const yttm_ctx *c) { return c ? c->err.c_str() : g_yttm_create_error.c_str(); }
 
 double yttm_stage_ms(const yttm_ctx *c, const char *stage) {
-  static const char *ph[] = {"loop_argmax", "loop_barrier1", "loop_apply", "loop_barrier2",
-                             "loop_apply_blkmax", "loop_apply_blkmean", "loop_predrain_blkmax"};
-  for (int i = 0; i < 7; i++)
+  static const char *ph[] = {"loop_drain", "loop_argmax", "loop_barrier1", "loop_apply", "loop_barrier2",
+                             "loop_apply_blkmax", "loop_apply_blkmean", "loop_drain_blkmax"};
+  for (int i = 0; i < 8; i++)
     if (!std::strcmp(stage, ph[i])) return c->loop_phase_ms[i];
   if (!std::strcmp(stage, "loop_iters")) return (double)c->loop_iters;
   if (!std::strcmp(stage, "loop_launches")) return (double)c->loop_relaunches;
@@ -770,17 +952,19 @@ static int finish_build(yttm_ctx *c, yttm_train_stats *stats) {
   return 0;
 }
 
-int yttm_train_build(yttm_ctx *c, yttm_train_stats *stats) {
-  YT_CUDA(c, cudaSetDevice(c->device));
-  if (!c->have_alphabet) YT_FAIL(c, "yttm_train_build: alphabet not set");
+// Phase 2a: word split + dedup of the current text -> wpos / wfreq (U unique words).  list != nullptr: the text is a
+// list of weighted words received from the other ranks (n_src sources, source k = words [word_off[k], word_off[k+1])
+// whose positions are relative to byte_off[k]).
+struct WordList { const uint64_t *pos, *freq; const uint64_t *word_off, *byte_off; uint32_t n_src; };
+static int build_word_table(yttm_ctx *c, const WordList *list, uint64_t *n_unique) {
   const uint64_t n = c->n_text;
   YT_CUDA(c, c->counters.reserve(64));
   auto *counters = c->counters.as<unsigned long long>();
-  // ---- word split + dedup (retry with a larger table on overflow)
   ytc::timer_begin(c, "word_count");
-  uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(ytc::pow2ceil(n / 16 + 1), 1u << 16), 1ull << 26);
+  const uint64_t guess = list ? list->word_off[list->n_src] * 2 + 1 : n / 16 + 1;
+  uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(ytc::pow2ceil(guess), 1u << 16), 1ull << 26);
   unsigned long long h_cnt[4] = {0, 0, 0, 0};
-  for (int attempt = 0;; attempt++) {
+  for (int attempt = 0;; attempt++) {  // retry with a larger table on overflow
     if (attempt > 10) YT_FAIL(c, "word table: too many retries");
     YT_CUDA(c, c->wkey.reserve(cap * 8));
     YT_CUDA(c, c->wcnt.reserve(cap * 8));
@@ -788,7 +972,15 @@ int yttm_train_build(yttm_ctx *c, yttm_train_stats *stats) {
     YT_CUDA(c, cudaMemsetAsync(c->wcnt.p, 0, cap * 8, c->stream));
     YT_CUDA(c, cudaMemsetAsync(counters, 0, 64, c->stream));
     WordTab wt{c->wkey.as<unsigned long long>(), c->wcnt.as<unsigned long long>(), cap - 1};
-    if (n) {
+    if (list) {
+      for (uint32_t k = 0; k < list->n_src; k++) {
+        const uint64_t w0 = list->word_off[k], nw = list->word_off[k + 1] - w0;
+        if (!nw) continue;
+        word_insert_list_kernel<<<grid_for(c, nw, 256, 8), 256, 0, c->stream>>>(c->d_text, n, list->byte_off[k], list->pos + w0,
+                                                                              list->freq + w0, nw, wt, counters, cap / 2);
+        c->launches++;
+      }
+    } else if (n) {
       word_insert_kernel<<<grid_for(c, n, 256, 8), 256, 0, c->stream>>>(c->d_text, n, wt, counters, cap / 2);
       c->launches++;
     }
@@ -799,7 +991,7 @@ int yttm_train_build(yttm_ctx *c, yttm_train_stats *stats) {
     cap *= 4;
   }
   c->n_word_occ = h_cnt[0];
-  uint64_t U = h_cnt[1];
+  const uint64_t U = h_cnt[1];
   YT_CUDA(c, c->wpos.reserve((U + 1) * 8));
   YT_CUDA(c, c->wfreq.reserve((U + 1) * 8));
   if (U) {
@@ -810,7 +1002,15 @@ int yttm_train_build(yttm_ctx *c, yttm_train_stats *stats) {
   }
   ytc::timer_end(c, "word_count");
   YT_CUDA(c, cudaGetLastError());
-  // ---- tokenise the unique words into the packed buffer
+  *n_unique = U;
+  c->n_unique = U;
+  return 0;
+}
+
+// Phase 2b + 3: tokenise the U unique words (wpos / wfreq) into the packed buffer, build the pair table.
+static int build_tokens(yttm_ctx *c, uint64_t U, yttm_train_stats *stats) {
+  const uint64_t n = c->n_text;
+  auto *counters = c->counters.as<unsigned long long>();
   ytc::timer_begin(c, "tokenise");
   YT_CUDA(c, c->wlen.reserve((U + 1) * 8));
   ytc::DevBuf &scanb = c->scratch_key;
@@ -846,6 +1046,151 @@ int yttm_train_build(yttm_ctx *c, yttm_train_stats *stats) {
   if (compact_words(c)) return 1;
   ytc::timer_end(c, "tokenise");
   return finish_build(c, stats);
+}
+
+int yttm_train_build(yttm_ctx *c, yttm_train_stats *stats) {
+  YT_CUDA(c, cudaSetDevice(c->device));
+  if (!c->have_alphabet) YT_FAIL(c, "yttm_train_build: alphabet not set");
+  uint64_t U = 0;
+  if (build_word_table(c, nullptr, &U)) return 1;
+  return build_tokens(c, U, stats);
+}
+
+// ---- multi-GPU (one process per GPU; include/yttm_b200.h has the protocol) ---------------------------------------
+struct XqHandle {  // what yttm_train_dist_handle writes (128 bytes)
+  uint64_t magic, pid, ptr, bytes;
+  int32_t device, pad;
+  cudaIpcMemHandle_t ipc;
+};
+static_assert(sizeof(XqHandle) <= 128, "XqHandle must fit the 128-byte slot of the C ABI");
+constexpr uint64_t XQ_MAGIC = 0x3151585f4d545459ull;
+
+int yttm_train_dist_init(yttm_ctx *c, uint32_t rank, uint32_t world, void *handle_out) {
+  YT_CUDA(c, cudaSetDevice(c->device));
+  if (world < 1 || world > (uint32_t)XQ_MAX_WORLD || rank >= world) YT_FAIL(c, "yttm_train_dist_init: world must be 1..8, rank < world");
+  if (ensure_ctl(c)) return 1;
+  YT_CUDA(c, cudaMemsetAsync(c->ctl.p, 0, sizeof(YtLoopCtl), c->stream));  // exchange rounds restart at 0 on every rank
+  if (xq_alloc(c, rank, world)) return 1;
+  XqHandle h{};
+  h.magic = XQ_MAGIC; h.pid = (uint64_t)getpid(); h.ptr = (uint64_t)(uintptr_t)c->xq_buf.p; h.bytes = c->xq_bytes;
+  h.device = c->device;
+  if (world > 1) YT_CUDA(c, cudaIpcGetMemHandle(&h.ipc, c->xq_buf.p));
+  std::memset(handle_out, 0, 128);
+  std::memcpy(handle_out, &h, sizeof(h));
+  return 0;
+}
+
+int yttm_train_dist_connect(yttm_ctx *c, const void *handles) {
+  YT_CUDA(c, cudaSetDevice(c->device));
+  if (!c->xq_buf.p) YT_FAIL(c, "yttm_train_dist_connect: yttm_train_dist_init has not run");
+  for (uint32_t d = 0; d < c->xq_world; d++) {
+    if (d == c->xq_me) continue;
+    XqHandle h;
+    std::memcpy(&h, static_cast<const unsigned char *>(handles) + 128 * d, sizeof(h));
+    if (h.magic != XQ_MAGIC || h.bytes != c->xq_bytes) YT_FAIL(c, "yttm_train_dist_connect: bad handle (ranks disagree on the geometry?)");
+    if (h.pid == (uint64_t)getpid()) {  // same process (tests, one thread per GPU): the pointer itself, peer access on
+      if (h.device != c->device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) YT_CUDA(c, e);
+        (void)cudaGetLastError();
+      }
+      c->xq_peer[d] = reinterpret_cast<void *>((uintptr_t)h.ptr);
+      c->xq_peer_ipc[d] = false;
+    } else {
+      void *p = nullptr;
+      YT_CUDA(c, cudaIpcOpenMemHandle(&p, h.ipc, cudaIpcMemLazyEnablePeerAccess));
+      c->xq_peer[d] = p;
+      c->xq_peer_ipc[d] = true;
+    }
+  }
+  c->xq_connected = true;
+  return 0;
+}
+
+int yttm_train_dist_word_table(yttm_ctx *c, uint64_t *n_unique) {
+  YT_CUDA(c, cudaSetDevice(c->device));
+  return build_word_table(c, nullptr, n_unique);
+}
+
+int yttm_train_dist_export_words(yttm_ctx *c, uint64_t *bytes_per_dst, uint64_t *words_per_dst, void **d_bytes,
+                                 void **d_pos, void **d_freq) {
+  YT_CUDA(c, cudaSetDevice(c->device));
+  const uint32_t world = c->xq_world;
+  const uint64_t U = c->n_unique;
+  YT_CUDA(c, c->counters.reserve(64));
+  ytc::DevBuf &cur = c->scan_tmp;  // 3 x world cursors
+  YT_CUDA(c, cur.reserve(3 * 8 * XQ_MAX_WORLD));
+  auto *cb = cur.as<unsigned long long>(), *cw = cb + XQ_MAX_WORLD, *base = cw + XQ_MAX_WORLD;
+  YT_CUDA(c, cudaMemsetAsync(cb, 0, 3 * 8 * XQ_MAX_WORLD, c->stream));
+  const unsigned grid = (unsigned)grid_for(c, std::max<uint64_t>(U, 1), 256, 8);
+  if (U) {
+    word_export_kernel<0><<<grid, 256, 0, c->stream>>>(c->d_text, c->n_text, c->wpos.as<uint64_t>(), c->wfreq.as<uint64_t>(), U,
+                                                       world, cb, cw, nullptr, nullptr, nullptr, nullptr);
+    c->launches++;
+  }
+  unsigned long long hb[2 * XQ_MAX_WORLD];
+  YT_CUDA(c, cudaMemcpyAsync(hb, cb, sizeof(hb), cudaMemcpyDeviceToHost, c->stream));
+  YT_CUDA(c, cudaStreamSynchronize(c->stream));
+  unsigned long long bb[XQ_MAX_WORLD], wb[XQ_MAX_WORLD], tb = 0, tw = 0;
+  for (uint32_t d = 0; d < world; d++) {
+    bytes_per_dst[d] = hb[d]; words_per_dst[d] = hb[XQ_MAX_WORLD + d];
+    bb[d] = tb; wb[d] = tw; tb += hb[d]; tw += hb[XQ_MAX_WORLD + d];
+  }
+  // the export buffers reuse table scratch that the word phase no longer needs
+  YT_CUDA(c, c->scratch_key.reserve(tb + 64));
+  YT_CUDA(c, c->scratch_cnt.reserve((tw + 1) * 8));
+  YT_CUDA(c, c->wlen.reserve((tw + 1) * 8));
+  YT_CUDA(c, cudaMemcpyAsync(cb, bb, 8 * world, cudaMemcpyHostToDevice, c->stream));
+  YT_CUDA(c, cudaMemcpyAsync(cw, wb, 8 * world, cudaMemcpyHostToDevice, c->stream));
+  YT_CUDA(c, cudaMemcpyAsync(base, bb, 8 * world, cudaMemcpyHostToDevice, c->stream));
+  if (U) {
+    word_export_kernel<1><<<grid, 256, 0, c->stream>>>(c->d_text, c->n_text, c->wpos.as<uint64_t>(), c->wfreq.as<uint64_t>(), U,
+                                                       world, cb, cw, base, c->scratch_key.as<uint8_t>(),
+                                                       c->scratch_cnt.as<uint64_t>(), c->wlen.as<uint64_t>());
+    c->launches++;
+  }
+  YT_CUDA(c, cudaGetLastError());
+  YT_CUDA(c, cudaStreamSynchronize(c->stream));
+  *d_bytes = c->scratch_key.p; *d_pos = c->scratch_cnt.p; *d_freq = c->wlen.p;
+  return 0;
+}
+
+int yttm_train_dist_import_words(yttm_ctx *c, const void *d_bytes, const uint64_t *bytes_per_src, const void *d_pos,
+                                 const void *d_freq, const uint64_t *words_per_src, yttm_train_stats *stats) {
+  YT_CUDA(c, cudaSetDevice(c->device));
+  if (!c->have_alphabet) YT_FAIL(c, "yttm_train_dist_import_words: alphabet not set");
+  const uint32_t world = c->xq_world;
+  uint64_t bo[XQ_MAX_WORLD + 1], wo[XQ_MAX_WORLD + 1];
+  bo[0] = wo[0] = 0;
+  for (uint32_t k = 0; k < world; k++) { bo[k + 1] = bo[k] + bytes_per_src[k]; wo[k + 1] = wo[k] + words_per_src[k]; }
+  const uint64_t n = bo[world], nw = wo[world];
+  if (n >= POS_MASK) YT_FAIL(c, "imported words too large");
+  // the received words become this rank's text (its own shard is no longer needed)
+  ytc::DevBuf fresh;
+  YT_CUDA(c, fresh.reserve(n + 64));
+  uint8_t *tb = fresh.as<uint8_t>();
+  YT_CUDA(c, cudaMemsetAsync(tb, ' ', 16, c->stream));
+  YT_CUDA(c, cudaMemsetAsync(tb + 16 + n, ' ', 32, c->stream));
+  if (n) YT_CUDA(c, cudaMemcpyAsync(tb + 16, d_bytes, n, cudaMemcpyDeviceToDevice, c->stream));
+  ytc::DevBuf lp, lf;  // private copies: the caller's buffers may be the export scratch of this context
+  YT_CUDA(c, lp.reserve((nw + 1) * 8));
+  YT_CUDA(c, lf.reserve((nw + 1) * 8));
+  if (nw) {
+    YT_CUDA(c, cudaMemcpyAsync(lp.p, d_pos, nw * 8, cudaMemcpyDeviceToDevice, c->stream));
+    YT_CUDA(c, cudaMemcpyAsync(lf.p, d_freq, nw * 8, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  YT_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->text_buf.release();
+  c->text_buf = fresh;
+  c->d_text = tb + 16;
+  c->n_text = n;
+  c->text_external = false;
+  WordList wl{lp.as<uint64_t>(), lf.as<uint64_t>(), wo, bo, world};
+  uint64_t U = 0;
+  int rc = build_word_table(c, &wl, &U);
+  if (!rc) rc = build_tokens(c, U, stats);
+  lp.release(); lf.release();
+  return rc;
 }
 
 int yttm_train_export_words(yttm_ctx *c, uint32_t *tokens, uint64_t tokens_cap, uint32_t *offsets, uint64_t *freq,
@@ -912,7 +1257,8 @@ int yttm_train_scan_once(yttm_ctx *c, double *ms, uint64_t *algo_bytes) {
   PairTab t;
   t.keys = c->scratch_key.as<unsigned long long>();
   t.cnts = c->scratch_cnt.as<unsigned long long>();
-  t.mask = cap - 1;
+  t.rmask = c->p_rmask;
+  t.nparts = c->p_nparts;
   t.n_keys = reinterpret_cast<uint32_t *>(c->counters.as<unsigned long long>() + 6);
   t.overflow = t.n_keys + 1;
   ytc::timer_begin(c, "scan");
@@ -958,46 +1304,7 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
   if (!c->pcap) YT_FAIL(c, "yttm_train_run: yttm_train_build has not run");
   *n_done_out = 0;
   if (max_merges == 0) return 0;
-  // launch geometry of the cooperative kernel: one 1024-thread block per SM, all co-resident,
-  // with (almost) all of the SM's shared memory as the tile buffer
-  if (!c->loop_blocks) {
-    int optin = 0;
-    YT_CUDA(c, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-    int dyn = optin - 4096;  // static shared memory of the kernel (3.4 KB) + margin
-    if (dyn < 64 * 1024) YT_FAIL(c, "merge_loop_kernel: not enough shared memory per block");
-    c->loop_smem = dyn;
-    const int tile_bytes = dyn - 32 * UQ_CAP * 16 - 2 * CLAIM_WORDS * 4;         // minus update queues and claim bitmap
-    // RESIDENT tile: per word 4 B offset + 8 B frequency (kept in shared memory too, so a rewritten
-    // word costs no L2 round trip for its frequency), the rest token slots
-    c->loop_word_cap = std::min<uint32_t>((uint32_t)(tile_bytes / 24 - 2), CLAIM_WORDS * 32 - 1) & ~1u;
-    c->loop_tok_cap = (uint32_t)((tile_bytes - 12 * (c->loop_word_cap + 2)) / 4) & ~3u;
-    // STREAMING: n_stage stages; a stage holds a window of q slots plus the overhang of its last
-    // word (words of up to q/4 slots stay on the shared-memory path) and at most q/2 + 1 offsets
-    {
-      int n_stage = 2;  // measured best on B200 (2: 46 %, 3: 44 %, 4: 41 %, 6: 34 %, 8: 30 % of HBM peak)
-      if (const char *e = std::getenv("YTTM_STAGES")) n_stage = std::max(2, std::min(MAX_STAGES, std::atoi(e)));
-
-      const uint32_t per_stage = (uint32_t)(tile_bytes / n_stage / 4) & ~3u;  // uint32 per stage
-      // tokens: q + q/4 + 8, offsets: q/2 + 16  ->  q * 1.75 + 24 <= per_stage
-      uint32_t q = (uint32_t)((per_stage - 24) / 1.75);
-      q &= ~15u;
-      c->loop_stages = n_stage;
-      c->loop_stream_q = q;
-      c->loop_stream_word_cap = (q / 2 + 16) & ~3u;
-      c->loop_stream_tok_cap = (per_stage - c->loop_stream_word_cap) & ~3u;
-    }
-    YT_CUDA(c, cudaFuncSetAttribute(merge_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-    YT_CUDA(c, cudaFuncSetAttribute(merge_loop_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-    int threads = 1024, per_sm = 0;
-    if (const char *e = std::getenv("YTTM_LOOP_THREADS")) threads = std::atoi(e);
-    YT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_loop_kernel, threads, dyn));
-    if (per_sm < 1) YT_FAIL(c, "merge_loop_kernel does not fit on an SM");
-    c->loop_threads = threads;
-    c->loop_blocks = c->n_sm;
-    // A/B knob: fewer blocks make the two grid barriers and the winner reduce cheaper and the per-block sweep /
-    // tile longer (the tile planner falls back to STREAMING by itself if the words no longer fit)
-    if (const char *e = std::getenv("YTTM_LOOP_BLOCKS")) c->loop_blocks = std::max(1, std::min(c->n_sm, std::atoi(e)));
-  }
+  if (ensure_loop_geometry(c)) return 1;
   YT_CUDA(c, c->blockbest.reserve((size_t)c->loop_blocks * 4 * 8));
   YT_CUDA(c, c->d_rules.reserve((size_t)max_merges * 12 + 16));
   YT_CUDA(c, c->d_rfreq.reserve((size_t)max_merges * 8 + 16));
@@ -1005,15 +1312,16 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
   YtLoopCtl h{};
   YT_CUDA(c, cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   YT_CUDA(c, cudaStreamSynchronize(c->stream));
-  h.n_done = 0; h.stop = 0; h.iters = 0;
+  h.n_done = 0; h.stop = 0; h.stop_why = 0; h.iters = 0;
   for (int i = 0; i < 8; i++) h.t_phase[i] = 0;
   for (int i = 0; i < 6; i++) (&h.blk[0][0])[i] = 0;
   YT_CUDA(c, cudaMemcpyAsync(ctl, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
   c->loop_relaunches = 0;
   ytc::timer_begin(c, "merge_loop");
   while (h.n_done < max_merges && h.stop != 1) {
-    LoopArgs a;
+    LoopArgs a{};
     if (plan_tiles(c, &a)) return 1;
+    if (xq_args(c, &a)) return 1;
     a.tok = c->tok[c->cur].as<uint32_t>();
     a.off = c->off[c->cur].as<uint32_t>();
     a.freq = c->freq[c->cur].as<uint64_t>();
@@ -1027,34 +1335,35 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
     a.max_total = max_merges;
     a.max_iters = max_merges;
     a.key_limit = (uint32_t)std::min<uint64_t>(c->pcap / 100 * pair_max_load_pct() + c->pcap % 100 * pair_max_load_pct() / 100,
-                                               0xfffffff0ull);  // rebuild above load 3/4 (default)
-    const bool wide = std::getenv("YTTM_LOOP_WIDEPROBE") != nullptr;  // experimental, see pair_add(PairTabWide)
-    c->timers["loop_variant"].ms = wide ? 1.f : 0.f;                   // yttm_stage_ms(ctx, "loop_variant")
+                                               0xfffffff0ull);  // rebuild above this load (default 1/2)
 #ifndef YT_SIMT_EMU
     void *args[] = {&a};
-    YT_CUDA(c, cudaLaunchCooperativeKernel(wide ? (void *)merge_loop_wide_kernel : (void *)merge_loop_kernel,
-                                           dim3(c->loop_blocks), dim3(c->loop_threads), args, (size_t)c->loop_smem, c->stream));
+    YT_CUDA(c, cudaLaunchCooperativeKernel((void *)merge_loop_kernel, dim3(c->loop_blocks), dim3(c->loop_threads), args,
+                                           (size_t)c->loop_smem, c->stream));
 #else  // tests/emul/simt: every block on its own OS thread, grid.sync() = pthread barrier
     emu::launch_cooperative((unsigned)c->loop_blocks, (unsigned)c->loop_threads, (size_t)c->loop_smem,
-                            [=]() { if (wide) merge_loop_wide_kernel(a); else merge_loop_kernel(a); });
+                            [=]() { merge_loop_kernel(a); });
 #endif
     c->launches++;
     YT_CUDA(c, cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     YT_CUDA(c, cudaStreamSynchronize(c->stream));
     c->loop_relaunches++;
     if (h.stop == 1 || h.n_done >= max_merges) break;
-    // stop == 3: compaction wanted; stop == 2: table wants a rebuild
-    uint32_t why = h.overflow ? 2u : h.stop;  // an overflowed table lost updates: rebuild it from the tokens
+    if (h.stop != 2 && h.stop != 3) YT_FAIL(c, "merge loop left without a reason (internal error)");
+    // stop == 3: compaction wanted (by some rank); stop == 2: the table wants a rebuild.  Every rank of a job
+    // leaves at the same merge for the same reason (merge_loop.cuh), so the steps below run in lockstep.
+    const uint32_t why = h.stop, reason = h.stop_why;
     if (compact_words(c)) return 1;
     if (why == 2) {
-      uint32_t keep_done = h.n_done;
-      // dead keys vanish in the rebuild, so the table usually keeps its size (it grows only if still above 3/8)
-      if (rebuild_pair_table(c, std::max<uint64_t>(h.overflow ? c->pcap * 2 : c->pcap / 2, pair_cap_floor()))) return 1;
-      h.n_done = keep_done;
-      YT_CUDA(c, cudaMemcpyAsync(&h.n_keys, &ctl->n_keys, 8, cudaMemcpyDeviceToHost, c->stream));
+      const uint32_t keep_done = h.n_done;
+      // dead keys vanish in the rebuild, so the table usually keeps its size; it grows when a partition filled up
+      const uint64_t want = (reason & 5u) ? c->pcap * 2 : c->pcap / 2;
+      if (rebuild_pair_table(c, std::max<uint64_t>(want, pair_cap_floor()))) return 1;
+      YT_CUDA(c, cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
       YT_CUDA(c, cudaStreamSynchronize(c->stream));
+      h.n_done = keep_done;
     }
-    h.stop = 0; h.dead = 0; h.slots = c->n_slots;
+    h.stop = 0; h.stop_why = 0; h.overflow = 0; h.dead = 0; h.slots = c->n_slots;
     YT_CUDA(c, cudaMemcpyAsync(ctl, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
   }
   ytc::timer_end(c, "merge_loop");
