@@ -77,6 +77,11 @@ def bind(L):
         "yttm_train_build": (i32, [vp, vp]),
         "yttm_train_export_words": (i32, [vp, vp, u64, vp, vp, u64, C.POINTER(u64), C.POINTER(u64)]),
         "yttm_train_import_words": (i32, [vp, vp, u64, vp, vp, u64, vp]),
+        "yttm_train_dist_init": (i32, [vp, C.c_uint32, C.c_uint32, vp]),
+        "yttm_train_dist_connect": (i32, [vp, vp]),
+        "yttm_train_dist_word_table": (i32, [vp, C.POINTER(u64)]),
+        "yttm_train_dist_export_words": (i32, [vp, vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+        "yttm_train_dist_import_words": (i32, [vp, vp, vp, vp, vp, vp, vp]),
         "yttm_train_run": (i32, [vp, C.c_uint32, C.c_uint32, vp, vp, C.POINTER(C.c_uint32)]),
         "yttm_train_dump_pairs": (i32, [vp, vp, vp, u64, C.POINTER(u64)]),
         "yttm_train_scan_once": (i32, [vp, C.POINTER(dbl), C.POINTER(u64)]),
@@ -98,7 +103,8 @@ EXPORTED_SYMBOLS_DEVICE_ABI = [
     "yttm_ctx_create", "yttm_ctx_destroy", "yttm_last_error", "yttm_device_count", "yttm_stage_ms",
     "yttm_launch_count", "yttm_train_load_corpus", "yttm_train_char_hist", "yttm_train_get_char_hist",
     "yttm_train_char_hist_devptr", "yttm_train_char_hist_refresh", "yttm_train_set_alphabet", "yttm_train_build",
-    "yttm_train_export_words", "yttm_train_import_words", "yttm_train_run", "yttm_train_dump_pairs",
+    "yttm_train_export_words", "yttm_train_import_words", "yttm_train_dist_init", "yttm_train_dist_connect",
+    "yttm_train_dist_word_table", "yttm_train_dist_export_words", "yttm_train_dist_import_words", "yttm_train_run", "yttm_train_dump_pairs",
     "yttm_train_scan_once", "yttm_train_synth_words", "yttm_enc_create", "yttm_enc_destroy", "yttm_enc_run",
     "yttm_enc_run_device",
 ]

@@ -590,10 +590,18 @@ static int build_table_once(yttm_ctx *c, uint64_t want_slots, bool *ok) {
     a.ctl = ctl;
     uint32_t round = 0;
     YT_CUDA(c, cudaMemcpyAsync(&round, &ctl->xq_round, 4, cudaMemcpyDeviceToHost, c->stream));
+    // the rounds publish a SNAPSHOT of the local histogram: absorbing the peers' pairs changes the table itself
+    YT_CUDA(c, c->scratch_key.reserve(cap * 8));
+    YT_CUDA(c, c->scratch_cnt.reserve(cap * 8));
+    YT_CUDA(c, cudaMemcpyAsync(c->scratch_key.p, c->pkey.p, cap * 8, cudaMemcpyDeviceToDevice, c->stream));
+    YT_CUDA(c, cudaMemcpyAsync(c->scratch_cnt.p, c->pcnt.p, cap * 8, cudaMemcpyDeviceToDevice, c->stream));
     YT_CUDA(c, cudaStreamSynchronize(c->stream));
+    LoopArgs snap = a;
+    snap.tab.keys = c->scratch_key.as<unsigned long long>();
+    snap.tab.cnts = c->scratch_cnt.as<unsigned long long>();
     for (uint32_t chunk = 0;; chunk++) {  // every rank runs the same number of rounds: "more" is OR-ed over all senders
       round += 1;
-      xq_publish_table_kernel<<<c->p_nparts, 256, 0, c->stream>>>(a, round, chunk, c->xq_arrive.as<unsigned int>());
+      xq_publish_table_kernel<<<c->p_nparts, 256, 0, c->stream>>>(snap, round, chunk, c->xq_arrive.as<unsigned int>());
       xq_absorb_kernel<<<c->p_nparts, 256, (XQ_MAX_WORLD * XQ_MAX_BLOCKS + 4) * 4, c->stream>>>(a, round);
       c->launches += 2;
       uint32_t f = 0;

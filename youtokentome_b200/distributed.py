@@ -4,13 +4,7 @@ Encode shards by sentence: contiguous ranges balanced by bytes, NO collective on
 (`shard_sentences`, `encode_sharded`).
 
 Training shards the corpus by byte range cut at ASCII spaces exactly as the reference cuts it
-between threads (bpe.cpp:864-873): every rank runs the two byte passes (code point histogram,
-word split + dedup) on its shard on its own GPU; the dense uint64 histogram is sum-allreduced
-in place in device memory (NCCL), the unique words of all ranks are all-gathered (duplicates
-across ranks are harmless — every statistic is additive in the word frequency, the same reason
-the reference can sum per-thread maps, bpe.cpp:1029-1039) and the merge loop then runs
-replicated on every rank: at L2/SMEM-resident sizes it is latency-bound (two grid barriers per
-merge), so splitting it would only add a per-merge collective.
+between threads (bpe.cpp:864-873); see train_distributed.
 """
 import ctypes as C
 
@@ -111,71 +105,176 @@ def encode_sharded(bpe, data, offsets, group=None, **kw):
     return lo, hi, ids, oo
 
 
-def train_distributed(data, model_path, vocab_size, coverage=1.0, pad_id=0, unk_id=1, bos_id=2, eos_id=3, group=None):
-    """Data-parallel training over the ranks of `group` (NCCL).  `data` is the WHOLE corpus as
-    bytes on every rank (each rank only uploads its own byte range).  Rank 0 writes the model."""
-    import torch
-    import torch.distributed as dist
-    from . import _lib
-    L = _lib.lib()
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
-    pos = split_byte_ranges(data, world)
-    shard = data[pos[rank]:pos[rank + 1]]
-    ctx = C.c_void_p()
-    if L.yttm_ctx_create(torch.cuda.current_device(), C.byref(ctx)) != 0:
-        raise ValueError(L.yttm_last_error(None).decode())
+def check_config(vocab_size, coverage, pad_id, unk_id, bos_id, eos_id):
+    """check_config of the reference (bpe.cpp:1295-1350), same texts; raises ValueError."""
+    if coverage <= 0 or coverage > 1:
+        raise ValueError("coverage value must be in the range (0, 1]. Current value of coverage = %f" % coverage)
+    if unk_id < 0 or unk_id >= vocab_size:
+        raise ValueError("unk_id: must be in the range [0, vocab_size - 1]. Current value of vocab_size = %d; unk_id = %d"
+                         % (vocab_size, unk_id))
+    for name, v, sep in (("pad_id", pad_id, ";"), ("bos_id", bos_id, ";"), ("eos_id", eos_id, "")):
+        if v < -1 or v >= vocab_size:
+            raise ValueError("%s must be in the range [-1, vocab_size - 1]. Current value of vocab_size = %d%s %s = %d"
+                             % (name, vocab_size, sep, name, v))
+    ids = [unk_id] + [v for v in (pad_id, bos_id, eos_id) if v != -1]
+    if len(set(ids)) != len(ids):
+        raise ValueError("All ids of special tokens must be different.")
 
-    def check(rc):
-        if rc != 0:
-            raise ValueError(L.yttm_last_error(ctx).decode())
+
+class TorchComm:
+    """The collectives train_distributed needs, over torch.distributed (NCCL on the GPUs; plumbing only — the per-merge
+    exchange of the merge loop is NOT here, it is peer stores inside the kernel, csrc/merge_loop.cuh)."""
+
+    def __init__(self, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+
+    def all_gather_bytes(self, b):
+        t = self.torch.frombuffer(bytearray(b), dtype=self.torch.uint8).to(self.dev)
+        out = [self.torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t, group=self.group)
+        return b"".join(bytes(o.cpu().numpy().tobytes()) for o in out)
+
+    def allreduce_sum_u64(self, ptr, n):
+        t = self.torch.as_tensor(_DevView(ptr, n, "<i8"), device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        self.torch.cuda.synchronize()
+
+    def agree(self, ok):
+        """False on every rank if any rank says False (a failure must not leave the others inside a collective)."""
+        t = self.torch.tensor([1 if ok else 0], dtype=self.torch.int32, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
+        return bool(t.item())
+
+    def all_to_all(self, ptr, counts, itemsize):
+        """counts[d] items of `itemsize` bytes go to rank d (device buffer at ptr, destinations back to back).
+        Returns (received tensor kept alive by the caller, its device pointer, counts per source)."""
+        torch, dist = self.torch, self.dist
+        send_n = torch.tensor([int(c) for c in counts], dtype=torch.int64, device=self.dev)
+        recv_n = torch.zeros_like(send_n)
+        dist.all_to_all_single(recv_n, send_n, group=self.group)
+        recv = [int(x) for x in recv_n.tolist()]
+        total = int(sum(int(c) for c in counts)) * itemsize
+        src = torch.as_tensor(_DevView(ptr, max(total, 1), "|u1"), device=self.dev)[:total]
+        out = torch.empty(max(sum(recv) * itemsize, 1), dtype=torch.uint8, device=self.dev)
+        dist.all_to_all_single(out[:sum(recv) * itemsize], src, [r * itemsize for r in recv],
+                               [int(c) * itemsize for c in counts], group=self.group)
+        torch.cuda.synchronize()
+        return out, out.data_ptr(), recv
+
+    def barrier(self):
+        self.dist.barrier(self.group)
+
+
+def train_distributed(data, model_path, vocab_size, coverage=1.0, pad_id=0, unk_id=1, bos_id=2, eos_id=3, group=None,
+                      comm=None, device=None, lib=None, sharded=False, stats_out=None):
+    """Training over the ranks of `group`, one process per GPU.  `data` is the WHOLE corpus as bytes on every rank (each
+    rank uploads only its own byte range, cut as the reference cuts it between threads, bpe.cpp:864-873) or, with
+    sharded=True, this rank's shard (which must end at a word boundary).  Every rank returns the number of merges;
+    rank 0 writes the model.
+
+    Front end on every GPU: code point histogram (one NCCL allreduce), word split + dedup of the shard, then the unique
+    words are hash-partitioned across the ranks (all-to-all of device buffers) so that equal words of different shards
+    meet on one rank and are counted once — the job-wide set of unique words is cut into `world` disjoint parts, the
+    reference's thread partition (bpe.cpp:1066-1069) and its merge of the per-thread word maps (:1029-1039).
+    Merge loop: every rank rewrites its own words; the count changes of a merge go straight into every peer's exchange
+    buffer (peer stores over NVLink inside the persistent kernel, csrc/merge_loop.cuh); every rank keeps the full pair
+    table and elects the same pair.  No collective call per merge."""
+    from . import _lib
+    L = lib or _lib.lib()
+    check_config(vocab_size, coverage, pad_id, unk_id, bos_id, eos_id)
+    comm = comm or TorchComm(group)
+    rank, world = comm.rank, comm.world
+    if world > 8:
+        raise ValueError("train_distributed: at most 8 ranks (one NVLink domain)")
+    if device is None:
+        import torch
+        device = torch.cuda.current_device()
+    if sharded:
+        shard = data
+    else:
+        pos = split_byte_ranges(data, world)
+        shard = data[pos[rank]:pos[rank + 1]]
+    ctx = C.c_void_p()
+    ok = L.yttm_ctx_create(device, C.byref(ctx)) == 0
+    err = None if ok else L.yttm_last_error(None).decode()
+    if not comm.agree(ok):
+        raise ValueError(err or "train_distributed: another rank failed to create its CUDA context")
+    keep = []  # received tensors stay alive until the import has copied them
+
+    def step(fn):
+        """run one local phase; every rank learns whether all of them succeeded before the next collective"""
+        msg = None
+        try:
+            rc = fn()
+            if rc:
+                msg = L.yttm_last_error(ctx).decode()
+        except ValueError as e:
+            msg = str(e)
+        if not comm.agree(msg is None):
+            raise ValueError(msg or "train_distributed: another rank failed")
 
     try:
-        check(L.yttm_train_load_corpus(ctx, C.cast(C.c_char_p(shard), C.c_void_p), len(shard), 0))
+        handle = C.create_string_buffer(128)
+        step(lambda: L.yttm_train_dist_init(ctx, rank, world, handle))
+        handles = comm.all_gather_bytes(handle.raw)
+        step(lambda: L.yttm_train_dist_connect(ctx, handles))
         dl, nd = C.c_uint64(0), C.c_uint64(0)
-        check(L.yttm_train_char_hist(ctx, C.byref(dl), C.byref(nd)))
-        # the one collective of the front-end: sum the dense code point histogram in place
+        step(lambda: L.yttm_train_load_corpus(ctx, C.cast(C.c_char_p(shard), C.c_void_p), len(shard), 0) or
+             L.yttm_train_char_hist(ctx, C.byref(dl), C.byref(nd)))
+        # the one collective of the byte passes: sum the dense code point histogram in place
         dptr, n64 = C.c_void_p(), C.c_uint64(0)
-        check(L.yttm_train_char_hist_devptr(ctx, C.byref(dptr), C.byref(n64)))
-        hist = torch.as_tensor(_DevView(dptr.value, n64.value, "<i8"), device="cuda")
-        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
-        torch.cuda.synchronize()
-        check(L.yttm_train_char_hist_refresh(ctx, C.byref(dl), C.byref(nd)))
+        step(lambda: L.yttm_train_char_hist_devptr(ctx, C.byref(dptr), C.byref(n64)))
+        comm.allreduce_sum_u64(dptr.value, n64.value)
+        step(lambda: L.yttm_train_char_hist_refresh(ctx, C.byref(dl), C.byref(nd)))
         cps = np.zeros(nd.value, dtype=np.uint32)
         cnt = np.zeros(nd.value, dtype=np.uint64)
         L.yttm_train_get_char_hist(ctx, cps.ctypes.data, cnt.ctypes.data)
         char2id, n_special = choose_alphabet(cps, cnt, dl.value, coverage, (pad_id, unk_id, bos_id, eos_id))
         used = len(char2id) + n_special
-        if used > vocab_size:
+        if used > vocab_size:  # identical on every rank (same histogram): no agreement round needed
             raise ValueError("Incorrect arguments. Vocabulary size too small. Set vocab_size>=%d.  Current value "
                              "for vocab_size=%d" % (used, vocab_size))
         kc = np.fromiter(char2id.keys(), dtype=np.uint32)
         ki = np.fromiter(char2id.values(), dtype=np.uint32)
-        check(L.yttm_train_set_alphabet(ctx, kc.ctypes.data, ki.ctypes.data, len(kc), char2id[9601]))
+        nu = C.c_uint64(0)
+        step(lambda: L.yttm_train_set_alphabet(ctx, kc.ctypes.data, ki.ctypes.data, len(kc), char2id[9601]) or
+             L.yttm_train_dist_word_table(ctx, C.byref(nu)))
+        # unique words -> their owner ranks (device buffers, all-to-all)
+        bpd, wpd = (C.c_uint64 * 8)(), (C.c_uint64 * 8)()
+        p_b, p_p, p_f = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        step(lambda: L.yttm_train_dist_export_words(ctx, bpd, wpd, C.byref(p_b), C.byref(p_p), C.byref(p_f)))
+        t_b, r_b, bps = comm.all_to_all(p_b.value, list(bpd)[:world], 1)
+        t_p, r_p, wps = comm.all_to_all(p_p.value, list(wpd)[:world], 8)
+        t_f, r_f, _ = comm.all_to_all(p_f.value, list(wpd)[:world], 8)
+        keep += [t_b, t_p, t_f]
         st = _lib.TrainStats()
-        check(L.yttm_train_build(ctx, C.byref(st)))
-        # unique words of every rank -> every rank (replicated merge loop)
-        nw, nt = C.c_uint64(0), C.c_uint64(0)
-        check(L.yttm_train_export_words(ctx, None, 0, None, None, 0, C.byref(nw), C.byref(nt)))
-        tok = np.zeros(max(nt.value, 1), dtype=np.uint32)
-        off = np.zeros(nw.value + 1, dtype=np.uint32)
-        frq = np.zeros(max(nw.value, 1), dtype=np.uint64)
-        check(L.yttm_train_export_words(ctx, tok.ctypes.data, len(tok), off.ctypes.data, frq.ctypes.data, len(frq),
-                                        C.byref(nw), C.byref(nt)))
-        toks = all_gather_arrays(tok[:nt.value], group)
-        offs = all_gather_arrays(off, group)
-        frqs = all_gather_arrays(frq[:nw.value], group)
-        mt, mo, mf = merge_word_exports(list(zip(toks, offs, frqs)))
-        check(L.yttm_train_import_words(ctx, mt.ctypes.data, len(mt), mo.ctypes.data, mf.ctypes.data, len(mf),
-                                        C.byref(st)))
+        bsrc, wsrc = (C.c_uint64 * 8)(*bps), (C.c_uint64 * 8)(*wps)
+        step(lambda: L.yttm_train_dist_import_words(ctx, r_b, bsrc, r_p, r_f, wsrc, C.byref(st)))
         n_merges = vocab_size - used
         rules = np.zeros(3 * max(n_merges, 1), dtype=np.uint32)
         freqs = np.zeros(max(n_merges, 1), dtype=np.uint64)
         done = C.c_uint32(0)
-        check(L.yttm_train_run(ctx, used, n_merges, rules.ctypes.data, freqs.ctypes.data, C.byref(done)))
+        step(lambda: L.yttm_train_run(ctx, used, n_merges, rules.ctypes.data, freqs.ctypes.data, C.byref(done)))
         rules = rules[:3 * done.value].reshape(-1, 3)
-        if rank == 0:
-            write_model(model_path, char2id, rules, (pad_id, unk_id, bos_id, eos_id), vocab_size)
-        dist.barrier(group)
+        stats = {"n_unique": int(st.n_unique), "n_tokens": int(st.n_tokens), "n_pairs": int(st.n_pairs),
+                                  "n_merges": int(done.value), "merge_loop_ms": L.yttm_stage_ms(ctx, b"merge_loop"),
+                                  "launches": L.yttm_stage_ms(ctx, b"loop_launches"),
+                                  "front_ms": {k: L.yttm_stage_ms(ctx, k.encode()) for k in
+                                               ("h2d", "char_hist", "word_count", "tokenise", "pair_hist")},
+                                  "phase_us_per_iter": {k: L.yttm_stage_ms(ctx, k.encode()) * 1e3 /
+                                                        max(L.yttm_stage_ms(ctx, b"loop_iters"), 1.0) for k in
+                                                        ("loop_drain", "loop_argmax", "loop_barrier1", "loop_apply",
+                                                         "loop_barrier2")}}
+        train_distributed.last = stats  # one process per rank; threads of a test harness pass stats_out instead
+        if stats_out is not None:
+            stats_out.update(stats)
+        if rank == 0 and model_path:
+            write_model(model_path, char2id, rules, (pad_id, unk_id, bos_id, eos_id), vocab_size, lib=L)
+        comm.barrier()
         return int(done.value)
     finally:
         L.yttm_ctx_destroy(ctx)
@@ -197,7 +296,7 @@ def choose_alphabet(cps, counts, data_len, coverage, special):
     return char2id, n_special
 
 
-def write_model(path, char2id, rules, special, vocab_size):
+def write_model(path, char2id, rules, special, vocab_size, lib=None):
     """rename_tokens (bpe.cpp:814-837) + BPEState::dump (utils.cpp:50-66); the char2id lines come in the
     reference's flat_hash_map iteration order (yttm_api_dump_order), so the file is byte-identical."""
     from . import _lib
@@ -212,7 +311,7 @@ def write_model(path, char2id, rules, special, vocab_size):
             cur += 1
     filled = np.array(sorted(char2id, key=lambda cp: char2id[cp]), dtype=np.uint32)
     order = np.zeros(len(filled), dtype=np.uint32)
-    L = _lib.lib()
+    L = lib or _lib.lib()
     if L.yttm_api_dump_order(filled.ctypes.data, len(filled), order.ctypes.data) != 0:
         raise ValueError("duplicate code points in char2id")
     with open(path, "w") as f:
