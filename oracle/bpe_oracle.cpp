@@ -348,7 +348,11 @@ static void encode(const Model &m, const uint8_t *s, uint64_t n, bool bos, bool 
       for (int i = 0; i != -1; i = nxt[i]) live.push_back(t[i]);
       t.swap(live);
     }
-    for (uint32_t v : t) out->push_back(v >= UNK_BASE ? m.unk : (int32_t)v);
+    // The reference starts its output at the first node whose token id is not 0 (dead nodes carry id 0,
+    // bpe.cpp:1591-1596): when U+2581 itself has id 0 (no special token sits at 0, e.g. pad_id = -1) a word-initial
+    // "▁" that was never merged is silently dropped.  Reproduced, not fixed.
+    const size_t first = (m.space_id == 0 && !t.empty() && t[0] == 0) ? 1 : 0;
+    for (size_t k = first; k < t.size(); k++) out->push_back(t[k] >= UNK_BASE ? m.unk : (int32_t)t[k]);
   }
   if (eos) out->push_back(m.eos);
   if (reverse) std::reverse(out->begin() + out0, out->end());

@@ -143,6 +143,12 @@ template <class T, class U> inline T atomicMax(T *p, U v) {
   return old;
 }
 
+template <class T, class U> inline T atomicMin(T *p, U v) {
+  T old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (old > (T)v && !__atomic_compare_exchange_n(p, &old, (T)v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return old;
+}
+
 // CUDA's overloaded ::min / ::max on mixed integer types
 template <class A, class B> inline typename std::common_type<A, B>::type min(A a, B b) {
   typedef typename std::common_type<A, B>::type C;

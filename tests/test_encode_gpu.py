@@ -93,6 +93,34 @@ def test_dropout_distribution_vs_reference(product, checkers, oracle):
     assert abs(g - r) / r < 0.02
 
 
+def check_space_id_zero(oracle, special):
+    import os
+    text = _cases.zipf().text(60_000) + b" zab zab ab z zz z q"
+    n_chars = len(set(text.decode().replace("\n", " ").replace(" ", "")))
+    m = tmp_model_path("orc")
+    oracle.train(text, m, n_chars + 5 + 25, 1.0, **special)
+    long_word = b"".join(_cases.zipf().sentences(12, 60, seed=6)).replace(b" ", b"")
+    sents = _cases.zipf_sentences(300) + list(_cases.EDGE_SENTENCES) + [b"zab", b"z", b"q z zz", long_word, b"q" + long_word]
+    g, o = GpuEncoder(m), oracle.encoder(m)
+    kws = [dict(), dict(reverse=True), dict(dropout=0.3, seed=5)]
+    if special["bos"] != -1:
+        kws.append(dict(bos=True, eos=True))
+    for plain in (False, True):
+        if plain:
+            os.environ["YTTM_ENC_PLAIN"] = "1"
+        try:
+            for kw in kws:
+                assert g.encode(sents, **kw) == o.encode(sents, **kw), (plain, kw)
+        finally:
+            os.environ.pop("YTTM_ENC_PLAIN", None)
+
+
+@pytest.mark.parametrize("special", [dict(pad=-1, unk=1, bos=2, eos=3), dict(pad=-1, unk=5, bos=-1, eos=-1)])
+def test_space_token_with_id_zero(product, oracle, special):
+    """The reference's id-0 quirk (bpe.cpp:1591-1596) on the GPU kernels, see check_space_id_zero."""
+    check_space_id_zero(oracle, special)
+
+
 def test_bos_eos_errors(product, oracle):
     m = tmp_model_path("orc")
     oracle.train(synth.readme_corpus(n_lines=200), m, 100, 1.0, pad=-1, unk=0, bos=-1, eos=-1)
@@ -118,8 +146,9 @@ def test_python_api_roundtrip(product, tmp_path):
     norm = [" ".join(l.split()) for l in test_lines]
     ids = bpe.encode(test_lines, output_type=yttm.OutputType.ID, bos=True, eos=True)
     dec = bpe.decode(ids, ignore_ids=[2, 3])
-    assert [d.replace("<UNK>", "e") for d in dec] == [n.replace("e", "e") for n in norm] or \
-        all(len(d) <= len(n) + 5 * n.count("e") for d, n in zip(dec, norm))
+    import re
+    # "e" is not in the alphabet: a maximal run of e inside a word is one <UNK> (bpe.cpp:1513-1533)
+    assert dec == [re.sub("e+", "<UNK>", n) for n in norm]
     sub = bpe.encode(test_lines, output_type=yttm.OutputType.SUBWORD)
     assert ["".join(s).replace("▁", " ").strip() for s in sub] == norm
     vocab = bpe.vocab()

@@ -58,6 +58,34 @@ def test_dirty_unicode(reference, oracle, cov):
     assert reference.encoder(m1).encode(sents) == oracle.encoder(m1).encode(sents)
 
 
+@pytest.mark.parametrize("special", [dict(pad=-1, unk=1, bos=2, eos=3), dict(pad=-1, unk=5, bos=-1, eos=-1)])
+def test_space_token_with_id_zero(reference, oracle, special):
+    """No special token at id 0 => U+2581 gets final id 0, and the reference drops a word-initial, never merged "▁" from
+    its output (it starts at the first node whose id is not 0, bpe.cpp:1591-1596).  Few merges, so most words keep it."""
+    text = _cases.zipf().text(60_000) + b" zab zab ab z zz z q"
+    m1, m2 = tmp_model_path("ref"), tmp_model_path("orc")
+    n_chars = len(set(text.decode().replace("\n", " ").replace(" ", "")))
+    vocab = n_chars + 5 + 25
+    reference.train(text, m1, vocab, 1.0, n_threads=1, **special)
+    oracle.train(text, m2, vocab, 1.0, **special)
+    assert read_model(m1) == read_model(m2)
+    assert read_model(m1)[0][9601] == 0
+    sents = _cases.zipf_sentences(400) + list(_cases.EDGE_SENTENCES) + [b"zab", b"z", b"q z zz", "\u2581\u2581z".encode()]
+    e1, e2 = reference.encoder(m1), oracle.encoder(m1)
+    kws = [dict(), dict(reverse=True)]
+    if special["bos"] != -1:
+        kws.append(dict(bos=True, eos=True))
+    for kw in kws:
+        got, want = e2.encode(sents, **kw), e1.encode(sents, **kw)
+        assert got == want
+    # the quirk really fires: a one-letter word whose ("▁", letter) pair has no rule comes out as ONE id
+    c2i, rules, _ = read_model(m1)
+    merged_with_space = {y for x, y, _ in rules if x == 0}
+    lone = [cp for cp, i in c2i.items() if cp != 9601 and i not in merged_with_space]
+    assert lone
+    assert e1.encode([chr(lone[0]).encode()]) == [[c2i[lone[0]]]] == e2.encode([chr(lone[0]).encode()])
+
+
 def test_vocab_too_small(reference, oracle):
     _train_both(reference, oracle, b"abcdefgh ijkl", 6, 1.0)
 

@@ -183,7 +183,7 @@ def test_encode_linear_product_id_is_refused_for_a_foreign_model(emu, oracle, mo
     sents = [synth.readme_corpus(n_lines=3, seed=4), b"abab cdcd abcd", b"dddd aaaa"]
     g = EG.GpuEncoder(m2)
     assert g.encode(sents) == oracle.encoder(m2).encode(sents)
-    assert emu.yttm_stage_ms(emu.yttm_api_device_context(g.h), b"enc_variant") == 0.0  # refused: default kernel
+    assert emu.yttm_stage_ms(emu.yttm_api_device_context(g.h), b"enc_variant") == 8.0  # refused: the default (dedup) path
 
 
 def test_encode_chunked_pipeline(emu, oracle, monkeypatch):
@@ -281,9 +281,12 @@ def test_train_deferred_list_overflow_falls_back_to_the_direct_pass(emu, oracle,
 
 
 def test_encode_long_words_block_kernel(emu, oracle, monkeypatch):
-    """YTTM_ENC_LONG (experimental, off by default): words of more than 512 slots get a whole block and are merged
-    pass by pass (all occurrences of the minimum rule per pass) instead of one merge at a time by one thread."""
+    """Words of more than 512 slots get a whole block and are merged pass by pass (all occurrences of the minimum rule
+    per pass) instead of one merge at a time by one thread (default since round 2, dropout = 0).  Here through the
+    bucketed kernel (YTTM_ENC_BUCKETED); the default dedup path hands its long representatives to the same kernel
+    (test_encode_dedup_variant, test_encode_space_token_with_id_zero)."""
     monkeypatch.setenv("YTTM_ENC_LONG", "1")
+    monkeypatch.setenv("YTTM_ENC_BUCKETED", "1")
     rng = np.random.default_rng(3)
     train = synth.readme_corpus(n_lines=400) + b" " + _cases.dirty_zipf_text(60_000)
     m = EG._model(oracle, train, 700)
@@ -313,7 +316,7 @@ def test_encode_long_words_block_kernel(emu, oracle, monkeypatch):
 @pytest.mark.parametrize("knobs", [dict(), dict(YTTM_ENC_DEDUP_SLOTS="4"), dict(YTTM_ENC_DEDUP_WEAKTAG="1"),
                                    dict(YTTM_ENC_DEDUP_SLOTS="64", YTTM_ENC_DEDUP_WEAKTAG="1")])
 def test_encode_dedup_variant(emu, oracle, monkeypatch, knobs):
-    """YTTM_ENC_DEDUP (experimental, off by default): every distinct word of the batch is encoded once, the other
+    """The word-dedup path (default since round 2 for dropout = 0): every distinct word of the batch is encoded once, the other
     occurrences copy the ids of their representative.  Same ids as the oracle, including words that differ only in
     what follows them (end of sentence / space / U+2581), prefixes of each other, truncated UTF-8, repeated long words
     (> LOCAL_W, merged in global slots); a 4-slot table (nearly every word represents itself), equal tags (every
@@ -328,16 +331,22 @@ def test_encode_dedup_variant(emu, oracle, monkeypatch, knobs):
             b"ab\xf0\x9f\x98 ab\xf0\x9f\x98\x80 ab\xf0\x9f\x98", b"abc abcd ab a abcd abc ab a", b"\xe2\x96\x81ab\xe2\x96\x81ab\xe2\x96",
             b"\xe2\x96 \xe2\x96", b"\x96 \x96\x81 \x96", b"", b" ", b"\xff\xff \xff \xff\xff", b"\x80 \x80 \xbf",
             long_word + b" " + long_word + b"x " + long_word, long_word[:41] + b" " + long_word[:40] + b" " + long_word[:41],
-            "☃ ☃☃ ☃ zz☃ zz☃".encode(), b"a" * 700 + b" " + b"a" * 700 + b" " + b"a" * 699]
+            "☃ ☃☃ ☃ zz☃ zz☃".encode(), b"a" * 700 + b" " + b"a" * 700 + b" " + b"a" * 699,
+            long_word * 3 + b" q " + long_word * 3 + b" " + long_word * 3 + b"q"]   # > 512 slots: block-per-word representatives
     sents = _cases.zipf_sentences(400) + _cases.EDGE_SENTENCES + edge + _cases.zipf_sentences(100) + edge[::-1]
     g, o = EG.GpuEncoder(m), oracle.encoder(m)
     for kw in EG.KW:
         assert g.encode(sents, **kw) == o.encode(sents, **kw)
     ctx = emu.yttm_api_device_context(g.h)
     assert emu.yttm_stage_ms(ctx, b"enc_variant") == 8.0
-    # with dropout every occurrence draws for itself: the default kernel runs
+    # with dropout every occurrence draws for itself: the per-word kernel runs
     assert g.encode(sents[:200], dropout=0.3, seed=5) == o.encode(sents[:200], dropout=0.3, seed=5)
     assert emu.yttm_stage_ms(ctx, b"enc_variant") == 0.0
+    monkeypatch.setenv("YTTM_ENC_PLAIN", "1")      # the round-1 kernels remain selectable
+    monkeypatch.delenv("YTTM_ENC_DEDUP")
+    assert g.encode(sents, eos=True) == o.encode(sents, eos=True)
+    assert emu.yttm_stage_ms(ctx, b"enc_variant") == 0.0
+    monkeypatch.delenv("YTTM_ENC_PLAIN")
     monkeypatch.setenv("YTTM_ENC_CHUNK_MB", "1")  # representatives never cross a chunk of the host-buffer pipeline
     big = sents * 40
     assert sum(map(len, big)) > 2 << 20
@@ -477,3 +486,11 @@ def test_train_staged_pinned_h2d(emu, oracle, monkeypatch, threads, chunk_kb):
     text = _cases.zipf().text(33_333)
     rules, _, _ = _abi_train(emu, text, 500)
     assert rules == _oracle_rules(oracle, text, 500)
+
+
+@pytest.mark.parametrize("special", [dict(pad=-1, unk=1, bos=2, eos=3), dict(pad=-1, unk=5, bos=-1, eos=-1)])
+def test_encode_space_token_with_id_zero(emu, oracle, special):
+    """U+2581 with final id 0 (no special token at 0): the reference drops a never-merged word-initial "▁"
+    (bpe.cpp:1591-1596; oracle pinned to it in test_oracle_vs_reference.py).  Default kernels (dedup + long words),
+    plain kernels and dropout."""
+    EG.check_space_id_zero(oracle, special)

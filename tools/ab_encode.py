@@ -1,6 +1,6 @@
-"""A/B of the encode kernels' experimental variants on the bench workload (run on a B200):
+"""A/B of the encode kernels' variants on the bench workload (run on a B200):
     python tools/ab_encode.py [n_sentences] [reps] [result.json] [model file]
-For each of {default, YTTM_ENC_FIND_CACHED, YTTM_ENC_BUCKETED, both, both + YTTM_ENC_ZLIN, YTTM_ENC_DEDUP, YTTM_ENC_FIND_VEC, both}: median CUDA-event ms of find / words / gather
+For each of {default, YTTM_ENC_PLAIN (the round-1 kernels), plain + one variant, ...}: median CUDA-event ms of find / words / gather
 over `reps` runs of yttm_enc_run_device on inputs resident in HBM, and a check that the ids are identical."""
 import ctypes as C
 import json
@@ -40,17 +40,17 @@ def main(L=None, n_sent=None, reps=None, train_bytes=20_000_000, vocab=8000):
         d_bytes, d_offs = d_bytes.cuda(), d_offs.cuda()
     base = None
     out = {}
-    for name, env in [("default", []), ("find_cached", ["YTTM_ENC_FIND_CACHED"]), ("bucketed", ["YTTM_ENC_BUCKETED"]),
-                      ("both", ["YTTM_ENC_FIND_CACHED", "YTTM_ENC_BUCKETED"]),
-                      ("both+zlin", ["YTTM_ENC_FIND_CACHED", "YTTM_ENC_BUCKETED", "YTTM_ENC_ZLIN"]),
-                      ("dedup", ["YTTM_ENC_DEDUP"]), ("dedup+find_cached", ["YTTM_ENC_DEDUP", "YTTM_ENC_FIND_CACHED"]),
-                      ("find_vec", ["YTTM_ENC_FIND_VEC"]), ("dedup+find_vec", ["YTTM_ENC_DEDUP", "YTTM_ENC_FIND_VEC"])]:
-        for k in ("YTTM_ENC_FIND_CACHED", "YTTM_ENC_BUCKETED", "YTTM_ENC_ZLIN", "YTTM_ENC_DEDUP", "YTTM_ENC_FIND_VEC"):
+    KNOBS = ("YTTM_ENC_PLAIN", "YTTM_ENC_FIND_CACHED", "YTTM_ENC_BUCKETED", "YTTM_ENC_ZLIN", "YTTM_ENC_DEDUP", "YTTM_ENC_FIND_VEC", "YTTM_ENC_LONG")
+    # default since round 2 = vector word finder + word dedup + block-per-long-word; "plain" = the round-1 kernels
+    for name, env in [("default", []), ("plain", ["YTTM_ENC_PLAIN"]), ("plain+find_vec", ["YTTM_ENC_PLAIN", "YTTM_ENC_FIND_VEC"]),
+                      ("plain+dedup", ["YTTM_ENC_PLAIN", "YTTM_ENC_DEDUP"]), ("bucketed", ["YTTM_ENC_BUCKETED"]),
+                      ("dedup+find_cached", ["YTTM_ENC_FIND_CACHED"])]:
+        for k in KNOBS:
             os.environ.pop(k, None)
         for k in env:
             os.environ[k] = "1"
         ms = {"enc_find": [], "enc_words": [], "enc_gather": [], "encode": []}
-        if "YTTM_ENC_DEDUP" in env:  # the three launches inside enc_words
+        if name in ("default", "plain+dedup", "dedup+find_cached"):  # the three launches inside enc_words
             ms.update({"enc_dedup": [], "enc_rep": [], "enc_copy": []})
         for _ in range(reps + 2):
             p_ids, p_off, n = C.c_void_p(), C.c_void_p(), C.c_uint64(0)
@@ -72,7 +72,7 @@ def main(L=None, n_sent=None, reps=None, train_bytes=20_000_000, vocab=8000):
         out[name]["ids_equal_default"] = same
         out[name]["n_ids"] = int(n.value)
     # BASELINE config 4 encodes with dropout_prob = 0.1: the default kernels' stage times there (ids are random by design)
-    for k in ("YTTM_ENC_FIND_CACHED", "YTTM_ENC_BUCKETED", "YTTM_ENC_ZLIN", "YTTM_ENC_DEDUP", "YTTM_ENC_FIND_VEC"):
+    for k in KNOBS:
         os.environ.pop(k, None)
     ms = {"enc_find": [], "enc_words": [], "enc_gather": [], "encode": []}
     for r in range(reps + 2):

@@ -18,7 +18,7 @@ from youtokentome_b200 import synth  # noqa: E402
 
 KNOBS = ["YT_EMU_SMS", "YT_EMU_SCHED_SEED", "YTTM_FORCE_STREAM", "YTTM_STREAM_Q", "YTTM_STAGES", "YTTM_PAIR_CAP_FLOOR", "YTTM_DEFER_CAP",
          "YTTM_ENC_BUCKETED", "YTTM_ENC_FIND_CACHED", "YTTM_ENC_ZLIN", "YTTM_ENC_LONG", "YTTM_ENC_CHUNK_MB",
-         "YTTM_ENC_DEDUP", "YTTM_ENC_DEDUP_SLOTS", "YTTM_ENC_DEDUP_WEAKTAG", "YTTM_ENC_FIND_VEC", "YTTM_LOOP_WIDEPROBE",
+         "YTTM_ENC_DEDUP", "YTTM_ENC_DEDUP_SLOTS", "YTTM_ENC_DEDUP_WEAKTAG", "YTTM_ENC_FIND_VEC", "YTTM_XQ_SEG_CAP", "YTTM_ENC_PLAIN",
          "YTTM_PAIR_MAX_LOAD_PCT", "YTTM_TRAIN_PINNED_H2D", "YTTM_TRAIN_PINNED_CHUNK_KB", "YTTM_LOOP_BLOCKS"]
 
 
@@ -126,7 +126,7 @@ def main():
         if rng.integers(0, 2):
             env["YTTM_PAIR_CAP_FLOOR"] = str(int(rng.choice([16, 64, 256, 2048])))
         if rng.integers(0, 2):
-            env["YTTM_LOOP_WIDEPROBE"] = "1"   # experimental merge loop: four table slots per round trip
+            env["YTTM_XQ_SEG_CAP"] = str(int(rng.choice([4, 8, 64])))   # exchange segments overflow -> rebuild path
         if rng.integers(0, 3) == 0:
             env["YTTM_PAIR_MAX_LOAD_PCT"] = str(int(rng.choice([30, 50, 90])))
         if rng.integers(0, 3) == 0:   # corpus through the pinned staging buffers, tiny chunks

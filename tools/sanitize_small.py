@@ -3,7 +3,7 @@
     compute-sanitizer --tool racecheck --error-exitcode 9 python tools/sanitize_small.py
     compute-sanitizer --tool synccheck --error-exitcode 9 python tools/sanitize_small.py
 Sizes are tiny on purpose (the tools slow kernels down 10 - 100x): stress-shaped and dirty multi-script corpora of a few
-KB, RESIDENT and forced-STREAMING merge loops (default and wide-probe kernels), the default encode kernels with and without dropout, then every
+KB, RESIDENT and forced-STREAMING merge loops (roomy and tiny exchange segments / table partitions), the default encode kernels with and without dropout, then every
 experimental encode variant.  Every result is also compared with the oracle (test infrastructure), so a run that is
 clean but wrong still fails.  `--emulate` runs the same script on the CPU SIMT emulator (a dry run of the script)."""
 import os
@@ -17,7 +17,7 @@ import _cases  # noqa: E402
 from _bind import read_model, tmp_model_path  # noqa: E402
 from youtokentome_b200 import _lib, synth  # noqa: E402
 
-ENC_KNOBS = ["YTTM_ENC_FIND_CACHED", "YTTM_ENC_FIND_VEC", "YTTM_ENC_BUCKETED", "YTTM_ENC_ZLIN", "YTTM_ENC_LONG", "YTTM_ENC_DEDUP"]
+ENC_KNOBS = ["YTTM_ENC_PLAIN", "YTTM_ENC_FIND_CACHED", "YTTM_ENC_FIND_VEC", "YTTM_ENC_BUCKETED", "YTTM_ENC_ZLIN", "YTTM_ENC_LONG", "YTTM_ENC_DEDUP"]
 
 
 def main():
@@ -31,13 +31,13 @@ def main():
     n_ok = 0
     corpora = [(synth.stress_text(3), 60, 1.0), (synth.stress_text(11), 90, 0.97), (_cases.dirty_zipf_text(30_000), 400, 0.98),
                (synth.readme_corpus(n_lines=60), 120, 1.0)]
-    for stream, wide in ((False, False), (True, False), (False, True), (True, True)):
-        for k in ("YTTM_FORCE_STREAM", "YTTM_STREAM_Q", "YTTM_STAGES", "YTTM_LOOP_WIDEPROBE"):
+    for stream, tiny in ((False, False), (True, False), (False, True), (True, True)):
+        for k in ("YTTM_FORCE_STREAM", "YTTM_STREAM_Q", "YTTM_STAGES", "YTTM_XQ_SEG_CAP", "YTTM_PAIR_CAP_FLOOR"):
             os.environ.pop(k, None)
         if stream:
             os.environ.update(YTTM_FORCE_STREAM="1", YTTM_STREAM_Q="256", YTTM_STAGES="3")
-        if wide:
-            os.environ["YTTM_LOOP_WIDEPROBE"] = "1"   # the experimental wide-probe merge loop
+        if tiny:   # exchange segments overflow, table partitions fill up: the rebuild / relaunch paths
+            os.environ.update(YTTM_XQ_SEG_CAP="8", YTTM_PAIR_CAP_FLOOR="16")
         for text, vocab, cov in corpora:
             m_o = tmp_model_path("so")
             orc.train(text, m_o, vocab, cov)

@@ -236,6 +236,15 @@ struct LinearZFn {
   }
 };
 
+// A quirk of the reference, reproduced: encode_sentence starts a word's output at the first node whose token id is
+// not 0, because merged-away nodes carry id 0 (bpe.cpp:1591-1596).  When U+2581 itself has id 0 — no special token
+// sits at 0, e.g. pad_id = -1 — a word-initial "▁" that no rule merged is therefore dropped from the output.
+YT_HD uint32_t drop_unmerged_space0(int32_t *t, uint32_t n, uint32_t space_id) {
+  if (space_id != 0 || n == 0 || t[0] != 0) return n;
+  for (uint32_t i = 0; i + 1 < n; i++) t[i] = t[i + 1];
+  return n - 1;
+}
+
 template <class RankFn, class ZFn = NoZFn>
 YT_HD uint32_t encode_word(const uint8_t *s, uint64_t p0, uint64_t lo, uint64_t hi, const uint32_t *cp2id,
                            uint32_t space_id, RankFn rank, uint32_t *zr, uint64_t drop_thresh, uint64_t seed, uint64_t sent_index,
@@ -272,7 +281,7 @@ YT_HD uint32_t encode_word(const uint8_t *s, uint64_t p0, uint64_t lo, uint64_t 
       if (bi > 0) { r[bi - 1] = rank((uint32_t)t[bi - 1], (uint32_t)t[bi], &z); if (zr) zr[bi - 1] = z; }
       if (bi + 1 < n) { r[bi] = rank((uint32_t)t[bi], (uint32_t)t[bi + 1], &z); if (zr) zr[bi] = z; }
     }
-    return n;
+    return drop_unmerged_space0(t, n, space_id);
   }
   // ---- dropout: stable node positions (linked list) + explicit stale events
   const uint32_t NIL = 0xffffffffu;
@@ -323,7 +332,7 @@ YT_HD uint32_t encode_word(const uint8_t *s, uint64_t p0, uint64_t lo, uint64_t 
   // compact the live nodes to the front of t (ascending positions, so writes trail reads)
   uint32_t w = 0;
   for (uint32_t i = 0; i != NIL; i = nx[i]) t[w++] = t[i];
-  return live;
+  return drop_unmerged_space0(t, live, space_id);
 }
 
 }  // namespace yt

@@ -329,9 +329,8 @@ void release_training_cache() {
 static Status train_on_buffer(const char *text, uint64_t n, int n_tokens, const std::string &output_file,
                               BpeConfig cfg, BPEState *out_state) {
   double t_start = now_s();
-  // one training context per host thread and device, kept between calls: its device buffers
-  // (corpus, word table, packed words, pair table) are reused instead of cudaMalloc'ed / freed
-  // on every train_bpe (release_training_cache() gives the memory back)
+  // one training context per host thread and device; with YTTM_TRAIN_KEEP_CACHE=1 it survives the call and its device
+  // buffers (corpus, word table, packed words, pair table) are reused by the next training of this thread
   TrainCache &cache = g_train_cache;
   // a context fixes its launch geometry when it first trains: the knobs that shape it are part of the cache key, so a
   // changed setting takes effect in a running process (the A/B tools and the tests vary them between calls)
@@ -410,6 +409,10 @@ static Status train_on_buffer(const char *text, uint64_t n, int n_tokens, const 
   r.pair_hist_ms = yttm_stage_ms(ctx, "pair_hist"); r.merge_loop_ms = yttm_stage_ms(ctx, "merge_loop");
   r.launches = yttm_launch_count(ctx) - launches0;
   r.total_s = now_s() - t_start;
+  // The context holds the corpus, the word table, the packed words and the pair table (more than the corpus itself).
+  // The reference's train_bpe is stateless, so the device memory goes back by default; YTTM_TRAIN_KEEP_CACHE=1 keeps
+  // the context for the next training of this thread (benchmarks, test loops), release_training_cache() frees it.
+  if (!std::getenv("YTTM_TRAIN_KEEP_CACHE")) release_training_cache();
   return Status();
 }
 

@@ -347,6 +347,8 @@ constexpr uint32_t LONG_W = 512;
 constexpr uint32_t DEAD_T = 0xfffffffeu;  // token merged away in the current pass (has UNK_FLAG set: never a rule operand)
 struct LongList {
   uint32_t *pos, *sent, *end;  // word start, sentence, word end (batch byte positions)
+  uint32_t *item;              // dedup path: the work item (representative) the word belongs to
+  uint32_t *n_tok;             // dedup path: per work item, the number of ids of its encoding (nullptr otherwise)
   unsigned long long *n;
   uint32_t cap;                // 0 = feature off
 };
@@ -417,7 +419,7 @@ __global__ void __launch_bounds__(128) encode_words_bucketed_kernel(EncArgs a, u
       uint32_t owned = (uint32_t)(q - p0) + 1, n;
       if (!DROPOUT && ll.cap && owned > LONG_W) {  // a whole block will take it (encode_long_words_kernel)
         const unsigned long long k = atomicAdd(ll.n, 1ull);
-        if (k < ll.cap) { ll.pos[k] = (uint32_t)p0; ll.sent[k] = (uint32_t)s; ll.end[k] = (uint32_t)q; continue; }
+        if (k < ll.cap) { ll.pos[k] = (uint32_t)p0; ll.sent[k] = (uint32_t)s; ll.end[k] = (uint32_t)q; ll.item[k] = 0; continue; }
       }
       if (owned <= LOCAL_W) {
         int32_t lt[LOCAL_W];
@@ -533,7 +535,9 @@ __global__ void __launch_bounds__(LONG_T) encode_long_words_kernel(EncArgs a, Lo
           if (r[i] < best) { best = r[i]; where = i; }
         const uint32_t rmin = long_block_min(best, s_red);
         if (rmin == NO_RANK) break;
-        if (best == rmin) s_hit = where;  // any of them
+        if (threadIdx.x == 0) s_hit = 0xffffffffu;
+        __syncthreads();
+        if (best == rmin) atomicMin(&s_hit, where);  // any of them would do; the minimum is race-free
         __syncthreads();
         if (threadIdx.x == 0) {
           const uint32_t x = t[s_hit], y = t[s_hit + 1];
@@ -587,13 +591,31 @@ __global__ void __launch_bounds__(LONG_T) encode_long_words_kernel(EncArgs a, Lo
         __syncthreads();
       }
     }
+    // ---- the reference's id-0 quirk (drop_unmerged_space0): a never-merged "▁" with id 0 leaves the output
+    if (!no_unit && a.space_id == 0) {
+      const bool drop = t[0] == 0;  // block-uniform (one value read by everyone)
+      __syncthreads();
+      if (drop) {
+        for (uint32_t b0 = 0; b0 + 1 < n; b0 += LONG_T) {  // chunk by chunk: reads before writes, destination < source
+          const uint32_t i = b0 + threadIdx.x;
+          const uint32_t v = i + 1 < n ? t[i + 1] : 0u;
+          __syncthreads();
+          if (i + 1 < n) t[i] = v;
+          __syncthreads();
+        }
+        n -= 1;
+      }
+    }
     // ---- final ids; the unused slots of the word go back to EMPTY
     const uint32_t n_out = no_unit ? 0 : n;
     for (uint32_t i = threadIdx.x; i < owned; i += LONG_T) {
       const uint32_t v = t[i];
       t[i] = i < n_out ? ((v & UNK_FLAG) ? (uint32_t)a.unk_id : v) : (uint32_t)EMPTY_SLOT;
     }
-    if (threadIdx.x == 0 && n_out) atomicAdd(a.n_ids + s, (unsigned long long)n_out);
+    if (threadIdx.x == 0) {
+      if (n_out) atomicAdd(a.n_ids + s, (unsigned long long)n_out);
+      if (ll.n_tok) ll.n_tok[ll.item[w]] = n_out;
+    }
     __syncthreads();
   }
 }
@@ -674,7 +696,7 @@ __global__ void __launch_bounds__(128) dedup_words_kernel(EncArgs a, uint64_t n_
   }
 }
 
-__global__ void __launch_bounds__(128) encode_rep_words_kernel(EncArgs a, DedupArgs d) {
+__global__ void __launch_bounds__(128) encode_rep_words_kernel(EncArgs a, DedupArgs d, LongList ll) {
   constexpr uint32_t LOCAL_W = 40;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t o0 = a.offs[0];
@@ -691,6 +713,10 @@ __global__ void __launch_bounds__(128) encode_rep_words_kernel(EncArgs a, DedupA
     uint32_t l;
     while (q < hi && !space_at(a.bytes, q, hi, &l)) q++;
     uint32_t owned = (uint32_t)(q - p0) + 1, n;
+    if (ll.cap && owned > LONG_W) {  // a whole block will take it (encode_long_words_kernel sets n_tok and n_ids)
+      const unsigned long long k = atomicAdd(ll.n, 1ull);
+      if (k < ll.cap) { ll.pos[k] = (uint32_t)p0; ll.sent[k] = (uint32_t)s; ll.end[k] = (uint32_t)q; ll.item[k] = w; continue; }
+    }
     if (owned <= LOCAL_W) {
       int32_t lt[LOCAL_W];
       uint32_t lr[LOCAL_W];
@@ -821,8 +847,8 @@ int enc_device(yttm_enc *enc, yttm_enc::Slot *e, const uint8_t *d_bytes, const u
     uint64_t blocks = std::min<uint64_t>((warps_needed + 7) / 8, (uint64_t)c->n_sm * 8);
     ytc::timer_begin(c, "enc_find");
     YT_CUDA(c, cudaMemsetAsync(a.slots, 0xff, n_slots * 4, c->stream));  // EMPTY_SLOT == -1
-    if (std::getenv("YTTM_ENC_FIND_VEC"))  // experimental, see the kernels
-      find_words_vec_kernel<<<(unsigned)std::max<uint64_t>(blocks, 1), 256, 0, c->stream>>>(a);
+    if (std::getenv("YTTM_ENC_FIND_VEC") || !(std::getenv("YTTM_ENC_PLAIN") || std::getenv("YTTM_ENC_FIND_CACHED")))
+      find_words_vec_kernel<<<(unsigned)std::max<uint64_t>(blocks, 1), 256, 0, c->stream>>>(a);  // default since round 2
     else if (std::getenv("YTTM_ENC_FIND_CACHED"))
       find_words_cached_kernel<<<(unsigned)std::max<uint64_t>(blocks, 1), 256, 0, c->stream>>>(a);
     else
@@ -836,22 +862,28 @@ int enc_device(yttm_enc *enc, yttm_enc::Slot *e, const uint8_t *d_bytes, const u
   if (n_words) {
     uint64_t blocks = std::min<uint64_t>((n_words + 127) / 128, (uint64_t)c->n_sm * 16);
     ytc::timer_begin(c, "enc_words");
-    // experimental kernels, see there; the linear product-id shortcut exists in the bucketed kernel only
+    // Defaults since round 2 (measured on B200, profiles/r02_ab_encode.json: find 1.24 -> 1.03 ms, words 3.45 -> 1.24 ms,
+    // ids identical): the 4-bytes-per-lane word finder, and for dropout = 0 the word-dedup path (every distinct word of
+    // the batch is encoded once) with words of more than LONG_W slots handed to a whole block each (a 16 KB word: 30 s
+    // on one thread, 9 ms on a block).  YTTM_ENC_PLAIN=1 selects the round-1 kernels (A/B, tests); the bucketed / zlin
+    // variants stay opt-in (bucketed: 3.45 -> 2.95 ms, superseded by dedup; zlin: slower).
+    const bool plain = std::getenv("YTTM_ENC_PLAIN") != nullptr;
     const bool zlin = enc->zlin_ok && std::getenv("YTTM_ENC_ZLIN") != nullptr;
-    const bool longw = a.drop_thresh == 0 && std::getenv("YTTM_ENC_LONG") != nullptr;
-    const bool bucketed = zlin || longw || std::getenv("YTTM_ENC_BUCKETED") != nullptr;
-    LongList ll{nullptr, nullptr, nullptr, nullptr, 0};
+    const bool dedup = a.drop_thresh == 0 && (std::getenv("YTTM_ENC_DEDUP") != nullptr || (!plain && !zlin && !std::getenv("YTTM_ENC_BUCKETED")));
+    const bool longw = a.drop_thresh == 0 && (std::getenv("YTTM_ENC_LONG") != nullptr || !plain);
+    const bool bucketed = !dedup && (zlin || longw || std::getenv("YTTM_ENC_BUCKETED") != nullptr);
+    LongList ll{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
     if (longw) {
       const uint32_t cap = (uint32_t)(n_bytes / LONG_W + 16);
-      YT_CUDA(c, e->longw.reserve((size_t)cap * 12 + 16));
+      YT_CUDA(c, e->longw.reserve((size_t)cap * 16 + 16));
       ll.n = e->longw.as<unsigned long long>();
       ll.pos = reinterpret_cast<uint32_t *>(ll.n + 2);
       ll.sent = ll.pos + cap;
       ll.end = ll.sent + cap;
+      ll.item = ll.end + cap;
       ll.cap = cap;
       YT_CUDA(c, cudaMemsetAsync(ll.n, 0, 8, c->stream));
     }
-    const bool dedup = a.drop_thresh == 0 && std::getenv("YTTM_ENC_DEDUP") != nullptr;  // takes precedence over the others
     c->timers["enc_variant"].ms = dedup ? 8.f : (float)((longw ? 4 : 0) + (zlin ? 2 : 0) + (bucketed ? 1 : 0));  // yttm_stage_ms(ctx, "enc_variant")
     if (dedup) {
       // table: 2 slots per occurrence up to 2^21 slots (16 MB, L2-resident); beyond that it works as a cache
@@ -871,7 +903,12 @@ int enc_device(yttm_enc *enc, yttm_enc::Slot *e, const uint8_t *d_bytes, const u
       dedup_words_kernel<<<(unsigned)blocks, 128, 0, c->stream>>>(a, n_words, d);
       ytc::timer_end(c, "enc_dedup");
       ytc::timer_begin(c, "enc_rep");
-      encode_rep_words_kernel<<<(unsigned)blocks, 128, 0, c->stream>>>(a, d);
+      if (longw) ll.n_tok = d.n_tok;
+      encode_rep_words_kernel<<<(unsigned)blocks, 128, 0, c->stream>>>(a, d, ll);
+      if (longw) {  // no host round trip: the blocks read the list length themselves
+        encode_long_words_kernel<<<(unsigned)c->n_sm, LONG_T, 0, c->stream>>>(a, ll);
+        c->launches++;
+      }
       ytc::timer_end(c, "enc_rep");
       ytc::timer_begin(c, "enc_copy");
       copy_word_ids_kernel<<<(unsigned)std::min<uint64_t>((n_words + 255) / 256, (uint64_t)c->n_sm * 8), 256, 0, c->stream>>>(a, n_words, d);

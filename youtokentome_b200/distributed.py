@@ -121,6 +121,26 @@ def check_config(vocab_size, coverage, pad_id, unk_id, bos_id, eos_id):
         raise ValueError("All ids of special tokens must be different.")
 
 
+class LocalComm:
+    """world = 1: the same code path as a multi-GPU job without torch.distributed (bench.py at --gpus 1, tests)."""
+    rank, world = 0, 1
+
+    def all_gather_bytes(self, b):
+        return bytes(b)
+
+    def allreduce_sum_u64(self, ptr, n):
+        pass
+
+    def agree(self, ok):
+        return bool(ok)
+
+    def all_to_all(self, ptr, counts, itemsize):
+        return None, ptr, [int(counts[0])]
+
+    def barrier(self):
+        pass
+
+
 class TorchComm:
     """The collectives train_distributed needs, over torch.distributed (NCCL on the GPUs; plumbing only — the per-merge
     exchange of the merge loop is NOT here, it is peer stores inside the kernel, csrc/merge_loop.cuh)."""

@@ -46,6 +46,7 @@ _SCRIPTS = {
     "cyrillic": (0x430, 32),     # 2-byte
     "greek": (0x3B1, 24),        # 2-byte
     "cjk": (0x4E00, 3000),       # 3-byte, large alphabet
+    "cjk8k": (0x4E00, 8000),     # 3-byte, the ~8k alphabet of BASELINE config 5
     "kana": (0x3041, 80),        # 3-byte
     "deva": (0x905, 50),         # 3-byte
     "arabic": (0x627, 36),       # 2-byte
@@ -233,6 +234,51 @@ class FastZipf:
         offs = np.zeros(n + 1, dtype=np.uint64)
         offs[1:] = ends[cut]
         return buf, offs
+
+
+# BASELINE config 5: Latin 40 %, Cyrillic 20 %, CJK 25 % (3-byte, ~8k alphabet), Arabic / Devanagari /
+# emoji (4-byte) 15 %; per-script Zipf lexicons, seed 777.  Rare CJK characters fall under coverage 0.9999.
+CONFIG5_MIX = {"latin": 0.40, "cyrillic": 0.20, "cjk8k": 0.25, "arabic": 0.06, "deva": 0.06, "emoji": 0.03}
+
+_GEN = {  # bench-scale corpora: kind -> (FastZipf arguments, first chunk seed)
+    "zipf": (dict(n_words=200_000, s=1.07, seed=1234), 5000),
+    "multilingual": (dict(n_words=300_000, s=1.05, seed=777, mix=CONFIG5_MIX), 7000),
+}
+_GEN_CACHE = {}
+
+
+def _gen_chunk(job):
+    kind, k, n_bytes, path = job
+    import os
+    if path and os.path.exists(path) and os.path.getsize(path) > 0:
+        with open(path, "rb") as f:
+            return f.read()
+    args, seed0 = _GEN[kind]
+    if kind not in _GEN_CACHE:
+        _GEN_CACHE[kind] = FastZipf(**args)
+    data = _GEN_CACHE[kind].text(n_bytes, seed=seed0 + k)
+    if path:
+        tmp = "%s.tmp%d" % (path, os.getpid())
+        with open(tmp, "wb") as f:
+            f.write(data)
+        os.replace(tmp, path)
+    return data
+
+
+def corpus_chunks(kind, chunk_ids, chunk_bytes=125_000_000, cache_dir=None, workers=None):
+    """A corpus defined as independently seeded chunks (chunk k: seed0 + k, ~chunk_bytes, ends with a newline), so that
+    a rank of a multi-GPU job can make exactly its part and every world size sees the same corpus.  Chunks are
+    generated by a process pool (FastZipf.text is single-threaded: ~3 s per 100 MB).  Returns list[bytes]."""
+    import os
+    from concurrent.futures import ProcessPoolExecutor
+    chunk_ids = list(chunk_ids)
+    jobs = [(kind, k, chunk_bytes, os.path.join(cache_dir, "%s_%d_%d.bin" % (kind, chunk_bytes, k)) if cache_dir else None)
+            for k in chunk_ids]
+    workers = workers or max(1, min(len(jobs), (os.cpu_count() or 2) // 2, 16))
+    if workers == 1 or len(jobs) == 1:
+        return [_gen_chunk(j) for j in jobs]
+    with ProcessPoolExecutor(max_workers=workers) as ex:
+        return list(ex.map(_gen_chunk, jobs))
 
 
 MULTILINGUAL_MIX = {"latin": 0.40, "cyrillic": 0.20, "cjk": 0.20, "kana": 0.05, "arabic": 0.05, "deva": 0.05,
