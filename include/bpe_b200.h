@@ -153,6 +153,17 @@ class BaseEncoder {
                        std::vector<uint64_t> *id_offsets, bool bos = false, bool eos = false, bool reverse = false,
                        double dropout_prob = 0) const;
 
+  // The same into caller-owned buffers, one call: Status code 2 (nothing written, *total_ids = size needed) when
+  // ids_cap is too small; ids_cap >= bytes + 3 * n_sentences always suffices.
+  Status encode_packed_into(const char *bytes, const uint64_t *offsets, uint64_t n_sentences, int32_t *ids, uint64_t ids_cap,
+                            uint64_t *id_offsets, uint64_t *total_ids, bool bos = false, bool eos = false,
+                            bool reverse = false, double dropout_prob = 0) const;
+  // DEVICE-resident input (d_bytes, d_offsets) and results left on the device: *d_ids / *d_id_offsets point into
+  // library-owned memory that stays valid until the next encode call on this object.
+  Status encode_packed_device(const char *d_bytes, const uint64_t *d_offsets, uint64_t n_bytes, uint64_t n_sentences,
+                              const int32_t **d_ids, const uint64_t **d_id_offsets, uint64_t *total_ids, bool bos = false,
+                              bool eos = false, bool reverse = false, double dropout_prob = 0) const;
+
   Status id_to_subword(int id, std::string *subword, bool replace_space = false) const;
   int subword_to_id(const std::string &token) const;
 

@@ -30,22 +30,40 @@ void yttm_api_close(void *handle);
 int yttm_api_vocab_size(void *handle);
 void yttm_api_set_dropout_seed(void *handle, uint64_t seed);
 
+/* Thread safety: every call that runs kernels holds a per-handle mutex; results of the two-call entry points below
+ * (encode_ids -> result_ids, encode_subwords / decode / vocab / id_to_subword -> result_counts / _text / _offsets) are
+ * kept per CALLING THREAD, so threads sharing one handle never see each other's results. */
+
 /* yttm.pyx:87-107 encode(output_type='id'): sentence i = bytes[offsets[i], offsets[i+1]) */
 int yttm_api_encode_ids(void *handle, const char *bytes, const uint64_t *offsets, uint64_t n_sent, int bos, int eos,
                         int reverse, double dropout, uint64_t *total_ids);
 void yttm_api_result_ids(void *handle, int32_t *ids, uint64_t *offsets /* n_sent + 1 */);
+/* the same in ONE call into caller-owned buffers: 0 ok, 1 error, 2 ids_cap too small (*total_ids = size needed);
+ * ids_cap >= bytes + 3 * n_sent always suffices */
+int yttm_api_encode_ids_into(void *handle, const char *bytes, const uint64_t *offsets, uint64_t n_sent, int bos, int eos,
+                             int reverse, double dropout, int32_t *ids_out, uint64_t ids_cap, uint64_t *offsets_out,
+                             uint64_t *total_ids);
+/* device-resident input and output (pointers into library-owned device memory, valid until the next encode call) */
+int yttm_api_encode_device(void *handle, const char *d_bytes, const uint64_t *d_offsets, uint64_t n_bytes, uint64_t n_sent,
+                           int bos, int eos, int reverse, double dropout, const int32_t **d_ids,
+                           const uint64_t **d_id_offsets, uint64_t *total_ids);
 
-/* yttm.pyx:108-124 encode(output_type='subword'): pieces joined by 0x01, sentences end with '\n' */
+/* yttm.pyx:108-124 encode(output_type='subword').  Piece lists are LENGTH-FRAMED (a piece may hold any character):
+ * the call returns the byte length of all pieces (or -1); yttm_api_result_counts gives (pieces, sentences),
+ * yttm_api_result_text the bytes, yttm_api_result_offsets the byte offset of every piece (+ end, n_pieces + 1 values)
+ * and the first piece of every sentence (+ end, n_sentences + 1 values; may be NULL). */
 int64_t yttm_api_encode_subwords(void *handle, const char *bytes, const uint64_t *offsets, uint64_t n_sent, int bos,
                                  int eos, int reverse, double dropout);
+void yttm_api_result_counts(void *handle, uint64_t *n_pieces, uint64_t *n_sentences);
 void yttm_api_result_text(void *handle, char *out);
+void yttm_api_result_offsets(void *handle, uint64_t *piece_off, uint64_t *sent_off);
 
-/* yttm.pyx:136-158 decode: one '\n'-terminated line per sentence */
+/* yttm.pyx:136-158 decode: one piece per sentence; id_to_subword: one piece; vocab: vocab_size pieces */
 int64_t yttm_api_decode(void *handle, const int32_t *ids, const uint64_t *offsets, uint64_t n_sent,
                         const int32_t *ignore, uint64_t n_ignore);
 int64_t yttm_api_id_to_subword(void *handle, int id);
 int yttm_api_subword_to_id(void *handle, const char *subword);
-int64_t yttm_api_vocab(void *handle); /* pieces joined by 0x01 */
+int64_t yttm_api_vocab(void *handle);
 
 int yttm_api_encode_cli(void *handle, const char *output_type, int stream, int bos, int eos, int reverse,
                         double dropout);

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import _cases
-from _bind import tmp_model_path
+from _bind import _pack, tmp_model_path
 from _gpu import GpuEncoder, gpu_train
 from youtokentome_b200 import synth
 
@@ -218,3 +218,76 @@ def test_cli_bpe_encode_roundtrip(product, tmp_path):
     dec = subprocess.run(base + ["decode", "--model", model, "--ignore_ids", "2,3"], input=enc, capture_output=True,
                          text=True, cwd=ROOT, check=True).stdout
     assert dec.split("\n")[:-1] == [" ".join(l.split()) for l in test_lines]
+
+
+def check_pieces_with_u0001(tmp_path):
+    """U+0001 is an ordinary alphabet character: piece lists travel length-framed, never split on a separator."""
+    import youtokentome_b200 as yttm
+    train = tmp_path / "t.txt"
+    train.write_bytes(b"a\x01b a\x01b ab \x01\x01 a\x01b ab\n" * 20)
+    bpe = yttm.BPE.train(data=str(train), model=str(tmp_path / "m.yttm"), vocab_size=12)
+    vocab = bpe.vocab()
+    assert len(vocab) == bpe.vocab_size() == 12 and all(vocab) and len(set(vocab)) == 12
+    assert any("\x01" in v for v in vocab)
+    sub = bpe.encode(["a\x01b ab", "\x01", ""], output_type=yttm.OutputType.SUBWORD)
+    assert ["".join(s).replace("\u2581", " ").strip() for s in sub] == ["a\x01b ab", "\x01", ""]
+    ids = bpe.encode(["a\x01b ab", "\x01"])
+    assert bpe.decode(ids) == ["a\x01b ab", "\x01"]
+    assert [bpe.id_to_subword(i) for i in range(12)] == vocab
+
+
+def check_shared_handle_between_threads(oracle):
+    """Two host threads share one BPE object (ctypes releases the GIL during foreign calls): results never mix."""
+    import threading
+    import youtokentome_b200 as yttm
+    m = _model(oracle, _cases.dirty_zipf_text(), 1200)
+    bpe = yttm.BPE(m)
+    batches = [[s.decode(errors="ignore") for s in _cases.zipf_sentences(40 + 17 * k)[k:]] for k in range(4)]
+    want = [bpe.encode(b) for b in batches]
+    want_sub = [bpe.encode(b, output_type=yttm.OutputType.SUBWORD) for b in batches]
+    errs = []
+
+    def body(k):
+        try:
+            for _ in range(6):
+                assert bpe.encode(batches[k]) == want[k]
+                assert bpe.encode(batches[k], output_type=yttm.OutputType.SUBWORD) == want_sub[k]
+                assert bpe.decode(want[k]) == bpe.decode(want[k])
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=body, args=(k,)) for k in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs[0]
+
+
+def test_pieces_with_u0001(product, tmp_path):
+    check_pieces_with_u0001(tmp_path)
+
+
+def test_shared_handle_between_threads(product, oracle):
+    check_shared_handle_between_threads(oracle)
+
+
+def test_encode_packed_outputs(product, oracle):
+    """encode_packed(out=...): numpy / torch / cuda give the same ids; device input stays on the device."""
+    import torch
+    import youtokentome_b200 as yttm
+    m = _model(oracle, _cases.dirty_zipf_text(), 1200)
+    bpe = yttm.BPE(m)
+    sents = _cases.zipf_sentences(500) + list(_cases.EDGE_SENTENCES)
+    buf, offs = _pack(sents)
+    want, woo = oracle.encoder(m).encode_packed(buf, offs, bos=True)
+    ids, oo = bpe.encode_packed(buf, offs, bos=True)
+    assert np.array_equal(ids, want) and np.array_equal(oo, woo)
+    t_ids, t_oo = bpe.encode_packed(buf, offs, bos=True, out="torch")
+    assert t_ids.dtype == torch.int32 and np.array_equal(t_ids.numpy(), want) and np.array_equal(t_oo.numpy(), woo.astype(np.int64))
+    d_bytes = torch.frombuffer(bytearray(buf), dtype=torch.uint8).cuda()
+    d_offs = torch.from_numpy(offs.astype(np.int64)).cuda()
+    c_ids, c_oo = bpe.encode_packed(d_bytes, d_offs, bos=True, out="cuda")
+    assert c_ids.is_cuda and c_oo.is_cuda and np.array_equal(c_ids.cpu().numpy(), want) and np.array_equal(c_oo.cpu().numpy(), woo.astype(np.int64))
+    h_ids, _ = bpe.encode_packed(buf, offs, bos=True, out="cuda")
+    assert h_ids.is_cuda and np.array_equal(h_ids.cpu().numpy(), want)

@@ -494,3 +494,25 @@ def test_encode_space_token_with_id_zero(emu, oracle, special):
     (bpe.cpp:1591-1596; oracle pinned to it in test_oracle_vs_reference.py).  Default kernels (dedup + long words),
     plain kernels and dropout."""
     EG.check_space_id_zero(oracle, special)
+
+
+def test_api_pieces_with_u0001(emu, tmp_path):
+    EG.check_pieces_with_u0001(tmp_path)
+
+
+def test_api_shared_handle_between_threads(emu, oracle):
+    EG.check_shared_handle_between_threads(oracle)
+
+
+def test_api_encode_packed_torch_output(emu, oracle):
+    import torch
+    import youtokentome_b200 as yttm
+    m = EG._model(oracle, _cases.dirty_zipf_text(), 1200)
+    bpe = yttm.BPE(m)
+    sents = _cases.zipf_sentences(200) + list(_cases.EDGE_SENTENCES)
+    buf, offs = EG._pack(sents)
+    want, woo = oracle.encoder(m).encode_packed(buf, offs, eos=True)
+    t_ids, t_oo = bpe.encode_packed(torch.frombuffer(bytearray(buf), dtype=torch.uint8), offs, eos=True, out="torch")
+    assert np.array_equal(t_ids.numpy(), want) and np.array_equal(t_oo.numpy(), woo.astype(np.int64))
+    ids, oo = bpe.encode_packed(np.frombuffer(buf, dtype=np.uint8), offs, eos=True)
+    assert np.array_equal(ids, want) and np.array_equal(oo, woo)

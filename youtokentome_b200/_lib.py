@@ -48,6 +48,10 @@ def bind(L):
         "yttm_api_set_dropout_seed": (None, [vp, u64]),
         "yttm_api_encode_ids": (i32, [vp, vp, vp, u64, i32, i32, i32, dbl, C.POINTER(u64)]),
         "yttm_api_result_ids": (None, [vp, vp, vp]),
+        "yttm_api_encode_ids_into": (i32, [vp, vp, vp, u64, i32, i32, i32, dbl, vp, u64, vp, C.POINTER(u64)]),
+        "yttm_api_encode_device": (i32, [vp, vp, vp, u64, u64, i32, i32, i32, dbl, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]),
+        "yttm_api_result_counts": (None, [vp, C.POINTER(u64), C.POINTER(u64)]),
+        "yttm_api_result_offsets": (None, [vp, vp, vp]),
         "yttm_api_encode_subwords": (i64, [vp, vp, vp, u64, i32, i32, i32, dbl]),
         "yttm_api_result_text": (None, [vp, vp]),
         "yttm_api_decode": (i64, [vp, vp, vp, u64, vp, u64]),
@@ -92,10 +96,16 @@ def bind(L):
         "yttm_enc_run_device": (i32, [vp, vp, vp, u64, u64, i32, i32, i32, dbl, u64, u64, C.POINTER(vp), C.POINTER(vp),
                                       C.POINTER(u64)]),
     }
+    missing = []
     for name, (res, args) in sig.items():
-        f = getattr(L, name)
+        try:
+            f = getattr(L, name)
+        except AttributeError:   # an older build of the library: reported when (and only when) the symbol is used
+            missing.append(name)
+            continue
         f.restype = res
         f.argtypes = args
+    L._yttm_missing = missing
     return L
 
 

@@ -542,6 +542,32 @@ Status BaseEncoder::encode_packed(const char *bytes, const uint64_t *offsets, ui
   return Status();
 }
 
+Status BaseEncoder::encode_packed_into(const char *bytes, const uint64_t *offsets, uint64_t n_sent, int32_t *ids,
+                                       uint64_t ids_cap, uint64_t *id_offsets, uint64_t *total_ids, bool bos, bool eos,
+                                       bool reverse, double dropout_prob) const {
+  if (bos && bpe_state.special_tokens.bos_id == -1) return Status(1, "Can't add <BOS> token. Model was trained without it.");
+  if (eos && bpe_state.special_tokens.eos_id == -1) return Status(1, "Can't add <EOS> token. Model was trained without it.");
+  if (!device_status_.ok()) return device_status_;
+  *total_ids = 0;
+  int rc = yttm_enc_run(enc_, bytes, offsets, n_sent, bos, eos, reverse, dropout_prob, dropout_seed_, sentence_counter_, ids,
+                        ids_cap, id_offsets, total_ids);
+  if (rc == 2) return Status(2, "encode_packed_into: output buffer too small");
+  if (rc) return Status(1, ctx_err(ctx_));
+  if (dropout_prob > 0) sentence_counter_ += n_sent;
+  return Status();
+}
+
+Status BaseEncoder::encode_packed_device(const char *d_bytes, const uint64_t *d_offsets, uint64_t n_bytes, uint64_t n_sent,
+                                         const int32_t **d_ids, const uint64_t **d_id_offsets, uint64_t *total_ids, bool bos,
+                                         bool eos, bool reverse, double dropout_prob) const {
+  if (!device_status_.ok()) return device_status_;
+  int rc = yttm_enc_run_device(enc_, d_bytes, d_offsets, n_bytes, n_sent, bos, eos, reverse, dropout_prob, dropout_seed_,
+                               sentence_counter_, d_ids, d_id_offsets, total_ids);
+  if (rc) return Status(1, ctx_err(ctx_));
+  if (dropout_prob > 0) sentence_counter_ += n_sent;
+  return Status();
+}
+
 Status BaseEncoder::encode_as_ids(const std::vector<std::string> &sentences, std::vector<std::vector<int>> *ids,
                                   bool bos, bool eos, bool reverse, double dropout_prob) const {
   std::vector<uint64_t> offs(sentences.size() + 1, 0);

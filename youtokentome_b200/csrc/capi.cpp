@@ -3,6 +3,7 @@
 // Cython module youtokentome/cpp/yttm.pyx).  Strings are UTF-8; errors come back as
 // (non-zero return, message in the handle / thread-local buffer).
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <unordered_set>
 #include <vector>
@@ -14,12 +15,25 @@ using namespace vkcom;
 
 namespace {
 thread_local std::string g_err;
+// Results of the two-call entry points live in THREAD-LOCAL storage, so two host threads that share one handle (ctypes
+// releases the GIL during foreign calls; the reference's Cython module does not) can never read each other's result or
+// overrun a buffer sized for another thread's total.  The encoder itself keeps mutable device state (double-buffered
+// per-call device buffers, the dropout sentence counter): every call that runs kernels holds the handle's mutex.
+struct Result {
+  std::vector<int32_t> ids;
+  std::vector<uint64_t> offs;
+  std::string text;                 // pieces back to back, no separators
+  std::vector<uint64_t> piece_off;  // n_pieces + 1 byte offsets into text
+  std::vector<uint64_t> sent_off;   // n_sentences + 1 piece indices
+  void clear_text() { text.clear(); piece_off.assign(1, 0); sent_off.assign(1, 0); }
+  void add_piece(const std::string &p) { text += p; piece_off.push_back(text.size()); }
+  void end_sentence() { sent_off.push_back(piece_off.size() - 1); }
+};
+thread_local Result g_res;
 struct Handle {
   BaseEncoder *enc = nullptr;
   std::string err;
-  std::vector<int32_t> ids;
-  std::vector<uint64_t> offs;
-  std::string text;  // last string result
+  std::mutex mu;
 };
 int fail(Handle *h, const std::string &m) { (h ? h->err : g_err) = m; return 1; }
 }  // namespace
@@ -80,90 +94,129 @@ void yttm_api_close(void *hv) {
 
 int yttm_api_vocab_size(void *hv) { return static_cast<Handle *>(hv)->enc->vocab_size(); }
 
-void yttm_api_set_dropout_seed(void *hv, uint64_t seed) { static_cast<Handle *>(hv)->enc->set_dropout_seed(seed); }
+void yttm_api_set_dropout_seed(void *hv, uint64_t seed) {
+  auto *h = static_cast<Handle *>(hv);
+  std::lock_guard<std::mutex> lock(h->mu);
+  h->enc->set_dropout_seed(seed);
+}
 
 int yttm_api_encode_ids(void *hv, const char *bytes, const uint64_t *offsets, uint64_t n_sent, int bos, int eos,
                         int reverse, double dropout, uint64_t *total_ids) {
   auto *h = static_cast<Handle *>(hv);
-  Status st = h->enc->encode_packed(bytes, offsets, n_sent, &h->ids, &h->offs, bos != 0, eos != 0, reverse != 0,
+  std::lock_guard<std::mutex> lock(h->mu);
+  Status st = h->enc->encode_packed(bytes, offsets, n_sent, &g_res.ids, &g_res.offs, bos != 0, eos != 0, reverse != 0,
                                     dropout);
   if (!st.ok()) return fail(h, st.message);
-  *total_ids = h->ids.size();
+  *total_ids = g_res.ids.size();
   return 0;
 }
 
-void yttm_api_result_ids(void *hv, int32_t *ids, uint64_t *offsets) {
-  auto *h = static_cast<Handle *>(hv);
-  if (!h->ids.empty()) std::memcpy(ids, h->ids.data(), h->ids.size() * 4);
-  std::memcpy(offsets, h->offs.data(), h->offs.size() * 8);
+void yttm_api_result_ids(void *, int32_t *ids, uint64_t *offsets) {  // the calling thread's last encode_ids
+  if (!g_res.ids.empty()) std::memcpy(ids, g_res.ids.data(), g_res.ids.size() * 4);
+  std::memcpy(offsets, g_res.offs.data(), g_res.offs.size() * 8);
 }
 
-// pieces joined by '\x01', sentences terminated by '\n'; returns the byte length (fetch with
-// yttm_api_result_text) or -1.
+// One call, caller-supplied buffers (ids_cap >= bytes + 3 * n_sent always suffices).  Returns 0, 1 (error) or 2 (ids_cap
+// too small: *total_ids holds the size needed, nothing written).
+int yttm_api_encode_ids_into(void *hv, const char *bytes, const uint64_t *offsets, uint64_t n_sent, int bos, int eos,
+                             int reverse, double dropout, int32_t *ids_out, uint64_t ids_cap, uint64_t *offsets_out,
+                             uint64_t *total_ids) {
+  auto *h = static_cast<Handle *>(hv);
+  std::lock_guard<std::mutex> lock(h->mu);
+  Status st = h->enc->encode_packed_into(bytes, offsets, n_sent, ids_out, ids_cap, offsets_out, total_ids, bos != 0, eos != 0,
+                                         reverse != 0, dropout);
+  if (st.code == 2) return 2;
+  if (!st.ok()) return fail(h, st.message);
+  return 0;
+}
+
+// Device-resident input and output (torch / CuPy callers): pointers into library-owned device memory, valid until the
+// next encode call on this handle — callers that share a handle between threads copy the result out under their own lock.
+int yttm_api_encode_device(void *hv, const char *d_bytes, const uint64_t *d_offsets, uint64_t n_bytes, uint64_t n_sent, int bos,
+                           int eos, int reverse, double dropout, const int32_t **d_ids, const uint64_t **d_id_offsets,
+                           uint64_t *total_ids) {
+  auto *h = static_cast<Handle *>(hv);
+  std::lock_guard<std::mutex> lock(h->mu);
+  Status st = h->enc->encode_packed_device(d_bytes, d_offsets, n_bytes, n_sent, d_ids, d_id_offsets, total_ids, bos != 0,
+                                           eos != 0, reverse != 0, dropout);
+  if (!st.ok()) return fail(h, st.message);
+  return 0;
+}
+
+// Pieces come back length-framed (no in-band separator: a piece may hold any character, U+0001 included):
+// yttm_api_result_counts -> (pieces, sentences), yttm_api_result_text -> the bytes, yttm_api_result_offsets -> byte
+// offset of every piece (+ end) and first piece of every sentence (+ end).  Returns the byte length or -1.
 int64_t yttm_api_encode_subwords(void *hv, const char *bytes, const uint64_t *offsets, uint64_t n_sent, int bos,
                                  int eos, int reverse, double dropout) {
   auto *h = static_cast<Handle *>(hv);
   std::vector<std::string> s(n_sent);
   for (uint64_t i = 0; i < n_sent; i++) s[i].assign(bytes + offsets[i], bytes + offsets[i + 1]);
   std::vector<std::vector<std::string>> out;
-  Status st = h->enc->encode_as_subwords(s, &out, bos != 0, eos != 0, reverse != 0, dropout);
-  if (!st.ok()) { fail(h, st.message); return -1; }
-  h->text.clear();
-  for (auto &sent : out) {
-    for (size_t j = 0; j < sent.size(); j++) {
-      if (j) h->text.push_back('\x01');
-      h->text += sent[j];
-    }
-    h->text.push_back('\n');
+  {
+    std::lock_guard<std::mutex> lock(h->mu);
+    Status st = h->enc->encode_as_subwords(s, &out, bos != 0, eos != 0, reverse != 0, dropout);
+    if (!st.ok()) { fail(h, st.message); return -1; }
   }
-  return (int64_t)h->text.size();
+  g_res.clear_text();
+  for (auto &sent : out) {
+    for (auto &p : sent) g_res.add_piece(p);
+    g_res.end_sentence();
+  }
+  return (int64_t)g_res.text.size();
 }
 
-void yttm_api_result_text(void *hv, char *out) {
-  auto *h = static_cast<Handle *>(hv);
-  std::memcpy(out, h->text.data(), h->text.size());
+void yttm_api_result_counts(void *, uint64_t *n_pieces, uint64_t *n_sentences) {
+  *n_pieces = g_res.piece_off.size() - 1;
+  *n_sentences = g_res.sent_off.size() - 1;
+}
+void yttm_api_result_text(void *, char *out) { std::memcpy(out, g_res.text.data(), g_res.text.size()); }
+void yttm_api_result_offsets(void *, uint64_t *piece_off, uint64_t *sent_off) {
+  std::memcpy(piece_off, g_res.piece_off.data(), g_res.piece_off.size() * 8);
+  if (sent_off) std::memcpy(sent_off, g_res.sent_off.data(), g_res.sent_off.size() * 8);
 }
 
 int64_t yttm_api_decode(void *hv, const int32_t *ids, const uint64_t *offsets, uint64_t n_sent,
-                        const int32_t *ignore, uint64_t n_ignore) {
+                        const int32_t *ignore, uint64_t n_ignore) {  // one piece per sentence
   auto *h = static_cast<Handle *>(hv);
   std::unordered_set<int> ign(ignore, ignore + n_ignore);
-  h->text.clear();
+  g_res.clear_text();
   for (uint64_t i = 0; i < n_sent; i++) {
     std::vector<int> v(ids + offsets[i], ids + offsets[i + 1]);
     std::string sent;
     Status st = h->enc->decode(v, &sent, &ign);
     if (!st.ok()) { fail(h, st.message); return -1; }
-    h->text += sent;
-    h->text.push_back('\n');
+    g_res.add_piece(sent);
+    g_res.end_sentence();
   }
-  return (int64_t)h->text.size();
+  return (int64_t)g_res.text.size();
 }
 
 int64_t yttm_api_id_to_subword(void *hv, int id) {
   auto *h = static_cast<Handle *>(hv);
-  Status st = h->enc->id_to_subword(id, &h->text);
+  std::string piece;
+  Status st = h->enc->id_to_subword(id, &piece);
   if (!st.ok()) { fail(h, st.message); return -1; }
-  return (int64_t)h->text.size();
+  g_res.clear_text();
+  g_res.add_piece(piece);
+  g_res.end_sentence();
+  return (int64_t)g_res.text.size();
 }
 
 int yttm_api_subword_to_id(void *hv, const char *subword) {
   return static_cast<Handle *>(hv)->enc->subword_to_id(subword);
 }
 
-int64_t yttm_api_vocab(void *hv) {  // '\n'-joined is ambiguous (a piece may be "\n"): use '\x01'
+int64_t yttm_api_vocab(void *hv) {  // length-framed like every piece list (yttm_api_result_counts / _offsets)
   auto *h = static_cast<Handle *>(hv);
-  h->text.clear();
-  auto v = h->enc->vocabulary();
-  for (size_t i = 0; i < v.size(); i++) {
-    if (i) h->text.push_back('\x01');
-    h->text += v[i];
-  }
-  return (int64_t)h->text.size();
+  g_res.clear_text();
+  for (auto &p : h->enc->vocabulary()) g_res.add_piece(p);
+  g_res.end_sentence();
+  return (int64_t)g_res.text.size();
 }
 
 int yttm_api_encode_cli(void *hv, const char *output_type, int stream, int bos, int eos, int reverse, double dropout) {
   auto *h = static_cast<Handle *>(hv);
+  std::lock_guard<std::mutex> lock(h->mu);
   Status st = h->enc->encode_cli(output_type, stream != 0, bos != 0, eos != 0, reverse != 0, dropout);
   if (!st.ok()) return fail(h, st.message);
   return 0;
