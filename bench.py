@@ -157,6 +157,30 @@ def cpu_reference_encode(model, buf, offs, cores, max_sent, reps=1):
                       (n, len(offs) - 1, float(o[-1]) / 1e6, sec, min(secs), reps)}, ids
 
 
+def ref_train_isolated(build, chunk_files, model, vocab, coverage, threads, timeout=600):
+    """The reference's train_bpe in a CHILD process, on the concatenation of cached corpus chunks.  Its multi-threaded
+    trainer is racy (SURVEY 4): on a 128-core host the assert of BigObjectQueue::top (bpe.cpp:232) has fired on the
+    config-5 corpus and would take the bench line with it.  Returns seconds, or a string saying what happened."""
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import _bind\n"
+            "data = b''.join(open(f, 'rb').read() for f in %r)\n"
+            "sec = _bind.Reference(%r).train(data, %r, %d, %r, n_threads=%d)\n"
+            "print('REF_SECONDS', sec)\n") % (ROOT, os.path.join(ROOT, "tests"), list(chunk_files), build, model, vocab, coverage, threads)
+    try:
+        r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout)
+    except subprocess.TimeoutExpired:
+        return "reference timed out after %d s" % timeout
+    for ln in r.stdout.decode(errors="replace").splitlines():
+        if ln.startswith("REF_SECONDS"):
+            return float(ln.split()[1])
+    tail = r.stderr.decode(errors="replace").strip().splitlines()[-1:] or ["no output"]
+    return "reference died (rc %d): %s" % (r.returncode, tail[0][-160:])
+
+
+def chunk_files(kind, ids):
+    return [os.path.join(CACHE, "%s_%d_%d.bin" % (kind, CHUNK, k)) for k in ids]
+
+
 def reference_model(text):
     """The 32k model of the reference arm, trained with the reference itself (DETERMINISTIC_QUEUE build = the tie-break
     order both implementations are pinned to), cached on disk."""
@@ -464,7 +488,7 @@ def main():
                                 "U": st["n_unique"], "T": st["n_tokens"]}
         if not args.no_cpu_baseline and _bind.have_reference("det"):
             mo = os.path.join(CACHE, "model_cfg1_ref.yttm")
-            sec = _bind.Reference("det").train(readme, mo, CFG1_VOCAB, 1.0, n_threads=1)
+            sec = _bind.Reference("det").train(readme, mo, CFG1_VOCAB, 1.0, n_threads=1)   # single-threaded: no race
             cfg_train["config1"]["equals_reference"] = _bind.read_model(mo) == _bind.read_model(m1)
             cfg_train["config1"]["cpu_reference_1thr_s"] = r3(sec)
 
@@ -477,9 +501,10 @@ def main():
                 mg = os.path.join(CACHE, "model_%s_chunk0_gpu.yttm" % key)
                 mr = os.path.join(CACHE, "model_%s_chunk0_ref.yttm" % key)
                 D.train_distributed(chunk, mg, vocab, cov, comm=comm, device=local, sharded=True)
-                sec = _bind.Reference("det").train(chunk, mr, vocab, cov, n_threads=min(8, cores))
-                cfg_train[key]["parity_chunk0"] = {"bytes": len(chunk), "equals_reference": _bind.read_model(mg) == _bind.read_model(mr),
-                                                   "reference_det_8thr_s": r3(sec)}
+                sec = ref_train_isolated("det", chunk_files(kind, [0]), mr, vocab, cov, 1)
+                ok = isinstance(sec, float) and _bind.read_model(mg) == _bind.read_model(mr)
+                cfg_train[key]["parity_chunk0"] = {"bytes": len(chunk), "equals_reference": ok if isinstance(sec, float) else None,
+                                                   "reference_det_1thr_s": r3(sec) if isinstance(sec, float) else sec}
 
         # ---- hot path (a) on a buffer >> L2: the per-merge scan in STREAMING mode (TMA-staged tiles).  Algorithmic
         # bytes 4T + 4U per merge (frequencies are read for rewritten words only); time = device-side timers of the
@@ -578,14 +603,14 @@ def main():
                     row, _ = cpu_reference_encode(model, buf, offs, th, 50_000 * th, reps=3)
                     cpu["n_threads_%d" % th] = {"value": r3(row["value"]), "sample": row["sample"]}
             if _bind.have_reference("prod") and "config3" in cfg_train and not old():
-                shard = b"".join(synth.corpus_chunks("zipf", range(8), CHUNK, cache_dir=CACHE))
-                sec8 = _bind.Reference("prod").train(shard, os.path.join(CACHE, "model_refprod.yttm"), VOCAB, 1.0,
-                                                     n_threads=min(8, cores))
-                sec1 = _bind.Reference("prod").train(shard[:len(shard) // 8].rsplit(b"\n", 1)[0] + b"\n",
-                                                     os.path.join(CACHE, "model_refprod1.yttm"), VOCAB, 1.0, n_threads=1)
-                cpu["train_1GB_8thr"] = {"seconds": r3(sec8), "GBps": r3(len(shard) / sec8 / 1e9)}
-                cpu["train_125MB_1thr"] = {"seconds": r3(sec1), "GBps": r3(len(shard) / 8 / sec1 / 1e9)}
-                cfg_train["config3"]["speedup_vs_reference_8thr"] = r3(sec8 / cfg_train["config3"]["wall_s"])
+                nb = cfg_train["config3"]["bytes"]
+                sec8 = ref_train_isolated("prod", chunk_files("zipf", range(8)), os.path.join(CACHE, "model_refprod.yttm"), VOCAB, 1.0,
+                                          min(8, cores))
+                sec1 = ref_train_isolated("prod", chunk_files("zipf", [0]), os.path.join(CACHE, "model_refprod1.yttm"), VOCAB, 1.0, 1)
+                cpu["train_1GB_8thr"] = {"seconds": r3(sec8), "GBps": r3(nb / sec8 / 1e9)} if isinstance(sec8, float) else {"error": sec8}
+                cpu["train_125MB_1thr"] = {"seconds": r3(sec1), "GBps": r3(nb / 8 / sec1 / 1e9)} if isinstance(sec1, float) else {"error": sec1}
+                if isinstance(sec8, float):
+                    cfg_train["config3"]["speedup_vs_reference_8thr"] = r3(sec8 / cfg_train["config3"]["wall_s"])
 
     if rank == 0:
         config = {"workload": WORKLOAD, "sharding": "per GPU: the workload above on every rank (weak scaling), no collective",

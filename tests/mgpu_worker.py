@@ -25,7 +25,16 @@ def main():
     text = _cases.dirty_zipf_text(2_000_000)
     model = "/tmp/yttm_mgpu_%d.yttm" % world
     for cov in (1.0, 0.98):
-        n = D.train_distributed(text, model, 3000, coverage=cov)
+        st = {}
+        n = D.train_distributed(text, model, 3000, coverage=cov, stats_out=st)
+        # every rank elected the same merges, and the job's unique words are a partition (each word on one rank)
+        t = torch.tensor([n, st["n_unique"], st["n_tokens"]], dtype=torch.int64, device="cuda")
+        g = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(g, t)
+        assert len({int(x[0]) for x in g}) == 1, "ranks disagree on the number of merges"
+        if rank == 0:
+            print("unique words per rank:", [int(x[1]) for x in g], "tokens per rank:", [int(x[2]) for x in g],
+                  "us/merge %.2f" % (st["merge_loop_ms"] * 1e3 / max(n, 1)), st["phase_us_per_iter"])
         if rank == 0:
             orc = Oracle()
             m = tmp_model_path("orc")

@@ -31,6 +31,9 @@ def main():
     n_ok = 0
     corpora = [(synth.stress_text(3), 60, 1.0), (synth.stress_text(11), 90, 0.97), (_cases.dirty_zipf_text(30_000), 400, 0.98),
                (synth.readme_corpus(n_lines=60), 120, 1.0)]
+    quick = bool(os.environ.get("YTTM_SANITIZE_QUICK"))   # under a sanitizer: fewer corpora, fewer encode variants
+    if quick:
+        corpora = corpora[1:3]
     for stream, tiny in ((False, False), (True, False), (False, True), (True, True)):
         for k in ("YTTM_FORCE_STREAM", "YTTM_STREAM_Q", "YTTM_STAGES", "YTTM_XQ_SEG_CAP", "YTTM_PAIR_CAP_FLOOR"):
             os.environ.pop(k, None)
@@ -53,7 +56,10 @@ def main():
     long_word = b"".join(zc.sentences(12, 60, seed=6)).replace(b" ", b"")
     sents = _cases.zipf_sentences(150) + list(_cases.EDGE_SENTENCES) + [long_word, b"a" * 700 + b" " + b"a" * 700, long_word + b" x " + long_word]
     g, o = GpuEncoder(model), orc.encoder(model)
-    for env in [[]] + [[k] for k in ENC_KNOBS] + [["YTTM_ENC_FIND_VEC", "YTTM_ENC_DEDUP"], ["YTTM_ENC_FIND_CACHED", "YTTM_ENC_BUCKETED", "YTTM_ENC_ZLIN"]]:
+    variants = [[]] + [[k] for k in ENC_KNOBS] + [["YTTM_ENC_FIND_VEC", "YTTM_ENC_DEDUP"], ["YTTM_ENC_FIND_CACHED", "YTTM_ENC_BUCKETED", "YTTM_ENC_ZLIN"]]
+    if quick:
+        variants = [[], ["YTTM_ENC_PLAIN"], ["YTTM_ENC_BUCKETED", "YTTM_ENC_LONG"]]
+    for env in variants:
         for k in ENC_KNOBS:
             os.environ.pop(k, None)
         for k in env:

@@ -13,42 +13,47 @@
 //   * the same segment is written, with the same stores, into the exchange buffer of every
 //     other GPU of the job over NVLink (peer pointers, Xq::base[]) — the exchange step of the
 //     multi-GPU merge loop is fused into the kernel, there is no NCCL call per merge;
-//   * after the grid barrier that ends the apply phase every block drains ALL segments of ALL
-//     GPUs, keeps the entries whose key it owns, applies them to its partition and then finds
-//     the best pair of its partition (exact arg-max under MergeCandidate::operator<,
-//     bpe.cpp:110-126); every GPU holds the full table, so every GPU elects the same pair
-//     without a second exchange;
-//   * a second grid barrier publishes the per-block winners; every block reduces them
-//     redundantly.
-// Per merge: two grid barriers (as before), but the table updates of merge k are applied by
-// their owners in parallel instead of by the block that happens to rewrite the word, and the
-// arg-max of a block covers cap/gridDim slots that only it has modified.
+//   * every block drains ALL segments of ALL GPUs, keeps the entries whose key it owns and
+//     applies them to its partition; every GPU holds the full table, so every GPU elects the
+//     same pair without a second exchange;
+//   * the arg-max of a partition (exact, under MergeCandidate::operator<, bpe.cpp:110-126) is
+//     CACHED per block and maintained from the drained entries (only touched slots can change);
+//     a full sweep of the partition happens at launch and after the block's best was consumed or
+//     lowered.
+// There is NO grid barrier in the loop.  The two synchronisation points of a merge are words
+// that carry their own stamp: a block ends its apply phase by storing "round | flags | entries"
+// for its segment (release); a block starts its drain by polling those words of all blocks (of
+// all GPUs) until they carry the round (acquire) — barrier and count fetch are one round trip.
+// Likewise every block publishes its cached best as two stamped 64-bit words and polls the
+// others': barrier and winner reduction are one round trip.  (Measured on B200, 100 MB Zipf
+// corpus: two cg grid.sync() + separate fetches cost 14 dependent L2 round trips = 18.7 us per
+// merge, profiles/r02_merge_loop_phases.md.)  The launch is still cooperative: all blocks must
+// be co-resident for the polling to terminate.
 // Words live in TILES: RESIDENT mode keeps tile b in the shared memory of block b for the whole
 // launch; STREAMING mode (token buffer larger than the chip's shared memory) stages tiles through
 // a TMA ring every merge (see below).
 #pragma once
 
-constexpr int SWEEP_UNROLL = 8;  // arg-max sweep: table counts in flight per thread
+constexpr int SWEEP_UNROLL = 8;  // partition sweep: table counts in flight per thread
 
 // ---- exchange buffer ("xq") --------------------------------------------------------------------
 // Every rank owns one region: [parity 0/1][sender 0..world-1]{ XqHdr, entries[nblocks][seg_cap] }.
-// Round r (r = 1, 2, ...) uses parity r & 1.  A sender writes its entries and per-block counts
-// into slot [r & 1][me] of EVERY rank's region (its own included), then — after a grid barrier
-// and a system-scope fence — the word seq_flags = (r << 8) | flags of the remote copies.
-// Double buffering suffices: a sender can start round r + 2 only after it has drained round
-// r + 1 of every peer, which those peers publish after they have finished draining round r.
+// Round r (r = 1, 2, ...) uses parity r & 1.  Block b of sender s writes its entries into segment
+// [r & 1][s][b] of EVERY rank's region (its own included) and then, after a fence, the count word
+// of that segment: (r << 32) | flags | entries.  Double buffering suffices: a block can write
+// round r + 2 only after it has seen every block's best of iteration r + 2, which those blocks
+// publish after they have finished draining round r.
 constexpr int XQ_MAX_WORLD = 8;
 constexpr int XQ_MAX_BLOCKS = 256;
-constexpr uint32_t XQF_COMPACT = 1u;    // sender wants a compaction of its packed words (rank-local state)
-constexpr uint32_t XQF_OVERFLOW = 2u;   // a segment of the sender overflowed: counts are stale, rebuild the table
-constexpr uint32_t XQF_MORE = 4u;       // out-of-loop table rounds: the sender has more chunks to publish
-constexpr uint32_t XQ_CNT_OVF = 0x80000000u;   // count word: the segment overflowed
-constexpr uint32_t XQ_CNT_MORE = 0x40000000u;  // count word (table rounds): further entries follow in the next round
-constexpr uint32_t XQ_CNT_MASK = 0x3fffffffu;
+constexpr uint32_t XQF_COMPACT = 1u;     // some block wants a compaction of its packed words
+constexpr uint32_t XQF_OVERFLOW = 2u;    // a segment overflowed: counts are stale, rebuild the table
+constexpr uint32_t XQF_MORE = 4u;        // out-of-loop table rounds: a sender has more chunks to publish
+constexpr uint32_t XQ_CNT_OVF = 0x80000000u;      // count word: the segment overflowed
+constexpr uint32_t XQ_CNT_MORE = 0x40000000u;     // count word (table rounds): further entries follow in the next round
+constexpr uint32_t XQ_CNT_COMPACT = 0x20000000u;  // count word: > 25 % of the block's token slots are dead
+constexpr uint32_t XQ_CNT_MASK = 0x0fffffffu;
 struct XqHdr {
-  unsigned long long seq_flags;       // written LAST by the sender (remote copies only)
-  unsigned long long pad;
-  uint32_t counts[XQ_MAX_BLOCKS];     // entries of the sender's segment b (bit 31: it overflowed)
+  unsigned long long counts[XQ_MAX_BLOCKS];  // (round << 32) | flags | entries of the sender's segment b
 };
 struct Xq {
   unsigned char *base[XQ_MAX_WORLD];  // region of every rank; base[me] is local memory
@@ -69,29 +74,57 @@ __device__ __forceinline__ XqHdr *xq_hdr(const Xq &x, uint32_t rank, uint32_t pa
 __device__ __forceinline__ size_t xq_seg_off(const Xq &x, uint32_t parity, uint32_t sender, uint32_t block) {
   return (size_t)(parity * x.world + sender) * x.per_sender + sizeof(XqHdr) + (size_t)block * x.seg_cap * sizeof(uint4);
 }
-// system-scope release store / acquire load of a flag word in (possibly peer) global memory
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+// release store / acquire load of a stamped word in (possibly peer) global memory; sys: system scope (NVLink peers)
+__device__ __forceinline__ void st_release(unsigned long long *p, unsigned long long v, bool sys) {
 #ifndef YT_SIMT_EMU
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+  if (sys) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+  else asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 #else
   __atomic_store_n(p, v, __ATOMIC_RELEASE);
 #endif
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long *p, bool sys) {
 #ifndef YT_SIMT_EMU
   unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  if (sys) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  else asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 #else
   return __atomic_load_n(p, __ATOMIC_ACQUIRE);
 #endif
 }
-__device__ __forceinline__ void fence_sys() {
+__device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long *p) {
 #ifndef YT_SIMT_EMU
-  __threadfence_system();
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+#else
+  return __atomic_load_n(p, __ATOMIC_RELAXED);
+#endif
+}
+__device__ __forceinline__ void st_relaxed(unsigned long long *p, unsigned long long v) {
+#ifndef YT_SIMT_EMU
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#else
+  __atomic_store_n(p, v, __ATOMIC_RELAXED);
+#endif
+}
+__device__ __forceinline__ void fence_scope(bool sys) {
+#ifndef YT_SIMT_EMU
+  if (sys) __threadfence_system(); else __threadfence();
 #else
   __atomic_thread_fence(__ATOMIC_SEQ_CST);
 #endif
+}
+
+// A block's best pair as two self-stamped 64-bit words (no barrier, no third word to order):
+//   w0 = stamp16 | count48          w1 = stamp16 | flags3 | prio45
+// prio45 orders like pair_prio (smaller max(x,y), then smaller min, then larger x) for ids < 2^22.
+constexpr uint32_t BB_ID_LIMIT = 1u << 22;
+constexpr unsigned long long BB_LOW48 = 0xffffffffffffull;
+__device__ __forceinline__ unsigned long long bb_prio45(uint32_t x, uint32_t y) {
+  const uint32_t mx = x > y ? x : y, mn = x > y ? y : x;
+  return ((unsigned long long)(0x3fffffu - mx) << 23) | ((unsigned long long)(0x3fffffu - mn) << 1) | (x >= y ? 1ull : 0ull);
 }
 
 struct LoopArgs {
@@ -113,13 +146,14 @@ struct LoopArgs {
   PairTab tab;                 // tab.nparts == gridDim.x
   Xq xq;
   YtLoopCtl *ctl;
-  unsigned long long *blockbest;  // 4 per block: count, prio, slot, flags
+  unsigned long long *blockbest;  // 2 self-stamped words per block (bb_* above); cleared before every launch
   uint32_t *rules;                // 3 per merge
   unsigned long long *rfreq;
   uint32_t first_new_id;          // id of merge number 0
   uint32_t max_total;             // stop when ctl->n_done reaches this
   uint32_t max_iters;             // iterations allowed in this launch
-  uint32_t key_limit;             // leave for a rebuild above this table occupancy
+  uint32_t part_limit;            // leave for a rebuild when a partition holds more keys than this
+  uint32_t dead_min_slots;        // a block wishes a compaction only if it owns more token slots than this
   unsigned long long spin_limit_ns;  // a peer that stays silent this long traps the kernel (never hang the box)
 };
 
@@ -430,46 +464,62 @@ extern __shared__ __align__(16) uint32_t yt_dyn_smem[];
 #define yt_dyn_smem (reinterpret_cast<uint32_t *>(emu::dyn_smem()))
 #endif
 
-// Wait until every OTHER rank has published round `round` into this rank's region; returns the
-// OR of their flags.  One thread per peer polls local memory (the peers wrote it over NVLink).
-__device__ __forceinline__ uint32_t xq_wait_peers(const LoopArgs &a, uint32_t round) {
+// Poll the count words of round `round` of every (sender, block) segment in this rank's region until they carry the
+// round, and leave the entry counts in s_pref[0 .. world * nblocks).  Barrier and count fetch in one: a word becomes
+// visible after its block's entries (release / acquire).  Thread t owns the consecutive segments [t * ipt, (t+1) * ipt).
+// Returns (block-uniform, through *s_acc) the OR of XQF_* flags seen; skip_self: this rank's own segments count as empty.
+__device__ __forceinline__ void xq_poll_counts(const LoopArgs &a, uint32_t round, bool skip_self, uint32_t *s_pref,
+                                               uint32_t *s_acc) {
+  const uint32_t nseg = a.xq.world * a.xq.nblocks, parity = round & 1u;
+  const uint32_t ipt = (nseg + blockDim.x - 1) / blockDim.x;
+  const bool sys = a.xq.world > 1;
   uint32_t flags = 0;
-  if (threadIdx.x < a.xq.world && threadIdx.x != a.xq.me) {
-    const XqHdr *h = xq_hdr(a.xq, a.xq.me, round & 1u, threadIdx.x);
-    const unsigned long long t0 = gtimer();
+  unsigned long long t0 = 0;
+  for (uint32_t k = 0; k < ipt; k++) {
+    const uint32_t j = threadIdx.x * ipt + k;
+    if (j >= nseg) break;
+    const uint32_t s = j / a.xq.nblocks, b = j - s * a.xq.nblocks;
+    const unsigned long long *w = &xq_hdr(a.xq, a.xq.me, parity, s)->counts[b];
+    unsigned long long v;
     for (uint32_t spin = 0;; spin++) {
-      const unsigned long long v = ld_acquire_sys(&h->seq_flags);
-      if ((uint32_t)(v >> 8) == round) { flags = (uint32_t)v & 0xffu; break; }
+      v = ld_acquire(w, sys);
+      if ((uint32_t)(v >> 32) == round) break;
 #ifdef YT_SIMT_EMU
       emu::yield();
 #endif
-      if ((spin & 1023u) == 1023u && gtimer() - t0 > a.spin_limit_ns) loop_trap();
+      if ((spin & 4095u) == 4095u) {
+        if (!t0) t0 = gtimer();
+        else if (gtimer() - t0 > a.spin_limit_ns) loop_trap();
+      }
     }
+    const uint32_t c = (uint32_t)v;
+    if (c & XQ_CNT_OVF) flags |= XQF_OVERFLOW;
+    if (c & XQ_CNT_MORE) flags |= XQF_MORE;
+    if (c & XQ_CNT_COMPACT) flags |= XQF_COMPACT;
+    uint32_t n = c & XQ_CNT_MASK;
+    if (n > a.xq.seg_cap) n = a.xq.seg_cap;
+    s_pref[j] = (skip_self && s == a.xq.me) ? 0u : n;
   }
-  return flags;
+  if (flags) atomicOr(s_acc, flags);
+  __syncthreads();
 }
 
-// Drain round `round`: every entry of every sender's segments whose key belongs to partition
-// blockIdx.x is applied to that partition.  s_pref: world * nblocks + 1 words of shared memory.
-// Returns (block-uniform) bit 0: a segment overflowed, bit 1: a sender announced more chunks; *s_occ_add is increased by the keys this call inserted.
-__device__ __forceinline__ uint32_t xq_drain(const LoopArgs &a, uint32_t round, bool skip_self, uint32_t *s_pref,
-                                             uint32_t *s_scan /* 33 words */, uint32_t *s_occ_add) {
+// Up to DRAIN_KEEP table slots a thread has updated in one drain (for the cached arg-max); more: the block sweeps.
+constexpr int DRAIN_KEEP = 4;
+struct Touched { uint64_t slot[DRAIN_KEEP]; unsigned long long key[DRAIN_KEEP]; uint32_t n; };
+
+// Drain: s_pref holds the entry counts (xq_poll_counts); every entry whose key belongs to partition blockIdx.x is
+// applied to that partition.  *s_occ_add is increased by the keys inserted; `tch` records what this thread touched.
+__device__ __forceinline__ void xq_drain(const LoopArgs &a, uint32_t round, uint32_t *s_pref, uint32_t *s_scan /* 33 words */,
+                                         uint32_t *s_occ_add, Touched &tch) {
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const uint32_t nseg = a.xq.world * a.xq.nblocks, parity = round & 1u;
-  // ---- segment sizes -> exclusive prefix in shared memory (items per thread: ceil(nseg / blockDim))
   const uint32_t ipt = (nseg + blockDim.x - 1) / blockDim.x;
-  uint32_t mine = 0, ovf = 0;
+  // ---- exclusive prefix of the segment sizes, in place
+  uint32_t mine = 0;
   for (uint32_t k = 0; k < ipt; k++) {
     const uint32_t j = threadIdx.x * ipt + k;
-    if (j < nseg) {
-      const uint32_t s = j / a.xq.nblocks, b = j - s * a.xq.nblocks;
-      uint32_t c = __ldcg(&xq_hdr(a.xq, a.xq.me, parity, s)->counts[b]);
-      if (c & XQ_CNT_OVF) ovf |= 1u;
-      if (c & XQ_CNT_MORE) ovf |= 2u;
-      c &= XQ_CNT_MASK;
-      if (skip_self && s == a.xq.me) c = 0;
-      mine += c < a.xq.seg_cap ? c : a.xq.seg_cap;
-    }
+    if (j < nseg) mine += s_pref[j];
   }
   uint32_t x = mine;
   for (int o = 1; o < 32; o <<= 1) {
@@ -477,7 +527,7 @@ __device__ __forceinline__ uint32_t xq_drain(const LoopArgs &a, uint32_t round, 
     if (lane >= (unsigned)o) x += y;
   }
   if (lane == 31) s_scan[wid] = x;
-  ovf = (__syncthreads_or((int)(ovf & 1u)) ? 1u : 0u) | (__syncthreads_or((int)(ovf & 2u)) ? 2u : 0u);
+  __syncthreads();
   if (wid == 0) {
     const uint32_t v = lane < nwarp ? s_scan[lane] : 0u;
     uint32_t xs = v;
@@ -493,17 +543,10 @@ __device__ __forceinline__ uint32_t xq_drain(const LoopArgs &a, uint32_t round, 
     uint32_t run = s_scan[wid] + x - mine;  // exclusive prefix of this thread's first item
     for (uint32_t k = 0; k < ipt; k++) {
       const uint32_t j = threadIdx.x * ipt + k;
-      if (j < nseg) {
-        const uint32_t s = j / a.xq.nblocks, b = j - s * a.xq.nblocks;
-        uint32_t c = (skip_self && s == a.xq.me) ? 0u : __ldcg(&xq_hdr(a.xq, a.xq.me, parity, s)->counts[b]) & XQ_CNT_MASK;
-        if (c > a.xq.seg_cap) c = a.xq.seg_cap;
-        s_pref[j] = run;
-        run += c;
-      }
+      if (j < nseg) { const uint32_t c = s_pref[j]; s_pref[j] = run; run += c; }
     }
   }
   const uint32_t total = s_scan[32];
-  __syncthreads();
   if (threadIdx.x == 0) s_pref[nseg] = total;
   __syncthreads();
   // ---- entries
@@ -521,20 +564,70 @@ __device__ __forceinline__ uint32_t xq_drain(const LoopArgs &a, uint32_t round, 
     const long long delta = (long long)(((unsigned long long)e.w << 32) | e.z);
     const uint64_t hh = mix64(key);
     if (pair_part(a.tab, hh) != blockIdx.x) continue;
-    added += pair_add_at(a.tab, (uint64_t)blockIdx.x * R, (uint32_t)hh & a.tab.rmask, key, delta) ? 1u : 0u;
+    uint64_t slot = ~0ull;
+    added += pair_add_at(a.tab, (uint64_t)blockIdx.x * R, (uint32_t)hh & a.tab.rmask, key, delta, &slot) ? 1u : 0u;
+    if (tch.n < (uint32_t)DRAIN_KEEP) {
+#pragma unroll
+      for (int q = 0; q < DRAIN_KEEP; q++)
+        if ((uint32_t)q == tch.n) { tch.slot[q] = slot; tch.key[q] = key; }
+    }
+    tch.n++;
   }
   if (added) atomicAdd(s_occ_add, added);
-  return ovf;
+}
+
+// Exact arg-max of this block's partition (all threads; two passes: the largest count first, keys only for the
+// slots that hold it).  Result in *s_out (shared); s_warp: 32 Best of scratch.
+__device__ __forceinline__ void sweep_partition(const LoopArgs &a, uint64_t pbase, uint32_t R, Best *s_warp, Best *s_out) {
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  unsigned long long cmax = 0;
+  for (uint32_t i0 = threadIdx.x; i0 < R; i0 += blockDim.x * SWEEP_UNROLL) {
+    unsigned long long c[SWEEP_UNROLL];
+#pragma unroll
+    for (int u = 0; u < SWEEP_UNROLL; u++) {
+      const uint32_t i = i0 + (uint32_t)u * blockDim.x;
+      c[u] = i < R ? __ldcg(a.tab.cnts + pbase + i) : 0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < SWEEP_UNROLL; u++) cmax = c[u] > cmax ? c[u] : cmax;
+  }
+  for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, cmax, o); cmax = v > cmax ? v : cmax; }
+  if (lane == 0) s_warp[wid].c = cmax;
+  __syncthreads();
+  {
+    unsigned long long v = lane < nwarp ? s_warp[lane].c : 0ull;
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
+    cmax = v;  // every warp computes the block maximum
+  }
+  __syncthreads();
+  Best b{0, 0, 0};
+  if (cmax) {
+    for (uint32_t i = threadIdx.x; i < R; i += blockDim.x) {   // counts again (L2 hits); keys of the maxima only
+      if (__ldcg(a.tab.cnts + pbase + i) != cmax) continue;
+      const unsigned long long k = __ldcg(a.tab.keys + pbase + i);
+      Best cand{cmax, pair_prio((uint32_t)(k >> 32), (uint32_t)k), pbase + i};
+      if (better(cand, b)) b = cand;
+    }
+  }
+  b = warp_best(b);
+  if (lane == 0) s_warp[wid] = b;
+  __syncthreads();
+  if (wid == 0) {
+    Best v = lane < nwarp ? s_warp[lane] : Best{0, 0, 0};
+    v = warp_best(v);
+    if (lane == 0) *s_out = v;
+  }
+  __syncthreads();
 }
 
 __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
-  cg::grid_group grid = cg::this_grid();
   __shared__ Best s_warp[32];
-  __shared__ Best s_best;
+  __shared__ Best s_best, s_cb;      // the elected pair of this iteration / the cached best of this block's partition
   __shared__ unsigned long long s_dead;
-  __shared__ uint32_t s_defer_n, s_direct, s_out_n, s_occ, s_xf, s_bflags, s_scan[33];
+  __shared__ uint32_t s_defer_n, s_direct, s_out_n, s_occ, s_xf, s_bflags, s_sweep, s_scan[33];
   __shared__ unsigned long long s_tpre;
   const bool dbgt = (a.dbg & 8u) != 0;  // per-block phase timing (diagnostic)
+  const bool sys = a.xq.world > 1;
   // dynamic shared memory: [segment prefix: XQ_MAX_WORLD * XQ_MAX_BLOCKS + 1 words][claim bitmaps][tile tokens][tile offsets]
   uint32_t *s_pref = yt_dyn_smem;
   uint32_t *s_claim = s_pref + (XQ_MAX_WORLD * XQ_MAX_BLOCKS + 4);  // 2 bitmaps of CLAIM_WORDS x 32 flags
@@ -561,137 +654,121 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   const uint32_t R = a.tab.rmask + 1;
   const uint64_t pbase = (uint64_t)blockIdx.x * R;  // this block's partition of the pair table
   const uint32_t n_done0 = a.ctl->n_done;
-  uint32_t round = a.ctl->xq_round;                   // last exchange round completed by every rank
-  bool pending = false;                               // a published round waits to be drained
+  uint32_t round = a.ctl->xq_round;                   // exchange rounds completed so far (same on every rank)
 
   // occupancy of this block's partition (keys never leave the table between rebuilds)
   {
     uint32_t occ = 0;
     for (uint32_t i = threadIdx.x; i < R; i += blockDim.x) occ += __ldcg(a.tab.keys + pbase + i) != PK_EMPTY ? 1u : 0u;
     for (int o = 16; o > 0; o >>= 1) occ += __shfl_xor_sync(0xffffffffu, occ, o);
-    if (threadIdx.x == 0) { s_occ = 0; s_xf = 0; s_bflags = 0; s_tpre = 0; }
+    if (threadIdx.x == 0) { s_occ = 0; s_xf = 0; s_bflags = 0; s_tpre = 0; s_sweep = 0; s_dead = 0; }
     __syncthreads();
     if (lane == 0 && occ) atomicAdd(&s_occ, occ);
   }
 
   // resident mode: this block's tile moves into shared memory once
   uint32_t rw0 = 0, rw1 = 0;
+  unsigned long long my_slots = 0;   // token slots this block owns (for its compaction wish)
   if (a.resident && blockIdx.x < a.n_tiles) {
     rw0 = a.tile_desc[blockIdx.x].x;
     rw1 = a.tile_desc[blockIdx.x + 1].x;
+    my_slots = a.tile_desc[blockIdx.x + 1].y - a.tile_desc[blockIdx.x].y;
     if (rw1 > rw0) {
       load_tile(a, rw0, rw1, stok, soff);
       for (uint32_t i = threadIdx.x; i < rw1 - rw0; i += blockDim.x) sfreq[i] = a.freq[rw0 + i];
     }
+  } else if (!a.resident) {
+    const uint32_t per_block = (a.n_tiles + gridDim.x - 1) / gridDim.x;
+    const uint32_t k0 = min(a.n_tiles, blockIdx.x * per_block), k1 = min(a.n_tiles, k0 + per_block);
+    my_slots = a.tile_desc[k1].y - a.tile_desc[k0].y;
   }
-  __syncthreads();
+  unsigned long long my_dead = 0;    // token slots of this block tombstoned in this launch (thread 0 keeps the sum)
+  sweep_partition(a, pbase, R, s_warp, &s_cb);   // the cached arg-max starts exact (has the block barriers)
 
   for (uint32_t it = 0; it <= a.max_iters; ++it) {
     const uint32_t n_done = n_done0 + it;
-    unsigned long long tq0 = gtid == 0 ? gtimer() : 0, tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0;
-    const unsigned long long tw0 = dbgt && lane == 0 ? gtimer() : 0;
-    // ---------------- drain: the count changes of the previous merge, from every GPU
-    if (pending) {  // block-uniform
-      if (a.xq.world > 1) {
-        const uint32_t f = xq_wait_peers(a, round);
-        if (f) atomicOr(&s_xf, f);
-        __syncthreads();  // the peers' data is ordered behind the acquire loads of the polling threads
+    const uint32_t stamp = (it % 65535u) + 1u;         // never 0: the array is cleared before the launch
+    unsigned long long tq0 = gtid == 0 ? gtimer() : 0, tq1 = 0, tq2 = 0, tq2b = 0, tq3 = 0;
+    // ---------------- publish this block's best (two self-stamped words) and poll everybody's: barrier + winner
+    // reduction in one round trip.  flags: 1 = this partition is over the load limit, 2 = it ran full (update lost).
+    if (threadIdx.x == 0) {
+      const Best cb = s_cb;
+      uint32_t fl = (s_occ > a.part_limit ? 1u : 0u) | (__ldcg(a.tab.overflow) ? 2u : 0u);
+      uint32_t x = 0, y = 0;
+      if (cb.c) {  // (x, y) from the 64-bit priority word
+        const uint32_t mx = 0xffffffffu - (uint32_t)(cb.prio >> 32), mn = 0x7fffffffu - (uint32_t)((cb.prio & 0xffffffffull) >> 1);
+        x = (cb.prio & 1ull) ? mx : mn;
+        y = (cb.prio & 1ull) ? mn : mx;
       }
-      if ((xq_drain(a, round, false, s_pref, s_scan, &s_occ) & 1u) && threadIdx.x == 0) atomicOr(&s_xf, XQF_OVERFLOW);
-      // this rank's own compaction wish is a function of ctl, which is quiescent since the barrier
-      if (threadIdx.x == 0) {
-        const unsigned long long dd = __ldcg(&a.ctl->dead), sl = __ldcg(&a.ctl->slots);
-        if (dd * 4 > sl && sl > 65536) atomicOr(&s_xf, XQF_COMPACT);
-      }
-      pending = false;
+      st_relaxed(a.blockbest + 2 * blockIdx.x, ((unsigned long long)stamp << 48) | (cb.c & BB_LOW48));
+      st_relaxed(a.blockbest + 2 * blockIdx.x + 1, ((unsigned long long)stamp << 48) | ((unsigned long long)fl << 45) |
+                                                    (cb.c ? bb_prio45(x, y) : 0ull));
     }
-    __syncthreads();  // the partition is up to date (drain's atomics are block-local traffic to L2: ordered by the barrier)
-    if (gtid == 0) tq1 = gtimer();
-    if (dbgt && lane == 0) atomicMax(&s_tpre, gtimer() - tw0);
-    // ---------------- arg-max over this block's partition under MergeCandidate::operator< (bpe.cpp:110-126)
-    Best b{0, 0, 0};
-    for (uint32_t i0 = threadIdx.x; i0 < R; i0 += blockDim.x * SWEEP_UNROLL) {
-      unsigned long long c[SWEEP_UNROLL];
-#pragma unroll
-      for (int u = 0; u < SWEEP_UNROLL; u++) {
-        const uint32_t i = i0 + (uint32_t)u * blockDim.x;
-        c[u] = i < R ? __ldcg(a.tab.cnts + pbase + i) : 0ull;
-      }
-#pragma unroll
-      for (int u = 0; u < SWEEP_UNROLL; u++) {
-        if (c[u] != 0 && c[u] >= b.c) {
-          const uint64_t i = pbase + i0 + (uint64_t)u * blockDim.x;
-          const unsigned long long k = __ldcg(a.tab.keys + i);
-          Best cand{c[u], pair_prio((uint32_t)(k >> 32), (uint32_t)k), i};
-          if (better(cand, b)) b = cand;
-        }
-      }
-    }
-    b = warp_best(b);
-    if (lane == 0) s_warp[wid] = b;
-    __syncthreads();
-    if (wid == 0) {
-      Best v = lane < nwarp ? s_warp[lane] : Best{0, 0, 0};
-      v = warp_best(v);
-      if (lane == 0) {
-        a.blockbest[4 * blockIdx.x + 0] = v.c;
-        a.blockbest[4 * blockIdx.x + 1] = v.prio;
-        a.blockbest[4 * blockIdx.x + 2] = v.slot;
-        // bit 0: this partition is nearly full (deterministic in the key set, hence the same on every rank);
-        // bits 8..: exchange flags seen by this block (identical in all blocks of all ranks)
-        a.blockbest[4 * blockIdx.x + 3] = ((unsigned long long)s_occ * 8ull > (unsigned long long)R * 7ull ? 1ull : 0ull) |
-                                          ((unsigned long long)s_xf << 8);
-      }
-    }
-    if (gtid == 0) tq2 = gtimer();
-    grid.sync();
-    if (gtid == 0) tq3 = gtimer();
-    uint32_t bflags = 0;
-    {  // every block reduces the per-block winners redundantly: one entry per thread, one round trip
-      Best v{0, 0, 0};
+    {
+      unsigned long long bc = 0, bp = 0;   // best (count48, prio45) this thread has seen
+      uint32_t bw = 0xffffffffu, fl = 0;   // ... and the block that owns it
+      unsigned long long t0 = 0;
       for (unsigned j = threadIdx.x; j < gridDim.x; j += blockDim.x) {
-        Best w{__ldcg(a.blockbest + 4 * j), __ldcg(a.blockbest + 4 * j + 1), __ldcg(a.blockbest + 4 * j + 2)};
-        bflags |= (uint32_t)__ldcg(a.blockbest + 4 * j + 3);
-        if (better(w, v)) v = w;
+        unsigned long long w0, w1;
+        for (uint32_t spin = 0;; spin++) {
+          w0 = ld_relaxed(a.blockbest + 2 * j);
+          w1 = ld_relaxed(a.blockbest + 2 * j + 1);
+          if ((uint32_t)(w0 >> 48) == stamp && (uint32_t)(w1 >> 48) == stamp) break;
+#ifdef YT_SIMT_EMU
+          emu::yield();
+#endif
+          if ((spin & 4095u) == 4095u) {
+            if (!t0) t0 = gtimer();
+            else if (gtimer() - t0 > a.spin_limit_ns) loop_trap();
+          }
+        }
+        const unsigned long long c = w0 & BB_LOW48, pr = w1 & ((1ull << 45) - 1ull);
+        fl |= (uint32_t)(w1 >> 45) & 7u;
+        if (c > bc || (c == bc && pr > bp)) { bc = c; bp = pr; bw = j; }
       }
+      for (int o = 16; o > 0; o >>= 1) {   // warp reduce (ties cannot happen between blocks: a pair has one owner)
+        const unsigned long long c2 = __shfl_xor_sync(0xffffffffu, bc, o), p2 = __shfl_xor_sync(0xffffffffu, bp, o);
+        const uint32_t w2 = __shfl_xor_sync(0xffffffffu, bw, o);
+        if (c2 > bc || (c2 == bc && p2 > bp)) { bc = c2; bp = p2; bw = w2; }
+      }
+      if (fl) atomicOr(&s_bflags, fl);
       const unsigned used_warps = (min(gridDim.x, blockDim.x) + 31) >> 5;
-      if (wid < used_warps) {
-        v = warp_best(v);
-        if (lane == 0) s_warp[wid] = v;
-      }
-      if (bflags) atomicOr(&s_bflags, bflags);
+      if (lane == 0 && wid < used_warps) { s_warp[wid].c = bc; s_warp[wid].prio = bp; s_warp[wid].slot = bw; }
       __syncthreads();
       if (wid == 0) {
-        Best u = lane < used_warps ? s_warp[lane] : Best{0, 0, 0};
-        u = warp_best(u);
-        if (lane == 0) { s_best = u; s_dead = 0; s_out_n = 0; }
+        bc = lane < used_warps ? s_warp[lane].c : 0ull;
+        bp = lane < used_warps ? s_warp[lane].prio : 0ull;
+        bw = lane < used_warps ? (uint32_t)s_warp[lane].slot : 0xffffffffu;
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long c2 = __shfl_xor_sync(0xffffffffu, bc, o), p2 = __shfl_xor_sync(0xffffffffu, bp, o);
+          const uint32_t w2 = __shfl_xor_sync(0xffffffffu, bw, o);
+          if (c2 > bc || (c2 == bc && p2 > bp)) { bc = c2; bp = p2; bw = w2; }
+        }
+        if (lane == 0) { s_best.c = bc; s_best.prio = bp; s_best.slot = bw; s_out_n = 0; }
       }
+      __syncthreads();
     }
-    __syncthreads();
-    const Best win = s_best;
-    bflags = s_bflags;
+    if (gtid == 0) tq1 = gtimer();
+    const Best win = s_best;             // .prio = prio45, .slot = owner block
+    const uint32_t bflags = s_bflags, xf = s_xf;
     // ---------------- uniform exit checks (every block of every rank evaluates the same values)
     {
       uint32_t stop = 0, why = 0;
-      const uint32_t xf = bflags >> 8;
-      if (bflags & 1u) why |= 1u;                                   // a partition is nearly full: grow the table
+      if (bflags & 1u) why |= 1u;                                   // a partition reached the load limit: rebuild (dead keys vanish)
       if (xf & XQF_OVERFLOW) why |= 2u;                             // lost count changes: rebuild from the tokens
-      if (__ldcg(a.tab.overflow)) why |= 4u;                        // a partition ran full: grow
-      if (__ldcg(a.tab.n_keys) > a.key_limit) why |= 8u;            // load factor: rebuild (dead keys vanish)
+      if (bflags & 2u) why |= 4u;                                   // a partition ran full: grow the table
       if (n_done >= a.max_total || it == a.max_iters) stop = 4;     // done (or launch budget spent)
       else if (why) stop = 2;
-      else if (xf & XQF_COMPACT) stop = 3;                          // some rank wants a compaction
+      else if (xf & XQF_COMPACT) stop = 3;                          // some block wants a compaction
       else if (win.c == 0) stop = 1;                                // no pair left (bpe.cpp:1137-1145)
       if (stop) {
         if (gtid == 0) { a.ctl->stop = stop == 4 ? 0u : stop; a.ctl->stop_why = why; }
         break;
       }
     }
-    const unsigned long long tw1 = dbgt && lane == 0 ? gtimer() : 0;
     MergeOp op;
-    {  // (x, y) is recoverable from the priority word (pair_prio), no dependent table load needed
-      const uint32_t mx = 0xffffffffu - (uint32_t)(win.prio >> 32);
-      const uint32_t mn = 0x7fffffffu - (uint32_t)((win.prio & 0xffffffffull) >> 1);
+    {
+      const uint32_t mx = 0x3fffffu - (uint32_t)(win.prio >> 23), mn = 0x3fffffu - (uint32_t)((win.prio >> 1) & 0x3fffffu);
       op.x = (win.prio & 1ull) ? mx : mn;
       op.y = (win.prio & 1ull) ? mn : mx;
       op.key = pair_key(op.x, op.y);
@@ -702,8 +779,10 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       a.rfreq[n_done] = win.c;
       a.ctl->n_done = n_done + 1;
     }
+    const bool i_own = (uint32_t)win.slot == blockIdx.x;
     // every occurrence of (x,y) is merged below and no deltas are emitted for it: its owner clears the count
-    if (threadIdx.x == 0 && win.slot >= pbase && win.slot < pbase + R) a.tab.cnts[win.slot] = 0;
+    if (i_own && threadIdx.x == 0) a.tab.cnts[s_cb.slot] = 0;
+    const unsigned long long tw1 = dbgt && lane == 0 ? gtimer() : 0;
     // ---------------- apply x y -> z: count changes go to this block's segment of round + 1 (on every rank)
     const uint32_t nround = round + 1;
     XqOut xo;
@@ -858,45 +937,78 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     if (lane == 0 && dead) atomicAdd(&s_dead, dead);
     __syncthreads();  // all entries of this block are on their way
     if (threadIdx.x == 0) {
-      if (s_dead) atomicAdd(&a.ctl->dead, s_dead);
+      my_dead += s_dead;
+      s_dead = 0;
       const uint32_t n = s_out_n;
-      const uint32_t word = n > a.xq.seg_cap ? (a.xq.seg_cap | XQ_CNT_OVF) : n;
+      uint32_t word = n > a.xq.seg_cap ? (a.xq.seg_cap | XQ_CNT_OVF) : n;
+      if (my_dead * 4 > my_slots && my_slots > a.dead_min_slots) word |= XQ_CNT_COMPACT;
+      fence_scope(sys);   // this block's entries, as observed through the barrier above, before the stamped word
+      const unsigned long long cw = ((unsigned long long)nround << 32) | word;
 #pragma unroll
       for (int d = 0; d < XQ_MAX_WORLD; d++)
-        if ((uint32_t)d < a.xq.world) xq_hdr(a.xq, (uint32_t)d, nround & 1u, a.xq.me)->counts[blockIdx.x] = word;
-      if (a.xq.world > 1) fence_sys();  // this block's entries and count, as observed through the barrier above
-      s_xf = 0; s_bflags = 0;  // next iteration's accumulators (read again only after the grid barrier below)
-      if (dbgt) {
-        const unsigned long long t = gtimer() - tw1;
-        atomicMax(&a.ctl->blk[it & 1][0], t);
-        atomicAdd(&a.ctl->blk[it & 1][1], t);
-        atomicMax(&a.ctl->blk[it & 1][2], s_tpre);
-        s_tpre = 0;
+        if ((uint32_t)d < a.xq.world) st_release(&xq_hdr(a.xq, (uint32_t)d, nround & 1u, a.xq.me)->counts[blockIdx.x], cw, sys);
+      s_xf = 0; s_bflags = 0; s_sweep = 0;   // accumulators of the phases below
+      if (dbgt) atomicMax(&a.ctl->blk[it & 1][0], gtimer() - tw1);
+    }
+    if (gtid == 0) tq2 = gtimer();
+    round = nround;
+    // the owner of the consumed pair sweeps its partition while the others finish their apply phase (the sweep sees
+    // the table BEFORE this round's changes; they are folded in below like everybody's)
+    __syncthreads();
+    if (i_own) sweep_partition(a, pbase, R, s_warp, &s_cb);
+    // ---------------- drain: the count changes of this merge, from every block of every GPU
+    const unsigned long long tw2 = dbgt && lane == 0 ? gtimer() : 0;
+    xq_poll_counts(a, round, false, s_pref, &s_xf);
+    if (gtid == 0) tq2b = gtimer();
+    Touched tch;
+    tch.n = 0;
+    xq_drain(a, round, s_pref, s_scan, &s_occ, tch);
+    if (tch.n > (uint32_t)DRAIN_KEEP) s_sweep = 1;   // (benign race: every writer stores 1)
+    __syncthreads();  // the partition is up to date (the drain's atomics went to L2 before the barrier)
+    {
+      // ---- cached arg-max: only touched slots can have changed.  Final counts are re-read (a slot may have
+      // received several entries); a lowered best invalidates the cache.
+      const Best cb = s_cb;
+      Best cand{0, 0, 0};
+      bool lowered = false;
+      const uint32_t nt = tch.n < (uint32_t)DRAIN_KEEP ? tch.n : (uint32_t)DRAIN_KEEP;
+#pragma unroll
+      for (int q = 0; q < DRAIN_KEEP; q++) {
+        if ((uint32_t)q >= nt || tch.slot[q] == ~0ull) continue;
+        const unsigned long long c = __ldcg(a.tab.cnts + tch.slot[q]);
+        if (tch.slot[q] == cb.slot && cb.c && c < cb.c) lowered = true;
+        if (c) {
+          Best v{c, pair_prio((uint32_t)(tch.key[q] >> 32), (uint32_t)tch.key[q]), tch.slot[q]};
+          if (better(v, cand)) cand = v;
+        }
+      }
+      if (lowered) s_sweep = 1;
+      cand = warp_best(cand);
+      if (lane == 0) s_warp[wid] = cand;
+      __syncthreads();
+      if (s_sweep) {
+        sweep_partition(a, pbase, R, s_warp, &s_cb);
+        if (threadIdx.x == 0) s_sweep = 0;
+      } else if (wid == 0) {
+        Best v = lane < nwarp ? s_warp[lane] : Best{0, 0, 0};
+        v = warp_best(v);
+        if (lane == 0 && better(v, cb)) s_cb = v;
       }
     }
-    if (gtid == 0) tq4 = gtimer();
-    grid.sync();
-    round = nround;
-    pending = true;
+    __syncthreads();
+    if (dbgt && lane == 0) atomicMax(&s_tpre, gtimer() - tw2);
     if (gtid == 0) {
-      unsigned long long tq5 = gtimer();
-      if (a.xq.world > 1) {  // publish: every peer may now read this rank's segments of `round`
-        const unsigned long long dd = __ldcg(&a.ctl->dead), sl = __ldcg(&a.ctl->slots);
-        const unsigned long long word = ((unsigned long long)round << 8) | ((dd * 4 > sl && sl > 65536) ? XQF_COMPACT : 0u);
-        fence_sys();
-#pragma unroll
-        for (int d = 0; d < XQ_MAX_WORLD; d++)
-          if ((uint32_t)d < a.xq.world && (uint32_t)d != a.xq.me)
-            st_release_sys(&xq_hdr(a.xq, (uint32_t)d, round & 1u, a.xq.me)->seq_flags, word);
-      }
+      tq3 = gtimer();
       if (dbgt) {
         a.ctl->t_phase[5] += __ldcg(&a.ctl->blk[it & 1][0]);
-        a.ctl->t_phase[6] += __ldcg(&a.ctl->blk[it & 1][1]) / gridDim.x;
-        a.ctl->t_phase[7] += __ldcg(&a.ctl->blk[it & 1][2]);
-        a.ctl->blk[it & 1][0] = 0; a.ctl->blk[it & 1][1] = 0; a.ctl->blk[it & 1][2] = 0;
+        a.ctl->blk[it & 1][0] = 0;
+        a.ctl->t_phase[7] += s_tpre;
+        s_tpre = 0;
       }
-      a.ctl->t_phase[0] += tq1 - tq0; a.ctl->t_phase[1] += tq2 - tq1; a.ctl->t_phase[2] += tq3 - tq2;
-      a.ctl->t_phase[3] += tq4 - tq3; a.ctl->t_phase[4] += tq5 - tq4;
+      a.ctl->t_phase[2] += tq1 - tq0;   // publish + poll of the blocks' bests ("barrier 1" + winner reduce)
+      a.ctl->t_phase[3] += tq2 - tq1;   // apply
+      a.ctl->t_phase[4] += tq2b - tq2;  // wait for the slowest block's count word ("barrier 2"; the owner's sweep hides here)
+      a.ctl->t_phase[0] += tq3 - tq2b;  // drain + cache update
       a.ctl->iters += 1;
     }
   }
@@ -911,10 +1023,11 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
 __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) { merge_loop_body(a); }
 
 // ---- exchange rounds outside the loop (multi-GPU table build): one block per partition -----------
-// xq_publish_table_kernel: block b enumerates the live (key, count) pairs of partition b of the LOCAL table in slot
-// order and copies those numbered [chunk * seg_cap, (chunk + 1) * seg_cap) into segment b of round `round` on every
-// OTHER rank; the count word says whether more follow.  The last block to finish publishes the round.
-__global__ void __launch_bounds__(256) xq_publish_table_kernel(LoopArgs a, uint32_t round, uint32_t chunk, unsigned int *arrive) {
+// xq_publish_table_kernel: block b enumerates the live (key, count) pairs of partition b of a SNAPSHOT of the local
+// table in slot order and copies those numbered [chunk * seg_cap, (chunk + 1) * seg_cap) into segment b of round
+// `round` on every OTHER rank, then stores its stamped count word everywhere (XQ_CNT_MORE: further chunks follow;
+// XQ_CNT_OVF: the local histogram had overflowed - every rank retries with a larger table).
+__global__ void __launch_bounds__(256) xq_publish_table_kernel(LoopArgs a, uint32_t round, uint32_t chunk, const uint32_t *local_overflow) {
   const uint32_t R = a.tab.rmask + 1;
   const uint64_t pbase = (uint64_t)blockIdx.x * R;
   const size_t off = xq_seg_off(a.xq, round & 1u, a.xq.me, blockIdx.x);
@@ -948,34 +1061,28 @@ __global__ void __launch_bounds__(256) xq_publish_table_kernel(LoopArgs a, uint3
     const uint64_t total = done;
     uint32_t word = total > lo ? (uint32_t)(total - lo < (uint64_t)a.xq.seg_cap ? total - lo : (uint64_t)a.xq.seg_cap) : 0u;
     if (total > hi) word |= XQ_CNT_MORE;
+    if (__ldcg(local_overflow)) word |= XQ_CNT_OVF;
+    fence_scope(true);
+    const unsigned long long cw = ((unsigned long long)round << 32) | word;
 #pragma unroll
     for (int d = 0; d < XQ_MAX_WORLD; d++)
-      if ((uint32_t)d < a.xq.world) xq_hdr(a.xq, (uint32_t)d, round & 1u, a.xq.me)->counts[blockIdx.x] = word;
-    fence_sys();
-    // the last block to arrive publishes the round (every block's stores precede its fence and its arrival)
-    if (atomicAdd(arrive, 1u) + 1u == gridDim.x) {
-      fence_sys();
-      const unsigned long long hw = ((unsigned long long)round << 8) | (__ldcg(a.tab.overflow) ? XQF_OVERFLOW : 0u);
-#pragma unroll
-      for (int d = 0; d < XQ_MAX_WORLD; d++)
-        if ((uint32_t)d < a.xq.world && (uint32_t)d != a.xq.me)
-          st_release_sys(&xq_hdr(a.xq, (uint32_t)d, round & 1u, a.xq.me)->seq_flags, hw);
-      *arrive = 0;
-    }
+      if ((uint32_t)d < a.xq.world) st_release(&xq_hdr(a.xq, (uint32_t)d, round & 1u, a.xq.me)->counts[blockIdx.x], cw, true);
   }
 }
-// xq_absorb_kernel: block b waits for round `round` of every peer and adds the peers' pairs it owns to partition b.
+// xq_absorb_kernel: block b waits for round `round` of every block of every rank and adds the peers' pairs it owns
+// to partition b of the live table.
 __global__ void __launch_bounds__(256) xq_absorb_kernel(LoopArgs a, uint32_t round) {
-  __shared__ uint32_t s_scan[33], s_occ;
+  __shared__ uint32_t s_scan[33], s_occ, s_acc;
   uint32_t *s_pref = yt_dyn_smem;
-  if (threadIdx.x == 0) s_occ = 0;
-  const uint32_t f = xq_wait_peers(a, round);
-  if (f) atomicOr(&a.ctl->xq_flags, f);
+  if (threadIdx.x == 0) { s_occ = 0; s_acc = 0; }
   __syncthreads();
-  const uint32_t r = xq_drain(a, round, true, s_pref, s_scan, &s_occ);
+  xq_poll_counts(a, round, true, s_pref, &s_acc);
+  Touched tch;
+  tch.n = 0;
+  xq_drain(a, round, s_pref, s_scan, &s_occ, tch);
+  __syncthreads();
   if (threadIdx.x == 0) {
-    if (r & 1u) atomicExch(a.tab.overflow, 1u);
-    if (r & 2u) atomicOr(&a.ctl->xq_flags, XQF_MORE);
+    if (s_acc) atomicOr(&a.ctl->xq_flags, s_acc);
     if (blockIdx.x == 0) a.ctl->xq_round = round;
   }
 }

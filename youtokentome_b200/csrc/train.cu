@@ -54,7 +54,8 @@ __device__ __forceinline__ uint32_t pair_part(const PairTab &t, uint64_t h) { re
 // Add delta to `key` inside the partition that starts at slot `base`, first probe at base + i0.
 // Returns true when the key was inserted.  A full partition drops the update and raises the flag.
 template <bool CAS_FIRST = false>
-__device__ __forceinline__ bool pair_add_at(const PairTab &t, uint64_t base, uint32_t i0, uint64_t key, long long delta) {
+__device__ __forceinline__ bool pair_add_at(const PairTab &t, uint64_t base, uint32_t i0, uint64_t key, long long delta,
+                                            uint64_t *slot_out = nullptr) {
   for (uint32_t probe = 0; probe <= t.rmask; probe++) {
     const uint64_t h = base + ((i0 + probe) & t.rmask);
     unsigned long long k;
@@ -75,6 +76,7 @@ __device__ __forceinline__ bool pair_add_at(const PairTab &t, uint64_t base, uin
     if (k == key) {
       atomicAdd(t.cnts + h, (unsigned long long)delta);
       if (fresh) atomicAdd(t.n_keys, 1u);
+      if (slot_out) *slot_out = h;
       return fresh;
     }
   }
@@ -91,22 +93,99 @@ __device__ __forceinline__ void pair_add(const PairTab &t, uint64_t key, long lo
 // ------------------------------------------------------------------------------------------
 constexpr int HIST_SMEM_BINS = 2048;  // every 1- and 2-byte code point
 
-__global__ void __launch_bounds__(512) char_hist_kernel(const uint8_t *__restrict__ s, uint64_t n,
+// decode_unit (bpe_core.cuh) on four bytes held in a register (b0 in the low byte): bytes beyond the text are spaces
+// there, which end every sequence exactly like the bounds check of the byte-wise version (a space is no continuation).
+__device__ __forceinline__ uint32_t decode_reg(uint32_t w, uint32_t *len) {
+  const uint32_t b0 = w & 0xffu, b1 = (w >> 8) & 0xffu, b2 = (w >> 16) & 0xffu, b3 = w >> 24;
+  *len = 1;
+  if (b0 < 0x80u) return b0;
+  const bool c1 = (b1 & 0xc0u) == 0x80u, c2 = (b2 & 0xc0u) == 0x80u, c3 = (b3 & 0xc0u) == 0x80u;
+  if ((b0 & 0xe0u) == 0xc0u) {
+    const uint32_t cp = ((b0 & 0x1fu) << 6) | (b1 & 0x3fu);
+    if (c1 && cp >= 0x80u) { *len = 2; return cp; }
+  } else if ((b0 & 0xf0u) == 0xe0u) {
+    const uint32_t cp = ((b0 & 0x0fu) << 12) | ((b1 & 0x3fu) << 6) | (b2 & 0x3fu);
+    if (c1 && c2 && cp >= 0x800u && valid_cp(cp)) { *len = 3; return cp; }
+  } else if ((b0 & 0xf8u) == 0xf0u) {
+    const uint32_t cp = ((b0 & 0x07u) << 18) | ((b1 & 0x3fu) << 12) | ((b2 & 0x3fu) << 6) | (b3 & 0x3fu);
+    if (c1 && c2 && c3 && cp >= 0x10000u && valid_cp(cp)) { *len = 4; return cp; }
+  }
+  return INVALID_CP;
+}
+__device__ __forceinline__ uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t shift_bits) {
+  return shift_bits ? (lo >> shift_bits) | (hi << (32u - shift_bits)) : lo;
+}
+// the aligned 32-bit word at text position p (p + address alignment is a multiple of 4), spaces outside [0, n)
+__device__ __forceinline__ uint32_t text_word(const uint8_t *__restrict__ s, int64_t p, int64_t n) {
+  if (p >= 0 && p + 4 <= n) return *reinterpret_cast<const uint32_t *>(s + p);
+  uint32_t w = 0x20202020u;
+  for (int k = 0; k < 4; k++)
+    if (p + k >= 0 && p + k < n) w = (w & ~(0xffu << (8 * k))) | ((uint32_t)s[p + k] << (8 * k));
+  return w;
+}
+
+// Phase 1 with 16 bytes per thread: one aligned 16-byte load, the 4 bytes before and after come from the neighbour
+// lanes by shuffle, and unit starts / code points are decided on that 24-byte register window (is_unit_start and
+// decode_unit restated on registers: a continuation byte is consumed iff the nearest non-continuation byte within 3
+// before it starts a valid sequence that covers it).  Round 1 issued 3 - 8 byte loads per position (57 GB/s).
+__global__ void __launch_bounds__(512) char_hist_kernel(const uint8_t *__restrict__ s, uint64_t n_text,
                                                         unsigned long long *__restrict__ hist) {
   __shared__ uint32_t sh[HIST_SMEM_BINS];
   __shared__ unsigned long long s_units;
   for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x) sh[i] = 0;
   if (threadIdx.x == 0) s_units = 0;
   __syncthreads();
+  const int64_t n = (int64_t)n_text;
+  const int64_t mis = (int64_t)(reinterpret_cast<uintptr_t>(s) & 15u);  // text position -mis is 16-byte aligned
+  const int64_t n_vec = (n + mis + 15) / 16;
+  const unsigned lane = threadIdx.x & 31;
   uint64_t units = 0;
-  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
-    if (!is_unit_start(s, p, 0, n)) continue;
-    units++;
-    uint32_t len, cp = decode_unit(s, p, n, &len);
-    if (cp == INVALID_CP || is_space_cp(cp)) continue;
-    if (cp < HIST_SMEM_BINS) atomicAdd(&sh[cp], 1u);
-    else atomicAdd(hist + cp, 1ull);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t rounds = (n_vec + stride - 1) / stride;
+  for (int64_t r = 0; r < rounds; r++) {  // warp-uniform trip count: every lane takes part in the shuffles
+    const int64_t v = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t p0 = v * 16 - mis;
+    uint32_t w[6];
+    if (v < n_vec && p0 >= 0 && p0 + 16 <= n) {
+      const uint4 q = *reinterpret_cast<const uint4 *>(s + p0);
+      w[1] = q.x; w[2] = q.y; w[3] = q.z; w[4] = q.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; k++) w[1 + k] = v < n_vec ? text_word(s, p0 + 4 * k, n) : 0x20202020u;
+    }
+    w[0] = __shfl_up_sync(0xffffffffu, w[4], 1);
+    w[5] = __shfl_down_sync(0xffffffffu, w[1], 1);
+    if (lane == 0) w[0] = text_word(s, p0 - 4, n);
+    if (lane == 31) w[5] = text_word(s, p0 + 16, n);
+    if (v >= n_vec) continue;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const int64_t p = p0 + i;
+      const int j = i + 4;  // window index of the byte
+      const uint32_t four = funnel_r(w[j >> 2], w[(j >> 2) + 1 < 6 ? (j >> 2) + 1 : 5], (uint32_t)(j & 3) * 8u);
+      const uint32_t b = four & 0xffu;
+      bool start = true;
+      if ((b & 0xc0u) == 0x80u) {  // continuation byte: covered by a valid sequence that starts 1..3 bytes earlier?
+#pragma unroll
+        for (int d = 1; d <= 3; d++) {
+          const int jq = j - d;
+          const uint32_t fq = funnel_r(w[jq >> 2], w[(jq >> 2) + 1], (uint32_t)(jq & 3) * 8u);
+          if ((fq & 0xc0u) != 0x80u) {
+            uint32_t lq;
+            decode_reg(fq, &lq);
+            start = !(lq > (uint32_t)d);
+            break;
+          }
+        }
+      }
+      if (!start || p < 0 || p >= n) continue;
+      units++;
+      uint32_t len;
+      const uint32_t cp = decode_reg(four, &len);
+      if (cp == INVALID_CP || is_space_cp(cp)) continue;
+      if (cp < HIST_SMEM_BINS) atomicAdd(&sh[cp], 1u);
+      else atomicAdd(hist + cp, 1ull);
+    }
   }
   for (int o = 16; o > 0; o >>= 1) units += __shfl_xor_sync(0xffffffffu, units, o);
   if ((threadIdx.x & 31) == 0 && units) atomicAdd(&s_units, (unsigned long long)units);
@@ -160,14 +239,53 @@ __device__ __forceinline__ bool word_table_insert(const uint8_t *__restrict__ s,
   return false;
 }
 
-__global__ void __launch_bounds__(256) word_insert_kernel(const uint8_t *__restrict__ s, uint64_t n, WordTab wt,
+// Word split + dedup of running text.  A block owns CHUNKS of WC_CHUNK consecutive bytes; inside a chunk the words are
+// first counted in a shared-memory table (entry = 32-bit tag | position of the first occurrence inside the chunk,
+// duplicates verified byte by byte against it — exactness never rests on the hash), and only one (word, count) per
+// distinct word of the chunk goes to the global table.  Why: natural text repeats its words (Zipf), and the round-1
+// kernel sent one 64-bit atomic per OCCURRENCE to the global counters — 1.2 M of the 16.7 M occurrences of the 100 MB
+// bench corpus hit the single counter of the most frequent word, where same-address atomics serialise in L2
+// (4.2 ms = 24 GB/s).  Words that find no room in the shared table (WC_PROBES) go to the global table directly.
+constexpr int WC_T = 512;
+constexpr uint32_t WC_CHUNK = 65536, WC_SLOTS = 4096, WC_PROBES = 12;
+__global__ void __launch_bounds__(WC_T) word_insert_kernel(const uint8_t *__restrict__ s, uint64_t n, WordTab wt,
                                                           unsigned long long *counters, uint64_t max_unique) {
-  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  __shared__ unsigned long long s_ent[WC_SLOTS];  // (tag32 << 32) | (position in the chunk + 1) ; 0 = empty
+  __shared__ uint32_t s_cnt[WC_SLOTS];
   uint64_t occ = 0;
-  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
-    if (!word_start_at(s, p, 0, n)) continue;
-    occ++;
-    word_table_insert(s, n, p, wt, counters, max_unique, 1ull);
+  const uint64_t n_chunks = (n + WC_CHUNK - 1) / WC_CHUNK;
+  for (uint64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {  // block-uniform
+    for (uint32_t i = threadIdx.x; i < WC_SLOTS; i += WC_T) { s_ent[i] = 0; s_cnt[i] = 0; }
+    __syncthreads();
+    const uint64_t base = ch * WC_CHUNK, end = base + WC_CHUNK < n ? base + WC_CHUNK : n;
+    for (uint64_t p = base + threadIdx.x; p < end; p += WC_T) {
+      if (!word_start_at(s, p, 0, n)) continue;
+      occ++;
+      uint64_t h = 0xcbf29ce484222325ull, q = p;
+      uint32_t l;
+      while (q < n && !space_at(s, q, n, &l)) { h = (h ^ s[q]) * 0x100000001b3ull; q++; }
+      const uint64_t len = q - p;
+      h = mix64(h ^ (len << 1));
+      const uint32_t tag = (uint32_t)(h >> 32);
+      const unsigned long long mine = ((unsigned long long)tag << 32) | (uint32_t)(p - base + 1);
+      uint32_t slot = (uint32_t)h & (WC_SLOTS - 1);
+      bool done = false;
+      for (uint32_t probe = 0; probe < WC_PROBES && !done; probe++, slot = (slot + 1) & (WC_SLOTS - 1)) {
+        unsigned long long k = s_ent[slot];
+        if (k == 0) {
+          k = atomicCAS(&s_ent[slot], 0ull, mine);
+          if (k == 0) { atomicAdd(&s_cnt[slot], 1u); done = true; break; }
+        }
+        if ((uint32_t)(k >> 32) == tag && same_word(s, n, base + (uint32_t)k - 1, p, len)) { atomicAdd(&s_cnt[slot], 1u); done = true; }
+      }
+      if (!done) word_table_insert(s, n, p, wt, counters, max_unique, 1ull);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < WC_SLOTS; i += WC_T) {
+      const unsigned long long k = s_ent[i];
+      if (k) word_table_insert(s, n, base + (uint32_t)k - 1, wt, counters, max_unique, (unsigned long long)s_cnt[i]);
+    }
+    __syncthreads();
   }
   for (int o = 16; o > 0; o >>= 1) occ += __shfl_xor_sync(0xffffffffu, occ, o);
   if ((threadIdx.x & 31) == 0 && occ) atomicAdd(counters + 0, (unsigned long long)occ);
@@ -601,7 +719,7 @@ static int build_table_once(yttm_ctx *c, uint64_t want_slots, bool *ok) {
     snap.tab.cnts = c->scratch_cnt.as<unsigned long long>();
     for (uint32_t chunk = 0;; chunk++) {  // every rank runs the same number of rounds: "more" is OR-ed over all senders
       round += 1;
-      xq_publish_table_kernel<<<c->p_nparts, 256, 0, c->stream>>>(snap, round, chunk, c->xq_arrive.as<unsigned int>());
+      xq_publish_table_kernel<<<c->p_nparts, 256, 0, c->stream>>>(snap, round, chunk, &ctl->overflow);
       xq_absorb_kernel<<<c->p_nparts, 256, (XQ_MAX_WORLD * XQ_MAX_BLOCKS + 4) * 4, c->stream>>>(a, round);
       c->launches += 2;
       uint32_t f = 0;
@@ -623,8 +741,9 @@ static int build_table_once(yttm_ctx *c, uint64_t want_slots, bool *ok) {
   peer_flags |= g[0];
   const uint64_t R = (uint64_t)c->p_rmask + 1;
   // local overflow is rank-specific, but it reaches every rank as XQF_OVERFLOW of this rank's round
+  // accept at half the load the loop leaves at, globally and in the fullest partition (+ 1/8 slack for imbalance)
   *ok = !h[1] && !(peer_flags & XQF_OVERFLOW) && (uint64_t)h[0] * 200 <= cap * pair_max_load_pct() &&
-        (uint64_t)g[1] * 4 <= R * 3;
+        (uint64_t)g[1] * 200 <= R * (pair_max_load_pct() + 25);
   if (*ok) { c->stats.n_pairs = h[0]; c->stats.table_capacity = cap; }
   return 0;
 }
@@ -897,7 +1016,7 @@ int yttm_train_char_hist(yttm_ctx *c, uint64_t *data_len, uint64_t *n_distinct) 
   YT_CUDA(c, cudaMemsetAsync(c->hist.p, 0, (CP_LIMIT + 1) * 8, c->stream));
   ytc::timer_begin(c, "char_hist");
   if (c->n_text) {
-    char_hist_kernel<<<grid_for(c, c->n_text, 512, 4), 512, 0, c->stream>>>(c->d_text, c->n_text,
+    char_hist_kernel<<<grid_for(c, c->n_text / 16 + 1, 512, 4), 512, 0, c->stream>>>(c->d_text, c->n_text,
                                                                             c->hist.as<unsigned long long>());
     c->launches++;
   }
@@ -989,7 +1108,8 @@ static int build_word_table(yttm_ctx *c, const WordList *list, uint64_t *n_uniqu
         c->launches++;
       }
     } else if (n) {
-      word_insert_kernel<<<grid_for(c, n, 256, 8), 256, 0, c->stream>>>(c->d_text, n, wt, counters, cap / 2);
+      const uint64_t n_chunks = (n + WC_CHUNK - 1) / WC_CHUNK;
+      word_insert_kernel<<<(unsigned)std::min<uint64_t>(n_chunks, (uint64_t)c->n_sm * 4), WC_T, 0, c->stream>>>(c->d_text, n, wt, counters, cap / 2);
       c->launches++;
     }
     YT_CUDA(c, cudaGetLastError());
@@ -1313,7 +1433,8 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
   *n_done_out = 0;
   if (max_merges == 0) return 0;
   if (ensure_loop_geometry(c)) return 1;
-  YT_CUDA(c, c->blockbest.reserve((size_t)c->loop_blocks * 4 * 8));
+  YT_CUDA(c, c->blockbest.reserve((size_t)c->loop_blocks * 2 * 8));
+  if (first_new_id + (uint64_t)max_merges >= BB_ID_LIMIT) YT_FAIL(c, "yttm_train_run: token ids beyond 2^22 are not supported by the merge loop");
   YT_CUDA(c, c->d_rules.reserve((size_t)max_merges * 12 + 16));
   YT_CUDA(c, c->d_rfreq.reserve((size_t)max_merges * 8 + 16));
   YtLoopCtl *ctl = c->ctl.as<YtLoopCtl>();
@@ -1342,8 +1463,10 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
     a.first_new_id = first_new_id;
     a.max_total = max_merges;
     a.max_iters = max_merges;
-    a.key_limit = (uint32_t)std::min<uint64_t>(c->pcap / 100 * pair_max_load_pct() + c->pcap % 100 * pair_max_load_pct() / 100,
-                                               0xfffffff0ull);  // rebuild above this load (default 1/2)
+    a.part_limit = (uint32_t)(((uint64_t)c->p_rmask + 1) * pair_max_load_pct() / 100);  // rebuild above this partition load (default 1/2)
+    a.dead_min_slots = 4096;
+    if (const char *e = std::getenv("YTTM_DEAD_MIN_SLOTS")) a.dead_min_slots = (uint32_t)std::max(0, std::atoi(e));
+    YT_CUDA(c, cudaMemsetAsync(c->blockbest.p, 0, (size_t)c->loop_blocks * 2 * 8, c->stream));  // stamps restart at 1
 #ifndef YT_SIMT_EMU
     void *args[] = {&a};
     YT_CUDA(c, cudaLaunchCooperativeKernel((void *)merge_loop_kernel, dim3(c->loop_blocks), dim3(c->loop_threads), args,
@@ -1365,7 +1488,7 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
     if (why == 2) {
       const uint32_t keep_done = h.n_done;
       // dead keys vanish in the rebuild, so the table usually keeps its size; it grows when a partition filled up
-      const uint64_t want = (reason & 5u) ? c->pcap * 2 : c->pcap / 2;
+      const uint64_t want = (reason & 4u) ? c->pcap * 2 : c->pcap / 2;
       if (rebuild_pair_table(c, std::max<uint64_t>(want, pair_cap_floor()))) return 1;
       YT_CUDA(c, cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
       YT_CUDA(c, cudaStreamSynchronize(c->stream));
