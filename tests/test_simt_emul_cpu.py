@@ -516,3 +516,8 @@ def test_api_encode_packed_torch_output(emu, oracle):
     assert np.array_equal(t_ids.numpy(), want) and np.array_equal(t_oo.numpy(), woo.astype(np.int64))
     ids, oo = bpe.encode_packed(np.frombuffer(buf, dtype=np.uint8), offs, eos=True)
     assert np.array_equal(ids, want) and np.array_equal(oo, woo)
+
+
+def test_train_edge_inputs(emu, oracle):
+    """Empty / all-space / one-letter / invalid-only corpora, vocab too small, merges running out."""
+    TG.test_edge_inputs(emu, oracle)

@@ -48,6 +48,7 @@ struct YtLoopCtl {
   uint32_t stop_why;              // stop == 2: 1 partition nearly full, 2 exchange segment overflowed, 4 partition full, 8 load factor
   uint32_t xq_flags;              // flags of the peers' last out-of-loop round (xq_absorb_kernel)
   uint32_t max_part_occ;          // part_occ_kernel: fullest partition of the table
+  unsigned long long n_sweeps;    // partition sweeps after a drain, summed over blocks (the winner's owner sweeps besides)
 };
 
 struct yttm_ctx {
@@ -102,7 +103,7 @@ struct yttm_ctx {
   uint32_t loop_tok_cap = 0, loop_word_cap = 0, loop_stream_q = 0, loop_stream_tok_cap = 0, loop_stream_word_cap = 0;
   int loop_blocks = 0, loop_threads = 0;
   double loop_phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  uint64_t loop_iters = 0, loop_relaunches = 0;
+  uint64_t loop_iters = 0, loop_relaunches = 0, loop_sweeps = 0;
 
   yttm_train_stats stats{};
 };

@@ -506,7 +506,7 @@ __device__ __forceinline__ void xq_poll_counts(const LoopArgs &a, uint32_t round
 
 // Up to DRAIN_KEEP table slots a thread has updated in one drain (for the cached arg-max); more: the block sweeps.
 constexpr int DRAIN_KEEP = 4;
-struct Touched { uint64_t slot[DRAIN_KEEP]; unsigned long long key[DRAIN_KEEP]; uint32_t n; };
+struct Touched { uint64_t slot[DRAIN_KEEP]; unsigned long long key[DRAIN_KEEP]; uint32_t n, dropped; };
 
 // Drain: s_pref holds the entry counts (xq_poll_counts); every entry whose key belongs to partition blockIdx.x is
 // applied to that partition.  *s_occ_add is increased by the keys inserted; `tch` records what this thread touched.
@@ -566,6 +566,7 @@ __device__ __forceinline__ void xq_drain(const LoopArgs &a, uint32_t round, uint
     if (pair_part(a.tab, hh) != blockIdx.x) continue;
     uint64_t slot = ~0ull;
     added += pair_add_at(a.tab, (uint64_t)blockIdx.x * R, (uint32_t)hh & a.tab.rmask, key, delta, &slot) ? 1u : 0u;
+    if (slot == ~0ull) tch.dropped = 1;
     if (tch.n < (uint32_t)DRAIN_KEEP) {
 #pragma unroll
       for (int q = 0; q < DRAIN_KEEP; q++)
@@ -624,7 +625,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   __shared__ Best s_warp[32];
   __shared__ Best s_best, s_cb;      // the elected pair of this iteration / the cached best of this block's partition
   __shared__ unsigned long long s_dead;
-  __shared__ uint32_t s_defer_n, s_direct, s_out_n, s_occ, s_xf, s_bflags, s_sweep, s_scan[33];
+  __shared__ uint32_t s_defer_n, s_direct, s_out_n, s_occ, s_xf, s_bflags, s_sweep, s_povf, s_scan[33];
   __shared__ unsigned long long s_tpre;
   const bool dbgt = (a.dbg & 8u) != 0;  // per-block phase timing (diagnostic)
   const bool sys = a.xq.world > 1;
@@ -655,13 +656,14 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   const uint64_t pbase = (uint64_t)blockIdx.x * R;  // this block's partition of the pair table
   const uint32_t n_done0 = a.ctl->n_done;
   uint32_t round = a.ctl->xq_round;                   // exchange rounds completed so far (same on every rank)
+  unsigned long long tacc0 = 0, tacc2 = 0, tacc3 = 0, tacc4 = 0, tacc5 = 0, tacc7 = 0, titers = 0;  // phase timers (block 0, thread 0)
 
   // occupancy of this block's partition (keys never leave the table between rebuilds)
   {
     uint32_t occ = 0;
     for (uint32_t i = threadIdx.x; i < R; i += blockDim.x) occ += __ldcg(a.tab.keys + pbase + i) != PK_EMPTY ? 1u : 0u;
     for (int o = 16; o > 0; o >>= 1) occ += __shfl_xor_sync(0xffffffffu, occ, o);
-    if (threadIdx.x == 0) { s_occ = 0; s_xf = 0; s_bflags = 0; s_tpre = 0; s_sweep = 0; s_dead = 0; }
+    if (threadIdx.x == 0) { s_occ = 0; s_xf = 0; s_bflags = 0; s_tpre = 0; s_sweep = 0; s_dead = 0; s_povf = __ldcg(a.tab.overflow) ? 1u : 0u; }
     __syncthreads();
     if (lane == 0 && occ) atomicAdd(&s_occ, occ);
   }
@@ -677,12 +679,13 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       load_tile(a, rw0, rw1, stok, soff);
       for (uint32_t i = threadIdx.x; i < rw1 - rw0; i += blockDim.x) sfreq[i] = a.freq[rw0 + i];
     }
-  } else if (!a.resident) {
+  } else if (!a.resident && a.n_tiles) {
     const uint32_t per_block = (a.n_tiles + gridDim.x - 1) / gridDim.x;
     const uint32_t k0 = min(a.n_tiles, blockIdx.x * per_block), k1 = min(a.n_tiles, k0 + per_block);
     my_slots = a.tile_desc[k1].y - a.tile_desc[k0].y;
   }
   unsigned long long my_dead = 0;    // token slots of this block tombstoned in this launch (thread 0 keeps the sum)
+  uint32_t n_sweeps = 0;             // sweeps of this block after a drain (thread 0; diagnostic)
   sweep_partition(a, pbase, R, s_warp, &s_cb);   // the cached arg-max starts exact (has the block barriers)
 
   for (uint32_t it = 0; it <= a.max_iters; ++it) {
@@ -693,7 +696,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     // reduction in one round trip.  flags: 1 = this partition is over the load limit, 2 = it ran full (update lost).
     if (threadIdx.x == 0) {
       const Best cb = s_cb;
-      uint32_t fl = (s_occ > a.part_limit ? 1u : 0u) | (__ldcg(a.tab.overflow) ? 2u : 0u);
+      uint32_t fl = (s_occ > a.part_limit ? 1u : 0u) | (s_povf ? 2u : 0u);
       uint32_t x = 0, y = 0;
       if (cb.c) {  // (x, y) from the 64-bit priority word
         const uint32_t mx = 0xffffffffu - (uint32_t)(cb.prio >> 32), mn = 0x7fffffffu - (uint32_t)((cb.prio & 0xffffffffull) >> 1);
@@ -961,9 +964,10 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     xq_poll_counts(a, round, false, s_pref, &s_xf);
     if (gtid == 0) tq2b = gtimer();
     Touched tch;
-    tch.n = 0;
+    tch.n = 0; tch.dropped = 0;
     xq_drain(a, round, s_pref, s_scan, &s_occ, tch);
     if (tch.n > (uint32_t)DRAIN_KEEP) s_sweep = 1;   // (benign race: every writer stores 1)
+    if (tch.dropped) s_povf = 1;                      // this partition ran full: an update was lost
     __syncthreads();  // the partition is up to date (the drain's atomics went to L2 before the barrier)
     {
       // ---- cached arg-max: only touched slots can have changed.  Final counts are re-read (a slot may have
@@ -988,7 +992,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       __syncthreads();
       if (s_sweep) {
         sweep_partition(a, pbase, R, s_warp, &s_cb);
-        if (threadIdx.x == 0) s_sweep = 0;
+        if (threadIdx.x == 0) { s_sweep = 0; n_sweeps++; }
       } else if (wid == 0) {
         Best v = lane < nwarp ? s_warp[lane] : Best{0, 0, 0};
         v = warp_best(v);
@@ -999,20 +1003,26 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     if (dbgt && lane == 0) atomicMax(&s_tpre, gtimer() - tw2);
     if (gtid == 0) {
       tq3 = gtimer();
-      if (dbgt) {
-        a.ctl->t_phase[5] += __ldcg(&a.ctl->blk[it & 1][0]);
+      if (dbgt) {  // diagnostics only: these global round trips sit on block 0's path
+        tacc5 += __ldcg(&a.ctl->blk[it & 1][0]);
         a.ctl->blk[it & 1][0] = 0;
-        a.ctl->t_phase[7] += s_tpre;
+        tacc7 += s_tpre;
         s_tpre = 0;
       }
-      a.ctl->t_phase[2] += tq1 - tq0;   // publish + poll of the blocks' bests ("barrier 1" + winner reduce)
-      a.ctl->t_phase[3] += tq2 - tq1;   // apply
-      a.ctl->t_phase[4] += tq2b - tq2;  // wait for the slowest block's count word ("barrier 2"; the owner's sweep hides here)
-      a.ctl->t_phase[0] += tq3 - tq2b;  // drain + cache update
-      a.ctl->iters += 1;
+      tacc2 += tq1 - tq0;   // publish + poll of the blocks' bests ("barrier 1" + winner reduce)
+      tacc3 += tq2 - tq1;   // apply
+      tacc4 += tq2b - tq2;  // wait for the slowest block's count word ("barrier 2"; the owner's sweep hides here)
+      tacc0 += tq3 - tq2b;  // drain + cache update
+      titers += 1;
     }
   }
-  if (gtid == 0) a.ctl->xq_round = round;
+  if (threadIdx.x == 0 && n_sweeps) atomicAdd(&a.ctl->n_sweeps, (unsigned long long)n_sweeps);
+  if (gtid == 0) {
+    a.ctl->xq_round = round;
+    a.ctl->t_phase[0] += tacc0; a.ctl->t_phase[2] += tacc2; a.ctl->t_phase[3] += tacc3; a.ctl->t_phase[4] += tacc4;
+    a.ctl->t_phase[5] += tacc5; a.ctl->t_phase[7] += tacc7;
+    a.ctl->iters += titers;
+  }
   // resident tiles go back to HBM on every exit path
   __syncthreads();
   if (a.resident && rw1 > rw0) {
@@ -1078,7 +1088,7 @@ __global__ void __launch_bounds__(256) xq_absorb_kernel(LoopArgs a, uint32_t rou
   __syncthreads();
   xq_poll_counts(a, round, true, s_pref, &s_acc);
   Touched tch;
-  tch.n = 0;
+  tch.n = 0; tch.dropped = 0;
   xq_drain(a, round, s_pref, s_scan, &s_occ, tch);
   __syncthreads();
   if (threadIdx.x == 0) {

@@ -925,6 +925,7 @@ double yttm_stage_ms(const yttm_ctx *c, const char *stage) {
   for (int i = 0; i < 8; i++)
     if (!std::strcmp(stage, ph[i])) return c->loop_phase_ms[i];
   if (!std::strcmp(stage, "loop_iters")) return (double)c->loop_iters;
+  if (!std::strcmp(stage, "loop_sweeps")) return (double)c->loop_sweeps;
   if (!std::strcmp(stage, "loop_launches")) return (double)c->loop_relaunches;
   if (!std::strcmp(stage, "table_capacity")) return (double)c->pcap;
   if (!std::strcmp(stage, "loop_resident")) return (double)c->loop_resident;
@@ -1441,7 +1442,7 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
   YtLoopCtl h{};
   YT_CUDA(c, cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   YT_CUDA(c, cudaStreamSynchronize(c->stream));
-  h.n_done = 0; h.stop = 0; h.stop_why = 0; h.iters = 0;
+  h.n_done = 0; h.stop = 0; h.stop_why = 0; h.iters = 0; h.n_sweeps = 0;
   for (int i = 0; i < 8; i++) h.t_phase[i] = 0;
   for (int i = 0; i < 6; i++) (&h.blk[0][0])[i] = 0;
   YT_CUDA(c, cudaMemcpyAsync(ctl, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
@@ -1500,6 +1501,7 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
   ytc::timer_end(c, "merge_loop");
   for (int i = 0; i < 8; i++) c->loop_phase_ms[i] = (double)h.t_phase[i] * 1e-6;
   c->loop_iters = h.iters;
+  c->loop_sweeps = h.n_sweeps;
   *n_done_out = h.n_done;
   if (h.n_done) {
     YT_CUDA(c, cudaMemcpyAsync(rules_xyz, c->d_rules.p, (size_t)h.n_done * 12, cudaMemcpyDeviceToHost, c->stream));
