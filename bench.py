@@ -389,7 +389,7 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    STAGES = ["enc_find", "enc_words", "enc_dedup", "enc_rep", "enc_copy", "enc_gather", "enc_scan"]
+    STAGES = ["enc_find", "enc_words", "enc_dedup", "enc_rep", "enc_copy", "enc_count", "enc_gather", "enc_scan"]
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -430,7 +430,8 @@ def main():
     # enc_words is the sum of its three launches in the dedup path: the roofline kernel is a single launch
     single = {k: v for k, v in kern.items() if v > 0 and not (k == "enc_words" and kern["enc_dedup"] > 0)}
     dom = max(single, key=lambda k: single[k])
-    names = {"enc_words": "encode_words_kernel", "enc_find": "find_words_vec_kernel", "enc_gather": "gather_ids_kernel",
+    names = {"enc_words": "encode_words_kernel", "enc_find": "find_words_vec_kernel", "enc_gather": "emit_ids_kernel",
+             "enc_count": "sentence_ids_kernel",
              "enc_scan": "scan", "enc_dedup": "dedup_words_kernel", "enc_rep": "encode_rep_words_kernel",
              "enc_copy": "copy_word_ids_kernel"}
     ach = algo / (single[dom] * 1e-3) / 1e9

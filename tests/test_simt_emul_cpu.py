@@ -183,7 +183,7 @@ def test_encode_linear_product_id_is_refused_for_a_foreign_model(emu, oracle, mo
     sents = [synth.readme_corpus(n_lines=3, seed=4), b"abab cdcd abcd", b"dddd aaaa"]
     g = EG.GpuEncoder(m2)
     assert g.encode(sents) == oracle.encoder(m2).encode(sents)
-    assert emu.yttm_stage_ms(emu.yttm_api_device_context(g.h), b"enc_variant") == 8.0  # refused: the default (dedup) path
+    assert emu.yttm_stage_ms(emu.yttm_api_device_context(g.h), b"enc_variant") == 24.0  # refused: the default path (dedup 8 + direct output 16)
 
 
 def test_encode_chunked_pipeline(emu, oracle, monkeypatch):
@@ -338,10 +338,15 @@ def test_encode_dedup_variant(emu, oracle, monkeypatch, knobs):
     for kw in EG.KW:
         assert g.encode(sents, **kw) == o.encode(sents, **kw)
     ctx = emu.yttm_api_device_context(g.h)
-    assert emu.yttm_stage_ms(ctx, b"enc_variant") == 8.0
-    # with dropout every occurrence draws for itself: the per-word kernel runs
+    assert emu.yttm_stage_ms(ctx, b"enc_variant") == 24.0   # dedup (8) + direct output (16)
+    # with dropout every occurrence draws for itself: the per-word kernel runs (direct output stays)
     assert g.encode(sents[:200], dropout=0.3, seed=5) == o.encode(sents[:200], dropout=0.3, seed=5)
-    assert emu.yttm_stage_ms(ctx, b"enc_variant") == 0.0
+    assert emu.yttm_stage_ms(ctx, b"enc_variant") == 16.0
+    monkeypatch.setenv("YTTM_ENC_SLOTS", "1")      # the same kernels through the round-1 slot flow (copy + ordered compaction)
+    for kw in EG.KW:
+        assert g.encode(sents, **kw) == o.encode(sents, **kw)
+    assert emu.yttm_stage_ms(ctx, b"enc_variant") == 8.0
+    monkeypatch.delenv("YTTM_ENC_SLOTS")
     monkeypatch.setenv("YTTM_ENC_PLAIN", "1")      # the round-1 kernels remain selectable
     monkeypatch.delenv("YTTM_ENC_DEDUP")
     assert g.encode(sents, eos=True) == o.encode(sents, eos=True)

@@ -34,7 +34,7 @@ def test_encode_variants_return_the_default_ids_on_the_bench_shape(product, tmp_
                        env=_clean_env(), stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=420)
     assert r.returncode == 0 and out_json.exists(), r.stderr.decode(errors="replace")[-1500:]
     res = json.loads(out_json.read_text())
-    assert res["default"]["n_ids"] > 0 and set(res) >= {"default", "plain", "plain+find_vec", "plain+dedup", "bucketed"}
+    assert res["default"]["n_ids"] > 0 and set(res) >= {"default", "slots", "plain", "plain+find_vec", "plain+dedup", "bucketed"}
     bad = [k for k, v in res.items() if not v.get("ids_equal_default", True)]
     assert not bad, "variants differ from the default ids on hardware: %s" % bad
     try:  # evidence (scratch directory; ignored if not writable)

@@ -40,9 +40,9 @@ def main(L=None, n_sent=None, reps=None, train_bytes=20_000_000, vocab=8000):
         d_bytes, d_offs = d_bytes.cuda(), d_offs.cuda()
     base = None
     out = {}
-    KNOBS = ("YTTM_ENC_PLAIN", "YTTM_ENC_FIND_CACHED", "YTTM_ENC_BUCKETED", "YTTM_ENC_ZLIN", "YTTM_ENC_DEDUP", "YTTM_ENC_FIND_VEC", "YTTM_ENC_LONG")
+    KNOBS = ("YTTM_ENC_PLAIN", "YTTM_ENC_SLOTS", "YTTM_ENC_FIND_CACHED", "YTTM_ENC_BUCKETED", "YTTM_ENC_ZLIN", "YTTM_ENC_DEDUP", "YTTM_ENC_FIND_VEC", "YTTM_ENC_LONG")
     # default since round 2 = vector word finder + word dedup + block-per-long-word; "plain" = the round-1 kernels
-    for name, env in [("default", []), ("plain", ["YTTM_ENC_PLAIN"]), ("plain+find_vec", ["YTTM_ENC_PLAIN", "YTTM_ENC_FIND_VEC"]),
+    for name, env in [("default", []), ("slots", ["YTTM_ENC_SLOTS"]), ("plain", ["YTTM_ENC_PLAIN"]), ("plain+find_vec", ["YTTM_ENC_PLAIN", "YTTM_ENC_FIND_VEC"]),
                       ("plain+dedup", ["YTTM_ENC_PLAIN", "YTTM_ENC_DEDUP"]), ("bucketed", ["YTTM_ENC_BUCKETED"]),
                       ("dedup+find_cached", ["YTTM_ENC_FIND_CACHED"])]:
         for k in KNOBS:
@@ -50,8 +50,8 @@ def main(L=None, n_sent=None, reps=None, train_bytes=20_000_000, vocab=8000):
         for k in env:
             os.environ[k] = "1"
         ms = {"enc_find": [], "enc_words": [], "enc_gather": [], "encode": []}
-        if name in ("default", "plain+dedup", "dedup+find_cached"):  # the three launches inside enc_words
-            ms.update({"enc_dedup": [], "enc_rep": [], "enc_copy": []})
+        if name in ("default", "slots", "plain+dedup", "dedup+find_cached"):  # the launches inside enc_words
+            ms.update({"enc_dedup": [], "enc_rep": [], "enc_copy": [], "enc_count": []})
         for _ in range(reps + 2):
             p_ids, p_off, n = C.c_void_p(), C.c_void_p(), C.c_uint64(0)
             rc = L.yttm_enc_run_device(enc, d_bytes.data_ptr(), d_offs.data_ptr(), len(buf), n_sent, 0, 0, 0, 0.0, 0, 0,

@@ -17,7 +17,7 @@ import _cases  # noqa: E402
 from _bind import read_model, tmp_model_path  # noqa: E402
 from youtokentome_b200 import _lib, synth  # noqa: E402
 
-ENC_KNOBS = ["YTTM_ENC_PLAIN", "YTTM_ENC_FIND_CACHED", "YTTM_ENC_FIND_VEC", "YTTM_ENC_BUCKETED", "YTTM_ENC_ZLIN", "YTTM_ENC_LONG", "YTTM_ENC_DEDUP"]
+ENC_KNOBS = ["YTTM_ENC_PLAIN", "YTTM_ENC_SLOTS", "YTTM_ENC_FIND_CACHED", "YTTM_ENC_FIND_VEC", "YTTM_ENC_BUCKETED", "YTTM_ENC_ZLIN", "YTTM_ENC_LONG", "YTTM_ENC_DEDUP"]
 
 
 def main():
@@ -58,7 +58,7 @@ def main():
     g, o = GpuEncoder(model), orc.encoder(model)
     variants = [[]] + [[k] for k in ENC_KNOBS] + [["YTTM_ENC_FIND_VEC", "YTTM_ENC_DEDUP"], ["YTTM_ENC_FIND_CACHED", "YTTM_ENC_BUCKETED", "YTTM_ENC_ZLIN"]]
     if quick:
-        variants = [[], ["YTTM_ENC_PLAIN"], ["YTTM_ENC_BUCKETED", "YTTM_ENC_LONG"]]
+        variants = [[], ["YTTM_ENC_PLAIN"], ["YTTM_ENC_SLOTS"], ["YTTM_ENC_BUCKETED", "YTTM_ENC_LONG"]]
     for env in variants:
         for k in ENC_KNOBS:
             os.environ.pop(k, None)

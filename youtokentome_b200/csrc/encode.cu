@@ -53,6 +53,10 @@ struct EncArgs {
   uint32_t *word_sent;       //            sentence index inside the batch
   unsigned long long *n_words;
   unsigned long long *n_ids;  // per sentence (uint64 so the generic scan applies)
+  uint32_t *sent_wbase;       // DIRECT output path: first work item / number of work items of every sentence
+  uint32_t *sent_wcnt;
+  uint32_t *n_tok;            // DIRECT output path: ids of every encoded work item
+  int direct;                 // 1: ids go from the encoded words straight to the packed output (no slot compaction)
   const uint32_t *cp2id;
   RuleTab rt;
   uint32_t space_id;
@@ -218,6 +222,20 @@ __device__ __forceinline__ uint32_t find_vec_word(const uint8_t *s, int64_t p, i
     }
   return w;
 }
+// SWAR helpers on four bytes at once: high bit of every byte that is an ASCII space (0x20 or 0x09..0x0d) / equals v
+__device__ __forceinline__ uint32_t swar_eq(uint32_t w, uint32_t v4) {
+  const uint32_t t = w ^ v4;
+  return ~(((t & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t | 0x7f7f7f7fu);
+}
+__device__ __forceinline__ uint32_t swar_space(uint32_t w) {
+  const uint32_t b7 = w & 0x7f7f7f7fu;
+  const uint32_t ge9 = b7 + 0x77777777u, ge14 = b7 + 0x72727272u;   // bit 7 of a byte: (b & 0x7f) >= 9 / >= 14 (no carry between bytes)
+  return (swar_eq(w, 0x20202020u) | (ge9 & ~ge14 & ~w)) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t swar_mask4(uint32_t hi) {  // 0x80 bits of four bytes -> 4-bit mask
+  const uint32_t m = hi >> 7;
+  return (m | (m >> 7) | (m >> 14) | (m >> 21)) & 15u;
+}
 // word-start flags (bit k = byte p + k) of the lane's four bytes
 __device__ __forceinline__ uint32_t find_vec_flags(const uint8_t *s, int64_t p, int64_t lo, int64_t hi, int64_t n_total,
                                                    unsigned lane) {
@@ -225,6 +243,15 @@ __device__ __forceinline__ uint32_t find_vec_flags(const uint8_t *s, int64_t p, 
   uint32_t pv = __shfl_up_sync(0xffffffffu, c, 1), nx = __shfl_down_sync(0xffffffffu, c, 1);
   if (lane == 0) pv = find_vec_word(s, p - 4, lo, hi, n_total);
   if (lane == 31) nx = find_vec_word(s, p + 4, lo, hi, n_total);
+  uint32_t inside = 15u;   // bytes of this lane that belong to the sentence
+  if (p < lo) inside &= lo - p >= 4 ? 0u : 15u << (uint32_t)(lo - p);
+  if (p + 4 > hi) inside &= hi <= p ? 0u : 15u >> (uint32_t)(p + 4 - hi);
+  if (!((swar_eq(pv, 0xe2e2e2e2u) | swar_eq(c, 0xe2e2e2e2u) | swar_eq(nx, 0xe2e2e2e2u)) & 0x80808080u)) {
+    // fast path (no 0xE2 within four bytes either side, so no U+2581 can touch these positions): a word starts where an
+    // ASCII space (or the sentinel in front of the sentence) is followed by a non-space byte
+    const uint32_t sp = swar_mask4(swar_space(c)), sp_prev = swar_mask4(swar_space(pv)) >> 3;
+    return ((sp << 1) | sp_prev) & ~sp & inside & 15u;
+  }
   const uint64_t X = (uint64_t)pv | ((uint64_t)c << 32), Y = (uint64_t)c | ((uint64_t)nx << 32);  // bytes p-4 .. p+3, p .. p+7
   uint32_t f = 0;
 #pragma unroll
@@ -232,63 +259,82 @@ __device__ __forceinline__ uint32_t find_vec_flags(const uint8_t *s, int64_t p, 
     const uint32_t t = (uint32_t)(X >> (8 * (1 + k))), u = (uint32_t)(Y >> (8 * k));  // t: bytes p+k-3 .., u: bytes p+k ..
     const bool before = is_space_byte((uint8_t)(t >> 16)) || (t & 0xffffffu) == 0x8196e2u;
     const bool at = is_space_byte((uint8_t)u) || (u & 0xffffffu) == 0x8196e2u;
-    if (p + k >= lo && p + k < hi && before && !at) f |= 1u << k;
+    if (before && !at) f |= 1u << k;
   }
-  return f;
+  return f & inside;
 }
+constexpr int FIND_SPW = 4;  // sentences per warp and round: one work-list reservation (atomic) per 32 sentences
 __global__ void __launch_bounds__(256) find_words_vec_kernel(EncArgs a) {
-  __shared__ unsigned long long s_cnt[8], s_base;
+  __shared__ unsigned long long s_cnt[8 * FIND_SPW], s_base;
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint64_t o0 = a.offs[0];
   const int64_t n_total = (int64_t)(a.offs[a.n_sent] - o0);
   const int64_t mis = (int64_t)(reinterpret_cast<uintptr_t>(a.bytes) & 3u);
-  for (uint64_t g = (uint64_t)blockIdx.x * 8; g < a.n_sent; g += (uint64_t)gridDim.x * 8) {  // block-uniform
-    const uint64_t s = g + wid;
-    const bool live = s < a.n_sent;
-    int64_t lo = 0, hi = 0, start = 0;
-    unsigned long long cnt = 0;
-    uint32_t cache = 0;
-    if (live) {
-      lo = (int64_t)(a.offs[s] - o0);
-      hi = (int64_t)(a.offs[s + 1] - o0);
-      start = lo - ((lo + mis) & 3);  // the address of batch byte `start` is 4-byte aligned
-      uint32_t mine = 0;
-      int j = 0;
-      for (int64_t pw = start; pw < hi; pw += 128, j++) {  // warp-uniform
-        const uint32_t f = find_vec_flags(a.bytes, pw + 4 * lane, lo, hi, n_total, lane);
-        if (j < FIND_VEC_CACHE) cache |= f << (4 * j);
-        mine += __popc(f);
+  constexpr uint64_t PER_ROUND = 8 * FIND_SPW;
+  for (uint64_t g = (uint64_t)blockIdx.x * PER_ROUND; g < a.n_sent; g += (uint64_t)gridDim.x * PER_ROUND) {  // block-uniform
+    int64_t lo[FIND_SPW], hi[FIND_SPW], start[FIND_SPW];
+    uint32_t cnt[FIND_SPW];
+    uint32_t cache = 0;  // flags of the first FIND_VEC_CACHE / FIND_SPW chunks of every sentence, 4 bits per chunk
+    constexpr int CPS = FIND_VEC_CACHE / FIND_SPW;  // cached chunks per sentence (2: a 128-byte sentence spans at most 2)
+#pragma unroll
+    for (int q = 0; q < FIND_SPW; q++) {
+      const uint64_t s = g + (uint64_t)wid * FIND_SPW + q;
+      lo[q] = hi[q] = start[q] = 0;
+      cnt[q] = 0;
+      if (s < a.n_sent) {  // warp-uniform
+        lo[q] = (int64_t)(a.offs[s] - o0);
+        hi[q] = (int64_t)(a.offs[s + 1] - o0);
+        start[q] = lo[q] - ((lo[q] + mis) & 3);  // the address of batch byte `start` is 4-byte aligned
+        uint32_t mine = 0;
+        int j = 0;
+        for (int64_t pw = start[q]; pw < hi[q]; pw += 128, j++) {  // warp-uniform
+          const uint32_t f = find_vec_flags(a.bytes, pw + 4 * lane, lo[q], hi[q], n_total, lane);
+          if (j < CPS) cache |= f << (4 * (q * CPS + j));
+          mine += __popc(f);
+        }
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        cnt[q] = mine;
+        if (lane == 0 && !a.direct) {
+          const uint64_t base = sent_base((uint64_t)lo[q], s), len = (uint64_t)(hi[q] - lo[q]);
+          a.n_ids[s] = (a.bos ? 1 : 0) + (a.eos ? 1 : 0);
+          if (a.bos) a.slots[base] = a.bos_id;
+          if (a.eos) a.slots[base + len + 2] = a.eos_id;
+        }
       }
-      for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-      cnt = mine;
-      if (lane == 0) {
-        const uint64_t base = sent_base((uint64_t)lo, s), len = (uint64_t)(hi - lo);
-        a.n_ids[s] = (a.bos ? 1 : 0) + (a.eos ? 1 : 0);
-        if (a.bos) a.slots[base] = a.bos_id;
-        if (a.eos) a.slots[base + len + 2] = a.eos_id;
+      if (lane == 0) s_cnt[wid * FIND_SPW + q] = cnt[q];
+    }
+    __syncthreads();
+    if (wid == 0) {  // exclusive prefix of the 32 sentence counts + ONE reservation for the round
+      const unsigned long long c = s_cnt[lane];
+      unsigned long long x = c;
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+        if ((int)lane >= o) x += y;
       }
-    }
-    if (lane == 0) s_cnt[wid] = cnt;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned long long tot = 0;
-      for (int i = 0; i < 8; i++) { unsigned long long c = s_cnt[i]; s_cnt[i] = tot; tot += c; }
-      s_base = tot ? atomicAdd(a.n_words, tot) : 0ull;
+      s_cnt[lane] = x - c;
+      if (lane == 31) s_base = x ? atomicAdd(a.n_words, x) : 0ull;
     }
     __syncthreads();
-    if (live && cnt) {
-      unsigned long long idx = s_base + s_cnt[wid];
+#pragma unroll
+    for (int q = 0; q < FIND_SPW; q++) {
+      const uint64_t s = g + (uint64_t)wid * FIND_SPW + q;
+      if (s >= a.n_sent) continue;  // warp-uniform
+      unsigned long long idx = s_base + s_cnt[wid * FIND_SPW + q];
+      if (lane == 0 && a.direct) { a.sent_wbase[s] = (uint32_t)idx; a.sent_wcnt[s] = cnt[q]; }
+      if (!cnt[q]) continue;
       const unsigned below = (1u << lane) - 1u;
       int j = 0;
-      for (int64_t pw = start; pw < hi; pw += 128, j++) {
+      for (int64_t pw = start[q]; pw < hi[q]; pw += 128, j++) {
         const int64_t p = pw + 4 * lane;
-        const uint32_t f = j < FIND_VEC_CACHE ? (cache >> (4 * j)) & 15u : find_vec_flags(a.bytes, p, lo, hi, n_total, lane);
+        const uint32_t f = j < CPS ? (cache >> (4 * (q * CPS + j))) & 15u : find_vec_flags(a.bytes, p, lo[q], hi[q], n_total, lane);
         const unsigned b0 = __ballot_sync(0xffffffffu, f & 1u), b1 = __ballot_sync(0xffffffffu, f & 2u),
                        b2 = __ballot_sync(0xffffffffu, f & 4u), b3 = __ballot_sync(0xffffffffu, f & 8u);
-        unsigned long long i = idx + __popc(b0 & below) + __popc(b1 & below) + __popc(b2 & below) + __popc(b3 & below);
+        // byte order: a lane's index = words in earlier lanes (all four bits) + its own lower bits
+        const unsigned all_below = __popc(b0 & below) + __popc(b1 & below) + __popc(b2 & below) + __popc(b3 & below);
+        unsigned long long i = idx + all_below;
 #pragma unroll
         for (int k = 0; k < 4; k++)
-          if ((f >> k) & 1u) {  // byte order: lanes first, then the lane's four bytes
+          if ((f >> k) & 1u) {
             a.word_pos[i] = (uint32_t)(p + k);
             a.word_sent[i] = (uint32_t)s;
             i++;
@@ -333,9 +379,11 @@ __global__ void __launch_bounds__(128) encode_words_kernel(EncArgs a, uint64_t n
                       a.first_sentence + s, t, a.ranks + slot0, DROPOUT ? a.aux + 6 * slot0 : nullptr, &owned);
       for (uint32_t i = 0; i < n; i++)
         if ((uint32_t)t[i] & UNK_FLAG) t[i] = a.unk_id;
-      for (uint32_t i = n; i < owned; i++) t[i] = EMPTY_SLOT;
+      if (!a.direct)
+        for (uint32_t i = n; i < owned; i++) t[i] = EMPTY_SLOT;
     }
-    if (n) atomicAdd(a.n_ids + s, (unsigned long long)n);
+    if (a.direct) a.n_tok[w] = n;
+    else if (n) atomicAdd(a.n_ids + s, (unsigned long long)n);
   }
 }
 
@@ -608,12 +656,12 @@ __global__ void __launch_bounds__(LONG_T) encode_long_words_kernel(EncArgs a, Lo
     }
     // ---- final ids; the unused slots of the word go back to EMPTY
     const uint32_t n_out = no_unit ? 0 : n;
-    for (uint32_t i = threadIdx.x; i < owned; i += LONG_T) {
+    for (uint32_t i = threadIdx.x; i < (a.direct ? n_out : owned); i += LONG_T) {
       const uint32_t v = t[i];
       t[i] = i < n_out ? ((v & UNK_FLAG) ? (uint32_t)a.unk_id : v) : (uint32_t)EMPTY_SLOT;
     }
     if (threadIdx.x == 0) {
-      if (n_out) atomicAdd(a.n_ids + s, (unsigned long long)n_out);
+      if (n_out && !a.direct) atomicAdd(a.n_ids + s, (unsigned long long)n_out);
       if (ll.n_tok) ll.n_tok[ll.item[w]] = n_out;
     }
     __syncthreads();
@@ -728,10 +776,11 @@ __global__ void __launch_bounds__(128) encode_rep_words_kernel(EncArgs a, DedupA
                       a.ranks + slot0, nullptr, &owned);
       for (uint32_t k = 0; k < n; k++)
         if ((uint32_t)t[k] & UNK_FLAG) t[k] = a.unk_id;
-      for (uint32_t k = n; k < owned; k++) t[k] = EMPTY_SLOT;
+      if (!a.direct)
+        for (uint32_t k = n; k < owned; k++) t[k] = EMPTY_SLOT;
     }
     d.n_tok[w] = n;
-    if (n) atomicAdd(a.n_ids + s, (unsigned long long)n);
+    if (n && !a.direct) atomicAdd(a.n_ids + s, (unsigned long long)n);
   }
 }
 
@@ -747,6 +796,67 @@ __global__ void __launch_bounds__(256) copy_word_ids_kernel(EncArgs a, uint64_t 
     int32_t *dst = a.slots + ((uint64_t)a.word_pos[w] + 3ull * s + 1);  // the same number of slots as the representative's
     for (uint32_t k = 0; k < n; k++) dst[k] = src[k];
     atomicAdd(a.n_ids + s, (unsigned long long)n);
+  }
+}
+
+// ---- DIRECT output path (default since round 2) ---------------------------------------------------------------
+// The words of sentence s are the work items [sent_wbase[s], + sent_wcnt[s]) in byte order (find_words_vec_kernel); the
+// ids of work item w are the n_tok[r] values at slot(word_pos[r] + 3 word_sent[r] + 1) of its representative r = rep[w]
+// (r = w without dedup).  Two warp-per-sentence kernels replace the 4 (B + 3 S)-byte slot buffer round trip of round 1
+// (memset + per-occurrence copy + ordered compaction: 1.5 GB of DRAM traffic per 128 MB batch, profiles/):
+//   sentence_ids_kernel   n_ids[s] = bos + eos + sum of n_tok over the sentence's words
+//   emit_ids_kernel       every lane takes one word, a warp scan gives its place, ids are copied from the
+//                         representative (reverse = mirrored index)
+__global__ void __launch_bounds__(256) sentence_ids_kernel(EncArgs a, const uint32_t *__restrict__ rep) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t s = warp; s < a.n_sent; s += nwarps) {
+    const uint32_t w0 = a.sent_wbase[s], nw = a.sent_wcnt[s];
+    uint32_t sum = 0;
+    for (uint32_t i = lane; i < nw; i += 32) {
+      const uint32_t w = w0 + i;
+      sum += a.n_tok[rep ? rep[w] : w];
+    }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) a.n_ids[s] = (unsigned long long)sum + (a.bos ? 1 : 0) + (a.eos ? 1 : 0);
+  }
+}
+
+__global__ void __launch_bounds__(256) emit_ids_kernel(EncArgs a, const uint32_t *__restrict__ rep,
+                                                       const unsigned long long *__restrict__ out_off, int32_t *__restrict__ out) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t s = warp; s < a.n_sent; s += nwarps) {
+    const uint32_t w0 = a.sent_wbase[s], nw = a.sent_wcnt[s];
+    const unsigned long long ob = out_off[s], total = a.n_ids[s];
+    auto at = [&](unsigned long long j) { return ob + (a.reverse ? total - 1 - j : j); };
+    if (lane == 0) {
+      if (a.bos) out[at(0)] = a.bos_id;
+      if (a.eos) out[at(total - 1)] = a.eos_id;
+    }
+    unsigned long long pos = a.bos ? 1 : 0;
+    for (uint32_t i0 = 0; i0 < nw; i0 += 32) {  // warp-uniform
+      const uint32_t i = i0 + lane;
+      uint32_t r = 0, n = 0;
+      if (i < nw) {
+        r = rep ? rep[w0 + i] : w0 + i;
+        n = a.n_tok[r];
+      }
+      uint32_t x = n;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if ((int)lane >= o) x += y;
+      }
+      const uint32_t all = __shfl_sync(0xffffffffu, x, 31);
+      if (n) {
+        const int32_t *src = a.slots + ((uint64_t)a.word_pos[r] + 3ull * a.word_sent[r] + 1);
+        const unsigned long long first = pos + (x - n);
+        for (uint32_t k = 0; k < n; k++) out[at(first + k)] = src[k];
+      }
+      pos += all;
+    }
   }
 }
 
@@ -794,10 +904,11 @@ struct yttm_enc {
   // (H2D of chunk i+1 and D2H of chunk i-1 overlap the kernels of chunk i)
   struct Slot {
     ytc::DevBuf d_bytes, d_offs, slots, ranks, aux, wpos, wsent, nids, out_off, out_ids, counter, longw;
-    ytc::DevBuf dd_tab, dd_rep, dd_ntok, dd_list;  // YTTM_ENC_DEDUP only
+    ytc::DevBuf dd_tab, dd_rep, dd_ntok, dd_list;  // word dedup
+    ytc::DevBuf swb, swc;                           // direct output path: per-sentence word ranges
     void release() {
       ytc::DevBuf *b[] = {&d_bytes, &d_offs, &slots, &ranks, &aux, &wpos, &wsent, &nids, &out_off, &out_ids, &counter, &longw,
-                          &dd_tab, &dd_rep, &dd_ntok, &dd_list};
+                          &dd_tab, &dd_rep, &dd_ntok, &dd_list, &swb, &swc};
       for (auto *x : b) x->release();
     }
   } slot[2];
@@ -842,38 +953,53 @@ int enc_device(yttm_enc *enc, yttm_enc::Slot *e, const uint8_t *d_bytes, const u
   auto *d_total = e->counter.as<unsigned long long>() + 1;
   if (n_sent == 0) return 0;
   ytc::timer_begin(c, "encode");
+  // Kernel selection.  Defaults since round 2 (measured on B200, profiles/r02_ab_encode_*.json, ids identical):
+  //   * the 4-bytes-per-lane word finder (SWAR space detection, 4 sentences per warp and round);
+  //   * dropout = 0: the word-dedup path — every distinct word of the batch is encoded once (3.45 -> 1.24 ms), words of
+  //     more than LONG_W slots get a whole block each (a 16 KB word: 30 s on one thread, 9 ms on a block);
+  //   * the DIRECT output path: ids go from the encoded words straight to the packed output (sentence_ids_kernel +
+  //     emit_ids_kernel) instead of through the 4 (B + 3 S)-byte slot buffer (memset + copy + ordered compaction).
+  // YTTM_ENC_PLAIN=1 selects the round-1 kernels and slot flow (A/B, tests); YTTM_ENC_SLOTS=1 keeps the new kernels
+  // but the slot flow; the bucketed / zlin / find_cached variants stay opt-in and use the slot flow.
+  const bool plain = std::getenv("YTTM_ENC_PLAIN") != nullptr;
+  const bool zlin = enc->zlin_ok && std::getenv("YTTM_ENC_ZLIN") != nullptr;
+  const bool want_bucketed = std::getenv("YTTM_ENC_BUCKETED") != nullptr;
+  const bool dedup = a.drop_thresh == 0 && (std::getenv("YTTM_ENC_DEDUP") != nullptr || (!plain && !zlin && !want_bucketed));
+  const bool longw = a.drop_thresh == 0 && (std::getenv("YTTM_ENC_LONG") != nullptr || !plain);
+  const bool bucketed = !dedup && (zlin || want_bucketed || (longw && std::getenv("YTTM_ENC_LONG") != nullptr));
+  const bool find_vec = std::getenv("YTTM_ENC_FIND_VEC") || !(plain || std::getenv("YTTM_ENC_FIND_CACHED"));
+  const bool direct = find_vec && !plain && !bucketed && !std::getenv("YTTM_ENC_SLOTS") && !std::getenv("YTTM_ENC_FIND_CACHED");
+  a.direct = direct ? 1 : 0;
+  a.sent_wbase = a.sent_wcnt = a.n_tok = nullptr;
+  if (direct) {
+    YT_CUDA(c, e->swb.reserve((n_sent + 1) * 4));
+    YT_CUDA(c, e->swc.reserve((n_sent + 1) * 4));
+    a.sent_wbase = e->swb.as<uint32_t>();
+    a.sent_wcnt = e->swc.as<uint32_t>();
+  }
   {
-    uint64_t warps_needed = n_sent;
-    uint64_t blocks = std::min<uint64_t>((warps_needed + 7) / 8, (uint64_t)c->n_sm * 8);
     ytc::timer_begin(c, "enc_find");
-    YT_CUDA(c, cudaMemsetAsync(a.slots, 0xff, n_slots * 4, c->stream));  // EMPTY_SLOT == -1
-    if (std::getenv("YTTM_ENC_FIND_VEC") || !(std::getenv("YTTM_ENC_PLAIN") || std::getenv("YTTM_ENC_FIND_CACHED")))
-      find_words_vec_kernel<<<(unsigned)std::max<uint64_t>(blocks, 1), 256, 0, c->stream>>>(a);  // default since round 2
-    else if (std::getenv("YTTM_ENC_FIND_CACHED"))
-      find_words_cached_kernel<<<(unsigned)std::max<uint64_t>(blocks, 1), 256, 0, c->stream>>>(a);
-    else
-      find_words_kernel<<<(unsigned)std::max<uint64_t>(blocks, 1), 256, 0, c->stream>>>(a);
+    if (!direct) YT_CUDA(c, cudaMemsetAsync(a.slots, 0xff, n_slots * 4, c->stream));  // EMPTY_SLOT == -1
+    if (find_vec) {
+      const uint64_t blocks = std::min<uint64_t>((n_sent + 8 * FIND_SPW - 1) / (8 * FIND_SPW), (uint64_t)c->n_sm * 8);
+      find_words_vec_kernel<<<(unsigned)std::max<uint64_t>(blocks, 1), 256, 0, c->stream>>>(a);
+    } else {
+      const uint64_t blocks = std::min<uint64_t>((n_sent + 7) / 8, (uint64_t)c->n_sm * 8);
+      if (std::getenv("YTTM_ENC_FIND_CACHED")) find_words_cached_kernel<<<(unsigned)std::max<uint64_t>(blocks, 1), 256, 0, c->stream>>>(a);
+      else find_words_kernel<<<(unsigned)std::max<uint64_t>(blocks, 1), 256, 0, c->stream>>>(a);
+    }
     ytc::timer_end(c, "enc_find");
     c->launches++;
   }
   unsigned long long n_words = 0;
   YT_CUDA(c, cudaMemcpyAsync(&n_words, a.n_words, 8, cudaMemcpyDeviceToHost, c->stream));
   YT_CUDA(c, cudaStreamSynchronize(c->stream));
+  const uint32_t *d_rep = nullptr;
   if (n_words) {
     uint64_t blocks = std::min<uint64_t>((n_words + 127) / 128, (uint64_t)c->n_sm * 16);
     ytc::timer_begin(c, "enc_words");
-    // Defaults since round 2 (measured on B200, profiles/r02_ab_encode.json: find 1.24 -> 1.03 ms, words 3.45 -> 1.24 ms,
-    // ids identical): the 4-bytes-per-lane word finder, and for dropout = 0 the word-dedup path (every distinct word of
-    // the batch is encoded once) with words of more than LONG_W slots handed to a whole block each (a 16 KB word: 30 s
-    // on one thread, 9 ms on a block).  YTTM_ENC_PLAIN=1 selects the round-1 kernels (A/B, tests); the bucketed / zlin
-    // variants stay opt-in (bucketed: 3.45 -> 2.95 ms, superseded by dedup; zlin: slower).
-    const bool plain = std::getenv("YTTM_ENC_PLAIN") != nullptr;
-    const bool zlin = enc->zlin_ok && std::getenv("YTTM_ENC_ZLIN") != nullptr;
-    const bool dedup = a.drop_thresh == 0 && (std::getenv("YTTM_ENC_DEDUP") != nullptr || (!plain && !zlin && !std::getenv("YTTM_ENC_BUCKETED")));
-    const bool longw = a.drop_thresh == 0 && (std::getenv("YTTM_ENC_LONG") != nullptr || !plain);
-    const bool bucketed = !dedup && (zlin || longw || std::getenv("YTTM_ENC_BUCKETED") != nullptr);
     LongList ll{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
-    if (longw) {
+    if (longw && (dedup || bucketed)) {
       const uint32_t cap = (uint32_t)(n_bytes / LONG_W + 16);
       YT_CUDA(c, e->longw.reserve((size_t)cap * 16 + 16));
       ll.n = e->longw.as<unsigned long long>();
@@ -884,36 +1010,42 @@ int enc_device(yttm_enc *enc, yttm_enc::Slot *e, const uint8_t *d_bytes, const u
       ll.cap = cap;
       YT_CUDA(c, cudaMemsetAsync(ll.n, 0, 8, c->stream));
     }
-    c->timers["enc_variant"].ms = dedup ? 8.f : (float)((longw ? 4 : 0) + (zlin ? 2 : 0) + (bucketed ? 1 : 0));  // yttm_stage_ms(ctx, "enc_variant")
+    // yttm_stage_ms(ctx, "enc_variant"): 8 dedup, +16 direct output; else 4 long + 2 zlin + 1 bucketed
+    c->timers["enc_variant"].ms = (float)((dedup ? 8 : (ll.cap ? 4 : 0) + (zlin ? 2 : 0) + (bucketed ? 1 : 0)) + (direct ? 16 : 0));
+    if (direct || dedup) YT_CUDA(c, e->dd_ntok.reserve(n_words * 4 + 16));
+    a.n_tok = direct ? e->dd_ntok.as<uint32_t>() : nullptr;
     if (dedup) {
       // table: 2 slots per occurrence up to 2^21 slots (16 MB, L2-resident); beyond that it works as a cache
       uint64_t tslots = std::max<uint64_t>(ytc::pow2ceil(std::min<uint64_t>(n_words, 1ull << 20) * 2), 1024);
       if (const char *env = std::getenv("YTTM_ENC_DEDUP_SLOTS")) tslots = ytc::pow2ceil((uint64_t)std::max(1, std::atoi(env)));  // tests: tiny tables
       YT_CUDA(c, e->dd_tab.reserve(tslots * 8));
       YT_CUDA(c, e->dd_rep.reserve(n_words * 4 + 16));
-      YT_CUDA(c, e->dd_ntok.reserve(n_words * 4 + 16));
       YT_CUDA(c, e->dd_list.reserve(n_words * 4 + 16));
       DedupArgs d;
       d.tab = e->dd_tab.as<unsigned long long>(); d.mask = (uint32_t)(tslots - 1);
       d.rep = e->dd_rep.as<uint32_t>(); d.n_tok = e->dd_ntok.as<uint32_t>(); d.list = e->dd_list.as<uint32_t>();
       d.n_list = e->counter.as<unsigned long long>() + 2;  // zeroed with the other counters above
       d.weak_tag = std::getenv("YTTM_ENC_DEDUP_WEAKTAG") != nullptr;  // tests: tag collisions everywhere
+      d_rep = d.rep;
       YT_CUDA(c, cudaMemsetAsync(d.tab, 0xff, tslots * 8, c->stream));
       ytc::timer_begin(c, "enc_dedup");
       dedup_words_kernel<<<(unsigned)blocks, 128, 0, c->stream>>>(a, n_words, d);
       ytc::timer_end(c, "enc_dedup");
       ytc::timer_begin(c, "enc_rep");
-      if (longw) ll.n_tok = d.n_tok;
+      if (ll.cap) ll.n_tok = d.n_tok;
       encode_rep_words_kernel<<<(unsigned)blocks, 128, 0, c->stream>>>(a, d, ll);
-      if (longw) {  // no host round trip: the blocks read the list length themselves
+      if (ll.cap) {  // no host round trip: the blocks read the list length themselves
         encode_long_words_kernel<<<(unsigned)c->n_sm, LONG_T, 0, c->stream>>>(a, ll);
         c->launches++;
       }
       ytc::timer_end(c, "enc_rep");
-      ytc::timer_begin(c, "enc_copy");
-      copy_word_ids_kernel<<<(unsigned)std::min<uint64_t>((n_words + 255) / 256, (uint64_t)c->n_sm * 8), 256, 0, c->stream>>>(a, n_words, d);
-      ytc::timer_end(c, "enc_copy");
-      c->launches += 2;
+      if (!direct) {
+        ytc::timer_begin(c, "enc_copy");
+        copy_word_ids_kernel<<<(unsigned)std::min<uint64_t>((n_words + 255) / 256, (uint64_t)c->n_sm * 8), 256, 0, c->stream>>>(a, n_words, d);
+        ytc::timer_end(c, "enc_copy");
+        c->launches++;
+      }
+      c->launches++;
     } else if (bucketed) {
       const unsigned wb = (unsigned)std::min<uint64_t>((n_words + BUCKET_WINDOW - 1) / BUCKET_WINDOW, (uint64_t)c->n_sm * 16);
       if (zlin) {
@@ -921,13 +1053,20 @@ int enc_device(yttm_enc *enc, yttm_enc::Slot *e, const uint8_t *d_bytes, const u
         else encode_words_bucketed_kernel<false, true><<<wb, 128, 0, c->stream>>>(a, n_words, enc->zlin, ll);
       } else if (a.drop_thresh) encode_words_bucketed_kernel<true, false><<<wb, 128, 0, c->stream>>>(a, n_words, enc->zlin, ll);
       else encode_words_bucketed_kernel<false, false><<<wb, 128, 0, c->stream>>>(a, n_words, enc->zlin, ll);
-      if (longw) {  // no host round trip: the blocks read the list length themselves
+      if (ll.cap) {  // no host round trip: the blocks read the list length themselves
         encode_long_words_kernel<<<(unsigned)c->n_sm, LONG_T, 0, c->stream>>>(a, ll);
         c->launches++;
       }
     } else if (a.drop_thresh) encode_words_kernel<true><<<(unsigned)blocks, 128, 0, c->stream>>>(a, n_words);
     else encode_words_kernel<false><<<(unsigned)blocks, 128, 0, c->stream>>>(a, n_words);
     ytc::timer_end(c, "enc_words");
+    c->launches++;
+  }
+  const uint64_t sblocks = std::max<uint64_t>(std::min<uint64_t>((n_sent + 7) / 8, (uint64_t)c->n_sm * 8), 1);
+  if (direct) {  // per-sentence id counts from the words' token counts
+    ytc::timer_begin(c, "enc_count");
+    sentence_ids_kernel<<<(unsigned)sblocks, 256, 0, c->stream>>>(a, d_rep);
+    ytc::timer_end(c, "enc_count");
     c->launches++;
   }
   // exclusive scan of the per-sentence id counts -> output offsets
@@ -941,10 +1080,9 @@ int enc_device(yttm_enc *enc, yttm_enc::Slot *e, const uint8_t *d_bytes, const u
   YT_CUDA(c, cudaStreamSynchronize(c->stream));
   YT_CUDA(c, e->out_ids.reserve((total + 8) * 4));
   {
-    uint64_t blocks = std::min<uint64_t>((n_sent + 7) / 8, (uint64_t)c->n_sm * 8);
     ytc::timer_begin(c, "enc_gather");
-    gather_ids_kernel<<<(unsigned)std::max<uint64_t>(blocks, 1), 256, 0, c->stream>>>(
-        a, e->out_off.as<unsigned long long>(), e->out_ids.as<int32_t>());
+    if (direct) emit_ids_kernel<<<(unsigned)sblocks, 256, 0, c->stream>>>(a, d_rep, e->out_off.as<unsigned long long>(), e->out_ids.as<int32_t>());
+    else gather_ids_kernel<<<(unsigned)sblocks, 256, 0, c->stream>>>(a, e->out_off.as<unsigned long long>(), e->out_ids.as<int32_t>());
     ytc::timer_end(c, "enc_gather");
     c->launches++;
   }
