@@ -102,6 +102,24 @@ __device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long lon
   return __atomic_load_n(p, __ATOMIC_RELAXED);
 #endif
 }
+__device__ __forceinline__ unsigned long long ld_relaxed_any(const unsigned long long *p, bool sys) {
+#ifndef YT_SIMT_EMU
+  unsigned long long v;
+  if (sys) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  else asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+#else
+  return __atomic_load_n(p, __ATOMIC_RELAXED);
+#endif
+}
+__device__ __forceinline__ void st_relaxed_any(unsigned long long *p, unsigned long long v, bool sys) {
+#ifndef YT_SIMT_EMU
+  if (sys) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+  else asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#else
+  __atomic_store_n(p, v, __ATOMIC_RELAXED);
+#endif
+}
 __device__ __forceinline__ void st_relaxed(unsigned long long *p, unsigned long long v) {
 #ifndef YT_SIMT_EMU
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -125,6 +143,30 @@ constexpr unsigned long long BB_LOW48 = 0xffffffffffffull;
 __device__ __forceinline__ unsigned long long bb_prio45(uint32_t x, uint32_t y) {
   const uint32_t mx = x > y ? x : y, mn = x > y ? y : x;
   return ((unsigned long long)(0x3fffffu - mx) << 23) | ((unsigned long long)(0x3fffffu - mn) << 1) | (x >= y ? 1ull : 0ull);
+}
+
+// Exchange ENTRIES are self-stamped too (the scheme of NCCL's LL protocol): an entry is two 64-bit words, each carrying
+// the low bits of its round, so neither the producer needs a fence between its entries and its count word nor the
+// consumer an acquire — an entry whose stamps are not the round's has simply not arrived yet (NVLink and L2 deliver an
+// aligned 8-byte word whole; nothing orders different addresses without a fence, and a system-scope fence after peer
+// stores cost 9 us per merge on 2 x B200).  w0 = stamp20 | x22 | y22, w1 = stamp20 | value44 (signed).
+// stamp = round % 0xfffff, never 0xfffff: the buffer starts as all-ones.  (A slot left untouched for exactly k * 0xfffff
+// rounds of its parity would carry a matching stamp again; with at most 2^22 merges per job that needs one slot to be
+// idle for half a million merges and then be read in the few hundred nanoseconds before its new content lands.)
+constexpr uint32_t XQ_STAMP_MOD = 0xfffffu;
+__device__ __forceinline__ uint4 xq_pack(uint32_t stamp, unsigned long long key, long long value) {
+  const unsigned long long st = (unsigned long long)stamp << 44;
+  const unsigned long long w0 = st | ((key >> 32) << 22) | (key & 0x3fffffull);
+  const unsigned long long w1 = st | ((unsigned long long)value & 0xfffffffffffull);
+  return make_uint4((uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32));
+}
+// true when both words carry `stamp`; then *key / *value hold the entry
+__device__ __forceinline__ bool xq_unpack(unsigned long long w0, unsigned long long w1, uint32_t stamp, unsigned long long *key,
+                                          long long *value) {
+  if ((uint32_t)(w0 >> 44) != stamp || (uint32_t)(w1 >> 44) != stamp) return false;
+  *key = (((w0 >> 22) & 0x3fffffull) << 32) | (w0 & 0x3fffffull);
+  *value = (long long)(w1 << 20) >> 20;   // sign-extend 44 bits
+  return true;
 }
 
 struct LoopArgs {
@@ -196,11 +238,12 @@ constexpr int CLAIM_WORDS = 1024;  // claim bitmap: up to 32768 words per shared
 struct XqOut {
   size_t off;        // byte offset of the segment inside a region
   uint32_t *s_n;     // shared-memory entry counter of the block (may run past cap: overflow)
+  uint32_t stamp;    // round % XQ_STAMP_MOD of the entries
 };
 __device__ __forceinline__ void xq_store(const LoopArgs &a, const XqOut &o, uint32_t i, unsigned long long key,
                                          long long delta) {
   if (i >= a.xq.seg_cap) return;  // overflow: the count word carries the flag, the host rebuilds the table
-  const uint4 e = make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)delta, (uint32_t)((unsigned long long)delta >> 32));
+  const uint4 e = xq_pack(o.stamp, key, delta);
 #pragma unroll
   for (int d = 0; d < XQ_MAX_WORLD; d++)
     if ((uint32_t)d < a.xq.world) reinterpret_cast<uint4 *>(a.xq.base[d] + o.off)[i] = e;
@@ -482,7 +525,7 @@ __device__ __forceinline__ void xq_poll_counts(const LoopArgs &a, uint32_t round
     const unsigned long long *w = &xq_hdr(a.xq, a.xq.me, parity, s)->counts[b];
     unsigned long long v;
     for (uint32_t spin = 0;; spin++) {
-      v = ld_acquire(w, sys);
+      v = ld_relaxed_any(w, sys);   // entries validate themselves: no acquire needed
       if ((uint32_t)(v >> 32) == round) break;
 #ifdef YT_SIMT_EMU
       emu::yield();
@@ -505,7 +548,7 @@ __device__ __forceinline__ void xq_poll_counts(const LoopArgs &a, uint32_t round
 }
 
 // Up to DRAIN_KEEP table slots a thread has updated in one drain (for the cached arg-max); more: the block sweeps.
-constexpr int DRAIN_KEEP = 4;
+constexpr int DRAIN_KEEP = 2;
 struct Touched { uint64_t slot[DRAIN_KEEP]; unsigned long long key[DRAIN_KEEP]; uint32_t n, dropped; };
 
 // Drain: s_pref holds the entry counts (xq_poll_counts); every entry whose key belongs to partition blockIdx.x is
@@ -559,9 +602,22 @@ __device__ __forceinline__ void xq_drain(const LoopArgs &a, uint32_t round, uint
       if (s_pref[mid] <= i) lo = mid; else hi = mid;
     }
     const uint32_t s = lo / a.xq.nblocks, b = lo - s * a.xq.nblocks;
-    const uint4 e = __ldcg(reinterpret_cast<const uint4 *>(xq_base(a.xq, a.xq.me) + xq_seg_off(a.xq, parity, s, b)) + (i - s_pref[lo]));
-    const unsigned long long key = ((unsigned long long)e.y << 32) | e.x;
-    const long long delta = (long long)(((unsigned long long)e.w << 32) | e.z);
+    const unsigned long long *ep = reinterpret_cast<const unsigned long long *>(
+        xq_base(a.xq, a.xq.me) + xq_seg_off(a.xq, parity, s, b) + (size_t)(i - s_pref[lo]) * sizeof(uint4));
+    unsigned long long key = 0;
+    long long delta = 0;
+    {
+      unsigned long long t0 = 0;
+      for (uint32_t spin = 0; !xq_unpack(ld_relaxed_any(ep, a.xq.world > 1), ld_relaxed_any(ep + 1, a.xq.world > 1), round % XQ_STAMP_MOD, &key, &delta); spin++) {
+#ifdef YT_SIMT_EMU
+        emu::yield();
+#endif
+        if ((spin & 4095u) == 4095u) {   // the count word overtook the entry: it is on its way
+          if (!t0) t0 = gtimer();
+          else if (gtimer() - t0 > a.spin_limit_ns) loop_trap();
+        }
+      }
+    }
     const uint64_t hh = mix64(key);
     if (pair_part(a.tab, hh) != blockIdx.x) continue;
     uint64_t slot = ~0ull;
@@ -577,53 +633,101 @@ __device__ __forceinline__ void xq_drain(const LoopArgs &a, uint32_t round, uint
   if (added) atomicAdd(s_occ_add, added);
 }
 
-// Exact arg-max of this block's partition (all threads; two passes: the largest count first, keys only for the
-// slots that hold it).  Result in *s_out (shared); s_warp: 32 Best of scratch.
-__device__ __forceinline__ void sweep_partition(const LoopArgs &a, uint64_t pbase, uint32_t R, Best *s_warp, Best *s_out) {
+// The cached arg-max of a partition: its TOPK best slots (exact counts) and a bound — the best pair that is NOT among
+// them.  Invariant: every slot outside top[] compares <= bound.  The partition's best is max(top[]) as long as that
+// is not below the bound; only then the partition is swept again.  (The reference keeps a lazy priority queue for the
+// same reason, bpe.cpp:149-314: most merges touch few pairs.)
+constexpr int TOPK = 8;
+constexpr int INS_CAP = 32;
+struct TopCache {
+  Best top[TOPK];
+  Best bound;
+  Best best;          // max(top[]), refreshed by topk_refresh()
+  Best ins[INS_CAP];  // outsiders that beat the bound in the current drain
+  uint32_t n_ins;
+};
+
+// Sweep: exact TOPK + 1 best slots of the partition under (count, pair_prio).  All threads; counts and the keys of the
+// non-zero slots are fetched once (two round trips), then TOPK + 1 block-wide arg-max rounds run on registers.
+#ifndef YT_SIMT_EMU
+#define YT_NOINLINE __noinline__
+#else
+#define YT_NOINLINE __attribute__((noinline))
+#endif
+__device__ YT_NOINLINE void sweep_topk(const LoopArgs &a, uint64_t pbase, uint32_t R, Best *s_warp, TopCache *tc) {
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  unsigned long long cmax = 0;
-  for (uint32_t i0 = threadIdx.x; i0 < R; i0 += blockDim.x * SWEEP_UNROLL) {
-    unsigned long long c[SWEEP_UNROLL];
+  if (threadIdx.x < TOPK) tc->top[threadIdx.x] = Best{0, 0, ~0ull};
+  if (threadIdx.x == 0) { tc->bound = Best{0, 0, ~0ull}; tc->best = Best{0, 0, ~0ull}; tc->n_ins = 0; }
+  // A thread owns the slots threadIdx.x + u * blockDim.x.  Up to SWEEP_UNROLL slots per thread (partitions of the
+  // RESIDENT regime: 8192 slots) live in registers for all rounds; larger partitions (STREAMING regime, where a merge
+  // costs hundreds of microseconds anyway) re-read their slots from L2 every round.
+  const bool small = R <= blockDim.x * SWEEP_UNROLL;
+  unsigned long long c[SWEEP_UNROLL], pr[SWEEP_UNROLL];
+  if (small) {
 #pragma unroll
     for (int u = 0; u < SWEEP_UNROLL; u++) {
-      const uint32_t i = i0 + (uint32_t)u * blockDim.x;
+      const uint32_t i = threadIdx.x + (uint32_t)u * blockDim.x;
       c[u] = i < R ? __ldcg(a.tab.cnts + pbase + i) : 0ull;
     }
 #pragma unroll
-    for (int u = 0; u < SWEEP_UNROLL; u++) cmax = c[u] > cmax ? c[u] : cmax;
-  }
-  for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, cmax, o); cmax = v > cmax ? v : cmax; }
-  if (lane == 0) s_warp[wid].c = cmax;
-  __syncthreads();
-  {
-    unsigned long long v = lane < nwarp ? s_warp[lane].c : 0ull;
-    for (int o = 16; o > 0; o >>= 1) { const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
-    cmax = v;  // every warp computes the block maximum
-  }
-  __syncthreads();
-  Best b{0, 0, 0};
-  if (cmax) {
-    for (uint32_t i = threadIdx.x; i < R; i += blockDim.x) {   // counts again (L2 hits); keys of the maxima only
-      if (__ldcg(a.tab.cnts + pbase + i) != cmax) continue;
-      const unsigned long long k = __ldcg(a.tab.keys + pbase + i);
-      Best cand{cmax, pair_prio((uint32_t)(k >> 32), (uint32_t)k), pbase + i};
-      if (better(cand, b)) b = cand;
+    for (int u = 0; u < SWEEP_UNROLL; u++) {
+      pr[u] = 0;
+      if (c[u]) {
+        const unsigned long long k = __ldcg(a.tab.keys + pbase + threadIdx.x + (uint64_t)u * blockDim.x);
+        pr[u] = pair_prio((uint32_t)(k >> 32), (uint32_t)k);
+      }
     }
   }
-  b = warp_best(b);
-  if (lane == 0) s_warp[wid] = b;
+  Best last{~0ull, ~0ull, ~0ull};  // everything compares below this; later: the previous round's winner
+  for (int round = 0; round <= TOPK; round++) {
+    Best b{0, 0, ~0ull};
+    if (small) {
+#pragma unroll
+      for (int u = 0; u < SWEEP_UNROLL; u++) {
+        const Best cand{c[u], pr[u], pbase + threadIdx.x + (uint64_t)u * blockDim.x};
+        if (c[u] && better(last, cand) && better(cand, b)) b = cand;   // not yet taken: strictly below the last winner
+      }
+    } else {
+      for (uint32_t i0 = threadIdx.x; i0 < R; i0 += blockDim.x * SWEEP_UNROLL) {
+        unsigned long long cc[SWEEP_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SWEEP_UNROLL; u++) {
+          const uint32_t i = i0 + (uint32_t)u * blockDim.x;
+          cc[u] = i < R ? __ldcg(a.tab.cnts + pbase + i) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < SWEEP_UNROLL; u++) {
+          if (cc[u] == 0 || cc[u] < b.c || cc[u] > last.c) continue;
+          const uint64_t i = pbase + i0 + (uint64_t)u * blockDim.x;
+          const unsigned long long k = __ldcg(a.tab.keys + i);
+          const Best cand{cc[u], pair_prio((uint32_t)(k >> 32), (uint32_t)k), i};
+          if (better(last, cand) && better(cand, b)) b = cand;
+        }
+      }
+    }
+    b = warp_best(b);
+    if (lane == 0) s_warp[wid] = b;
+    __syncthreads();
+    Best v = lane < nwarp ? s_warp[lane] : Best{0, 0, ~0ull};
+    v = warp_best(v);   // every warp reduces the block's candidates
+    __syncthreads();
+    if (v.c == 0) break;                     // nothing left (block-uniform)
+    if (threadIdx.x == 0) { if (round < TOPK) tc->top[round] = v; else tc->bound = v; }
+    last = v;
+  }
   __syncthreads();
-  if (wid == 0) {
-    Best v = lane < nwarp ? s_warp[lane] : Best{0, 0, 0};
-    v = warp_best(v);
-    if (lane == 0) *s_out = v;
+  if (threadIdx.x == 0) {
+    Best m = tc->top[0];
+    for (int k = 1; k < TOPK; k++) if (better(tc->top[k], m)) m = tc->top[k];
+    tc->best = m;
   }
   __syncthreads();
 }
 
 __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   __shared__ Best s_warp[32];
-  __shared__ Best s_best, s_cb;      // the elected pair of this iteration / the cached best of this block's partition
+  __shared__ Best s_best;            // the elected pair of this iteration
+  __shared__ TopCache s_tc;          // the cached arg-max of this block's partition
   __shared__ unsigned long long s_dead;
   __shared__ uint32_t s_defer_n, s_direct, s_out_n, s_occ, s_xf, s_bflags, s_sweep, s_povf, s_scan[33];
   __shared__ unsigned long long s_tpre;
@@ -686,7 +790,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   }
   unsigned long long my_dead = 0;    // token slots of this block tombstoned in this launch (thread 0 keeps the sum)
   uint32_t n_sweeps = 0;             // sweeps of this block after a drain (thread 0; diagnostic)
-  sweep_partition(a, pbase, R, s_warp, &s_cb);   // the cached arg-max starts exact (has the block barriers)
+  sweep_topk(a, pbase, R, s_warp, &s_tc);   // the cached arg-max starts exact (has the block barriers)
 
   for (uint32_t it = 0; it <= a.max_iters; ++it) {
     const uint32_t n_done = n_done0 + it;
@@ -695,7 +799,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     // ---------------- publish this block's best (two self-stamped words) and poll everybody's: barrier + winner
     // reduction in one round trip.  flags: 1 = this partition is over the load limit, 2 = it ran full (update lost).
     if (threadIdx.x == 0) {
-      const Best cb = s_cb;
+      const Best cb = s_tc.best;
       uint32_t fl = (s_occ > a.part_limit ? 1u : 0u) | (s_povf ? 2u : 0u);
       uint32_t x = 0, y = 0;
       if (cb.c) {  // (x, y) from the 64-bit priority word
@@ -783,14 +887,20 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       a.ctl->n_done = n_done + 1;
     }
     const bool i_own = (uint32_t)win.slot == blockIdx.x;
-    // every occurrence of (x,y) is merged below and no deltas are emitted for it: its owner clears the count
-    if (i_own && threadIdx.x == 0) a.tab.cnts[s_cb.slot] = 0;
+    // every occurrence of (x,y) is merged below and no deltas are emitted for it: its owner clears the count (in the
+    // table and in the cache; the cache decides after the drain whether its other members still beat the bound)
+    if (i_own && threadIdx.x == 0) {
+      a.tab.cnts[s_tc.best.slot] = 0;
+      for (int k = 0; k < TOPK; k++)
+        if (s_tc.top[k].slot == s_tc.best.slot) s_tc.top[k].c = 0;
+    }
     const unsigned long long tw1 = dbgt && lane == 0 ? gtimer() : 0;
     // ---------------- apply x y -> z: count changes go to this block's segment of round + 1 (on every rank)
     const uint32_t nround = round + 1;
     XqOut xo;
     xo.off = xq_seg_off(a.xq, nround & 1u, a.xq.me, blockIdx.x);
     xo.s_n = &s_out_n;
+    xo.stamp = nround % XQ_STAMP_MOD;
     unsigned long long dead = 0;
     if (a.resident) {
       if (rw1 > rw0) dead = process_tile(stok, soff, rw1 - rw0, soff[rw1 - rw0], s_claim,
@@ -945,21 +1055,18 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       const uint32_t n = s_out_n;
       uint32_t word = n > a.xq.seg_cap ? (a.xq.seg_cap | XQ_CNT_OVF) : n;
       if (my_dead * 4 > my_slots && my_slots > a.dead_min_slots) word |= XQ_CNT_COMPACT;
-      fence_scope(sys);   // this block's entries, as observed through the barrier above, before the stamped word
+      // no fence: the entries carry their own stamps, the count word may overtake them
       const unsigned long long cw = ((unsigned long long)nround << 32) | word;
 #pragma unroll
       for (int d = 0; d < XQ_MAX_WORLD; d++)
-        if ((uint32_t)d < a.xq.world) st_release(&xq_hdr(a.xq, (uint32_t)d, nround & 1u, a.xq.me)->counts[blockIdx.x], cw, sys);
+        if ((uint32_t)d < a.xq.world) st_relaxed_any(&xq_hdr(a.xq, (uint32_t)d, nround & 1u, a.xq.me)->counts[blockIdx.x], cw, sys);
       s_xf = 0; s_bflags = 0; s_sweep = 0;   // accumulators of the phases below
       if (dbgt) atomicMax(&a.ctl->blk[it & 1][0], gtimer() - tw1);
     }
     if (gtid == 0) tq2 = gtimer();
     round = nround;
-    // the owner of the consumed pair sweeps its partition while the others finish their apply phase (the sweep sees
-    // the table BEFORE this round's changes; they are folded in below like everybody's)
-    __syncthreads();
-    if (i_own) sweep_partition(a, pbase, R, s_warp, &s_cb);
     // ---------------- drain: the count changes of this merge, from every block of every GPU
+    __syncthreads();
     const unsigned long long tw2 = dbgt && lane == 0 ? gtimer() : 0;
     xq_poll_counts(a, round, false, s_pref, &s_xf);
     if (gtid == 0) tq2b = gtimer();
@@ -970,33 +1077,52 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     if (tch.dropped) s_povf = 1;                      // this partition ran full: an update was lost
     __syncthreads();  // the partition is up to date (the drain's atomics went to L2 before the barrier)
     {
-      // ---- cached arg-max: only touched slots can have changed.  Final counts are re-read (a slot may have
-      // received several entries); a lowered best invalidates the cache.
-      const Best cb = s_cb;
-      Best cand{0, 0, 0};
-      bool lowered = false;
+      // ---- cached arg-max: only touched slots can have changed.  Final counts are re-read (a slot may have received
+      // several entries).  Members of the cache take their new count; an outsider that now beats the bound is queued.
       const uint32_t nt = tch.n < (uint32_t)DRAIN_KEEP ? tch.n : (uint32_t)DRAIN_KEEP;
 #pragma unroll
       for (int q = 0; q < DRAIN_KEEP; q++) {
         if ((uint32_t)q >= nt || tch.slot[q] == ~0ull) continue;
         const unsigned long long c = __ldcg(a.tab.cnts + tch.slot[q]);
-        if (tch.slot[q] == cb.slot && cb.c && c < cb.c) lowered = true;
-        if (c) {
-          Best v{c, pair_prio((uint32_t)(tch.key[q] >> 32), (uint32_t)tch.key[q]), tch.slot[q]};
-          if (better(v, cand)) cand = v;
+        bool member = false;
+#pragma unroll
+        for (int k = 0; k < TOPK; k++)
+          if (s_tc.top[k].slot == tch.slot[q]) { s_tc.top[k].c = c; member = true; }   // same final value from every writer
+        if (member) continue;
+        const Best v{c, pair_prio((uint32_t)(tch.key[q] >> 32), (uint32_t)tch.key[q]), tch.slot[q]};
+        if (c && better(v, s_tc.bound)) {
+          const uint32_t at = atomicAdd(&s_tc.n_ins, 1u);
+          if (at < (uint32_t)INS_CAP) s_tc.ins[at] = v; else s_sweep = 1;
         }
       }
-      if (lowered) s_sweep = 1;
-      cand = warp_best(cand);
-      if (lane == 0) s_warp[wid] = cand;
+      __syncthreads();
+      if (threadIdx.x == 0 && !s_sweep) {   // a handful of items at most: sequential
+        const uint32_t n = s_tc.n_ins;
+        for (uint32_t j = 0; j < n; j++) {
+          const Best v = s_tc.ins[j];
+          int worst = 0;
+          bool dup = false;
+          for (int k = 0; k < TOPK; k++) {
+            if (s_tc.top[k].slot == v.slot) dup = true;             // queued twice (several entries hit the slot)
+            if (better(s_tc.top[worst], s_tc.top[k])) worst = k;
+          }
+          if (dup) continue;
+          if (better(v, s_tc.top[worst])) {                          // enters; the evicted member is an outsider now
+            const Best ev = s_tc.top[worst];
+            s_tc.top[worst] = v;
+            if (ev.c && better(ev, s_tc.bound)) s_tc.bound = ev;
+          } else if (better(v, s_tc.bound)) s_tc.bound = v;          // stays outside: the bound must cover it
+        }
+        s_tc.n_ins = 0;
+        Best m = s_tc.top[0];
+        for (int k = 1; k < TOPK; k++) if (better(s_tc.top[k], m)) m = s_tc.top[k];
+        s_tc.best = m;
+        if (s_tc.bound.c && better(s_tc.bound, m)) s_sweep = 1;     // the cache cannot certify its best any more
+      }
       __syncthreads();
       if (s_sweep) {
-        sweep_partition(a, pbase, R, s_warp, &s_cb);
+        sweep_topk(a, pbase, R, s_warp, &s_tc);
         if (threadIdx.x == 0) { s_sweep = 0; n_sweeps++; }
-      } else if (wid == 0) {
-        Best v = lane < nwarp ? s_warp[lane] : Best{0, 0, 0};
-        v = warp_best(v);
-        if (lane == 0 && better(v, cb)) s_cb = v;
       }
     }
     __syncthreads();
@@ -1058,7 +1184,7 @@ __global__ void __launch_bounds__(256) xq_publish_table_kernel(LoopArgs a, uint3
     if (has) {
       const uint64_t idx = (uint64_t)done + before + __popc(m & ((1u << lane) - 1u));
       if (idx >= lo && idx < hi) {
-        const uint4 e = make_uint4((uint32_t)k, (uint32_t)(k >> 32), (uint32_t)c, (uint32_t)(c >> 32));
+        const uint4 e = xq_pack(round % XQ_STAMP_MOD, k, (long long)c);
 #pragma unroll
         for (int d = 0; d < XQ_MAX_WORLD; d++)
           if ((uint32_t)d < a.xq.world && (uint32_t)d != a.xq.me) reinterpret_cast<uint4 *>(a.xq.base[d] + off)[idx - lo] = e;
@@ -1072,11 +1198,10 @@ __global__ void __launch_bounds__(256) xq_publish_table_kernel(LoopArgs a, uint3
     uint32_t word = total > lo ? (uint32_t)(total - lo < (uint64_t)a.xq.seg_cap ? total - lo : (uint64_t)a.xq.seg_cap) : 0u;
     if (total > hi) word |= XQ_CNT_MORE;
     if (__ldcg(local_overflow)) word |= XQ_CNT_OVF;
-    fence_scope(true);
     const unsigned long long cw = ((unsigned long long)round << 32) | word;
 #pragma unroll
     for (int d = 0; d < XQ_MAX_WORLD; d++)
-      if ((uint32_t)d < a.xq.world) st_release(&xq_hdr(a.xq, (uint32_t)d, round & 1u, a.xq.me)->counts[blockIdx.x], cw, true);
+      if ((uint32_t)d < a.xq.world) st_relaxed_any(&xq_hdr(a.xq, (uint32_t)d, round & 1u, a.xq.me)->counts[blockIdx.x], cw, true);
   }
 }
 // xq_absorb_kernel: block b waits for round `round` of every block of every rank and adds the peers' pairs it owns

@@ -647,7 +647,8 @@ int xq_alloc(yttm_ctx *c, uint32_t me, uint32_t world) {
   c->xq_bytes = 2ull * world * c->xq_per_sender;
   YT_CUDA(c, c->xq_buf.reserve(c->xq_bytes));
   YT_CUDA(c, c->xq_arrive.reserve(64));
-  // only the headers need clearing (sequence numbers start at 0, counts are rewritten every round)
+  // entries start as all-ones (a stamp no round uses), count words as round 0
+  YT_CUDA(c, cudaMemsetAsync(c->xq_buf.p, 0xff, c->xq_bytes, c->stream));
   for (uint32_t k = 0; k < 2 * world; k++)
     YT_CUDA(c, cudaMemsetAsync(c->xq_buf.as<unsigned char>() + k * c->xq_per_sender, 0, sizeof(XqHdr), c->stream));
   YT_CUDA(c, cudaMemsetAsync(c->xq_arrive.p, 0, 64, c->stream));
