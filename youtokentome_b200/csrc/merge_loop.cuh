@@ -197,6 +197,7 @@ struct LoopArgs {
   uint32_t part_limit;            // leave for a rebuild when a partition holds more keys than this
   uint32_t dead_min_slots;        // a block wishes a compaction only if it owns more token slots than this
   unsigned long long spin_limit_ns;  // a peer that stays silent this long traps the kernel (never hang the box)
+  unsigned long long *dbg_blk;       // YTTM_DBG & 16: 8 accumulators per block (ns): poll bests, apply, wait counts (+ owner sweep), drain, cache, sweeps
 };
 
 struct Best { unsigned long long c, prio, slot; };
@@ -548,7 +549,7 @@ __device__ __forceinline__ void xq_poll_counts(const LoopArgs &a, uint32_t round
 }
 
 // Up to DRAIN_KEEP table slots a thread has updated in one drain (for the cached arg-max); more: the block sweeps.
-constexpr int DRAIN_KEEP = 2;
+constexpr int DRAIN_KEEP = 4;
 struct Touched { uint64_t slot[DRAIN_KEEP]; unsigned long long key[DRAIN_KEEP]; uint32_t n, dropped; };
 
 // Drain: s_pref holds the entry counts (xq_poll_counts); every entry whose key belongs to partition blockIdx.x is
@@ -633,101 +634,53 @@ __device__ __forceinline__ void xq_drain(const LoopArgs &a, uint32_t round, uint
   if (added) atomicAdd(s_occ_add, added);
 }
 
-// The cached arg-max of a partition: its TOPK best slots (exact counts) and a bound — the best pair that is NOT among
-// them.  Invariant: every slot outside top[] compares <= bound.  The partition's best is max(top[]) as long as that
-// is not below the bound; only then the partition is swept again.  (The reference keeps a lazy priority queue for the
-// same reason, bpe.cpp:149-314: most merges touch few pairs.)
-constexpr int TOPK = 8;
-constexpr int INS_CAP = 32;
-struct TopCache {
-  Best top[TOPK];
-  Best bound;
-  Best best;          // max(top[]), refreshed by topk_refresh()
-  Best ins[INS_CAP];  // outsiders that beat the bound in the current drain
-  uint32_t n_ins;
-};
-
-// Sweep: exact TOPK + 1 best slots of the partition under (count, pair_prio).  All threads; counts and the keys of the
-// non-zero slots are fetched once (two round trips), then TOPK + 1 block-wide arg-max rounds run on registers.
-#ifndef YT_SIMT_EMU
-#define YT_NOINLINE __noinline__
-#else
-#define YT_NOINLINE __attribute__((noinline))
-#endif
-__device__ YT_NOINLINE void sweep_topk(const LoopArgs &a, uint64_t pbase, uint32_t R, Best *s_warp, TopCache *tc) {
+// Exact arg-max of this block's partition (all threads; two passes: the largest count first, keys only for the
+// slots that hold it).  Result in *s_out (shared); s_warp: 32 Best of scratch.
+__device__ __forceinline__ void sweep_partition(const LoopArgs &a, uint64_t pbase, uint32_t R, Best *s_warp, Best *s_out) {
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  if (threadIdx.x < TOPK) tc->top[threadIdx.x] = Best{0, 0, ~0ull};
-  if (threadIdx.x == 0) { tc->bound = Best{0, 0, ~0ull}; tc->best = Best{0, 0, ~0ull}; tc->n_ins = 0; }
-  // A thread owns the slots threadIdx.x + u * blockDim.x.  Up to SWEEP_UNROLL slots per thread (partitions of the
-  // RESIDENT regime: 8192 slots) live in registers for all rounds; larger partitions (STREAMING regime, where a merge
-  // costs hundreds of microseconds anyway) re-read their slots from L2 every round.
-  const bool small = R <= blockDim.x * SWEEP_UNROLL;
-  unsigned long long c[SWEEP_UNROLL], pr[SWEEP_UNROLL];
-  if (small) {
+  unsigned long long cmax = 0;
+  for (uint32_t i0 = threadIdx.x; i0 < R; i0 += blockDim.x * SWEEP_UNROLL) {
+    unsigned long long c[SWEEP_UNROLL];
 #pragma unroll
     for (int u = 0; u < SWEEP_UNROLL; u++) {
-      const uint32_t i = threadIdx.x + (uint32_t)u * blockDim.x;
+      const uint32_t i = i0 + (uint32_t)u * blockDim.x;
       c[u] = i < R ? __ldcg(a.tab.cnts + pbase + i) : 0ull;
     }
 #pragma unroll
-    for (int u = 0; u < SWEEP_UNROLL; u++) {
-      pr[u] = 0;
-      if (c[u]) {
-        const unsigned long long k = __ldcg(a.tab.keys + pbase + threadIdx.x + (uint64_t)u * blockDim.x);
-        pr[u] = pair_prio((uint32_t)(k >> 32), (uint32_t)k);
-      }
-    }
+    for (int u = 0; u < SWEEP_UNROLL; u++) cmax = c[u] > cmax ? c[u] : cmax;
   }
-  Best last{~0ull, ~0ull, ~0ull};  // everything compares below this; later: the previous round's winner
-  for (int round = 0; round <= TOPK; round++) {
-    Best b{0, 0, ~0ull};
-    if (small) {
-#pragma unroll
-      for (int u = 0; u < SWEEP_UNROLL; u++) {
-        const Best cand{c[u], pr[u], pbase + threadIdx.x + (uint64_t)u * blockDim.x};
-        if (c[u] && better(last, cand) && better(cand, b)) b = cand;   // not yet taken: strictly below the last winner
-      }
-    } else {
-      for (uint32_t i0 = threadIdx.x; i0 < R; i0 += blockDim.x * SWEEP_UNROLL) {
-        unsigned long long cc[SWEEP_UNROLL];
-#pragma unroll
-        for (int u = 0; u < SWEEP_UNROLL; u++) {
-          const uint32_t i = i0 + (uint32_t)u * blockDim.x;
-          cc[u] = i < R ? __ldcg(a.tab.cnts + pbase + i) : 0ull;
-        }
-#pragma unroll
-        for (int u = 0; u < SWEEP_UNROLL; u++) {
-          if (cc[u] == 0 || cc[u] < b.c || cc[u] > last.c) continue;
-          const uint64_t i = pbase + i0 + (uint64_t)u * blockDim.x;
-          const unsigned long long k = __ldcg(a.tab.keys + i);
-          const Best cand{cc[u], pair_prio((uint32_t)(k >> 32), (uint32_t)k), i};
-          if (better(last, cand) && better(cand, b)) b = cand;
-        }
-      }
-    }
-    b = warp_best(b);
-    if (lane == 0) s_warp[wid] = b;
-    __syncthreads();
-    Best v = lane < nwarp ? s_warp[lane] : Best{0, 0, ~0ull};
-    v = warp_best(v);   // every warp reduces the block's candidates
-    __syncthreads();
-    if (v.c == 0) break;                     // nothing left (block-uniform)
-    if (threadIdx.x == 0) { if (round < TOPK) tc->top[round] = v; else tc->bound = v; }
-    last = v;
+  for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, cmax, o); cmax = v > cmax ? v : cmax; }
+  if (lane == 0) s_warp[wid].c = cmax;
+  __syncthreads();
+  {
+    unsigned long long v = lane < nwarp ? s_warp[lane].c : 0ull;
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
+    cmax = v;  // every warp computes the block maximum
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    Best m = tc->top[0];
-    for (int k = 1; k < TOPK; k++) if (better(tc->top[k], m)) m = tc->top[k];
-    tc->best = m;
+  Best b{0, 0, 0};
+  if (cmax) {
+    for (uint32_t i = threadIdx.x; i < R; i += blockDim.x) {   // counts again (L2 hits); keys of the maxima only
+      if (__ldcg(a.tab.cnts + pbase + i) != cmax) continue;
+      const unsigned long long k = __ldcg(a.tab.keys + pbase + i);
+      Best cand{cmax, pair_prio((uint32_t)(k >> 32), (uint32_t)k), pbase + i};
+      if (better(cand, b)) b = cand;
+    }
+  }
+  b = warp_best(b);
+  if (lane == 0) s_warp[wid] = b;
+  __syncthreads();
+  if (wid == 0) {
+    Best v = lane < nwarp ? s_warp[lane] : Best{0, 0, 0};
+    v = warp_best(v);
+    if (lane == 0) *s_out = v;
   }
   __syncthreads();
 }
 
 __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   __shared__ Best s_warp[32];
-  __shared__ Best s_best;            // the elected pair of this iteration
-  __shared__ TopCache s_tc;          // the cached arg-max of this block's partition
+  __shared__ Best s_best, s_cb;      // the elected pair of this iteration / the cached best of this block's partition
   __shared__ unsigned long long s_dead;
   __shared__ uint32_t s_defer_n, s_direct, s_out_n, s_occ, s_xf, s_bflags, s_sweep, s_povf, s_scan[33];
   __shared__ unsigned long long s_tpre;
@@ -761,6 +714,8 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   const uint32_t n_done0 = a.ctl->n_done;
   uint32_t round = a.ctl->xq_round;                   // exchange rounds completed so far (same on every rank)
   unsigned long long tacc0 = 0, tacc2 = 0, tacc3 = 0, tacc4 = 0, tacc5 = 0, tacc7 = 0, titers = 0;  // phase timers (block 0, thread 0)
+  const bool dbgb = (a.dbg & 16u) != 0 && threadIdx.x == 0;   // per-block phase accumulators (thread 0 of every block)
+  unsigned long long bacc[6] = {0, 0, 0, 0, 0, 0}, bt = 0;
 
   // occupancy of this block's partition (keys never leave the table between rebuilds)
   {
@@ -790,16 +745,17 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   }
   unsigned long long my_dead = 0;    // token slots of this block tombstoned in this launch (thread 0 keeps the sum)
   uint32_t n_sweeps = 0;             // sweeps of this block after a drain (thread 0; diagnostic)
-  sweep_topk(a, pbase, R, s_warp, &s_tc);   // the cached arg-max starts exact (has the block barriers)
+  sweep_partition(a, pbase, R, s_warp, &s_cb);   // the cached arg-max starts exact (has the block barriers)
 
   for (uint32_t it = 0; it <= a.max_iters; ++it) {
     const uint32_t n_done = n_done0 + it;
     const uint32_t stamp = (it % 65535u) + 1u;         // never 0: the array is cleared before the launch
     unsigned long long tq0 = gtid == 0 ? gtimer() : 0, tq1 = 0, tq2 = 0, tq2b = 0, tq3 = 0;
+    if (dbgb) bt = gtimer();
     // ---------------- publish this block's best (two self-stamped words) and poll everybody's: barrier + winner
     // reduction in one round trip.  flags: 1 = this partition is over the load limit, 2 = it ran full (update lost).
     if (threadIdx.x == 0) {
-      const Best cb = s_tc.best;
+      const Best cb = s_cb;
       uint32_t fl = (s_occ > a.part_limit ? 1u : 0u) | (s_povf ? 2u : 0u);
       uint32_t x = 0, y = 0;
       if (cb.c) {  // (x, y) from the 64-bit priority word
@@ -856,6 +812,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       __syncthreads();
     }
     if (gtid == 0) tq1 = gtimer();
+    if (dbgb) { const unsigned long long t = gtimer(); bacc[0] += t - bt; bt = t; }
     const Best win = s_best;             // .prio = prio45, .slot = owner block
     const uint32_t bflags = s_bflags, xf = s_xf;
     // ---------------- uniform exit checks (every block of every rank evaluates the same values)
@@ -887,13 +844,8 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       a.ctl->n_done = n_done + 1;
     }
     const bool i_own = (uint32_t)win.slot == blockIdx.x;
-    // every occurrence of (x,y) is merged below and no deltas are emitted for it: its owner clears the count (in the
-    // table and in the cache; the cache decides after the drain whether its other members still beat the bound)
-    if (i_own && threadIdx.x == 0) {
-      a.tab.cnts[s_tc.best.slot] = 0;
-      for (int k = 0; k < TOPK; k++)
-        if (s_tc.top[k].slot == s_tc.best.slot) s_tc.top[k].c = 0;
-    }
+    // every occurrence of (x,y) is merged below and no deltas are emitted for it: its owner clears the count
+    if (i_own && threadIdx.x == 0) a.tab.cnts[s_cb.slot] = 0;
     const unsigned long long tw1 = dbgt && lane == 0 ? gtimer() : 0;
     // ---------------- apply x y -> z: count changes go to this block's segment of round + 1 (on every rank)
     const uint32_t nround = round + 1;
@@ -1064,68 +1016,57 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       if (dbgt) atomicMax(&a.ctl->blk[it & 1][0], gtimer() - tw1);
     }
     if (gtid == 0) tq2 = gtimer();
+    if (dbgb) { const unsigned long long t = gtimer(); bacc[1] += t - bt; bt = t; }
     round = nround;
-    // ---------------- drain: the count changes of this merge, from every block of every GPU
+    // the owner of the consumed pair sweeps its partition while the others finish their apply phase (the sweep sees
+    // the table BEFORE this round's changes; they are folded in below like everybody's)
     __syncthreads();
+    if (i_own) sweep_partition(a, pbase, R, s_warp, &s_cb);
+    // ---------------- drain: the count changes of this merge, from every block of every GPU
     const unsigned long long tw2 = dbgt && lane == 0 ? gtimer() : 0;
     xq_poll_counts(a, round, false, s_pref, &s_xf);
     if (gtid == 0) tq2b = gtimer();
+    if (dbgb) { const unsigned long long t = gtimer(); bacc[2] += t - bt; bt = t; }
     Touched tch;
     tch.n = 0; tch.dropped = 0;
     xq_drain(a, round, s_pref, s_scan, &s_occ, tch);
     if (tch.n > (uint32_t)DRAIN_KEEP) s_sweep = 1;   // (benign race: every writer stores 1)
     if (tch.dropped) s_povf = 1;                      // this partition ran full: an update was lost
     __syncthreads();  // the partition is up to date (the drain's atomics went to L2 before the barrier)
+    if (dbgb) { const unsigned long long t = gtimer(); bacc[3] += t - bt; bt = t; }
     {
-      // ---- cached arg-max: only touched slots can have changed.  Final counts are re-read (a slot may have received
-      // several entries).  Members of the cache take their new count; an outsider that now beats the bound is queued.
+      // ---- cached arg-max: only touched slots can have changed.  Final counts are re-read (a slot may have
+      // received several entries); a lowered best invalidates the cache.
+      const Best cb = s_cb;
+      Best cand{0, 0, 0};
+      bool lowered = false;
       const uint32_t nt = tch.n < (uint32_t)DRAIN_KEEP ? tch.n : (uint32_t)DRAIN_KEEP;
 #pragma unroll
       for (int q = 0; q < DRAIN_KEEP; q++) {
         if ((uint32_t)q >= nt || tch.slot[q] == ~0ull) continue;
         const unsigned long long c = __ldcg(a.tab.cnts + tch.slot[q]);
-        bool member = false;
-#pragma unroll
-        for (int k = 0; k < TOPK; k++)
-          if (s_tc.top[k].slot == tch.slot[q]) { s_tc.top[k].c = c; member = true; }   // same final value from every writer
-        if (member) continue;
-        const Best v{c, pair_prio((uint32_t)(tch.key[q] >> 32), (uint32_t)tch.key[q]), tch.slot[q]};
-        if (c && better(v, s_tc.bound)) {
-          const uint32_t at = atomicAdd(&s_tc.n_ins, 1u);
-          if (at < (uint32_t)INS_CAP) s_tc.ins[at] = v; else s_sweep = 1;
+        if (tch.slot[q] == cb.slot && cb.c && c < cb.c) lowered = true;
+        if (c) {
+          Best v{c, pair_prio((uint32_t)(tch.key[q] >> 32), (uint32_t)tch.key[q]), tch.slot[q]};
+          if (better(v, cand)) cand = v;
         }
       }
-      __syncthreads();
-      if (threadIdx.x == 0 && !s_sweep) {   // a handful of items at most: sequential
-        const uint32_t n = s_tc.n_ins;
-        for (uint32_t j = 0; j < n; j++) {
-          const Best v = s_tc.ins[j];
-          int worst = 0;
-          bool dup = false;
-          for (int k = 0; k < TOPK; k++) {
-            if (s_tc.top[k].slot == v.slot) dup = true;             // queued twice (several entries hit the slot)
-            if (better(s_tc.top[worst], s_tc.top[k])) worst = k;
-          }
-          if (dup) continue;
-          if (better(v, s_tc.top[worst])) {                          // enters; the evicted member is an outsider now
-            const Best ev = s_tc.top[worst];
-            s_tc.top[worst] = v;
-            if (ev.c && better(ev, s_tc.bound)) s_tc.bound = ev;
-          } else if (better(v, s_tc.bound)) s_tc.bound = v;          // stays outside: the bound must cover it
-        }
-        s_tc.n_ins = 0;
-        Best m = s_tc.top[0];
-        for (int k = 1; k < TOPK; k++) if (better(s_tc.top[k], m)) m = s_tc.top[k];
-        s_tc.best = m;
-        if (s_tc.bound.c && better(s_tc.bound, m)) s_sweep = 1;     // the cache cannot certify its best any more
-      }
+      if (lowered) s_sweep = 1;
+      cand = warp_best(cand);
+      if (lane == 0) s_warp[wid] = cand;
       __syncthreads();
       if (s_sweep) {
-        sweep_topk(a, pbase, R, s_warp, &s_tc);
+        sweep_partition(a, pbase, R, s_warp, &s_cb);
         if (threadIdx.x == 0) { s_sweep = 0; n_sweeps++; }
+        if (dbgb) bacc[5] += 1;
+      } else if (wid == 0) {
+        Best v = lane < nwarp ? s_warp[lane] : Best{0, 0, 0};
+        v = warp_best(v);
+        if (lane == 0 && better(v, cb)) s_cb = v;
       }
     }
     __syncthreads();
+    if (dbgb) { const unsigned long long t = gtimer(); bacc[4] += t - bt; bt = t; }
     if (dbgt && lane == 0) atomicMax(&s_tpre, gtimer() - tw2);
     if (gtid == 0) {
       tq3 = gtimer();
@@ -1143,6 +1084,8 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     }
   }
   if (threadIdx.x == 0 && n_sweeps) atomicAdd(&a.ctl->n_sweeps, (unsigned long long)n_sweeps);
+  if (dbgb && a.dbg_blk)
+    for (int k = 0; k < 6; k++) a.dbg_blk[8 * blockIdx.x + k] += bacc[k];
   if (gtid == 0) {
     a.ctl->xq_round = round;
     a.ctl->t_phase[0] += tacc0; a.ctl->t_phase[2] += tacc2; a.ctl->t_phase[3] += tacc3; a.ctl->t_phase[4] += tacc4;

@@ -17,6 +17,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -1466,6 +1467,12 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
     a.max_total = max_merges;
     a.max_iters = max_merges;
     a.part_limit = (uint32_t)(((uint64_t)c->p_rmask + 1) * pair_max_load_pct() / 100);  // rebuild above this partition load (default 1/2)
+    a.dbg_blk = nullptr;
+    if (a.dbg & 16u) {   // diagnostic: where do the blocks spend a merge?  (printed to stderr after the run)
+      if (!c->scratch_cnt.p || c->scratch_cnt.cap < (size_t)c->loop_blocks * 64) YT_CUDA(c, c->scratch_cnt.reserve((size_t)c->loop_blocks * 64));
+      if (c->loop_relaunches == 0) YT_CUDA(c, cudaMemsetAsync(c->scratch_cnt.p, 0, (size_t)c->loop_blocks * 64, c->stream));
+      a.dbg_blk = c->scratch_cnt.as<unsigned long long>();
+    }
     a.dead_min_slots = 4096;
     if (const char *e = std::getenv("YTTM_DEAD_MIN_SLOTS")) a.dead_min_slots = (uint32_t)std::max(0, std::atoi(e));
     YT_CUDA(c, cudaMemsetAsync(c->blockbest.p, 0, (size_t)c->loop_blocks * 2 * 8, c->stream));  // stamps restart at 1
@@ -1500,6 +1507,27 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
     YT_CUDA(c, cudaMemcpyAsync(ctl, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
   }
   ytc::timer_end(c, "merge_loop");
+  if (const char *e = std::getenv("YTTM_DBG")) {
+    if ((std::atoi(e) & 16) && h.iters) {
+      std::vector<unsigned long long> blk((size_t)c->loop_blocks * 8);
+      YT_CUDA(c, cudaMemcpyAsync(blk.data(), c->scratch_cnt.p, blk.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+      YT_CUDA(c, cudaStreamSynchronize(c->stream));
+      static const char *nm[] = {"poll_bests", "apply", "wait_counts+owner_sweep", "drain", "cache_update(+sweep)", "sweeps"};
+      const double it = (double)h.iters;
+      for (int k = 0; k < 6; k++) {
+        double mn = 1e30, mx = 0, sum = 0;
+        int imn = 0, imx = 0;
+        for (int b = 0; b < c->loop_blocks; b++) {
+          const double v = (double)blk[(size_t)b * 8 + k] / it * (k == 5 ? 1.0 : 1e-3);
+          sum += v;
+          if (v < mn) { mn = v; imn = b; }
+          if (v > mx) { mx = v; imx = b; }
+        }
+        std::fprintf(stderr, "YTTM_DBG16 %-24s per merge: mean %8.3f  min %8.3f (block %d)  max %8.3f (block %d)%s\n", nm[k],
+                     sum / c->loop_blocks, mn, imn, mx, imx, k == 5 ? "  [count]" : " us");
+      }
+    }
+  }
   for (int i = 0; i < 8; i++) c->loop_phase_ms[i] = (double)h.t_phase[i] * 1e-6;
   c->loop_iters = h.iters;
   c->loop_sweeps = h.n_sweeps;
