@@ -299,6 +299,7 @@ def train_leg(comm, device, kind, chunk_ids, vocab, coverage, tag, runs=None, ca
             "merge_loop_ms": r3(st["merge_loop_ms"]), "launches": int(st["launches"]), "U": uniq, "T": toks,
             "front_ms_rank0": {k: r3(v) for k, v in fm.items()},
             "phase_us": {k.replace("loop_", ""): r3(v) for k, v in st["phase_us_per_iter"].items()},
+            "host_ms_rank0": {k: r3(v) for k, v in st.get("host_ms", {}).items()},
             "model_sha1": sha, "gen_s": r3(gen_s)}, shard, model
 
 

@@ -688,8 +688,6 @@ constexpr unsigned long long DEDUP_EMPTY = ~0ull;
 constexpr uint32_t DEDUP_PROBES = 8;
 struct DedupArgs {
   unsigned long long *tab;     // (tag << 32) | representative work item ; DEDUP_EMPTY = free
-  uint4 *pre;                  // per slot: the first 16 bytes of the representative's word (zero padded)
-  uint32_t *plen;              // per slot: DEDUP_READY | its length, stored (release) after `pre`; 0xffffffff = not yet
   uint32_t mask;
   uint32_t *rep;               // per work item: its representative (itself if it is one)
   uint32_t *n_tok;             // per representative: number of ids of its encoding
@@ -698,7 +696,6 @@ struct DedupArgs {
   uint32_t weak_tag;           // tests only: all tags equal, so every probe ends in the byte compare
 };
 
-constexpr uint32_t DEDUP_READY = 0x40000000u;
 __global__ void __launch_bounds__(128) dedup_words_kernel(EncArgs a, uint64_t n_words, DedupArgs d) {
   const unsigned lane = threadIdx.x & 31;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -709,18 +706,8 @@ __global__ void __launch_bounds__(128) dedup_words_kernel(EncArgs a, uint64_t n_
     if (w < n_words) {
       const uint64_t p0 = a.word_pos[w], hi = a.offs[(uint64_t)a.word_sent[w] + 1] - o0;
       uint64_t q = p0, h = 0xcbf29ce484222325ull;
-      uint32_t l, pw[4] = {0, 0, 0, 0};   // the word's first 16 bytes, zero padded
-      while (q < hi && !space_at(a.bytes, q, hi, &l)) {
-        const uint32_t b = a.bytes[q];
-        const uint32_t i = (uint32_t)(q - p0);
-        if (i < 16) {
-#pragma unroll
-          for (int k = 0; k < 4; k++)
-            if ((i >> 2) == (uint32_t)k) pw[k] |= b << (8 * (i & 3));
-        }
-        h = (h ^ b) * 0x100000001b3ull;
-        q++;
-      }
+      uint32_t l;
+      while (q < hi && !space_at(a.bytes, q, hi, &l)) { h = (h ^ a.bytes[q]) * 0x100000001b3ull; q++; }
       const uint64_t len = q - p0;
       h = mix64(h);
       const uint32_t tag = d.weak_tag ? 7u : (uint32_t)(h >> 32);
@@ -731,33 +718,16 @@ __global__ void __launch_bounds__(128) dedup_words_kernel(EncArgs a, uint64_t n_
         unsigned long long cur = *(volatile unsigned long long *)(d.tab + idx);
         if (cur == DEDUP_EMPTY) {
           cur = atomicCAS(d.tab + idx, DEDUP_EMPTY, mine);
-          if (cur == DEDUP_EMPTY) {  // slot claimed: this occurrence represents the word; publish its prefix for the others
-            d.pre[idx] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
-            __threadfence();
-            *(volatile uint32_t *)(d.plen + idx) = DEDUP_READY | (uint32_t)(len < DEDUP_READY ? len : DEDUP_READY - 1);
-            break;
-          }
+          if (cur == DEDUP_EMPTY) break;  // slot claimed: this occurrence represents the word
         }
         if ((uint32_t)(cur >> 32) != tag) continue;
         const uint32_t w2 = (uint32_t)cur;  // written by find_words (the previous launch), like everything read below
-        // Fast compare against the prefix kept in the (L2-resident) table; while the claimer has not published it yet,
-        // or for the part of a word beyond 16 bytes, the bytes of the representative are read from the batch itself.
-        const uint32_t pl = *(volatile uint32_t *)(d.plen + idx);
-        uint64_t from = 0;
-        bool same = true;
-        if (pl != 0xffffffffu) {
-          __threadfence();  // the prefix was stored before the length word
-          if ((pl & (DEDUP_READY - 1)) != (uint32_t)(len < DEDUP_READY ? len : DEDUP_READY - 1)) continue;
-          const uint4 pv = __ldcg(d.pre + idx);
-          if (pv.x != pw[0] || pv.y != pw[1] || pv.z != pw[2] || pv.w != pw[3]) continue;
-          if (len <= 16) { r = w2; is_rep = false; break; }   // lengths and all bytes equal
-          from = 16;
-        }
         const uint64_t p2 = a.word_pos[w2], hi2 = a.offs[(uint64_t)a.word_sent[w2] + 1] - o0;
         // Equal iff the len bytes match AND the word at p2 ends right after them.  No space unit can start inside the
         // matching bytes: an ASCII space or a whole E2 96 81 there would be one in this word too, and an E2 96 81 that
         // starts inside and ends beyond leaves a continuation byte at p2 + len, which the end check rejects.
-        for (uint64_t i = from; i < len; i++)
+        bool same = true;
+        for (uint64_t i = 0; i < len; i++)
           if (p2 + i >= hi2 || a.bytes[p2 + i] != a.bytes[p0 + i]) { same = false; break; }
         if (same && p2 + len < hi2 && !space_at(a.bytes, p2 + len, hi2, &l)) same = false;  // the other word is longer
         if (same) { r = w2; is_rep = false; break; }
@@ -1045,23 +1015,19 @@ int enc_device(yttm_enc *enc, yttm_enc::Slot *e, const uint8_t *d_bytes, const u
     if (direct || dedup) YT_CUDA(c, e->dd_ntok.reserve(n_words * 4 + 16));
     a.n_tok = direct ? e->dd_ntok.as<uint32_t>() : nullptr;
     if (dedup) {
-      // table: 2 slots per occurrence up to 2^20 slots (28 B per slot with the word prefixes: 29 MB, L2-resident); beyond
-      // that it works as a cache
-      uint64_t tslots = std::max<uint64_t>(ytc::pow2ceil(std::min<uint64_t>(n_words, 1ull << 19) * 2), 1024);
+      // table: 2 slots per occurrence up to 2^21 slots (16 MB, L2-resident); beyond that it works as a cache
+      uint64_t tslots = std::max<uint64_t>(ytc::pow2ceil(std::min<uint64_t>(n_words, 1ull << 20) * 2), 1024);
       if (const char *env = std::getenv("YTTM_ENC_DEDUP_SLOTS")) tslots = ytc::pow2ceil((uint64_t)std::max(1, std::atoi(env)));  // tests: tiny tables
-      YT_CUDA(c, e->dd_tab.reserve(tslots * 28));
+      YT_CUDA(c, e->dd_tab.reserve(tslots * 8));
       YT_CUDA(c, e->dd_rep.reserve(n_words * 4 + 16));
       YT_CUDA(c, e->dd_list.reserve(n_words * 4 + 16));
       DedupArgs d;
       d.tab = e->dd_tab.as<unsigned long long>(); d.mask = (uint32_t)(tslots - 1);
-      d.pre = reinterpret_cast<uint4 *>(d.tab + tslots);
-      d.plen = reinterpret_cast<uint32_t *>(d.pre + tslots);
       d.rep = e->dd_rep.as<uint32_t>(); d.n_tok = e->dd_ntok.as<uint32_t>(); d.list = e->dd_list.as<uint32_t>();
       d.n_list = e->counter.as<unsigned long long>() + 2;  // zeroed with the other counters above
       d.weak_tag = std::getenv("YTTM_ENC_DEDUP_WEAKTAG") != nullptr;  // tests: tag collisions everywhere
       d_rep = d.rep;
       YT_CUDA(c, cudaMemsetAsync(d.tab, 0xff, tslots * 8, c->stream));
-      YT_CUDA(c, cudaMemsetAsync(d.plen, 0xff, tslots * 4, c->stream));
       ytc::timer_begin(c, "enc_dedup");
       dedup_words_kernel<<<(unsigned)blocks, 128, 0, c->stream>>>(a, n_words, d);
       ytc::timer_end(c, "enc_dedup");

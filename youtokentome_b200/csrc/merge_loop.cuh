@@ -638,16 +638,20 @@ __device__ __forceinline__ void xq_drain(const LoopArgs &a, uint32_t round, uint
 // slots that hold it).  Result in *s_out (shared); s_warp: 32 Best of scratch.
 __device__ __forceinline__ void sweep_partition(const LoopArgs &a, uint64_t pbase, uint32_t R, Best *s_warp, Best *s_out) {
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  // Partitions of the RESIDENT regime (R <= SWEEP_UNROLL x blockDim: 8192 slots) keep their counts in registers for
+  // both passes; larger ones re-read them, SWEEP_UNROLL loads in flight per thread.  (Round 2, measured: a second
+  // pass that re-read one slot per loop trip cost 8 dependent L2 round trips = 6.4 of the sweep's 9.5 us.)
+  const bool small = R <= blockDim.x * SWEEP_UNROLL;
+  unsigned long long c0[SWEEP_UNROLL];
   unsigned long long cmax = 0;
   for (uint32_t i0 = threadIdx.x; i0 < R; i0 += blockDim.x * SWEEP_UNROLL) {
-    unsigned long long c[SWEEP_UNROLL];
 #pragma unroll
     for (int u = 0; u < SWEEP_UNROLL; u++) {
       const uint32_t i = i0 + (uint32_t)u * blockDim.x;
-      c[u] = i < R ? __ldcg(a.tab.cnts + pbase + i) : 0ull;
+      c0[u] = i < R ? __ldcg(a.tab.cnts + pbase + i) : 0ull;
     }
 #pragma unroll
-    for (int u = 0; u < SWEEP_UNROLL; u++) cmax = c[u] > cmax ? c[u] : cmax;
+    for (int u = 0; u < SWEEP_UNROLL; u++) cmax = c0[u] > cmax ? c0[u] : cmax;
   }
   for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, cmax, o); cmax = v > cmax ? v : cmax; }
   if (lane == 0) s_warp[wid].c = cmax;
@@ -660,11 +664,24 @@ __device__ __forceinline__ void sweep_partition(const LoopArgs &a, uint64_t pbas
   __syncthreads();
   Best b{0, 0, 0};
   if (cmax) {
-    for (uint32_t i = threadIdx.x; i < R; i += blockDim.x) {   // counts again (L2 hits); keys of the maxima only
-      if (__ldcg(a.tab.cnts + pbase + i) != cmax) continue;
-      const unsigned long long k = __ldcg(a.tab.keys + pbase + i);
-      Best cand{cmax, pair_prio((uint32_t)(k >> 32), (uint32_t)k), pbase + i};
-      if (better(cand, b)) b = cand;
+    for (uint32_t i0 = threadIdx.x; i0 < R; i0 += blockDim.x * SWEEP_UNROLL) {   // keys of the maxima only, all in flight
+      unsigned long long c[SWEEP_UNROLL], k[SWEEP_UNROLL];
+#pragma unroll
+      for (int u = 0; u < SWEEP_UNROLL; u++) {
+        const uint32_t i = i0 + (uint32_t)u * blockDim.x;
+        c[u] = small ? c0[u] : (i < R ? __ldcg(a.tab.cnts + pbase + i) : 0ull);
+      }
+#pragma unroll
+      for (int u = 0; u < SWEEP_UNROLL; u++) {
+        const uint32_t i = i0 + (uint32_t)u * blockDim.x;
+        k[u] = c[u] == cmax ? __ldcg(a.tab.keys + pbase + i) : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < SWEEP_UNROLL; u++) {
+        if (c[u] != cmax) continue;
+        const Best cand{cmax, pair_prio((uint32_t)(k[u] >> 32), (uint32_t)k[u]), pbase + i0 + (uint64_t)u * blockDim.x};
+        if (better(cand, b)) b = cand;
+      }
     }
   }
   b = warp_best(b);

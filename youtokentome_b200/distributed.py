@@ -224,6 +224,13 @@ def train_distributed(data, model_path, vocab_size, coverage=1.0, pad_id=0, unk_
     if not comm.agree(ok):
         raise ValueError(err or "train_distributed: another rank failed to create its CUDA context")
     keep = []  # received tensors stay alive until the import has copied them
+    import time
+    walls, t_last = {}, [time.perf_counter()]
+
+    def lap(name):   # host wall clock between the steps of the protocol (stats_out["host_ms"])
+        now = time.perf_counter()
+        walls[name] = walls.get(name, 0.0) + (now - t_last[0]) * 1e3
+        t_last[0] = now
 
     def step(fn):
         """run one local phase; every rank learns whether all of them succeeded before the next collective"""
@@ -242,9 +249,11 @@ def train_distributed(data, model_path, vocab_size, coverage=1.0, pad_id=0, unk_
         step(lambda: L.yttm_train_dist_init(ctx, rank, world, handle))
         handles = comm.all_gather_bytes(handle.raw)
         step(lambda: L.yttm_train_dist_connect(ctx, handles))
+        lap("ctx+exchange_buffer")
         dl, nd = C.c_uint64(0), C.c_uint64(0)
         step(lambda: L.yttm_train_load_corpus(ctx, C.cast(C.c_char_p(shard), C.c_void_p), len(shard), 0) or
              L.yttm_train_char_hist(ctx, C.byref(dl), C.byref(nd)))
+        lap("load_corpus+char_hist")
         # the one collective of the byte passes: sum the dense code point histogram in place
         dptr, n64 = C.c_void_p(), C.c_uint64(0)
         step(lambda: L.yttm_train_char_hist_devptr(ctx, C.byref(dptr), C.byref(n64)))
@@ -260,9 +269,11 @@ def train_distributed(data, model_path, vocab_size, coverage=1.0, pad_id=0, unk_
                              "for vocab_size=%d" % (used, vocab_size))
         kc = np.fromiter(char2id.keys(), dtype=np.uint32)
         ki = np.fromiter(char2id.values(), dtype=np.uint32)
+        lap("allreduce+alphabet")
         nu = C.c_uint64(0)
         step(lambda: L.yttm_train_set_alphabet(ctx, kc.ctypes.data, ki.ctypes.data, len(kc), char2id[9601]) or
              L.yttm_train_dist_word_table(ctx, C.byref(nu)))
+        lap("word_table")
         # unique words -> their owner ranks (device buffers, all-to-all)
         bpd, wpd = (C.c_uint64 * 8)(), (C.c_uint64 * 8)()
         p_b, p_p, p_f = C.c_void_p(), C.c_void_p(), C.c_void_p()
@@ -271,15 +282,18 @@ def train_distributed(data, model_path, vocab_size, coverage=1.0, pad_id=0, unk_
         t_p, r_p, wps = comm.all_to_all(p_p.value, list(wpd)[:world], 8)
         t_f, r_f, _ = comm.all_to_all(p_f.value, list(wpd)[:world], 8)
         keep += [t_b, t_p, t_f]
+        lap("word_exchange")
         st = _lib.TrainStats()
         bsrc, wsrc = (C.c_uint64 * 8)(*bps), (C.c_uint64 * 8)(*wps)
         step(lambda: L.yttm_train_dist_import_words(ctx, r_b, bsrc, r_p, r_f, wsrc, C.byref(st)))
+        lap("import+tokenise+pair_table")
         n_merges = vocab_size - used
         rules = np.zeros(3 * max(n_merges, 1), dtype=np.uint32)
         freqs = np.zeros(max(n_merges, 1), dtype=np.uint64)
         done = C.c_uint32(0)
         step(lambda: L.yttm_train_run(ctx, used, n_merges, rules.ctypes.data, freqs.ctypes.data, C.byref(done)))
         rules = rules[:3 * done.value].reshape(-1, 3)
+        lap("merge_loop")
         stats = {"n_unique": int(st.n_unique), "n_tokens": int(st.n_tokens), "n_pairs": int(st.n_pairs),
                                   "n_merges": int(done.value), "merge_loop_ms": L.yttm_stage_ms(ctx, b"merge_loop"),
                                   "launches": L.yttm_stage_ms(ctx, b"loop_launches"),
@@ -295,6 +309,9 @@ def train_distributed(data, model_path, vocab_size, coverage=1.0, pad_id=0, unk_
         if rank == 0 and model_path:
             write_model(model_path, char2id, rules, (pad_id, unk_id, bos_id, eos_id), vocab_size, lib=L)
         comm.barrier()
+        lap("write_model")
+        if stats_out is not None:
+            stats_out["host_ms"] = {k: round(v, 2) for k, v in walls.items()}
         return int(done.value)
     finally:
         L.yttm_ctx_destroy(ctx)
