@@ -52,8 +52,13 @@ constexpr uint32_t XQ_CNT_OVF = 0x80000000u;      // count word: the segment ove
 constexpr uint32_t XQ_CNT_MORE = 0x40000000u;     // count word (table rounds): further entries follow in the next round
 constexpr uint32_t XQ_CNT_COMPACT = 0x20000000u;  // count word: > 25 % of the block's token slots are dead
 constexpr uint32_t XQ_CNT_MASK = 0x0fffffffu;
+constexpr uint32_t XQ_CNT_STRIDE = 16;   // count words sit 128 bytes apart
 struct XqHdr {
-  unsigned long long counts[XQ_MAX_BLOCKS];  // (round << 32) | flags | entries of the sender's segment b
+  // (round << 32) | flags | entries of the sender's segment b lives at counts[b * XQ_CNT_STRIDE]: one 128-byte line per
+  // word.  Every block polls every word; packed, the 148 words shared ten L2 lines and the ~6 k sector requests of a poll
+  // round queued at a couple of L2 slices (about one request per clock each): 2.5 us per merge.  One line per word
+  // spreads them over all slices.
+  unsigned long long counts[XQ_MAX_BLOCKS * 16];
 };
 struct Xq {
   unsigned char *base[XQ_MAX_WORLD];  // region of every rank; base[me] is local memory
@@ -523,7 +528,7 @@ __device__ __forceinline__ void xq_poll_counts(const LoopArgs &a, uint32_t round
     const uint32_t j = threadIdx.x * ipt + k;
     if (j >= nseg) break;
     const uint32_t s = j / a.xq.nblocks, b = j - s * a.xq.nblocks;
-    const unsigned long long *w = &xq_hdr(a.xq, a.xq.me, parity, s)->counts[b];
+    const unsigned long long *w = &xq_hdr(a.xq, a.xq.me, parity, s)->counts[b * XQ_CNT_STRIDE];
     unsigned long long v;
     for (uint32_t spin = 0;; spin++) {
       v = ld_relaxed_any(w, sys);   // entries validate themselves: no acquire needed
@@ -699,7 +704,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   __shared__ Best s_warp[32];
   __shared__ Best s_best, s_cb;      // the elected pair of this iteration / the cached best of this block's partition
   __shared__ unsigned long long s_dead;
-  __shared__ uint32_t s_defer_n, s_direct, s_out_n, s_occ, s_xf, s_bflags, s_sweep, s_povf, s_scan[33];
+  __shared__ uint32_t s_defer_n, s_direct, s_out_n, s_occ, s_xf, s_bflags, s_sweep, s_povf, s_last, s_scan[33];
   __shared__ unsigned long long s_tpre;
   const bool dbgt = (a.dbg & 8u) != 0;  // per-block phase timing (diagnostic)
   const bool sys = a.xq.world > 1;
@@ -769,8 +774,12 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     const uint32_t stamp = (it % 65535u) + 1u;         // never 0: the array is cleared before the launch
     unsigned long long tq0 = gtid == 0 ? gtimer() : 0, tq1 = 0, tq2 = 0, tq2b = 0, tq3 = 0;
     if (dbgb) bt = gtimer();
-    // ---------------- publish this block's best (two self-stamped words) and poll everybody's: barrier + winner
-    // reduction in one round trip.  flags: 1 = this partition is over the load limit, 2 = it ran full (update lost).
+    // ---------------- elect the pair: every block stores its best (two self-stamped words) and arrives on a counter;
+    // the LAST block to arrive reads all bests, reduces them and stores the winner (two self-stamped words) that one
+    // thread per block polls.  O(blocks) L2 requests per poll round.  (The first version had every block poll every
+    // block's words: 148 x 148 x 2 loads = 23.7 k sector requests per round on a handful of L2 lines, which one L2
+    // slice serves at about one per clock — 10.8 us per merge in that poll alone, found with YTTM_DBG=16.)
+    // flags: 1 = this partition is over the load limit, 2 = it ran full (update lost).
     if (threadIdx.x == 0) {
       const Best cb = s_cb;
       uint32_t fl = (s_occ > a.part_limit ? 1u : 0u) | (s_povf ? 2u : 0u);
@@ -783,14 +792,20 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       st_relaxed(a.blockbest + 2 * blockIdx.x, ((unsigned long long)stamp << 48) | (cb.c & BB_LOW48));
       st_relaxed(a.blockbest + 2 * blockIdx.x + 1, ((unsigned long long)stamp << 48) | ((unsigned long long)fl << 45) |
                                                     (cb.c ? bb_prio45(x, y) : 0ull));
+      __threadfence();   // the two words before the arrival
+      const unsigned long long old = atomicAdd(a.blockbest + 2 * gridDim.x + 2, 1ull);
+      s_last = old + 1 == (unsigned long long)(it + 1) * gridDim.x ? 1u : 0u;
+      s_out_n = 0;
     }
-    {
+    __syncthreads();
+    if (s_last) {  // block-uniform: this block arrived last, every best is in memory
+      __threadfence();
       unsigned long long bc = 0, bp = 0;   // best (count48, prio45) this thread has seen
-      uint32_t bw = 0xffffffffu, fl = 0;   // ... and the block that owns it
+      uint32_t fl = 0;
       unsigned long long t0 = 0;
       for (unsigned j = threadIdx.x; j < gridDim.x; j += blockDim.x) {
         unsigned long long w0, w1;
-        for (uint32_t spin = 0;; spin++) {
+        for (uint32_t spin = 0;; spin++) {   // (the stamps are there; the loop only guards the memory model)
           w0 = ld_relaxed(a.blockbest + 2 * j);
           w1 = ld_relaxed(a.blockbest + 2 * j + 1);
           if ((uint32_t)(w0 >> 48) == stamp && (uint32_t)(w1 >> 48) == stamp) break;
@@ -804,33 +819,51 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
         }
         const unsigned long long c = w0 & BB_LOW48, pr = w1 & ((1ull << 45) - 1ull);
         fl |= (uint32_t)(w1 >> 45) & 7u;
-        if (c > bc || (c == bc && pr > bp)) { bc = c; bp = pr; bw = j; }
+        if (c > bc || (c == bc && pr > bp)) { bc = c; bp = pr; }
       }
       for (int o = 16; o > 0; o >>= 1) {   // warp reduce (ties cannot happen between blocks: a pair has one owner)
         const unsigned long long c2 = __shfl_xor_sync(0xffffffffu, bc, o), p2 = __shfl_xor_sync(0xffffffffu, bp, o);
-        const uint32_t w2 = __shfl_xor_sync(0xffffffffu, bw, o);
-        if (c2 > bc || (c2 == bc && p2 > bp)) { bc = c2; bp = p2; bw = w2; }
+        if (c2 > bc || (c2 == bc && p2 > bp)) { bc = c2; bp = p2; }
       }
       if (fl) atomicOr(&s_bflags, fl);
       const unsigned used_warps = (min(gridDim.x, blockDim.x) + 31) >> 5;
-      if (lane == 0 && wid < used_warps) { s_warp[wid].c = bc; s_warp[wid].prio = bp; s_warp[wid].slot = bw; }
+      if (lane == 0 && wid < used_warps) { s_warp[wid].c = bc; s_warp[wid].prio = bp; }
       __syncthreads();
       if (wid == 0) {
         bc = lane < used_warps ? s_warp[lane].c : 0ull;
         bp = lane < used_warps ? s_warp[lane].prio : 0ull;
-        bw = lane < used_warps ? (uint32_t)s_warp[lane].slot : 0xffffffffu;
         for (int o = 16; o > 0; o >>= 1) {
           const unsigned long long c2 = __shfl_xor_sync(0xffffffffu, bc, o), p2 = __shfl_xor_sync(0xffffffffu, bp, o);
-          const uint32_t w2 = __shfl_xor_sync(0xffffffffu, bw, o);
-          if (c2 > bc || (c2 == bc && p2 > bp)) { bc = c2; bp = p2; bw = w2; }
+          if (c2 > bc || (c2 == bc && p2 > bp)) { bc = c2; bp = p2; }
         }
-        if (lane == 0) { s_best.c = bc; s_best.prio = bp; s_best.slot = bw; s_out_n = 0; }
+        if (lane == 0) {
+          s_best.c = bc; s_best.prio = bp;
+          st_relaxed(a.blockbest + 2 * gridDim.x, ((unsigned long long)stamp << 48) | bc);
+          st_relaxed(a.blockbest + 2 * gridDim.x + 1, ((unsigned long long)stamp << 48) | ((unsigned long long)(s_bflags & 7u) << 45) | bp);
+        }
       }
-      __syncthreads();
+    } else if (threadIdx.x == 0) {  // one poller per block
+      unsigned long long w0, w1, t0 = 0;
+      for (uint32_t spin = 0;; spin++) {
+        w0 = ld_relaxed(a.blockbest + 2 * gridDim.x);
+        w1 = ld_relaxed(a.blockbest + 2 * gridDim.x + 1);
+        if ((uint32_t)(w0 >> 48) == stamp && (uint32_t)(w1 >> 48) == stamp) break;
+#ifdef YT_SIMT_EMU
+        emu::yield();
+#endif
+        if ((spin & 4095u) == 4095u) {
+          if (!t0) t0 = gtimer();
+          else if (gtimer() - t0 > a.spin_limit_ns) loop_trap();
+        }
+      }
+      s_best.c = w0 & BB_LOW48;
+      s_best.prio = w1 & ((1ull << 45) - 1ull);
+      s_bflags = (uint32_t)(w1 >> 45) & 7u;
     }
+    __syncthreads();
     if (gtid == 0) tq1 = gtimer();
     if (dbgb) { const unsigned long long t = gtimer(); bacc[0] += t - bt; bt = t; }
-    const Best win = s_best;             // .prio = prio45, .slot = owner block
+    const Best win = s_best;             // .prio = prio45
     const uint32_t bflags = s_bflags, xf = s_xf;
     // ---------------- uniform exit checks (every block of every rank evaluates the same values)
     {
@@ -860,7 +893,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       a.rfreq[n_done] = win.c;
       a.ctl->n_done = n_done + 1;
     }
-    const bool i_own = (uint32_t)win.slot == blockIdx.x;
+    const bool i_own = pair_part(a.tab, mix64(op.key)) == blockIdx.x;   // the partition that holds (x, y)
     // every occurrence of (x,y) is merged below and no deltas are emitted for it: its owner clears the count
     if (i_own && threadIdx.x == 0) a.tab.cnts[s_cb.slot] = 0;
     const unsigned long long tw1 = dbgt && lane == 0 ? gtimer() : 0;
@@ -1028,7 +1061,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       const unsigned long long cw = ((unsigned long long)nround << 32) | word;
 #pragma unroll
       for (int d = 0; d < XQ_MAX_WORLD; d++)
-        if ((uint32_t)d < a.xq.world) st_relaxed_any(&xq_hdr(a.xq, (uint32_t)d, nround & 1u, a.xq.me)->counts[blockIdx.x], cw, sys);
+        if ((uint32_t)d < a.xq.world) st_relaxed_any(&xq_hdr(a.xq, (uint32_t)d, nround & 1u, a.xq.me)->counts[blockIdx.x * XQ_CNT_STRIDE], cw, sys);
       s_xf = 0; s_bflags = 0; s_sweep = 0;   // accumulators of the phases below
       if (dbgt) atomicMax(&a.ctl->blk[it & 1][0], gtimer() - tw1);
     }
@@ -1161,7 +1194,7 @@ __global__ void __launch_bounds__(256) xq_publish_table_kernel(LoopArgs a, uint3
     const unsigned long long cw = ((unsigned long long)round << 32) | word;
 #pragma unroll
     for (int d = 0; d < XQ_MAX_WORLD; d++)
-      if ((uint32_t)d < a.xq.world) st_relaxed_any(&xq_hdr(a.xq, (uint32_t)d, round & 1u, a.xq.me)->counts[blockIdx.x], cw, true);
+      if ((uint32_t)d < a.xq.world) st_relaxed_any(&xq_hdr(a.xq, (uint32_t)d, round & 1u, a.xq.me)->counts[blockIdx.x * XQ_CNT_STRIDE], cw, true);
   }
 }
 // xq_absorb_kernel: block b waits for round `round` of every block of every rank and adds the peers' pairs it owns

@@ -1436,7 +1436,7 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
   *n_done_out = 0;
   if (max_merges == 0) return 0;
   if (ensure_loop_geometry(c)) return 1;
-  YT_CUDA(c, c->blockbest.reserve((size_t)c->loop_blocks * 2 * 8));
+  YT_CUDA(c, c->blockbest.reserve(((size_t)c->loop_blocks * 2 + 4) * 8));  // per-block bests, winner words, arrival counter
   if (first_new_id + (uint64_t)max_merges >= BB_ID_LIMIT) YT_FAIL(c, "yttm_train_run: token ids beyond 2^22 are not supported by the merge loop");
   YT_CUDA(c, c->d_rules.reserve((size_t)max_merges * 12 + 16));
   YT_CUDA(c, c->d_rfreq.reserve((size_t)max_merges * 8 + 16));
@@ -1475,7 +1475,7 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
     }
     a.dead_min_slots = 4096;
     if (const char *e = std::getenv("YTTM_DEAD_MIN_SLOTS")) a.dead_min_slots = (uint32_t)std::max(0, std::atoi(e));
-    YT_CUDA(c, cudaMemsetAsync(c->blockbest.p, 0, (size_t)c->loop_blocks * 2 * 8, c->stream));  // stamps restart at 1
+    YT_CUDA(c, cudaMemsetAsync(c->blockbest.p, 0, ((size_t)c->loop_blocks * 2 + 4) * 8, c->stream));  // stamps restart at 1
 #ifndef YT_SIMT_EMU
     void *args[] = {&a};
     YT_CUDA(c, cudaLaunchCooperativeKernel((void *)merge_loop_kernel, dim3(c->loop_blocks), dim3(c->loop_threads), args,
