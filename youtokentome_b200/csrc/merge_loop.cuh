@@ -643,13 +643,39 @@ __device__ __forceinline__ void xq_drain(const LoopArgs &a, uint32_t round, uint
 // slots that hold it).  Result in *s_out (shared); s_warp: 32 Best of scratch.
 __device__ __forceinline__ void sweep_partition(const LoopArgs &a, uint64_t pbase, uint32_t R, Best *s_warp, Best *s_out) {
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  // Partitions of the RESIDENT regime (R <= SWEEP_UNROLL x blockDim: 8192 slots) keep their counts in registers for
-  // both passes; larger ones re-read them, SWEEP_UNROLL loads in flight per thread.  (Round 2, measured: a second
-  // pass that re-read one slot per loop trip cost 8 dependent L2 round trips = 6.4 of the sweep's 9.5 us.)
-  const bool small = R <= blockDim.x * SWEEP_UNROLL;
-  unsigned long long c0[SWEEP_UNROLL];
+  // Partitions of the RESIDENT regime (R <= SWEEP_UNROLL x blockDim: 8192 slots) fetch counts AND keys in one round trip
+  // and reduce (count, priority) directly; larger ones take the largest count first and then only the keys of the slots
+  // that hold it, SWEEP_UNROLL loads in flight per thread.  (Round 2, measured: a second pass that re-read one slot per
+  // loop trip cost 8 dependent L2 round trips.)
+  if (R <= blockDim.x * SWEEP_UNROLL) {
+    unsigned long long c[SWEEP_UNROLL], k[SWEEP_UNROLL];
+#pragma unroll
+    for (int u = 0; u < SWEEP_UNROLL; u++) {
+      const uint32_t i = threadIdx.x + (uint32_t)u * blockDim.x;
+      c[u] = i < R ? __ldcg(a.tab.cnts + pbase + i) : 0ull;
+      k[u] = i < R ? __ldcg(a.tab.keys + pbase + i) : 0ull;
+    }
+    Best b{0, 0, 0};
+#pragma unroll
+    for (int u = 0; u < SWEEP_UNROLL; u++) {
+      if (c[u] == 0 || c[u] < b.c) continue;
+      const Best cand{c[u], pair_prio((uint32_t)(k[u] >> 32), (uint32_t)k[u]), pbase + threadIdx.x + (uint64_t)u * blockDim.x};
+      if (better(cand, b)) b = cand;
+    }
+    b = warp_best(b);
+    if (lane == 0) s_warp[wid] = b;
+    __syncthreads();
+    if (wid == 0) {
+      Best v = lane < nwarp ? s_warp[lane] : Best{0, 0, 0};
+      v = warp_best(v);
+      if (lane == 0) *s_out = v;
+    }
+    __syncthreads();
+    return;
+  }
   unsigned long long cmax = 0;
   for (uint32_t i0 = threadIdx.x; i0 < R; i0 += blockDim.x * SWEEP_UNROLL) {
+    unsigned long long c0[SWEEP_UNROLL];
 #pragma unroll
     for (int u = 0; u < SWEEP_UNROLL; u++) {
       const uint32_t i = i0 + (uint32_t)u * blockDim.x;
@@ -674,7 +700,7 @@ __device__ __forceinline__ void sweep_partition(const LoopArgs &a, uint64_t pbas
 #pragma unroll
       for (int u = 0; u < SWEEP_UNROLL; u++) {
         const uint32_t i = i0 + (uint32_t)u * blockDim.x;
-        c[u] = small ? c0[u] : (i < R ? __ldcg(a.tab.cnts + pbase + i) : 0ull);
+        c[u] = i < R ? __ldcg(a.tab.cnts + pbase + i) : 0ull;
       }
 #pragma unroll
       for (int u = 0; u < SWEEP_UNROLL; u++) {
@@ -704,7 +730,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   __shared__ Best s_warp[32];
   __shared__ Best s_best, s_cb;      // the elected pair of this iteration / the cached best of this block's partition
   __shared__ unsigned long long s_dead;
-  __shared__ uint32_t s_defer_n, s_direct, s_out_n, s_occ, s_xf, s_bflags, s_sweep, s_povf, s_last, s_scan[33];
+  __shared__ uint32_t s_defer_n, s_direct, s_out_n, s_occ, s_xf, s_bflags, s_sweep, s_povf, s_scan[33];
   __shared__ unsigned long long s_tpre;
   const bool dbgt = (a.dbg & 8u) != 0;  // per-block phase timing (diagnostic)
   const bool sys = a.xq.world > 1;
@@ -774,11 +800,12 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     const uint32_t stamp = (it % 65535u) + 1u;         // never 0: the array is cleared before the launch
     unsigned long long tq0 = gtid == 0 ? gtimer() : 0, tq1 = 0, tq2 = 0, tq2b = 0, tq3 = 0;
     if (dbgb) bt = gtimer();
-    // ---------------- elect the pair: every block stores its best (two self-stamped words) and arrives on a counter;
-    // the LAST block to arrive reads all bests, reduces them and stores the winner (two self-stamped words) that one
-    // thread per block polls.  O(blocks) L2 requests per poll round.  (The first version had every block poll every
-    // block's words: 148 x 148 x 2 loads = 23.7 k sector requests per round on a handful of L2 lines, which one L2
-    // slice serves at about one per clock — 10.8 us per merge in that poll alone, found with YTTM_DBG=16.)
+    // ---------------- elect the pair: every block stores its best as two self-stamped words; BLOCK 0 polls them (one
+    // reader: no contention), reduces and stores the winner, again two self-stamped words, which one thread per block
+    // polls.  Two store -> load round trips, O(blocks) L2 requests per poll round.  (First version: every block polled
+    // every block's words — 148 x 148 x 2 loads = 23.7 k sector requests per round on a handful of L2 lines, which an L2
+    // slice serves at about one per clock: 10.8 us per merge in that poll alone.  Second version: arrival counter, the
+    // last block reduces: fence + atomic + read = 7.2 us.  Found with YTTM_DBG=16.)
     // flags: 1 = this partition is over the load limit, 2 = it ran full (update lost).
     if (threadIdx.x == 0) {
       const Best cb = s_cb;
@@ -792,20 +819,15 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       st_relaxed(a.blockbest + 2 * blockIdx.x, ((unsigned long long)stamp << 48) | (cb.c & BB_LOW48));
       st_relaxed(a.blockbest + 2 * blockIdx.x + 1, ((unsigned long long)stamp << 48) | ((unsigned long long)fl << 45) |
                                                     (cb.c ? bb_prio45(x, y) : 0ull));
-      __threadfence();   // the two words before the arrival
-      const unsigned long long old = atomicAdd(a.blockbest + 2 * gridDim.x + 2, 1ull);
-      s_last = old + 1 == (unsigned long long)(it + 1) * gridDim.x ? 1u : 0u;
       s_out_n = 0;
     }
-    __syncthreads();
-    if (s_last) {  // block-uniform: this block arrived last, every best is in memory
-      __threadfence();
+    if (blockIdx.x == 0) {  // the reducer
       unsigned long long bc = 0, bp = 0;   // best (count48, prio45) this thread has seen
       uint32_t fl = 0;
       unsigned long long t0 = 0;
       for (unsigned j = threadIdx.x; j < gridDim.x; j += blockDim.x) {
         unsigned long long w0, w1;
-        for (uint32_t spin = 0;; spin++) {   // (the stamps are there; the loop only guards the memory model)
+        for (uint32_t spin = 0;; spin++) {
           w0 = ld_relaxed(a.blockbest + 2 * j);
           w1 = ld_relaxed(a.blockbest + 2 * j + 1);
           if ((uint32_t)(w0 >> 48) == stamp && (uint32_t)(w1 >> 48) == stamp) break;
