@@ -240,53 +240,19 @@ __device__ __forceinline__ bool word_table_insert(const uint8_t *__restrict__ s,
   return false;
 }
 
-// Word split + dedup of running text.  A block owns CHUNKS of WC_CHUNK consecutive bytes; inside a chunk the words are
-// first counted in a shared-memory table (entry = 32-bit tag | position of the first occurrence inside the chunk,
-// duplicates verified byte by byte against it — exactness never rests on the hash), and only one (word, count) per
-// distinct word of the chunk goes to the global table.  Why: natural text repeats its words (Zipf), and the round-1
-// kernel sent one 64-bit atomic per OCCURRENCE to the global counters — 1.2 M of the 16.7 M occurrences of the 100 MB
-// bench corpus hit the single counter of the most frequent word, where same-address atomics serialise in L2
-// (4.2 ms = 24 GB/s).  Words that find no room in the shared table (WC_PROBES) go to the global table directly.
-constexpr int WC_T = 512;
-constexpr uint32_t WC_CHUNK = 65536, WC_SLOTS = 4096, WC_PROBES = 12;
-__global__ void __launch_bounds__(WC_T) word_insert_kernel(const uint8_t *__restrict__ s, uint64_t n, WordTab wt,
+// Word split + dedup of running text: thread per byte position; a position that starts a word hashes it and inserts
+// it into the global word table (exact byte compare on a tag match).  ncu (profiles/r02_prof_front.*): instruction
+// bound — the per-word hash / compare loops run with ~5 of 32 lanes active.  A variant that first aggregated the words
+// of a 64 KB chunk in a shared-memory table (to take the hot words' same-address atomics off L2) was measured SLOWER
+// on B200 (5.5 - 6.4 ms vs 4.4 ms per 100 MB: 4.1 G warp instructions) and was dropped.
+__global__ void __launch_bounds__(256) word_insert_kernel(const uint8_t *__restrict__ s, uint64_t n, WordTab wt,
                                                           unsigned long long *counters, uint64_t max_unique) {
-  __shared__ unsigned long long s_ent[WC_SLOTS];  // (tag32 << 32) | (position in the chunk + 1) ; 0 = empty
-  __shared__ uint32_t s_cnt[WC_SLOTS];
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   uint64_t occ = 0;
-  const uint64_t n_chunks = (n + WC_CHUNK - 1) / WC_CHUNK;
-  for (uint64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {  // block-uniform
-    for (uint32_t i = threadIdx.x; i < WC_SLOTS; i += WC_T) { s_ent[i] = 0; s_cnt[i] = 0; }
-    __syncthreads();
-    const uint64_t base = ch * WC_CHUNK, end = base + WC_CHUNK < n ? base + WC_CHUNK : n;
-    for (uint64_t p = base + threadIdx.x; p < end; p += WC_T) {
-      if (!word_start_at(s, p, 0, n)) continue;
-      occ++;
-      uint64_t h = 0xcbf29ce484222325ull, q = p;
-      uint32_t l;
-      while (q < n && !space_at(s, q, n, &l)) { h = (h ^ s[q]) * 0x100000001b3ull; q++; }
-      const uint64_t len = q - p;
-      h = mix64(h ^ (len << 1));
-      const uint32_t tag = (uint32_t)(h >> 32);
-      const unsigned long long mine = ((unsigned long long)tag << 32) | (uint32_t)(p - base + 1);
-      uint32_t slot = (uint32_t)h & (WC_SLOTS - 1);
-      bool done = false;
-      for (uint32_t probe = 0; probe < WC_PROBES && !done; probe++, slot = (slot + 1) & (WC_SLOTS - 1)) {
-        unsigned long long k = s_ent[slot];
-        if (k == 0) {
-          k = atomicCAS(&s_ent[slot], 0ull, mine);
-          if (k == 0) { atomicAdd(&s_cnt[slot], 1u); done = true; break; }
-        }
-        if ((uint32_t)(k >> 32) == tag && same_word(s, n, base + (uint32_t)k - 1, p, len)) { atomicAdd(&s_cnt[slot], 1u); done = true; }
-      }
-      if (!done) word_table_insert(s, n, p, wt, counters, max_unique, 1ull);
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < WC_SLOTS; i += WC_T) {
-      const unsigned long long k = s_ent[i];
-      if (k) word_table_insert(s, n, base + (uint32_t)k - 1, wt, counters, max_unique, (unsigned long long)s_cnt[i]);
-    }
-    __syncthreads();
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+    if (!word_start_at(s, p, 0, n)) continue;
+    occ++;
+    word_table_insert(s, n, p, wt, counters, max_unique, 1ull);
   }
   for (int o = 16; o > 0; o >>= 1) occ += __shfl_xor_sync(0xffffffffu, occ, o);
   if ((threadIdx.x & 31) == 0 && occ) atomicAdd(counters + 0, (unsigned long long)occ);
@@ -1111,8 +1077,7 @@ static int build_word_table(yttm_ctx *c, const WordList *list, uint64_t *n_uniqu
         c->launches++;
       }
     } else if (n) {
-      const uint64_t n_chunks = (n + WC_CHUNK - 1) / WC_CHUNK;
-      word_insert_kernel<<<(unsigned)std::min<uint64_t>(n_chunks, (uint64_t)c->n_sm * 4), WC_T, 0, c->stream>>>(c->d_text, n, wt, counters, cap / 2);
+      word_insert_kernel<<<grid_for(c, n, 256, 8), 256, 0, c->stream>>>(c->d_text, n, wt, counters, cap / 2);
       c->launches++;
     }
     YT_CUDA(c, cudaGetLastError());
