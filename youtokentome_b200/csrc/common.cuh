@@ -48,7 +48,7 @@ struct YtLoopCtl {
   uint32_t stop_why;              // stop == 2: 1 partition nearly full, 2 exchange segment overflowed, 4 partition full, 8 load factor
   uint32_t xq_flags;              // flags of the peers' last out-of-loop round (xq_absorb_kernel)
   uint32_t max_part_occ;          // part_occ_kernel: fullest partition of the table
-  unsigned long long n_sweeps;    // partition sweeps after a drain, summed over blocks (the winner's owner sweeps besides)
+  unsigned long long n_sweeps;    // refreshes of the replicated front (merge_loop.cuh)
 };
 
 struct yttm_ctx {
@@ -98,7 +98,7 @@ struct yttm_ctx {
   bool xq_connected = false;
 
   // ---- merge loop
-  ytc::DevBuf ctl, blockbest, d_rules, d_rfreq, tiles, defer;
+  ytc::DevBuf ctl, frontbuf, d_rules, d_rfreq, tiles, defer;
   int loop_smem = 0, loop_resident = 0, loop_stages = 2;
   uint32_t loop_tok_cap = 0, loop_word_cap = 0, loop_stream_q = 0, loop_stream_tok_cap = 0, loop_stream_word_cap = 0;
   int loop_blocks = 0, loop_threads = 0;

@@ -48,10 +48,14 @@ constexpr int XQ_MAX_BLOCKS = 256;
 constexpr uint32_t XQF_COMPACT = 1u;     // some block wants a compaction of its packed words
 constexpr uint32_t XQF_OVERFLOW = 2u;    // a segment overflowed: counts are stale, rebuild the table
 constexpr uint32_t XQF_MORE = 4u;        // out-of-loop table rounds: a sender has more chunks to publish
+constexpr uint32_t XQF_PLIMIT = 8u;      // a partition is over the load limit: rebuild (dead keys vanish)
+constexpr uint32_t XQF_PFULL = 16u;      // a partition ran full: grow the table
 constexpr uint32_t XQ_CNT_OVF = 0x80000000u;      // count word: the segment overflowed
 constexpr uint32_t XQ_CNT_MORE = 0x40000000u;     // count word (table rounds): further entries follow in the next round
 constexpr uint32_t XQ_CNT_COMPACT = 0x20000000u;  // count word: > 25 % of the block's token slots are dead
-constexpr uint32_t XQ_CNT_MASK = 0x0fffffffu;
+constexpr uint32_t XQ_CNT_PLIMIT = 0x10000000u;   // count word: the block's partition is over the load limit
+constexpr uint32_t XQ_CNT_PFULL = 0x08000000u;    // count word: the block's partition ran full (an update was lost)
+constexpr uint32_t XQ_CNT_MASK = 0x07ffffffu;
 constexpr uint32_t XQ_CNT_STRIDE = 16;   // count words sit 128 bytes apart
 struct XqHdr {
   // (round << 32) | flags | entries of the sender's segment b lives at counts[b * XQ_CNT_STRIDE]: one 128-byte line per
@@ -193,7 +197,7 @@ struct LoopArgs {
   PairTab tab;                 // tab.nparts == gridDim.x
   Xq xq;
   YtLoopCtl *ctl;
-  unsigned long long *blockbest;  // 2 self-stamped words per block (bb_* above); cleared before every launch
+  unsigned long long *frontbuf;   // gather buffer of the front refreshes (front_buf_words()); cleared before every launch
   uint32_t *rules;                // 3 per merge
   unsigned long long *rfreq;
   uint32_t first_new_id;          // id of merge number 0
@@ -545,6 +549,8 @@ __device__ __forceinline__ void xq_poll_counts(const LoopArgs &a, uint32_t round
     if (c & XQ_CNT_OVF) flags |= XQF_OVERFLOW;
     if (c & XQ_CNT_MORE) flags |= XQF_MORE;
     if (c & XQ_CNT_COMPACT) flags |= XQF_COMPACT;
+    if (c & XQ_CNT_PLIMIT) flags |= XQF_PLIMIT;
+    if (c & XQ_CNT_PFULL) flags |= XQF_PFULL;
     uint32_t n = c & XQ_CNT_MASK;
     if (n > a.xq.seg_cap) n = a.xq.seg_cap;
     s_pref[j] = (skip_self && s == a.xq.me) ? 0u : n;
@@ -553,18 +559,13 @@ __device__ __forceinline__ void xq_poll_counts(const LoopArgs &a, uint32_t round
   __syncthreads();
 }
 
-// Up to DRAIN_KEEP table slots a thread has updated in one drain (for the cached arg-max); more: the block sweeps.
-constexpr int DRAIN_KEEP = 4;
-struct Touched { uint64_t slot[DRAIN_KEEP]; unsigned long long key[DRAIN_KEEP]; uint32_t n, dropped; };
-
-// Drain: s_pref holds the entry counts (xq_poll_counts); every entry whose key belongs to partition blockIdx.x is
-// applied to that partition.  *s_occ_add is increased by the keys inserted; `tch` records what this thread touched.
-__device__ __forceinline__ void xq_drain(const LoopArgs &a, uint32_t round, uint32_t *s_pref, uint32_t *s_scan /* 33 words */,
-                                         uint32_t *s_occ_add, Touched &tch) {
+// Drain of the out-of-loop table rounds (xq_absorb_kernel): s_pref holds the entry counts (xq_poll_counts); every entry
+// whose key belongs to partition blockIdx.x is added to that partition.  *s_occ_add is increased by the keys inserted.
+__device__ __forceinline__ void xq_prefix(const LoopArgs &a, uint32_t *s_pref, uint32_t *s_scan /* 33 words */) {
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  const uint32_t nseg = a.xq.world * a.xq.nblocks, parity = round & 1u;
+  const uint32_t nseg = a.xq.world * a.xq.nblocks;
   const uint32_t ipt = (nseg + blockDim.x - 1) / blockDim.x;
-  // ---- exclusive prefix of the segment sizes, in place
+  // ---- exclusive prefix of the segment sizes, in place; s_pref[nseg] = total
   uint32_t mine = 0;
   for (uint32_t k = 0; k < ipt; k++) {
     const uint32_t j = threadIdx.x * ipt + k;
@@ -595,126 +596,108 @@ __device__ __forceinline__ void xq_drain(const LoopArgs &a, uint32_t round, uint
       if (j < nseg) { const uint32_t c = s_pref[j]; s_pref[j] = run; run += c; }
     }
   }
-  const uint32_t total = s_scan[32];
-  if (threadIdx.x == 0) s_pref[nseg] = total;
+  if (threadIdx.x == 0) s_pref[nseg] = s_scan[32];
   __syncthreads();
-  // ---- entries
+}
+// entry i (0 <= i < s_pref[nseg]) of round `round` in this rank's region; spins until both words carry the round's stamp
+__device__ __forceinline__ void xq_entry(const LoopArgs &a, uint32_t round, const uint32_t *s_pref, uint32_t i,
+                                         unsigned long long *key, long long *delta) {
+  const uint32_t nseg = a.xq.world * a.xq.nblocks;
+  uint32_t lo = 0, hi = nseg;  // largest j with s_pref[j] <= i (empty segments share a prefix value: take the last)
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (s_pref[mid] <= i) lo = mid; else hi = mid;
+  }
+  const uint32_t s = lo / a.xq.nblocks, b = lo - s * a.xq.nblocks;
+  const unsigned long long *ep = reinterpret_cast<const unsigned long long *>(
+      xq_base(a.xq, a.xq.me) + xq_seg_off(a.xq, round & 1u, s, b) + (size_t)(i - s_pref[lo]) * sizeof(uint4));
+  const bool sys = a.xq.world > 1;
+  unsigned long long t0 = 0;
+  for (uint32_t spin = 0; !xq_unpack(ld_relaxed_any(ep, sys), ld_relaxed_any(ep + 1, sys), round % XQ_STAMP_MOD, key, delta); spin++) {
+#ifdef YT_SIMT_EMU
+    emu::yield();
+#endif
+    if ((spin & 4095u) == 4095u) {   // the count word overtook the entry: it is on its way
+      if (!t0) t0 = gtimer();
+      else if (gtimer() - t0 > a.spin_limit_ns) loop_trap();
+    }
+  }
+}
+__device__ __forceinline__ void xq_drain(const LoopArgs &a, uint32_t round, uint32_t *s_pref, uint32_t *s_scan /* 33 words */,
+                                         uint32_t *s_occ_add) {
+  xq_prefix(a, s_pref, s_scan);
+  const uint32_t nseg = a.xq.world * a.xq.nblocks, total = s_pref[nseg];
   const uint32_t R = a.tab.rmask + 1;
   uint32_t added = 0;
   for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
-    uint32_t lo = 0, hi = nseg;  // largest j with s_pref[j] <= i (empty segments share a prefix value: take the last)
-    while (hi - lo > 1) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (s_pref[mid] <= i) lo = mid; else hi = mid;
-    }
-    const uint32_t s = lo / a.xq.nblocks, b = lo - s * a.xq.nblocks;
-    const unsigned long long *ep = reinterpret_cast<const unsigned long long *>(
-        xq_base(a.xq, a.xq.me) + xq_seg_off(a.xq, parity, s, b) + (size_t)(i - s_pref[lo]) * sizeof(uint4));
     unsigned long long key = 0;
     long long delta = 0;
-    {
-      unsigned long long t0 = 0;
-      for (uint32_t spin = 0; !xq_unpack(ld_relaxed_any(ep, a.xq.world > 1), ld_relaxed_any(ep + 1, a.xq.world > 1), round % XQ_STAMP_MOD, &key, &delta); spin++) {
-#ifdef YT_SIMT_EMU
-        emu::yield();
-#endif
-        if ((spin & 4095u) == 4095u) {   // the count word overtook the entry: it is on its way
-          if (!t0) t0 = gtimer();
-          else if (gtimer() - t0 > a.spin_limit_ns) loop_trap();
-        }
-      }
-    }
+    xq_entry(a, round, s_pref, i, &key, &delta);
     const uint64_t hh = mix64(key);
     if (pair_part(a.tab, hh) != blockIdx.x) continue;
-    uint64_t slot = ~0ull;
-    added += pair_add_at(a.tab, (uint64_t)blockIdx.x * R, (uint32_t)hh & a.tab.rmask, key, delta, &slot) ? 1u : 0u;
-    if (slot == ~0ull) tch.dropped = 1;
-    if (tch.n < (uint32_t)DRAIN_KEEP) {
-#pragma unroll
-      for (int q = 0; q < DRAIN_KEEP; q++)
-        if ((uint32_t)q == tch.n) { tch.slot[q] = slot; tch.key[q] = key; }
-    }
-    tch.n++;
+    added += pair_add_at(a.tab, (uint64_t)blockIdx.x * R, (uint32_t)hh & a.tab.rmask, key, delta) ? 1u : 0u;
   }
   if (added) atomicAdd(s_occ_add, added);
 }
 
-// Exact arg-max of this block's partition (all threads; two passes: the largest count first, keys only for the
-// slots that hold it).  Result in *s_out (shared); s_warp: 32 Best of scratch.
-__device__ __forceinline__ void sweep_partition(const LoopArgs &a, uint64_t pbase, uint32_t R, Best *s_warp, Best *s_out) {
+// ---- the replicated FRONT ----------------------------------------------------------------------------------------
+// Every block (of every GPU) keeps the same small set of leading pairs with their exact counts in shared memory and
+// elects the pair of a merge from it, alone: every block reads every count change of a merge anyway (the drain), so the
+// copies stay identical without a word being exchanged.  What makes this exact:
+//   * pairs are totally ordered by (count, priority) — MergeCandidate::operator<, bpe.cpp:110-126;
+//   * a REFRESH takes the FRONT_TOP leading pairs of every partition (its owner sweeps it, the blocks of a GPU gather
+//     the lists through a small buffer) and sets BOUND = the largest FRONT_TOP-th pair of any partition: every pair
+//     above the bound is in the front;
+//   * the count of a pair outside the front can only fall (a merge only removes occurrences of existing tokens), except
+//     for the pairs of the token created by the merge itself: those are aggregated per round and enter the front if
+//     they are not below the bound.  Hence "every pair outside the front is below the bound" holds between refreshes,
+//     and the largest member of the front is the global arg-max as long as it is not below the bound;
+//   * otherwise (front exhausted, front too full, too many new pairs in one round) all blocks — they see the same
+//     front — refresh in the same iteration.  A refresh costs FRONT_TOP partition sweeps and one gather, and pays for
+//     a few hundred merges (148 partitions x 8 pairs; the bound sits where the first partition runs out).
+// The pair table in HBM/L2 stays the ground truth (rebuilds, refreshes, the multi-GPU table build): a block parks the
+// entries it owns in shared memory during the drain and adds them to its partition while it waits for the other blocks'
+// next count words — off the critical path of the merge.
+constexpr uint32_t FRONT_SLOTS = 2048;   // shared-memory hash table (key, count), per block
+constexpr uint32_t FRONT_FILL = 1280;    // members that trigger a refresh (dead members are only dropped there)
+constexpr uint32_t NEWP_SLOTS = 1024;    // the round's pairs with the new token, aggregated before they meet the bound
+constexpr uint32_t OWN_CAP = 512;        // parked entries of one round (more: added to the partition at once)
+constexpr int FRONT_TOP = 8;             // pairs a partition contributes to a refresh
+constexpr size_t LOOP_FRONT_BYTES = ((size_t)FRONT_SLOTS * 2 + NEWP_SLOTS * 2 + OWN_CAP * 2) * 8;
+// global gather buffer of a refresh: [nblocks flag words, 128 bytes apart][nblocks x FRONT_TOP x (count, key)]
+YT_HD size_t front_buf_words(uint32_t nblocks) { return (size_t)nblocks * 16 + (size_t)nblocks * FRONT_TOP * 2; }
+
+__device__ __forceinline__ uint32_t smem_home(uint64_t hh, uint32_t mask) { return (uint32_t)(hh >> 20) & mask; }
+// slot of `key` or ~0u (no insert may run concurrently)
+__device__ __forceinline__ uint32_t smem_tab_find(const unsigned long long *keys, uint32_t mask, uint64_t hh, unsigned long long key) {
+  uint32_t i = smem_home(hh, mask);
+  for (uint32_t p = 0; p <= mask; p++, i = (i + 1) & mask) {
+    const unsigned long long k = keys[i];
+    if (k == key) return i;
+    if (k == PK_EMPTY) return ~0u;
+  }
+  return ~0u;
+}
+// insert-or-add; false: the table is full
+__device__ __forceinline__ bool smem_tab_add(unsigned long long *keys, unsigned long long *cnts, uint32_t mask, uint64_t hh,
+                                             unsigned long long key, long long delta, uint32_t *occ) {
+  uint32_t i = smem_home(hh, mask);
+  for (uint32_t p = 0; p <= mask; p++, i = (i + 1) & mask) {
+    unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(keys + i);
+    if (k == PK_EMPTY) {
+      k = atomicCAS(keys + i, PK_EMPTY, key);
+      if (k == PK_EMPTY) { atomicAdd(occ, 1u); k = key; }
+    }
+    if (k == key) { atomicAdd(cnts + i, (unsigned long long)delta); return true; }
+  }
+  return false;
+}
+__device__ __forceinline__ unsigned long long prio_key(unsigned long long prio) {   // inverse of pair_prio
+  const uint32_t mx = 0xffffffffu - (uint32_t)(prio >> 32), mn = 0x7fffffffu - (uint32_t)((prio & 0xffffffffull) >> 1);
+  return (prio & 1ull) ? pair_key(mx, mn) : pair_key(mn, mx);
+}
+__device__ __forceinline__ void block_best(Best b, Best *s_warp, Best *s_out) {   // ends with a block barrier
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  // Partitions of the RESIDENT regime (R <= SWEEP_UNROLL x blockDim: 8192 slots) fetch counts AND keys in one round trip
-  // and reduce (count, priority) directly; larger ones take the largest count first and then only the keys of the slots
-  // that hold it, SWEEP_UNROLL loads in flight per thread.  (Round 2, measured: a second pass that re-read one slot per
-  // loop trip cost 8 dependent L2 round trips.)
-  if (R <= blockDim.x * SWEEP_UNROLL) {
-    unsigned long long c[SWEEP_UNROLL], k[SWEEP_UNROLL];
-#pragma unroll
-    for (int u = 0; u < SWEEP_UNROLL; u++) {
-      const uint32_t i = threadIdx.x + (uint32_t)u * blockDim.x;
-      c[u] = i < R ? __ldcg(a.tab.cnts + pbase + i) : 0ull;
-      k[u] = i < R ? __ldcg(a.tab.keys + pbase + i) : 0ull;
-    }
-    Best b{0, 0, 0};
-#pragma unroll
-    for (int u = 0; u < SWEEP_UNROLL; u++) {
-      if (c[u] == 0 || c[u] < b.c) continue;
-      const Best cand{c[u], pair_prio((uint32_t)(k[u] >> 32), (uint32_t)k[u]), pbase + threadIdx.x + (uint64_t)u * blockDim.x};
-      if (better(cand, b)) b = cand;
-    }
-    b = warp_best(b);
-    if (lane == 0) s_warp[wid] = b;
-    __syncthreads();
-    if (wid == 0) {
-      Best v = lane < nwarp ? s_warp[lane] : Best{0, 0, 0};
-      v = warp_best(v);
-      if (lane == 0) *s_out = v;
-    }
-    __syncthreads();
-    return;
-  }
-  unsigned long long cmax = 0;
-  for (uint32_t i0 = threadIdx.x; i0 < R; i0 += blockDim.x * SWEEP_UNROLL) {
-    unsigned long long c0[SWEEP_UNROLL];
-#pragma unroll
-    for (int u = 0; u < SWEEP_UNROLL; u++) {
-      const uint32_t i = i0 + (uint32_t)u * blockDim.x;
-      c0[u] = i < R ? __ldcg(a.tab.cnts + pbase + i) : 0ull;
-    }
-#pragma unroll
-    for (int u = 0; u < SWEEP_UNROLL; u++) cmax = c0[u] > cmax ? c0[u] : cmax;
-  }
-  for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, cmax, o); cmax = v > cmax ? v : cmax; }
-  if (lane == 0) s_warp[wid].c = cmax;
-  __syncthreads();
-  {
-    unsigned long long v = lane < nwarp ? s_warp[lane].c : 0ull;
-    for (int o = 16; o > 0; o >>= 1) { const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
-    cmax = v;  // every warp computes the block maximum
-  }
-  __syncthreads();
-  Best b{0, 0, 0};
-  if (cmax) {
-    for (uint32_t i0 = threadIdx.x; i0 < R; i0 += blockDim.x * SWEEP_UNROLL) {   // keys of the maxima only, all in flight
-      unsigned long long c[SWEEP_UNROLL], k[SWEEP_UNROLL];
-#pragma unroll
-      for (int u = 0; u < SWEEP_UNROLL; u++) {
-        const uint32_t i = i0 + (uint32_t)u * blockDim.x;
-        c[u] = i < R ? __ldcg(a.tab.cnts + pbase + i) : 0ull;
-      }
-#pragma unroll
-      for (int u = 0; u < SWEEP_UNROLL; u++) {
-        const uint32_t i = i0 + (uint32_t)u * blockDim.x;
-        k[u] = c[u] == cmax ? __ldcg(a.tab.keys + pbase + i) : 0ull;
-      }
-#pragma unroll
-      for (int u = 0; u < SWEEP_UNROLL; u++) {
-        if (c[u] != cmax) continue;
-        const Best cand{cmax, pair_prio((uint32_t)(k[u] >> 32), (uint32_t)k[u]), pbase + i0 + (uint64_t)u * blockDim.x};
-        if (better(cand, b)) b = cand;
-      }
-    }
-  }
   b = warp_best(b);
   if (lane == 0) s_warp[wid] = b;
   __syncthreads();
@@ -725,23 +708,51 @@ __device__ __forceinline__ void sweep_partition(const LoopArgs &a, uint64_t pbas
   }
   __syncthreads();
 }
+// The largest pair of this block's partition that is strictly below `lim` (all threads; counts and keys of
+// SWEEP_UNROLL slots per thread in flight, no dependent loads).  Result in *s_out; s_warp: 32 Best of scratch.
+__device__ __forceinline__ void sweep_below(const LoopArgs &a, uint64_t pbase, uint32_t R, const Best lim, Best *s_warp, Best *s_out) {
+  Best b{0, 0, 0};
+  for (uint32_t i0 = threadIdx.x; i0 < R; i0 += blockDim.x * SWEEP_UNROLL) {
+    unsigned long long c[SWEEP_UNROLL], k[SWEEP_UNROLL];
+#pragma unroll
+    for (int u = 0; u < SWEEP_UNROLL; u++) {
+      const uint32_t i = i0 + (uint32_t)u * blockDim.x;
+      c[u] = i < R ? __ldcg(a.tab.cnts + pbase + i) : 0ull;
+      k[u] = i < R ? __ldcg(a.tab.keys + pbase + i) : 0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < SWEEP_UNROLL; u++) {
+      if (c[u] == 0 || c[u] < b.c || c[u] > lim.c) continue;
+      const Best cand{c[u], pair_prio((uint32_t)(k[u] >> 32), (uint32_t)k[u]), pbase + i0 + (uint64_t)u * blockDim.x};
+      if (!better(lim, cand)) continue;
+      if (better(cand, b)) b = cand;
+    }
+  }
+  block_best(b, s_warp, s_out);
+}
 
 __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   __shared__ Best s_warp[32];
-  __shared__ Best s_best, s_cb;      // the elected pair of this iteration / the cached best of this block's partition
+  __shared__ Best s_best, s_bound, s_tmp;   // the elected pair / the bound of the front / scratch of a refresh
   __shared__ unsigned long long s_dead;
-  __shared__ uint32_t s_defer_n, s_direct, s_out_n, s_occ, s_xf, s_bflags, s_sweep, s_povf, s_scan[33];
-  __shared__ unsigned long long s_tpre;
-  const bool dbgt = (a.dbg & 8u) != 0;  // per-block phase timing (diagnostic)
+  __shared__ uint32_t s_defer_n, s_direct, s_out_n, s_occ, s_xf, s_povf, s_focc, s_nocc, s_own_n, s_refresh, s_scan[33];
   const bool sys = a.xq.world > 1;
-  // dynamic shared memory: [segment prefix: XQ_MAX_WORLD * XQ_MAX_BLOCKS + 1 words][claim bitmaps][tile tokens][tile offsets]
+  // dynamic shared memory: [segment prefix: XQ_MAX_WORLD * XQ_MAX_BLOCKS + 4 words][claim bitmaps][front keys, counts]
+  // [new-pair keys, counts][parked keys, deltas][tile tokens][tile offsets][word frequencies]
   uint32_t *s_pref = yt_dyn_smem;
   uint32_t *s_claim = s_pref + (XQ_MAX_WORLD * XQ_MAX_BLOCKS + 4);  // 2 bitmaps of CLAIM_WORDS x 32 flags
-  uint32_t *stok = s_claim + 2 * CLAIM_WORDS;
+  unsigned long long *fk = reinterpret_cast<unsigned long long *>(s_claim + 2 * CLAIM_WORDS);
+  unsigned long long *fc = fk + FRONT_SLOTS;
+  unsigned long long *nk = fc + FRONT_SLOTS;
+  unsigned long long *nc = nk + NEWP_SLOTS;
+  unsigned long long *ownk = nc + NEWP_SLOTS;
+  long long *ownd = reinterpret_cast<long long *>(ownk + OWN_CAP);
+  uint32_t *stok = reinterpret_cast<uint32_t *>(ownd + OWN_CAP);
   uint32_t *soff = stok + a.smem_tok_cap;
   // RESIDENT only: word frequencies behind the offsets (8-byte aligned: both caps are even)
   unsigned long long *sfreq = reinterpret_cast<unsigned long long *>(soff + a.smem_word_cap + 2);
   for (uint32_t i = threadIdx.x; i < 2 * CLAIM_WORDS; i += blockDim.x) s_claim[i] = 0;
+  for (uint32_t i = threadIdx.x; i < NEWP_SLOTS; i += blockDim.x) { nk[i] = PK_EMPTY; nc[i] = 0; }
   // STREAMING carve of the same region: NSTAGE stages of (tokens, offsets), each 16-byte aligned;
   // full[s]: TMA bytes landed (tx count), empty[s]: all consumer warps are done with stage s
   __shared__ __align__(8) unsigned long long s_full[MAX_STAGES], s_empty[MAX_STAGES];
@@ -761,7 +772,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   const uint64_t pbase = (uint64_t)blockIdx.x * R;  // this block's partition of the pair table
   const uint32_t n_done0 = a.ctl->n_done;
   uint32_t round = a.ctl->xq_round;                   // exchange rounds completed so far (same on every rank)
-  unsigned long long tacc0 = 0, tacc2 = 0, tacc3 = 0, tacc4 = 0, tacc5 = 0, tacc7 = 0, titers = 0;  // phase timers (block 0, thread 0)
+  unsigned long long tacc0 = 0, tacc2 = 0, tacc3 = 0, tacc4 = 0, titers = 0;  // phase timers (block 0, thread 0)
   const bool dbgb = (a.dbg & 16u) != 0 && threadIdx.x == 0;   // per-block phase accumulators (thread 0 of every block)
   unsigned long long bacc[6] = {0, 0, 0, 0, 0, 0}, bt = 0;
 
@@ -770,7 +781,11 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     uint32_t occ = 0;
     for (uint32_t i = threadIdx.x; i < R; i += blockDim.x) occ += __ldcg(a.tab.keys + pbase + i) != PK_EMPTY ? 1u : 0u;
     for (int o = 16; o > 0; o >>= 1) occ += __shfl_xor_sync(0xffffffffu, occ, o);
-    if (threadIdx.x == 0) { s_occ = 0; s_xf = 0; s_bflags = 0; s_tpre = 0; s_sweep = 0; s_dead = 0; s_povf = __ldcg(a.tab.overflow) ? 1u : 0u; }
+    if (threadIdx.x == 0) {
+      s_occ = 0; s_xf = 0; s_dead = 0; s_focc = 0; s_nocc = 0; s_own_n = 0; s_refresh = 1; s_out_n = 0;
+      s_povf = __ldcg(a.tab.overflow) ? 1u : 0u;
+      s_bound = Best{0, 0, 0};
+    }
     __syncthreads();
     if (lane == 0 && occ) atomicAdd(&s_occ, occ);
   }
@@ -792,45 +807,62 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     my_slots = a.tile_desc[k1].y - a.tile_desc[k0].y;
   }
   unsigned long long my_dead = 0;    // token slots of this block tombstoned in this launch (thread 0 keeps the sum)
-  uint32_t n_sweeps = 0;             // sweeps of this block after a drain (thread 0; diagnostic)
-  sweep_partition(a, pbase, R, s_warp, &s_cb);   // the cached arg-max starts exact (has the block barriers)
+  uint32_t n_refresh = 0, fseq = 0;  // refreshes of this launch (block-uniform)
+  __syncthreads();
 
-  for (uint32_t it = 0; it <= a.max_iters; ++it) {
-    const uint32_t n_done = n_done0 + it;
-    const uint32_t stamp = (it % 65535u) + 1u;         // never 0: the array is cleared before the launch
-    unsigned long long tq0 = gtid == 0 ? gtimer() : 0, tq1 = 0, tq2 = 0, tq2b = 0, tq3 = 0;
-    if (dbgb) bt = gtimer();
-    // ---------------- elect the pair: every block stores its best as two self-stamped words; BLOCK 0 polls them (one
-    // reader: no contention), reduces and stores the winner, again two self-stamped words, which one thread per block
-    // polls.  Two store -> load round trips, O(blocks) L2 requests per poll round.  (First version: every block polled
-    // every block's words — 148 x 148 x 2 loads = 23.7 k sector requests per round on a handful of L2 lines, which an L2
-    // slice serves at about one per clock: 10.8 us per merge in that poll alone.  Second version: arrival counter, the
-    // last block reduces: fence + atomic + read = 7.2 us.  Found with YTTM_DBG=16.)
-    // flags: 1 = this partition is over the load limit, 2 = it ran full (update lost).
-    if (threadIdx.x == 0) {
-      const Best cb = s_cb;
-      uint32_t fl = (s_occ > a.part_limit ? 1u : 0u) | (s_povf ? 2u : 0u);
-      uint32_t x = 0, y = 0;
-      if (cb.c) {  // (x, y) from the 64-bit priority word
-        const uint32_t mx = 0xffffffffu - (uint32_t)(cb.prio >> 32), mn = 0x7fffffffu - (uint32_t)((cb.prio & 0xffffffffull) >> 1);
-        x = (cb.prio & 1ull) ? mx : mn;
-        y = (cb.prio & 1ull) ? mn : mx;
-      }
-      st_relaxed(a.blockbest + 2 * blockIdx.x, ((unsigned long long)stamp << 48) | (cb.c & BB_LOW48));
-      st_relaxed(a.blockbest + 2 * blockIdx.x + 1, ((unsigned long long)stamp << 48) | ((unsigned long long)fl << 45) |
-                                                    (cb.c ? bb_prio45(x, y) : 0ull));
-      s_out_n = 0;
+  // parked entries -> this block's partition (all threads; leaves the list empty)
+  auto flush_own = [&]() {
+    __syncthreads();
+    const uint32_t n = min(s_own_n, OWN_CAP);
+    uint32_t added = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned long long key = ownk[i];
+      uint64_t slot = ~0ull;
+      added += pair_add_at(a.tab, pbase, (uint32_t)mix64(key) & a.tab.rmask, key, ownd[i], &slot) ? 1u : 0u;
+      if (slot == ~0ull) s_povf = 1;   // this partition ran full: an update was lost (benign race: every writer stores 1)
     }
-    if (blockIdx.x == 0) {  // the reducer
-      unsigned long long bc = 0, bp = 0;   // best (count48, prio45) this thread has seen
-      uint32_t fl = 0;
+    if (added) atomicAdd(&s_occ, added);
+    __syncthreads();
+    if (threadIdx.x == 0) s_own_n = 0;
+  };
+  // the largest member of the front -> s_best (.slot = its slot in the front)
+  auto select = [&]() {
+    Best b{0, 0, 0};
+    for (uint32_t i = threadIdx.x; i < FRONT_SLOTS; i += blockDim.x) {
+      const unsigned long long c = fc[i];
+      if (c == 0 || c < b.c) continue;
+      const unsigned long long k = fk[i];
+      const Best cand{c, pair_prio((uint32_t)(k >> 32), (uint32_t)k), i};
+      if (better(cand, b)) b = cand;
+    }
+    block_best(b, s_warp, &s_best);
+  };
+  // rebuild the front from the partitions (see above); every block of this GPU runs it in the same iteration
+  auto refresh = [&]() {
+    flush_own();
+    fseq++;
+    n_refresh++;
+    unsigned long long *gdata = a.frontbuf + (size_t)gridDim.x * 16;
+    unsigned long long *mine = gdata + (size_t)blockIdx.x * FRONT_TOP * 2;
+    for (uint32_t i = threadIdx.x; i < FRONT_SLOTS; i += blockDim.x) { fk[i] = PK_EMPTY; fc[i] = 0; }
+    Best lim{~0ull, ~0ull, 0};
+    int k = 0;
+    for (; k < FRONT_TOP; k++) {
+      sweep_below(a, pbase, R, lim, s_warp, &s_tmp);
+      const Best t = s_tmp;
+      if (t.c == 0) break;   // block-uniform
+      if (threadIdx.x == 0) { st_relaxed(mine + 2 * k, t.c); st_relaxed(mine + 2 * k + 1, prio_key(t.prio)); }
+      lim = t;
+    }
+    if (threadIdx.x == 0) {
+      for (int q = k; q < FRONT_TOP; q++) { st_relaxed(mine + 2 * q, 0ull); st_relaxed(mine + 2 * q + 1, 0ull); }
+      s_focc = 0; s_refresh = 0;
+      st_release(a.frontbuf + (size_t)blockIdx.x * 16, (unsigned long long)fseq, false);   // orders the stores above
+    }
+    {
       unsigned long long t0 = 0;
-      for (unsigned j = threadIdx.x; j < gridDim.x; j += blockDim.x) {
-        unsigned long long w0, w1;
-        for (uint32_t spin = 0;; spin++) {
-          w0 = ld_relaxed(a.blockbest + 2 * j);
-          w1 = ld_relaxed(a.blockbest + 2 * j + 1);
-          if ((uint32_t)(w0 >> 48) == stamp && (uint32_t)(w1 >> 48) == stamp) break;
+      for (unsigned j = threadIdx.x; j < gridDim.x; j += blockDim.x)
+        for (uint32_t spin = 0; ld_acquire(a.frontbuf + (size_t)j * 16, false) != (unsigned long long)fseq; spin++) {
 #ifdef YT_SIMT_EMU
           emu::yield();
 #endif
@@ -839,86 +871,80 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
             else if (gtimer() - t0 > a.spin_limit_ns) loop_trap();
           }
         }
-        const unsigned long long c = w0 & BB_LOW48, pr = w1 & ((1ull << 45) - 1ull);
-        fl |= (uint32_t)(w1 >> 45) & 7u;
-        if (c > bc || (c == bc && pr > bp)) { bc = c; bp = pr; }
-      }
-      for (int o = 16; o > 0; o >>= 1) {   // warp reduce (ties cannot happen between blocks: a pair has one owner)
-        const unsigned long long c2 = __shfl_xor_sync(0xffffffffu, bc, o), p2 = __shfl_xor_sync(0xffffffffu, bp, o);
-        if (c2 > bc || (c2 == bc && p2 > bp)) { bc = c2; bp = p2; }
-      }
-      if (fl) atomicOr(&s_bflags, fl);
-      const unsigned used_warps = (min(gridDim.x, blockDim.x) + 31) >> 5;
-      if (lane == 0 && wid < used_warps) { s_warp[wid].c = bc; s_warp[wid].prio = bp; }
-      __syncthreads();
-      if (wid == 0) {
-        bc = lane < used_warps ? s_warp[lane].c : 0ull;
-        bp = lane < used_warps ? s_warp[lane].prio : 0ull;
-        for (int o = 16; o > 0; o >>= 1) {
-          const unsigned long long c2 = __shfl_xor_sync(0xffffffffu, bc, o), p2 = __shfl_xor_sync(0xffffffffu, bp, o);
-          if (c2 > bc || (c2 == bc && p2 > bp)) { bc = c2; bp = p2; }
-        }
-        if (lane == 0) {
-          s_best.c = bc; s_best.prio = bp;
-          st_relaxed(a.blockbest + 2 * gridDim.x, ((unsigned long long)stamp << 48) | bc);
-          st_relaxed(a.blockbest + 2 * gridDim.x + 1, ((unsigned long long)stamp << 48) | ((unsigned long long)(s_bflags & 7u) << 45) | bp);
-        }
-      }
-    } else if (threadIdx.x == 0) {  // one poller per block
-      unsigned long long w0, w1, t0 = 0;
-      for (uint32_t spin = 0;; spin++) {
-        w0 = ld_relaxed(a.blockbest + 2 * gridDim.x);
-        w1 = ld_relaxed(a.blockbest + 2 * gridDim.x + 1);
-        if ((uint32_t)(w0 >> 48) == stamp && (uint32_t)(w1 >> 48) == stamp) break;
-#ifdef YT_SIMT_EMU
-        emu::yield();
-#endif
-        if ((spin & 4095u) == 4095u) {
-          if (!t0) t0 = gtimer();
-          else if (gtimer() - t0 > a.spin_limit_ns) loop_trap();
-        }
-      }
-      s_best.c = w0 & BB_LOW48;
-      s_best.prio = w1 & ((1ull << 45) - 1ull);
-      s_bflags = (uint32_t)(w1 >> 45) & 7u;
     }
     __syncthreads();
-    if (gtid == 0) tq1 = gtimer();
-    if (dbgb) { const unsigned long long t = gtimer(); bacc[0] += t - bt; bt = t; }
-    const Best win = s_best;             // .prio = prio45
-    const uint32_t bflags = s_bflags, xf = s_xf;
-    // ---------------- uniform exit checks (every block of every rank evaluates the same values)
+    Best bd{0, 0, 0};   // the bound: the last pair of every list that is full (a shorter list holds its whole partition)
+    for (unsigned j = threadIdx.x; j < gridDim.x; j += blockDim.x) {
+      const unsigned long long c = ld_relaxed(gdata + ((size_t)j * FRONT_TOP + FRONT_TOP - 1) * 2);
+      const unsigned long long key = ld_relaxed(gdata + ((size_t)j * FRONT_TOP + FRONT_TOP - 1) * 2 + 1);
+      if (!c) continue;
+      const Best cand{c, pair_prio((uint32_t)(key >> 32), (uint32_t)key), 0};
+      if (better(cand, bd)) bd = cand;
+    }
+    for (unsigned e = threadIdx.x; e < gridDim.x * FRONT_TOP; e += blockDim.x) {
+      const unsigned long long c = ld_relaxed(gdata + (size_t)e * 2), key = ld_relaxed(gdata + (size_t)e * 2 + 1);
+      if (c) smem_tab_add(fk, fc, FRONT_SLOTS - 1, mix64(key), key, (long long)c, &s_focc);   // 148 x 8 < FRONT_SLOTS
+    }
+    block_best(bd, s_warp, &s_bound);
+  };
+
+  for (uint32_t it = 0; it <= a.max_iters; ++it) {
+    const uint32_t n_done = n_done0 + it;
+    unsigned long long tq0 = gtid == 0 ? gtimer() : 0, tq1 = 0, tq2 = 0, tq2b = 0, tq3 = 0;
+    if (dbgb) bt = gtimer();
+    // ---------------- uniform exit checks: the flags every block read off the last round's count words
+    const uint32_t xf = s_xf;
     {
       uint32_t stop = 0, why = 0;
-      if (bflags & 1u) why |= 1u;                                   // a partition reached the load limit: rebuild (dead keys vanish)
+      if (xf & XQF_PLIMIT) why |= 1u;                               // a partition reached the load limit: rebuild (dead keys vanish)
       if (xf & XQF_OVERFLOW) why |= 2u;                             // lost count changes: rebuild from the tokens
-      if (bflags & 2u) why |= 4u;                                   // a partition ran full: grow the table
+      if (xf & XQF_PFULL) why |= 4u;                                // a partition ran full: grow the table
       if (n_done >= a.max_total || it == a.max_iters) stop = 4;     // done (or launch budget spent)
       else if (why) stop = 2;
       else if (xf & XQF_COMPACT) stop = 3;                          // some block wants a compaction
-      else if (win.c == 0) stop = 1;                                // no pair left (bpe.cpp:1137-1145)
       if (stop) {
         if (gtid == 0) { a.ctl->stop = stop == 4 ? 0u : stop; a.ctl->stop_why = why; }
         break;
       }
     }
-    MergeOp op;
-    {
-      const uint32_t mx = 0x3fffffu - (uint32_t)(win.prio >> 23), mn = 0x3fffffu - (uint32_t)((win.prio >> 1) & 0x3fffffu);
-      op.x = (win.prio & 1ull) ? mx : mn;
-      op.y = (win.prio & 1ull) ? mn : mx;
-      op.key = pair_key(op.x, op.y);
+    // ---------------- elect the pair from the front (no communication)
+    bool fresh = false;
+    if (s_refresh || s_focc > FRONT_FILL) { refresh(); fresh = true; }
+    select();
+    if (!fresh && (s_best.c == 0 || better(s_bound, s_best))) {   // the front is exhausted
+      __syncthreads();
+      refresh();
+      select();
     }
+    const Best win = s_best;
+    if (win.c == 0) {                                               // no pair left (bpe.cpp:1137-1145)
+      if (gtid == 0) { a.ctl->stop = 1; a.ctl->stop_why = 0; }
+      break;
+    }
+    MergeOp op;
+    op.key = fk[win.slot];
+    op.x = (uint32_t)(op.key >> 32);
+    op.y = (uint32_t)op.key;
     op.z = a.first_new_id + n_done;
     if (gtid == 0) {
       a.rules[3 * n_done + 0] = op.x; a.rules[3 * n_done + 1] = op.y; a.rules[3 * n_done + 2] = op.z;
       a.rfreq[n_done] = win.c;
       a.ctl->n_done = n_done + 1;
     }
-    const bool i_own = pair_part(a.tab, mix64(op.key)) == blockIdx.x;   // the partition that holds (x, y)
-    // every occurrence of (x,y) is merged below and no deltas are emitted for it: its owner clears the count
-    if (i_own && threadIdx.x == 0) a.tab.cnts[s_cb.slot] = 0;
-    const unsigned long long tw1 = dbgt && lane == 0 ? gtimer() : 0;
+    if (gtid == 0) tq1 = gtimer();
+    if (dbgb) { const unsigned long long t = gtimer(); bacc[0] += t - bt; bt = t; }
+    // every occurrence of (x,y) is merged below and no count changes are emitted for it: the front drops it here, its
+    // owner parks the matching update of the partition (the front's count is exact)
+    if (threadIdx.x == 0) {
+      fc[win.slot] = 0;
+      s_out_n = 0;
+      if (pair_part(a.tab, mix64(op.key)) == blockIdx.x) {
+        const uint32_t q = s_own_n++;   // (only thread 0 touches the list between the drain and flush_own)
+        if (q < OWN_CAP) { ownk[q] = op.key; ownd[q] = -(long long)win.c; }
+        else { pair_add_at(a.tab, pbase, (uint32_t)mix64(op.key) & a.tab.rmask, op.key, -(long long)win.c); s_own_n = OWN_CAP; }
+      }
+    }
+    __syncthreads();
     // ---------------- apply x y -> z: count changes go to this block's segment of round + 1 (on every rank)
     const uint32_t nround = round + 1;
     XqOut xo;
@@ -1069,6 +1095,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
 #ifndef YT_SIMT_EMU
       asm volatile("fence.proxy.async;" ::: "memory");
 #endif
+    
     }
     for (int o = 16; o > 0; o >>= 1) dead += __shfl_xor_sync(0xffffffffu, dead, o);
     if (lane == 0 && dead) atomicAdd(&s_dead, dead);
@@ -1079,89 +1106,90 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       const uint32_t n = s_out_n;
       uint32_t word = n > a.xq.seg_cap ? (a.xq.seg_cap | XQ_CNT_OVF) : n;
       if (my_dead * 4 > my_slots && my_slots > a.dead_min_slots) word |= XQ_CNT_COMPACT;
+      if (s_occ > a.part_limit) word |= XQ_CNT_PLIMIT;   // state of the partition as of the last flush
+      if (s_povf) word |= XQ_CNT_PFULL;
       // no fence: the entries carry their own stamps, the count word may overtake them
       const unsigned long long cw = ((unsigned long long)nround << 32) | word;
 #pragma unroll
       for (int d = 0; d < XQ_MAX_WORLD; d++)
         if ((uint32_t)d < a.xq.world) st_relaxed_any(&xq_hdr(a.xq, (uint32_t)d, nround & 1u, a.xq.me)->counts[blockIdx.x * XQ_CNT_STRIDE], cw, sys);
-      s_xf = 0; s_bflags = 0; s_sweep = 0;   // accumulators of the phases below
-      if (dbgt) atomicMax(&a.ctl->blk[it & 1][0], gtimer() - tw1);
+      s_xf = 0;   // accumulator of the poll below
     }
     if (gtid == 0) tq2 = gtimer();
     if (dbgb) { const unsigned long long t = gtimer(); bacc[1] += t - bt; bt = t; }
     round = nround;
-    // the owner of the consumed pair sweeps its partition while the others finish their apply phase (the sweep sees
-    // the table BEFORE this round's changes; they are folded in below like everybody's)
-    __syncthreads();
-    if (i_own) sweep_partition(a, pbase, R, s_warp, &s_cb);
+    // ---------------- while the other blocks finish their apply phase: the parked entries of the previous round (and
+    // the consumed pair) go into this block's partition
+    flush_own();
     // ---------------- drain: the count changes of this merge, from every block of every GPU
-    const unsigned long long tw2 = dbgt && lane == 0 ? gtimer() : 0;
     xq_poll_counts(a, round, false, s_pref, &s_xf);
     if (gtid == 0) tq2b = gtimer();
     if (dbgb) { const unsigned long long t = gtimer(); bacc[2] += t - bt; bt = t; }
-    Touched tch;
-    tch.n = 0; tch.dropped = 0;
-    xq_drain(a, round, s_pref, s_scan, &s_occ, tch);
-    if (tch.n > (uint32_t)DRAIN_KEEP) s_sweep = 1;   // (benign race: every writer stores 1)
-    if (tch.dropped) s_povf = 1;                      // this partition ran full: an update was lost
-    __syncthreads();  // the partition is up to date (the drain's atomics went to L2 before the barrier)
-    if (dbgb) { const unsigned long long t = gtimer(); bacc[3] += t - bt; bt = t; }
+    xq_prefix(a, s_pref, s_scan);
     {
-      // ---- cached arg-max: only touched slots can have changed.  Final counts are re-read (a slot may have
-      // received several entries); a lowered best invalidates the cache.
-      const Best cb = s_cb;
-      Best cand{0, 0, 0};
-      bool lowered = false;
-      const uint32_t nt = tch.n < (uint32_t)DRAIN_KEEP ? tch.n : (uint32_t)DRAIN_KEEP;
-#pragma unroll
-      for (int q = 0; q < DRAIN_KEEP; q++) {
-        if ((uint32_t)q >= nt || tch.slot[q] == ~0ull) continue;
-        const unsigned long long c = __ldcg(a.tab.cnts + tch.slot[q]);
-        if (tch.slot[q] == cb.slot && cb.c && c < cb.c) lowered = true;
-        if (c) {
-          Best v{c, pair_prio((uint32_t)(tch.key[q] >> 32), (uint32_t)tch.key[q]), tch.slot[q]};
-          if (better(v, cand)) cand = v;
+      const uint32_t total = s_pref[a.xq.world * a.xq.nblocks];
+      uint32_t added = 0;
+      for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+        unsigned long long key = 0;
+        long long delta = 0;
+        xq_entry(a, round, s_pref, i, &key, &delta);
+        const uint64_t hh = mix64(key);
+        const uint32_t fs = smem_tab_find(fk, FRONT_SLOTS - 1, hh, key);
+        if (fs != ~0u) atomicAdd(fc + fs, (unsigned long long)delta);
+        else if ((uint32_t)(key >> 32) == op.z || (uint32_t)key == op.z) {   // a pair of the new token: cannot be in the front yet
+          if (!smem_tab_add(nk, nc, NEWP_SLOTS - 1, hh, key, delta, &s_nocc)) s_refresh = 1;   // too many: the refresh finds them
+        }
+        if (pair_part(a.tab, hh) == blockIdx.x) {
+          const uint32_t q = atomicAdd(&s_own_n, 1u);
+          if (q < OWN_CAP) { ownk[q] = key; ownd[q] = delta; }
+          else {
+            uint64_t slot = ~0ull;
+            added += pair_add_at(a.tab, pbase, (uint32_t)hh & a.tab.rmask, key, delta, &slot) ? 1u : 0u;
+            if (slot == ~0ull) s_povf = 1;
+          }
         }
       }
-      if (lowered) s_sweep = 1;
-      cand = warp_best(cand);
-      if (lane == 0) s_warp[wid] = cand;
-      __syncthreads();
-      if (s_sweep) {
-        sweep_partition(a, pbase, R, s_warp, &s_cb);
-        if (threadIdx.x == 0) { s_sweep = 0; n_sweeps++; }
-        if (dbgb) bacc[5] += 1;
-      } else if (wid == 0) {
-        Best v = lane < nwarp ? s_warp[lane] : Best{0, 0, 0};
-        v = warp_best(v);
-        if (lane == 0 && better(v, cb)) s_cb = v;
+      if (added) atomicAdd(&s_occ, added);
+    }
+    __syncthreads();
+    if (dbgb) { const unsigned long long t = gtimer(); bacc[3] += t - bt; bt = t; }
+    // ---- the new token's pairs: those not below the bound join the front
+    if (s_nocc) {   // block-uniform (read after the barrier)
+      const Best bd = s_bound;
+      for (uint32_t i = threadIdx.x; i < NEWP_SLOTS; i += blockDim.x) {
+        const unsigned long long k = nk[i];
+        if (k == PK_EMPTY) continue;
+        const unsigned long long c = nc[i];
+        nk[i] = PK_EMPTY; nc[i] = 0;
+        if ((long long)c <= 0) continue;
+        const Best cand{c, pair_prio((uint32_t)(k >> 32), (uint32_t)k), 0};
+        if (better(bd, cand)) continue;
+        if (!smem_tab_add(fk, fc, FRONT_SLOTS - 1, mix64(k), k, (long long)c, &s_focc)) s_refresh = 1;
       }
+      __syncthreads();
+      if (threadIdx.x == 0) s_nocc = 0;
     }
     __syncthreads();
     if (dbgb) { const unsigned long long t = gtimer(); bacc[4] += t - bt; bt = t; }
-    if (dbgt && lane == 0) atomicMax(&s_tpre, gtimer() - tw2);
     if (gtid == 0) {
       tq3 = gtimer();
-      if (dbgt) {  // diagnostics only: these global round trips sit on block 0's path
-        tacc5 += __ldcg(&a.ctl->blk[it & 1][0]);
-        a.ctl->blk[it & 1][0] = 0;
-        tacc7 += s_tpre;
-        s_tpre = 0;
-      }
-      tacc2 += tq1 - tq0;   // publish + poll of the blocks' bests ("barrier 1" + winner reduce)
+      tacc2 += tq1 - tq0;   // election from the front (+ refreshes)
       tacc3 += tq2 - tq1;   // apply
-      tacc4 += tq2b - tq2;  // wait for the slowest block's count word ("barrier 2"; the owner's sweep hides here)
-      tacc0 += tq3 - tq2b;  // drain + cache update
+      tacc4 += tq2b - tq2;  // partition update + wait for the slowest block's count word
+      tacc0 += tq3 - tq2b;  // drain + new pairs
       titers += 1;
     }
   }
-  if (threadIdx.x == 0 && n_sweeps) atomicAdd(&a.ctl->n_sweeps, (unsigned long long)n_sweeps);
-  if (dbgb && a.dbg_blk)
+  flush_own();   // every exit path: the partition is complete again
+  if (threadIdx.x == 0 && s_povf) atomicExch(a.tab.overflow, 1u);
+  if (gtid == 0 && n_refresh) atomicAdd(&a.ctl->n_sweeps, (unsigned long long)n_refresh);
+  if (dbgb && a.dbg_blk) {
+    bacc[5] = n_refresh;
     for (int k = 0; k < 6; k++) a.dbg_blk[8 * blockIdx.x + k] += bacc[k];
+  }
   if (gtid == 0) {
     a.ctl->xq_round = round;
     a.ctl->t_phase[0] += tacc0; a.ctl->t_phase[2] += tacc2; a.ctl->t_phase[3] += tacc3; a.ctl->t_phase[4] += tacc4;
-    a.ctl->t_phase[5] += tacc5; a.ctl->t_phase[7] += tacc7;
     a.ctl->iters += titers;
   }
   // resident tiles go back to HBM on every exit path
@@ -1172,6 +1200,8 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   }
 }
 __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(LoopArgs a) { merge_loop_body(a); }
+// the same loop compiled for at most 512 threads per block (128 registers per thread instead of 64)
+__global__ void __launch_bounds__(512, 1) merge_loop_kernel_512(LoopArgs a) { merge_loop_body(a); }
 
 // ---- exchange rounds outside the loop (multi-GPU table build): one block per partition -----------
 // xq_publish_table_kernel: block b enumerates the live (key, count) pairs of partition b of a SNAPSHOT of the local
@@ -1227,9 +1257,7 @@ __global__ void __launch_bounds__(256) xq_absorb_kernel(LoopArgs a, uint32_t rou
   if (threadIdx.x == 0) { s_occ = 0; s_acc = 0; }
   __syncthreads();
   xq_poll_counts(a, round, true, s_pref, &s_acc);
-  Touched tch;
-  tch.n = 0; tch.dropped = 0;
-  xq_drain(a, round, s_pref, s_scan, &s_occ, tch);
+  xq_drain(a, round, s_pref, s_scan, &s_occ);
   __syncthreads();
   if (threadIdx.x == 0) {
     if (s_acc) atomicOr(&a.ctl->xq_flags, s_acc);

@@ -560,7 +560,7 @@ static uint64_t pair_cap_floor() {
 // Launch geometry of the cooperative merge loop: one block per SM, all co-resident, with (almost) all of the SM's
 // shared memory as the tile buffer.  Fixed per context before the first table is built, because the pair table has one
 // partition per block.
-constexpr int LOOP_SMEM_HEAD = (XQ_MAX_WORLD * XQ_MAX_BLOCKS + 4) * 4 + 2 * CLAIM_WORDS * 4;  // segment prefix + claim bitmaps
+constexpr int LOOP_SMEM_HEAD = (XQ_MAX_WORLD * XQ_MAX_BLOCKS + 4) * 4 + 2 * CLAIM_WORDS * 4 + (int)LOOP_FRONT_BYTES;  // segment prefix + claim bitmaps + front
 int ensure_loop_geometry(yttm_ctx *c) {
   if (c->loop_blocks) return 0;
   int optin = 0;
@@ -588,12 +588,14 @@ int ensure_loop_geometry(yttm_ctx *c) {
     c->loop_stream_tok_cap = (per_stage - c->loop_stream_word_cap) & ~3u;
   }
   YT_CUDA(c, cudaFuncSetAttribute(merge_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+  YT_CUDA(c, cudaFuncSetAttribute(merge_loop_kernel_512, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
   int threads = 1024, per_sm = 0;
-  if (const char *e = std::getenv("YTTM_LOOP_THREADS")) threads = std::atoi(e);
-  YT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_loop_kernel, threads, dyn));
+  if (const char *e = std::getenv("YTTM_LOOP_THREADS")) threads = std::max(64, std::min(1024, std::atoi(e) / 32 * 32));
+  YT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, threads <= 512 ? merge_loop_kernel_512 : merge_loop_kernel, threads, dyn));
   if (per_sm < 1) YT_FAIL(c, "merge_loop_kernel does not fit on an SM");
   c->loop_threads = threads;
-  int blocks = std::min(c->n_sm, XQ_MAX_BLOCKS);
+  // (a refresh of the front takes FRONT_TOP pairs from every block's partition and must leave room for new pairs)
+  int blocks = std::min(std::min(c->n_sm, XQ_MAX_BLOCKS), (int)(FRONT_FILL / FRONT_TOP));
   // A/B knob: fewer blocks make the two grid barriers and the winner reduce cheaper and the per-block partition /
   // tile larger (the tile planner falls back to STREAMING by itself if the words no longer fit)
   if (const char *e = std::getenv("YTTM_LOOP_BLOCKS")) blocks = std::max(1, std::min(blocks, std::atoi(e)));
@@ -875,7 +877,7 @@ void yttm_ctx_destroy(yttm_ctx *c) {
   cudaStreamSynchronize(c->stream);
   ytc::DevBuf *bufs[] = {&c->text_buf, &c->hist, &c->cp2id, &c->wkey, &c->wcnt, &c->wpos, &c->wfreq, &c->wlen,
                          &c->scan_tmp, &c->counters, &c->tok[0], &c->tok[1], &c->off[0], &c->off[1], &c->freq[0],
-                         &c->freq[1], &c->pkey, &c->pcnt, &c->scratch_key, &c->scratch_cnt, &c->ctl, &c->blockbest, &c->tiles, &c->defer,
+                         &c->freq[1], &c->pkey, &c->pcnt, &c->scratch_key, &c->scratch_cnt, &c->ctl, &c->frontbuf, &c->tiles, &c->defer,
                          &c->d_rules, &c->d_rfreq, &c->xq_arrive, &c->xq_buf};
   for (int d = 0; d < 8; d++)
     if (c->xq_peer_ipc[d] && c->xq_peer[d]) { cudaIpcCloseMemHandle(c->xq_peer[d]); c->xq_peer[d] = nullptr; }
@@ -1401,7 +1403,7 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
   *n_done_out = 0;
   if (max_merges == 0) return 0;
   if (ensure_loop_geometry(c)) return 1;
-  YT_CUDA(c, c->blockbest.reserve(((size_t)c->loop_blocks * 2 + 4) * 8));  // per-block bests, winner words, arrival counter
+  YT_CUDA(c, c->frontbuf.reserve(front_buf_words((uint32_t)c->loop_blocks) * 8));  // gather buffer of the front refreshes
   if (first_new_id + (uint64_t)max_merges >= BB_ID_LIMIT) YT_FAIL(c, "yttm_train_run: token ids beyond 2^22 are not supported by the merge loop");
   YT_CUDA(c, c->d_rules.reserve((size_t)max_merges * 12 + 16));
   YT_CUDA(c, c->d_rfreq.reserve((size_t)max_merges * 8 + 16));
@@ -1425,7 +1427,7 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
     a.n_words = c->n_words;
     a.tab = tab_of(c);
     a.ctl = ctl;
-    a.blockbest = c->blockbest.as<unsigned long long>();
+    a.frontbuf = c->frontbuf.as<unsigned long long>();
     a.rules = c->d_rules.as<uint32_t>();
     a.rfreq = c->d_rfreq.as<unsigned long long>();
     a.first_new_id = first_new_id;
@@ -1440,11 +1442,11 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
     }
     a.dead_min_slots = 4096;
     if (const char *e = std::getenv("YTTM_DEAD_MIN_SLOTS")) a.dead_min_slots = (uint32_t)std::max(0, std::atoi(e));
-    YT_CUDA(c, cudaMemsetAsync(c->blockbest.p, 0, ((size_t)c->loop_blocks * 2 + 4) * 8, c->stream));  // stamps restart at 1
+    YT_CUDA(c, cudaMemsetAsync(c->frontbuf.p, 0, front_buf_words((uint32_t)c->loop_blocks) * 8, c->stream));  // refresh numbers restart at 1
 #ifndef YT_SIMT_EMU
     void *args[] = {&a};
-    YT_CUDA(c, cudaLaunchCooperativeKernel((void *)merge_loop_kernel, dim3(c->loop_blocks), dim3(c->loop_threads), args,
-                                           (size_t)c->loop_smem, c->stream));
+    YT_CUDA(c, cudaLaunchCooperativeKernel(c->loop_threads <= 512 ? (void *)merge_loop_kernel_512 : (void *)merge_loop_kernel,
+                                           dim3(c->loop_blocks), dim3(c->loop_threads), args, (size_t)c->loop_smem, c->stream));
 #else  // tests/emul/simt: every block on its own OS thread, grid.sync() = pthread barrier
     emu::launch_cooperative((unsigned)c->loop_blocks, (unsigned)c->loop_threads, (size_t)c->loop_smem,
                             [=]() { merge_loop_kernel(a); });
@@ -1477,19 +1479,19 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
       std::vector<unsigned long long> blk((size_t)c->loop_blocks * 8);
       YT_CUDA(c, cudaMemcpyAsync(blk.data(), c->scratch_cnt.p, blk.size() * 8, cudaMemcpyDeviceToHost, c->stream));
       YT_CUDA(c, cudaStreamSynchronize(c->stream));
-      static const char *nm[] = {"poll_bests", "apply", "wait_counts+owner_sweep", "drain", "cache_update(+sweep)", "sweeps"};
+      static const char *nm[] = {"elect(+refresh)", "apply", "partition_update+wait_counts", "drain", "new_pairs", "refreshes"};
       const double it = (double)h.iters;
       for (int k = 0; k < 6; k++) {
         double mn = 1e30, mx = 0, sum = 0;
         int imn = 0, imx = 0;
         for (int b = 0; b < c->loop_blocks; b++) {
-          const double v = (double)blk[(size_t)b * 8 + k] / it * (k == 5 ? 1.0 : 1e-3);
+          const double v = (double)blk[(size_t)b * 8 + k] / (k == 5 ? 1.0 : it) * (k == 5 ? 1.0 : 1e-3);
           sum += v;
           if (v < mn) { mn = v; imn = b; }
           if (v > mx) { mx = v; imx = b; }
         }
         std::fprintf(stderr, "YTTM_DBG16 %-24s per merge: mean %8.3f  min %8.3f (block %d)  max %8.3f (block %d)%s\n", nm[k],
-                     sum / c->loop_blocks, mn, imn, mx, imx, k == 5 ? "  [count]" : " us");
+                     sum / c->loop_blocks, mn, imn, mx, imx, k == 5 ? "  [count per run]" : " us");
       }
     }
   }
