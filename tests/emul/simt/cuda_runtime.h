@@ -97,6 +97,14 @@ inline unsigned __ballot_sync(unsigned, int pred) {
     if (((live >> i) & 1u) && g[i]) m |= 1u << i;
   return m;
 }
+inline unsigned __reduce_max_sync(unsigned, unsigned v) {
+  uint32_t live;
+  const uint64_t *g = emu::warp_gather((uint64_t)v, &live);
+  unsigned m = 0;
+  for (int i = 0; i < 32; i++)
+    if (((live >> i) & 1u) && (unsigned)g[i] > m) m = (unsigned)g[i];
+  return m;
+}
 inline void __syncwarp(unsigned = 0xffffffffu) { uint32_t live; emu::warp_gather(0, &live); }
 inline void __syncthreads() { emu::block_sync(); }
 inline int __syncthreads_or(int pred) {  // three rendezvous: previous readers are gone, the flag is cleared, all have voted

@@ -16,19 +16,19 @@
 //   * every block drains ALL segments of ALL GPUs, keeps the entries whose key it owns and
 //     applies them to its partition; every GPU holds the full table, so every GPU elects the
 //     same pair without a second exchange;
-//   * the arg-max of a partition (exact, under MergeCandidate::operator<, bpe.cpp:110-126) is
-//     CACHED per block and maintained from the drained entries (only touched slots can change);
-//     a full sweep of the partition happens at launch and after the block's best was consumed or
-//     lowered.
-// There is NO grid barrier in the loop.  The two synchronisation points of a merge are words
-// that carry their own stamp: a block ends its apply phase by storing "round | flags | entries"
-// for its segment (release); a block starts its drain by polling those words of all blocks (of
-// all GPUs) until they carry the round (acquire) — barrier and count fetch are one round trip.
-// Likewise every block publishes its cached best as two stamped 64-bit words and polls the
-// others': barrier and winner reduction are one round trip.  (Measured on B200, 100 MB Zipf
-// corpus: two cg grid.sync() + separate fetches cost 14 dependent L2 round trips = 18.7 us per
-// merge, profiles/r02_merge_loop_phases.md.)  The launch is still cooperative: all blocks must
-// be co-resident for the polling to terminate.
+//   * the pair of a merge is elected WITHOUT an exchange: every block keeps an identical copy of the leading pairs
+//     (the "front", exact counts, shared memory) and maintains it from the entries it drains anyway; the front is
+//     rebuilt from the partitions every few hundred merges (see "the replicated FRONT" below);
+//   * a block parks the drained entries it owns in shared memory and adds them to its partition while it waits for
+//     the other blocks' next count words, so the table's L2 round trips are off the critical path of a merge.
+// There is NO grid barrier in the loop and ONE store -> load hop per merge: a block ends its apply phase by storing
+// "round | flags | entries" for its segment; a block starts its drain by polling those words of all blocks (of all
+// GPUs) until they carry the round — barrier and count fetch are one round trip; the entries carry their own stamps
+// (no fence).  History, measured on B200 with a 100 MB Zipf corpus (profiles/r02_merge_loop_phases.md): two cg
+// grid.sync() + separate fetches 18.7 us per merge; stamped words with every block polling every block's best 17.3 us
+// (the 23.7 k sector requests of a poll round queue at a few L2 slices); last-arriver / block-0 reducer 16.4 - 16.9 us
+// (two more hops and the skew of the owner's partition sweep); replicated front: see DESIGN.md section 7.
+// The launch is still cooperative: all blocks must be co-resident for the polling to terminate.
 // Words live in TILES: RESIDENT mode keeps tile b in the shared memory of block b for the whole
 // launch; STREAMING mode (token buffer larger than the chip's shared memory) stages tiles through
 // a TMA ring every merge (see below).
@@ -39,10 +39,10 @@ constexpr int SWEEP_UNROLL = 8;  // partition sweep: table counts in flight per 
 // ---- exchange buffer ("xq") --------------------------------------------------------------------
 // Every rank owns one region: [parity 0/1][sender 0..world-1]{ XqHdr, entries[nblocks][seg_cap] }.
 // Round r (r = 1, 2, ...) uses parity r & 1.  Block b of sender s writes its entries into segment
-// [r & 1][s][b] of EVERY rank's region (its own included) and then, after a fence, the count word
-// of that segment: (r << 32) | flags | entries.  Double buffering suffices: a block can write
-// round r + 2 only after it has seen every block's best of iteration r + 2, which those blocks
-// publish after they have finished draining round r.
+// [r & 1][s][b] of EVERY rank's region (its own included) and then the count word of that segment:
+// (r << 32) | flags | entries.  Double buffering suffices: a block writes round r + 2 only after it has
+// seen every block's count word of round r + 1 (it drains round r + 1 before it can elect the next pair),
+// and a block stores that word after its apply phase r + 1, i.e. after it has finished draining round r.
 constexpr int XQ_MAX_WORLD = 8;
 constexpr int XQ_MAX_BLOCKS = 256;
 constexpr uint32_t XQF_COMPACT = 1u;     // some block wants a compaction of its packed words
@@ -144,15 +144,8 @@ __device__ __forceinline__ void fence_scope(bool sys) {
 #endif
 }
 
-// A block's best pair as two self-stamped 64-bit words (no barrier, no third word to order):
-//   w0 = stamp16 | count48          w1 = stamp16 | flags3 | prio45
-// prio45 orders like pair_prio (smaller max(x,y), then smaller min, then larger x) for ids < 2^22.
+// Token ids must fit 22 bits (the packed exchange entries below).
 constexpr uint32_t BB_ID_LIMIT = 1u << 22;
-constexpr unsigned long long BB_LOW48 = 0xffffffffffffull;
-__device__ __forceinline__ unsigned long long bb_prio45(uint32_t x, uint32_t y) {
-  const uint32_t mx = x > y ? x : y, mn = x > y ? y : x;
-  return ((unsigned long long)(0x3fffffu - mx) << 23) | ((unsigned long long)(0x3fffffu - mn) << 1) | (x >= y ? 1ull : 0ull);
-}
 
 // Exchange ENTRIES are self-stamped too (the scheme of NCCL's LL protocol): an entry is two 64-bit words, each carrying
 // the low bits of its round, so neither the producer needs a fence between its entries and its count word nor the
@@ -663,7 +656,8 @@ constexpr uint32_t FRONT_FILL = 1280;    // members that trigger a refresh (dead
 constexpr uint32_t NEWP_SLOTS = 1024;    // the round's pairs with the new token, aggregated before they meet the bound
 constexpr uint32_t OWN_CAP = 512;        // parked entries of one round (more: added to the partition at once)
 constexpr int FRONT_TOP = 8;             // pairs a partition contributes to a refresh
-constexpr size_t LOOP_FRONT_BYTES = ((size_t)FRONT_SLOTS * 2 + NEWP_SLOTS * 2 + OWN_CAP * 2) * 8;
+constexpr int XQ_INLINE = 4;             // entries of a segment its polling thread handles on its own
+constexpr size_t LOOP_FRONT_BYTES = ((size_t)FRONT_SLOTS * 2 + NEWP_SLOTS * 2 + OWN_CAP * 2) * 8 + (size_t)NEWP_SLOTS * 4;
 // global gather buffer of a refresh: [nblocks flag words, 128 bytes apart][nblocks x FRONT_TOP x (count, key)]
 YT_HD size_t front_buf_words(uint32_t nblocks) { return (size_t)nblocks * 16 + (size_t)nblocks * FRONT_TOP * 2; }
 
@@ -678,15 +672,19 @@ __device__ __forceinline__ uint32_t smem_tab_find(const unsigned long long *keys
   }
   return ~0u;
 }
-// insert-or-add; false: the table is full
+// insert-or-add; false: the table is full.  list (optional): the slots taken, in order of arrival (mask + 1 places)
 __device__ __forceinline__ bool smem_tab_add(unsigned long long *keys, unsigned long long *cnts, uint32_t mask, uint64_t hh,
-                                             unsigned long long key, long long delta, uint32_t *occ) {
+                                             unsigned long long key, long long delta, uint32_t *occ, uint32_t *list = nullptr) {
   uint32_t i = smem_home(hh, mask);
   for (uint32_t p = 0; p <= mask; p++, i = (i + 1) & mask) {
     unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(keys + i);
     if (k == PK_EMPTY) {
       k = atomicCAS(keys + i, PK_EMPTY, key);
-      if (k == PK_EMPTY) { atomicAdd(occ, 1u); k = key; }
+      if (k == PK_EMPTY) {
+        const uint32_t q = atomicAdd(occ, 1u);
+        if (list) list[q] = i;
+        k = key;
+      }
     }
     if (k == key) { atomicAdd(cnts + i, (unsigned long long)delta); return true; }
   }
@@ -707,6 +705,32 @@ __device__ __forceinline__ void block_best(Best b, Best *s_warp, Best *s_out) { 
     if (lane == 0) *s_out = v;
   }
   __syncthreads();
+}
+// Warp arg-max of (count, priority) with four redux.sync instead of thirty shuffles; .slot must fit 32 bits.
+__device__ __forceinline__ Best warp_best_redux(Best v) {
+  const unsigned full = 0xffffffffu;
+  bool ok = true;
+  uint32_t m = __reduce_max_sync(full, (uint32_t)(v.c >> 32));
+  ok = (uint32_t)(v.c >> 32) == m;
+  uint32_t m2 = __reduce_max_sync(full, ok ? (uint32_t)v.c : 0u);
+  ok = ok && (uint32_t)v.c == m2;
+  const unsigned long long c = ((unsigned long long)m << 32) | m2;
+  m = __reduce_max_sync(full, ok ? (uint32_t)(v.prio >> 32) : 0u);
+  ok = ok && (uint32_t)(v.prio >> 32) == m;
+  m2 = __reduce_max_sync(full, ok ? (uint32_t)v.prio : 0u);
+  ok = ok && (uint32_t)v.prio == m2;
+  const unsigned who = __ballot_sync(full, ok);   // never empty: the lanes that hold the maximum
+  const uint32_t slot = __shfl_sync(full, (uint32_t)v.slot, __ffs(who) - 1);
+  return Best{c, c ? ((unsigned long long)m << 32) | m2 : 0ull, slot};
+}
+// Block arg-max with ONE barrier: every warp reduces the per-warp results again, every thread returns the result.
+// s_warp must not be written again before another block barrier.
+__device__ __forceinline__ Best block_best_all(Best b, Best *s_warp) {
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  b = warp_best_redux(b);
+  if (lane == 0) s_warp[wid] = b;
+  __syncthreads();
+  return warp_best_redux(lane < nwarp ? s_warp[lane] : Best{0, 0, 0});
 }
 // The largest pair of this block's partition that is strictly below `lim` (all threads; counts and keys of
 // SWEEP_UNROLL slots per thread in flight, no dependent loads).  Result in *s_out; s_warp: 32 Best of scratch.
@@ -733,12 +757,12 @@ __device__ __forceinline__ void sweep_below(const LoopArgs &a, uint64_t pbase, u
 
 __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   __shared__ Best s_warp[32];
-  __shared__ Best s_best, s_bound, s_tmp;   // the elected pair / the bound of the front / scratch of a refresh
+  __shared__ Best s_bound, s_tmp;   // the bound of the front / scratch of a refresh
   __shared__ unsigned long long s_dead;
   __shared__ uint32_t s_defer_n, s_direct, s_out_n, s_occ, s_xf, s_povf, s_focc, s_nocc, s_own_n, s_refresh, s_scan[33];
   const bool sys = a.xq.world > 1;
   // dynamic shared memory: [segment prefix: XQ_MAX_WORLD * XQ_MAX_BLOCKS + 4 words][claim bitmaps][front keys, counts]
-  // [new-pair keys, counts][parked keys, deltas][tile tokens][tile offsets][word frequencies]
+  // [new-pair keys, counts][parked keys, deltas][new-pair slot list][tile tokens][tile offsets][word frequencies]
   uint32_t *s_pref = yt_dyn_smem;
   uint32_t *s_claim = s_pref + (XQ_MAX_WORLD * XQ_MAX_BLOCKS + 4);  // 2 bitmaps of CLAIM_WORDS x 32 flags
   unsigned long long *fk = reinterpret_cast<unsigned long long *>(s_claim + 2 * CLAIM_WORDS);
@@ -747,7 +771,8 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   unsigned long long *nc = nk + NEWP_SLOTS;
   unsigned long long *ownk = nc + NEWP_SLOTS;
   long long *ownd = reinterpret_cast<long long *>(ownk + OWN_CAP);
-  uint32_t *stok = reinterpret_cast<uint32_t *>(ownd + OWN_CAP);
+  uint32_t *nlist = reinterpret_cast<uint32_t *>(ownd + OWN_CAP);   // slots of nk taken in this round
+  uint32_t *stok = nlist + NEWP_SLOTS;
   uint32_t *soff = stok + a.smem_tok_cap;
   // RESIDENT only: word frequencies behind the offsets (8-byte aligned: both caps are even)
   unsigned long long *sfreq = reinterpret_cast<unsigned long long *>(soff + a.smem_word_cap + 2);
@@ -810,10 +835,13 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   uint32_t n_refresh = 0, fseq = 0;  // refreshes of this launch (block-uniform)
   __syncthreads();
 
-  // parked entries -> this block's partition (all threads; leaves the list empty)
+  // parked entries -> this block's partition (all threads; leaves the list empty).  The list counter s_own_n only grows:
+  // entry q sits at place q - own_base (no reset, hence no barrier between a flush and the next round's parking).
+  uint32_t own_base = 0;
   auto flush_own = [&]() {
     __syncthreads();
-    const uint32_t n = min(s_own_n, OWN_CAP);
+    const uint32_t end = s_own_n, n = min(end - own_base, OWN_CAP);
+    own_base = end;
     uint32_t added = 0;
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
       const unsigned long long key = ownk[i];
@@ -823,9 +851,8 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     }
     if (added) atomicAdd(&s_occ, added);
     __syncthreads();
-    if (threadIdx.x == 0) s_own_n = 0;
   };
-  // the largest member of the front -> s_best (.slot = its slot in the front)
+  // the largest member of the front (.slot = its slot in the front), in every thread; one block barrier
   auto select = [&]() {
     Best b{0, 0, 0};
     for (uint32_t i = threadIdx.x; i < FRONT_SLOTS; i += blockDim.x) {
@@ -835,7 +862,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       const Best cand{c, pair_prio((uint32_t)(k >> 32), (uint32_t)k), i};
       if (better(cand, b)) b = cand;
     }
-    block_best(b, s_warp, &s_best);
+    return block_best_all(b, s_warp);
   };
   // rebuild the front from the partitions (see above); every block of this GPU runs it in the same iteration
   auto refresh = [&]() {
@@ -910,13 +937,11 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     // ---------------- elect the pair from the front (no communication)
     bool fresh = false;
     if (s_refresh || s_focc > FRONT_FILL) { refresh(); fresh = true; }
-    select();
-    if (!fresh && (s_best.c == 0 || better(s_bound, s_best))) {   // the front is exhausted
-      __syncthreads();
+    Best win = select();
+    if (!fresh && (win.c == 0 || better(s_bound, win))) {   // the front is exhausted
       refresh();
-      select();
+      win = select();
     }
-    const Best win = s_best;
     if (win.c == 0) {                                               // no pair left (bpe.cpp:1137-1145)
       if (gtid == 0) { a.ctl->stop = 1; a.ctl->stop_why = 0; }
       break;
@@ -939,9 +964,9 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       fc[win.slot] = 0;
       s_out_n = 0;
       if (pair_part(a.tab, mix64(op.key)) == blockIdx.x) {
-        const uint32_t q = s_own_n++;   // (only thread 0 touches the list between the drain and flush_own)
+        const uint32_t q = s_own_n++ - own_base;   // (only thread 0 touches the list between the drain and flush_own)
         if (q < OWN_CAP) { ownk[q] = op.key; ownd[q] = -(long long)win.c; }
-        else { pair_add_at(a.tab, pbase, (uint32_t)mix64(op.key) & a.tab.rmask, op.key, -(long long)win.c); s_own_n = OWN_CAP; }
+        else pair_add_at(a.tab, pbase, (uint32_t)mix64(op.key) & a.tab.rmask, op.key, -(long long)win.c);
       }
     }
     __syncthreads();
@@ -1121,32 +1146,91 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     // ---------------- while the other blocks finish their apply phase: the parked entries of the previous round (and
     // the consumed pair) go into this block's partition
     flush_own();
-    // ---------------- drain: the count changes of this merge, from every block of every GPU
-    xq_poll_counts(a, round, false, s_pref, &s_xf);
     if (gtid == 0) tq2b = gtimer();
     if (dbgb) { const unsigned long long t = gtimer(); bacc[2] += t - bt; bt = t; }
-    xq_prefix(a, s_pref, s_scan);
+    // ---------------- drain: the count changes of this merge, from every block of every GPU.  Thread j polls the count
+    // word of segment j (barrier and count fetch in one) and, when the segment is short, fetches and handles its entries
+    // right away — no block barrier sits between the arrival of a count word and the loads of its entries; longer
+    // segments (the first rounds of a run) are shared by the whole block afterwards.
     {
-      const uint32_t total = s_pref[a.xq.world * a.xq.nblocks];
       uint32_t added = 0;
-      for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
-        unsigned long long key = 0;
-        long long delta = 0;
-        xq_entry(a, round, s_pref, i, &key, &delta);
+      auto take = [&](unsigned long long key, long long delta) {
         const uint64_t hh = mix64(key);
         const uint32_t fs = smem_tab_find(fk, FRONT_SLOTS - 1, hh, key);
         if (fs != ~0u) atomicAdd(fc + fs, (unsigned long long)delta);
         else if ((uint32_t)(key >> 32) == op.z || (uint32_t)key == op.z) {   // a pair of the new token: cannot be in the front yet
-          if (!smem_tab_add(nk, nc, NEWP_SLOTS - 1, hh, key, delta, &s_nocc)) s_refresh = 1;   // too many: the refresh finds them
+          if (!smem_tab_add(nk, nc, NEWP_SLOTS - 1, hh, key, delta, &s_nocc, nlist)) s_refresh = 1;   // too many: the refresh finds them
         }
         if (pair_part(a.tab, hh) == blockIdx.x) {
-          const uint32_t q = atomicAdd(&s_own_n, 1u);
+          const uint32_t q = atomicAdd(&s_own_n, 1u) - own_base;
           if (q < OWN_CAP) { ownk[q] = key; ownd[q] = delta; }
           else {
             uint64_t slot = ~0ull;
             added += pair_add_at(a.tab, pbase, (uint32_t)hh & a.tab.rmask, key, delta, &slot) ? 1u : 0u;
             if (slot == ~0ull) s_povf = 1;
           }
+        }
+      };
+      const uint32_t nseg = a.xq.world * a.xq.nblocks, parity = round & 1u, stamp = round % XQ_STAMP_MOD;
+      uint32_t flags = 0, big = 0;
+      unsigned long long t0 = 0;
+      for (uint32_t j = threadIdx.x; j < nseg; j += blockDim.x) {
+        const uint32_t sd = j / a.xq.nblocks, b = j - sd * a.xq.nblocks;
+        const unsigned long long *w = &xq_hdr(a.xq, a.xq.me, parity, sd)->counts[b * XQ_CNT_STRIDE];
+        unsigned long long v;
+        for (uint32_t spin = 0;; spin++) {
+          v = ld_relaxed_any(w, sys);   // entries validate themselves: no acquire needed
+          if ((uint32_t)(v >> 32) == round) break;
+#ifdef YT_SIMT_EMU
+          emu::yield();
+#endif
+          if ((spin & 4095u) == 4095u) {
+            if (!t0) t0 = gtimer();
+            else if (gtimer() - t0 > a.spin_limit_ns) loop_trap();
+          }
+        }
+        const uint32_t c = (uint32_t)v;
+        if (c & XQ_CNT_OVF) flags |= XQF_OVERFLOW;
+        if (c & XQ_CNT_COMPACT) flags |= XQF_COMPACT;
+        if (c & XQ_CNT_PLIMIT) flags |= XQF_PLIMIT;
+        if (c & XQ_CNT_PFULL) flags |= XQF_PFULL;
+        uint32_t n = c & XQ_CNT_MASK;
+        if (n > a.xq.seg_cap) n = a.xq.seg_cap;
+        if (n > (uint32_t)XQ_INLINE) { s_pref[j] = n; big = 1; continue; }
+        s_pref[j] = 0;
+        if (!n) continue;
+        const unsigned long long *ep = reinterpret_cast<const unsigned long long *>(xq_base(a.xq, a.xq.me) + xq_seg_off(a.xq, parity, sd, b));
+        unsigned long long w0[XQ_INLINE], w1[XQ_INLINE];
+#pragma unroll
+        for (int e = 0; e < XQ_INLINE; e++)
+          if ((uint32_t)e < n) { w0[e] = ld_relaxed_any(ep + 2 * e, sys); w1[e] = ld_relaxed_any(ep + 2 * e + 1, sys); }
+#pragma unroll
+        for (int e = 0; e < XQ_INLINE; e++) {
+          if ((uint32_t)e >= n) continue;
+          unsigned long long key = 0;
+          long long delta = 0;
+          for (uint32_t spin = 0; !xq_unpack(w0[e], w1[e], stamp, &key, &delta); spin++) {   // the count word overtook the entry
+#ifdef YT_SIMT_EMU
+            emu::yield();
+#endif
+            if ((spin & 4095u) == 4095u) {
+              if (!t0) t0 = gtimer();
+              else if (gtimer() - t0 > a.spin_limit_ns) loop_trap();
+            }
+            w0[e] = ld_relaxed_any(ep + 2 * e, sys); w1[e] = ld_relaxed_any(ep + 2 * e + 1, sys);
+          }
+          take(key, delta);
+        }
+      }
+      if (flags) atomicOr(&s_xf, flags);
+      if (__syncthreads_or((int)big)) {   // block-uniform
+        xq_prefix(a, s_pref, s_scan);
+        const uint32_t total = s_pref[nseg];
+        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+          unsigned long long key = 0;
+          long long delta = 0;
+          xq_entry(a, round, s_pref, i, &key, &delta);
+          take(key, delta);
         }
       }
       if (added) atomicAdd(&s_occ, added);
@@ -1156,9 +1240,10 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     // ---- the new token's pairs: those not below the bound join the front
     if (s_nocc) {   // block-uniform (read after the barrier)
       const Best bd = s_bound;
-      for (uint32_t i = threadIdx.x; i < NEWP_SLOTS; i += blockDim.x) {
+      const uint32_t nn = s_nocc;   // <= NEWP_SLOTS: one per slot taken
+      for (uint32_t q = threadIdx.x; q < nn; q += blockDim.x) {
+        const uint32_t i = nlist[q];
         const unsigned long long k = nk[i];
-        if (k == PK_EMPTY) continue;
         const unsigned long long c = nc[i];
         nk[i] = PK_EMPTY; nc[i] = 0;
         if ((long long)c <= 0) continue;
