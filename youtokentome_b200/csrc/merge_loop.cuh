@@ -56,14 +56,15 @@ constexpr uint32_t XQ_CNT_COMPACT = 0x20000000u;  // count word: > 25 % of the b
 constexpr uint32_t XQ_CNT_PLIMIT = 0x10000000u;   // count word: the block's partition is over the load limit
 constexpr uint32_t XQ_CNT_PFULL = 0x08000000u;    // count word: the block's partition ran full (an update was lost)
 constexpr uint32_t XQ_CNT_MASK = 0x07ffffffu;
-constexpr uint32_t XQ_CNT_STRIDE = 16;   // count words sit 128 bytes apart
 struct XqHdr {
-  // (round << 32) | flags | entries of the sender's segment b lives at counts[b * XQ_CNT_STRIDE]: one 128-byte line per
-  // word.  Every block polls every word; packed, the 148 words shared ten L2 lines and the ~6 k sector requests of a poll
-  // round queued at a couple of L2 slices (about one request per clock each): 2.5 us per merge.  One line per word
-  // spreads them over all slices.
-  unsigned long long counts[XQ_MAX_BLOCKS * 16];
+  // MAILBOXES: the count word (round << 32) | flags | entries of the sender's segment b exists once per READER block r, at
+  // counts[r * XQ_MAX_BLOCKS + b]: the sender stores it nblocks times (posted stores to distinct lines), reader r polls
+  // its own row — nblocks consecutive words that nobody else reads.  (Round 2, measured on B200: with one word per
+  // segment, polled by all 148 blocks, a poll round was 21.9 k sector requests on 148 lines shared by every SM.)
+  unsigned long long counts[XQ_MAX_BLOCKS * XQ_MAX_BLOCKS];
 };
+// count word of sender block `sb` in the mailbox row of reader block `rb`
+__device__ __forceinline__ unsigned long long *xq_cnt(XqHdr *h, uint32_t rb, uint32_t sb) { return &h->counts[(size_t)rb * XQ_MAX_BLOCKS + sb]; }
 struct Xq {
   unsigned char *base[XQ_MAX_WORLD];  // region of every rank; base[me] is local memory
   uint32_t world, me, nblocks, seg_cap;
@@ -525,7 +526,7 @@ __device__ __forceinline__ void xq_poll_counts(const LoopArgs &a, uint32_t round
     const uint32_t j = threadIdx.x * ipt + k;
     if (j >= nseg) break;
     const uint32_t s = j / a.xq.nblocks, b = j - s * a.xq.nblocks;
-    const unsigned long long *w = &xq_hdr(a.xq, a.xq.me, parity, s)->counts[b * XQ_CNT_STRIDE];
+    const unsigned long long *w = xq_cnt(xq_hdr(a.xq, a.xq.me, parity, s), blockIdx.x, b);
     unsigned long long v;
     for (uint32_t spin = 0;; spin++) {
       v = ld_relaxed_any(w, sys);   // entries validate themselves: no acquire needed
@@ -831,7 +832,6 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     const uint32_t k0 = min(a.n_tiles, blockIdx.x * per_block), k1 = min(a.n_tiles, k0 + per_block);
     my_slots = a.tile_desc[k1].y - a.tile_desc[k0].y;
   }
-  unsigned long long my_dead = 0;    // token slots of this block tombstoned in this launch (thread 0 keeps the sum)
   uint32_t n_refresh = 0, fseq = 0;  // refreshes of this launch (block-uniform)
   __syncthreads();
 
@@ -1125,20 +1125,21 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     for (int o = 16; o > 0; o >>= 1) dead += __shfl_xor_sync(0xffffffffu, dead, o);
     if (lane == 0 && dead) atomicAdd(&s_dead, dead);
     __syncthreads();  // all entries of this block are on their way
-    if (threadIdx.x == 0) {
-      my_dead += s_dead;
-      s_dead = 0;
+    {
+      // the count word of this segment, into the mailbox of every block of every rank (every thread computes the same
+      // word and stores a share).  No fence: the entries carry their own stamps, the count word may overtake them.
       const uint32_t n = s_out_n;
       uint32_t word = n > a.xq.seg_cap ? (a.xq.seg_cap | XQ_CNT_OVF) : n;
-      if (my_dead * 4 > my_slots && my_slots > a.dead_min_slots) word |= XQ_CNT_COMPACT;
+      if (s_dead * 4 > my_slots && my_slots > a.dead_min_slots) word |= XQ_CNT_COMPACT;   // s_dead: tombstoned in this launch
       if (s_occ > a.part_limit) word |= XQ_CNT_PLIMIT;   // state of the partition as of the last flush
       if (s_povf) word |= XQ_CNT_PFULL;
-      // no fence: the entries carry their own stamps, the count word may overtake them
       const unsigned long long cw = ((unsigned long long)nround << 32) | word;
-#pragma unroll
-      for (int d = 0; d < XQ_MAX_WORLD; d++)
-        if ((uint32_t)d < a.xq.world) st_relaxed_any(&xq_hdr(a.xq, (uint32_t)d, nround & 1u, a.xq.me)->counts[blockIdx.x * XQ_CNT_STRIDE], cw, sys);
-      s_xf = 0;   // accumulator of the poll below
+      const uint32_t nbox = a.xq.world * a.xq.nblocks;
+      for (uint32_t t = threadIdx.x; t < nbox; t += blockDim.x) {
+        const uint32_t d = t / a.xq.nblocks, rb = t - d * a.xq.nblocks;
+        st_relaxed_any(xq_cnt(xq_hdr(a.xq, d, nround & 1u, a.xq.me), rb, blockIdx.x), cw, sys);
+      }
+      if (threadIdx.x == 0) s_xf = 0;   // accumulator of the poll below
     }
     if (gtid == 0) tq2 = gtimer();
     if (dbgb) { const unsigned long long t = gtimer(); bacc[1] += t - bt; bt = t; }
@@ -1176,7 +1177,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       unsigned long long t0 = 0;
       for (uint32_t j = threadIdx.x; j < nseg; j += blockDim.x) {
         const uint32_t sd = j / a.xq.nblocks, b = j - sd * a.xq.nblocks;
-        const unsigned long long *w = &xq_hdr(a.xq, a.xq.me, parity, sd)->counts[b * XQ_CNT_STRIDE];
+        const unsigned long long *w = xq_cnt(xq_hdr(a.xq, a.xq.me, parity, sd), blockIdx.x, b);
         unsigned long long v;
         for (uint32_t spin = 0;; spin++) {
           v = ld_relaxed_any(w, sys);   // entries validate themselves: no acquire needed
@@ -1323,15 +1324,17 @@ __global__ void __launch_bounds__(256) xq_publish_table_kernel(LoopArgs a, uint3
     done += all;
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
+  {
     const uint64_t total = done;
     uint32_t word = total > lo ? (uint32_t)(total - lo < (uint64_t)a.xq.seg_cap ? total - lo : (uint64_t)a.xq.seg_cap) : 0u;
     if (total > hi) word |= XQ_CNT_MORE;
     if (__ldcg(local_overflow)) word |= XQ_CNT_OVF;
     const unsigned long long cw = ((unsigned long long)round << 32) | word;
-#pragma unroll
-    for (int d = 0; d < XQ_MAX_WORLD; d++)
-      if ((uint32_t)d < a.xq.world) st_relaxed_any(&xq_hdr(a.xq, (uint32_t)d, round & 1u, a.xq.me)->counts[blockIdx.x * XQ_CNT_STRIDE], cw, true);
+    const uint32_t nbox = a.xq.world * a.xq.nblocks;
+    for (uint32_t t = threadIdx.x; t < nbox; t += blockDim.x) {
+      const uint32_t d = t / a.xq.nblocks, rb = t - d * a.xq.nblocks;
+      st_relaxed_any(xq_cnt(xq_hdr(a.xq, d, round & 1u, a.xq.me), rb, blockIdx.x), cw, true);
+    }
   }
 }
 // xq_absorb_kernel: block b waits for round `round` of every block of every rank and adds the peers' pairs it owns
