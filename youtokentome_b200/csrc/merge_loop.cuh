@@ -65,8 +65,16 @@ struct XqHdr {
 };
 // count word of sender block `sb` in the mailbox row of reader block `rb`
 __device__ __forceinline__ unsigned long long *xq_cnt(XqHdr *h, uint32_t rb, uint32_t sb) { return &h->counts[(size_t)rb * XQ_MAX_BLOCKS + sb]; }
+// MAILBOX LINES (local senders only): 128 bytes per (parity, reader block, sender block) = a 16-byte header (the count
+// word, twice) + the first XQ_BOX entries of the sender's segment.  The sender stores the line once per reader; a
+// reader's lines are read by nobody else, and header + first entry share a 32-byte sector, so the usual segment (0 or 1
+// entries) costs ONE L2 round trip after its arrival.  (Round 2, measured on B200: with shared segments every entry line
+// is loaded by all 148 SMs at the same moment and the requests queue at its L2 slice — ~1 us per dependent load, two of
+// them per merge.)  Entries XQ_BOX.. of a segment, and everything a REMOTE rank reads, live in the shared segments.
+constexpr int XQ_BOX = 7;
 struct Xq {
   unsigned char *base[XQ_MAX_WORLD];  // region of every rank; base[me] is local memory
+  unsigned char *box;                 // mailbox lines of this rank: [parity][reader][sender][128]
   uint32_t world, me, nblocks, seg_cap;
   unsigned long long per_sender;      // bytes of one {header, entries} slot
 };
@@ -79,6 +87,9 @@ __device__ __forceinline__ unsigned char *xq_base(const Xq &x, uint32_t rank) {
 }
 __device__ __forceinline__ XqHdr *xq_hdr(const Xq &x, uint32_t rank, uint32_t parity, uint32_t sender) {
   return reinterpret_cast<XqHdr *>(xq_base(x, rank) + (size_t)(parity * x.world + sender) * x.per_sender);
+}
+__device__ __forceinline__ unsigned char *xq_box_line(const Xq &x, uint32_t parity, uint32_t reader, uint32_t sender) {
+  return x.box + ((size_t)(parity * x.nblocks + reader) * x.nblocks + sender) * 128;
 }
 // byte offset (inside any rank's region) of segment `block` of (parity, sender)
 __device__ __forceinline__ size_t xq_seg_off(const Xq &x, uint32_t parity, uint32_t sender, uint32_t block) {
@@ -120,6 +131,15 @@ __device__ __forceinline__ unsigned long long ld_relaxed_any(const unsigned long
   return v;
 #else
   return __atomic_load_n(p, __ATOMIC_RELAXED);
+#endif
+}
+// two consecutive 64-bit words (16-byte aligned) with one relaxed load
+__device__ __forceinline__ void ld_relaxed2(const unsigned long long *p, unsigned long long *a, unsigned long long *b) {
+#ifndef YT_SIMT_EMU
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(*a), "=l"(*b) : "l"(p) : "memory");
+#else
+  *a = __atomic_load_n(p, __ATOMIC_RELAXED);
+  *b = __atomic_load_n(p + 1, __ATOMIC_RELAXED);
 #endif
 }
 __device__ __forceinline__ void st_relaxed_any(unsigned long long *p, unsigned long long v, bool sys) {
@@ -200,6 +220,7 @@ struct LoopArgs {
   uint32_t part_limit;            // leave for a rebuild when a partition holds more keys than this
   uint32_t dead_min_slots;        // a block wishes a compaction only if it owns more token slots than this
   unsigned long long spin_limit_ns;  // a peer that stays silent this long traps the kernel (never hang the box)
+  uint32_t front_top;                // pairs a partition contributes to a front refresh (1 .. FRONT_TOP)
   unsigned long long *dbg_blk;       // YTTM_DBG & 16: 8 accumulators per block (ns): poll bests, apply, wait counts (+ owner sweep), drain, cache, sweeps
 };
 
@@ -243,11 +264,16 @@ struct XqOut {
   size_t off;        // byte offset of the segment inside a region
   uint32_t *s_n;     // shared-memory entry counter of the block (may run past cap: overflow)
   uint32_t stamp;    // round % XQ_STAMP_MOD of the entries
+  uint4 *s_box;      // shared-memory copy of the first XQ_BOX entries (they go out with the mailbox lines)
 };
 __device__ __forceinline__ void xq_store(const LoopArgs &a, const XqOut &o, uint32_t i, unsigned long long key,
                                          long long delta) {
   if (i >= a.xq.seg_cap) return;  // overflow: the count word carries the flag, the host rebuilds the table
   const uint4 e = xq_pack(o.stamp, key, delta);
+  if (i < (uint32_t)XQ_BOX) {
+    o.s_box[i] = e;
+    if (a.xq.world == 1) return;   // nobody reads these places of the shared segment
+  }
 #pragma unroll
   for (int d = 0; d < XQ_MAX_WORLD; d++)
     if ((uint32_t)d < a.xq.world) reinterpret_cast<uint4 *>(a.xq.base[d] + o.off)[i] = e;
@@ -594,8 +620,9 @@ __device__ __forceinline__ void xq_prefix(const LoopArgs &a, uint32_t *s_pref, u
   __syncthreads();
 }
 // entry i (0 <= i < s_pref[nseg]) of round `round` in this rank's region; spins until both words carry the round's stamp
+// local_off: places of a LOCAL sender's segment that travelled by mailbox instead (the merge loop: XQ_BOX)
 __device__ __forceinline__ void xq_entry(const LoopArgs &a, uint32_t round, const uint32_t *s_pref, uint32_t i,
-                                         unsigned long long *key, long long *delta) {
+                                         unsigned long long *key, long long *delta, uint32_t local_off = 0) {
   const uint32_t nseg = a.xq.world * a.xq.nblocks;
   uint32_t lo = 0, hi = nseg;  // largest j with s_pref[j] <= i (empty segments share a prefix value: take the last)
   while (hi - lo > 1) {
@@ -604,7 +631,7 @@ __device__ __forceinline__ void xq_entry(const LoopArgs &a, uint32_t round, cons
   }
   const uint32_t s = lo / a.xq.nblocks, b = lo - s * a.xq.nblocks;
   const unsigned long long *ep = reinterpret_cast<const unsigned long long *>(
-      xq_base(a.xq, a.xq.me) + xq_seg_off(a.xq, round & 1u, s, b) + (size_t)(i - s_pref[lo]) * sizeof(uint4));
+      xq_base(a.xq, a.xq.me) + xq_seg_off(a.xq, round & 1u, s, b) + (size_t)(i - s_pref[lo] + (s == a.xq.me ? local_off : 0u)) * sizeof(uint4));
   const bool sys = a.xq.world > 1;
   unsigned long long t0 = 0;
   for (uint32_t spin = 0; !xq_unpack(ld_relaxed_any(ep, sys), ld_relaxed_any(ep + 1, sys), round % XQ_STAMP_MOD, key, delta); spin++) {
@@ -657,7 +684,7 @@ constexpr uint32_t FRONT_FILL = 1280;    // members that trigger a refresh (dead
 constexpr uint32_t NEWP_SLOTS = 1024;    // the round's pairs with the new token, aggregated before they meet the bound
 constexpr uint32_t OWN_CAP = 512;        // parked entries of one round (more: added to the partition at once)
 constexpr int FRONT_TOP = 8;             // pairs a partition contributes to a refresh
-constexpr int XQ_INLINE = 4;             // entries of a segment its polling thread handles on its own
+constexpr int XQ_INLINE = 4;             // entries of a REMOTE segment its polling thread handles on its own
 constexpr size_t LOOP_FRONT_BYTES = ((size_t)FRONT_SLOTS * 2 + NEWP_SLOTS * 2 + OWN_CAP * 2) * 8 + (size_t)NEWP_SLOTS * 4;
 // global gather buffer of a refresh: [nblocks flag words, 128 bytes apart][nblocks x FRONT_TOP x (count, key)]
 YT_HD size_t front_buf_words(uint32_t nblocks) { return (size_t)nblocks * 16 + (size_t)nblocks * FRONT_TOP * 2; }
@@ -759,6 +786,7 @@ __device__ __forceinline__ void sweep_below(const LoopArgs &a, uint64_t pbase, u
 __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   __shared__ Best s_warp[32];
   __shared__ Best s_bound, s_tmp;   // the bound of the front / scratch of a refresh
+  __shared__ uint4 s_box[XQ_BOX + 1];   // the first entries of this block's segment (xq_store)
   __shared__ unsigned long long s_dead;
   __shared__ uint32_t s_defer_n, s_direct, s_out_n, s_occ, s_xf, s_povf, s_focc, s_nocc, s_own_n, s_refresh, s_scan[33];
   const bool sys = a.xq.world > 1;
@@ -800,7 +828,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   uint32_t round = a.ctl->xq_round;                   // exchange rounds completed so far (same on every rank)
   unsigned long long tacc0 = 0, tacc2 = 0, tacc3 = 0, tacc4 = 0, titers = 0;  // phase timers (block 0, thread 0)
   const bool dbgb = (a.dbg & 16u) != 0 && threadIdx.x == 0;   // per-block phase accumulators (thread 0 of every block)
-  unsigned long long bacc[6] = {0, 0, 0, 0, 0, 0}, bt = 0;
+  unsigned long long bacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, bt = 0;
 
   // occupancy of this block's partition (keys never leave the table between rebuilds)
   {
@@ -874,7 +902,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     for (uint32_t i = threadIdx.x; i < FRONT_SLOTS; i += blockDim.x) { fk[i] = PK_EMPTY; fc[i] = 0; }
     Best lim{~0ull, ~0ull, 0};
     int k = 0;
-    for (; k < FRONT_TOP; k++) {
+    for (; k < (int)a.front_top; k++) {
       sweep_below(a, pbase, R, lim, s_warp, &s_tmp);
       const Best t = s_tmp;
       if (t.c == 0) break;   // block-uniform
@@ -902,8 +930,8 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     __syncthreads();
     Best bd{0, 0, 0};   // the bound: the last pair of every list that is full (a shorter list holds its whole partition)
     for (unsigned j = threadIdx.x; j < gridDim.x; j += blockDim.x) {
-      const unsigned long long c = ld_relaxed(gdata + ((size_t)j * FRONT_TOP + FRONT_TOP - 1) * 2);
-      const unsigned long long key = ld_relaxed(gdata + ((size_t)j * FRONT_TOP + FRONT_TOP - 1) * 2 + 1);
+      const unsigned long long c = ld_relaxed(gdata + ((size_t)j * FRONT_TOP + a.front_top - 1) * 2);
+      const unsigned long long key = ld_relaxed(gdata + ((size_t)j * FRONT_TOP + a.front_top - 1) * 2 + 1);
       if (!c) continue;
       const Best cand{c, pair_prio((uint32_t)(key >> 32), (uint32_t)key), 0};
       if (better(cand, bd)) bd = cand;
@@ -976,6 +1004,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     xo.off = xq_seg_off(a.xq, nround & 1u, a.xq.me, blockIdx.x);
     xo.s_n = &s_out_n;
     xo.stamp = nround % XQ_STAMP_MOD;
+    xo.s_box = s_box;
     unsigned long long dead = 0;
     if (a.resident) {
       if (rw1 > rw0) dead = process_tile(stok, soff, rw1 - rw0, soff[rw1 - rw0], s_claim,
@@ -1134,10 +1163,23 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       if (s_occ > a.part_limit) word |= XQ_CNT_PLIMIT;   // state of the partition as of the last flush
       if (s_povf) word |= XQ_CNT_PFULL;
       const unsigned long long cw = ((unsigned long long)nround << 32) | word;
-      const uint32_t nbox = a.xq.world * a.xq.nblocks;
-      for (uint32_t t = threadIdx.x; t < nbox; t += blockDim.x) {
-        const uint32_t d = t / a.xq.nblocks, rb = t - d * a.xq.nblocks;
-        st_relaxed_any(xq_cnt(xq_hdr(a.xq, d, nround & 1u, a.xq.me), rb, blockIdx.x), cw, sys);
+      // local readers: one mailbox line each = header + the first entries
+      {
+        const uint32_t nb = n < (uint32_t)XQ_BOX ? n : (uint32_t)XQ_BOX;
+        const uint4 hd = make_uint4((uint32_t)cw, (uint32_t)(cw >> 32), (uint32_t)cw, (uint32_t)(cw >> 32));
+        for (uint32_t r = threadIdx.x; r < a.xq.nblocks; r += blockDim.x) {
+          uint4 *line = reinterpret_cast<uint4 *>(xq_box_line(a.xq, nround & 1u, r, blockIdx.x));
+          for (uint32_t e = 0; e < nb; e++) line[1 + e] = s_box[e];
+          line[0] = hd;
+        }
+      }
+      // readers on the other ranks: the count word into their mailbox rows (their entries sit in the shared segments)
+      if (a.xq.world > 1) {
+        const uint32_t nbox = a.xq.world * a.xq.nblocks;
+        for (uint32_t t = threadIdx.x; t < nbox; t += blockDim.x) {
+          const uint32_t d = t / a.xq.nblocks, rb = t - d * a.xq.nblocks;
+          if (d != a.xq.me) st_relaxed_any(xq_cnt(xq_hdr(a.xq, d, nround & 1u, a.xq.me), rb, blockIdx.x), cw, true);
+        }
       }
       if (threadIdx.x == 0) s_xf = 0;   // accumulator of the poll below
     }
@@ -1175,20 +1217,37 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       const uint32_t nseg = a.xq.world * a.xq.nblocks, parity = round & 1u, stamp = round % XQ_STAMP_MOD;
       uint32_t flags = 0, big = 0;
       unsigned long long t0 = 0;
+      auto spin_check = [&](uint32_t spin) {   // a peer that stays silent traps the kernel (never hang the box)
+#ifdef YT_SIMT_EMU
+        emu::yield();
+#endif
+        if ((spin & 4095u) == 4095u) {
+          if (!t0) t0 = gtimer();
+          else if (gtimer() - t0 > a.spin_limit_ns) loop_trap();
+        }
+      };
+      auto word_of = [&](uint32_t sd, uint32_t b) -> const unsigned long long * {   // where segment (sd, b)'s count word arrives
+        return sd == a.xq.me ? reinterpret_cast<const unsigned long long *>(xq_box_line(a.xq, parity, blockIdx.x, b))
+                             : xq_cnt(xq_hdr(a.xq, a.xq.me, parity, sd), blockIdx.x, b);
+      };
+      if (a.dbg & 16u) {   // diagnostic: when have ALL count words arrived (hop + skew of the apply phases)?
+        for (uint32_t j = threadIdx.x; j < nseg; j += blockDim.x) {
+          const uint32_t sd = j / a.xq.nblocks, b = j - sd * a.xq.nblocks;
+          for (uint32_t spin = 0; (uint32_t)(ld_relaxed_any(word_of(sd, b), sys) >> 32) != round; spin++) spin_check(spin);
+        }
+        __syncthreads();
+        if (dbgb) bacc[6] += gtimer() - bt;
+      }
       for (uint32_t j = threadIdx.x; j < nseg; j += blockDim.x) {
         const uint32_t sd = j / a.xq.nblocks, b = j - sd * a.xq.nblocks;
-        const unsigned long long *w = xq_cnt(xq_hdr(a.xq, a.xq.me, parity, sd), blockIdx.x, b);
-        unsigned long long v;
+        const unsigned long long *w = word_of(sd, b);
+        const bool local = sd == a.xq.me;
+        unsigned long long v, v2, e0a = 0, e0b = 0;
         for (uint32_t spin = 0;; spin++) {
-          v = ld_relaxed_any(w, sys);   // entries validate themselves: no acquire needed
+          if (local) { ld_relaxed2(w, &v, &v2); ld_relaxed2(w + 2, &e0a, &e0b); }   // header + first entry: one sector
+          else v = ld_relaxed_any(w, sys);
           if ((uint32_t)(v >> 32) == round) break;
-#ifdef YT_SIMT_EMU
-          emu::yield();
-#endif
-          if ((spin & 4095u) == 4095u) {
-            if (!t0) t0 = gtimer();
-            else if (gtimer() - t0 > a.spin_limit_ns) loop_trap();
-          }
+          spin_check(spin);
         }
         const uint32_t c = (uint32_t)v;
         if (c & XQ_CNT_OVF) flags |= XQF_OVERFLOW;
@@ -1197,6 +1256,29 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
         if (c & XQ_CNT_PFULL) flags |= XQF_PFULL;
         uint32_t n = c & XQ_CNT_MASK;
         if (n > a.xq.seg_cap) n = a.xq.seg_cap;
+        if (local) {
+          const uint32_t nb = n < (uint32_t)XQ_BOX ? n : (uint32_t)XQ_BOX;
+          s_pref[j] = n - nb;   // the rest sits in the shared segment, from place XQ_BOX on
+          if (n > nb) big = 1;
+          unsigned long long w0[XQ_BOX], w1[XQ_BOX];
+          w0[0] = e0a; w1[0] = e0b;
+#pragma unroll
+          for (int e = 1; e < XQ_BOX; e++)
+            if ((uint32_t)e < nb) ld_relaxed2(w + 2 + 2 * e, &w0[e], &w1[e]);
+#pragma unroll
+          for (int e = 0; e < XQ_BOX; e++) {
+            if ((uint32_t)e >= nb) continue;
+            unsigned long long key = 0;
+            long long delta = 0;
+            for (uint32_t spin = 0; !xq_unpack(w0[e], w1[e], stamp, &key, &delta); spin++) {   // the header overtook the entry
+              if (dbgb) bacc[11] += 1;
+              spin_check(spin);
+              ld_relaxed2(w + 2 + 2 * e, &w0[e], &w1[e]);
+            }
+            take(key, delta);
+          }
+          continue;
+        }
         if (n > (uint32_t)XQ_INLINE) { s_pref[j] = n; big = 1; continue; }
         s_pref[j] = 0;
         if (!n) continue;
@@ -1211,26 +1293,24 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
           unsigned long long key = 0;
           long long delta = 0;
           for (uint32_t spin = 0; !xq_unpack(w0[e], w1[e], stamp, &key, &delta); spin++) {   // the count word overtook the entry
-#ifdef YT_SIMT_EMU
-            emu::yield();
-#endif
-            if ((spin & 4095u) == 4095u) {
-              if (!t0) t0 = gtimer();
-              else if (gtimer() - t0 > a.spin_limit_ns) loop_trap();
-            }
+            spin_check(spin);
             w0[e] = ld_relaxed_any(ep + 2 * e, sys); w1[e] = ld_relaxed_any(ep + 2 * e + 1, sys);
           }
           take(key, delta);
         }
       }
       if (flags) atomicOr(&s_xf, flags);
-      if (__syncthreads_or((int)big)) {   // block-uniform
+      if (dbgb) bacc[8] += gtimer() - bt;    // thread 0 is through with its own segment
+      const int anybig = __syncthreads_or((int)big);
+      if (dbgb) bacc[9] += gtimer() - bt;    // every thread is
+      if (anybig) {   // block-uniform
+        if (dbgb) bacc[7] += 1;
         xq_prefix(a, s_pref, s_scan);
         const uint32_t total = s_pref[nseg];
         for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
           unsigned long long key = 0;
           long long delta = 0;
-          xq_entry(a, round, s_pref, i, &key, &delta);
+          xq_entry(a, round, s_pref, i, &key, &delta, XQ_BOX);
           take(key, delta);
         }
       }
@@ -1271,7 +1351,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   if (gtid == 0 && n_refresh) atomicAdd(&a.ctl->n_sweeps, (unsigned long long)n_refresh);
   if (dbgb && a.dbg_blk) {
     bacc[5] = n_refresh;
-    for (int k = 0; k < 6; k++) a.dbg_blk[8 * blockIdx.x + k] += bacc[k];
+    for (int k = 0; k < 16; k++) a.dbg_blk[16 * blockIdx.x + k] += bacc[k];
   }
   if (gtid == 0) {
     a.ctl->xq_round = round;

@@ -616,6 +616,10 @@ int xq_alloc(yttm_ctx *c, uint32_t me, uint32_t world) {
   c->xq_bytes = 2ull * world * c->xq_per_sender;
   YT_CUDA(c, c->xq_buf.reserve(c->xq_bytes));
   YT_CUDA(c, c->xq_arrive.reserve(64));
+  // mailbox lines of the local blocks: all-ones = a round and stamps no real round uses
+  c->xq_box_bytes = 2ull * c->xq_nblocks * c->xq_nblocks * 128;
+  YT_CUDA(c, c->xq_box.reserve(c->xq_box_bytes));
+  YT_CUDA(c, cudaMemsetAsync(c->xq_box.p, 0xff, c->xq_box_bytes, c->stream));
   // entries start as all-ones (a stamp no round uses), count words as round 0
   YT_CUDA(c, cudaMemsetAsync(c->xq_buf.p, 0xff, c->xq_bytes, c->stream));
   for (uint32_t k = 0; k < 2 * world; k++)
@@ -637,6 +641,7 @@ int xq_args(yttm_ctx *c, LoopArgs *a) {
   for (int d = 0; d < XQ_MAX_WORLD; d++) a->xq.base[d] = static_cast<unsigned char *>(c->xq_peer[d < (int)c->xq_world ? d : (int)c->xq_me]);
   a->xq.world = c->xq_world; a->xq.me = c->xq_me; a->xq.nblocks = c->xq_nblocks; a->xq.seg_cap = c->xq_seg_cap;
   a->xq.per_sender = c->xq_per_sender;
+  a->xq.box = static_cast<unsigned char *>(c->xq_box.p);
   a->spin_limit_ns = xq_spin_limit_ns();
   return 0;
 }
@@ -877,7 +882,7 @@ void yttm_ctx_destroy(yttm_ctx *c) {
   cudaStreamSynchronize(c->stream);
   ytc::DevBuf *bufs[] = {&c->text_buf, &c->hist, &c->cp2id, &c->wkey, &c->wcnt, &c->wpos, &c->wfreq, &c->wlen,
                          &c->scan_tmp, &c->counters, &c->tok[0], &c->tok[1], &c->off[0], &c->off[1], &c->freq[0],
-                         &c->freq[1], &c->pkey, &c->pcnt, &c->scratch_key, &c->scratch_cnt, &c->ctl, &c->frontbuf, &c->tiles, &c->defer,
+                         &c->freq[1], &c->pkey, &c->pcnt, &c->scratch_key, &c->scratch_cnt, &c->ctl, &c->frontbuf, &c->xq_box, &c->tiles, &c->defer,
                          &c->d_rules, &c->d_rfreq, &c->xq_arrive, &c->xq_buf};
   for (int d = 0; d < 8; d++)
     if (c->xq_peer_ipc[d] && c->xq_peer[d]) { cudaIpcCloseMemHandle(c->xq_peer[d]); c->xq_peer[d] = nullptr; }
@@ -1436,10 +1441,12 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
     a.part_limit = (uint32_t)(((uint64_t)c->p_rmask + 1) * pair_max_load_pct() / 100);  // rebuild above this partition load (default 1/2)
     a.dbg_blk = nullptr;
     if (a.dbg & 16u) {   // diagnostic: where do the blocks spend a merge?  (printed to stderr after the run)
-      if (!c->scratch_cnt.p || c->scratch_cnt.cap < (size_t)c->loop_blocks * 64) YT_CUDA(c, c->scratch_cnt.reserve((size_t)c->loop_blocks * 64));
-      if (c->loop_relaunches == 0) YT_CUDA(c, cudaMemsetAsync(c->scratch_cnt.p, 0, (size_t)c->loop_blocks * 64, c->stream));
+      if (!c->scratch_cnt.p || c->scratch_cnt.cap < (size_t)c->loop_blocks * 128) YT_CUDA(c, c->scratch_cnt.reserve((size_t)c->loop_blocks * 128));
+      if (c->loop_relaunches == 0) YT_CUDA(c, cudaMemsetAsync(c->scratch_cnt.p, 0, (size_t)c->loop_blocks * 128, c->stream));
       a.dbg_blk = c->scratch_cnt.as<unsigned long long>();
     }
+    a.front_top = 4;   // measured on B200 (100 MB Zipf): 8 -> 9.6, 4 -> 8.8, 2 -> 9.3 us per merge (smaller front: shorter probes and scans, more refreshes)
+    if (const char *e = std::getenv("YTTM_FRONT_TOP")) a.front_top = (uint32_t)std::max(1, std::min((int)FRONT_TOP, std::atoi(e)));
     a.dead_min_slots = 4096;
     if (const char *e = std::getenv("YTTM_DEAD_MIN_SLOTS")) a.dead_min_slots = (uint32_t)std::max(0, std::atoi(e));
     YT_CUDA(c, cudaMemsetAsync(c->frontbuf.p, 0, front_buf_words((uint32_t)c->loop_blocks) * 8, c->stream));  // refresh numbers restart at 1
@@ -1476,22 +1483,24 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
   ytc::timer_end(c, "merge_loop");
   if (const char *e = std::getenv("YTTM_DBG")) {
     if ((std::atoi(e) & 16) && h.iters) {
-      std::vector<unsigned long long> blk((size_t)c->loop_blocks * 8);
+      std::vector<unsigned long long> blk((size_t)c->loop_blocks * 16);
       YT_CUDA(c, cudaMemcpyAsync(blk.data(), c->scratch_cnt.p, blk.size() * 8, cudaMemcpyDeviceToHost, c->stream));
       YT_CUDA(c, cudaStreamSynchronize(c->stream));
-      static const char *nm[] = {"elect(+refresh)", "apply", "partition_update", "wait_counts+drain", "new_pairs", "refreshes"};
+      static const char *nm[] = {"elect(+refresh)", "apply", "partition_update", "wait_counts+drain", "new_pairs", "refreshes", "  of it: until all count words are in", "rounds with a shared (long) segment",
+                                 "  .. thread 0 done with its segment", "  .. all threads done", "", "entry re-loads of thread 0 [count]"};
       const double it = (double)h.iters;
-      for (int k = 0; k < 6; k++) {
+      for (int k = 0; k < 12; k++) {
+        if (!nm[k][0]) continue;
         double mn = 1e30, mx = 0, sum = 0;
         int imn = 0, imx = 0;
         for (int b = 0; b < c->loop_blocks; b++) {
-          const double v = (double)blk[(size_t)b * 8 + k] / (k == 5 ? 1.0 : it) * (k == 5 ? 1.0 : 1e-3);
+          const double v = (double)blk[(size_t)b * 16 + k] / (k == 5 ? 1.0 : it) * (k == 5 || k == 7 || k == 11 ? 1.0 : 1e-3);
           sum += v;
           if (v < mn) { mn = v; imn = b; }
           if (v > mx) { mx = v; imx = b; }
         }
-        std::fprintf(stderr, "YTTM_DBG16 %-24s per merge: mean %8.3f  min %8.3f (block %d)  max %8.3f (block %d)%s\n", nm[k],
-                     sum / c->loop_blocks, mn, imn, mx, imx, k == 5 ? "  [count per run]" : " us");
+        std::fprintf(stderr, "YTTM_DBG16 %-36s per merge: mean %8.3f  min %8.3f (block %d)  max %8.3f (block %d)%s\n", nm[k],
+                     sum / c->loop_blocks, mn, imn, mx, imx, k == 5 ? "  [count per run]" : k == 7 ? "  [fraction]" : " us");
       }
     }
   }
