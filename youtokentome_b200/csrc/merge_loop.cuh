@@ -700,6 +700,20 @@ __device__ __forceinline__ uint32_t smem_tab_find(const unsigned long long *keys
   }
   return ~0u;
 }
+// 64-bit add in shared memory out of two NATIVE 32-bit atomics (low word, then high word + carry).  atomicAdd on a
+// 64-bit shared word compiles to a compare-and-swap loop (ATOMS.CAST.SPIN), and the count changes of a merge pile up
+// on few keys (the new token next to its most frequent neighbours): the retries of a few dozen threads on one word
+// cost microseconds.  The sum is exact once all adds have landed (nobody reads a count inside the drain).
+__device__ __forceinline__ void smem_add64(unsigned long long *p, unsigned long long delta) {
+  uint32_t *w = reinterpret_cast<uint32_t *>(p);   // little endian: w[0] low, w[1] high
+  const uint32_t dlo = (uint32_t)delta, dhi = (uint32_t)(delta >> 32);
+  uint32_t carry = 0;
+  if (dlo) {
+    const uint32_t old = atomicAdd(w, dlo);
+    carry = old + dlo < old ? 1u : 0u;
+  }
+  if (dhi + carry) atomicAdd(w + 1, dhi + carry);
+}
 // insert-or-add; false: the table is full.  list (optional): the slots taken, in order of arrival (mask + 1 places)
 __device__ __forceinline__ bool smem_tab_add(unsigned long long *keys, unsigned long long *cnts, uint32_t mask, uint64_t hh,
                                              unsigned long long key, long long delta, uint32_t *occ, uint32_t *list = nullptr) {
@@ -714,7 +728,7 @@ __device__ __forceinline__ bool smem_tab_add(unsigned long long *keys, unsigned 
         k = key;
       }
     }
-    if (k == key) { atomicAdd(cnts + i, (unsigned long long)delta); return true; }
+    if (k == key) { smem_add64(cnts + i, (unsigned long long)delta); return true; }
   }
   return false;
 }
@@ -787,7 +801,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   __shared__ Best s_warp[32];
   __shared__ Best s_bound, s_tmp;   // the bound of the front / scratch of a refresh
   __shared__ uint4 s_box[XQ_BOX + 1];   // the first entries of this block's segment (xq_store)
-  __shared__ unsigned long long s_dead;
+  __shared__ uint32_t s_dead;   // token slots of this block tombstoned in this launch
   __shared__ uint32_t s_defer_n, s_direct, s_out_n, s_occ, s_xf, s_povf, s_focc, s_nocc, s_own_n, s_refresh, s_scan[33];
   const bool sys = a.xq.world > 1;
   // dynamic shared memory: [segment prefix: XQ_MAX_WORLD * XQ_MAX_BLOCKS + 4 words][claim bitmaps][front keys, counts]
@@ -1152,14 +1166,14 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     
     }
     for (int o = 16; o > 0; o >>= 1) dead += __shfl_xor_sync(0xffffffffu, dead, o);
-    if (lane == 0 && dead) atomicAdd(&s_dead, dead);
+    if (lane == 0 && dead) atomicAdd(&s_dead, (uint32_t)dead);
     __syncthreads();  // all entries of this block are on their way
     {
       // the count word of this segment, into the mailbox of every block of every rank (every thread computes the same
       // word and stores a share).  No fence: the entries carry their own stamps, the count word may overtake them.
       const uint32_t n = s_out_n;
       uint32_t word = n > a.xq.seg_cap ? (a.xq.seg_cap | XQ_CNT_OVF) : n;
-      if (s_dead * 4 > my_slots && my_slots > a.dead_min_slots) word |= XQ_CNT_COMPACT;   // s_dead: tombstoned in this launch
+      if ((unsigned long long)s_dead * 4 > my_slots && my_slots > a.dead_min_slots) word |= XQ_CNT_COMPACT;   // s_dead: tombstoned in this launch
       if (s_occ > a.part_limit) word |= XQ_CNT_PLIMIT;   // state of the partition as of the last flush
       if (s_povf) word |= XQ_CNT_PFULL;
       const unsigned long long cw = ((unsigned long long)nround << 32) | word;
@@ -1200,7 +1214,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       auto take = [&](unsigned long long key, long long delta) {
         const uint64_t hh = mix64(key);
         const uint32_t fs = smem_tab_find(fk, FRONT_SLOTS - 1, hh, key);
-        if (fs != ~0u) atomicAdd(fc + fs, (unsigned long long)delta);
+        if (fs != ~0u) smem_add64(fc + fs, (unsigned long long)delta);
         else if ((uint32_t)(key >> 32) == op.z || (uint32_t)key == op.z) {   // a pair of the new token: cannot be in the front yet
           if (!smem_tab_add(nk, nc, NEWP_SLOTS - 1, hh, key, delta, &s_nocc, nlist)) s_refresh = 1;   // too many: the refresh finds them
         }
