@@ -797,6 +797,52 @@ __device__ __forceinline__ void sweep_below(const LoopArgs &a, uint64_t pbase, u
   block_best(b, s_warp, s_out);
 }
 
+#ifndef YT_SIMT_EMU
+#define YT_NOINLINE __noinline__
+#else
+#define YT_NOINLINE
+#endif
+// What a drained entry needs (merge_loop_body): the front, the round's new pairs, the parked list, the partition.
+struct FrontCtx {
+  unsigned long long *fk, *fc, *nk, *nc, *ownk;
+  long long *ownd;
+  uint32_t *nlist, *s_nocc, *s_own_n, *s_refresh, *s_povf, *s_occ;
+  uint32_t own_base, z, part;
+  uint64_t pbase;
+  PairTab tab;
+};
+// One drained entry.  NOT inlined on purpose: the drain has a dozen call sites (unrolled mailbox places), and with this
+// body inlined in each the loop outgrew the instruction cache — measured on B200: every added copy cost ~0.1 us per
+// merge, the 7-place mailbox version was 0.9 us SLOWER than the 4-place one although it saved a round trip.
+__device__ YT_NOINLINE void front_take(const FrontCtx &f, unsigned long long key, long long delta) {
+  const uint64_t hh = mix64(key);
+  const uint32_t fs = smem_tab_find(f.fk, FRONT_SLOTS - 1, hh, key);
+  if (fs != ~0u) smem_add64(f.fc + fs, (unsigned long long)delta);
+  else if ((uint32_t)(key >> 32) == f.z || (uint32_t)key == f.z) {   // a pair of the new token: cannot be in the front yet
+    if (!smem_tab_add(f.nk, f.nc, NEWP_SLOTS - 1, hh, key, delta, f.s_nocc, f.nlist)) *f.s_refresh = 1;   // too many: the refresh finds them
+  }
+  if (pair_part(f.tab, hh) == f.part) {
+    const uint32_t q = atomicAdd(f.s_own_n, 1u) - f.own_base;
+    if (q < OWN_CAP) { f.ownk[q] = key; f.ownd[q] = delta; }
+    else {   // the list is full: straight into the partition
+      uint64_t slot = ~0ull;
+      if (pair_add_at(f.tab, f.pbase, (uint32_t)hh & f.tab.rmask, key, delta, &slot)) atomicAdd(f.s_occ, 1u);
+      if (slot == ~0ull) *f.s_povf = 1;
+    }
+  }
+}
+// parked entries -> the partition (all threads of the block)
+__device__ YT_NOINLINE void front_flush(const FrontCtx &f, uint32_t n) {
+  uint32_t added = 0;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const unsigned long long key = f.ownk[i];
+    uint64_t slot = ~0ull;
+    added += pair_add_at(f.tab, f.pbase, (uint32_t)mix64(key) & f.tab.rmask, key, f.ownd[i], &slot) ? 1u : 0u;
+    if (slot == ~0ull) *f.s_povf = 1;   // this partition ran full: an update was lost (benign race: every writer stores 1)
+  }
+  if (added) atomicAdd(f.s_occ, added);
+}
+
 __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   __shared__ Best s_warp[32];
   __shared__ Best s_bound, s_tmp;   // the bound of the front / scratch of a refresh
@@ -879,19 +925,15 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
 
   // parked entries -> this block's partition (all threads; leaves the list empty).  The list counter s_own_n only grows:
   // entry q sits at place q - own_base (no reset, hence no barrier between a flush and the next round's parking).
-  uint32_t own_base = 0;
+  FrontCtx fx;
+  fx.fk = fk; fx.fc = fc; fx.nk = nk; fx.nc = nc; fx.ownk = ownk; fx.ownd = ownd; fx.nlist = nlist;
+  fx.s_nocc = &s_nocc; fx.s_own_n = &s_own_n; fx.s_refresh = &s_refresh; fx.s_povf = &s_povf; fx.s_occ = &s_occ;
+  fx.own_base = 0; fx.z = 0; fx.part = blockIdx.x; fx.pbase = pbase; fx.tab = a.tab;
   auto flush_own = [&]() {
     __syncthreads();
-    const uint32_t end = s_own_n, n = min(end - own_base, OWN_CAP);
-    own_base = end;
-    uint32_t added = 0;
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-      const unsigned long long key = ownk[i];
-      uint64_t slot = ~0ull;
-      added += pair_add_at(a.tab, pbase, (uint32_t)mix64(key) & a.tab.rmask, key, ownd[i], &slot) ? 1u : 0u;
-      if (slot == ~0ull) s_povf = 1;   // this partition ran full: an update was lost (benign race: every writer stores 1)
-    }
-    if (added) atomicAdd(&s_occ, added);
+    const uint32_t end = s_own_n, n = min(end - fx.own_base, OWN_CAP);
+    fx.own_base = end;
+    front_flush(fx, n);
     __syncthreads();
   };
   // the largest member of the front (.slot = its slot in the front), in every thread; one block barrier
@@ -977,12 +1019,12 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       }
     }
     // ---------------- elect the pair from the front (no communication)
-    bool fresh = false;
-    if (s_refresh || s_focc > FRONT_FILL) { refresh(); fresh = true; }
-    Best win = select();
-    if (!fresh && (win.c == 0 || better(s_bound, win))) {   // the front is exhausted
-      refresh();
+    Best win;
+    for (bool need = s_refresh || s_focc > FRONT_FILL;; need = true) {   // at most two trips: "the front is exhausted" shows in the election
+      if (need) refresh();
       win = select();
+      if (need || !(win.c == 0 || better(s_bound, win))) break;
+      __syncthreads();   // (s_warp of the election is free again)
     }
     if (win.c == 0) {                                               // no pair left (bpe.cpp:1137-1145)
       if (gtid == 0) { a.ctl->stop = 1; a.ctl->stop_why = 0; }
@@ -1006,7 +1048,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       fc[win.slot] = 0;
       s_out_n = 0;
       if (pair_part(a.tab, mix64(op.key)) == blockIdx.x) {
-        const uint32_t q = s_own_n++ - own_base;   // (only thread 0 touches the list between the drain and flush_own)
+        const uint32_t q = s_own_n++ - fx.own_base;   // (only thread 0 touches the list between the drain and flush_own)
         if (q < OWN_CAP) { ownk[q] = op.key; ownd[q] = -(long long)win.c; }
         else pair_add_at(a.tab, pbase, (uint32_t)mix64(op.key) & a.tab.rmask, op.key, -(long long)win.c);
       }
@@ -1210,24 +1252,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     // right away — no block barrier sits between the arrival of a count word and the loads of its entries; longer
     // segments (the first rounds of a run) are shared by the whole block afterwards.
     {
-      uint32_t added = 0;
-      auto take = [&](unsigned long long key, long long delta) {
-        const uint64_t hh = mix64(key);
-        const uint32_t fs = smem_tab_find(fk, FRONT_SLOTS - 1, hh, key);
-        if (fs != ~0u) smem_add64(fc + fs, (unsigned long long)delta);
-        else if ((uint32_t)(key >> 32) == op.z || (uint32_t)key == op.z) {   // a pair of the new token: cannot be in the front yet
-          if (!smem_tab_add(nk, nc, NEWP_SLOTS - 1, hh, key, delta, &s_nocc, nlist)) s_refresh = 1;   // too many: the refresh finds them
-        }
-        if (pair_part(a.tab, hh) == blockIdx.x) {
-          const uint32_t q = atomicAdd(&s_own_n, 1u) - own_base;
-          if (q < OWN_CAP) { ownk[q] = key; ownd[q] = delta; }
-          else {
-            uint64_t slot = ~0ull;
-            added += pair_add_at(a.tab, pbase, (uint32_t)hh & a.tab.rmask, key, delta, &slot) ? 1u : 0u;
-            if (slot == ~0ull) s_povf = 1;
-          }
-        }
-      };
+      fx.z = op.z;
       const uint32_t nseg = a.xq.world * a.xq.nblocks, parity = round & 1u, stamp = round % XQ_STAMP_MOD;
       uint32_t flags = 0, big = 0;
       unsigned long long t0 = 0;
@@ -1289,7 +1314,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
               spin_check(spin);
               ld_relaxed2(w + 2 + 2 * e, &w0[e], &w1[e]);
             }
-            take(key, delta);
+            front_take(fx, key, delta);
           }
           continue;
         }
@@ -1310,7 +1335,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
             spin_check(spin);
             w0[e] = ld_relaxed_any(ep + 2 * e, sys); w1[e] = ld_relaxed_any(ep + 2 * e + 1, sys);
           }
-          take(key, delta);
+          front_take(fx, key, delta);
         }
       }
       if (flags) atomicOr(&s_xf, flags);
@@ -1325,10 +1350,9 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
           unsigned long long key = 0;
           long long delta = 0;
           xq_entry(a, round, s_pref, i, &key, &delta, XQ_BOX);
-          take(key, delta);
+          front_take(fx, key, delta);
         }
       }
-      if (added) atomicAdd(&s_occ, added);
     }
     __syncthreads();
     if (dbgb) { const unsigned long long t = gtimer(); bacc[3] += t - bt; bt = t; }
