@@ -684,6 +684,7 @@ constexpr uint32_t FRONT_FILL = 1280;    // members that trigger a refresh (dead
 constexpr uint32_t NEWP_SLOTS = 1024;    // the round's pairs with the new token, aggregated before they meet the bound
 constexpr uint32_t OWN_CAP = 512;        // parked entries of one round (more: added to the partition at once)
 constexpr int FRONT_TOP = 8;             // pairs a partition contributes to a refresh
+constexpr int DRAIN_ITEMS = 3;           // mailbox places per thread in the drain: nblocks x XQ_BOX <= DRAIN_ITEMS x blockDim
 constexpr int XQ_INLINE = 4;             // entries of a REMOTE segment its polling thread handles on its own
 constexpr size_t LOOP_FRONT_BYTES = ((size_t)FRONT_SLOTS * 2 + NEWP_SLOTS * 2 + OWN_CAP * 2) * 8 + (size_t)NEWP_SLOTS * 4;
 // global gather buffer of a refresh: [nblocks flag words, 128 bytes apart][nblocks x FRONT_TOP x (count, key)]
@@ -811,10 +812,9 @@ struct FrontCtx {
   uint64_t pbase;
   PairTab tab;
 };
-// One drained entry.  NOT inlined on purpose: the drain has a dozen call sites (unrolled mailbox places), and with this
-// body inlined in each the loop outgrew the instruction cache — measured on B200: every added copy cost ~0.1 us per
-// merge, the 7-place mailbox version was 0.9 us SLOWER than the 4-place one although it saved a round trip.
-__device__ YT_NOINLINE void front_take(const FrontCtx &f, unsigned long long key, long long delta) {
+// One drained entry.  (Tried out of line, to shrink the loop: the calls and the context struct in local memory made the
+// drain 2 us per merge SLOWER on B200.)
+__device__ __forceinline__ void front_take(const FrontCtx &f, unsigned long long key, long long delta) {
   const uint64_t hh = mix64(key);
   const uint32_t fs = smem_tab_find(f.fk, FRONT_SLOTS - 1, hh, key);
   if (fs != ~0u) smem_add64(f.fc + fs, (unsigned long long)delta);
@@ -832,7 +832,7 @@ __device__ YT_NOINLINE void front_take(const FrontCtx &f, unsigned long long key
   }
 }
 // parked entries -> the partition (all threads of the block)
-__device__ YT_NOINLINE void front_flush(const FrontCtx &f, uint32_t n) {
+__device__ __forceinline__ void front_flush(const FrontCtx &f, uint32_t n) {
   uint32_t added = 0;
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
     const unsigned long long key = f.ownk[i];
@@ -1277,14 +1277,69 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
         __syncthreads();
         if (dbgb) bacc[6] += gtimer() - bt;
       }
+      // LOCAL senders: one work item per (sender block, mailbox place) — every place has its own thread, which polls the
+      // header of its line and loads its place together with it (same line, private to this block): one round trip after
+      // the line's arrival, no barrier, and the entries of a round spread over the whole block instead of piling up on the
+      // sender's polling thread.  (First version: thread j handled all places of sender j — the takes of a warp's 32
+      // senders ran one after the other, 3 - 4 us per merge.)  Up to DRAIN_ITEMS items per thread, loads of all in flight.
+      {
+        const uint32_t nitems = a.xq.nblocks * (uint32_t)XQ_BOX;
+        for (uint32_t base = threadIdx.x; base < nitems; base += (uint32_t)DRAIN_ITEMS * blockDim.x) {   // (one trip with >= 352 threads)
+        unsigned long long hv[DRAIN_ITEMS], e0[DRAIN_ITEMS], e1[DRAIN_ITEMS];
+#pragma unroll
+        for (int k = 0; k < DRAIN_ITEMS; k++) {
+          const uint32_t item = base + (uint32_t)k * blockDim.x;
+          hv[k] = 0; e0[k] = 0; e1[k] = 0;
+          if (item < nitems) {
+            const uint32_t b = item / (uint32_t)XQ_BOX, e = item - b * (uint32_t)XQ_BOX;
+            const unsigned long long *w = reinterpret_cast<const unsigned long long *>(xq_box_line(a.xq, parity, blockIdx.x, b));
+            hv[k] = ld_relaxed(w);
+            ld_relaxed2(w + 2 + 2 * e, &e0[k], &e1[k]);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < DRAIN_ITEMS; k++) {
+          const uint32_t item = base + (uint32_t)k * blockDim.x;
+          if (item >= nitems) continue;
+          const uint32_t b = item / (uint32_t)XQ_BOX, e = item - b * (uint32_t)XQ_BOX;
+          const unsigned long long *w = reinterpret_cast<const unsigned long long *>(xq_box_line(a.xq, parity, blockIdx.x, b));
+          for (uint32_t spin = 0; (uint32_t)(hv[k] >> 32) != round; spin++) {
+            spin_check(spin);
+            hv[k] = ld_relaxed(w);
+            ld_relaxed2(w + 2 + 2 * e, &e0[k], &e1[k]);
+          }
+          const uint32_t c = (uint32_t)hv[k];
+          uint32_t n = c & XQ_CNT_MASK;
+          if (n > a.xq.seg_cap) n = a.xq.seg_cap;
+          if (e == 0) {   // the place-0 thread speaks for the segment
+            if (c & XQ_CNT_OVF) flags |= XQF_OVERFLOW;
+            if (c & XQ_CNT_COMPACT) flags |= XQF_COMPACT;
+            if (c & XQ_CNT_PLIMIT) flags |= XQF_PLIMIT;
+            if (c & XQ_CNT_PFULL) flags |= XQF_PFULL;
+            const uint32_t nb = n < (uint32_t)XQ_BOX ? n : (uint32_t)XQ_BOX;
+            s_pref[a.xq.me * a.xq.nblocks + b] = n - nb;   // the rest sits in the shared segment, from place XQ_BOX on
+            if (n > nb) big = 1;
+          }
+          if (e >= n) continue;
+          unsigned long long key = 0;
+          long long delta = 0;
+          for (uint32_t spin = 0; !xq_unpack(e0[k], e1[k], stamp, &key, &delta); spin++) {   // the header overtook the entry
+            if (dbgb) bacc[11] += 1;
+            spin_check(spin);
+            ld_relaxed2(w + 2 + 2 * e, &e0[k], &e1[k]);
+          }
+          front_take(fx, key, delta);
+        }
+        }
+      }
+      // REMOTE senders (multi-GPU): thread per segment; count word in this block's mailbox row, entries in the shared segment
       for (uint32_t j = threadIdx.x; j < nseg; j += blockDim.x) {
         const uint32_t sd = j / a.xq.nblocks, b = j - sd * a.xq.nblocks;
+        if (sd == a.xq.me) continue;
         const unsigned long long *w = word_of(sd, b);
-        const bool local = sd == a.xq.me;
-        unsigned long long v, v2, e0a = 0, e0b = 0;
+        unsigned long long v;
         for (uint32_t spin = 0;; spin++) {
-          if (local) { ld_relaxed2(w, &v, &v2); ld_relaxed2(w + 2, &e0a, &e0b); }   // header + first entry: one sector
-          else v = ld_relaxed_any(w, sys);
+          v = ld_relaxed_any(w, sys);
           if ((uint32_t)(v >> 32) == round) break;
           spin_check(spin);
         }
@@ -1295,46 +1350,15 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
         if (c & XQ_CNT_PFULL) flags |= XQF_PFULL;
         uint32_t n = c & XQ_CNT_MASK;
         if (n > a.xq.seg_cap) n = a.xq.seg_cap;
-        if (local) {
-          const uint32_t nb = n < (uint32_t)XQ_BOX ? n : (uint32_t)XQ_BOX;
-          s_pref[j] = n - nb;   // the rest sits in the shared segment, from place XQ_BOX on
-          if (n > nb) big = 1;
-          unsigned long long w0[XQ_BOX], w1[XQ_BOX];
-          w0[0] = e0a; w1[0] = e0b;
-#pragma unroll
-          for (int e = 1; e < XQ_BOX; e++)
-            if ((uint32_t)e < nb) ld_relaxed2(w + 2 + 2 * e, &w0[e], &w1[e]);
-#pragma unroll
-          for (int e = 0; e < XQ_BOX; e++) {
-            if ((uint32_t)e >= nb) continue;
-            unsigned long long key = 0;
-            long long delta = 0;
-            for (uint32_t spin = 0; !xq_unpack(w0[e], w1[e], stamp, &key, &delta); spin++) {   // the header overtook the entry
-              if (dbgb) bacc[11] += 1;
-              spin_check(spin);
-              ld_relaxed2(w + 2 + 2 * e, &w0[e], &w1[e]);
-            }
-            front_take(fx, key, delta);
-          }
-          continue;
-        }
         if (n > (uint32_t)XQ_INLINE) { s_pref[j] = n; big = 1; continue; }
         s_pref[j] = 0;
         if (!n) continue;
         const unsigned long long *ep = reinterpret_cast<const unsigned long long *>(xq_base(a.xq, a.xq.me) + xq_seg_off(a.xq, parity, sd, b));
-        unsigned long long w0[XQ_INLINE], w1[XQ_INLINE];
-#pragma unroll
-        for (int e = 0; e < XQ_INLINE; e++)
-          if ((uint32_t)e < n) { w0[e] = ld_relaxed_any(ep + 2 * e, sys); w1[e] = ld_relaxed_any(ep + 2 * e + 1, sys); }
-#pragma unroll
-        for (int e = 0; e < XQ_INLINE; e++) {
-          if ((uint32_t)e >= n) continue;
+        for (uint32_t e = 0; e < n; e++) {
           unsigned long long key = 0;
           long long delta = 0;
-          for (uint32_t spin = 0; !xq_unpack(w0[e], w1[e], stamp, &key, &delta); spin++) {   // the count word overtook the entry
-            spin_check(spin);
-            w0[e] = ld_relaxed_any(ep + 2 * e, sys); w1[e] = ld_relaxed_any(ep + 2 * e + 1, sys);
-          }
+          for (uint32_t spin = 0; !xq_unpack(ld_relaxed_any(ep + 2 * e, sys), ld_relaxed_any(ep + 2 * e + 1, sys), stamp, &key, &delta); spin++)
+            spin_check(spin);   // the count word overtook the entry
           front_take(fx, key, delta);
         }
       }
