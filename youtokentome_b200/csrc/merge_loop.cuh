@@ -733,6 +733,24 @@ __device__ __forceinline__ bool smem_tab_add(unsigned long long *keys, unsigned 
   }
   return false;
 }
+// slot of `key`, inserted if absent; ~0u: the table is full
+__device__ __forceinline__ uint32_t smem_tab_slot(unsigned long long *keys, uint32_t mask, uint64_t hh, unsigned long long key,
+                                                  uint32_t *occ, uint32_t *list) {
+  uint32_t i = smem_home(hh, mask);
+  for (uint32_t p = 0; p <= mask; p++, i = (i + 1) & mask) {
+    unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(keys + i);
+    if (k == PK_EMPTY) {
+      k = atomicCAS(keys + i, PK_EMPTY, key);
+      if (k == PK_EMPTY) {
+        const uint32_t q = atomicAdd(occ, 1u);
+        if (list) list[q] = i;
+        return i;
+      }
+    }
+    if (k == key) return i;
+  }
+  return ~0u;
+}
 __device__ __forceinline__ unsigned long long prio_key(unsigned long long prio) {   // inverse of pair_prio
   const uint32_t mx = 0xffffffffu - (uint32_t)(prio >> 32), mn = 0x7fffffffu - (uint32_t)((prio & 0xffffffffull) >> 1);
   return (prio & 1ull) ? pair_key(mx, mn) : pair_key(mn, mx);
@@ -817,10 +835,14 @@ struct FrontCtx {
 __device__ __forceinline__ void front_take(const FrontCtx &f, unsigned long long key, long long delta) {
   const uint64_t hh = mix64(key);
   const uint32_t fs = smem_tab_find(f.fk, FRONT_SLOTS - 1, hh, key);
-  if (fs != ~0u) smem_add64(f.fc + fs, (unsigned long long)delta);
+  unsigned long long *cnt = nullptr;   // the count this entry changes: a member of the front, or a new pair of this round
+  if (fs != ~0u) cnt = f.fc + fs;
   else if ((uint32_t)(key >> 32) == f.z || (uint32_t)key == f.z) {   // a pair of the new token: cannot be in the front yet
-    if (!smem_tab_add(f.nk, f.nc, NEWP_SLOTS - 1, hh, key, delta, f.s_nocc, f.nlist)) *f.s_refresh = 1;   // too many: the refresh finds them
+    const uint32_t ns = smem_tab_slot(f.nk, NEWP_SLOTS - 1, hh, key, f.s_nocc, f.nlist);
+    if (ns != ~0u) cnt = f.nc + ns;
+    else *f.s_refresh = 1;   // too many new pairs: the refresh finds them
   }
+  if (cnt) smem_add64(cnt, (unsigned long long)delta);
   if (pair_part(f.tab, hh) == f.part) {
     const uint32_t q = atomicAdd(f.s_own_n, 1u) - f.own_base;
     if (q < OWN_CAP) { f.ownk[q] = key; f.ownd[q] = delta; }
@@ -1291,7 +1313,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
           const uint32_t item = base + (uint32_t)k * blockDim.x;
           hv[k] = 0; e0[k] = 0; e1[k] = 0;
           if (item < nitems) {
-            const uint32_t b = item / (uint32_t)XQ_BOX, e = item - b * (uint32_t)XQ_BOX;
+            const uint32_t e = item / a.xq.nblocks, b = item - e * a.xq.nblocks;   // place-major: see below
             const unsigned long long *w = reinterpret_cast<const unsigned long long *>(xq_box_line(a.xq, parity, blockIdx.x, b));
             hv[k] = ld_relaxed(w);
             ld_relaxed2(w + 2 + 2 * e, &e0[k], &e1[k]);
@@ -1301,7 +1323,9 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
         for (int k = 0; k < DRAIN_ITEMS; k++) {
           const uint32_t item = base + (uint32_t)k * blockDim.x;
           if (item >= nitems) continue;
-          const uint32_t b = item / (uint32_t)XQ_BOX, e = item - b * (uint32_t)XQ_BOX;
+          // place-major numbering: the first blockDim items are the places 0, 1, 2 (, 3) of all senders — the ones that
+          // usually hold an entry — so a warp makes ONE pass through front_take; the later items are almost always empty
+          const uint32_t e = item / a.xq.nblocks, b = item - e * a.xq.nblocks;
           const unsigned long long *w = reinterpret_cast<const unsigned long long *>(xq_box_line(a.xq, parity, blockIdx.x, b));
           for (uint32_t spin = 0; (uint32_t)(hv[k] >> 32) != round; spin++) {
             spin_check(spin);
