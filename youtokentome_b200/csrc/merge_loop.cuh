@@ -368,10 +368,21 @@ __device__ __forceinline__ uint32_t warp_apply_word(uint32_t *st, uint32_t cap, 
   const bool h1 = old_changed && ro.nxt < n && pair_key(t, ro.b) != op.key;
   const bool h2 = new_changed && rn.L >= 2;
   const bool h3 = new_changed && rn.nxt < n2;
-  xq_push(a, xo, h0, pair_key(t, t), -f * (long long)(ro.L >> 1), lane);
-  xq_push(a, xo, h1, pair_key(t, ro.b), -f, lane);
-  xq_push(a, xo, h2, pair_key(t2, t2), f * (long long)(rn.L >> 1), lane);
-  xq_push(a, xo, h3, pair_key(t2, rn.b), f, lane);
+  {  // one reservation in the segment for all four kinds (a returning shared-memory atomic costs ~100 cycles)
+    const unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
+    const unsigned m2 = __ballot_sync(0xffffffffu, h2), m3 = __ballot_sync(0xffffffffu, h3);
+    const uint32_t c0 = __popc(m0), c1 = __popc(m1), c2 = __popc(m2), tot = c0 + c1 + c2 + __popc(m3);
+    if (tot) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(xo.s_n, tot);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      const unsigned below = (1u << lane) - 1u;
+      if (h0) xq_store(a, xo, base + __popc(m0 & below), pair_key(t, t), -f * (long long)(ro.L >> 1));
+      if (h1) xq_store(a, xo, base + c0 + __popc(m1 & below), pair_key(t, ro.b), -f);
+      if (h2) xq_store(a, xo, base + c0 + c1 + __popc(m2 & below), pair_key(t2, t2), f * (long long)(rn.L >> 1));
+      if (h3) xq_store(a, xo, base + c0 + c1 + c2 + __popc(m3 & below), pair_key(t2, rn.b), f);
+    }
+  }
   return n - n2;
 }
 
@@ -1066,16 +1077,15 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     if (dbgb) { const unsigned long long t = gtimer(); bacc[0] += t - bt; bt = t; }
     // every occurrence of (x,y) is merged below and no count changes are emitted for it: the front drops it here, its
     // owner parks the matching update of the partition (the front's count is exact)
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0) {   // (no barrier needed behind this: the apply phase touches none of it)
       fc[win.slot] = 0;
-      s_out_n = 0;
+      s_nocc = 0;             // last read in the previous iteration's fold, next written in this iteration's drain
       if (pair_part(a.tab, mix64(op.key)) == blockIdx.x) {
         const uint32_t q = s_own_n++ - fx.own_base;   // (only thread 0 touches the list between the drain and flush_own)
         if (q < OWN_CAP) { ownk[q] = op.key; ownd[q] = -(long long)win.c; }
         else pair_add_at(a.tab, pbase, (uint32_t)mix64(op.key) & a.tab.rmask, op.key, -(long long)win.c);
       }
     }
-    __syncthreads();
     // ---------------- apply x y -> z: count changes go to this block's segment of round + 1 (on every rank)
     const uint32_t nround = round + 1;
     XqOut xo;
@@ -1267,6 +1277,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     // ---------------- while the other blocks finish their apply phase: the parked entries of the previous round (and
     // the consumed pair) go into this block's partition
     flush_own();
+    if (threadIdx.x == 0) s_out_n = 0;   // (read by all before flush_own's barriers; next used in the next apply phase)
     if (gtid == 0) tq2b = gtimer();
     if (dbgb) { const unsigned long long t = gtimer(); bacc[2] += t - bt; bt = t; }
     // ---------------- drain: the count changes of this merge, from every block of every GPU.  Thread j polls the count
@@ -1418,8 +1429,6 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
         if (better(bd, cand)) continue;
         if (!smem_tab_add(fk, fc, FRONT_SLOTS - 1, mix64(k), k, (long long)c, &s_focc)) s_refresh = 1;
       }
-      __syncthreads();
-      if (threadIdx.x == 0) s_nocc = 0;
     }
     __syncthreads();
     if (dbgb) { const unsigned long long t = gtimer(); bacc[4] += t - bt; bt = t; }
