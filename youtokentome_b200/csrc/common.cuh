@@ -90,9 +90,9 @@ struct yttm_ctx {
   uint32_t p_rmask = 0, p_nparts = 0;
 
   // ---- exchange buffer of the merge loop (merge_loop.cuh); world > 1: peers[] are the other ranks' regions
-  ytc::DevBuf xq_buf, xq_arrive, xq_box;
+  ytc::DevBuf xq_buf, xq_arrive;
   uint32_t xq_world = 1, xq_me = 0, xq_seg_cap = 0, xq_nblocks = 0;
-  uint64_t xq_per_sender = 0, xq_bytes = 0, xq_box_bytes = 0;
+  uint64_t xq_per_sender = 0, xq_bytes = 0;
   void *xq_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool xq_peer_ipc[8] = {false, false, false, false, false, false, false, false};
   bool xq_connected = false;

@@ -56,25 +56,27 @@ constexpr uint32_t XQ_CNT_COMPACT = 0x20000000u;  // count word: > 25 % of the b
 constexpr uint32_t XQ_CNT_PLIMIT = 0x10000000u;   // count word: the block's partition is over the load limit
 constexpr uint32_t XQ_CNT_PFULL = 0x08000000u;    // count word: the block's partition ran full (an update was lost)
 constexpr uint32_t XQ_CNT_MASK = 0x07ffffffu;
+// What bounds the exchange on B200 is the SM's load/store unit, not L2: a warp-wide load or store costs ~2 cycles per
+// 128-byte line it touches, so 32 lanes on 32 lines are 64 cycles, and a POLL LOOP that does this from 16 warps keeps
+// the unit busy for a microsecond per sweep (ncu, profiles/r02_merge_loop_stalls.md).  Hence the layout:
+//   * count words: one ROW per reader block (XqHdr::counts[reader][sender]) — the words a block polls are consecutive
+//     (a warp's poll touches 2 lines) and are read by nobody else (no hot L2 lines);
+//   * the first XQ_BOX entries of every segment sit in a place-major MATRIX (XqHdr::places[place][sender]): lanes that
+//     handle the same place of consecutive senders read consecutive 16-byte slots (4 lines per warp);
+//   * entries XQ_BOX.. of a segment (the first rounds of a run) stay in the sender's own segment.
+constexpr int XQ_BOX = 7;
 struct XqHdr {
   // MAILBOXES: the count word (round << 32) | flags | entries of the sender's segment b exists once per READER block r, at
   // counts[r * XQ_MAX_BLOCKS + b]: the sender stores it nblocks times (posted stores to distinct lines), reader r polls
   // its own row — nblocks consecutive words that nobody else reads.  (Round 2, measured on B200: with one word per
   // segment, polled by all 148 blocks, a poll round was 21.9 k sector requests on 148 lines shared by every SM.)
   unsigned long long counts[XQ_MAX_BLOCKS * XQ_MAX_BLOCKS];
+  uint4 places[XQ_BOX * XQ_MAX_BLOCKS];   // entry e (< XQ_BOX) of the sender's block b: places[e * XQ_MAX_BLOCKS + b]
 };
 // count word of sender block `sb` in the mailbox row of reader block `rb`
 __device__ __forceinline__ unsigned long long *xq_cnt(XqHdr *h, uint32_t rb, uint32_t sb) { return &h->counts[(size_t)rb * XQ_MAX_BLOCKS + sb]; }
-// MAILBOX LINES (local senders only): 128 bytes per (parity, reader block, sender block) = a 16-byte header (the count
-// word, twice) + the first XQ_BOX entries of the sender's segment.  The sender stores the line once per reader; a
-// reader's lines are read by nobody else, and header + first entry share a 32-byte sector, so the usual segment (0 or 1
-// entries) costs ONE L2 round trip after its arrival.  (Round 2, measured on B200: with shared segments every entry line
-// is loaded by all 148 SMs at the same moment and the requests queue at its L2 slice — ~1 us per dependent load, two of
-// them per merge.)  Entries XQ_BOX.. of a segment, and everything a REMOTE rank reads, live in the shared segments.
-constexpr int XQ_BOX = 7;
 struct Xq {
   unsigned char *base[XQ_MAX_WORLD];  // region of every rank; base[me] is local memory
-  unsigned char *box;                 // mailbox lines of this rank: [parity][reader][sender][128]
   uint32_t world, me, nblocks, seg_cap;
   unsigned long long per_sender;      // bytes of one {header, entries} slot
 };
@@ -87,9 +89,6 @@ __device__ __forceinline__ unsigned char *xq_base(const Xq &x, uint32_t rank) {
 }
 __device__ __forceinline__ XqHdr *xq_hdr(const Xq &x, uint32_t rank, uint32_t parity, uint32_t sender) {
   return reinterpret_cast<XqHdr *>(xq_base(x, rank) + (size_t)(parity * x.world + sender) * x.per_sender);
-}
-__device__ __forceinline__ unsigned char *xq_box_line(const Xq &x, uint32_t parity, uint32_t reader, uint32_t sender) {
-  return x.box + ((size_t)(parity * x.nblocks + reader) * x.nblocks + sender) * 128;
 }
 // byte offset (inside any rank's region) of segment `block` of (parity, sender)
 __device__ __forceinline__ size_t xq_seg_off(const Xq &x, uint32_t parity, uint32_t sender, uint32_t block) {
@@ -134,9 +133,10 @@ __device__ __forceinline__ unsigned long long ld_relaxed_any(const unsigned long
 #endif
 }
 // two consecutive 64-bit words (16-byte aligned) with one relaxed load
-__device__ __forceinline__ void ld_relaxed2(const unsigned long long *p, unsigned long long *a, unsigned long long *b) {
+__device__ __forceinline__ void ld_relaxed2(const unsigned long long *p, unsigned long long *a, unsigned long long *b, bool sys) {
 #ifndef YT_SIMT_EMU
-  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(*a), "=l"(*b) : "l"(p) : "memory");
+  if (sys) asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(*a), "=l"(*b) : "l"(p) : "memory");
+  else asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(*a), "=l"(*b) : "l"(p) : "memory");
 #else
   *a = __atomic_load_n(p, __ATOMIC_RELAXED);
   *b = __atomic_load_n(p + 1, __ATOMIC_RELAXED);
@@ -264,15 +264,17 @@ struct XqOut {
   size_t off;        // byte offset of the segment inside a region
   uint32_t *s_n;     // shared-memory entry counter of the block (may run past cap: overflow)
   uint32_t stamp;    // round % XQ_STAMP_MOD of the entries
-  uint4 *s_box;      // shared-memory copy of the first XQ_BOX entries (they go out with the mailbox lines)
+  uint32_t parity;   // round & 1
 };
 __device__ __forceinline__ void xq_store(const LoopArgs &a, const XqOut &o, uint32_t i, unsigned long long key,
                                          long long delta) {
   if (i >= a.xq.seg_cap) return;  // overflow: the count word carries the flag, the host rebuilds the table
   const uint4 e = xq_pack(o.stamp, key, delta);
-  if (i < (uint32_t)XQ_BOX) {
-    o.s_box[i] = e;
-    if (a.xq.world == 1) return;   // nobody reads these places of the shared segment
+  if (i < (uint32_t)XQ_BOX) {   // the place-major matrix of the round
+#pragma unroll
+    for (int d = 0; d < XQ_MAX_WORLD; d++)
+      if ((uint32_t)d < a.xq.world) xq_hdr(a.xq, (uint32_t)d, o.parity, a.xq.me)->places[i * XQ_MAX_BLOCKS + blockIdx.x] = e;
+    return;
   }
 #pragma unroll
   for (int d = 0; d < XQ_MAX_WORLD; d++)
@@ -631,9 +633,9 @@ __device__ __forceinline__ void xq_prefix(const LoopArgs &a, uint32_t *s_pref, u
   __syncthreads();
 }
 // entry i (0 <= i < s_pref[nseg]) of round `round` in this rank's region; spins until both words carry the round's stamp
-// local_off: places of a LOCAL sender's segment that travelled by mailbox instead (the merge loop: XQ_BOX)
+// first: index of the first entry that sits in the segment (the merge loop keeps entries 0 .. XQ_BOX-1 in XqHdr::places)
 __device__ __forceinline__ void xq_entry(const LoopArgs &a, uint32_t round, const uint32_t *s_pref, uint32_t i,
-                                         unsigned long long *key, long long *delta, uint32_t local_off = 0) {
+                                         unsigned long long *key, long long *delta, uint32_t first = 0) {
   const uint32_t nseg = a.xq.world * a.xq.nblocks;
   uint32_t lo = 0, hi = nseg;  // largest j with s_pref[j] <= i (empty segments share a prefix value: take the last)
   while (hi - lo > 1) {
@@ -642,7 +644,7 @@ __device__ __forceinline__ void xq_entry(const LoopArgs &a, uint32_t round, cons
   }
   const uint32_t s = lo / a.xq.nblocks, b = lo - s * a.xq.nblocks;
   const unsigned long long *ep = reinterpret_cast<const unsigned long long *>(
-      xq_base(a.xq, a.xq.me) + xq_seg_off(a.xq, round & 1u, s, b) + (size_t)(i - s_pref[lo] + (s == a.xq.me ? local_off : 0u)) * sizeof(uint4));
+      xq_base(a.xq, a.xq.me) + xq_seg_off(a.xq, round & 1u, s, b) + (size_t)(i - s_pref[lo] + first) * sizeof(uint4));
   const bool sys = a.xq.world > 1;
   unsigned long long t0 = 0;
   for (uint32_t spin = 0; !xq_unpack(ld_relaxed_any(ep, sys), ld_relaxed_any(ep + 1, sys), round % XQ_STAMP_MOD, key, delta); spin++) {
@@ -695,8 +697,7 @@ constexpr uint32_t FRONT_FILL = 1280;    // members that trigger a refresh (dead
 constexpr uint32_t NEWP_SLOTS = 1024;    // the round's pairs with the new token, aggregated before they meet the bound
 constexpr uint32_t OWN_CAP = 512;        // parked entries of one round (more: added to the partition at once)
 constexpr int FRONT_TOP = 8;             // pairs a partition contributes to a refresh
-constexpr int DRAIN_ITEMS = 3;           // mailbox places per thread in the drain: nblocks x XQ_BOX <= DRAIN_ITEMS x blockDim
-constexpr int XQ_INLINE = 4;             // entries of a REMOTE segment its polling thread handles on its own
+constexpr int DRAIN_ITEMS = 3;           // (place, segment) items per thread and trip of the drain
 constexpr size_t LOOP_FRONT_BYTES = ((size_t)FRONT_SLOTS * 2 + NEWP_SLOTS * 2 + OWN_CAP * 2) * 8 + (size_t)NEWP_SLOTS * 4;
 // global gather buffer of a refresh: [nblocks flag words, 128 bytes apart][nblocks x FRONT_TOP x (count, key)]
 YT_HD size_t front_buf_words(uint32_t nblocks) { return (size_t)nblocks * 16 + (size_t)nblocks * FRONT_TOP * 2; }
@@ -879,7 +880,6 @@ __device__ __forceinline__ void front_flush(const FrontCtx &f, uint32_t n) {
 __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   __shared__ Best s_warp[32];
   __shared__ Best s_bound, s_tmp;   // the bound of the front / scratch of a refresh
-  __shared__ uint4 s_box[XQ_BOX + 1];   // the first entries of this block's segment (xq_store)
   __shared__ uint32_t s_dead;   // token slots of this block tombstoned in this launch
   __shared__ uint32_t s_defer_n, s_direct, s_out_n, s_occ, s_xf, s_povf, s_focc, s_nocc, s_own_n, s_refresh, s_scan[33];
   const bool sys = a.xq.world > 1;
@@ -1092,7 +1092,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     xo.off = xq_seg_off(a.xq, nround & 1u, a.xq.me, blockIdx.x);
     xo.s_n = &s_out_n;
     xo.stamp = nround % XQ_STAMP_MOD;
-    xo.s_box = s_box;
+    xo.parity = nround & 1u;
     unsigned long long dead = 0;
     if (a.resident) {
       if (rw1 > rw0) dead = process_tile(stok, soff, rw1 - rw0, soff[rw1 - rw0], s_claim,
@@ -1251,23 +1251,10 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       if (s_occ > a.part_limit) word |= XQ_CNT_PLIMIT;   // state of the partition as of the last flush
       if (s_povf) word |= XQ_CNT_PFULL;
       const unsigned long long cw = ((unsigned long long)nround << 32) | word;
-      // local readers: one mailbox line each = header + the first entries
-      {
-        const uint32_t nb = n < (uint32_t)XQ_BOX ? n : (uint32_t)XQ_BOX;
-        const uint4 hd = make_uint4((uint32_t)cw, (uint32_t)(cw >> 32), (uint32_t)cw, (uint32_t)(cw >> 32));
-        for (uint32_t r = threadIdx.x; r < a.xq.nblocks; r += blockDim.x) {
-          uint4 *line = reinterpret_cast<uint4 *>(xq_box_line(a.xq, nround & 1u, r, blockIdx.x));
-          for (uint32_t e = 0; e < nb; e++) line[1 + e] = s_box[e];
-          line[0] = hd;
-        }
-      }
-      // readers on the other ranks: the count word into their mailbox rows (their entries sit in the shared segments)
-      if (a.xq.world > 1) {
-        const uint32_t nbox = a.xq.world * a.xq.nblocks;
-        for (uint32_t t = threadIdx.x; t < nbox; t += blockDim.x) {
-          const uint32_t d = t / a.xq.nblocks, rb = t - d * a.xq.nblocks;
-          if (d != a.xq.me) st_relaxed_any(xq_cnt(xq_hdr(a.xq, d, nround & 1u, a.xq.me), rb, blockIdx.x), cw, true);
-        }
+      const uint32_t nbox = a.xq.world * a.xq.nblocks;
+      for (uint32_t t = threadIdx.x; t < nbox; t += blockDim.x) {
+        const uint32_t d = t / a.xq.nblocks, rb = t - d * a.xq.nblocks;
+        st_relaxed_any(xq_cnt(xq_hdr(a.xq, d, nround & 1u, a.xq.me), rb, blockIdx.x), cw, sys);
       }
       if (threadIdx.x == 0) s_xf = 0;   // accumulator of the poll below
     }
@@ -1298,103 +1285,71 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
           else if (gtimer() - t0 > a.spin_limit_ns) loop_trap();
         }
       };
-      auto word_of = [&](uint32_t sd, uint32_t b) -> const unsigned long long * {   // where segment (sd, b)'s count word arrives
-        return sd == a.xq.me ? reinterpret_cast<const unsigned long long *>(xq_box_line(a.xq, parity, blockIdx.x, b))
-                             : xq_cnt(xq_hdr(a.xq, a.xq.me, parity, sd), blockIdx.x, b);
-      };
       if (a.dbg & 16u) {   // diagnostic: when have ALL count words arrived (hop + skew of the apply phases)?
         for (uint32_t j = threadIdx.x; j < nseg; j += blockDim.x) {
           const uint32_t sd = j / a.xq.nblocks, b = j - sd * a.xq.nblocks;
-          for (uint32_t spin = 0; (uint32_t)(ld_relaxed_any(word_of(sd, b), sys) >> 32) != round; spin++) spin_check(spin);
+          for (uint32_t spin = 0; (uint32_t)(ld_relaxed_any(xq_cnt(xq_hdr(a.xq, a.xq.me, parity, sd), blockIdx.x, b), sys) >> 32) != round; spin++) spin_check(spin);
         }
         __syncthreads();
         if (dbgb) bacc[6] += gtimer() - bt;
       }
-      // LOCAL senders: one work item per (sender block, mailbox place) — every place has its own thread, which polls the
-      // header of its line and loads its place together with it (same line, private to this block): one round trip after
-      // the line's arrival, no barrier, and the entries of a round spread over the whole block instead of piling up on the
-      // sender's polling thread.  (First version: thread j handled all places of sender j — the takes of a warp's 32
-      // senders ran one after the other, 3 - 4 us per merge.)  Up to DRAIN_ITEMS items per thread, loads of all in flight.
+      // One work item per (place e, segment j), numbered place-major: item = e * nseg + j.  The thread of an item polls
+      // the count word of segment j in this block's row and loads place e of that segment from the matrix — consecutive
+      // lanes touch consecutive words / slots, and the entries of a round spread over the whole block.  No barrier between
+      // the arrival of a count word and the handling of its entries.  DRAIN_ITEMS items per thread and trip, their loads
+      // all in flight.  (Versions measured before this one: thread j handling all places of sender j — the entry
+      // handlers of a warp's 32 senders ran one after the other; one private 128-byte line per (reader, sender) — every
+      // lane on its own line, 64 cycles of load/store unit per warp instruction, polled: 1 us per sweep.)
       {
-        const uint32_t nitems = a.xq.nblocks * (uint32_t)XQ_BOX;
-        for (uint32_t base = threadIdx.x; base < nitems; base += (uint32_t)DRAIN_ITEMS * blockDim.x) {   // (one trip with >= 352 threads)
-        unsigned long long hv[DRAIN_ITEMS], e0[DRAIN_ITEMS], e1[DRAIN_ITEMS];
+        const uint32_t nitems = nseg * (uint32_t)XQ_BOX;
+        for (uint32_t base = threadIdx.x; base < nitems; base += (uint32_t)DRAIN_ITEMS * blockDim.x) {   // (one trip: 1 GPU, >= 352 threads)
+          unsigned long long hv[DRAIN_ITEMS], e0[DRAIN_ITEMS], e1[DRAIN_ITEMS];
+          const unsigned long long *wp[DRAIN_ITEMS], *ep[DRAIN_ITEMS];
 #pragma unroll
-        for (int k = 0; k < DRAIN_ITEMS; k++) {
-          const uint32_t item = base + (uint32_t)k * blockDim.x;
-          hv[k] = 0; e0[k] = 0; e1[k] = 0;
-          if (item < nitems) {
-            const uint32_t e = item / a.xq.nblocks, b = item - e * a.xq.nblocks;   // place-major: see below
-            const unsigned long long *w = reinterpret_cast<const unsigned long long *>(xq_box_line(a.xq, parity, blockIdx.x, b));
-            hv[k] = ld_relaxed(w);
-            ld_relaxed2(w + 2 + 2 * e, &e0[k], &e1[k]);
+          for (int k = 0; k < DRAIN_ITEMS; k++) {
+            const uint32_t item = base + (uint32_t)k * blockDim.x;
+            hv[k] = 0; e0[k] = 0; e1[k] = 0; wp[k] = nullptr; ep[k] = nullptr;
+            if (item < nitems) {
+              const uint32_t e = item / nseg, j = item - e * nseg, sd = j / a.xq.nblocks, b = j - sd * a.xq.nblocks;
+              XqHdr *h = xq_hdr(a.xq, a.xq.me, parity, sd);
+              wp[k] = xq_cnt(h, blockIdx.x, b);
+              ep[k] = reinterpret_cast<const unsigned long long *>(h->places + e * XQ_MAX_BLOCKS + b);
+              hv[k] = ld_relaxed_any(wp[k], sys);
+              ld_relaxed2(ep[k], &e0[k], &e1[k], sys);
+            }
           }
-        }
 #pragma unroll
-        for (int k = 0; k < DRAIN_ITEMS; k++) {
-          const uint32_t item = base + (uint32_t)k * blockDim.x;
-          if (item >= nitems) continue;
-          // place-major numbering: the first blockDim items are the places 0, 1, 2 (, 3) of all senders — the ones that
-          // usually hold an entry — so a warp makes ONE pass through front_take; the later items are almost always empty
-          const uint32_t e = item / a.xq.nblocks, b = item - e * a.xq.nblocks;
-          const unsigned long long *w = reinterpret_cast<const unsigned long long *>(xq_box_line(a.xq, parity, blockIdx.x, b));
-          for (uint32_t spin = 0; (uint32_t)(hv[k] >> 32) != round; spin++) {
-            spin_check(spin);
-            hv[k] = ld_relaxed(w);
-            ld_relaxed2(w + 2 + 2 * e, &e0[k], &e1[k]);
+          for (int k = 0; k < DRAIN_ITEMS; k++) {
+            const uint32_t item = base + (uint32_t)k * blockDim.x;
+            if (item >= nitems) continue;
+            const uint32_t e = item / nseg, j = item - e * nseg;
+            for (uint32_t spin = 0; (uint32_t)(hv[k] >> 32) != round; spin++) {
+              spin_check(spin);
+              hv[k] = ld_relaxed_any(wp[k], sys);
+              ld_relaxed2(ep[k], &e0[k], &e1[k], sys);
+            }
+            const uint32_t c = (uint32_t)hv[k];
+            uint32_t n = c & XQ_CNT_MASK;
+            if (n > a.xq.seg_cap) n = a.xq.seg_cap;
+            if (e == 0) {   // the place-0 thread speaks for the segment
+              if (c & XQ_CNT_OVF) flags |= XQF_OVERFLOW;
+              if (c & XQ_CNT_COMPACT) flags |= XQF_COMPACT;
+              if (c & XQ_CNT_PLIMIT) flags |= XQF_PLIMIT;
+              if (c & XQ_CNT_PFULL) flags |= XQF_PFULL;
+              const uint32_t nb = n < (uint32_t)XQ_BOX ? n : (uint32_t)XQ_BOX;
+              s_pref[j] = n - nb;   // the rest sits in the sender's segment, from entry XQ_BOX on
+              if (n > nb) big = 1;
+            }
+            if (e >= n) continue;
+            unsigned long long key = 0;
+            long long delta = 0;
+            for (uint32_t spin = 0; !xq_unpack(e0[k], e1[k], stamp, &key, &delta); spin++) {   // the count word overtook the entry
+              if (dbgb) bacc[11] += 1;
+              spin_check(spin);
+              ld_relaxed2(ep[k], &e0[k], &e1[k], sys);
+            }
+            front_take(fx, key, delta);
           }
-          const uint32_t c = (uint32_t)hv[k];
-          uint32_t n = c & XQ_CNT_MASK;
-          if (n > a.xq.seg_cap) n = a.xq.seg_cap;
-          if (e == 0) {   // the place-0 thread speaks for the segment
-            if (c & XQ_CNT_OVF) flags |= XQF_OVERFLOW;
-            if (c & XQ_CNT_COMPACT) flags |= XQF_COMPACT;
-            if (c & XQ_CNT_PLIMIT) flags |= XQF_PLIMIT;
-            if (c & XQ_CNT_PFULL) flags |= XQF_PFULL;
-            const uint32_t nb = n < (uint32_t)XQ_BOX ? n : (uint32_t)XQ_BOX;
-            s_pref[a.xq.me * a.xq.nblocks + b] = n - nb;   // the rest sits in the shared segment, from place XQ_BOX on
-            if (n > nb) big = 1;
-          }
-          if (e >= n) continue;
-          unsigned long long key = 0;
-          long long delta = 0;
-          for (uint32_t spin = 0; !xq_unpack(e0[k], e1[k], stamp, &key, &delta); spin++) {   // the header overtook the entry
-            if (dbgb) bacc[11] += 1;
-            spin_check(spin);
-            ld_relaxed2(w + 2 + 2 * e, &e0[k], &e1[k]);
-          }
-          front_take(fx, key, delta);
-        }
-        }
-      }
-      // REMOTE senders (multi-GPU): thread per segment; count word in this block's mailbox row, entries in the shared segment
-      for (uint32_t j = threadIdx.x; j < nseg; j += blockDim.x) {
-        const uint32_t sd = j / a.xq.nblocks, b = j - sd * a.xq.nblocks;
-        if (sd == a.xq.me) continue;
-        const unsigned long long *w = word_of(sd, b);
-        unsigned long long v;
-        for (uint32_t spin = 0;; spin++) {
-          v = ld_relaxed_any(w, sys);
-          if ((uint32_t)(v >> 32) == round) break;
-          spin_check(spin);
-        }
-        const uint32_t c = (uint32_t)v;
-        if (c & XQ_CNT_OVF) flags |= XQF_OVERFLOW;
-        if (c & XQ_CNT_COMPACT) flags |= XQF_COMPACT;
-        if (c & XQ_CNT_PLIMIT) flags |= XQF_PLIMIT;
-        if (c & XQ_CNT_PFULL) flags |= XQF_PFULL;
-        uint32_t n = c & XQ_CNT_MASK;
-        if (n > a.xq.seg_cap) n = a.xq.seg_cap;
-        if (n > (uint32_t)XQ_INLINE) { s_pref[j] = n; big = 1; continue; }
-        s_pref[j] = 0;
-        if (!n) continue;
-        const unsigned long long *ep = reinterpret_cast<const unsigned long long *>(xq_base(a.xq, a.xq.me) + xq_seg_off(a.xq, parity, sd, b));
-        for (uint32_t e = 0; e < n; e++) {
-          unsigned long long key = 0;
-          long long delta = 0;
-          for (uint32_t spin = 0; !xq_unpack(ld_relaxed_any(ep + 2 * e, sys), ld_relaxed_any(ep + 2 * e + 1, sys), stamp, &key, &delta); spin++)
-            spin_check(spin);   // the count word overtook the entry
-          front_take(fx, key, delta);
         }
       }
       if (flags) atomicOr(&s_xf, flags);

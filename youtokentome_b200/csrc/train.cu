@@ -616,14 +616,10 @@ int xq_alloc(yttm_ctx *c, uint32_t me, uint32_t world) {
   c->xq_bytes = 2ull * world * c->xq_per_sender;
   YT_CUDA(c, c->xq_buf.reserve(c->xq_bytes));
   YT_CUDA(c, c->xq_arrive.reserve(64));
-  // mailbox lines of the local blocks: all-ones = a round and stamps no real round uses
-  c->xq_box_bytes = 2ull * c->xq_nblocks * c->xq_nblocks * 128;
-  YT_CUDA(c, c->xq_box.reserve(c->xq_box_bytes));
-  YT_CUDA(c, cudaMemsetAsync(c->xq_box.p, 0xff, c->xq_box_bytes, c->stream));
   // entries start as all-ones (a stamp no round uses), count words as round 0
   YT_CUDA(c, cudaMemsetAsync(c->xq_buf.p, 0xff, c->xq_bytes, c->stream));
   for (uint32_t k = 0; k < 2 * world; k++)
-    YT_CUDA(c, cudaMemsetAsync(c->xq_buf.as<unsigned char>() + k * c->xq_per_sender, 0, sizeof(XqHdr), c->stream));
+    YT_CUDA(c, cudaMemsetAsync(c->xq_buf.as<unsigned char>() + k * c->xq_per_sender, 0, offsetof(XqHdr, places), c->stream));   // count words: round 0; entry places stay all-ones
   YT_CUDA(c, cudaMemsetAsync(c->xq_arrive.p, 0, 64, c->stream));
   YT_CUDA(c, cudaStreamSynchronize(c->stream));
   for (int d = 0; d < XQ_MAX_WORLD; d++) c->xq_peer[d] = nullptr;
@@ -641,7 +637,6 @@ int xq_args(yttm_ctx *c, LoopArgs *a) {
   for (int d = 0; d < XQ_MAX_WORLD; d++) a->xq.base[d] = static_cast<unsigned char *>(c->xq_peer[d < (int)c->xq_world ? d : (int)c->xq_me]);
   a->xq.world = c->xq_world; a->xq.me = c->xq_me; a->xq.nblocks = c->xq_nblocks; a->xq.seg_cap = c->xq_seg_cap;
   a->xq.per_sender = c->xq_per_sender;
-  a->xq.box = static_cast<unsigned char *>(c->xq_box.p);
   a->spin_limit_ns = xq_spin_limit_ns();
   return 0;
 }
@@ -882,7 +877,7 @@ void yttm_ctx_destroy(yttm_ctx *c) {
   cudaStreamSynchronize(c->stream);
   ytc::DevBuf *bufs[] = {&c->text_buf, &c->hist, &c->cp2id, &c->wkey, &c->wcnt, &c->wpos, &c->wfreq, &c->wlen,
                          &c->scan_tmp, &c->counters, &c->tok[0], &c->tok[1], &c->off[0], &c->off[1], &c->freq[0],
-                         &c->freq[1], &c->pkey, &c->pcnt, &c->scratch_key, &c->scratch_cnt, &c->ctl, &c->frontbuf, &c->xq_box, &c->tiles, &c->defer,
+                         &c->freq[1], &c->pkey, &c->pcnt, &c->scratch_key, &c->scratch_cnt, &c->ctl, &c->frontbuf, &c->tiles, &c->defer,
                          &c->d_rules, &c->d_rfreq, &c->xq_arrive, &c->xq_buf};
   for (int d = 0; d < 8; d++)
     if (c->xq_peer_ipc[d] && c->xq_peer[d]) { cudaIpcCloseMemHandle(c->xq_peer[d]); c->xq_peer[d] = nullptr; }
