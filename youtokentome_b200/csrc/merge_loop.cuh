@@ -692,13 +692,17 @@ __device__ __forceinline__ void xq_drain(const LoopArgs &a, uint32_t round, uint
 // The pair table in HBM/L2 stays the ground truth (rebuilds, refreshes, the multi-GPU table build): a block parks the
 // entries it owns in shared memory during the drain and adds them to its partition while it waits for the other blocks'
 // next count words — off the critical path of the merge.
-constexpr uint32_t FRONT_SLOTS = 2048;   // shared-memory hash table (key, count), per block
-constexpr uint32_t FRONT_FILL = 1280;    // members that trigger a refresh (dead members are only dropped there)
+// (Load factor: the drain looks every entry of a round up, mostly keys that are NOT in the front, and a miss walks to the
+// end of its cluster; at 2048 slots / up to 1280 members the longest clusters of linear probing cost ~3 us per merge
+// — some lane of some warp hit one every round.  4096 slots / <= 1024 members: clusters of a few slots.)
+constexpr uint32_t FRONT_SLOTS = 4096;   // shared-memory hash table (key, count), per block
+constexpr uint32_t FRONT_FILL = 1024;    // members that trigger a refresh (dead members are only dropped there)
+constexpr uint32_t FRONT_LIST = FRONT_FILL + 1024 + 64;   // member list: a round adds at most NEWP_SLOTS members
 constexpr uint32_t NEWP_SLOTS = 1024;    // the round's pairs with the new token, aggregated before they meet the bound
-constexpr uint32_t OWN_CAP = 512;        // parked entries of one round (more: added to the partition at once)
-constexpr int FRONT_TOP = 8;             // pairs a partition contributes to a refresh
+constexpr uint32_t OWN_CAP = 256;        // parked entries of one round (more: added to the partition at once)
+constexpr int FRONT_TOP = 6;             // most pairs a partition contributes to a refresh (LoopArgs::front_top, default 4)
 constexpr int DRAIN_ITEMS = 3;           // (place, segment) items per thread and trip of the drain
-constexpr size_t LOOP_FRONT_BYTES = ((size_t)FRONT_SLOTS * 2 + NEWP_SLOTS * 2 + OWN_CAP * 2) * 8 + (size_t)NEWP_SLOTS * 4;
+constexpr size_t LOOP_FRONT_BYTES = ((size_t)FRONT_SLOTS * 2 + NEWP_SLOTS * 2 + OWN_CAP * 2) * 8 + ((size_t)NEWP_SLOTS + FRONT_LIST) * 4;
 // global gather buffer of a refresh: [nblocks flag words, 128 bytes apart][nblocks x FRONT_TOP x (count, key)]
 YT_HD size_t front_buf_words(uint32_t nblocks) { return (size_t)nblocks * 16 + (size_t)nblocks * FRONT_TOP * 2; }
 
@@ -894,7 +898,8 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   unsigned long long *ownk = nc + NEWP_SLOTS;
   long long *ownd = reinterpret_cast<long long *>(ownk + OWN_CAP);
   uint32_t *nlist = reinterpret_cast<uint32_t *>(ownd + OWN_CAP);   // slots of nk taken in this round
-  uint32_t *stok = nlist + NEWP_SLOTS;
+  uint32_t *flist = nlist + NEWP_SLOTS;                              // slots of fk taken since the last refresh
+  uint32_t *stok = flist + FRONT_LIST;
   uint32_t *soff = stok + a.smem_tok_cap;
   // RESIDENT only: word frequencies behind the offsets (8-byte aligned: both caps are even)
   unsigned long long *sfreq = reinterpret_cast<unsigned long long *>(soff + a.smem_word_cap + 2);
@@ -972,7 +977,9 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   // the largest member of the front (.slot = its slot in the front), in every thread; one block barrier
   auto select = [&]() {
     Best b{0, 0, 0};
-    for (uint32_t i = threadIdx.x; i < FRONT_SLOTS; i += blockDim.x) {
+    const uint32_t nm = s_focc;   // members (<= FRONT_LIST)
+    for (uint32_t q = threadIdx.x; q < nm; q += blockDim.x) {
+      const uint32_t i = flist[q];
       const unsigned long long c = fc[i];
       if (c == 0 || c < b.c) continue;
       const unsigned long long k = fk[i];
@@ -1027,7 +1034,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     }
     for (unsigned e = threadIdx.x; e < gridDim.x * FRONT_TOP; e += blockDim.x) {
       const unsigned long long c = ld_relaxed(gdata + (size_t)e * 2), key = ld_relaxed(gdata + (size_t)e * 2 + 1);
-      if (c) smem_tab_add(fk, fc, FRONT_SLOTS - 1, mix64(key), key, (long long)c, &s_focc);   // 148 x 8 < FRONT_SLOTS
+      if (c) smem_tab_add(fk, fc, FRONT_SLOTS - 1, mix64(key), key, (long long)c, &s_focc, flist);   // nblocks x FRONT_TOP <= FRONT_FILL
     }
     block_best(bd, s_warp, &s_bound);
   };
@@ -1382,7 +1389,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
         if ((long long)c <= 0) continue;
         const Best cand{c, pair_prio((uint32_t)(k >> 32), (uint32_t)k), 0};
         if (better(bd, cand)) continue;
-        if (!smem_tab_add(fk, fc, FRONT_SLOTS - 1, mix64(k), k, (long long)c, &s_focc)) s_refresh = 1;
+        if (!smem_tab_add(fk, fc, FRONT_SLOTS - 1, mix64(k), k, (long long)c, &s_focc, flist)) s_refresh = 1;
       }
     }
     __syncthreads();
