@@ -837,6 +837,21 @@ __device__ __forceinline__ void sweep_below(const LoopArgs &a, uint64_t pbase, u
 #else
 #define YT_NOINLINE
 #endif
+// A work item of the drain: place `e` of segment j = (sender rank sd, block b); e == ~0u: no item.  cnt_off / plc_off:
+// byte offsets of its count word (in this block's row) and of its place inside the sender's {XqHdr, segments} slot.
+struct DrainItem { uint32_t e, j, sd, cnt_off, plc_off; };
+__device__ __forceinline__ DrainItem drain_item(const LoopArgs &a, uint32_t item, uint32_t nseg) {
+  DrainItem d;
+  d.e = ~0u; d.j = 0; d.sd = 0; d.cnt_off = 0; d.plc_off = 0;
+  if (item >= nseg * (uint32_t)XQ_BOX) return d;
+  d.e = item / nseg;
+  d.j = item - d.e * nseg;
+  d.sd = d.j / a.xq.nblocks;
+  const uint32_t b = d.j - d.sd * a.xq.nblocks;
+  d.cnt_off = (uint32_t)(offsetof(XqHdr, counts) + ((size_t)blockIdx.x * XQ_MAX_BLOCKS + b) * 8);
+  d.plc_off = (uint32_t)(offsetof(XqHdr, places) + ((size_t)d.e * XQ_MAX_BLOCKS + b) * 16);
+  return d;
+}
 // What a drained entry needs (merge_loop_body): the front, the round's new pairs, the parked list, the partition.
 struct FrontCtx {
   unsigned long long *fk, *fc, *nk, *nc, *ownk;
@@ -967,6 +982,10 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   fx.fk = fk; fx.fc = fc; fx.nk = nk; fx.nc = nc; fx.ownk = ownk; fx.ownd = ownd; fx.nlist = nlist;
   fx.s_nocc = &s_nocc; fx.s_own_n = &s_own_n; fx.s_refresh = &s_refresh; fx.s_povf = &s_povf; fx.s_occ = &s_occ;
   fx.own_base = 0; fx.z = 0; fx.part = blockIdx.x; fx.pbase = pbase; fx.tab = a.tab;
+  const uint32_t pub_d = threadIdx.x / a.xq.nblocks, pub_rb = threadIdx.x - pub_d * a.xq.nblocks;   // the reader this thread stores the count word to
+  DrainItem ditem[DRAIN_ITEMS];   // this thread's items of the first trip of the drain
+#pragma unroll
+  for (int k = 0; k < DRAIN_ITEMS; k++) ditem[k] = drain_item(a, threadIdx.x + (uint32_t)k * blockDim.x, a.xq.world * a.xq.nblocks);
   auto flush_own = [&]() {
     __syncthreads();
     const uint32_t end = s_own_n, n = min(end - fx.own_base, OWN_CAP);
@@ -1259,7 +1278,8 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       if (s_povf) word |= XQ_CNT_PFULL;
       const unsigned long long cw = ((unsigned long long)nround << 32) | word;
       const uint32_t nbox = a.xq.world * a.xq.nblocks;
-      for (uint32_t t = threadIdx.x; t < nbox; t += blockDim.x) {
+      if (threadIdx.x < nbox) st_relaxed_any(xq_cnt(xq_hdr(a.xq, pub_d, nround & 1u, a.xq.me), pub_rb, blockIdx.x), cw, sys);
+      for (uint32_t t = threadIdx.x + blockDim.x; t < nbox; t += blockDim.x) {   // (more readers than threads: 4+ GPUs)
         const uint32_t d = t / a.xq.nblocks, rb = t - d * a.xq.nblocks;
         st_relaxed_any(xq_cnt(xq_hdr(a.xq, d, nround & 1u, a.xq.me), rb, blockIdx.x), cw, sys);
       }
@@ -1309,31 +1329,30 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       // lane on its own line, 64 cycles of load/store unit per warp instruction, polled: 1 us per sweep.)
       {
         const uint32_t nitems = nseg * (uint32_t)XQ_BOX;
-        for (uint32_t base = threadIdx.x; base < nitems; base += (uint32_t)DRAIN_ITEMS * blockDim.x) {   // (one trip: 1 GPU, >= 352 threads)
-          unsigned long long hv[DRAIN_ITEMS], e0[DRAIN_ITEMS], e1[DRAIN_ITEMS];
+        const unsigned char *region = xq_base(a.xq, a.xq.me) + (size_t)parity * a.xq.world * a.xq.per_sender;   // [sender]{XqHdr, segments} of this parity
+        for (uint32_t base = threadIdx.x, trip = 0; base < nitems; base += (uint32_t)DRAIN_ITEMS * blockDim.x, trip++) {   // (one trip: 1 GPU, >= 352 threads)
+          uint32_t ie[DRAIN_ITEMS], ij[DRAIN_ITEMS];
           const unsigned long long *wp[DRAIN_ITEMS], *ep[DRAIN_ITEMS];
+          unsigned long long hv[DRAIN_ITEMS], e0 = 0, e1 = 0;
 #pragma unroll
           for (int k = 0; k < DRAIN_ITEMS; k++) {
-            const uint32_t item = base + (uint32_t)k * blockDim.x;
-            hv[k] = 0; e0[k] = 0; e1[k] = 0; wp[k] = nullptr; ep[k] = nullptr;
-            if (item < nitems) {
-              const uint32_t e = item / nseg, j = item - e * nseg, sd = j / a.xq.nblocks, b = j - sd * a.xq.nblocks;
-              XqHdr *h = xq_hdr(a.xq, a.xq.me, parity, sd);
-              wp[k] = xq_cnt(h, blockIdx.x, b);
-              ep[k] = reinterpret_cast<const unsigned long long *>(h->places + e * XQ_MAX_BLOCKS + b);
-              hv[k] = ld_relaxed_any(wp[k], sys);
-              ld_relaxed2(ep[k], &e0[k], &e1[k], sys);
-            }
+            DrainItem di = ditem[k];   // first trip: decoded once per launch (the divisions cost ~25 instructions each)
+            if (trip) di = drain_item(a, base + (uint32_t)k * blockDim.x, nseg);
+            ie[k] = di.e; ij[k] = di.j;
+            const unsigned char *h = region + (size_t)di.sd * a.xq.per_sender;
+            wp[k] = reinterpret_cast<const unsigned long long *>(h + di.cnt_off);
+            ep[k] = reinterpret_cast<const unsigned long long *>(h + di.plc_off);
+            hv[k] = di.e != ~0u ? ld_relaxed_any(wp[k], sys) : 0ull;
           }
+          if (ie[0] != ~0u) ld_relaxed2(ep[0], &e0, &e1, sys);   // speculative: places 0 .. 2 (3) usually hold an entry
 #pragma unroll
           for (int k = 0; k < DRAIN_ITEMS; k++) {
-            const uint32_t item = base + (uint32_t)k * blockDim.x;
-            if (item >= nitems) continue;
-            const uint32_t e = item / nseg, j = item - e * nseg;
+            if (ie[k] == ~0u) continue;
+            const uint32_t e = ie[k], j = ij[k];
             for (uint32_t spin = 0; (uint32_t)(hv[k] >> 32) != round; spin++) {
               spin_check(spin);
               hv[k] = ld_relaxed_any(wp[k], sys);
-              ld_relaxed2(ep[k], &e0[k], &e1[k], sys);
+              if (k == 0) ld_relaxed2(ep[0], &e0, &e1, sys);
             }
             const uint32_t c = (uint32_t)hv[k];
             uint32_t n = c & XQ_CNT_MASK;
@@ -1348,12 +1367,13 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
               if (n > nb) big = 1;
             }
             if (e >= n) continue;
+            if (k != 0) ld_relaxed2(ep[k], &e0, &e1, sys);   // the later items of a thread are the rarely used places
             unsigned long long key = 0;
             long long delta = 0;
-            for (uint32_t spin = 0; !xq_unpack(e0[k], e1[k], stamp, &key, &delta); spin++) {   // the count word overtook the entry
+            for (uint32_t spin = 0; !xq_unpack(e0, e1, stamp, &key, &delta); spin++) {   // the count word overtook the entry
               if (dbgb) bacc[11] += 1;
               spin_check(spin);
-              ld_relaxed2(ep[k], &e0[k], &e1[k], sys);
+              ld_relaxed2(ep[k], &e0, &e1, sys);
             }
             front_take(fx, key, delta);
           }
