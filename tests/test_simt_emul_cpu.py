@@ -34,12 +34,25 @@ def test_train_stress(emu, oracle, seed):
 
 @pytest.mark.parametrize("sms", ["1", "3", "5"])
 def test_train_other_grid_sizes(emu, oracle, monkeypatch, sms):
-    """1, 3 and 5 blocks: tile ownership, the per-block winners of the arg-max and the grid barrier count change."""
+    """1, 3 and 5 blocks: tile ownership, table partitions, exchange rows and the front's gather all change shape."""
     monkeypatch.setenv("YT_EMU_SMS", sms)
     for seed in (1, 4, 9):
         text, vocab, cov, _ = _cases.stress_case(seed)
         TG._same(oracle, text, vocab, cov)
     TG._same(oracle, _cases.dirty_zipf_text(60_000), 700, 0.98)
+
+
+@pytest.mark.parametrize("top,sms", [("1", "4"), ("2", "3"), ("6", "2")])
+def test_train_front_refresh(emu, oracle, monkeypatch, top, sms):
+    """The replicated front: with one or two pairs per partition the front is exhausted every few merges (refresh,
+    bound, new pairs below / above the bound), with 6 it fills up from the new pairs instead."""
+    monkeypatch.setenv("YTTM_FRONT_TOP", top)
+    monkeypatch.setenv("YT_EMU_SMS", sms)
+    for seed in (2, 7):
+        text, vocab, cov, _ = _cases.stress_case(seed)
+        TG._same(oracle, text, vocab, cov)
+    TG._same(oracle, _cases.dirty_zipf_text(50_000), 600, 0.98)
+    TG._same(oracle, synth.readme_corpus(n_lines=200), 250)
 
 
 def test_train_unicode_and_runs(emu, oracle):
