@@ -401,17 +401,21 @@ __device__ __forceinline__ unsigned long long process_tile(uint32_t *stok, const
                                                            const MergeOp &op, const LoopArgs &a, const XqOut &xo) {
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   unsigned long long dead = 0;
-  // a lane compares four tokens from one 16-byte shared load (stok is 16-byte aligned, its capacity a
-  // multiple of 4); the token after them comes from the next lane
-  for (uint32_t base = wid * 128; base < span; base += nwarp * 128) {
-    const uint32_t p = base + lane * 4;
-    uint4 v = make_uint4(DEAD, DEAD, DEAD, DEAD);
+  // a lane compares eight tokens from two 16-byte shared loads (stok is 16-byte aligned, its capacity a multiple
+  // of 4); the token after them comes from the next lane.  (Four per lane: twice the trips; the loop is latency bound —
+  // one warp issues a dependent instruction every ~5 cycles — so instructions per token are what counts.)
+  for (uint32_t base = wid * 256; base < span; base += nwarp * 256) {
+    const uint32_t p = base + lane * 8;
+    uint4 v = make_uint4(DEAD, DEAD, DEAD, DEAD), u = v;
     if (p < span) v = *reinterpret_cast<const uint4 *>(stok + p);
+    if (p + 4 < span) u = *reinterpret_cast<const uint4 *>(stok + p + 4);
     uint32_t nxt = __shfl_down_sync(0xffffffffu, v.x, 1);
-    if (lane == 31) nxt = p + 4 < span ? stok[p + 4] : DEAD;
+    if (lane == 31) nxt = p + 8 < span ? stok[p + 8] : DEAD;
     uint32_t m = (v.x == op.x && v.y == op.y ? 1u : 0u) | (v.y == op.x && v.z == op.y ? 2u : 0u) |
-                 (v.z == op.x && v.w == op.y ? 4u : 0u) | (v.w == op.x && nxt == op.y ? 8u : 0u);
-    if (p + 4 >= span) m &= span > p + 1 ? (1u << (span - p - 1)) - 1u : 0u;  // occurrence i needs i + 1 < span
+                 (v.z == op.x && v.w == op.y ? 4u : 0u) | (v.w == op.x && u.x == op.y ? 8u : 0u) |
+                 (u.x == op.x && u.y == op.y ? 16u : 0u) | (u.y == op.x && u.z == op.y ? 32u : 0u) |
+                 (u.z == op.x && u.w == op.y ? 64u : 0u) | (u.w == op.x && nxt == op.y ? 128u : 0u);
+    if (p + 8 >= span) m &= span > p + 1 ? (1u << (span - p - 1)) - 1u : 0u;  // occurrence i needs i + 1 < span
     while (__ballot_sync(0xffffffffu, m != 0)) {  // one round per hit of the busiest lane (almost always one)
       uint32_t w = 0, o = 0, cap = 0;
       bool own = false;
