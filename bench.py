@@ -526,14 +526,13 @@ def main():
                                         C.byref(nd)) == 0, L.yttm_last_error(c2)
                 g = lambda k: L.yttm_stage_ms(c2, k.encode())
                 it = max(g("loop_iters"), 1.0)
-                t_scan = (g("loop_apply") + g("loop_barrier2")) / it          # ms per merge
+                t_scan = (g("loop_apply") + g("loop_partition") + g("loop_drain")) / it          # ms per merge
                 ab = 4 * args.scan_tokens + 4 * n_w
                 a_ = ab / (t_scan * 1e-3) / 1e9
                 ms, ab2 = C.c_double(0), C.c_uint64(0)
                 L.yttm_train_scan_once(c2, C.byref(ms), C.byref(ab2))
                 out = {"achieved": r3(a_), "frac": r3(a_ / hbm_peak), "ms_per_merge_scan": r3(t_scan),
-                       "ms_per_merge_all": r3(sum(g(k) for k in ("loop_drain", "loop_argmax", "loop_barrier1", "loop_apply",
-                                                                 "loop_barrier2")) / it),
+                       "ms_per_merge_all": r3(sum(g(k) for k in ("loop_elect", "loop_apply", "loop_partition", "loop_drain")) / it),
                        "resident": int(g("loop_resident")),
                        "pair_hist_GBps": r3(ab2.value / (ms.value * 1e-3) / 1e9)}
                 L.yttm_ctx_destroy(c2)

@@ -16,10 +16,10 @@ rules = np.zeros(3 * iters, dtype=np.uint32); fr = np.zeros(iters, dtype=np.uint
 assert L.yttm_train_run(c2, 4 + n_first + alpha, iters, rules.ctypes.data, fr.ctypes.data, C.byref(nd)) == 0, L.yttm_last_error(c2)
 g = lambda k: L.yttm_stage_ms(c2, k.encode())
 it = max(g("loop_iters"), 1.0)
-t_scan = (g("loop_apply") + g("loop_barrier2")) / it
+t_scan = (g("loop_apply") + g("loop_partition") + g("loop_drain")) / it
 ab = 4 * T + 4 * (T // wl)
 print(json.dumps({"log2_first": log2_first, "T": T, "wl": wl, "iters": int(nd.value), "resident": g("loop_resident"), "ms_scan": t_scan,
                   "GBps": ab / (t_scan * 1e-3) / 1e9, "frac_of_6571.6": ab / (t_scan * 1e-3) / 1e9 / 6571.6,
-                  "phase_ms": {k: g(k) / it for k in ["loop_argmax", "loop_barrier1", "loop_apply", "loop_barrier2"]},
+                  "phase_ms": {k: g(k) / it for k in ["loop_elect", "loop_apply", "loop_partition", "loop_drain"]},
                   "rules_head": rules[:6].tolist(), "freq_head": fr[:2].tolist()}))
 L.yttm_ctx_destroy(c2)

@@ -29,6 +29,6 @@ for rep in range(2):
     it = max(g("loop_iters"), 1)
     print(json.dumps({"corpus": which, "bytes": len(text), "U": st.n_unique, "T": st.n_tokens, "P0": st.n_pairs, "cap": g("table_capacity"),
         "merges": nd2.value, "loop_ms": g("merge_loop"), "wall_ms": wall * 1e3, "us_per_merge": g("merge_loop") * 1e3 / max(nd2.value, 1),
-        "launches": g("loop_launches"), "sweeps_per_iter": g("loop_sweeps") / it, "phase_us_per_iter": {k: g(k) * 1e3 / it for k in ["loop_drain", "loop_argmax", "loop_barrier1", "loop_apply", "loop_barrier2", "loop_apply_blkmax", "loop_apply_blkmean", "loop_drain_blkmax"]},
+        "launches": g("loop_launches"), "refreshes": g("loop_refreshes"), "phase_us_per_iter": {k: g(k) * 1e3 / it for k in ["loop_elect", "loop_apply", "loop_partition", "loop_drain"]},
         "front_ms": {k: g(k) for k in ["h2d", "char_hist", "word_count", "tokenise", "pair_hist"]}}))
 L.yttm_ctx_destroy(ctx)

@@ -890,12 +890,14 @@ void yttm_ctx_destroy(yttm_ctx *c) {
 const char *yttm_last_error(const yttm_ctx *c) { return c ? c->err.c_str() : g_yttm_create_error.c_str(); }
 
 double yttm_stage_ms(const yttm_ctx *c, const char *stage) {
-  static const char *ph[] = {"loop_drain", "loop_argmax", "loop_barrier1", "loop_apply", "loop_barrier2",
-                             "loop_apply_blkmax", "loop_apply_blkmean", "loop_drain_blkmax"};
+  // block 0's share of a merge (merge_loop.cuh): drain = wait for the count words + entries + new pairs; elect = front
+  // scan (+ refreshes); apply = token scan + rewrites + count word; partition = parked entries into the table
+  static const char *ph[] = {"loop_drain", "loop_unused1", "loop_elect", "loop_apply", "loop_partition",
+                             "loop_unused5", "loop_unused6", "loop_unused7"};
   for (int i = 0; i < 8; i++)
     if (!std::strcmp(stage, ph[i])) return c->loop_phase_ms[i];
   if (!std::strcmp(stage, "loop_iters")) return (double)c->loop_iters;
-  if (!std::strcmp(stage, "loop_sweeps")) return (double)c->loop_sweeps;
+  if (!std::strcmp(stage, "loop_refreshes")) return (double)c->loop_sweeps;
   if (!std::strcmp(stage, "loop_launches")) return (double)c->loop_relaunches;
   if (!std::strcmp(stage, "table_capacity")) return (double)c->pcap;
   if (!std::strcmp(stage, "loop_resident")) return (double)c->loop_resident;

@@ -301,8 +301,7 @@ def train_distributed(data, model_path, vocab_size, coverage=1.0, pad_id=0, unk_
                                                ("h2d", "char_hist", "word_count", "tokenise", "pair_hist")},
                                   "phase_us_per_iter": {k: L.yttm_stage_ms(ctx, k.encode()) * 1e3 /
                                                         max(L.yttm_stage_ms(ctx, b"loop_iters"), 1.0) for k in
-                                                        ("loop_drain", "loop_argmax", "loop_barrier1", "loop_apply",
-                                                         "loop_barrier2")}}
+                                                        ("loop_elect", "loop_apply", "loop_partition", "loop_drain")}}
         train_distributed.last = stats  # one process per rank; threads of a test harness pass stats_out instead
         if stats_out is not None:
             stats_out.update(stats)
