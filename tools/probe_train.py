@@ -8,6 +8,8 @@ which = sys.argv[1] if len(sys.argv) > 1 else "zipf"
 vocab = int(sys.argv[2]) if len(sys.argv) > 2 else 32000
 if which == "readme":
     text = synth.readme_corpus(); vocab = 5000
+elif which == "multilingual":   # a chunk of bench.py's config-5 corpus
+    text = b"".join(synth.corpus_chunks("multilingual", [0], int(float(sys.argv[3]) if len(sys.argv) > 3 else 125e6)))
 else:
     text = synth.FastZipf().text(int(float(sys.argv[3]) if len(sys.argv) > 3 else 100e6))
 ctx = C.c_void_p(); assert L.yttm_ctx_create(0, C.byref(ctx)) == 0
