@@ -55,6 +55,18 @@ def test_train_front_refresh(emu, oracle, monkeypatch, top, sms):
     TG._same(oracle, synth.readme_corpus(n_lines=200), 250)
 
 
+@pytest.mark.parametrize("limit", ["1", "3"])
+def test_train_new_pairs_beyond_the_table(emu, oracle, monkeypatch, limit):
+    """More new pairs in a round than the per-round table takes: the rest is only bounded (hash-bucket sums raise the
+    bound of the front) — the front must refresh early enough to stay exact."""
+    monkeypatch.setenv("YTTM_NEWP_LIMIT", limit)
+    monkeypatch.setenv("YT_EMU_SMS", "3")
+    for seed in (3, 8):
+        text, vocab, cov, _ = _cases.stress_case(seed)
+        TG._same(oracle, text, vocab, cov)
+    TG._same(oracle, _cases.dirty_zipf_text(50_000), 600, 0.98)
+
+
 def test_train_unicode_and_runs(emu, oracle):
     TG._same(oracle, _cases.dirty_zipf_text(120_000), 900, 0.98)
     TG._same(oracle, b"a" * 500 + b" " + b"ab" * 300 + b" aaa aaaa aaaaa " + b"b" * 1001, 40)

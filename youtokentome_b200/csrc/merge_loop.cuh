@@ -221,6 +221,7 @@ struct LoopArgs {
   uint32_t dead_min_slots;        // a block wishes a compaction only if it owns more token slots than this
   unsigned long long spin_limit_ns;  // a peer that stays silent this long traps the kernel (never hang the box)
   uint32_t front_top;                // pairs a partition contributes to a front refresh (1 .. FRONT_TOP)
+  uint32_t newp_limit;               // keys the new-pair table takes per round (NEWP_LIMIT; tests: YTTM_NEWP_LIMIT)
   unsigned long long *dbg_blk;       // YTTM_DBG & 16: 8 accumulators per block (ns): poll bests, apply, wait counts (+ owner sweep), drain, cache, sweeps
 };
 
@@ -703,10 +704,12 @@ constexpr uint32_t FRONT_SLOTS = 4096;   // shared-memory hash table (key, count
 constexpr uint32_t FRONT_FILL = 1024;    // members that trigger a refresh (dead members are only dropped there)
 constexpr uint32_t FRONT_LIST = FRONT_FILL + 1024 + 64;   // member list: a round adds at most NEWP_SLOTS members
 constexpr uint32_t NEWP_SLOTS = 1024;    // the round's pairs with the new token, aggregated before they meet the bound
+constexpr uint32_t NEWP_LIMIT = 768;     // keys the table takes; a round with more new pairs only BOUNDS them (sketch)
+constexpr uint32_t NEWP_SKETCH = 1024;   // u64 buckets: sum of the counts of ALL new pairs of the round, by hash
 constexpr uint32_t OWN_CAP = 256;        // parked entries of one round (more: added to the partition at once)
 constexpr int FRONT_TOP = 6;             // most pairs a partition contributes to a refresh (LoopArgs::front_top, default 4)
 constexpr int DRAIN_ITEMS = 3;           // (place, segment) items per thread and trip of the drain
-constexpr size_t LOOP_FRONT_BYTES = ((size_t)FRONT_SLOTS * 2 + NEWP_SLOTS * 2 + OWN_CAP * 2) * 8 + ((size_t)NEWP_SLOTS + FRONT_LIST) * 4;
+constexpr size_t LOOP_FRONT_BYTES = ((size_t)FRONT_SLOTS * 2 + NEWP_SLOTS * 2 + OWN_CAP * 2) * 8 + ((size_t)NEWP_SLOTS + FRONT_LIST) * 4 + (size_t)NEWP_SKETCH * 8;
 // global gather buffer of a refresh: [nblocks flag words, 128 bytes apart][nblocks x FRONT_TOP x (count, key)]
 YT_HD size_t front_buf_words(uint32_t nblocks) { return (size_t)nblocks * 16 + (size_t)nblocks * FRONT_TOP * 2; }
 
@@ -753,13 +756,14 @@ __device__ __forceinline__ bool smem_tab_add(unsigned long long *keys, unsigned 
   }
   return false;
 }
-// slot of `key`, inserted if absent; ~0u: the table is full
+// slot of `key`, inserted if absent; ~0u: absent and the table already holds `limit` keys
 __device__ __forceinline__ uint32_t smem_tab_slot(unsigned long long *keys, uint32_t mask, uint64_t hh, unsigned long long key,
-                                                  uint32_t *occ, uint32_t *list) {
+                                                  uint32_t *occ, uint32_t *list, uint32_t limit) {
   uint32_t i = smem_home(hh, mask);
   for (uint32_t p = 0; p <= mask; p++, i = (i + 1) & mask) {
     unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(keys + i);
     if (k == PK_EMPTY) {
+      if (*reinterpret_cast<volatile uint32_t *>(occ) >= limit) return ~0u;
       k = atomicCAS(keys + i, PK_EMPTY, key);
       if (k == PK_EMPTY) {
         const uint32_t q = atomicAdd(occ, 1u);
@@ -860,8 +864,9 @@ __device__ __forceinline__ DrainItem drain_item(const LoopArgs &a, uint32_t item
 struct FrontCtx {
   unsigned long long *fk, *fc, *nk, *nc, *ownk;
   long long *ownd;
-  uint32_t *nlist, *s_nocc, *s_own_n, *s_refresh, *s_povf, *s_occ;
-  uint32_t own_base, z, part;
+  unsigned long long *nsk;
+  uint32_t *nlist, *s_nocc, *s_own_n, *s_refresh, *s_povf, *s_occ, *s_lost;
+  uint32_t own_base, z, part, newp_limit;
   uint64_t pbase;
   PairTab tab;
 };
@@ -873,9 +878,15 @@ __device__ __forceinline__ void front_take(const FrontCtx &f, unsigned long long
   unsigned long long *cnt = nullptr;   // the count this entry changes: a member of the front, or a new pair of this round
   if (fs != ~0u) cnt = f.fc + fs;
   else if ((uint32_t)(key >> 32) == f.z || (uint32_t)key == f.z) {   // a pair of the new token: cannot be in the front yet
-    const uint32_t ns = smem_tab_slot(f.nk, NEWP_SLOTS - 1, hh, key, f.s_nocc, f.nlist);
+    // Every new pair is counted twice: exactly, in the table of the round (nk / nc) as long as it has room, and in a
+    // hash-bucket sketch that always has.  A round with more new pairs than the table takes (a frequent token next to
+    // thousands of different neighbours) discards the table — WHICH pairs found room depends on the order of arrival and
+    // differs between blocks — and raises the bound of the front to the largest bucket instead: an upper bound of every
+    // new pair's count, the same in every block.  Exact: the invariant is "every pair outside the front is below the bound".
+    smem_add64(f.nsk + ((uint32_t)(hh >> 12) & (NEWP_SKETCH - 1)), (unsigned long long)delta);
+    const uint32_t ns = smem_tab_slot(f.nk, NEWP_SLOTS - 1, hh, key, f.s_nocc, f.nlist, f.newp_limit);
     if (ns != ~0u) cnt = f.nc + ns;
-    else *f.s_refresh = 1;   // too many new pairs: the refresh finds them
+    else *f.s_lost = 1;
   }
   if (cnt) smem_add64(cnt, (unsigned long long)delta);
   if (pair_part(f.tab, hh) == f.part) {
@@ -904,7 +915,8 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   __shared__ Best s_warp[32];
   __shared__ Best s_bound, s_tmp;   // the bound of the front / scratch of a refresh
   __shared__ uint32_t s_dead;   // token slots of this block tombstoned in this launch
-  __shared__ uint32_t s_defer_n, s_direct, s_out_n, s_occ, s_xf, s_povf, s_focc, s_nocc, s_own_n, s_refresh, s_scan[33];
+  __shared__ uint32_t s_defer_n, s_direct, s_out_n, s_occ, s_xf, s_povf, s_focc, s_nocc, s_own_n, s_refresh, s_lost, s_scan[33];
+  __shared__ unsigned long long s_lostmax;
   const bool sys = a.xq.world > 1;
   // dynamic shared memory: [segment prefix: XQ_MAX_WORLD * XQ_MAX_BLOCKS + 4 words][claim bitmaps][front keys, counts]
   // [new-pair keys, counts][parked keys, deltas][new-pair slot list][tile tokens][tile offsets][word frequencies]
@@ -918,12 +930,14 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   long long *ownd = reinterpret_cast<long long *>(ownk + OWN_CAP);
   uint32_t *nlist = reinterpret_cast<uint32_t *>(ownd + OWN_CAP);   // slots of nk taken in this round
   uint32_t *flist = nlist + NEWP_SLOTS;                              // slots of fk taken since the last refresh
-  uint32_t *stok = flist + FRONT_LIST;
+  unsigned long long *nsk = reinterpret_cast<unsigned long long *>(flist + FRONT_LIST);   // sketch of the round's new pairs
+  uint32_t *stok = reinterpret_cast<uint32_t *>(nsk + NEWP_SKETCH);
   uint32_t *soff = stok + a.smem_tok_cap;
   // RESIDENT only: word frequencies behind the offsets (8-byte aligned: both caps are even)
   unsigned long long *sfreq = reinterpret_cast<unsigned long long *>(soff + a.smem_word_cap + 2);
   for (uint32_t i = threadIdx.x; i < 2 * CLAIM_WORDS; i += blockDim.x) s_claim[i] = 0;
   for (uint32_t i = threadIdx.x; i < NEWP_SLOTS; i += blockDim.x) { nk[i] = PK_EMPTY; nc[i] = 0; }
+  for (uint32_t i = threadIdx.x; i < NEWP_SKETCH; i += blockDim.x) nsk[i] = 0;
   // STREAMING carve of the same region: NSTAGE stages of (tokens, offsets), each 16-byte aligned;
   // full[s]: TMA bytes landed (tx count), empty[s]: all consumer warps are done with stage s
   __shared__ __align__(8) unsigned long long s_full[MAX_STAGES], s_empty[MAX_STAGES];
@@ -953,7 +967,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     for (uint32_t i = threadIdx.x; i < R; i += blockDim.x) occ += __ldcg(a.tab.keys + pbase + i) != PK_EMPTY ? 1u : 0u;
     for (int o = 16; o > 0; o >>= 1) occ += __shfl_xor_sync(0xffffffffu, occ, o);
     if (threadIdx.x == 0) {
-      s_occ = 0; s_xf = 0; s_dead = 0; s_focc = 0; s_nocc = 0; s_own_n = 0; s_refresh = 1; s_out_n = 0;
+      s_occ = 0; s_xf = 0; s_dead = 0; s_focc = 0; s_nocc = 0; s_own_n = 0; s_refresh = 1; s_out_n = 0; s_lost = 0; s_lostmax = 0;
       s_povf = __ldcg(a.tab.overflow) ? 1u : 0u;
       s_bound = Best{0, 0, 0};
     }
@@ -985,6 +999,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   FrontCtx fx;
   fx.fk = fk; fx.fc = fc; fx.nk = nk; fx.nc = nc; fx.ownk = ownk; fx.ownd = ownd; fx.nlist = nlist;
   fx.s_nocc = &s_nocc; fx.s_own_n = &s_own_n; fx.s_refresh = &s_refresh; fx.s_povf = &s_povf; fx.s_occ = &s_occ;
+  fx.nsk = nsk; fx.s_lost = &s_lost; fx.newp_limit = a.newp_limit;
   fx.own_base = 0; fx.z = 0; fx.part = blockIdx.x; fx.pbase = pbase; fx.tab = a.tab;
   const uint32_t pub_d = threadIdx.x / a.xq.nblocks, pub_rb = threadIdx.x - pub_d * a.xq.nblocks;   // the reader this thread stores the count word to
   DrainItem ditem[DRAIN_ITEMS];   // this thread's items of the first trip of the drain
@@ -1401,19 +1416,32 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     }
     __syncthreads();
     if (dbgb) { const unsigned long long t = gtimer(); bacc[3] += t - bt; bt = t; }
-    // ---- the new token's pairs: those not below the bound join the front
-    if (s_nocc) {   // block-uniform (read after the barrier)
+    // ---- the new token's pairs: those not below the bound join the front — or, in a round with more of them than
+    // the table takes, all of them stay outside and the bound rises to the largest sketch bucket (front_take)
+    if (s_nocc) {   // block-uniform (read after the barrier); 0: the round had no new pair
       const Best bd = s_bound;
-      const uint32_t nn = s_nocc;   // <= NEWP_SLOTS: one per slot taken
+      const uint32_t nn = min(s_nocc, NEWP_SLOTS);   // one list entry per slot taken
+      const bool lost = s_lost != 0 || s_nocc > a.newp_limit;   // the same verdict in every block (distinct new pairs > limit)
       for (uint32_t q = threadIdx.x; q < nn; q += blockDim.x) {
         const uint32_t i = nlist[q];
         const unsigned long long k = nk[i];
         const unsigned long long c = nc[i];
         nk[i] = PK_EMPTY; nc[i] = 0;
-        if ((long long)c <= 0) continue;
+        if (lost || (long long)c <= 0) continue;
         const Best cand{c, pair_prio((uint32_t)(k >> 32), (uint32_t)k), 0};
         if (better(bd, cand)) continue;
         if (!smem_tab_add(fk, fc, FRONT_SLOTS - 1, mix64(k), k, (long long)c, &s_focc, flist)) s_refresh = 1;
+      }
+      unsigned long long m = 0;
+      for (uint32_t i = threadIdx.x; i < NEWP_SKETCH; i += blockDim.x) { m = max(m, nsk[i]); nsk[i] = 0; }
+      if (lost) {
+        if (m) atomicMax(&s_lostmax, m);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          const Best lb{s_lostmax, ~0ull, 0};
+          if (better(lb, s_bound)) s_bound = lb;
+          s_lost = 0; s_lostmax = 0;
+        }
       }
     }
     __syncthreads();

@@ -1444,6 +1444,8 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
     }
     a.front_top = 4;   // measured on B200 (100 MB Zipf): 8 -> 9.6, 4 -> 8.8, 2 -> 9.3 us per merge (smaller front: shorter probes and scans, more refreshes)
     if (const char *e = std::getenv("YTTM_FRONT_TOP")) a.front_top = (uint32_t)std::max(1, std::min((int)FRONT_TOP, std::atoi(e)));
+    a.newp_limit = NEWP_LIMIT;
+    if (const char *e = std::getenv("YTTM_NEWP_LIMIT")) a.newp_limit = (uint32_t)std::max(1, std::min((int)NEWP_LIMIT, std::atoi(e)));
     a.dead_min_slots = 4096;
     if (const char *e = std::getenv("YTTM_DEAD_MIN_SLOTS")) a.dead_min_slots = (uint32_t)std::max(0, std::atoi(e));
     YT_CUDA(c, cudaMemsetAsync(c->frontbuf.p, 0, front_buf_words((uint32_t)c->loop_blocks) * 8, c->stream));  // refresh numbers restart at 1
