@@ -1032,9 +1032,12 @@ int yttm_train_set_alphabet(yttm_ctx *c, const uint32_t *cps, const uint32_t *id
 
 static int finish_build(yttm_ctx *c, yttm_train_stats *stats) {
   ytc::timer_begin(c, "pair_hist");
-  // start small and let rebuild_pair_table grow to load <= 1/4: the arg-max sweeps the whole table
-  // every merge, so a tight table is worth a few extra histogram launches here
-  int rc = rebuild_pair_table(c, pair_cap_floor());
+  // first guess: one slot per two tokens (the distinct pairs of the corpora measured so far are 2 - 13 % of the tokens;
+  // the table is accepted at load <= 1/4).  Starting at the floor and doubling cost five histogram passes on the
+  // multilingual corpus (60 ms per GB); a partition is only swept by the rare refreshes of the front, so a roomy table
+  // costs nothing per merge.  (YTTM_PAIR_CAP_FLOOR still forces small tables in the tests.)
+  const uint64_t guess = std::getenv("YTTM_PAIR_CAP_FLOOR") ? 0 : c->n_slots / 2;
+  int rc = rebuild_pair_table(c, std::max<uint64_t>(pair_cap_floor(), guess));
   ytc::timer_end(c, "pair_hist");
   if (rc) return rc;
   YtLoopCtl *ctl = c->ctl.as<YtLoopCtl>();
@@ -1060,7 +1063,7 @@ static int build_word_table(yttm_ctx *c, const WordList *list, uint64_t *n_uniqu
   const uint64_t n = c->n_text;
   YT_CUDA(c, c->counters.reserve(64));
   auto *counters = c->counters.as<unsigned long long>();
-  ytc::timer_begin(c, "word_count");
+  ytc::timer_begin(c, list ? "word_import" : "word_count");
   const uint64_t guess = list ? list->word_off[list->n_src] * 2 + 1 : n / 16 + 1;
   uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(ytc::pow2ceil(guess), 1u << 16), 1ull << 26);
   unsigned long long h_cnt[4] = {0, 0, 0, 0};
@@ -1100,7 +1103,7 @@ static int build_word_table(yttm_ctx *c, const WordList *list, uint64_t *n_uniqu
                                                                          c->wfreq.as<uint64_t>());
     c->launches++;
   }
-  ytc::timer_end(c, "word_count");
+  ytc::timer_end(c, list ? "word_import" : "word_count");
   YT_CUDA(c, cudaGetLastError());
   *n_unique = U;
   c->n_unique = U;

@@ -298,7 +298,7 @@ def train_distributed(data, model_path, vocab_size, coverage=1.0, pad_id=0, unk_
                                   "n_merges": int(done.value), "merge_loop_ms": L.yttm_stage_ms(ctx, b"merge_loop"),
                                   "launches": L.yttm_stage_ms(ctx, b"loop_launches"),
                                   "front_ms": {k: L.yttm_stage_ms(ctx, k.encode()) for k in
-                                               ("h2d", "char_hist", "word_count", "tokenise", "pair_hist")},
+                                               ("h2d", "char_hist", "word_count", "word_import", "tokenise", "pair_hist")},
                                   "phase_us_per_iter": {k: L.yttm_stage_ms(ctx, k.encode()) * 1e3 /
                                                         max(L.yttm_stage_ms(ctx, b"loop_iters"), 1.0) for k in
                                                         ("loop_elect", "loop_apply", "loop_partition", "loop_drain")}}
