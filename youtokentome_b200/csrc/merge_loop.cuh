@@ -884,9 +884,11 @@ __device__ __forceinline__ void front_take(const FrontCtx &f, unsigned long long
     // differs between blocks — and raises the bound of the front to the largest bucket instead: an upper bound of every
     // new pair's count, the same in every block.  Exact: the invariant is "every pair outside the front is below the bound".
     smem_add64(f.nsk + ((uint32_t)(hh >> 12) & (NEWP_SKETCH - 1)), (unsigned long long)delta);
-    const uint32_t ns = smem_tab_slot(f.nk, NEWP_SLOTS - 1, hh, key, f.s_nocc, f.nlist, f.newp_limit);
-    if (ns != ~0u) cnt = f.nc + ns;
-    else *f.s_lost = 1;
+    if (*reinterpret_cast<volatile uint32_t *>(f.s_lost) == 0) {   // (once the round is lost its table is dead weight)
+      const uint32_t ns = smem_tab_slot(f.nk, NEWP_SLOTS - 1, hh, key, f.s_nocc, f.nlist, f.newp_limit);
+      if (ns != ~0u) cnt = f.nc + ns;
+      else *f.s_lost = 1;
+    }
   }
   if (cnt) smem_add64(cnt, (unsigned long long)delta);
   if (pair_part(f.tab, hh) == f.part) {

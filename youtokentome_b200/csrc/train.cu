@@ -821,7 +821,18 @@ int plan_tiles(yttm_ctx *c, LoopArgs *a) {
     uint32_t h[2];
     YT_CUDA(c, cudaMemcpyAsync(h, d_stats, 8, cudaMemcpyDeviceToHost, c->stream));
     YT_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (h[0] <= c->loop_tok_cap && h[1] <= c->loop_word_cap) { a->resident = 1; c->loop_resident = 1; break; }
+    // RESIDENT if the largest tile fits the block's tile bytes: 4 B per token slot (rounded up to 16 B) + 12 B per word
+    // (+ 2 sentinel offsets); the split between tokens and words follows the corpus
+    {
+      const uint64_t tok = ((uint64_t)h[0] + 7) & ~3ull, wrd = ((uint64_t)h[1] + 3) & ~1ull;
+      const uint64_t tile_bytes = (uint64_t)c->loop_smem - LOOP_SMEM_HEAD;
+      if (wrd <= CLAIM_WORDS * 32 - 1 && tok * 4 + (wrd + 2) * 12 + 64 <= tile_bytes) {
+        a->smem_tok_cap = (uint32_t)tok;
+        a->smem_word_cap = (uint32_t)wrd;
+        a->resident = 1; c->loop_resident = 1;
+        break;
+      }
+    }
   }
   YT_CUDA(c, cudaGetLastError());
   return 0;
