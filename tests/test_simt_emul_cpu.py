@@ -67,6 +67,20 @@ def test_train_new_pairs_beyond_the_table(emu, oracle, monkeypatch, limit):
     TG._same(oracle, _cases.dirty_zipf_text(50_000), 600, 0.98)
 
 
+@pytest.mark.parametrize("piece_kb", ["1", "7"])
+def test_train_pipelined_ingest(emu, oracle, monkeypatch, piece_kb):
+    """The corpus copied in pieces that end behind an ASCII space / newline, histogram + word table per piece: multi-byte
+    characters, U+2581, invalid bytes and words at the piece ends; a text without any space (one piece)."""
+    monkeypatch.setenv("YTTM_TRAIN_PIPELINE", "1")
+    monkeypatch.setenv("YTTM_TRAIN_PIPELINE_PIECE_KB", piece_kb)
+    TG._same(oracle, _cases.dirty_zipf_text(60_000), 700, 0.98)
+    for seed in (0, 5, 11):
+        text, vocab, cov, _ = _cases.stress_case(seed)
+        TG._same(oracle, text, vocab, cov)
+    TG._same(oracle, synth.readme_corpus(n_lines=200), 250)
+    TG._same(oracle, b"ab" * 3000 + "\u2581x\u2581".encode() + b"cd" * 2000, 30)
+
+
 def test_train_unicode_and_runs(emu, oracle):
     TG._same(oracle, _cases.dirty_zipf_text(120_000), 900, 0.98)
     TG._same(oracle, b"a" * 500 + b" " + b"ab" * 300 + b" aaa aaaa aaaaa " + b"b" * 1001, 40)

@@ -73,6 +73,11 @@ struct yttm_ctx {
   uint64_t data_len = 0;
   uint32_t space_id = 0;
   bool have_alphabet = false;
+  // pipelined ingest (yttm_train_load_corpus): the histogram / the word table of the text were built while it was copied
+  bool pipe_hist = false;
+  uint64_t pipe_wtab_cap = 0;
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_pipe = nullptr;
 
   // ---- word table / unique words
   ytc::DevBuf wkey, wcnt, wpos, wfreq, wlen, scan_tmp, counters;

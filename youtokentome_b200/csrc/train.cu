@@ -245,11 +245,11 @@ __device__ __forceinline__ bool word_table_insert(const uint8_t *__restrict__ s,
 // bound — the per-word hash / compare loops run with ~5 of 32 lanes active.  A variant that first aggregated the words
 // of a 64 KB chunk in a shared-memory table (to take the hot words' same-address atomics off L2) was measured SLOWER
 // on B200 (5.5 - 6.4 ms vs 4.4 ms per 100 MB: 4.1 G warp instructions) and was dropped.
-__global__ void __launch_bounds__(256) word_insert_kernel(const uint8_t *__restrict__ s, uint64_t n, WordTab wt,
-                                                          unsigned long long *counters, uint64_t max_unique) {
-  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+__global__ void __launch_bounds__(256) word_insert_kernel(const uint8_t *__restrict__ s, uint64_t n, uint64_t lo, uint64_t hi,
+                                                          WordTab wt, unsigned long long *counters, uint64_t max_unique) {
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;   // word starts in [lo, hi) of the text [0, n)
   uint64_t occ = 0;
-  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+  for (uint64_t p = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < hi; p += stride) {
     if (!word_start_at(s, p, 0, n)) continue;
     occ++;
     word_table_insert(s, n, p, wt, counters, max_unique, 1ull);
@@ -894,6 +894,8 @@ void yttm_ctx_destroy(yttm_ctx *c) {
     if (c->xq_peer_ipc[d] && c->xq_peer[d]) { cudaIpcCloseMemHandle(c->xq_peer[d]); c->xq_peer[d] = nullptr; }
   for (auto *b : bufs) b->release();
   for (auto &kv : c->timers) { if (kv.second.a) cudaEventDestroy(kv.second.a); if (kv.second.b) cudaEventDestroy(kv.second.b); }
+  if (c->stream2) cudaStreamDestroy(c->stream2);
+  if (c->ev_pipe) cudaEventDestroy(c->ev_pipe);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -955,6 +957,51 @@ static int staged_h2d(yttm_ctx *c, uint8_t *dst, const char *src, uint64_t n, in
   return 0;
 }
 
+// The corpus comes from pageable host memory at ~11 GB/s, and the two byte passes over it (code point histogram, word
+// split + dedup) need neither each other nor the alphabet: the text is copied in pieces that END WITH an ASCII space or
+// newline, and both passes run on a piece (second stream) while the next one is copied.  A piece that ends with a
+// space is self-contained for both: no UTF-8 sequence and no word crosses its end, and what precedes its start is a
+// space (the kernels' view of "outside the text").  Corpora without a space in 32 MB fall back to one piece.
+static int pipelined_load(yttm_ctx *c, uint8_t *dst, const char *src, uint64_t n) {
+  if (!c->stream2) {
+    YT_CUDA(c, cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    YT_CUDA(c, cudaEventCreateWithFlags(&c->ev_pipe, cudaEventDisableTiming));
+  }
+  uint64_t piece = 32ull << 20;
+  if (const char *e = std::getenv("YTTM_TRAIN_PIPELINE_PIECE_KB")) piece = (uint64_t)std::max(1, std::atoi(e)) << 10;   // tests
+  YT_CUDA(c, c->hist.reserve((CP_LIMIT + 1) * 8));
+  YT_CUDA(c, cudaMemsetAsync(c->hist.p, 0, (CP_LIMIT + 1) * 8, c->stream));
+  YT_CUDA(c, c->counters.reserve(64));
+  auto *counters = c->counters.as<unsigned long long>();
+  const uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(ytc::pow2ceil(n / 16 + 1), 1u << 16), 1ull << 26);   // as build_word_table
+  YT_CUDA(c, c->wkey.reserve(cap * 8));
+  YT_CUDA(c, c->wcnt.reserve(cap * 8));
+  YT_CUDA(c, cudaMemsetAsync(c->wkey.p, 0, cap * 8, c->stream));
+  YT_CUDA(c, cudaMemsetAsync(c->wcnt.p, 0, cap * 8, c->stream));
+  YT_CUDA(c, cudaMemsetAsync(counters, 0, 64, c->stream));
+  WordTab wt{c->wkey.as<unsigned long long>(), c->wcnt.as<unsigned long long>(), cap - 1};
+  for (uint64_t lo = 0; lo < n;) {
+    uint64_t hi = std::min<uint64_t>(n, lo + piece);
+    if (hi < n) {   // end the piece behind its last ASCII space / newline
+      const char *a = static_cast<const char *>(memrchr(src + lo, ' ', hi - lo));
+      const char *b = static_cast<const char *>(memrchr(src + lo, '\n', hi - lo));
+      const char *q = a > b ? a : b;   // (nullptr compares low)
+      hi = q ? (uint64_t)(q - src) + 1 : n;
+    }
+    YT_CUDA(c, cudaMemcpyAsync(dst + lo, src + lo, hi - lo, cudaMemcpyHostToDevice, c->stream));
+    YT_CUDA(c, cudaEventRecord(c->ev_pipe, c->stream));
+    YT_CUDA(c, cudaStreamWaitEvent(c->stream2, c->ev_pipe, 0));
+    char_hist_kernel<<<grid_for(c, (hi - lo) / 16 + 1, 512, 4), 512, 0, c->stream2>>>(dst + lo, hi - lo, c->hist.as<unsigned long long>());
+    word_insert_kernel<<<grid_for(c, hi - lo, 256, 8), 256, 0, c->stream2>>>(dst, n, lo, hi, wt, counters, cap / 2);
+    c->launches += 2;
+    lo = hi;
+  }
+  YT_CUDA(c, cudaGetLastError());
+  c->pipe_hist = true;
+  c->pipe_wtab_cap = cap;
+  return 0;
+}
+
 int yttm_train_load_corpus(yttm_ctx *c, const char *bytes, uint64_t n, int on_device) {
   YT_CUDA(c, cudaSetDevice(c->device));
   if (n >= POS_MASK) YT_FAIL(c, "corpus shard too large (>= 2^40 bytes)");
@@ -973,11 +1020,20 @@ int yttm_train_load_corpus(yttm_ctx *c, const char *bytes, uint64_t n, int on_de
   int staged = 0;
   if (const char *e = std::getenv("YTTM_TRAIN_PINNED_H2D")) staged = std::max(0, std::min(64, std::atoi(e)));
   c->timers["h2d_variant"].ms = (float)staged;  // yttm_stage_ms(ctx, "h2d_variant")
-  if (n && staged) { if (staged_h2d(c, base + 16, bytes, n, staged)) return 1; }
-  else if (n) YT_CUDA(c, cudaMemcpyAsync(base + 16, bytes, n, cudaMemcpyHostToDevice, c->stream));
-  ytc::timer_end(c, "h2d");
   c->d_text = base + 16;
   c->text_external = false;
+  c->pipe_hist = false;
+  c->pipe_wtab_cap = 0;
+  uint64_t pipe_min = 64ull << 20;   // below this the passes are too short to be worth a second stream
+  if (const char *e = std::getenv("YTTM_TRAIN_PIPELINE")) pipe_min = std::atoi(e) > 0 ? (uint64_t)std::atoi(e) : ~0ull;   // bytes; 0 = off
+  if (n && staged) { if (staged_h2d(c, base + 16, bytes, n, staged)) return 1; }
+  else if (n >= pipe_min) { if (pipelined_load(c, base + 16, bytes, n)) return 1; }
+  else if (n) YT_CUDA(c, cudaMemcpyAsync(base + 16, bytes, n, cudaMemcpyHostToDevice, c->stream));
+  ytc::timer_end(c, "h2d");
+  if (c->pipe_hist) {   // the kernels of the last pieces: everything after this call sees them done
+    YT_CUDA(c, cudaEventRecord(c->ev_pipe, c->stream2));
+    YT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_pipe, 0));
+  }
   return 0;
 }
 
@@ -996,6 +1052,10 @@ static int hist_summarise(yttm_ctx *c, uint64_t *data_len, uint64_t *n_distinct)
 
 int yttm_train_char_hist(yttm_ctx *c, uint64_t *data_len, uint64_t *n_distinct) {
   YT_CUDA(c, cudaSetDevice(c->device));
+  if (c->pipe_hist) {   // counted while the text was copied (yttm_train_load_corpus)
+    c->pipe_hist = false;
+    return hist_summarise(c, data_len, n_distinct);
+  }
   YT_CUDA(c, c->hist.reserve((CP_LIMIT + 1) * 8));
   YT_CUDA(c, cudaMemsetAsync(c->hist.p, 0, (CP_LIMIT + 1) * 8, c->stream));
   ytc::timer_begin(c, "char_hist");
@@ -1078,7 +1138,16 @@ static int build_word_table(yttm_ctx *c, const WordList *list, uint64_t *n_uniqu
   const uint64_t guess = list ? list->word_off[list->n_src] * 2 + 1 : n / 16 + 1;
   uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(ytc::pow2ceil(guess), 1u << 16), 1ull << 26);
   unsigned long long h_cnt[4] = {0, 0, 0, 0};
-  for (int attempt = 0;; attempt++) {  // retry with a larger table on overflow
+  bool piped = false;
+  if (!list && c->pipe_wtab_cap) {   // built while the text was copied (yttm_train_load_corpus)
+    cap = c->pipe_wtab_cap;
+    c->pipe_wtab_cap = 0;
+    YT_CUDA(c, cudaMemcpyAsync(h_cnt, counters, 32, cudaMemcpyDeviceToHost, c->stream));
+    YT_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!h_cnt[2]) piped = true;
+    else cap *= 4;   // it overflowed: the plain passes below start over with a larger table
+  }
+  for (int attempt = 0; !piped; attempt++) {  // retry with a larger table on overflow
     if (attempt > 10) YT_FAIL(c, "word table: too many retries");
     YT_CUDA(c, c->wkey.reserve(cap * 8));
     YT_CUDA(c, c->wcnt.reserve(cap * 8));
@@ -1095,7 +1164,7 @@ static int build_word_table(yttm_ctx *c, const WordList *list, uint64_t *n_uniqu
         c->launches++;
       }
     } else if (n) {
-      word_insert_kernel<<<grid_for(c, n, 256, 8), 256, 0, c->stream>>>(c->d_text, n, wt, counters, cap / 2);
+      word_insert_kernel<<<grid_for(c, n, 256, 8), 256, 0, c->stream>>>(c->d_text, n, 0, n, wt, counters, cap / 2);
       c->launches++;
     }
     YT_CUDA(c, cudaGetLastError());
