@@ -457,14 +457,19 @@ def main():
         fm = c3["front_ms_rank0"]
         if rank == 0:
             nb = len(shard3)
-            roofline["train_front"] = {"bytes_rank0": nb, "char_hist_GBps": r3(nb / fm["char_hist"] / 1e6),
-                                       "word_count_GBps": r3(nb / fm["word_count"] / 1e6), "h2d_GBps": r3(nb / fm["h2d"] / 1e6),
+            piped = fm["char_hist"] <= 0   # both byte passes ran per piece behind the H2D copy (train.cu: pipelined_load)
+            roofline["train_front"] = {"bytes_rank0": nb, "h2d_GBps": r3(nb / fm["h2d"] / 1e6),
+                                       "char_hist_GBps": None if piped else r3(nb / fm["char_hist"] / 1e6),
+                                       "word_count_GBps": None if piped else r3(nb / fm["word_count"] / 1e6),
+                                       "note": ("char_hist + word split run per 32 MB piece on a second stream while the next piece is "
+                                                "copied: their time is inside h2d (kernel rates: profiles/r02_prof_front.raw.csv, "
+                                                "57 / 25 GB/s)") if piped else None,
                                        "algorithmic_bytes": "B per pass (SURVEY 8d)"}
         del shard3
         # ---- BASELINE configs[4] shape: multilingual, vocab 64k, coverage 0.9999, 1.25 GB per GPU (weak)
         if not old():
             c5, shard5, _ = train_leg(comm, local, "multilingual", range(rank * 10, rank * 10 + 10), VOCAB5, 0.9999, "cfg5",
-                                      runs=1, cache=(world == 1))
+                                      cache=(world == 1))
             c5["scaling"] = "weak (1.25 GB per GPU)"
             cfg_train["config5"] = c5
         else:
