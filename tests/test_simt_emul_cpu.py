@@ -81,6 +81,18 @@ def test_train_pipelined_ingest(emu, oracle, monkeypatch, piece_kb):
     TG._same(oracle, b"ab" * 3000 + "\u2581x\u2581".encode() + b"cd" * 2000, 30)
 
 
+@pytest.mark.parametrize("places", ["1", "2"])
+def test_train_drain_places(emu, oracle, monkeypatch, places):
+    """Multi-GPU geometry of the drain: only the first place(s) of a segment are handled by per-thread items, the rest
+    (place matrix, then the sender's segment) by the shared walk."""
+    monkeypatch.setenv("YTTM_DRAIN_PLACES", places)
+    monkeypatch.setenv("YT_EMU_SMS", "3")
+    for seed in (1, 6):
+        text, vocab, cov, _ = _cases.stress_case(seed)
+        TG._same(oracle, text, vocab, cov)
+    TG._same(oracle, _cases.dirty_zipf_text(50_000), 600, 0.98)
+
+
 def test_train_unicode_and_runs(emu, oracle):
     TG._same(oracle, _cases.dirty_zipf_text(120_000), 900, 0.98)
     TG._same(oracle, b"a" * 500 + b" " + b"ab" * 300 + b" aaa aaaa aaaaa " + b"b" * 1001, 40)

@@ -72,6 +72,10 @@ struct XqHdr {
   // segment, polled by all 148 blocks, a poll round was 21.9 k sector requests on 148 lines shared by every SM.)
   unsigned long long counts[XQ_MAX_BLOCKS * XQ_MAX_BLOCKS];
   uint4 places[XQ_BOX * XQ_MAX_BLOCKS];   // entry e (< XQ_BOX) of the sender's block b: places[e * XQ_MAX_BLOCKS + b]
+  // count words of the merge loop for the readers of ANOTHER rank: one per sender block, polled by all blocks of that
+  // rank.  (Per-reader rows across NVLink were 1036 eight-byte stores per block and merge at 8 GPUs: ~11 us of a 35 us
+  // merge on the wire.  The rows above stay for the local readers and for the out-of-loop table rounds.)
+  unsigned long long shared[XQ_MAX_BLOCKS];
 };
 // count word of sender block `sb` in the mailbox row of reader block `rb`
 __device__ __forceinline__ unsigned long long *xq_cnt(XqHdr *h, uint32_t rb, uint32_t sb) { return &h->counts[(size_t)rb * XQ_MAX_BLOCKS + sb]; }
@@ -222,6 +226,8 @@ struct LoopArgs {
   unsigned long long spin_limit_ns;  // a peer that stays silent this long traps the kernel (never hang the box)
   uint32_t front_top;                // pairs a partition contributes to a front refresh (1 .. FRONT_TOP)
   uint32_t newp_limit;               // keys the new-pair table takes per round (NEWP_LIMIT; tests: YTTM_NEWP_LIMIT)
+  uint32_t drain_places;             // places per segment the drain covers with per-thread items (1 .. XQ_BOX); the rest of a
+                                     // segment goes through the shared walk.  Host: as many as one trip of the items holds.
   unsigned long long *dbg_blk;       // YTTM_DBG & 16: 8 accumulators per block (ns): poll bests, apply, wait counts (+ owner sweep), drain, cache, sweeps
 };
 
@@ -638,7 +644,7 @@ __device__ __forceinline__ void xq_prefix(const LoopArgs &a, uint32_t *s_pref, u
   __syncthreads();
 }
 // entry i (0 <= i < s_pref[nseg]) of round `round` in this rank's region; spins until both words carry the round's stamp
-// first: index of the first entry that sits in the segment (the merge loop keeps entries 0 .. XQ_BOX-1 in XqHdr::places)
+// first: number of the first entry this walk covers (the merge loop: the entries its per-place items left over)
 __device__ __forceinline__ void xq_entry(const LoopArgs &a, uint32_t round, const uint32_t *s_pref, uint32_t i,
                                          unsigned long long *key, long long *delta, uint32_t first = 0) {
   const uint32_t nseg = a.xq.world * a.xq.nblocks;
@@ -648,8 +654,10 @@ __device__ __forceinline__ void xq_entry(const LoopArgs &a, uint32_t round, cons
     if (s_pref[mid] <= i) lo = mid; else hi = mid;
   }
   const uint32_t s = lo / a.xq.nblocks, b = lo - s * a.xq.nblocks;
-  const unsigned long long *ep = reinterpret_cast<const unsigned long long *>(
-      xq_base(a.xq, a.xq.me) + xq_seg_off(a.xq, round & 1u, s, b) + (size_t)(i - s_pref[lo] + first) * sizeof(uint4));
+  const uint32_t idx = i - s_pref[lo] + first;   // the entry's number inside its segment
+  const unsigned long long *ep = first && idx < (uint32_t)XQ_BOX   // (the merge loop: entries 0 .. XQ_BOX-1 sit in the place matrix)
+      ? reinterpret_cast<const unsigned long long *>(xq_hdr(a.xq, a.xq.me, round & 1u, s)->places + idx * XQ_MAX_BLOCKS + b)
+      : reinterpret_cast<const unsigned long long *>(xq_base(a.xq, a.xq.me) + xq_seg_off(a.xq, round & 1u, s, b) + (size_t)idx * sizeof(uint4));
   const bool sys = a.xq.world > 1;
   unsigned long long t0 = 0;
   for (uint32_t spin = 0; !xq_unpack(ld_relaxed_any(ep, sys), ld_relaxed_any(ep + 1, sys), round % XQ_STAMP_MOD, key, delta); spin++) {
@@ -851,12 +859,13 @@ struct DrainItem { uint32_t e, j, sd, cnt_off, plc_off; };
 __device__ __forceinline__ DrainItem drain_item(const LoopArgs &a, uint32_t item, uint32_t nseg) {
   DrainItem d;
   d.e = ~0u; d.j = 0; d.sd = 0; d.cnt_off = 0; d.plc_off = 0;
-  if (item >= nseg * (uint32_t)XQ_BOX) return d;
+  if (item >= nseg * a.drain_places) return d;
   d.e = item / nseg;
   d.j = item - d.e * nseg;
   d.sd = d.j / a.xq.nblocks;
   const uint32_t b = d.j - d.sd * a.xq.nblocks;
-  d.cnt_off = (uint32_t)(offsetof(XqHdr, counts) + ((size_t)blockIdx.x * XQ_MAX_BLOCKS + b) * 8);
+  d.cnt_off = d.sd == a.xq.me ? (uint32_t)(offsetof(XqHdr, counts) + ((size_t)blockIdx.x * XQ_MAX_BLOCKS + b) * 8)
+                              : (uint32_t)(offsetof(XqHdr, shared) + (size_t)b * 8);
   d.plc_off = (uint32_t)(offsetof(XqHdr, places) + ((size_t)d.e * XQ_MAX_BLOCKS + b) * 16);
   return d;
 }
@@ -1003,7 +1012,6 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
   fx.s_nocc = &s_nocc; fx.s_own_n = &s_own_n; fx.s_refresh = &s_refresh; fx.s_povf = &s_povf; fx.s_occ = &s_occ;
   fx.nsk = nsk; fx.s_lost = &s_lost; fx.newp_limit = a.newp_limit;
   fx.own_base = 0; fx.z = 0; fx.part = blockIdx.x; fx.pbase = pbase; fx.tab = a.tab;
-  const uint32_t pub_d = threadIdx.x / a.xq.nblocks, pub_rb = threadIdx.x - pub_d * a.xq.nblocks;   // the reader this thread stores the count word to
   DrainItem ditem[DRAIN_ITEMS];   // this thread's items of the first trip of the drain
 #pragma unroll
   for (int k = 0; k < DRAIN_ITEMS; k++) ditem[k] = drain_item(a, threadIdx.x + (uint32_t)k * blockDim.x, a.xq.world * a.xq.nblocks);
@@ -1298,12 +1306,11 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       if (s_occ > a.part_limit) word |= XQ_CNT_PLIMIT;   // state of the partition as of the last flush
       if (s_povf) word |= XQ_CNT_PFULL;
       const unsigned long long cw = ((unsigned long long)nround << 32) | word;
-      const uint32_t nbox = a.xq.world * a.xq.nblocks;
-      if (threadIdx.x < nbox) st_relaxed_any(xq_cnt(xq_hdr(a.xq, pub_d, nround & 1u, a.xq.me), pub_rb, blockIdx.x), cw, sys);
-      for (uint32_t t = threadIdx.x + blockDim.x; t < nbox; t += blockDim.x) {   // (more readers than threads: 4+ GPUs)
-        const uint32_t d = t / a.xq.nblocks, rb = t - d * a.xq.nblocks;
-        st_relaxed_any(xq_cnt(xq_hdr(a.xq, d, nround & 1u, a.xq.me), rb, blockIdx.x), cw, sys);
-      }
+      // local readers: one word per reader block (its private row); the other ranks: one word per rank
+      for (uint32_t rb = threadIdx.x; rb < a.xq.nblocks; rb += blockDim.x)
+        st_relaxed_any(xq_cnt(xq_hdr(a.xq, a.xq.me, nround & 1u, a.xq.me), rb, blockIdx.x), cw, false);
+      if (threadIdx.x < a.xq.world && threadIdx.x != a.xq.me)
+        st_relaxed_any(&xq_hdr(a.xq, threadIdx.x, nround & 1u, a.xq.me)->shared[blockIdx.x], cw, true);
       if (threadIdx.x == 0) s_xf = 0;   // accumulator of the poll below
     }
     if (gtid == 0) tq2 = gtimer();
@@ -1336,7 +1343,9 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       if (a.dbg & 16u) {   // diagnostic: when have ALL count words arrived (hop + skew of the apply phases)?
         for (uint32_t j = threadIdx.x; j < nseg; j += blockDim.x) {
           const uint32_t sd = j / a.xq.nblocks, b = j - sd * a.xq.nblocks;
-          for (uint32_t spin = 0; (uint32_t)(ld_relaxed_any(xq_cnt(xq_hdr(a.xq, a.xq.me, parity, sd), blockIdx.x, b), sys) >> 32) != round; spin++) spin_check(spin);
+          XqHdr *hh = xq_hdr(a.xq, a.xq.me, parity, sd);
+          const unsigned long long *cwp = sd == a.xq.me ? xq_cnt(hh, blockIdx.x, b) : &hh->shared[b];
+          for (uint32_t spin = 0; (uint32_t)(ld_relaxed_any(cwp, sys) >> 32) != round; spin++) spin_check(spin);
         }
         __syncthreads();
         if (dbgb) bacc[6] += gtimer() - bt;
@@ -1349,7 +1358,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
       // handlers of a warp's 32 senders ran one after the other; one private 128-byte line per (reader, sender) — every
       // lane on its own line, 64 cycles of load/store unit per warp instruction, polled: 1 us per sweep.)
       {
-        const uint32_t nitems = nseg * (uint32_t)XQ_BOX;
+        const uint32_t nitems = nseg * a.drain_places;
         const unsigned char *region = xq_base(a.xq, a.xq.me) + (size_t)parity * a.xq.world * a.xq.per_sender;   // [sender]{XqHdr, segments} of this parity
         for (uint32_t base = threadIdx.x, trip = 0; base < nitems; base += (uint32_t)DRAIN_ITEMS * blockDim.x, trip++) {   // (one trip: 1 GPU, >= 352 threads)
           uint32_t ie[DRAIN_ITEMS], ij[DRAIN_ITEMS];
@@ -1383,8 +1392,8 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
               if (c & XQ_CNT_COMPACT) flags |= XQF_COMPACT;
               if (c & XQ_CNT_PLIMIT) flags |= XQF_PLIMIT;
               if (c & XQ_CNT_PFULL) flags |= XQF_PFULL;
-              const uint32_t nb = n < (uint32_t)XQ_BOX ? n : (uint32_t)XQ_BOX;
-              s_pref[j] = n - nb;   // the rest sits in the sender's segment, from entry XQ_BOX on
+              const uint32_t nb = n < a.drain_places ? n : a.drain_places;
+              s_pref[j] = n - nb;   // the rest: the shared walk below (place matrix up to XQ_BOX, then the sender's segment)
               if (n > nb) big = 1;
             }
             if (e >= n) continue;
@@ -1411,7 +1420,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
         for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
           unsigned long long key = 0;
           long long delta = 0;
-          xq_entry(a, round, s_pref, i, &key, &delta, XQ_BOX);
+          xq_entry(a, round, s_pref, i, &key, &delta, a.drain_places);
           front_take(fx, key, delta);
         }
       }

@@ -1527,6 +1527,11 @@ int yttm_train_run(yttm_ctx *c, uint32_t first_new_id, uint32_t max_merges, uint
     }
     a.front_top = 4;   // measured on B200 (100 MB Zipf): 8 -> 9.6, 4 -> 8.8, 2 -> 9.3 us per merge (smaller front: shorter probes and scans, more refreshes)
     if (const char *e = std::getenv("YTTM_FRONT_TOP")) a.front_top = (uint32_t)std::max(1, std::min((int)FRONT_TOP, std::atoi(e)));
+    {  // as many places per segment as ONE trip of the drain's items holds (1 GPU: all 7; 8 GPUs: 1)
+      const uint32_t nseg = c->xq_world * c->xq_nblocks;
+      a.drain_places = std::max<uint32_t>(1, std::min<uint32_t>(XQ_BOX, (uint32_t)DRAIN_ITEMS * (uint32_t)c->loop_threads / std::max<uint32_t>(nseg, 1)));
+      if (const char *e = std::getenv("YTTM_DRAIN_PLACES")) a.drain_places = (uint32_t)std::max(1, std::min((int)XQ_BOX, std::atoi(e)));
+    }
     a.newp_limit = NEWP_LIMIT;
     if (const char *e = std::getenv("YTTM_NEWP_LIMIT")) a.newp_limit = (uint32_t)std::max(1, std::min((int)NEWP_LIMIT, std::atoi(e)));
     a.dead_min_slots = 4096;
