@@ -734,8 +734,10 @@ __device__ __forceinline__ uint32_t smem_tab_find(const unsigned long long *keys
 }
 // 64-bit add in shared memory out of two NATIVE 32-bit atomics (low word, then high word + carry).  atomicAdd on a
 // 64-bit shared word compiles to a compare-and-swap loop (ATOMS.CAST.SPIN), and the count changes of a merge pile up
-// on few keys (the new token next to its most frequent neighbours): the retries of a few dozen threads on one word
-// cost microseconds.  The sum is exact once all adds have landed (nobody reads a count inside the drain).
+// on few keys (the new token next to its most frequent neighbours), where a loop retries.  (Introduced when the drain
+// was thought to be atomics bound; the session that added it measured no gain by itself — the real limit was the
+// load/store unit, profiles/r02_merge_loop_stalls.md — it stayed because it bounds the work per add.)  The sum is exact
+// once all adds have landed (nobody reads a count inside the drain).
 __device__ __forceinline__ void smem_add64(unsigned long long *p, unsigned long long delta) {
   uint32_t *w = reinterpret_cast<uint32_t *>(p);   // little endian: w[0] low, w[1] high
   const uint32_t dlo = (uint32_t)delta, dhi = (uint32_t)(delta >> 32);
