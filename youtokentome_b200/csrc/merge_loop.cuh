@@ -1046,6 +1046,7 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     unsigned long long *gdata = a.frontbuf + (size_t)gridDim.x * 16;
     unsigned long long *mine = gdata + (size_t)blockIdx.x * FRONT_TOP * 2;
     for (uint32_t i = threadIdx.x; i < FRONT_SLOTS; i += blockDim.x) { fk[i] = PK_EMPTY; fc[i] = 0; }
+    for (uint32_t i = threadIdx.x; i < NEWP_SKETCH; i += blockDim.x) nsk[i] = 0;   // (the new bound covers every pair of the table)
     Best lim{~0ull, ~0ull, 0};
     int k = 0;
     for (; k < (int)a.front_top; k++) {
@@ -1445,9 +1446,12 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
         if (better(bd, cand)) continue;
         if (!smem_tab_add(fk, fc, FRONT_SLOTS - 1, mix64(k), k, (long long)c, &s_focc, flist)) s_refresh = 1;
       }
-      unsigned long long m = 0;
-      for (uint32_t i = threadIdx.x; i < NEWP_SKETCH; i += blockDim.x) { m = max(m, nsk[i]); nsk[i] = 0; }
+      // The sketch is read and cleared only here, in a lost round (and cleared by every refresh): between two such
+      // points its buckets keep adding up the new pairs of ALL rounds — still an upper bound of each of them (counts of
+      // pairs outside the front only fall), a little looser, and the usual round pays nothing for it.
       if (lost) {
+        unsigned long long m = 0;
+        for (uint32_t i = threadIdx.x; i < NEWP_SKETCH; i += blockDim.x) { m = max(m, nsk[i]); nsk[i] = 0; }
         if (m) atomicMax(&s_lostmax, m);
         __syncthreads();
         if (threadIdx.x == 0) {
