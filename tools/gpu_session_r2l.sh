@@ -4,8 +4,8 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 {
 echo "### probe_train 100 MB zipf"; timeout 300 python tools/probe_train.py zipf 32000 100e6 2>&1 | tail -1 | cut -c1-700
-echo "### probe_train multilingual 1.25 GB (one chunk)"; timeout 900 python tools/probe_train.py multilingual 64000 1.25e9 2>&1 | tail -1 | cut -c1-900
-echo "### bench"; timeout 1200 python bench.py > gpurun_out/r02l_bench.json 2> gpurun_out/r02l_bench.err; echo "bench rc=$?"; tail -c 200 gpurun_out/r02l_bench.err
+echo "### probe_train readme"; timeout 300 python tools/probe_train.py readme 2>&1 | tail -1 | cut -c1-700
+echo "### bench"; timeout 1200 python bench.py > gpurun_out/r02p_bench.json 2> gpurun_out/r02p_bench.err; echo "bench rc=$?"; tail -c 200 gpurun_out/r02p_bench.err
 echo "### train parity tests"; timeout 900 python -m pytest tests/test_train_gpu.py tests/test_train_scale_gpu.py -x -q -m gpu 2>&1 | tail -3
-} > gpurun_out/r02_sessionL.log 2>&1
-cut -c1-900 gpurun_out/r02_sessionL.log | tail -30
+} > gpurun_out/r02_sessionP.log 2>&1
+cut -c1-900 gpurun_out/r02_sessionP.log | tail -30
