@@ -66,7 +66,7 @@ constexpr uint32_t XQ_CNT_MASK = 0x07ffffffu;
 //   * entries XQ_BOX.. of a segment (the first rounds of a run) stay in the sender's own segment.
 constexpr int XQ_BOX = 7;
 struct XqHdr {
-  // MAILBOXES: the count word (round << 32) | flags | entries of the sender's segment b exists once per READER block r, at
+  // ROWS: the count word (round << 32) | flags | entries of the sender's segment b exists once per local READER block r, at
   // counts[r * XQ_MAX_BLOCKS + b]: the sender stores it nblocks times (posted stores to distinct lines), reader r polls
   // its own row — nblocks consecutive words that nobody else reads.  (Round 2, measured on B200: with one word per
   // segment, polled by all 148 blocks, a poll round was 21.9 k sector requests on 148 lines shared by every SM.)
@@ -77,7 +77,7 @@ struct XqHdr {
   // merge on the wire.  The rows above stay for the local readers and for the out-of-loop table rounds.)
   unsigned long long shared[XQ_MAX_BLOCKS];
 };
-// count word of sender block `sb` in the mailbox row of reader block `rb`
+// count word of sender block `sb` in the row of reader block `rb`
 __device__ __forceinline__ unsigned long long *xq_cnt(XqHdr *h, uint32_t rb, uint32_t sb) { return &h->counts[(size_t)rb * XQ_MAX_BLOCKS + sb]; }
 struct Xq {
   unsigned char *base[XQ_MAX_WORLD];  // region of every rank; base[me] is local memory
@@ -1301,8 +1301,8 @@ __device__ __forceinline__ void merge_loop_body(const LoopArgs &a) {
     if (lane == 0 && dead) atomicAdd(&s_dead, (uint32_t)dead);
     __syncthreads();  // all entries of this block are on their way
     {
-      // the count word of this segment, into the mailbox of every block of every rank (every thread computes the same
-      // word and stores a share).  No fence: the entries carry their own stamps, the count word may overtake them.
+      // the count word of this segment, into the row of every local block and once into every other rank (every thread
+      // computes the same word and stores a share).  No fence: the entries carry their own stamps, the count word may overtake them.
       const uint32_t n = s_out_n;
       uint32_t word = n > a.xq.seg_cap ? (a.xq.seg_cap | XQ_CNT_OVF) : n;
       if ((unsigned long long)s_dead * 4 > my_slots && my_slots > a.dead_min_slots) word |= XQ_CNT_COMPACT;   // s_dead: tombstoned in this launch
