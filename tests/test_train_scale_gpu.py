@@ -57,13 +57,15 @@ def np_apply(tok, x, y, z):
     return out
 
 
-@pytest.mark.parametrize("log2_first", [0, 6])
-def test_streaming_merges_equal_a_numpy_recount(product, log2_first):
+@pytest.mark.parametrize("log2_first,alpha", [(0, 300), (6, 300), (0, 2000)])
+def test_streaming_merges_equal_a_numpy_recount(product, log2_first, alpha):
+    """alpha 2000: every merge creates more new pairs than the per-round table of the front takes (768) — the rounds
+    whose new pairs are only bounded by the hash-bucket sketch (merge_loop.cuh: front_take)."""
     L = product
     ctx = C.c_void_p()
     assert L.yttm_ctx_create(0, C.byref(ctx)) == 0
     try:
-        wl, alpha, iters = 8, 300, 6
+        wl, iters = 8, 6
         n_w = 1_500_000                     # 12 M tokens = 48 MB: beyond the 148 x ~200 KB of shared memory
         assert L.yttm_train_synth_words(ctx, n_w, wl, alpha | (log2_first << 24), 7) == 0, L.yttm_last_error(ctx)
         nw, nt = C.c_uint64(0), C.c_uint64(0)
