@@ -53,6 +53,19 @@ def test_distributed_training_equals_the_oracle(emu, oracle, monkeypatch, world)
         assert read_model(single) == read_model(m)
 
 
+@pytest.mark.parametrize("sms,places", [("1", "1"), ("2", None), ("3", "2")])
+def test_distributed_training_eight_ranks(emu, oracle, monkeypatch, sms, places):
+    """The largest world (XQ_MAX_WORLD = 8): one block per rank, the drain geometry of an 8-GPU job (one place per
+    segment handled by the items, the rest by the shared walk), one count word per remote rank."""
+    monkeypatch.setenv("YT_EMU_SMS", sms)
+    if places:
+        monkeypatch.setenv("YTTM_DRAIN_PLACES", places)
+    monkeypatch.setenv("YTTM_XQ_TIMEOUT_MS", "240000")
+    for text, vocab, cov in [(_cases.zipf().text(20_000), 400, 1.0), (_cases.dirty_zipf_text(20_000), 300, 0.98)]:
+        m, res = _train(emu, 8, text, vocab, cov)
+        assert read_model(m) == read_model(_oracle_model(oracle, text, vocab, cov))
+
+
 def test_distributed_words_are_deduplicated_across_ranks(emu, oracle, monkeypatch):
     """Two ranks whose shards hold the SAME words: after the exchange the job holds each word once (the round-1 path
     kept one copy per rank, which made the replicated loop N times larger)."""
