@@ -38,7 +38,10 @@ uint64_t yttm_launch_count(const yttm_ctx *ctx);
 
 /* Phase 0 — corpus shard.  `bytes` is a HOST pointer (copied H2D) unless on_device != 0, in
  * which case it is a device pointer that must stay valid until yttm_train_build returns.
- * Replaces fast_read_file_utf8's buffer (bpe.cpp:67-84) as the input of the passes below. */
+ * Replaces fast_read_file_utf8's buffer (bpe.cpp:67-84) as the input of the passes below.
+ * Host corpora of >= 64 MB are copied in pieces that end behind an ASCII space / newline; phase 1
+ * and the word table of phase 2 run per piece on a second stream behind the copy of the next piece
+ * (the calls below then only collect the results; YTTM_TRAIN_PIPELINE=0 turns this off). */
 int yttm_train_load_corpus(yttm_ctx *ctx, const char *bytes, uint64_t n, int on_device);
 
 /* Phase 1 — compute_char_count (bpe.cpp:839-857): *data_len = number of decode units (spaces
