@@ -19,7 +19,8 @@ from youtokentome_b200 import synth  # noqa: E402
 KNOBS = ["YT_EMU_SMS", "YT_EMU_SCHED_SEED", "YTTM_FORCE_STREAM", "YTTM_STREAM_Q", "YTTM_STAGES", "YTTM_PAIR_CAP_FLOOR", "YTTM_DEFER_CAP",
          "YTTM_ENC_BUCKETED", "YTTM_ENC_FIND_CACHED", "YTTM_ENC_ZLIN", "YTTM_ENC_LONG", "YTTM_ENC_CHUNK_MB",
          "YTTM_ENC_DEDUP", "YTTM_ENC_DEDUP_SLOTS", "YTTM_ENC_DEDUP_WEAKTAG", "YTTM_ENC_FIND_VEC", "YTTM_XQ_SEG_CAP", "YTTM_ENC_PLAIN", "YTTM_ENC_SLOTS",
-         "YTTM_PAIR_MAX_LOAD_PCT", "YTTM_TRAIN_PINNED_H2D", "YTTM_TRAIN_PINNED_CHUNK_KB", "YTTM_LOOP_BLOCKS"]
+         "YTTM_PAIR_MAX_LOAD_PCT", "YTTM_TRAIN_PINNED_H2D", "YTTM_TRAIN_PINNED_CHUNK_KB", "YTTM_LOOP_BLOCKS",
+         "YTTM_FRONT_TOP", "YTTM_NEWP_LIMIT", "YTTM_DRAIN_PLACES", "YTTM_TRAIN_PIPELINE", "YTTM_TRAIN_PIPELINE_PIECE_KB", "YTTM_LOOP_THREADS"]
 
 
 def sentences(rng, text):
@@ -134,6 +135,18 @@ def main():
             env["YTTM_TRAIN_PINNED_CHUNK_KB"] = str(int(rng.choice([1, 2, 16])))
         if rng.integers(0, 4) == 0:
             env["YTTM_LOOP_BLOCKS"] = str(int(rng.integers(1, 4)))
+        # round 2: the replicated front (refresh rate, lost rounds), the drain geometry, the pipelined ingest
+        if rng.integers(0, 2):
+            env["YTTM_FRONT_TOP"] = str(int(rng.integers(1, 7)))
+        if rng.integers(0, 2):
+            env["YTTM_NEWP_LIMIT"] = str(int(rng.choice([1, 2, 5, 20, 768])))
+        if rng.integers(0, 2):
+            env["YTTM_DRAIN_PLACES"] = str(int(rng.integers(1, 8)))
+        if rng.integers(0, 3) == 0 and "YTTM_TRAIN_PINNED_H2D" not in env:
+            env["YTTM_TRAIN_PIPELINE"] = "1"
+            env["YTTM_TRAIN_PIPELINE_PIECE_KB"] = str(int(rng.choice([1, 3, 16])))
+        if rng.integers(0, 3) == 0:
+            env["YTTM_LOOP_THREADS"] = str(int(rng.choice([64, 128, 256, 1024])))
         for k in KNOBS:
             os.environ.pop(k, None)
         os.environ.update(env)
